@@ -1,0 +1,162 @@
+/*
+ * sqmp_b200.h — C ABI of libsqmp_b200.so: the state-validity (FK + collision) and near-neighbour
+ * inner loop of squirrel_motion_planner's birrt_star / squirrel_8dof_planner on NVIDIA B200 (sm_100a).
+ *
+ * The reference has no FFI; its boundary for this path is a set of C++ member functions.  Each entry
+ * point below names the reference interface it sits behind (file:line in /root/reference):
+ *   CC = birrt_star/robot_motion_planning/birrt_star_algorithm/include/birrt_star_algorithm/collision_checker.hpp
+ *   BS = birrt_star/robot_motion_planning/birrt_star_algorithm/src/birrt_star.cpp
+ *   BH = .../birrt_star_algorithm/include/birrt_star_algorithm/birrt_star.h
+ *   DH = birrt_star/robot_motion_planning/planning_heuristics/src/distance_heuristics.cpp
+ *   DS = birrt_star/robot_motion_planning/planner_data_structures/include/planner_data_structures/data_structs.h
+ *   KM = birrt_star/robot_motion_control/kuka_motion_control/src/kdl_kuka_model.cpp
+ *
+ * Conventions: every call is synchronous from the planner thread (the reference's checker is not
+ * re-entrant either, CC:141-142); int return 0 = OK, <0 = error (sqmp_strerror); no exception crosses
+ * the boundary; the caller owns all host buffers, the library owns all device memory; one context per
+ * GPU.  There is no CPU fallback: without a usable CUDA device sqmp_create fails.
+ * All joint vectors have SQMP_DOF = 8 doubles: x, y, theta, arm joints 1..5 (BS:6868-6870 hard-codes 8).
+ */
+#ifndef SQMP_B200_H
+#define SQMP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SQMP_DOF 8
+#define SQMP_MAX_SEG 8
+#define SQMP_MAX_SPHERES 128
+#define SQMP_MAX_PAIRS 4096
+#define SQMP_MAX_TREES 8
+
+#define SQMP_JOINT_ROT 1
+#define SQMP_JOINT_TRANS 2
+
+/* flags of the validity calls: the two bools of isInCollision(q, checkSelf, checkMap) (CC:104) */
+#define SQMP_CHECK_SELF 1u
+#define SQMP_CHECK_MAP 2u
+
+#define SQMP_OK 0
+#define SQMP_ERR_INVALID (-1)   /* bad argument */
+#define SQMP_ERR_CUDA (-2)      /* CUDA runtime error, see sqmp_last_error */
+#define SQMP_ERR_NOMEM (-3)
+#define SQMP_ERR_OVERFLOW (-4)  /* radius search: more hits than the per-query buffer even at batch size 1 */
+#define SQMP_ERR_NODEVICE (-5)
+
+typedef struct sqmp_ctx sqmp_ctx;
+
+/*
+ * Robot description = what CollisionChecker builds at start-up (CC:176-351, 353-393), pre-folded by the
+ * host (squirrel_motion_planner_b200/robot_desc.py: compile_robot) into a serial chain of planning
+ * segments with rigid sphere groups.  Frames are 12 doubles: R row-major (9) then p (3).
+ *   world frame of segment k:  T_k = T_{k-1} * seg_pre[k] * Motion(seg_axis[k], q[seg_qidx[k]])
+ *   T_{-1} = Frame(root_offset) for the collision path (CC:199-201), identity for sqmp_fk (KM:278).
+ */
+typedef struct sqmp_robot_desc {
+  int32_t n_seg;
+  int32_t seg_type[SQMP_MAX_SEG];      /* SQMP_JOINT_ROT | SQMP_JOINT_TRANS */
+  int32_t seg_qidx[SQMP_MAX_SEG];      /* index into the 8-vector */
+  double seg_pre[SQMP_MAX_SEG][12];    /* fixed frame before the joint motion */
+  double seg_axis[SQMP_MAX_SEG][3];    /* unit axis in the joint frame */
+  double root_offset[3];
+  double ee_tip[12];                   /* last segment -> FK tip link (SRDF chain tip, hand_wrist_link) */
+  int32_t n_spheres;
+  const int32_t *sph_seg;              /* [n] segment carrying the sphere, -1 = root; sorted ascending */
+  const int32_t *sph_link;             /* [n] link index 0..63 (bit position in the disable mask) */
+  const double *sph_center;            /* [n*3] in the segment frame */
+  const double *sph_radius;            /* [n] */
+  int32_t n_pairs;                     /* enabled sphere pairs across different segments (CC:353-393) */
+  const int32_t *pair_a;
+  const int32_t *pair_b;
+  int32_t self_const_collision;        /* 1: an enabled pair inside one rigid group always collides */
+} sqmp_robot_desc;
+
+/* ---- life cycle ------------------------------------------------------------------------------- */
+/* CollisionChecker::CollisionChecker()/initialize() (CC:66-74, 156-172).  NULL on failure
+ * (*err_out receives the code); the shim then fails closed like CC:106-107. */
+sqmp_ctx *sqmp_create(int device, const sqmp_robot_desc *desc, int *err_out);
+void sqmp_destroy(sqmp_ctx *ctx);
+const char *sqmp_last_error(const sqmp_ctx *ctx);
+const char *sqmp_strerror(int code);
+/* Build tag + compiled SASS architecture ("sm_100a"). */
+const char *sqmp_version(void);
+
+/* ---- map -------------------------------------------------------------------------------------- */
+/* CollisionChecker::setOcTree (CC:76-88) on a dense copy of the octomap: bit (k*gy+j)*gx+i of `bits`
+ * is voxel (i,j,k) = origin + [i,i+1] x [j,j+1] x [k,k+1] * res; 1 = occupied, unknown = free.  The
+ * caller folds the octree's z = -0.02 offset (CC:87) into origin.  NULL bits is ignored (CC:78-79).
+ * Deep-copies, replaces the previous grid, and rebuilds the distance field used as a conservative
+ * filter.  Before the first call every map check reports "free" (CC:556-557). */
+int sqmp_set_voxel_grid(sqmp_ctx *ctx, const uint32_t *bits, int gx, int gy, int gz, const double origin[3],
+                        double res);
+/* CollisionChecker::setDisabledLinkMapCollisions (CC:90-102): bit i = link i is skipped by the map check. */
+int sqmp_set_disabled_links(sqmp_ctx *ctx, uint64_t link_mask);
+
+/* ---- state validity ---------------------------------------------------------------------------- */
+/* CollisionChecker::isInCollision (CC:104-121) over S states; BiRRTstarPlanner::isConfigValid
+ * (BS:6897-6908).  q: S*8 row-major.  mask_out: ceil(S/32) words, bit s%32 of word s/32 = 1 ⇒ state s
+ * is in collision.  flags == 0 ⇒ all zero (CC:109-110). */
+int sqmp_check_states(sqmp_ctx *ctx, const double *q, int64_t S, unsigned flags, uint32_t *mask_out);
+/* connectNodesInterpolation/interpolateConfigurations (BS:4380-4490) + isEdgeValid (BS:6864-6895) over E
+ * edges: state k of edge e is q_start + k*((q_end-q_start)/num_points), k = 0..num_points (BS:4461-4478).
+ * mask_out: bit e*(num_points+1)+k.  first_invalid[e]: first colliding k or -1 (may be NULL);
+ * isEdgeValid's last_valid_node_idx is max(first_invalid-1, 0), or num_points when valid. */
+int sqmp_check_edges(sqmp_ctx *ctx, const double *q_start, const double *q_end, int64_t E, int num_points,
+                     unsigned flags, uint32_t *mask_out, int32_t *first_invalid);
+/* CollisionChecker::getCollisions (CC:123-133, 594-631) for one state: link_map_hit[64] (1 = link hits
+ * the map; like the reference, ignores the disable mask) and pair_hit[n_pairs] per enabled sphere pair. */
+int sqmp_get_collisions(sqmp_ctx *ctx, const double q[SQMP_DOF], uint8_t *link_map_hit, uint8_t *pair_hit);
+
+/* ---- forward kinematics ------------------------------------------------------------------------- */
+/* KDLRobotModel::compute_FK (KM:278-305): S*7 doubles x y z qx qy qz qw of the chain tip. */
+int sqmp_fk(sqmp_ctx *ctx, const double *q, int64_t S, double *ee_pose_out);
+
+/* ---- tree mirror (DS:29-54; mutation sites BS:3298-3322, 5173-5193, 5518-5520) ------------------- */
+/* Invariant kept from the reference: node_id == index.  tree in [0, SQMP_MAX_TREES). */
+int sqmp_tree_reset(sqmp_ctx *ctx, int tree);
+int sqmp_tree_append(sqmp_ctx *ctx, int tree, const double q[SQMP_DOF], double cost, int32_t *id_out);
+int sqmp_tree_append_batch(sqmp_ctx *ctx, int tree, const double *q, const double *cost, int64_t n,
+                           int32_t *first_id_out);
+int sqmp_tree_update(sqmp_ctx *ctx, int tree, int32_t id, const double q[SQMP_DOF], double cost);
+int sqmp_tree_update_costs(sqmp_ctx *ctx, int tree, const int32_t *ids, const double *cost, int64_t n);
+int sqmp_tree_size(sqmp_ctx *ctx, int tree, int64_t *n_out);
+
+/* ---- near neighbours ---------------------------------------------------------------------------- */
+/* find_nearest_neighbour_interpolation (BS:4076-4133) with euclidean_joint_space_distance (DH:128-156):
+ * argmin_n sqrt(sum_i (node_n[i]-query[i])^2), fp64, summed in index order without FMA contraction,
+ * strict '<' in serial order (lowest id wins ties), min initialised to 10000.0 and id to 0. */
+int sqmp_nn_nearest(sqmp_ctx *ctx, int tree, const double *queries, int64_t Q, int32_t *id_out);
+/* find_near_vertices_interpolation (BS:4272-4324): {n : d(n, query) < r and n != exclude_id[q]} ordered by
+ * (cost asc, id asc) — DS:41-44 orders by cost; the id tie-break makes std::sort's unstable order
+ * deterministic.  low_ids[q*k + t]: t-th lowest (choose-parent / connect walk, BS:4618-4623, 2823);
+ * high_ids[q*k + t]: t-th highest (rewire walk from the end, BS:5075-5089); -1 padded.
+ * count_out[q]: number of near vertices.  exclude_id may be NULL (no exclusion). */
+int sqmp_nn_radius(sqmp_ctx *ctx, int tree, const double *queries, const int32_t *exclude_id, int64_t Q, double r,
+                   int k, int32_t *low_ids, int32_t *high_ids, int32_t *count_out);
+
+/* ---- device-pointer variants (benchmark harness, multi-GPU sharding) ---------------------------- */
+/* Same semantics; all pointers are device pointers on the context's GPU; work is enqueued on `stream`
+ * (a cudaStream_t, NULL = default stream) and NOT synchronised. */
+int sqmp_check_states_dev(sqmp_ctx *ctx, const double *d_q, int64_t S, unsigned flags, uint32_t *d_mask,
+                          void *stream);
+int sqmp_check_edges_dev(sqmp_ctx *ctx, const double *d_q_start, const double *d_q_end, int64_t E, int num_points,
+                         unsigned flags, uint32_t *d_mask, int32_t *d_first_invalid, void *stream);
+int sqmp_fk_dev(sqmp_ctx *ctx, const double *d_q, int64_t S, double *d_ee_pose, void *stream);
+int sqmp_nn_nearest_dev(sqmp_ctx *ctx, int tree, const double *d_queries, int64_t Q, int32_t *d_id, void *stream);
+/* d_overflow: one int32, set to 1 if some query had more hits than the internal per-query buffer. */
+int sqmp_nn_radius_dev(sqmp_ctx *ctx, int tree, const double *d_queries, const int32_t *d_exclude_id, int64_t Q,
+                       double r, int k, int32_t *d_low_ids, int32_t *d_high_ids, int32_t *d_count,
+                       int32_t *d_overflow, void *stream);
+
+/* Introspection for the bench: number of kernels this context has launched so far. */
+int64_t sqmp_kernel_launches(const sqmp_ctx *ctx);
+/* Tuning knobs (implementation detail, stable names): "fk_precision" 32|64, "nn_variant" 0=auto|1|2 ... */
+int sqmp_set_option(sqmp_ctx *ctx, const char *name, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SQMP_B200_H */

@@ -1,0 +1,785 @@
+// capi.cu — the C ABI of libsqmp_b200.so (include/sqmp_b200.h): context, device memory, host<->device staging.
+// No CPU fallback anywhere: every entry point either runs the CUDA kernels or returns an error code.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "sqmp_common.cuh"
+
+namespace sqmp {
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+};
+
+struct Ctx {
+  int device = 0;
+  int sm_count = 148;
+  RobotDev rb;
+  GridDev gd;
+  int sph_link[SQMP_MAX_SPHERES];
+  int n_pairs = 0;
+  SelfPair *d_pairs = nullptr;
+  std::vector<SelfPair> h_pairs;
+  uint32_t *d_occ = nullptr;
+  uint8_t *d_edt = nullptr;
+  TreeDev trees[SQMP_MAX_TREES];
+  NNScratch nn;
+  size_t nn_part_bytes = 0, nn_hits_bytes = 0;
+  DevBuf scratch[8];  // grow-only staging buffers for the host-pointer entry points
+  cudaStream_t streams[2] = {nullptr, nullptr};
+  int64_t launches = 0;
+  int fk_precision = 64;  // 64 | 32 (validity + FK chain arithmetic)
+  int fk_float_ok = 0;
+  int nn_variant = 0;     // 0 auto | 1 QT | 2 WQ
+  int64_t nn_hit_pool_bytes = int64_t(1) << 30;
+  int64_t pipeline_chunk = 1 << 18;  // states per H2D/kernel/D2H pipeline stage
+  std::string err;
+};
+
+static int fail(Ctx *c, int code, const char *what, cudaError_t e = cudaSuccess) {
+  if (c) {
+    c->err = what;
+    if (e != cudaSuccess) {
+      c->err += ": ";
+      c->err += cudaGetErrorString(e);
+    }
+  }
+  return code;
+}
+#define CU(call)                                                  \
+  do {                                                            \
+    cudaError_t e__ = (call);                                     \
+    if (e__ != cudaSuccess) return fail(c, SQMP_ERR_CUDA, #call, e__); \
+  } while (0)
+
+static int ensure(Ctx *c, int slot, size_t bytes, void **out) {
+  DevBuf &b = c->scratch[slot];
+  if (b.bytes < bytes) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+    size_t want = bytes + bytes / 4;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+      e = cudaMalloc(&b.p, bytes);
+      want = bytes;
+    }
+    if (e != cudaSuccess) return fail(c, SQMP_ERR_NOMEM, "cudaMalloc(scratch)", e);
+    b.bytes = want;
+  }
+  *out = b.p;
+  return SQMP_OK;
+}
+
+static int axis_code_of(const double *a) {
+  const double eps = 0.0;
+  if (a[1] == eps && a[2] == eps && a[0] == 1.0) return AX_PX;
+  if (a[1] == eps && a[2] == eps && a[0] == -1.0) return AX_NX;
+  if (a[0] == eps && a[2] == eps && a[1] == 1.0) return AX_PY;
+  if (a[0] == eps && a[2] == eps && a[1] == -1.0) return AX_NY;
+  if (a[0] == eps && a[1] == eps && a[2] == 1.0) return AX_PZ;
+  if (a[0] == eps && a[1] == eps && a[2] == -1.0) return AX_NZ;
+  return AX_GENERAL;
+}
+static int frame_kind_of(const double *f) {
+  const bool rot_id = f[0] == 1.0 && f[4] == 1.0 && f[8] == 1.0 && f[1] == 0.0 && f[2] == 0.0 && f[3] == 0.0 &&
+                      f[5] == 0.0 && f[6] == 0.0 && f[7] == 0.0;
+  if (!rot_id) return 2;
+  return (f[9] == 0.0 && f[10] == 0.0 && f[11] == 0.0) ? 0 : 1;
+}
+
+// per-grid sphere constants: distance-field threshold and scan half-extent
+static void refresh_sphere_grid_params(Ctx *c) {
+  for (int i = 0; i < c->rb.n_spheres; ++i) {
+    const double r = c->rb.sph[i][3];
+    if (!c->gd.has_grid) {
+      c->rb.sph_thr8[i] = 255;
+      c->rb.sph_ncell[i] = 0;
+      continue;
+    }
+    const double t = std::floor(4.0 * r / c->gd.res);
+    c->rb.sph_thr8[i] = (unsigned char)(t > 255.0 ? 255.0 : t);
+    const double n = std::ceil(r / c->gd.res);
+    c->rb.sph_ncell[i] = (unsigned char)(n > 250.0 ? 250.0 : n);
+  }
+}
+
+static int tree_reserve(Ctx *c, TreeDev &t, int64_t need) {
+  if (need <= t.cap) return SQMP_OK;
+  int64_t cap = t.cap > 0 ? t.cap : 4096;
+  while (cap < need) cap *= 2;
+  // one allocation for the 8 coordinate columns + cost; columns 256-byte aligned
+  const int64_t pitch = (cap + 31) / 32 * 32;
+  double *blk = nullptr;
+  cudaError_t e = cudaMalloc(&blk, size_t(pitch) * (SQMP_DOF + 1) * sizeof(double));
+  if (e != cudaSuccess) return fail(c, SQMP_ERR_NOMEM, "cudaMalloc(tree)", e);
+  for (int d = 0; d <= SQMP_DOF; ++d) {
+    double *dst = blk + int64_t(d) * pitch;
+    const double *src = d < SQMP_DOF ? t.q[d] : t.cost;
+    if (t.n > 0) {
+      e = cudaMemcpy(dst, src, size_t(t.n) * sizeof(double), cudaMemcpyDeviceToDevice);
+      if (e != cudaSuccess) {
+        cudaFree(blk);
+        return fail(c, SQMP_ERR_CUDA, "cudaMemcpy(tree grow)", e);
+      }
+    }
+  }
+  if (t.q[0]) cudaFree(t.q[0]);
+  for (int d = 0; d < SQMP_DOF; ++d) t.q[d] = blk + int64_t(d) * pitch;
+  t.cost = blk + int64_t(SQMP_DOF) * pitch;
+  t.cap = cap;
+  return SQMP_OK;
+}
+
+// smallest double s with sqrt(s) >= r: then  sqrt(x) < r  <=>  x < s   (sqrt is monotone and correctly rounded)
+static double sumsq_threshold(double r) {
+  if (!(r > 0.0)) return 0.0;
+  double s = r * r;
+  while (std::sqrt(s) >= r && s > 0.0) s = std::nextafter(s, 0.0);
+  while (std::sqrt(s) < r) s = std::nextafter(s, INFINITY);
+  return s;
+}
+
+static int pick_variant(const Ctx *c, int64_t Q) {
+  if (c->nn_variant == 1 || c->nn_variant == 2) return c->nn_variant;
+  return Q >= 2048 ? 1 : 2;
+}
+static int pick_chunk_hint(const Ctx *c, int variant, int64_t N, int64_t Q) {
+  if (N <= 0) return 1;
+  int64_t chunks;
+  if (variant == 1) {
+    const int64_t qtiles = (Q + 127) / 128;
+    chunks = (int64_t(c->sm_count) * 16 + qtiles - 1) / qtiles;
+    const int64_t maxc = (N + 2047) / 2048;
+    if (chunks > maxc) chunks = maxc;
+  } else {
+    chunks = (int64_t(c->sm_count) * 32 + Q - 1) / Q;
+    const int64_t maxc = (N + 255) / 256;
+    if (chunks > maxc) chunks = maxc;
+  }
+  if (chunks < 1) chunks = 1;
+  if (chunks > 4096) chunks = 4096;
+  return int(chunks);
+}
+static int nn_prepare(Ctx *c, int64_t Q, int chunks_hint, bool radius, int64_t N) {
+  const size_t part = size_t(chunks_hint + 1) * size_t(Q);
+  if (c->nn_part_bytes < part * 12) {
+    if (c->nn.part_d) cudaFree(c->nn.part_d);
+    if (c->nn.part_id) cudaFree(c->nn.part_id);
+    c->nn.part_d = nullptr;
+    c->nn.part_id = nullptr;
+    c->nn_part_bytes = 0;
+    CU(cudaMalloc(&c->nn.part_d, part * sizeof(double)));
+    CU(cudaMalloc(&c->nn.part_id, part * sizeof(int32_t)));
+    c->nn_part_bytes = part * 12;
+  }
+  if (radius) {
+    int64_t cap = c->nn_hit_pool_bytes / 4 / (Q > 0 ? Q : 1);
+    if (cap > N) cap = N;
+    if (cap < 32) cap = 32;
+    const size_t bytes = size_t(cap) * size_t(Q) * sizeof(int32_t);
+    if (c->nn_hits_bytes < bytes) {
+      if (c->nn.hits) cudaFree(c->nn.hits);
+      c->nn.hits = nullptr;
+      c->nn_hits_bytes = 0;
+      CU(cudaMalloc(&c->nn.hits, bytes));
+      c->nn_hits_bytes = bytes;
+    }
+    c->nn.hit_cap = cap;
+  }
+  return SQMP_OK;
+}
+
+}  // namespace sqmp
+
+using namespace sqmp;
+
+struct sqmp_ctx : public sqmp::Ctx {};
+
+#define CHECK_CTX()                        \
+  if (!ctx) return SQMP_ERR_INVALID;       \
+  Ctx *c = ctx;                            \
+  {                                        \
+    cudaError_t e0 = cudaSetDevice(c->device); \
+    if (e0 != cudaSuccess) return fail(c, SQMP_ERR_CUDA, "cudaSetDevice", e0); \
+  }
+
+extern "C" {
+
+const char *sqmp_version(void) { return "libsqmp_b200 r1 (sm_100a)"; }
+
+const char *sqmp_strerror(int code) {
+  switch (code) {
+    case SQMP_OK: return "ok";
+    case SQMP_ERR_INVALID: return "invalid argument";
+    case SQMP_ERR_CUDA: return "CUDA error";
+    case SQMP_ERR_NOMEM: return "out of device memory";
+    case SQMP_ERR_OVERFLOW: return "radius search hit buffer overflow";
+    case SQMP_ERR_NODEVICE: return "no usable CUDA device (there is no CPU fallback)";
+    default: return "unknown error";
+  }
+}
+
+const char *sqmp_last_error(const sqmp_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+sqmp_ctx *sqmp_create(int device, const sqmp_robot_desc *d, int *err_out) {
+  auto bail = [&](int code) -> sqmp_ctx * {
+    if (err_out) *err_out = code;
+    return nullptr;
+  };
+  if (!d || d->n_seg < 1 || d->n_seg > SQMP_MAX_SEG || d->n_spheres < 0 || d->n_spheres > SQMP_MAX_SPHERES ||
+      d->n_pairs < 0 || d->n_pairs > SQMP_MAX_PAIRS)
+    return bail(SQMP_ERR_INVALID);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return bail(SQMP_ERR_NODEVICE);
+  if (cudaSetDevice(device) != cudaSuccess) return bail(SQMP_ERR_NODEVICE);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(SQMP_ERR_NODEVICE);
+  if (prop.major != 10) return bail(SQMP_ERR_NODEVICE);  // the library only contains sm_100a SASS
+
+  sqmp_ctx *c = new (std::nothrow) sqmp_ctx();
+  if (!c) return bail(SQMP_ERR_NOMEM);
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  std::memset(&c->rb, 0, sizeof(c->rb));
+  std::memset(&c->gd, 0, sizeof(c->gd));
+  std::memset(c->trees, 0, sizeof(c->trees));
+  std::memset(&c->nn, 0, sizeof(c->nn));
+  RobotDev &rb = c->rb;
+  rb.n_seg = d->n_seg;
+  rb.n_spheres = d->n_spheres;
+  rb.self_const_collision = d->self_const_collision;
+  rb.ref_seg = -1;
+  bool leading = true;
+  for (int s = 0; s < d->n_seg; ++s) {
+    if ((d->seg_type[s] != SQMP_JOINT_ROT && d->seg_type[s] != SQMP_JOINT_TRANS) || d->seg_qidx[s] < 0 ||
+        d->seg_qidx[s] >= SQMP_DOF) {
+      delete c;
+      return bail(SQMP_ERR_INVALID);
+    }
+    rb.seg_type[s] = d->seg_type[s];
+    rb.seg_qidx[s] = d->seg_qidx[s];
+    std::memcpy(rb.seg_pre[s], d->seg_pre[s], sizeof(double) * 12);
+    std::memcpy(rb.seg_axis[s], d->seg_axis[s], sizeof(double) * 3);
+    rb.seg_axis_code[s] = axis_code_of(d->seg_axis[s]);
+    rb.seg_pre_kind[s] = frame_kind_of(d->seg_pre[s]);
+    if (leading && d->seg_type[s] == SQMP_JOINT_TRANS && rb.seg_pre_kind[s] <= 1) rb.ref_seg = s;
+    else leading = false;
+  }
+  std::memcpy(rb.root_off, d->root_offset, sizeof(double) * 3);
+  std::memcpy(rb.ee_tip, d->ee_tip, sizeof(double) * 12);
+  rb.ee_tip_kind = frame_kind_of(d->ee_tip);
+  int prev = -1;
+  for (int s = 0; s <= SQMP_MAX_SEG + 1; ++s) rb.seg_sph_end[s] = 0;
+  c->fk_float_ok = 1;
+  for (int i = 0; i < d->n_spheres; ++i) {
+    const int sg = d->sph_seg[i];
+    if (sg < prev || sg < -1 || sg >= d->n_seg || d->sph_link[i] < 0 || d->sph_link[i] > 63 ||
+        !(d->sph_radius[i] > 0.0)) {
+      delete c;
+      return bail(SQMP_ERR_INVALID);
+    }
+    prev = sg;
+    rb.seg_sph_end[sg + 2] = i + 1;
+    rb.sph[i][0] = d->sph_center[3 * i + 0];
+    rb.sph[i][1] = d->sph_center[3 * i + 1];
+    rb.sph[i][2] = d->sph_center[3 * i + 2];
+    rb.sph[i][3] = d->sph_radius[i];
+    c->sph_link[i] = d->sph_link[i];
+    if (sg <= rb.ref_seg) c->fk_float_ok = 0;  // float chain starts after the prismatic base
+  }
+  for (int s = 1; s <= SQMP_MAX_SEG + 1; ++s)
+    if (rb.seg_sph_end[s] < rb.seg_sph_end[s - 1]) rb.seg_sph_end[s] = rb.seg_sph_end[s - 1];
+  for (int w = 0; w < SQMP_MAX_SPHERES / 32; ++w) rb.sph_enabled[w] = 0xffffffffu;
+  refresh_sphere_grid_params(c);
+
+  c->n_pairs = d->n_pairs;
+  c->h_pairs.resize(size_t(d->n_pairs) + 1);
+  for (int p = 0; p < d->n_pairs; ++p) {
+    const int a = d->pair_a[p], b = d->pair_b[p];
+    if (a < 0 || b < 0 || a >= d->n_spheres || b >= d->n_spheres) {
+      delete c;
+      return bail(SQMP_ERR_INVALID);
+    }
+    const double rs = d->sph_radius[a] + d->sph_radius[b];
+    c->h_pairs[p].a = (unsigned char)a;
+    c->h_pairs[p].b = (unsigned char)b;
+    c->h_pairs[p].pad0 = c->h_pairs[p].pad1 = 0;
+    c->h_pairs[p].rsum2 = float(rs * rs);
+  }
+  bool ok = cudaMalloc(&c->d_pairs, sizeof(SelfPair) * (size_t(d->n_pairs) + 1)) == cudaSuccess;
+  ok = ok && cudaMemcpy(c->d_pairs, c->h_pairs.data(), sizeof(SelfPair) * (size_t(d->n_pairs) + 1),
+                        cudaMemcpyHostToDevice) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&c->streams[0], cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&c->streams[1], cudaStreamNonBlocking) == cudaSuccess;
+  if (!ok) {
+    sqmp_destroy(c);
+    return bail(SQMP_ERR_CUDA);
+  }
+  if (err_out) *err_out = SQMP_OK;
+  return c;
+}
+
+void sqmp_destroy(sqmp_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  if (ctx->d_pairs) cudaFree(ctx->d_pairs);
+  if (ctx->d_occ) cudaFree(ctx->d_occ);
+  if (ctx->d_edt) cudaFree(ctx->d_edt);
+  for (auto &t : ctx->trees)
+    if (t.q[0]) cudaFree(t.q[0]);
+  if (ctx->nn.part_d) cudaFree(ctx->nn.part_d);
+  if (ctx->nn.part_id) cudaFree(ctx->nn.part_id);
+  if (ctx->nn.hits) cudaFree(ctx->nn.hits);
+  for (auto &b : ctx->scratch)
+    if (b.p) cudaFree(b.p);
+  for (auto &s : ctx->streams)
+    if (s) cudaStreamDestroy(s);
+  delete ctx;
+}
+
+int64_t sqmp_kernel_launches(const sqmp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int sqmp_set_option(sqmp_ctx *ctx, const char *name, int64_t value) {
+  if (!ctx || !name) return SQMP_ERR_INVALID;
+  Ctx *c = ctx;
+  const std::string n(name);
+  if (n == "fk_precision") {
+    if (value != 32 && value != 64) return fail(c, SQMP_ERR_INVALID, "fk_precision must be 32 or 64");
+    if (value == 32 && !c->fk_float_ok) return fail(c, SQMP_ERR_INVALID, "float chain needs a translation-only base");
+    c->fk_precision = int(value);
+  } else if (n == "nn_variant") {
+    if (value < 0 || value > 2) return fail(c, SQMP_ERR_INVALID, "nn_variant must be 0, 1 or 2");
+    c->nn_variant = int(value);
+  } else if (n == "nn_hit_pool_bytes") {
+    if (value < 4096) return fail(c, SQMP_ERR_INVALID, "nn_hit_pool_bytes too small");
+    c->nn_hit_pool_bytes = value;
+  } else if (n == "pipeline_chunk") {
+    if (value < 1024) return fail(c, SQMP_ERR_INVALID, "pipeline_chunk too small");
+    c->pipeline_chunk = (value + 31) / 32 * 32;
+  } else {
+    return fail(c, SQMP_ERR_INVALID, "unknown option");
+  }
+  return SQMP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- map
+int sqmp_set_voxel_grid(sqmp_ctx *ctx, const uint32_t *bits, int gx, int gy, int gz, const double origin[3],
+                        double res) {
+  CHECK_CTX();
+  if (!bits) return SQMP_OK;  // CC:78-79
+  if (gx <= 0 || gy <= 0 || gz <= 0 || !origin || !(res > 0.0)) return fail(c, SQMP_ERR_INVALID, "bad grid");
+  const int64_t nvox = int64_t(gx) * gy * gz;
+  if (nvox > (int64_t(1) << 33)) return fail(c, SQMP_ERR_INVALID, "grid too large");
+  double rmax = 0.0;
+  for (int i = 0; i < c->rb.n_spheres; ++i) rmax = std::fmax(rmax, c->rb.sph[i][3]);
+  int window = int(std::ceil(rmax / res)) + 2;
+  if (window > 62) return fail(c, SQMP_ERR_INVALID, "sphere radius too large for this resolution (> 60 voxels)");
+  if (window < 4) window = 4;
+  const int row_words = (gx + 31) / 32 + 1;
+  const size_t lin_words = size_t((nvox + 31) / 32) + 1;
+  const size_t occ_words = size_t(gy) * gz * row_words;
+  CU(cudaDeviceSynchronize());
+  uint32_t *d_lin = nullptr, *d_occ = nullptr;
+  uint8_t *d_a = nullptr, *d_edt = nullptr;
+  uint16_t *d_b = nullptr;
+  auto cleanup = [&]() {
+    if (d_lin) cudaFree(d_lin);
+    if (d_a) cudaFree(d_a);
+    if (d_b) cudaFree(d_b);
+  };
+  cudaError_t e = cudaMalloc(&d_lin, lin_words * 4);
+  if (e == cudaSuccess) e = cudaMemset(d_lin, 0, lin_words * 4);
+  if (e == cudaSuccess) e = cudaMemcpy(d_lin, bits, size_t((nvox + 31) / 32) * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&d_occ, occ_words * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&d_a, size_t(nvox));
+  if (e == cudaSuccess) e = cudaMalloc(&d_b, size_t(nvox) * 2);
+  if (e == cudaSuccess) e = cudaMalloc(&d_edt, size_t(nvox));
+  if (e == cudaSuccess) e = launch_pack_rows(d_lin, gx, gy, gz, row_words, d_occ, nullptr);
+  int nl = 1;
+  if (e == cudaSuccess) e = launch_edt_build(d_occ, row_words, gx, gy, gz, window, d_a, d_b, d_edt, nullptr, &nl);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cleanup();
+  if (e != cudaSuccess) {
+    if (d_occ) cudaFree(d_occ);
+    if (d_edt) cudaFree(d_edt);
+    return fail(c, e == cudaErrorMemoryAllocation ? SQMP_ERR_NOMEM : SQMP_ERR_CUDA, "set_voxel_grid", e);
+  }
+  c->launches += nl;
+  if (c->d_occ) cudaFree(c->d_occ);  // previous collision object deleted (CC:84-85)
+  if (c->d_edt) cudaFree(c->d_edt);
+  c->d_occ = d_occ;
+  c->d_edt = d_edt;
+  GridDev &g = c->gd;
+  g.occ = d_occ; g.edt = d_edt;
+  g.gx = gx; g.gy = gy; g.gz = gz; g.row_words = row_words;
+  g.ox = origin[0]; g.oy = origin[1]; g.oz = origin[2];
+  g.res = res; g.inv_res = 1.0 / res;
+  g.has_grid = 1;
+  refresh_sphere_grid_params(c);
+  return SQMP_OK;
+}
+
+int sqmp_set_disabled_links(sqmp_ctx *ctx, uint64_t link_mask) {
+  CHECK_CTX();
+  for (int w = 0; w < SQMP_MAX_SPHERES / 32; ++w) c->rb.sph_enabled[w] = 0;
+  for (int i = 0; i < c->rb.n_spheres; ++i)
+    if (!((link_mask >> c->sph_link[i]) & 1ull)) c->rb.sph_enabled[i >> 5] |= 1u << (i & 31);
+  return SQMP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- validity
+int sqmp_check_states_dev(sqmp_ctx *ctx, const double *d_q, int64_t S, unsigned flags, uint32_t *d_mask,
+                          void *stream) {
+  CHECK_CTX();
+  if (S < 0 || (S > 0 && (!d_q || !d_mask))) return fail(c, SQMP_ERR_INVALID, "check_states_dev: null pointer");
+  if (S == 0) return SQMP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!(flags & (SQMP_CHECK_SELF | SQMP_CHECK_MAP))) {  // CC:109-110
+    CU(cudaMemsetAsync(d_mask, 0, size_t((S + 31) / 32) * 4, st));
+    return SQMP_OK;
+  }
+  int nl = 0;
+  CU(launch_check_states(c->rb, c->gd, c->d_pairs, c->n_pairs, d_q, nullptr, 0, S, flags, d_mask, c->fk_precision,
+                         st, &nl));
+  c->launches += nl;
+  return SQMP_OK;
+}
+
+int sqmp_check_edges_dev(sqmp_ctx *ctx, const double *d_a, const double *d_b, int64_t E, int num_points,
+                         unsigned flags, uint32_t *d_mask, int32_t *d_first, void *stream) {
+  CHECK_CTX();
+  if (E < 0 || num_points < 1 || num_points > 255 || (E > 0 && (!d_a || !d_b || !d_mask)))
+    return fail(c, SQMP_ERR_INVALID, "check_edges_dev: bad argument");
+  if (E == 0) return SQMP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int P1 = num_points + 1;
+  const int64_t S = E * P1;
+  if (!(flags & (SQMP_CHECK_SELF | SQMP_CHECK_MAP))) {
+    CU(cudaMemsetAsync(d_mask, 0, size_t((S + 31) / 32) * 4, st));
+  } else {
+    int nl = 0;
+    CU(launch_check_states(c->rb, c->gd, c->d_pairs, c->n_pairs, d_a, d_b, num_points, S, flags, d_mask,
+                           c->fk_precision, st, &nl));
+    c->launches += nl;
+  }
+  if (d_first) {
+    CU(launch_first_invalid(d_mask, E, P1, d_first, st));
+    c->launches += 1;
+  }
+  return SQMP_OK;
+}
+
+int sqmp_check_states(sqmp_ctx *ctx, const double *q, int64_t S, unsigned flags, uint32_t *mask_out) {
+  CHECK_CTX();
+  if (S < 0 || (S > 0 && (!q || !mask_out))) return fail(c, SQMP_ERR_INVALID, "check_states: null pointer");
+  if (S == 0) return SQMP_OK;
+  // H2D -> kernel -> D2H in stages over two streams so that copies overlap compute for large batches
+  const int64_t chunk = c->pipeline_chunk;
+  void *dq[2], *dm[2];
+  const int64_t cs = S < chunk ? ((S + 31) / 32 * 32) : chunk;
+  for (int b = 0; b < 2; ++b) {
+    int rc = ensure(c, b, size_t(cs) * SQMP_DOF * sizeof(double), &dq[b]);
+    if (rc) return rc;
+    rc = ensure(c, 2 + b, size_t(cs / 32 + 1) * 4, &dm[b]);
+    if (rc) return rc;
+  }
+  int b = 0;
+  for (int64_t s0 = 0; s0 < S; s0 += cs, b ^= 1) {
+    const int64_t n = S - s0 < cs ? S - s0 : cs;
+    cudaStream_t st = c->streams[b];
+    CU(cudaMemcpyAsync(dq[b], q + s0 * SQMP_DOF, size_t(n) * SQMP_DOF * sizeof(double), cudaMemcpyHostToDevice, st));
+    int rc = sqmp_check_states_dev(ctx, (const double *)dq[b], n, flags, (uint32_t *)dm[b], st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(mask_out + s0 / 32, dm[b], size_t((n + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(c->streams[0]));
+  CU(cudaStreamSynchronize(c->streams[1]));
+  return SQMP_OK;
+}
+
+int sqmp_check_edges(sqmp_ctx *ctx, const double *qa, const double *qb, int64_t E, int num_points, unsigned flags,
+                     uint32_t *mask_out, int32_t *first_invalid) {
+  CHECK_CTX();
+  if (E < 0 || num_points < 1 || num_points > 255 || (E > 0 && (!qa || !qb || !mask_out)))
+    return fail(c, SQMP_ERR_INVALID, "check_edges: bad argument");
+  if (E == 0) return SQMP_OK;
+  const int64_t S = E * (num_points + 1);
+  void *da, *db, *dm, *df;
+  int rc;
+  if ((rc = ensure(c, 0, size_t(E) * SQMP_DOF * 8, &da))) return rc;
+  if ((rc = ensure(c, 1, size_t(E) * SQMP_DOF * 8, &db))) return rc;
+  if ((rc = ensure(c, 2, size_t((S + 31) / 32) * 4, &dm))) return rc;
+  if ((rc = ensure(c, 3, size_t(E) * 4, &df))) return rc;
+  cudaStream_t st = c->streams[0];
+  CU(cudaMemcpyAsync(da, qa, size_t(E) * SQMP_DOF * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(db, qb, size_t(E) * SQMP_DOF * 8, cudaMemcpyHostToDevice, st));
+  rc = sqmp_check_edges_dev(ctx, (const double *)da, (const double *)db, E, num_points, flags, (uint32_t *)dm,
+                            first_invalid ? (int32_t *)df : nullptr, st);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(mask_out, dm, size_t((S + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
+  if (first_invalid) CU(cudaMemcpyAsync(first_invalid, df, size_t(E) * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return SQMP_OK;
+}
+
+int sqmp_get_collisions(sqmp_ctx *ctx, const double q[SQMP_DOF], uint8_t *link_map_hit, uint8_t *pair_hit) {
+  CHECK_CTX();
+  if (!q || !link_map_hit) return fail(c, SQMP_ERR_INVALID, "get_collisions: null pointer");
+  void *dq, *ds, *dp;
+  int rc;
+  if ((rc = ensure(c, 0, SQMP_DOF * 8, &dq))) return rc;
+  if ((rc = ensure(c, 2, SQMP_MAX_SPHERES, &ds))) return rc;
+  if ((rc = ensure(c, 3, size_t(c->n_pairs) + 1, &dp))) return rc;
+  cudaStream_t st = c->streams[0];
+  CU(cudaMemcpyAsync(dq, q, SQMP_DOF * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(ds, 0, SQMP_MAX_SPHERES, st));
+  CU(cudaMemsetAsync(dp, 0, size_t(c->n_pairs) + 1, st));
+  CU(launch_get_collisions(c->rb, c->gd, c->d_pairs, c->n_pairs, (const double *)dq, (uint8_t *)ds, (uint8_t *)dp, st));
+  c->launches += 1;
+  uint8_t sh[SQMP_MAX_SPHERES];
+  CU(cudaMemcpyAsync(sh, ds, SQMP_MAX_SPHERES, cudaMemcpyDeviceToHost, st));
+  if (pair_hit && c->n_pairs) CU(cudaMemcpyAsync(pair_hit, dp, size_t(c->n_pairs), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  std::memset(link_map_hit, 0, 64);
+  for (int i = 0; i < c->rb.n_spheres; ++i)
+    if (sh[i]) link_map_hit[c->sph_link[i]] = 1;
+  return SQMP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- FK
+int sqmp_fk_dev(sqmp_ctx *ctx, const double *d_q, int64_t S, double *d_out, void *stream) {
+  CHECK_CTX();
+  if (S < 0 || (S > 0 && (!d_q || !d_out))) return fail(c, SQMP_ERR_INVALID, "fk_dev: null pointer");
+  if (S == 0) return SQMP_OK;
+  CU(launch_fk(c->rb, d_q, S, d_out, c->fk_precision, (cudaStream_t)stream));
+  c->launches += 1;
+  return SQMP_OK;
+}
+
+int sqmp_fk(sqmp_ctx *ctx, const double *q, int64_t S, double *out) {
+  CHECK_CTX();
+  if (S < 0 || (S > 0 && (!q || !out))) return fail(c, SQMP_ERR_INVALID, "fk: null pointer");
+  if (S == 0) return SQMP_OK;
+  void *dq, *dout;
+  int rc;
+  if ((rc = ensure(c, 0, size_t(S) * SQMP_DOF * 8, &dq))) return rc;
+  if ((rc = ensure(c, 4, size_t(S) * 7 * 8, &dout))) return rc;
+  cudaStream_t st = c->streams[0];
+  CU(cudaMemcpyAsync(dq, q, size_t(S) * SQMP_DOF * 8, cudaMemcpyHostToDevice, st));
+  rc = sqmp_fk_dev(ctx, (const double *)dq, S, (double *)dout, st);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(out, dout, size_t(S) * 7 * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return SQMP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- tree
+#define CHECK_TREE()                                                                 \
+  if (tree < 0 || tree >= SQMP_MAX_TREES) return fail(c, SQMP_ERR_INVALID, "bad tree index"); \
+  TreeDev &t = c->trees[tree];
+
+int sqmp_tree_reset(sqmp_ctx *ctx, int tree) {
+  CHECK_CTX();
+  CHECK_TREE();
+  t.n = 0;
+  return SQMP_OK;
+}
+int sqmp_tree_size(sqmp_ctx *ctx, int tree, int64_t *n_out) {
+  CHECK_CTX();
+  CHECK_TREE();
+  if (n_out) *n_out = t.n;
+  return SQMP_OK;
+}
+int sqmp_tree_append(sqmp_ctx *ctx, int tree, const double q[SQMP_DOF], double cost, int32_t *id_out) {
+  CHECK_CTX();
+  CHECK_TREE();
+  if (!q) return fail(c, SQMP_ERR_INVALID, "tree_append: null q");
+  if (t.n >= 0x7fffffff) return fail(c, SQMP_ERR_INVALID, "tree full");
+  CU(cudaStreamSynchronize(c->streams[0]));
+  int rc = tree_reserve(c, t, t.n + 1);
+  if (rc) return rc;
+  CU(launch_tree_set_one(t, t.n, q, cost, c->streams[0]));
+  CU(cudaStreamSynchronize(c->streams[0]));
+  c->launches += 1;
+  if (id_out) *id_out = int32_t(t.n);
+  t.n += 1;
+  return SQMP_OK;
+}
+int sqmp_tree_append_batch(sqmp_ctx *ctx, int tree, const double *q, const double *cost, int64_t n,
+                           int32_t *first_id_out) {
+  CHECK_CTX();
+  CHECK_TREE();
+  if (n < 0 || (n > 0 && (!q || !cost))) return fail(c, SQMP_ERR_INVALID, "tree_append_batch: null pointer");
+  if (t.n + n > 0x7fffffff) return fail(c, SQMP_ERR_INVALID, "tree full");
+  if (first_id_out) *first_id_out = int32_t(t.n);
+  if (n == 0) return SQMP_OK;
+  int rc = tree_reserve(c, t, t.n + n);
+  if (rc) return rc;
+  void *dq, *dc;
+  if ((rc = ensure(c, 0, size_t(n) * SQMP_DOF * 8, &dq))) return rc;
+  if ((rc = ensure(c, 1, size_t(n) * 8, &dc))) return rc;
+  cudaStream_t st = c->streams[0];
+  CU(cudaMemcpyAsync(dq, q, size_t(n) * SQMP_DOF * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dc, cost, size_t(n) * 8, cudaMemcpyHostToDevice, st));
+  CU(launch_tree_append(t, (const double *)dq, (const double *)dc, t.n, n, st));
+  CU(cudaStreamSynchronize(st));
+  c->launches += 1;
+  t.n += n;
+  return SQMP_OK;
+}
+int sqmp_tree_update(sqmp_ctx *ctx, int tree, int32_t id, const double q[SQMP_DOF], double cost) {
+  CHECK_CTX();
+  CHECK_TREE();
+  if (!q || id < 0 || id >= t.n) return fail(c, SQMP_ERR_INVALID, "tree_update: bad id");
+  CU(launch_tree_set_one(t, id, q, cost, c->streams[0]));
+  CU(cudaStreamSynchronize(c->streams[0]));
+  c->launches += 1;
+  return SQMP_OK;
+}
+int sqmp_tree_update_costs(sqmp_ctx *ctx, int tree, const int32_t *ids, const double *cost, int64_t n) {
+  CHECK_CTX();
+  CHECK_TREE();
+  if (n < 0 || (n > 0 && (!ids || !cost))) return fail(c, SQMP_ERR_INVALID, "tree_update_costs: null pointer");
+  if (n == 0) return SQMP_OK;
+  for (int64_t i = 0; i < n; ++i)
+    if (ids[i] < 0 || ids[i] >= t.n) return fail(c, SQMP_ERR_INVALID, "tree_update_costs: bad id");
+  void *di, *dc;
+  int rc;
+  if ((rc = ensure(c, 0, size_t(n) * 4, &di))) return rc;
+  if ((rc = ensure(c, 1, size_t(n) * 8, &dc))) return rc;
+  cudaStream_t st = c->streams[0];
+  CU(cudaMemcpyAsync(di, ids, size_t(n) * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dc, cost, size_t(n) * 8, cudaMemcpyHostToDevice, st));
+  CU(launch_tree_update_costs(t, (const int32_t *)di, (const double *)dc, n, st));
+  CU(cudaStreamSynchronize(st));
+  c->launches += 1;
+  return SQMP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- NN
+int sqmp_nn_nearest_dev(sqmp_ctx *ctx, int tree, const double *d_queries, int64_t Q, int32_t *d_id, void *stream) {
+  CHECK_CTX();
+  CHECK_TREE();
+  if (Q < 0 || (Q > 0 && (!d_queries || !d_id))) return fail(c, SQMP_ERR_INVALID, "nn_nearest_dev: null pointer");
+  if (Q == 0) return SQMP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (t.n == 0) {  // BS:4084: id stays 0 (the reference would then index an empty vector; we report 0)
+    CU(cudaMemsetAsync(d_id, 0, size_t(Q) * 4, st));
+    return SQMP_OK;
+  }
+  const int variant = pick_variant(c, Q);
+  const int hint = pick_chunk_hint(c, variant, t.n, Q);
+  int rc = nn_prepare(c, Q, hint, false, t.n);
+  if (rc) return rc;
+  int nl = 0;
+  CU(launch_nn_nearest(t, d_queries, Q, d_id, c->nn, hint, variant, st, &nl));
+  c->launches += nl;
+  return SQMP_OK;
+}
+
+int sqmp_nn_radius_dev(sqmp_ctx *ctx, int tree, const double *d_queries, const int32_t *d_exclude, int64_t Q,
+                       double r, int k, int32_t *d_low, int32_t *d_high, int32_t *d_count, int32_t *d_overflow,
+                       void *stream) {
+  CHECK_CTX();
+  CHECK_TREE();
+  if (Q < 0 || k < 1 || k > 1024 || (Q > 0 && (!d_queries || !d_low || !d_high || !d_count || !d_overflow)))
+    return fail(c, SQMP_ERR_INVALID, "nn_radius_dev: bad argument");
+  if (Q == 0) return SQMP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaMemsetAsync(d_overflow, 0, 4, st));
+  if (t.n == 0) {
+    CU(cudaMemsetAsync(d_count, 0, size_t(Q) * 4, st));
+    CU(cudaMemsetAsync(d_low, 0xff, size_t(Q) * k * 4, st));
+    CU(cudaMemsetAsync(d_high, 0xff, size_t(Q) * k * 4, st));
+    return SQMP_OK;
+  }
+  const int variant = pick_variant(c, Q);
+  const int hint = pick_chunk_hint(c, variant, t.n, Q);
+  int rc = nn_prepare(c, Q, hint, true, t.n);
+  if (rc) return rc;
+  int nl = 0;
+  CU(launch_nn_radius(t, d_queries, d_exclude, Q, sumsq_threshold(r), k, d_low, d_high, d_count, d_overflow, c->nn,
+                      hint, variant, st, &nl));
+  c->launches += nl;
+  return SQMP_OK;
+}
+
+int sqmp_nn_nearest(sqmp_ctx *ctx, int tree, const double *queries, int64_t Q, int32_t *id_out) {
+  CHECK_CTX();
+  if (Q < 0 || (Q > 0 && (!queries || !id_out))) return fail(c, SQMP_ERR_INVALID, "nn_nearest: null pointer");
+  if (Q == 0) return SQMP_OK;
+  void *dq, *di;
+  int rc;
+  if ((rc = ensure(c, 0, size_t(Q) * SQMP_DOF * 8, &dq))) return rc;
+  if ((rc = ensure(c, 2, size_t(Q) * 4, &di))) return rc;
+  cudaStream_t st = c->streams[0];
+  CU(cudaMemcpyAsync(dq, queries, size_t(Q) * SQMP_DOF * 8, cudaMemcpyHostToDevice, st));
+  rc = sqmp_nn_nearest_dev(ctx, tree, (const double *)dq, Q, (int32_t *)di, st);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(id_out, di, size_t(Q) * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return SQMP_OK;
+}
+
+static int radius_host_range(sqmp_ctx *ctx, int tree, const double *queries, const int32_t *exclude, int64_t q0,
+                             int64_t nq, double r, int k, int32_t *low, int32_t *high, int32_t *count, int *overflow) {
+  Ctx *c = ctx;
+  void *dq, *de, *dl, *dh, *dc, *dv;
+  int rc;
+  if ((rc = ensure(c, 0, size_t(nq) * SQMP_DOF * 8, &dq))) return rc;
+  if ((rc = ensure(c, 1, size_t(nq) * 4, &de))) return rc;
+  if ((rc = ensure(c, 2, size_t(nq) * k * 4, &dl))) return rc;
+  if ((rc = ensure(c, 3, size_t(nq) * k * 4, &dh))) return rc;
+  if ((rc = ensure(c, 4, size_t(nq) * 4, &dc))) return rc;
+  if ((rc = ensure(c, 5, 64, &dv))) return rc;
+  cudaStream_t st = c->streams[0];
+  CU(cudaMemcpyAsync(dq, queries + q0 * SQMP_DOF, size_t(nq) * SQMP_DOF * 8, cudaMemcpyHostToDevice, st));
+  if (exclude) CU(cudaMemcpyAsync(de, exclude + q0, size_t(nq) * 4, cudaMemcpyHostToDevice, st));
+  rc = sqmp_nn_radius_dev(ctx, tree, (const double *)dq, exclude ? (const int32_t *)de : nullptr, nq, r, k,
+                          (int32_t *)dl, (int32_t *)dh, (int32_t *)dc, (int32_t *)dv, st);
+  if (rc) return rc;
+  int32_t ov = 0;
+  CU(cudaMemcpyAsync(&ov, dv, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  *overflow = ov;
+  if (ov) return SQMP_OK;
+  CU(cudaMemcpyAsync(low + q0 * k, dl, size_t(nq) * k * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(high + q0 * k, dh, size_t(nq) * k * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(count + q0, dc, size_t(nq) * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return SQMP_OK;
+}
+
+int sqmp_nn_radius(sqmp_ctx *ctx, int tree, const double *queries, const int32_t *exclude_id, int64_t Q, double r,
+                   int k, int32_t *low_ids, int32_t *high_ids, int32_t *count_out) {
+  CHECK_CTX();
+  if (Q < 0 || k < 1 || k > 1024 || (Q > 0 && (!queries || !low_ids || !high_ids || !count_out)))
+    return fail(c, SQMP_ERR_INVALID, "nn_radius: bad argument");
+  if (Q == 0) return SQMP_OK;
+  // The per-query hit buffer shares a fixed pool; if a batch overflows it, halve the batch (the buffer per
+  // query doubles) until it fits — at batch size 1 the buffer holds the whole tree.
+  int64_t batch = Q;
+  for (int64_t q0 = 0; q0 < Q;) {
+    const int64_t nq = Q - q0 < batch ? Q - q0 : batch;
+    int ov = 0;
+    int rc = radius_host_range(ctx, tree, queries, exclude_id, q0, nq, r, k, low_ids, high_ids, count_out, &ov);
+    if (rc) return rc;
+    if (ov) {
+      if (nq == 1) return fail(c, SQMP_ERR_OVERFLOW, "nn_radius: hit pool smaller than the tree");
+      batch = (nq + 1) / 2;
+      continue;
+    }
+    q0 += nq;
+  }
+  return SQMP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,181 @@
+// fk.cu — K2: batched end-effector forward kinematics, 64 B in / 56 B out per state (the HBM-bound kernel).
+//
+// Reference path replaced: KDLRobotModel::compute_FK (kdl_kuka_model.cpp:278-305), which copies the KDL chain by
+// value and constructs a ChainFkSolverPos_recursive for every single call, as invoked 21x per candidate edge by
+// BiRRTstarPlanner::interpolateConfigurations (birrt_star.cpp:4486-4487).
+//
+// Data movement: a CTA owns a tile of FK_TILE consecutive states.  The 64-byte input rows and 56-byte output
+// rows are contiguous in global memory, so the tile is moved with 1-D bulk async copies (TMA, cp.async.bulk ->
+// SASS UBLKCP) between global and shared memory: one elected thread issues the load and waits on an mbarrier,
+// every thread then reads its own row from shared memory, computes the chain in registers, writes its 7 doubles
+// back to shared memory, and one elected thread issues the bulk store.  Global traffic is therefore exactly the
+// algorithmic 120 B/state in full 128-byte lines, with no per-thread strided LDG/STG.
+#include "fk_device.cuh"
+
+namespace sqmp {
+
+constexpr int FK_TILE = 128;  // states per CTA iteration == threads per CTA
+// row pitches in shared memory (doubles).  Input rows keep the global pitch (8) because the bulk copy is a flat
+// byte copy; reading q[j] of row t hits bank pair (16 t + 2 j) mod 32: threads t and t+2 collide (16-way).  The
+// reads are therefore rotated per thread (column (j + t/2) mod 8), which makes the 8-byte accesses of a
+// half-warp hit 16 distinct bank pairs.  Outputs use pitch 7 (odd) and are conflict-free as they are.
+constexpr int FK_IN_PITCH = 8, FK_OUT_PITCH = 7;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// The chain for one state: T = double everywhere, or T = float for the rotational part with the prismatic base
+// added in double (see DESIGN.md for the error budget against the 1e-5 m / 1e-5 rad tolerance).
+template <typename T>
+__device__ __forceinline__ void fk_one(const RobotDev &rb, const double (&q)[SQMP_DOF], double *out7) {
+  Frame<T> f;
+  frame_set_translation<T>(f, T(0), T(0), T(0));
+  double off[3] = {0.0, 0.0, 0.0};
+  int sg0 = 0;
+  if (sizeof(T) == 4) {
+    for (int sg = 0; sg <= rb.ref_seg; ++sg) {
+      const int qi = rb.seg_qidx[sg];
+      double qv = q[0];
+#pragma unroll
+      for (int j = 1; j < SQMP_DOF; ++j) qv = (qi == j) ? q[j] : qv;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) off[i] += rb.seg_pre[sg][9 + i] + rb.seg_axis[sg][i] * qv;
+    }
+    sg0 = rb.ref_seg + 1;
+  }
+  for (int sg = sg0; sg < rb.n_seg; ++sg) frame_advance<T>(f, rb, sg, q);
+  frame_mul_const<T>(f, rb.ee_tip, rb.ee_tip_kind);
+  double R[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = double(f.r[i]);
+  out7[0] = double(f.p[0]) + off[0];
+  out7[1] = double(f.p[1]) + off[1];
+  out7[2] = double(f.p[2]) + off[2];
+  get_quaternion(R, out7[3], out7[4], out7[5], out7[6]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(FK_TILE)
+k2_fk(const __grid_constant__ RobotDev rb, const double *__restrict__ q_in, int64_t S, double *__restrict__ out) {
+  __shared__ __align__(128) double s_in[2][FK_TILE * FK_IN_PITCH];
+  __shared__ __align__(128) double s_out[FK_TILE * FK_OUT_PITCH];
+  __shared__ __align__(8) uint64_t bar[2];
+  const int t = threadIdx.x;
+  const int64_t n_tiles = (S + FK_TILE - 1) / FK_TILE;
+  if (t == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto tile_rows = [&](int64_t tile) { return int(imin64(FK_TILE, S - tile * FK_TILE)); };
+  int64_t tile = blockIdx.x;
+  if (t == 0 && tile < n_tiles) {
+    const uint32_t bytes = uint32_t(tile_rows(tile)) * SQMP_DOF * sizeof(double);
+    mbar_expect_tx(&bar[0], bytes);
+    bulk_g2s(s_in[0], q_in + tile * FK_TILE * SQMP_DOF, bytes, &bar[0]);
+  }
+  uint32_t phase[2] = {0, 0};
+  int buf = 0;
+  for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+    // prefetch the next tile of this CTA into the other buffer (its previous contents were consumed one
+    // iteration ago, before the __syncthreads at the end of that iteration)
+    const int64_t next = tile + gridDim.x;
+    if (t == 0 && next < n_tiles) {
+      const uint32_t bytes = uint32_t(tile_rows(next)) * SQMP_DOF * sizeof(double);
+      mbar_expect_tx(&bar[buf ^ 1], bytes);
+      bulk_g2s(s_in[buf ^ 1], q_in + next * FK_TILE * SQMP_DOF, bytes, &bar[buf ^ 1]);
+    }
+    mbar_wait(&bar[buf], phase[buf]);
+    phase[buf] ^= 1;
+
+    const int rows = tile_rows(tile);
+    if (t < rows) {
+      double q[SQMP_DOF];
+      const double *row = s_in[buf] + t * FK_IN_PITCH;
+      const int rot = (t >> 1) & 7;
+#pragma unroll
+      for (int j = 0; j < SQMP_DOF; ++j) {
+        const double v = row[(j + rot) & 7];  // element (j+rot)&7 -> register slot decided below
+        // scatter v into q[(j+rot)&7] without dynamic register indexing
+#pragma unroll
+        for (int m = 0; m < SQMP_DOF; ++m)
+          if (((j + rot) & 7) == m) q[m] = v;
+      }
+      double o[7];
+      fk_one<T>(rb, q, o);
+      // the previous tile's bulk store must have finished reading s_out before it is overwritten
+      // (wait executed by the issuing thread below, made visible to all by the __syncthreads)
+      if (rows == FK_TILE) {
+        double *orow = s_out + t * FK_OUT_PITCH;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) orow[j] = o[j];
+      } else {
+        // ragged last tile: its byte count need not be a multiple of 16, which bulk copies require
+        double *orow = out + (tile * FK_TILE + t) * 7;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) orow[j] = o[j];
+      }
+    }
+    fence_async_smem();  // make the generic-proxy writes to s_out visible to the async (bulk copy) proxy
+    __syncthreads();
+    if (t == 0 && rows == FK_TILE) {
+      bulk_s2g(out + tile * FK_TILE * 7, s_out, uint32_t(FK_TILE) * 7 * sizeof(double));
+      bulk_commit();
+      bulk_wait_read0();  // s_out may be rewritten once the copy engine has read it
+    }
+    __syncthreads();
+  }
+  if (t == 0) bulk_wait0();
+}
+
+cudaError_t launch_fk(const RobotDev &rb, const double *d_q, int64_t S, double *d_out, int fk_precision,
+                      cudaStream_t st) {
+  if (S <= 0) return cudaSuccess;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t n_tiles = (S + FK_TILE - 1) / FK_TILE;
+  // persistent CTAs: a multiple of the SM count, enough resident warps to cover the fp64 latency
+  const unsigned blocks = unsigned(imin64(n_tiles, int64_t(sms) * 8));
+  if (fk_precision == 32)
+    k2_fk<float><<<blocks, FK_TILE, 0, st>>>(rb, d_q, S, d_out);
+  else
+    k2_fk<double><<<blocks, FK_TILE, 0, st>>>(rb, d_q, S, d_out);
+  return cudaGetLastError();
+}
+
+}  // namespace sqmp

@@ -1,0 +1,393 @@
+// nn.cu — device tree mirror and K3/K4: exact brute-force nearest / radius + top-k-by-cost search.
+//
+// Reference path replaced (file:line in /root/reference, tags as in include/sqmp_b200.h):
+//   DistanceHeuristics::euclidean_joint_space_distance DH:128-156 (fp64, sum in index order, sqrt),
+//   BiRRTstarPlanner::find_nearest_neighbour_interpolation BS:4076-4133 (strict '<', serial order, min0 = 10000, id0 = 0),
+//   find_near_vertices_interpolation BS:4272-4324 (d < r, id != x_new.id, sort by cost_reach.total DS:41-44),
+//   consumers BS:4618-4623 (first max_near_nodes) and BS:5075-5089 (last max_near_nodes, walked backwards),
+//   tree types DS:11-54 and mutation sites BS:3298-3322, 5173-5193, 5518-5520.
+// The reference keeps an AoS of std::vector-laden Nodes and deep-copies Nodes to sort them.  Here the tree is a
+// device-resident SoA (q[d][n] + cost[n]); distances are evaluated with explicit round-to-nearest mul/add
+// intrinsics (never contracted to FMA) in the reference's summation order, so sums of squares are bit-identical
+// to the CPU's, sqrt is IEEE (sqrt.rn.f64), and every comparison is made on the same values the reference
+// compares.  Ties resolve to the lowest node id, which is what the reference's serial loop does.
+//
+// Two mappings, both exact:
+//   QT ("query per thread", many queries): nodes stream through shared memory in tiles and are broadcast to
+//      all lanes; each lane keeps its query and running best in registers; no cross-lane traffic at all.
+//   WQ ("warp per query", few queries — the planner's own call shape): lanes stride over the nodes of a chunk,
+//      the warp reduces (distance, id) lexicographically with shuffles, radius hits are compacted with a ballot.
+// Both write one partial result per (query, node chunk); a merge kernel folds the chunks in id order.
+#include <math_constants.h>
+
+#include "sqmp_common.cuh"
+
+namespace sqmp {
+
+// ---------------------------------------------------------------------------------------------------------
+// tree mirror
+// ---------------------------------------------------------------------------------------------------------
+struct TreePtrs {
+  double *q[SQMP_DOF];
+  double *cost;
+};
+static inline TreePtrs ptrs_of(const TreeDev &t) {
+  TreePtrs p;
+  for (int d = 0; d < SQMP_DOF; ++d) p.q[d] = t.q[d];
+  p.cost = t.cost;
+  return p;
+}
+
+// rows (AoS, n x 8) -> SoA at [first, first+n)
+__global__ void k_tree_append(TreePtrs t, const double *__restrict__ rows, const double *__restrict__ cost,
+                              int64_t first, int64_t n) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 *r4 = reinterpret_cast<const double4 *>(rows + i * SQMP_DOF);
+  const double4 a = r4[0], b = r4[1];
+  t.q[0][first + i] = a.x; t.q[1][first + i] = a.y; t.q[2][first + i] = a.z; t.q[3][first + i] = a.w;
+  t.q[4][first + i] = b.x; t.q[5][first + i] = b.y; t.q[6][first + i] = b.z; t.q[7][first + i] = b.w;
+  t.cost[first + i] = cost[i];
+}
+struct OneNode {
+  double q[SQMP_DOF];
+  double cost;
+};
+__global__ void k_tree_set_one(TreePtrs t, int64_t id, OneNode v) {
+  if (threadIdx.x < SQMP_DOF) t.q[threadIdx.x][id] = v.q[threadIdx.x];
+  if (threadIdx.x == SQMP_DOF) t.cost[id] = v.cost;
+}
+__global__ void k_tree_update_costs(TreePtrs t, const int32_t *__restrict__ ids, const double *__restrict__ cost,
+                                    int64_t n, int64_t size) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n && ids[i] >= 0 && ids[i] < size) t.cost[ids[i]] = cost[i];
+}
+cudaError_t launch_tree_append(TreeDev &t, const double *d_q_rows, const double *d_cost, int64_t first, int64_t n,
+                               cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  k_tree_append<<<unsigned((n + 255) / 256), 256, 0, st>>>(ptrs_of(t), d_q_rows, d_cost, first, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_tree_set_one(TreeDev &t, int64_t id, const double q[SQMP_DOF], double cost, cudaStream_t st) {
+  OneNode v;
+  for (int d = 0; d < SQMP_DOF; ++d) v.q[d] = q[d];
+  v.cost = cost;
+  k_tree_set_one<<<1, 32, 0, st>>>(ptrs_of(t), id, v);
+  return cudaGetLastError();
+}
+cudaError_t launch_tree_update_costs(TreeDev &t, const int32_t *d_ids, const double *d_cost, int64_t n,
+                                     cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  k_tree_update_costs<<<unsigned((n + 255) / 256), 256, 0, st>>>(ptrs_of(t), d_ids, d_cost, n, t.n);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// distance: sum_error_sq += (d*d) for i = 0..7, d = node[i] - query[i]   (DH:145-149; argument order BS:4119)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double sumsq8(const double (&node)[SQMP_DOF], const double (&query)[SQMP_DOF]) {
+  // conf_start = node, conf_end = query  =>  distance_vec[i] = query[i] - node[i]
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < SQMP_DOF; ++i) {
+    const double d = __dsub_rn(query[i], node[i]);
+    s = __dadd_rn(s, __dmul_rn(d, d));
+  }
+  return s;
+}
+
+constexpr double NN_INIT_DIST = 10000.0;      // BS:4090
+constexpr double NN_INIT_SUMSQ = 100000000.0;  // 10000^2, exactly representable; sqrt(1e8) == 1e4 exactly
+
+struct Best {
+  double s;   // sum of squares of the incumbent (a node can only win if its sum is strictly smaller)
+  double d;   // sqrt of it: the value the reference compares
+  int32_t id;
+};
+// candidate (s, id) against the incumbent; ids must be offered in increasing order per thread
+__device__ __forceinline__ void offer(Best &b, double s, int32_t id) {
+  if (s < b.s) {                 // necessary for sqrt(s) < b.d (sqrt is monotone); rare after warm-up
+    const double d = sqrt(s);    // IEEE round-to-nearest
+    if (d < b.d) { b.s = s; b.d = d; b.id = id; }   // BS:4122 strict '<'
+  }
+}
+// lexicographic (d, id) minimum: equal distances keep the lower id = what the serial reference loop keeps
+__device__ __forceinline__ bool better(double d1, int32_t id1, double d2, int32_t id2) {
+  return d1 < d2 || (d1 == d2 && id1 < id2);
+}
+
+constexpr int NN_THREADS = 128;
+constexpr int NN_TILE = 256;  // nodes per shared-memory tile (QT)
+
+// ---------------------------------------------------------------------------------------------------------
+// K3 nearest — QT variant.  grid = (ceil(Q/128), chunks)
+// ---------------------------------------------------------------------------------------------------------
+template <bool RADIUS>
+__global__ void __launch_bounds__(NN_THREADS)
+k_nn_qt(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ queries, int64_t Q,
+        double *__restrict__ part_d, int32_t *__restrict__ part_id,
+        // radius mode
+        const int32_t *__restrict__ exclude, double s_thr, int32_t *__restrict__ count, int32_t *__restrict__ hits,
+        int64_t hit_cap) {
+  __shared__ double tile[SQMP_DOF][NN_TILE];
+  const int64_t qi = int64_t(blockIdx.x) * NN_THREADS + threadIdx.x;
+  const bool active = qi < Q;
+  double query[SQMP_DOF];
+  if (active) {
+    const double4 *p4 = reinterpret_cast<const double4 *>(queries + qi * SQMP_DOF);
+    const double4 a = p4[0], b = p4[1];
+    query[0] = a.x; query[1] = a.y; query[2] = a.z; query[3] = a.w;
+    query[4] = b.x; query[5] = b.y; query[6] = b.z; query[7] = b.w;
+  } else {
+#pragma unroll
+    for (int d = 0; d < SQMP_DOF; ++d) query[d] = 0.0;
+  }
+  const int32_t excl = (RADIUS && active && exclude) ? exclude[qi] : -1;
+  Best best = {NN_INIT_SUMSQ, NN_INIT_DIST, 0};
+  const int64_t n0 = int64_t(blockIdx.y) * chunk_len, n1 = min(N, n0 + chunk_len);
+
+  for (int64_t base = n0; base < n1; base += NN_TILE) {
+    const int len = int(imin64(NN_TILE, n1 - base));
+    __syncthreads();
+    for (int i = threadIdx.x; i < NN_TILE; i += NN_THREADS) {
+#pragma unroll
+      for (int d = 0; d < SQMP_DOF; ++d) tile[d][i] = (i < len) ? t.q[d][base + i] : CUDART_INF;
+    }
+    __syncthreads();
+    if (!active) continue;
+#pragma unroll 4
+    for (int i = 0; i < len; ++i) {
+      double node[SQMP_DOF];
+#pragma unroll
+      for (int d = 0; d < SQMP_DOF; ++d) node[d] = tile[d][i];  // broadcast read
+      const double s = sumsq8(node, query);
+      const int32_t id = int32_t(base + i);
+      if (RADIUS) {
+        if (s < s_thr && id != excl) {   // sqrt(s) < r  <=>  s < s_thr (s_thr from the host, exact)
+          const int32_t slot = atomicAdd(&count[qi], 1);
+          if (slot < hit_cap) hits[qi * hit_cap + slot] = id;
+        }
+      } else {
+        offer(best, s, id);
+      }
+    }
+  }
+  if (!RADIUS && active) {
+    part_d[int64_t(blockIdx.y) * Q + qi] = best.d;
+    part_id[int64_t(blockIdx.y) * Q + qi] = best.id;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K3/K4 — WQ variant.  grid = (Q, ceil(chunks / warps_per_cta)); every warp owns one node chunk of one query
+// ---------------------------------------------------------------------------------------------------------
+template <bool RADIUS>
+__global__ void __launch_bounds__(NN_THREADS)
+k_nn_wq(TreePtrs t, int64_t N, int64_t chunk_len, int chunks, const double *__restrict__ queries, int64_t Q,
+        double *__restrict__ part_d, int32_t *__restrict__ part_id, const int32_t *__restrict__ exclude,
+        double s_thr, int32_t *__restrict__ count, int32_t *__restrict__ hits, int64_t hit_cap) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t qi = blockIdx.x;
+  const int chunk = blockIdx.y * (NN_THREADS / 32) + warp;
+  if (chunk >= chunks) return;  // whole warp leaves together
+  double query[SQMP_DOF];
+#pragma unroll
+  for (int d = 0; d < SQMP_DOF; ++d) query[d] = __ldg(queries + qi * SQMP_DOF + d);
+  const int32_t excl = (RADIUS && exclude) ? exclude[qi] : -1;
+  Best best = {NN_INIT_SUMSQ, NN_INIT_DIST, 0};
+  const int64_t n0 = int64_t(chunk) * chunk_len, n1 = min(N, n0 + chunk_len);
+  for (int64_t base = n0; base < n1; base += 32) {
+    const int64_t n = base + lane;
+    bool hit = false;
+    if (n < n1) {
+      double node[SQMP_DOF];
+#pragma unroll
+      for (int d = 0; d < SQMP_DOF; ++d) node[d] = t.q[d][n];  // coalesced: 32 consecutive doubles per dim
+      const double s = sumsq8(node, query);
+      if (RADIUS) hit = s < s_thr && int32_t(n) != excl;
+      else offer(best, s, int32_t(n));
+    }
+    if (RADIUS) {
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m) {
+        int32_t slot0 = 0;
+        if (lane == 0) slot0 = atomicAdd(&count[qi], __popc(m));
+        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+        const int32_t slot = slot0 + __popc(m & ((1u << lane) - 1u));  // ballot compaction
+        if (hit && slot < hit_cap) hits[qi * hit_cap + slot] = int32_t(n);
+      }
+    }
+  }
+  if (!RADIUS) {
+    // warp argmin over (d, id), lexicographic
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double od = __shfl_xor_sync(0xffffffffu, best.d, o);
+      const int32_t oid = __shfl_xor_sync(0xffffffffu, best.id, o);
+      // a lane that never improved on the initial value carries (10000.0, 0): it must not win on id
+      // against a real candidate with the same distance -- d == 10000.0 can only be the initial value
+      // because real candidates need d < 10000.0 (strict) to be taken at all.
+      if (better(od, oid, best.d, best.id)) { best.d = od; best.id = oid; }
+    }
+    if (lane == 0) {
+      part_d[int64_t(chunk) * Q + qi] = best.d;
+      part_id[int64_t(chunk) * Q + qi] = best.id;
+    }
+  }
+}
+
+// fold the per-chunk partial results in chunk (= id) order; strict '<' keeps the lowest id on ties (BS:4122)
+__global__ void k_nn_merge(const double *__restrict__ part_d, const int32_t *__restrict__ part_id, int chunks,
+                           int64_t Q, int32_t *__restrict__ id_out) {
+  const int64_t qi = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (qi >= Q) return;
+  double bd = NN_INIT_DIST;
+  int32_t bid = 0;
+  for (int c = 0; c < chunks; ++c) {
+    const double d = part_d[int64_t(c) * Q + qi];
+    if (d < bd) { bd = d; bid = part_id[int64_t(c) * Q + qi]; }
+  }
+  id_out[qi] = bid;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K4 selection: one warp per query picks the k lowest and k highest (cost, id) among the compacted hits
+// ---------------------------------------------------------------------------------------------------------
+struct Key {
+  double c;
+  int32_t id;
+};
+__device__ __forceinline__ bool key_lt(const Key &a, const Key &b) { return a.c < b.c || (a.c == b.c && a.id < b.id); }
+__device__ __forceinline__ Key warp_min_key(Key v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Key w;
+    w.c = __shfl_xor_sync(0xffffffffu, v.c, o);
+    w.id = __shfl_xor_sync(0xffffffffu, v.id, o);
+    if (key_lt(w, v)) v = w;
+  }
+  return v;
+}
+__device__ __forceinline__ Key warp_max_key(Key v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Key w;
+    w.c = __shfl_xor_sync(0xffffffffu, v.c, o);
+    w.id = __shfl_xor_sync(0xffffffffu, v.id, o);
+    if (key_lt(v, w)) v = w;
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(NN_THREADS)
+k_nn_topk(const double *__restrict__ cost, const int32_t *__restrict__ hits, int64_t hit_cap,
+          const int32_t *__restrict__ count, int64_t Q, int k, int32_t *__restrict__ low, int32_t *__restrict__ high,
+          int32_t *__restrict__ overflow) {
+  const int lane = threadIdx.x & 31;
+  const int64_t qi = int64_t(blockIdx.x) * (NN_THREADS / 32) + (threadIdx.x >> 5);
+  if (qi >= Q) return;
+  const int32_t total = count[qi];
+  if (total > hit_cap) {
+    if (lane == 0) atomicExch(overflow, 1);
+  }
+  const int32_t m = int32_t(imin64(total, hit_cap));
+  const int32_t *h = hits + qi * hit_cap;
+  const Key kmax = {CUDART_INF, 0x7fffffff}, kmin = {-CUDART_INF, -1};
+  Key last = kmin;
+  for (int tsel = 0; tsel < k; ++tsel) {   // t-th lowest = smallest key strictly above the previous pick
+    Key mine = kmax;
+    for (int i = lane; i < m; i += 32) {
+      Key c;
+      c.id = h[i];
+      c.c = cost[c.id];
+      if (key_lt(last, c) && key_lt(c, mine)) mine = c;
+    }
+    const Key w = warp_min_key(mine);
+    const bool found = w.id != kmax.id;
+    if (lane == 0) low[qi * k + tsel] = found ? w.id : -1;
+    if (!found) {
+      for (int r = tsel + 1 + lane; r < k; r += 32) low[qi * k + r] = -1;
+      break;
+    }
+    last = w;
+  }
+  last = kmax;
+  for (int tsel = 0; tsel < k; ++tsel) {   // t-th highest = largest key strictly below the previous pick
+    Key mine = kmin;
+    for (int i = lane; i < m; i += 32) {
+      Key c;
+      c.id = h[i];
+      c.c = cost[c.id];
+      if (key_lt(c, last) && key_lt(mine, c)) mine = c;
+    }
+    const Key w = warp_max_key(mine);
+    const bool found = w.id != kmin.id;
+    if (lane == 0) high[qi * k + tsel] = found ? w.id : -1;
+    if (!found) {
+      for (int r = tsel + 1 + lane; r < k; r += 32) high[qi * k + r] = -1;
+      break;
+    }
+    last = w;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------------
+static void pick_chunks(int64_t N, int64_t Q, int variant, int chunks_hint, int &chunks, int64_t &chunk_len) {
+  (void)Q;
+  chunks = chunks_hint < 1 ? 1 : chunks_hint;
+  chunk_len = (N + chunks - 1) / chunks;
+  const int64_t gran = variant == 2 ? 32 : NN_TILE;
+  chunk_len = ((chunk_len + gran - 1) / gran) * gran;
+  if (chunk_len < gran) chunk_len = gran;
+  chunks = int((N + chunk_len - 1) / chunk_len);
+  if (chunks < 1) chunks = 1;
+}
+
+cudaError_t launch_nn_nearest(const TreeDev &t, const double *d_queries, int64_t Q, int32_t *d_id, NNScratch &sc,
+                              int chunks_hint, int variant, cudaStream_t st, int *n_launch) {
+  if (Q <= 0) return cudaSuccess;
+  int chunks;
+  int64_t chunk_len;
+  pick_chunks(t.n, Q, variant, chunks_hint, chunks, chunk_len);
+  if (variant == 2) {
+    dim3 grid(unsigned(Q), unsigned((chunks + NN_THREADS / 32 - 1) / (NN_THREADS / 32)));
+    k_nn_wq<false><<<grid, NN_THREADS, 0, st>>>(ptrs_of(t), t.n, chunk_len, chunks, d_queries, Q, sc.part_d,
+                                                sc.part_id, nullptr, 0.0, nullptr, nullptr, 0);
+  } else {
+    dim3 grid(unsigned((Q + NN_THREADS - 1) / NN_THREADS), unsigned(chunks));
+    k_nn_qt<false><<<grid, NN_THREADS, 0, st>>>(ptrs_of(t), t.n, chunk_len, d_queries, Q, sc.part_d, sc.part_id,
+                                                nullptr, 0.0, nullptr, nullptr, 0);
+  }
+  k_nn_merge<<<unsigned((Q + 255) / 256), 256, 0, st>>>(sc.part_d, sc.part_id, chunks, Q, d_id);
+  if (n_launch) *n_launch += 2;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_nn_radius(const TreeDev &t, const double *d_queries, const int32_t *d_exclude, int64_t Q,
+                             double s_thr, int k, int32_t *d_low, int32_t *d_high, int32_t *d_count,
+                             int32_t *d_overflow, NNScratch &sc, int chunks_hint, int variant, cudaStream_t st,
+                             int *n_launch) {
+  if (Q <= 0) return cudaSuccess;
+  int chunks;
+  int64_t chunk_len;
+  pick_chunks(t.n, Q, variant, chunks_hint, chunks, chunk_len);
+  cudaError_t e = cudaMemsetAsync(d_count, 0, size_t(Q) * sizeof(int32_t), st);
+  if (e != cudaSuccess) return e;
+  if (variant == 2) {
+    dim3 grid(unsigned(Q), unsigned((chunks + NN_THREADS / 32 - 1) / (NN_THREADS / 32)));
+    k_nn_wq<true><<<grid, NN_THREADS, 0, st>>>(ptrs_of(t), t.n, chunk_len, chunks, d_queries, Q, nullptr, nullptr,
+                                               d_exclude, s_thr, d_count, sc.hits, sc.hit_cap);
+  } else {
+    dim3 grid(unsigned((Q + NN_THREADS - 1) / NN_THREADS), unsigned(chunks));
+    k_nn_qt<true><<<grid, NN_THREADS, 0, st>>>(ptrs_of(t), t.n, chunk_len, d_queries, Q, nullptr, nullptr, d_exclude,
+                                               s_thr, d_count, sc.hits, sc.hit_cap);
+  }
+  k_nn_topk<<<unsigned((Q + NN_THREADS / 32 - 1) / (NN_THREADS / 32)), NN_THREADS, 0, st>>>(
+      t.cost, sc.hits, sc.hit_cap, d_count, Q, k, d_low, d_high, d_overflow);
+  if (n_launch) *n_launch += 2;
+  return cudaGetLastError();
+}
+
+}  // namespace sqmp

@@ -1,0 +1,98 @@
+// sqmp_common.cuh — device-side descriptors shared by the kernels of libsqmp_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sqmp_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libsqmp_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace sqmp {
+
+// axis codes: the joint axes of the reference robot are all signed unit axes (URDF:30-66, 615-759);
+// a general axis takes the Rodrigues path.
+__host__ __device__ __forceinline__ int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
+
+enum AxisCode : int { AX_GENERAL = 0, AX_PX = 1, AX_NX = 2, AX_PY = 3, AX_NY = 4, AX_PZ = 5, AX_NZ = 6 };
+
+// Chain + sphere table, passed by value as a __grid_constant__ kernel parameter: every access is
+// warp-uniform, so it is served from the constant bank / uniform datapath and never touches the LSU.
+struct RobotDev {
+  int n_seg;
+  int n_spheres;
+  int ref_seg;                            // last segment of the leading prismatic run (base position)
+  int self_const_collision;
+  int seg_type[SQMP_MAX_SEG];
+  int seg_qidx[SQMP_MAX_SEG];
+  int seg_axis_code[SQMP_MAX_SEG];
+  int seg_pre_kind[SQMP_MAX_SEG];         // 0 identity, 1 translation only, 2 general
+  int seg_sph_end[SQMP_MAX_SEG + 2];      // spheres of segment s (-1 = root) are [end[s+1-1], end[s+1])
+  double seg_pre[SQMP_MAX_SEG][12];
+  double seg_axis[SQMP_MAX_SEG][3];
+  double root_off[3];
+  double ee_tip[12];
+  int ee_tip_kind;
+  double sph[SQMP_MAX_SPHERES][4];        // cx cy cz r in the segment frame
+  // per-grid derived values (recomputed by sqmp_set_voxel_grid)
+  unsigned char sph_thr8[SQMP_MAX_SPHERES];   // distance-field filter threshold, units of res/4
+  unsigned char sph_ncell[SQMP_MAX_SPHERES];  // ceil(r / res)
+  // per-request (sqmp_set_disabled_links)
+  uint32_t sph_enabled[SQMP_MAX_SPHERES / 32];
+};
+
+struct GridDev {
+  const uint32_t *occ;   // bit-packed rows along x, row_words words per (j,k) row (>= 1 zero pad word)
+  const uint8_t *edt;    // [gz][gy][gx]: floor(4 * box-to-box distance to the nearest occupied voxel / res), <= 255
+  int gx, gy, gz, row_words;
+  int has_grid;
+  double ox, oy, oz, res, inv_res;
+};
+
+struct SelfPair {   // 8 bytes
+  unsigned char a, b, pad0, pad1;
+  float rsum2;      // (ra + rb)^2
+};
+
+// ---- launch helpers (defined in the .cu files) ---------------------------------------------------------
+struct Ctx;
+
+cudaError_t launch_check_states(const RobotDev &rb, const GridDev &gd, const SelfPair *pairs, int n_pairs,
+                                const double *d_q, const double *d_q_end, int num_points, int64_t S,
+                                unsigned flags, uint32_t *d_mask, int fk_precision, cudaStream_t st, int *n_launch);
+cudaError_t launch_first_invalid(const uint32_t *d_mask, int64_t E, int P1, int32_t *d_first, cudaStream_t st);
+cudaError_t launch_get_collisions(const RobotDev &rb, const GridDev &gd, const SelfPair *pairs, int n_pairs,
+                                  const double *d_q, uint8_t *d_sphere_hit, uint8_t *d_pair_hit, cudaStream_t st);
+cudaError_t launch_fk(const RobotDev &rb, const double *d_q, int64_t S, double *d_out, int fk_precision,
+                      cudaStream_t st);
+cudaError_t launch_edt_build(const uint32_t *d_occ, int row_words, int gx, int gy, int gz, int window,
+                             uint8_t *d_tmp_a, uint16_t *d_tmp_b, uint8_t *d_edt, cudaStream_t st, int *n_launch);
+cudaError_t launch_pack_rows(const uint32_t *d_bits_linear, int gx, int gy, int gz, int row_words, uint32_t *d_occ,
+                             cudaStream_t st);
+
+struct TreeDev {
+  double *q[SQMP_DOF];   // SoA: q[d][n]
+  double *cost;
+  int64_t n, cap;
+};
+cudaError_t launch_tree_append(TreeDev &t, const double *d_q_rows, const double *d_cost, int64_t first, int64_t n,
+                               cudaStream_t st);
+cudaError_t launch_tree_set_one(TreeDev &t, int64_t id, const double q[SQMP_DOF], double cost, cudaStream_t st);
+cudaError_t launch_tree_update_costs(TreeDev &t, const int32_t *d_ids, const double *d_cost, int64_t n,
+                                     cudaStream_t st);
+
+struct NNScratch {
+  double *part_d;      // [chunks][Q]
+  int32_t *part_id;    // [chunks][Q]
+  int32_t *hits;       // [Q][hit_cap]
+  int64_t hit_cap;
+};
+cudaError_t launch_nn_nearest(const TreeDev &t, const double *d_queries, int64_t Q, int32_t *d_id, NNScratch &sc,
+                              int chunks, int variant, cudaStream_t st, int *n_launch);
+cudaError_t launch_nn_radius(const TreeDev &t, const double *d_queries, const int32_t *d_exclude, int64_t Q,
+                             double s_thr, int k, int32_t *d_low, int32_t *d_high, int32_t *d_count,
+                             int32_t *d_overflow, NNScratch &sc, int chunks, int variant, cudaStream_t st,
+                             int *n_launch);
+
+}  // namespace sqmp
