@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the state-validity hot path (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload config2|config4]
+
+One "step" = one pass of the fused FK + collision kernel (K1) over one batch of 2^20 interpolated 8-DOF
+states against the resident 256^3 voxel world W256, map check on.  With N > 1 (torchrun,
+one rank per GPU) every rank checks its own 2^20-state shard, writes its mask straight into its slot of the
+gathered buffer, and one NCCL all-gather completes the step (weak scaling).  `--workload config4` runs the
+2^26-state batch of configs[3] sharded over the ranks instead (strong scaling).
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port (the reference itself cannot be
+built here: ROS/KDL/FCL/octomap are absent — DESIGN.md) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+S_CONFIG2 = 1 << 20
+S_CONFIG4 = 1 << 26
+BYTES_PER_STATE = 64.125          # 8 x f64 in + 1 bit out
+METRIC = "collision-checked 8-DOF configs/sec"
+UNIT = "configs/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed regions run."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag, self.ok = index, [], False, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.max_sm = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((sm, util, int(reasons)))
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": ["nvml unavailable"]}
+        nv = self.nv
+        loaded = [s for s in self.samples if s[1] > 0] or self.samples
+        sm = sorted(s[0] for s in loaded)[len(loaded) // 2]
+        bits = 0
+        for s in loaded:
+            bits |= s[2]
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        return {"sm_mhz": sm, "sm_max_mhz": self.max_sm, "reasons": [k for k, v in names.items() if bits & v],
+                "samples": len(loaded)}
+
+
+def build_inputs(n_states, seed):
+    from squirrel_motion_planner_b200 import synthetic as syn
+    return syn.state_batch(n_states, seed=seed)
+
+
+def make_world():
+    from squirrel_motion_planner_b200 import robot_desc as rd, synthetic as syn
+    w = syn.box_world(g=256, n_boxes=64, seed=1234)
+    origin = w.origin + np.array([0.0, 0.0, rd.OCTREE_Z_OFFSET])   # CC:87
+    return w, origin
+
+
+def cpu_baseline_sample(n_threads, target_s=12.0):
+    """Oracle port of the reference checker (early-exit path) on a bounded sample of the same workload."""
+    import oracle
+    from squirrel_motion_planner_b200 import robot_desc as rd
+    lt, fx = rd.load_fixture()
+    spheres = [(n, tuple(c), r) for n, c, r in fx["spheres"]]
+    orc = oracle.Oracle(lt, spheres)
+    w, origin = make_world()
+    orc.set_grid(w.bits, w.dims, origin, w.res)
+    q_all = build_inputs(S_CONFIG2, 42)
+    n, dt = 21 * 2000, 0.0
+    while True:                                   # grow the sample until it is worth target_s of CPU work
+        q = q_all[:n]
+        t0 = time.perf_counter()
+        orc.check_states(q, oracle.FLAG_MAP, nthreads=n_threads)
+        dt = time.perf_counter() - t0
+        if dt >= 0.5 * target_s or n >= S_CONFIG2:
+            break
+        n = int(min(S_CONFIG2, max(2 * n, n * target_s / max(dt, 1e-3))))
+    if dt < 0.5 * target_s:                       # the whole batch is too quick: repeat it
+        reps = int(max(1, target_s / max(dt, 1e-3)))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            orc.check_states(q, oracle.FLAG_MAP, nthreads=n_threads)
+        dt = (time.perf_counter() - t0) / reps
+    return orc, n / dt, n, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    threads = max(1, min(oracle.max_threads(), os.cpu_count() or 1))
+    orc, rate, n_probe, _ = cpu_baseline_sample(threads, target_s=3.0)
+    budget_s = 150.0 / max(1, args.steps + args.warmup)
+    n = int(min(S_CONFIG2, max(2100, rate * min(budget_s, 8.0))))
+    q = build_inputs(S_CONFIG2, 42)[:n]
+    for _ in range(args.warmup):
+        orc.check_states(q, oracle.FLAG_MAP, nthreads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.check_states(q, oracle.FLAG_MAP, nthreads=threads)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    sample = "first %d of the 2^20 config-2 states per step (W256, map check), oracle early-exit path" % n
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "config2: 2^20 interpolated 8-DOF states vs W256 (256^3 voxels, res 0.05), map check",
+                   "note": "CPU oracle port of CollisionChecker::isInCollision on host cores; the reference itself "
+                           "needs ROS/KDL/FCL/octomap, absent here"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_own(args):
+    import torch
+    import torch.distributed as dist
+    from squirrel_motion_planner_b200 import api, synthetic as syn
+
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world_size > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    ctx = api.default_context(local_rank)      # raises if libsqmp_b200.so or the GPU is missing
+    w, origin = make_world()
+    ctx.set_voxel_grid(w.bits, w.dims, origin, w.res)
+
+    if args.workload == "config4":
+        total = S_CONFIG4
+        s_rank = total // world_size
+        scaling = "strong"
+        n_rot = 1                                  # 2^26/8 states x 64 B = 512 MiB per rank > 126 MiB L2
+        batches = [syn.state_batch(total, seed=42)[rank * s_rank:(rank + 1) * s_rank]] if world_size == 1 else \
+            [syn.state_batch(s_rank, seed=42 + rank)]
+        wl = "config4: 2^26 interpolated states sharded over %d GPU(s), W256, map check, NCCL mask all-gather" % world_size
+    else:
+        s_rank = S_CONFIG2
+        scaling = "weak"
+        n_rot = 4                                  # 4 x 64 MiB distinct batches = 256 MiB > 126 MiB L2
+        batches = [build_inputs(s_rank, 42 + 7919 * (rank * n_rot + i)) for i in range(n_rot)]
+        wl = "config2: 2^20 interpolated 8-DOF states per GPU vs W256 (256^3 voxels, res 0.05), map check"
+    d_q = [torch.from_numpy(b).to(dev) for b in batches]
+    words = (s_rank + 31) // 32
+    d_all = torch.zeros(world_size * words, dtype=torch.int32, device=dev)   # gathered mask, every rank
+    d_mine = d_all[rank * words:(rank + 1) * words]                          # kernel writes straight into its slot
+    flags = api.CHECK_MAP
+
+    def step(i):
+        ctx.check_states_dev(d_q[i % n_rot], s_rank, flags, d_mine, stream)
+        if world_size > 1:
+            dist.all_gather_into_tensor(d_all, d_mine)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    torch.cuda.synchronize()
+    if world_size > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    l0 = ctx.kernel_launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start.record()
+    for i in range(args.steps):
+        ev[i][0].record()
+        ctx.check_states_dev(d_q[i % n_rot], s_rank, flags, d_mine, stream)
+        ev[i][1].record()
+        if world_size > 1:
+            dist.all_gather_into_tensor(d_all, d_mine)
+    e_stop.record()
+    torch.cuda.synchronize()
+    if world_size > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    launches = ctx.kernel_launches - l0
+    total_ms = e_start.elapsed_time(e_stop)
+    kern_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    if world_size > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = s_rank * world_size * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: the host-buffer C-ABI call (pinned host memory in, mask back on the host), same workload ----
+    h_q = torch.from_numpy(batches[0]).pin_memory()
+    h_mask = torch.zeros(words, dtype=torch.int32).pin_memory()
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(2):
+        ctx.check_states(h_q, flags, out=h_mask)
+    torch.cuda.synchronize()
+    if world_size > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.check_states(h_q, flags, out=h_mask)      # synchronous: H2D + K1 + D2H inside
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world_size > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = s_rank * world_size * e2e_steps / e2e_s
+    n_colliding = int(np.unpackbits(h_mask.numpy().view(np.uint8)).sum())
+
+    extra = {}
+    if rank == 0 and not args.no_extra:
+        extra = side_metrics(ctx, torch, dev, stream, d_q[0], s_rank)
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        achieved = s_rank * BYTES_PER_STATE / (kern_ms * 1e-3) / 1e9
+        cpu = None
+        if world_size == 1 and not args.no_cpu:
+            import oracle
+            threads = max(1, min(oracle.max_threads(), os.cpu_count() or 1))
+            _, rate, n, dt = cpu_baseline_sample(threads, target_s=12.0)
+            cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": "first %d of the 2^20 config-2 states, W256, map check, oracle early-exit path, %.1f s" % (n, dt)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl, "states_per_gpu": s_rank, "flags": "MAP",
+                       "l2": "inputs rotate over %d distinct batches (%d MiB > 126 MiB L2); the 18 MiB grid + distance "
+                             "field stay resident by design" % (n_rot, n_rot * s_rank * 64 >> 20),
+                       "colliding_fraction": n_colliding / s_rank, "entry": "sqmp_check_states_dev"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "k1_check_states<double,false,0>",
+                         "kernel_ms": kern_ms, "bytes_per_state": BYTES_PER_STATE},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": s_rank * 64, "d2h_bytes_per_step": words * 4,
+                    "entry": "sqmp_check_states (pinned host buffers)", "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "extra": extra,
+        }
+        traffic_file = os.path.join(ROOT, "profiles", "k1_traffic.json")
+        if os.path.exists(traffic_file):
+            with open(traffic_file) as f:
+                line["roofline"]["traffic"] = json.load(f).get("dram_bytes_per_launch")
+        print(json.dumps(line))
+    ctx.close()
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+def side_metrics(ctx, torch, dev, stream, d_q, S):
+    """Secondary numbers of the same run (not the headline): FK-only, self-collision, edges entry, NN."""
+    from squirrel_motion_planner_b200 import api, synthetic as syn
+    peak, _ = measured_peaks()
+
+    def t_ms(fn, n=5, warm=2):
+        for _ in range(warm):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    out = {}
+    d_mask = torch.zeros((S + 31) // 32, dtype=torch.int32, device=dev)
+    d_pose = torch.empty((S, 7), dtype=torch.float64, device=dev)
+    ms = t_ms(lambda: ctx.fk_dev(d_q, S, d_pose, stream))
+    out["fk_states_per_s"] = S / ms * 1e3
+    out["fk_hbm_frac"] = S * 120 / (ms * 1e-3) / 1e9 / peak
+    ms = t_ms(lambda: ctx.check_states_dev(d_q, S, api.CHECK_MAP | api.CHECK_SELF, d_mask, stream))
+    out["map_plus_self_states_per_s"] = S / ms * 1e3
+    E = S // 21
+    a, b = syn.edge_batch(E, 42)
+    da, db = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
+    d_first = torch.empty(E, dtype=torch.int32, device=dev)
+    ms = t_ms(lambda: ctx.check_edges_dev(da, db, E, 20, api.CHECK_MAP, d_mask, d_first, stream))
+    out["edges_entry_states_per_s"] = E * 21 / ms * 1e3
+    N, Q = 1 << 20, 1 << 16
+    nodes, cost = syn.random_tree(N, 7, 9)
+    ctx.tree_reset(0)
+    ctx.tree_append_batch(0, nodes, cost)
+    d_qs = torch.from_numpy(syn.sample_configs(Q, 8)).to(dev)
+    d_ids = torch.empty(Q, dtype=torch.int32, device=dev)
+    ms = t_ms(lambda: ctx.nn_nearest_dev(0, d_qs, Q, d_ids, stream), n=2, warm=1)
+    out["nn_nearest_queries_per_s"] = Q / ms * 1e3
+    out["nn_nearest_pairs_per_s"] = N * Q / ms * 1e3
+    out["nn_nearest_hbm_frac"] = (N * 64 + Q * 68) / (ms * 1e-3) / 1e9 / peak
+    d_low = torch.empty((Q, 20), dtype=torch.int32, device=dev)
+    d_high = torch.empty_like(d_low)
+    d_cnt = torch.empty(Q, dtype=torch.int32, device=dev)
+    d_ov = torch.zeros(1, dtype=torch.int32, device=dev)
+    ms = t_ms(lambda: ctx.nn_radius_dev(0, d_qs, None, Q, 1.5, 20, d_low, d_high, d_cnt, d_ov, stream), n=2, warm=1)
+    out["nn_radius_queries_per_s"] = Q / ms * 1e3
+    out["nn_config"] = "N=2^20 nodes, Q=2^16 queries, r=1.5, k=20"
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--workload", default="config2", choices=["config2", "config4"])
+    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -72,9 +72,10 @@ class CollisionChecker:
         cr = self.ctx.compiled
         pairs = []
         for p in np.nonzero(ph)[0]:
-            a, b = names[cr.sph_link[cr.pair_a[p]]], names[cr.sph_link[cr.pair_b[p]]]
-            if (a, b) not in pairs:
-                pairs.append((a, b))
+            la, lb = sorted((int(cr.sph_link[cr.pair_a[p]]), int(cr.sph_link[cr.pair_b[p]])))   # CC:387-390: i < j
+            if (la, lb) not in pairs:
+                pairs.append((la, lb))
+        pairs = [(names[a], names[b]) for a, b in sorted(pairs)]
         return pairs, sorted(names[i] for i in np.nonzero(lm[:len(names)])[0])   # std::map order (CC:614)
 
 

@@ -1,0 +1,351 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle and the committed goldens.
+
+Bars (BASELINE.json north_star): near-neighbour indices bit-exact (ties -> lowest id); collision verdicts identical
+except for states whose minimum clearance is within 1e-5 m of contact; FK within 1e-5 m / 1e-5 rad.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN, unpack
+from squirrel_motion_planner_b200 import api, planner_shim, robot_desc as rd, synthetic as syn
+
+pytestmark = pytest.mark.gpu
+BAND = 1e-5          # metres — the north star's clearance band
+FK_TOL = 1e-5        # metres / radians
+
+
+def _verdict_parity(ctx, orc, q, flags, band=BAND):
+    got = unpack(ctx.check_states(q, flags), len(q))
+    ref_mask, cm, cs = orc.check_states(q, flags, clearance=True, nthreads=8)
+    ref = unpack(ref_mask, len(q))
+    clr = np.minimum(cm, cs)
+    differs = got != ref
+    assert not np.any(differs & (np.abs(clr) > band)), \
+        "verdicts differ outside the band: %d states, |clearance| up to %g" % (differs.sum(), np.abs(clr[differs]).max())
+    return got, ref, clr, differs
+
+
+@pytest.fixture()
+def world_ctx(ctx, orc, small_world):
+    w, origin = small_world
+    ctx.set_disabled_links(0)
+    orc.set_disabled_links(0)
+    ctx.set_voxel_grid(w.bits, w.dims, origin, w.res)
+    orc.set_grid(w.bits, w.dims, origin, w.res)
+    return ctx, orc, w, origin
+
+
+# --------------------------------------------------------------------------------------- state validity
+@pytest.mark.parametrize("prec", [64, 32])
+@pytest.mark.parametrize("flags", [api.CHECK_MAP, api.CHECK_SELF, api.CHECK_MAP | api.CHECK_SELF])
+def test_check_states_matches_oracle(world_ctx, prec, flags):
+    ctx, orc, w, origin = world_ctx
+    ctx.set_option("fk_precision", prec)
+    try:
+        q = syn.state_batch(21 * 600 + 5, seed=17, xy_half=2.2)       # ragged: not a multiple of 32 or 128
+        got, ref, clr, differs = _verdict_parity(ctx, orc, q, flags)
+        assert 0.05 < got.mean() < 0.95
+        if prec == 64:
+            assert differs.sum() == 0                                 # fp64 chain: no disagreement at all here
+    finally:
+        ctx.set_option("fk_precision", 64)
+
+
+def test_check_states_golden_numpy_world(ctx, orc):
+    g = np.load(os.path.join(GOLDEN, "collision_numpy.npz"))
+    ctx.set_voxel_grid(g["bits"], g["dims"], g["origin"], float(g["res"]))
+    got = unpack(ctx.check_states(g["q"], api.CHECK_MAP), len(g["q"]))
+    want = g["clearance"] <= 0.0
+    assert not np.any((got != want) & (np.abs(g["clearance"]) > BAND))
+    for s in range(0, len(g["q"]), 8):                                # getCollisions (CC:123-133)
+        lm, _ = ctx.get_collisions(g["q"][s])
+        assert np.array_equal(lm[:g["per_link"].shape[1]], g["per_link"][s])
+
+
+def test_edge_cases_empty_flags_nogrid(fixture_data, small_world):
+    lt, fx, spheres = fixture_data
+    c2 = api.Context(rd.compile_robot(lt, spheres), 0)
+    try:
+        q = syn.state_batch(100, seed=3)
+        assert not unpack(c2.check_states(q, api.CHECK_MAP), 100).any()          # CC:556-557: no octomap yet
+        assert not unpack(c2.check_states(q, 0), 100).any()                        # CC:109-110
+        assert c2.check_states(np.zeros((0, 8)), api.CHECK_MAP).size == 0           # empty batch
+        w, origin = small_world
+        c2.set_voxel_grid(w.bits, w.dims, origin, w.res)
+        one = c2.check_states(q[:1], api.CHECK_MAP)
+        assert one.size == 1
+        # far outside the grid: unknown space is free
+        far = q.copy(); far[:, 0] += 500.0
+        assert not unpack(c2.check_states(far, api.CHECK_MAP), 100).any()
+        with pytest.raises(api.SqmpError):
+            c2.set_voxel_grid(w.bits, (0, 4, 4), origin, w.res)
+    finally:
+        c2.close()
+
+
+def test_disabled_links_mask(world_ctx, fixture_data):
+    ctx, orc, w, origin = world_ctx
+    lt = fixture_data[0]
+    q = syn.state_batch(21 * 200, seed=23, xy_half=2.2)
+    names = ["base_body_link", "shell_base_link_front", "hand_wrist_link", "head_link"]
+    mask = rd.link_mask(lt, names)
+    try:
+        ctx.set_disabled_links(mask)
+        orc.set_disabled_links(mask)
+        got, ref, _, differs = _verdict_parity(ctx, orc, q, api.CHECK_MAP)
+        assert differs.sum() == 0
+        ctx.set_disabled_links(0)
+        full = unpack(ctx.check_states(q, api.CHECK_MAP), len(q))
+        assert full.sum() > got.sum()                                  # disabling links can only free states
+        ctx.set_disabled_links((1 << 64) - 1)
+        assert not unpack(ctx.check_states(q, api.CHECK_MAP), len(q)).any()
+    finally:
+        ctx.set_disabled_links(0)
+        orc.set_disabled_links(0)
+
+
+def test_grid_partially_covering_the_robot(ctx, orc):
+    """Spheres straddling the grid border and grids whose x size is not a multiple of 32."""
+    w = syn.box_world(g=40, n_boxes=10, seed=8, dims=(37, 45, 21), z_low=-0.2)
+    origin = w.origin + np.array([0.3, -0.2, rd.OCTREE_Z_OFFSET])
+    ctx.set_voxel_grid(w.bits, w.dims, origin, w.res)
+    orc.set_grid(w.bits, w.dims, origin, w.res)
+    q = syn.state_batch(21 * 300, seed=29, xy_half=1.6)
+    got, ref, _, differs = _verdict_parity(ctx, orc, q, api.CHECK_MAP)
+    assert differs.sum() == 0 and 0.02 < got.mean() < 0.98
+
+
+def test_check_edges_matches_oracle_and_states_entry(world_ctx):
+    ctx, orc, w, origin = world_ctx
+    a, b = syn.edge_batch(777, seed=31, xy_half=2.2)
+    mask, first = ctx.check_edges(a, b, 20, api.CHECK_MAP)
+    ref_mask, ref_first = orc.check_edges(a, b, 20, oracle.FLAG_MAP, nthreads=8)
+    assert np.array_equal(mask, ref_mask) and np.array_equal(first, ref_first)
+    # device-side interpolation == host-side interpolation (BS:4461-4478), state for state
+    states = syn.interpolate_edges(a, b, 20)
+    assert np.array_equal(ctx.check_states(states, api.CHECK_MAP), mask)
+    assert (first == -1).any() and (first == 0).any() and (first > 1).any()
+    m5, f5 = ctx.check_edges(a[:50], b[:50], 7, api.CHECK_MAP | api.CHECK_SELF)
+    r5, rf5 = orc.check_edges(a[:50], b[:50], 7, oracle.FLAG_MAP | oracle.FLAG_SELF)
+    assert np.array_equal(m5, r5) and np.array_equal(f5, rf5)
+
+
+def test_shim_collision_checker_and_edge_validity(fixture_data, small_world, orc):
+    w, origin = small_world
+    cc = planner_shim.CollisionChecker(0)
+    assert cc.initialized
+    cc.setOcTree(None)                                                # CC:78-79
+    cc.setOcTree(w)                                                   # applies the -0.02 offset itself
+    orc.set_grid(w.bits, w.dims, origin, w.res)
+    hp = planner_shim.BiRRTstarHotPath(cc)
+    q = syn.state_batch(21 * 40, seed=37, xy_half=2.2)
+    for s in range(0, len(q), 17):
+        for cs_, cm_ in ((True, True), (False, True), (True, False), (False, False)):
+            assert cc.isInCollision(q[s], cs_, cm_) == orc.is_in_collision(q[s], cs_, cm_)
+            assert hp.isConfigValid(q[s], cs_, cm_) == (not orc.is_in_collision(q[s], cs_, cm_))
+    for e in range(40):
+        traj = q[e * 21:(e + 1) * 21]
+        assert hp.isEdgeValid(planner_shim.Edge(traj), False, True) == orc.is_edge_valid(traj, False, True)
+        assert hp.isEdgeValid(planner_shim.Edge(traj), True, True) == orc.is_edge_valid(traj, True, True)
+    pairs, links = cc.getCollisions(q[3])
+    lm, ph = orc.get_collisions(q[3])
+    lt = fixture_data[0]
+    assert links == sorted(lt.names[i] for i in np.nonzero(lm)[0])
+    want_pairs = set((lt.names[i], lt.names[j]) for i, j in zip(*np.nonzero(ph)))
+    # the kernel reports cross-group pairs; same-group pairs are constant and none collides in this model
+    assert set(pairs) == want_pairs
+    cc.setDisabledLinkMapCollisions(["base_body_link"])
+    orc.set_disabled_links(rd.link_mask(lt, ["base_body_link"]))
+    assert cc.isInCollision(q[3], False, True) == orc.is_in_collision(q[3], False, True)
+    orc.set_disabled_links(0)
+
+
+# --------------------------------------------------------------------------------------- FK
+def _fk_err(a, b):
+    pos = np.abs(a[:, :3] - b[:, :3]).max()
+    # rotation angle between the two orientations: 2*asin(|dq|/2) ~ |dq| * 2 for unit quaternions aligned in sign
+    # (2*acos(dot) is ill-conditioned near 1 and would report sqrt(eps) for identical rotations)
+    sgn = np.sign((a[:, 3:] * b[:, 3:]).sum(1))[:, None]
+    ang = (2.0 * np.arcsin(np.clip(np.linalg.norm(a[:, 3:] - sgn * b[:, 3:], axis=1) / 2.0, 0, 1))).max()
+    return pos, ang
+
+
+@pytest.mark.parametrize("prec", [64, 32])
+def test_fk_matches_oracle_and_golden(ctx, orc, prec):
+    ctx.set_option("fk_precision", prec)
+    try:
+        g = np.load(os.path.join(GOLDEN, "fk_scipy.npz"))
+        got = ctx.fk(g["q"])
+        pos, ang = _fk_err(got, g["ee"])
+        assert pos < FK_TOL and ang < FK_TOL
+        for n in (1, 127, 128, 129, 1000, 4097):                       # ragged tiles around the 128-state CTA tile
+            q = syn.sample_configs(n, seed=41 + n, xy_half=12.0)
+            got, ref = ctx.fk(q), orc.fk(q)
+            pos, ang = _fk_err(got, ref)
+            assert pos < FK_TOL and ang < FK_TOL, (n, pos, ang)
+            if prec == 64:
+                assert np.abs(got - ref).max() < 1e-12               # same quaternion sign convention too
+    finally:
+        ctx.set_option("fk_precision", 64)
+
+
+# --------------------------------------------------------------------------------------- near neighbours
+@pytest.mark.parametrize("variant", [1, 2])
+def test_nearest_bit_exact(ctx, variant):
+    ctx.set_option("nn_variant", variant)
+    try:
+        g = np.load(os.path.join(GOLDEN, "nn_numpy.npz"))
+        ctx.tree_reset(0)
+        assert ctx.tree_append_batch(0, g["nodes"], g["cost"]) == 0
+        assert np.array_equal(ctx.nn_nearest(0, g["queries"]), g["nearest"])
+        for N, Q, seed in ((1, 5, 1), (31, 40, 2), (257, 129, 3), (20011, 300, 4)):
+            nodes, cost = syn.random_tree(N, seed=seed, cost_seed=seed + 1)
+            if N > 100:
+                nodes[N // 2] = nodes[7]; nodes[N - 1] = nodes[7]      # duplicates -> ties
+            queries = syn.sample_configs(Q, seed=seed + 2)
+            queries[0] = nodes[min(7, N - 1)]
+            ctx.tree_reset(1)
+            ctx.tree_append_batch(1, nodes, cost)
+            assert np.array_equal(ctx.nn_nearest(1, queries), oracle.nearest(nodes, queries, nthreads=8)), (N, Q)
+    finally:
+        ctx.set_option("nn_variant", 0)
+
+
+def test_nearest_quirks_and_tree_mutation(ctx):
+    ctx.tree_reset(2)
+    assert ctx.nn_nearest(2, np.zeros((3, 8))).tolist() == [0, 0, 0]   # empty tree: id stays 0 (BS:4084)
+    far = np.full((5, 8), 1e6)
+    ctx.tree_append_batch(2, far, np.zeros(5))
+    assert ctx.nn_nearest(2, np.zeros((1, 8)))[0] == 0                  # nothing below 10000.0 (BS:4090)
+    nid = ctx.tree_append(2, np.full(8, 2.0), 1.0)
+    assert nid == 5 and ctx.tree_size(2) == 6
+    assert ctx.nn_nearest(2, np.zeros((1, 8)))[0] == 5
+    ctx.tree_update(2, 1, np.full(8, 1.0), 2.0)                         # rewire moves a node (BS:5173-5193)
+    assert ctx.nn_nearest(2, np.zeros((1, 8)))[0] == 1
+    for i in range(300):                                                # growth past the initial capacity
+        ctx.tree_append(2, np.full(8, 50.0 + i), float(i))
+    assert ctx.tree_size(2) == 306 and ctx.nn_nearest(2, np.full((1, 8), 60.2))[0] == 16
+    ctx.tree_reset(2)
+    assert ctx.tree_size(2) == 0
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_radius_topk_bit_exact(ctx, variant):
+    ctx.set_option("nn_variant", variant)
+    try:
+        g = np.load(os.path.join(GOLDEN, "nn_numpy.npz"))
+        ctx.tree_reset(0)
+        ctx.tree_append_batch(0, g["nodes"], g["cost"])
+        low, high, cnt = ctx.nn_radius(0, g["queries"], None, 1.5, 20)
+        assert np.array_equal(cnt, g["near_count"])
+        off = 0
+        for k in range(len(g["queries"])):
+            n = int(cnt[k]); want = g["near_flat"][off:off + n]; off += n
+            assert np.array_equal(low[k][low[k] >= 0], want[:20])
+            assert np.array_equal(high[k][high[k] >= 0], want[::-1][:20])
+        for N, Q, r, k, seed in ((500, 33, 3.0, 20, 11), (20011, 200, 2.2, 20, 12), (3000, 64, 50.0, 7, 13)):
+            nodes, cost = syn.random_tree(N, seed=seed, cost_seed=seed + 1)
+            cost[::7] = cost[3]                                        # equal costs -> id tie-break
+            queries = syn.sample_configs(Q, seed=seed + 2)
+            excl = np.random.default_rng(seed).integers(-1, N, size=Q).astype(np.int32)
+            ctx.tree_reset(1)
+            ctx.tree_append_batch(1, nodes, cost)
+            got = ctx.nn_radius(1, queries, excl, r, k)
+            want = oracle.near_topk(nodes, cost, queries, excl, r, k, nthreads=8)
+            for a, b, name in zip(got, want, ("low", "high", "count")):
+                assert np.array_equal(a, b), (N, Q, r, name)
+            # cost updates (recursiveNodeCostUpdate, BS:5518-5520)
+            ids = np.arange(0, N, 5, dtype=np.int32)
+            cost[ids] = cost[ids] * 0.5 + 1.0
+            ctx.tree_update_costs(1, ids, cost[ids])
+            got = ctx.nn_radius(1, queries, excl, r, k)
+            want = oracle.near_topk(nodes, cost, queries, excl, r, k, nthreads=8)
+            for a, b in zip(got, want):
+                assert np.array_equal(a, b)
+    finally:
+        ctx.set_option("nn_variant", 0)
+
+
+def test_radius_overflow_retry_is_exact(ctx):
+    """A hit pool far too small for the batch: the host entry point halves the batch until it fits."""
+    nodes, cost = syn.random_tree(4000, seed=21, cost_seed=22)
+    queries = syn.sample_configs(200, seed=23)
+    ctx.tree_reset(1)
+    ctx.tree_append_batch(1, nodes, cost)
+    ctx.set_option("nn_hit_pool_bytes", 200 * 32 * 4)                  # 32 slots per query, most need far more
+    try:
+        got = ctx.nn_radius(1, queries, None, 100.0, 20)
+        want = oracle.near_topk(nodes, cost, queries, None, 100.0, 20, nthreads=8)
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b)
+        assert got[2].min() == 4000
+    finally:
+        ctx.set_option("nn_hit_pool_bytes", 1 << 30)
+
+
+def test_shim_nearest_and_near_vertices(fixture_data):
+    cc = planner_shim.CollisionChecker(0)
+    hp = planner_shim.BiRRTstarHotPath(cc)
+    tree = planner_shim.Rrt_star_tree("START", index=3)
+    hp.resetTree(tree)
+    nodes, cost = syn.random_tree(600, seed=51, cost_seed=52, xy_half=1.0)
+    for i in range(600):
+        assert hp.insertNode(tree, planner_shim.Node(config=nodes[i], cost_reach_total=cost[i])) == i
+    x = syn.sample_configs(1, seed=53, xy_half=1.0)[0]
+    assert hp.find_nearest_neighbour_interpolation(tree, x).node_id == oracle.nearest(nodes, x[None])[0]
+    x_new = tree.nodes[17]
+    lo, hi, n = hp.find_near_vertices_interpolation(tree, x_new)
+    want = oracle.near_vertices(nodes, cost, x_new.config, 17, 1.5)
+    assert n == len(want) and lo == list(want[:20]) and hi == list(want[::-1][:20]) and 17 not in lo
+
+
+# --------------------------------------------------------------------------------------- full-size properties
+def test_full_size_config2_properties(ctx, orc):
+    """2^20 states vs W256 (BASELINE.json configs[1]): entry points agree with each other, precisions agree outside
+    the band, and a seeded sample of the full batch agrees with the oracle."""
+    w = syn.box_world(g=256, n_boxes=64, seed=1234)
+    origin = w.origin + np.array([0, 0, rd.OCTREE_Z_OFFSET])
+    ctx.set_voxel_grid(w.bits, w.dims, origin, w.res)
+    orc.set_grid(w.bits, w.dims, origin, w.res)
+    S = 1 << 20
+    E = (S + 20) // 21
+    a, b = syn.edge_batch(E, seed=42)
+    q = np.ascontiguousarray(syn.interpolate_edges(a, b)[:S])
+    m_states = ctx.check_states(q, api.CHECK_MAP)
+    m_edges, first = ctx.check_edges(a, b, 20, api.CHECK_MAP)
+    assert np.array_equal(unpack(m_states, S), unpack(m_edges, S))            # idempotent across entry points
+    assert np.array_equal(ctx.check_states(q, api.CHECK_MAP), m_states)       # and across runs
+    bits = unpack(m_edges, E * 21).reshape(E, 21)
+    assert np.array_equal(first, np.where(bits.any(1), bits.argmax(1), -1))
+    ctx.set_option("fk_precision", 32)
+    m32 = ctx.check_states(q, api.CHECK_MAP)
+    ctx.set_option("fk_precision", 64)
+    idx = np.nonzero(unpack(m32, S) != unpack(m_states, S))[0]
+    if idx.size:
+        _, cm, _ = orc.check_states(q[idx], oracle.FLAG_MAP, clearance=True, nthreads=8)
+        assert np.abs(cm).max() <= BAND
+    sel = np.random.default_rng(0).choice(S, 40000, replace=False)
+    ref, cm, _ = orc.check_states(q[sel], oracle.FLAG_MAP, clearance=True, nthreads=8)
+    assert not np.any((unpack(ref, len(sel)) != unpack(m_states, S)[sel]) & (np.abs(cm) > BAND))
+
+
+def test_full_size_config3_properties(ctx):
+    """2^20-node tree (configs[2]): a seeded subset of queries against the oracle, bit-exact, both mappings."""
+    N = 1 << 20
+    nodes, cost = syn.random_tree(N, seed=7, cost_seed=9)
+    queries = syn.sample_configs(4096, seed=8)
+    ctx.tree_reset(0)
+    ctx.tree_append_batch(0, nodes, cost)
+    ids = ctx.nn_nearest(0, queries)                                          # QT mapping (Q >= 2048)
+    sub = np.arange(0, 4096, 64)
+    want = oracle.nearest(nodes, queries[sub], nthreads=8)
+    assert np.array_equal(ids[sub], want)
+    assert np.array_equal(ctx.nn_nearest(0, queries[sub]), want)              # WQ mapping (Q = 64)
+    low, high, cnt = ctx.nn_radius(0, queries, None, 1.5, 20)
+    wl, wh, wc = oracle.near_topk(nodes, cost, queries[sub], None, 1.5, 20, nthreads=8)
+    assert np.array_equal(cnt[sub], wc) and np.array_equal(low[sub], wl) and np.array_equal(high[sub], wh)
+    l2, h2, c2 = ctx.nn_radius(0, queries[sub], None, 1.5, 20)
+    assert np.array_equal(c2, wc) and np.array_equal(l2, wl) and np.array_equal(h2, wh)

@@ -1,0 +1,177 @@
+"""CPU: host-side logic — robot description folding, synthetic inputs, C-ABI exports, sharding over gloo."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, unpack
+from squirrel_motion_planner_b200 import api, robot_desc as rd, sharding, sphere_model, synthetic as syn
+
+
+def test_compile_robot_structure(fixture_data):
+    lt, fx, spheres = fixture_data
+    assert lt.n == 39 and int(lt.shaped.sum()) == 27 and len(lt.disabled_pairs) == 245   # URDF / SRDF:26-271
+    cr = rd.compile_robot(lt, spheres)
+    assert cr.n_seg == 8 and list(cr.seg_qidx) == list(range(8))
+    assert list(cr.seg_type) == [2, 2, 1, 1, 1, 1, 1, 1]
+    assert np.array_equal(cr.seg_axis[3], [0, -1, 0]) and np.array_equal(cr.seg_axis[4], [0, 1, 0])   # URDF:615-650
+    assert cr.root_offset[2] == 0.02 and cr.self_const_collision == 0
+    assert cr.n_spheres == len(spheres) <= api.MAX_SPHERES
+    assert np.all(np.diff(cr.sph_seg) >= 0)
+    assert set(lt.names[i] for i in cr.sph_link) == set(n for n, s in zip(lt.names, lt.shaped) if s)
+    assert np.all(cr.sph_seg[cr.pair_a] != cr.sph_seg[cr.pair_b])
+
+
+def test_compiled_chain_equals_link_walk(fixture_data, orc):
+    """The 8-segment folding reproduces the 39-link walk (CC:519-539) for every sphere centre."""
+    lt, fx, spheres = fixture_data
+    cr = rd.compile_robot(lt, spheres)
+    q = syn.sample_configs(20, seed=3)
+    for s in range(len(q)):
+        fr = orc.update_transforms(q[s])
+        T = rd.frame(p=cr.root_offset)
+        seg_T = {-1: T.copy()}
+        for k in range(cr.n_seg):
+            T = T @ rd.frame(cr.seg_pre[k][:9].reshape(3, 3), cr.seg_pre[k][9:])
+            v = q[s][cr.seg_qidx[k]]
+            if cr.seg_type[k] == rd.JOINT_TRANS:
+                T = T @ rd.frame(p=cr.seg_axis[k] * v)
+            else:
+                from scipy.spatial.transform import Rotation as Rot
+                T = T @ rd.frame(Rot.from_rotvec(cr.seg_axis[k] * v).as_matrix())
+            seg_T[k] = T.copy()
+        by_link = {}
+        for n, c, r in spheres:
+            by_link.setdefault(n, []).append(np.array(c))
+        want = []
+        for i in range(cr.n_spheres):
+            name = lt.names[cr.sph_link[i]]
+            F = fr[cr.sph_link[i]]
+            cands = [F[:9].reshape(3, 3) @ c + F[9:] for c in by_link[name]]
+            got = seg_T[int(cr.sph_seg[i])][:3, :3] @ cr.sph_center[i] + seg_T[int(cr.sph_seg[i])][:3, 3]
+            assert min(np.abs(got - c).max() for c in cands) < 1e-12
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference"), reason="reference tree only exists in the build container")
+def test_fixture_is_regenerable_from_reference(fixture_data):
+    lt = fixture_data[0]
+    cfg = "/root/reference/squirrel_8dof_planner/config/"
+    lt2 = rd.link_table_from_urdf(open(cfg + "robotino_plan.urdf").read(), open(cfg + "robotino_plan.srdf").read())
+    assert lt2.names == lt.names
+    assert np.array_equal(lt2.to_parent, lt.to_parent) and np.array_equal(lt2.parent, lt.parent)
+    assert [tuple(p) for p in lt2.disabled_pairs] == [tuple(p) for p in lt.disabled_pairs]
+    assert [(n, tuple(c), r) for n, c, r in sphere_model.spheres_for()] == fixture_data[2]
+
+
+def test_world_and_state_generators_are_seeded():
+    w1, w2 = syn.box_world(64, n_boxes=8, seed=1), syn.box_world(64, n_boxes=8, seed=1)
+    assert np.array_equal(w1.bits, w2.bits) and w1.bits.dtype == np.uint32
+    occ = w1.occupancy()
+    assert occ[:8].all() and not occ[-1].all()            # floor slab below z = 0
+    assert np.array_equal(syn.pack_occupancy(occ), w1.bits)
+    s = syn.state_batch(1000, seed=42)
+    assert s.shape == (1000, 8) and np.array_equal(s, syn.state_batch(1000, seed=42))
+    a, b = syn.edge_batch(48, seed=42)
+    assert np.array_equal(s[:21], syn.interpolate_edges(a[:1], b[:1]))
+    d_rev = np.sqrt(((b - a)[:, 2:] ** 2).sum(1))
+    d_pri = np.sqrt(((b - a)[:, :2] ** 2).sum(1))
+    assert np.all(d_rev < 0.6 + 1e-12) and np.all(d_pri < 0.6 + 1e-12)     # one extend step (BS:5778-5799)
+
+
+def test_shared_library_exports_the_declared_c_abi():
+    hdr = open(os.path.join(ROOT, "include", "sqmp_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(sqmp_[a-z0-9_]+)\s*\(", hdr)))
+    assert set(declared) == set(api.EXPORTS)
+    L = api.load_library()
+    for fn in declared:
+        assert hasattr(L, fn), fn
+    assert b"sm_100a" in L.sqmp_version()
+    out = subprocess.run(["nm", "-D", "--defined-only", api.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (sqmp_[a-z0-9_]+)", out))
+    assert set(declared) <= exported
+
+
+def test_library_contains_only_sm100a_code():
+    out = subprocess.run(["cuobjdump", "-lelf", api.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_no_cpu_fallback_without_gpu(fixture_data):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lt, fx, spheres = fixture_data
+    with pytest.raises(api.SqmpError) as e:
+        api.Context(rd.compile_robot(lt, spheres), 0)
+    assert e.value.code == -5                                   # SQMP_ERR_NODEVICE
+    from squirrel_motion_planner_b200 import planner_shim
+    cc = planner_shim.CollisionChecker()
+    assert not cc.initialized and cc.isInCollision(np.zeros(8), True, True)   # fails closed (CC:106-107)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "squirrel_motion_planner_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in txt and "sqmp_oracle" not in txt and "liboracle" not in txt, f
+
+
+def test_shard_ranges_cover_and_align():
+    for S in (1, 31, 32, 33, 1000, 1 << 20, (1 << 26) + 5):
+        for R in (1, 2, 3, 4, 8):
+            prev = 0
+            for r in range(R):
+                lo, hi, per = sharding.shard_range(S, r, R)
+                assert lo == prev or lo == S
+                assert per % 32 == 0 and (lo % 32 == 0 or lo == S)
+                prev = hi
+            assert prev == S
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch, torch.distributed as dist
+import oracle
+from squirrel_motion_planner_b200 import robot_desc as rd, sharding, synthetic as syn
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=rank, world_size=world)
+lt, fx = rd.load_fixture()
+spheres = [(n, tuple(c), r) for n, c, r in fx["spheres"]]
+orc = oracle.Oracle(lt, spheres)           # CPU stand-in for the kernel: the test is about the plumbing
+w = syn.box_world(g=64, n_boxes=8, seed=5)
+orc.set_grid(w.bits, w.dims, w.origin + np.array([0, 0, -0.02]), w.res)
+S = 21 * 101 + 7
+q = syn.state_batch(S, seed=42, xy_half=1.4)
+lo, hi, per = sharding.shard_range(S, rank, world)
+local = np.zeros(per // 32, dtype=np.uint32)
+m = orc.check_states(q[lo:hi], oracle.FLAG_MAP)
+local[:m.size] = m
+full = sharding.gather_masks(torch.from_numpy(local.view(np.int32)), S, rank, world)
+want = orc.check_states(q, oracle.FLAG_MAP)
+assert np.array_equal(full.numpy().view(np.uint32), want), "gathered mask differs from the unsharded one"
+assert 0 < sharding.unpack_mask(want, S).sum() < S
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_mask_allgather_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    port = str(29600 + os.getpid() % 300)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT, port], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=240)
+        assert p.returncode == 0, out

@@ -1,0 +1,151 @@
+"""CPU: the oracle (oracle/sqmp_oracle.c) against golden vectors made by independent code (tests/golden/make_golden.py).
+
+The reference ships no tests or fixtures for this path ("parity unpinned", oracle/sqmp_oracle.h); these goldens pin
+the oracle to scipy / numpy restatements computed straight from the reference's URDF constants.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN, unpack
+
+
+def _quat_close(a, b, tol):
+    return np.minimum(np.abs(a - b).max(1), np.abs(a + b).max(1)).max() < tol
+
+
+def test_fk_matches_scipy_urdf_chain(orc):
+    g = np.load(os.path.join(GOLDEN, "fk_scipy.npz"))
+    ee = orc.fk(g["q"])
+    assert np.abs(ee[:, :3] - g["ee"][:, :3]).max() < 1e-12
+    assert _quat_close(ee[:, 3:], g["ee"][:, 3:], 1e-12)
+    assert np.abs(np.linalg.norm(ee[:, 3:], axis=1) - 1).max() < 1e-12
+
+
+def test_link_frames_match_scipy(orc, fixture_data):
+    lt = fixture_data[0]
+    g = np.load(os.path.join(GOLDEN, "fk_scipy.npz"))
+    for s in range(0, len(g["q"]), 16):
+        fr = orc.update_transforms(g["q"][s])
+        for n in g["frame_names"]:
+            assert np.abs(fr[lt.index(str(n))] - g["frame_" + str(n)][s]).max() < 1e-12, n
+
+
+def test_root_offset_and_frozen_joints(orc, fixture_data):
+    lt = fixture_data[0]
+    fr = orc.update_transforms(np.zeros(8))
+    assert fr[0, 11] == 0.02 and np.all(fr[0, 9:11] == 0)          # CC:199-201
+    assert abs(fr[lt.index("base_neck_link"), 11] - (0.676 + 0.02)) < 1e-15   # URDF base_neck_joint, frozen
+
+
+def test_collision_clearance_matches_numpy_bruteforce(orc):
+    g = np.load(os.path.join(GOLDEN, "collision_numpy.npz"))
+    orc.set_disabled_links(0)
+    orc.set_grid(g["bits"], g["dims"], g["origin"], float(g["res"]))
+    mask, cm, _ = orc.check_states(g["q"], oracle.FLAG_MAP, clearance=True, cap=10.0)
+    assert np.abs(cm - g["clearance"]).max() < 1e-12
+    hit = unpack(mask, len(g["q"]))
+    assert np.array_equal(hit, g["clearance"] <= 0.0)
+    assert 0.1 < hit.mean() < 0.9
+    # the early-exit path gives the same verdicts
+    assert np.array_equal(unpack(orc.check_states(g["q"], oracle.FLAG_MAP), len(g["q"])), hit)
+    # getCollisions (CC:610-631): per-link map hits
+    for s in range(0, len(g["q"]), 8):
+        lm, _ = orc.get_collisions(g["q"][s])
+        assert np.array_equal(lm, g["per_link"][s])
+
+
+def test_disabled_links_and_flags(orc):
+    g = np.load(os.path.join(GOLDEN, "collision_numpy.npz"))
+    orc.set_grid(g["bits"], g["dims"], g["origin"], float(g["res"]))
+    q = g["q"]
+    assert not orc.is_in_collision(q[0], False, False)               # CC:109-110
+    orc.set_disabled_links((1 << 64) - 1)
+    assert not unpack(orc.check_states(q, oracle.FLAG_MAP), len(q)).any()
+    orc.set_disabled_links(0)
+
+
+def test_nearest_and_radius_match_numpy(orc):
+    g = np.load(os.path.join(GOLDEN, "nn_numpy.npz"))
+    ids = oracle.nearest(g["nodes"], g["queries"])
+    assert np.array_equal(ids, g["nearest"])
+    assert ids[0] == 50                                               # duplicates at 50, 100, 2000: lowest id wins
+    off = 0
+    for k, x in enumerate(g["queries"]):
+        n = int(g["near_count"][k])
+        want = g["near_flat"][off:off + n]
+        off += n
+        got = oracle.near_vertices(g["nodes"], g["cost"], x, -1, 1.5)
+        assert np.array_equal(got, want)
+        if n:
+            ex = int(want[0])
+            got_ex = oracle.near_vertices(g["nodes"], g["cost"], x, ex, 1.5)
+            assert np.array_equal(got_ex, want[1:])                   # BS:4295 excludes x_new itself
+    low, high, cnt = oracle.near_topk(g["nodes"], g["cost"], g["queries"], None, 1.5, 20)
+    assert np.array_equal(cnt, g["near_count"])
+
+
+def test_nearest_quirks():
+    far = np.full((5, 8), 1e6)
+    assert oracle.nearest(far, np.zeros((1, 8)))[0] == 0              # nothing below 10000.0: id stays 0 (BS:4084-4090)
+    nodes = np.zeros((3, 8)); nodes[0, 0] = 20000.0; nodes[1, 0] = 3.0; nodes[2, 0] = 3.0
+    assert oracle.nearest(nodes, np.zeros((1, 8)))[0] == 1
+
+
+def test_interpolation_matches_numpy(orc):
+    g = np.load(os.path.join(GOLDEN, "interp_numpy.npz"))
+    for e in range(len(g["start"])):
+        got = oracle.interpolate(g["start"][e], g["end"][e], 20)
+        assert np.array_equal(got, g["states"][e * 21:(e + 1) * 21])   # bit-exact
+        assert np.array_equal(got[0], g["start"][e])
+
+
+def test_is_edge_valid_last_valid_idx(orc):
+    g = np.load(os.path.join(GOLDEN, "collision_numpy.npz"))
+    orc.set_grid(g["bits"], g["dims"], g["origin"], float(g["res"]))
+    from squirrel_motion_planner_b200 import synthetic as syn
+    a, b = syn.edge_batch(200, seed=9, xy_half=1.0)
+    mask, first = orc.check_edges(a, b, 20, oracle.FLAG_MAP)
+    bits = unpack(mask, 200 * 21).reshape(200, 21)
+    seen = set()
+    for e in range(200):
+        traj = oracle.interpolate(a[e], b[e], 20)
+        ok, last = orc.is_edge_valid(traj, False, True)
+        bad = np.nonzero(bits[e])[0]
+        assert ok == (bad.size == 0)
+        assert first[e] == (bad[0] if bad.size else -1)
+        assert last == (20 if ok else max(bad[0] - 1, 0))             # BS:6878-6895
+        seen.add(int(first[e]))
+    assert -1 in seen and 0 in seen and len(seen) > 3
+
+
+def test_edge_cost_and_step(orc):
+    from squirrel_motion_planner_b200 import synthetic as syn
+    a = syn.sample_configs(50, seed=1)
+    r = syn.sample_configs(50, seed=2)
+    r[:5, :2] = a[:5, :2] + 1e-4          # prismatic target already reached
+    r[5:10, 2:] = a[5:10, 2:]             # revolute target already reached
+    r[10:12] = a[10:12]
+    stepped = syn.step_towards(a, r, 0.6)
+    for i in range(50):
+        reached, x = oracle.step_towards(a[i], r[i], syn.IS_REVOLUTE, 0.6)
+        assert np.array_equal(x, stepped[i])                          # the vectorised host version is bit-exact
+        assert reached == (np.array_equal(x, r[i]))
+    traj = oracle.interpolate(a[20], stepped[20], 20)
+    c = oracle.edge_cost(traj, syn.IS_REVOLUTE)
+    seg = np.diff(traj, axis=0)
+    assert abs(c[0] - np.sqrt((seg ** 2).sum(1)).sum()) < 1e-12
+    assert abs(c[1] - np.sqrt((seg[:, 2:] ** 2).sum(1)).sum()) < 1e-12
+    assert abs(c[2] - np.sqrt((seg[:, :2] ** 2).sum(1)).sum()) < 1e-12
+
+
+def test_published_poses_are_self_collision_free(orc, fixture_data):
+    """Sanity of the authored sphere model against poses the real robot executes
+    (config/parameters.yaml:37 folded arm; folding_poses_tuw-robotino2.yaml key-frames 2..24)."""
+    fx = fixture_data[1]
+    poses = [fx["pose_folded_arm"]] + fx["folding_poses"][1:]
+    q = np.array([[0.3, -0.2, 0.7] + list(a) for a in poses])
+    hit = unpack(orc.check_states(q, oracle.FLAG_SELF), len(q))
+    assert not hit.any()
