@@ -20,7 +20,8 @@ struct DevBuf {
 struct Ctx {
   int device = 0;
   int sm_count = 148;
-  RobotDev rb;
+  RobotDev rb;        // metres (FK kernel)
+  RobotDev rb_grid;   // grid units of the current voxel grid (validity kernel); == rb while no grid is set
   GridDev gd;
   int sph_link[SQMP_MAX_SPHERES];
   int n_pairs = 0;
@@ -94,20 +95,42 @@ static int frame_kind_of(const double *f) {
   return (f[9] == 0.0 && f[10] == 0.0 && f[11] == 0.0) ? 0 : 1;
 }
 
-// per-grid sphere constants: distance-field threshold and scan half-extent
-static void refresh_sphere_grid_params(Ctx *c) {
-  for (int i = 0; i < c->rb.n_spheres; ++i) {
-    const double r = c->rb.sph[i][3];
-    if (!c->gd.has_grid) {
-      c->rb.sph_thr8[i] = 255;
-      c->rb.sph_ncell[i] = 0;
+// Grid-unit copy of the robot for the validity kernel: lengths / res, root offset measured from the grid origin,
+// per-sphere distance-field threshold and scan half-extent, self-pair radii in grid units.  Re-derived whenever
+// the grid (CC:76-88) or the link-disable mask (CC:90-102) changes.
+static int refresh_grid_robot(Ctx *c) {
+  const RobotDev &rb = c->rb;
+  RobotDev &g = c->rb_grid;
+  g = rb;
+  const bool has = c->gd.has_grid != 0;
+  const double inv = has ? c->gd.inv_res : 1.0;
+  const double o[3] = {has ? c->gd.ox : 0.0, has ? c->gd.oy : 0.0, has ? c->gd.oz : 0.0};
+  g.len_scale = inv;
+  for (int s = 0; s < rb.n_seg; ++s)
+    for (int i = 9; i < 12; ++i) g.seg_pre[s][i] = rb.seg_pre[s][i] * inv;
+  for (int i = 0; i < 3; ++i) g.root_off[i] = (rb.root_off[i] - o[i]) * inv;
+  for (int i = 0; i < rb.n_spheres; ++i) {
+    for (int k = 0; k < 4; ++k) g.sph[i][k] = rb.sph[i][k] * inv;
+    const double r = rb.sph[i][3];
+    if (!has) {
+      g.sph_thr8[i] = 255;
+      g.sph_ncell[i] = 0;
       continue;
     }
     const double t = std::floor(4.0 * r / c->gd.res);
-    c->rb.sph_thr8[i] = (unsigned char)(t > 255.0 ? 255.0 : t);
+    g.sph_thr8[i] = (unsigned char)(t > 255.0 ? 255.0 : t);
     const double n = std::ceil(r / c->gd.res);
-    c->rb.sph_ncell[i] = (unsigned char)(n > 250.0 ? 250.0 : n);
+    g.sph_ncell[i] = (unsigned char)(n > 250.0 ? 250.0 : n);
   }
+  for (int p = 0; p < c->n_pairs; ++p) {
+    const double rs = (rb.sph[c->h_pairs[p].a][3] + rb.sph[c->h_pairs[p].b][3]) * inv;
+    c->h_pairs[p].rsum2 = float(rs * rs);
+  }
+  if (c->d_pairs && c->n_pairs > 0) {
+    cudaError_t e = cudaMemcpy(c->d_pairs, c->h_pairs.data(), sizeof(SelfPair) * size_t(c->n_pairs), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return fail(c, SQMP_ERR_CUDA, "cudaMemcpy(self pairs)", e);
+  }
+  return SQMP_OK;
 }
 
 static int tree_reserve(Ctx *c, TreeDev &t, int64_t need) {
@@ -256,6 +279,8 @@ sqmp_ctx *sqmp_create(int device, const sqmp_robot_desc *d, int *err_out) {
   rb.n_spheres = d->n_spheres;
   rb.self_const_collision = d->self_const_collision;
   rb.ref_seg = -1;
+  rb.trans_mask = 0;
+  rb.len_scale = 1.0;
   bool leading = true;
   for (int s = 0; s < d->n_seg; ++s) {
     if ((d->seg_type[s] != SQMP_JOINT_ROT && d->seg_type[s] != SQMP_JOINT_TRANS) || d->seg_qidx[s] < 0 ||
@@ -265,6 +290,7 @@ sqmp_ctx *sqmp_create(int device, const sqmp_robot_desc *d, int *err_out) {
     }
     rb.seg_type[s] = d->seg_type[s];
     rb.seg_qidx[s] = d->seg_qidx[s];
+    if (d->seg_type[s] == SQMP_JOINT_TRANS) rb.trans_mask |= 1u << d->seg_qidx[s];
     std::memcpy(rb.seg_pre[s], d->seg_pre[s], sizeof(double) * 12);
     std::memcpy(rb.seg_axis[s], d->seg_axis[s], sizeof(double) * 3);
     rb.seg_axis_code[s] = axis_code_of(d->seg_axis[s]);
@@ -297,7 +323,6 @@ sqmp_ctx *sqmp_create(int device, const sqmp_robot_desc *d, int *err_out) {
   for (int s = 1; s <= SQMP_MAX_SEG + 1; ++s)
     if (rb.seg_sph_end[s] < rb.seg_sph_end[s - 1]) rb.seg_sph_end[s] = rb.seg_sph_end[s - 1];
   for (int w = 0; w < SQMP_MAX_SPHERES / 32; ++w) rb.sph_enabled[w] = 0xffffffffu;
-  refresh_sphere_grid_params(c);
 
   c->n_pairs = d->n_pairs;
   c->h_pairs.resize(size_t(d->n_pairs) + 1);
@@ -318,7 +343,7 @@ sqmp_ctx *sqmp_create(int device, const sqmp_robot_desc *d, int *err_out) {
                         cudaMemcpyHostToDevice) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&c->streams[0], cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&c->streams[1], cudaStreamNonBlocking) == cudaSuccess;
-  if (!ok) {
+  if (!ok || refresh_grid_robot(c) != SQMP_OK) {
     sqmp_destroy(c);
     return bail(SQMP_ERR_CUDA);
   }
@@ -423,8 +448,7 @@ int sqmp_set_voxel_grid(sqmp_ctx *ctx, const uint32_t *bits, int gx, int gy, int
   g.ox = origin[0]; g.oy = origin[1]; g.oz = origin[2];
   g.res = res; g.inv_res = 1.0 / res;
   g.has_grid = 1;
-  refresh_sphere_grid_params(c);
-  return SQMP_OK;
+  return refresh_grid_robot(c);
 }
 
 int sqmp_set_disabled_links(sqmp_ctx *ctx, uint64_t link_mask) {
@@ -432,7 +456,8 @@ int sqmp_set_disabled_links(sqmp_ctx *ctx, uint64_t link_mask) {
   for (int w = 0; w < SQMP_MAX_SPHERES / 32; ++w) c->rb.sph_enabled[w] = 0;
   for (int i = 0; i < c->rb.n_spheres; ++i)
     if (!((link_mask >> c->sph_link[i]) & 1ull)) c->rb.sph_enabled[i >> 5] |= 1u << (i & 31);
-  return SQMP_OK;
+  CU(cudaDeviceSynchronize());
+  return refresh_grid_robot(c);
 }
 
 // ---------------------------------------------------------------------------------------------------- validity
@@ -447,7 +472,7 @@ int sqmp_check_states_dev(sqmp_ctx *ctx, const double *d_q, int64_t S, unsigned 
     return SQMP_OK;
   }
   int nl = 0;
-  CU(launch_check_states(c->rb, c->gd, c->d_pairs, c->n_pairs, d_q, nullptr, 0, S, flags, d_mask, c->fk_precision,
+  CU(launch_check_states(c->rb_grid, c->gd, c->d_pairs, c->n_pairs, d_q, nullptr, 0, S, flags, d_mask, c->fk_precision,
                          st, &nl));
   c->launches += nl;
   return SQMP_OK;
@@ -466,7 +491,7 @@ int sqmp_check_edges_dev(sqmp_ctx *ctx, const double *d_a, const double *d_b, in
     CU(cudaMemsetAsync(d_mask, 0, size_t((S + 31) / 32) * 4, st));
   } else {
     int nl = 0;
-    CU(launch_check_states(c->rb, c->gd, c->d_pairs, c->n_pairs, d_a, d_b, num_points, S, flags, d_mask,
+    CU(launch_check_states(c->rb_grid, c->gd, c->d_pairs, c->n_pairs, d_a, d_b, num_points, S, flags, d_mask,
                            c->fk_precision, st, &nl));
     c->launches += nl;
   }
@@ -542,7 +567,7 @@ int sqmp_get_collisions(sqmp_ctx *ctx, const double q[SQMP_DOF], uint8_t *link_m
   CU(cudaMemcpyAsync(dq, q, SQMP_DOF * 8, cudaMemcpyHostToDevice, st));
   CU(cudaMemsetAsync(ds, 0, SQMP_MAX_SPHERES, st));
   CU(cudaMemsetAsync(dp, 0, size_t(c->n_pairs) + 1, st));
-  CU(launch_get_collisions(c->rb, c->gd, c->d_pairs, c->n_pairs, (const double *)dq, (uint8_t *)ds, (uint8_t *)dp, st));
+  CU(launch_get_collisions(c->rb_grid, c->gd, c->d_pairs, c->n_pairs, (const double *)dq, (uint8_t *)ds, (uint8_t *)dp, st));
   c->launches += 1;
   uint8_t sh[SQMP_MAX_SPHERES];
   CU(cudaMemcpyAsync(sh, ds, SQMP_MAX_SPHERES, cudaMemcpyDeviceToHost, st));

@@ -24,6 +24,8 @@ struct RobotDev {
   int n_spheres;
   int ref_seg;                            // last segment of the leading prismatic run (base position)
   int self_const_collision;
+  unsigned trans_mask;                    // bit j: q[j] drives a prismatic joint (a length)
+  double len_scale;                       // 1 (metres) or 1/res (grid units, the copy K1 runs on)
   int seg_type[SQMP_MAX_SEG];
   int seg_qidx[SQMP_MAX_SEG];
   int seg_axis_code[SQMP_MAX_SEG];

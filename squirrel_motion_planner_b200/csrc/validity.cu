@@ -15,47 +15,31 @@
 namespace sqmp {
 
 // ------------------------------------------------------------------------------------------------
-// exact sphere vs occupied-voxel-boxes test
+// exact sphere vs occupied-voxel-boxes test, in GRID UNITS: voxel (i,j,k) is the unit cube [i,i+1]x[j,j+1]x[k,k+1],
+// the sphere has centre u and radius rg = r / res.  true <=> dist(u, some occupied unit cube) <= rg.
+// Per (j,k) row the admissible x-interval is closed-form, so a row costs one (rarely two) word loads.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double axis_gap(double c, double lo, double hi) {
-  return fmax(fmax(lo - c, c - hi), 0.0);
-}
-
-// true  <=> dist(centre, AABB of some occupied voxel) <= r.   thr8 / ncell: per-sphere constants for this grid.
-__device__ __forceinline__ bool sphere_hits_map(const GridDev &g, double cx, double cy, double cz, double r,
-                                                int thr8, int ncell) {
-  const double ux = (cx - g.ox) * g.inv_res, uy = (cy - g.oy) * g.inv_res, uz = (cz - g.oz) * g.inv_res;
-  // reject anything that cannot reach the grid (also keeps the int conversions below in range)
-  const double reach = double(ncell + 1);
-  if (!(ux > -reach && uy > -reach && uz > -reach && ux < g.gx + reach && uy < g.gy + reach && uz < g.gz + reach))
-    return false;
-  const int ix = __double2int_rd(ux), iy = __double2int_rd(uy), iz = __double2int_rd(uz);
-  if (ix >= 0 && iy >= 0 && iz >= 0 && ix < g.gx && iy < g.gy && iz < g.gz) {
-    // box-to-box distance of this cell to the nearest occupied cell bounds dist(c, occupied) from below
-    const int e = g.edt[(size_t(iz) * g.gy + iy) * g.gx + ix];
-    if (e > thr8) return false;
-  }
-  const double rc = r * g.inv_res, r2 = r * r;
-  const int k0 = max(__double2int_rd(uz - rc), 0), k1 = min(__double2int_rd(uz + rc), g.gz - 1);
-  const int j0 = max(__double2int_rd(uy - rc), 0), j1 = min(__double2int_rd(uy + rc), g.gy - 1);
-  for (int k = k0; k <= k1; ++k) {
-    const double dz = axis_gap(cz, fma(double(k), g.res, g.oz), fma(double(k + 1), g.res, g.oz));
-    const double remz = r2 - dz * dz;
+__device__ __forceinline__ bool exact_scan(const GridDev &g, double ux, double uy, double uz, double rg) {
+  const double r2 = rg * rg;
+  const int k0 = max(__double2int_rd(uz - rg), 0), k1 = min(__double2int_rd(uz + rg), g.gz - 1);
+  const int j0 = max(__double2int_rd(uy - rg), 0), j1 = min(__double2int_rd(uy + rg), g.gy - 1);
+  double kd = double(k0);
+  for (int k = k0; k <= k1; ++k, kd += 1.0) {
+    const double dz = fmax(fmax(kd - uz, uz - (kd + 1.0)), 0.0);
+    const double remz = fma(-dz, dz, r2);
     if (remz < 0.0) continue;
     const uint32_t *slab = g.occ + size_t(k) * g.gy * g.row_words;
-    for (int j = j0; j <= j1; ++j) {
-      const double dy = axis_gap(cy, fma(double(j), g.res, g.oy), fma(double(j + 1), g.res, g.oy));
-      const double rem = remz - dy * dy;
+    double jd = double(j0);
+    for (int j = j0; j <= j1; ++j, jd += 1.0) {
+      const double dy = fmax(fmax(jd - uy, uy - (jd + 1.0)), 0.0);
+      const double rem = fma(-dy, dy, remz);
       if (rem < 0.0) continue;
-      const double wc = sqrt(rem) * g.inv_res;  // half-width of the admissible x interval, in cells
-      // voxel i is within reach  <=>  ox + (i+1) res >= cx - w  and  ox + i res <= cx + w
-      int i0 = __double2int_ru(ux - wc) - 1, i1 = __double2int_rd(ux + wc);
-      i0 = max(i0, 0);
-      i1 = min(i1, g.gx - 1);
-      if (i0 > i1) continue;
+      const double w = sqrt(rem);  // half-width of the admissible x interval
+      // cube i is within reach  <=>  i + 1 >= ux - w  and  i <= ux + w
+      int i0 = max(__double2int_ru(ux - w) - 1, 0);
+      const int i1 = min(__double2int_rd(ux + w), g.gx - 1);
       const uint32_t *row = slab + size_t(j) * g.row_words;
-      // [i0, i1] is at most 2*ncell+2 wide: one word, two when it straddles a word boundary
-      while (i0 <= i1) {
+      while (i0 <= i1) {  // at most 2*ceil(rg)+2 wide: one word, two when it straddles a word boundary
         const int sh = i0 & 31;
         const int n = min(32 - sh, i1 - i0 + 1);
         const uint32_t bits = (row[i0 >> 5] >> sh) & (n >= 32 ? ~0u : ((1u << n) - 1u));
@@ -71,126 +55,209 @@ __device__ __forceinline__ bool sphere_hits_map(const GridDev &g, double cx, dou
 // K1
 // ------------------------------------------------------------------------------------------------
 constexpr int K1_THREADS = 128;
+constexpr int K1_QCAP = 64;       // deferred exact-scan items per warp (drained 32 at a time)
+constexpr int K1_BATCH = 4;       // spheres whose distance-field gathers are in flight together
+constexpr unsigned FULL = 0xffffffffu;
+
+struct WarpQueue {   // shared memory, one per warp
+  double x[K1_QCAP], y[K1_QCAP], z[K1_QCAP], r[K1_QCAP];
+  int info[K1_QCAP];   // sphere index << 8 | owner lane
+};
 
 // MODE 0: verdict bit per state.  MODE 1 (diagnostics, one state): per-sphere / per-pair hits, no early exit.
+//
+// rb is the GRID-UNIT copy of the robot (translations, sphere centres and radii divided by res, root offset
+// measured from the grid origin), so a sphere centre comes out of the chain directly in voxel coordinates.
+//
+// Divergence control: the cheap filter (one byte gather from the distance field) runs in lockstep for all lanes;
+// the few spheres it cannot clear are NOT scanned on the spot (that left ~4 of 32 lanes active) but pushed, by
+// ballot compaction, on a per-warp queue in shared memory, and scanned 32 at a time with one item per lane.
 template <typename T, bool EDGES, int MODE>
 __global__ void __launch_bounds__(K1_THREADS)
 k1_check_states(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd,
                 const SelfPair *__restrict__ pairs, int n_pairs, const double *__restrict__ q_in,
                 const double *__restrict__ q_end, int num_points, int64_t S, unsigned flags,
                 uint32_t *__restrict__ mask_out, uint8_t *__restrict__ sphere_hit, uint8_t *__restrict__ pair_hit) {
-  extern __shared__ float s_rel[];  // [3][n_spheres][blockDim] sphere centres relative to the base, SELF only
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WarpQueue *wq = reinterpret_cast<WarpQueue *>(smem_raw) + (threadIdx.x >> 5);
+  float *s_rel = reinterpret_cast<float *>(smem_raw + sizeof(WarpQueue) * (K1_THREADS / 32));  // [3][n][blockDim]
+  const int lane = threadIdx.x & 31;
   const int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool active = s < S;
+  const int64_t sl = active ? s : S - 1;  // idle lanes of the last warp shadow the last state (lockstep loops)
   const bool do_map = (flags & SQMP_CHECK_MAP) && gd.has_grid;
   const bool do_self = (flags & SQMP_CHECK_SELF) != 0;
   bool hit = false;
+  int qcount = 0;  // warp-uniform
 
-  if (active) {
-    // ---- the state: either given, or interpolated from the edge end points (BS:4461-4462, 4478; no FMA) ----
-    double q[SQMP_DOF];
-    if (EDGES) {
-      const int P1 = num_points + 1;
-      const int64_t e = s / P1;
-      const int kk = int(s - e * P1);
-      const double4 *a4 = reinterpret_cast<const double4 *>(q_in + e * SQMP_DOF);
-      const double4 *b4 = reinterpret_cast<const double4 *>(q_end + e * SQMP_DOF);
-      const double4 a0 = a4[0], a1 = a4[1], b0 = b4[0], b1 = b4[1];
-      const double st[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const double en[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      const double np = double(num_points), fk = double(kk);
+  // ---- the state: either given, or interpolated from the edge end points (BS:4461-4462, 4478; no FMA) ----
+  double q[SQMP_DOF];
+  if (EDGES) {
+    const int P1 = num_points + 1;
+    const int64_t e = sl / P1;
+    const int kk = int(sl - e * P1);
+    const double4 *a4 = reinterpret_cast<const double4 *>(q_in + e * SQMP_DOF);
+    const double4 *b4 = reinterpret_cast<const double4 *>(q_end + e * SQMP_DOF);
+    const double4 a0 = a4[0], a1 = a4[1], b0 = b4[0], b1 = b4[1];
+    const double st[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const double en[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const double np = double(num_points), fk = double(kk);
 #pragma unroll
-      for (int j = 0; j < SQMP_DOF; ++j)
-        q[j] = __dadd_rn(st[j], __dmul_rn(fk, __ddiv_rn(__dsub_rn(en[j], st[j]), np)));
-    } else {
-      const double4 *p4 = reinterpret_cast<const double4 *>(q_in + s * SQMP_DOF);
-      const double4 v0 = p4[0], v1 = p4[1];
-      q[0] = v0.x; q[1] = v0.y; q[2] = v0.z; q[3] = v0.w;
-      q[4] = v1.x; q[5] = v1.y; q[6] = v1.z; q[7] = v1.w;
-    }
-
-    // ---- base reference point (world) = position after the leading prismatic run ----
-    double pref[3] = {rb.root_off[0], rb.root_off[1], rb.root_off[2]};
-    if (do_self || sizeof(T) == 4) {
-      for (int sg = 0; sg <= rb.ref_seg; ++sg) {
-        const int qi = rb.seg_qidx[sg];
-        double qv = q[0];
+    for (int j = 0; j < SQMP_DOF; ++j)
+      q[j] = __dadd_rn(st[j], __dmul_rn(fk, __ddiv_rn(__dsub_rn(en[j], st[j]), np)));
+  } else {
+    const double4 *p4 = reinterpret_cast<const double4 *>(q_in + sl * SQMP_DOF);
+    const double4 v0 = p4[0], v1 = p4[1];
+    q[0] = v0.x; q[1] = v0.y; q[2] = v0.z; q[3] = v0.w;
+    q[4] = v1.x; q[5] = v1.y; q[6] = v1.z; q[7] = v1.w;
+  }
+  // prismatic joint values are lengths: into grid units with everything else
 #pragma unroll
-        for (int j = 1; j < SQMP_DOF; ++j) qv = (qi == j) ? q[j] : qv;
+  for (int j = 0; j < SQMP_DOF; ++j) q[j] = ((rb.trans_mask >> j) & 1) ? q[j] * rb.len_scale : q[j];
+
+  // ---- base reference point = position after the leading prismatic run ----
+  double pref[3] = {rb.root_off[0], rb.root_off[1], rb.root_off[2]};
+  if (do_self || sizeof(T) == 4) {
+    for (int sg = 0; sg <= rb.ref_seg; ++sg) {
+      const int qi = rb.seg_qidx[sg];
+      double qv = q[0];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) pref[i] += rb.seg_pre[sg][9 + i] + rb.seg_axis[sg][i] * qv;
-      }
+      for (int j = 1; j < SQMP_DOF; ++j) qv = (qi == j) ? q[j] : qv;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) pref[i] += rb.seg_pre[sg][9 + i] + rb.seg_axis[sg][i] * qv;
     }
+  }
 
-    // ---- chain walk; T = double walks the whole chain in world coordinates, T = float walks the part after
-    //      the prismatic base relative to pref (host guarantees the leading run is translation-only) ----
-    Frame<T> f;
-    double off[3];
-    int sg0;
-    if (sizeof(T) == 8) {
-      frame_set_translation<T>(f, T(rb.root_off[0]), T(rb.root_off[1]), T(rb.root_off[2]));
-      off[0] = off[1] = off[2] = 0.0;
-      sg0 = 0;
-    } else {
-      frame_set_translation<T>(f, T(0), T(0), T(0));
-      off[0] = pref[0]; off[1] = pref[1]; off[2] = pref[2];
-      sg0 = rb.ref_seg + 1;
+  // ---- chain walk; T = double walks the whole chain, T = float walks the part after the prismatic base
+  //      relative to pref (host guarantees the leading run is translation-only) ----
+  Frame<T> f;
+  double off[3];
+  int sg0;
+  if (sizeof(T) == 8) {
+    frame_set_translation<T>(f, T(rb.root_off[0]), T(rb.root_off[1]), T(rb.root_off[2]));
+    off[0] = off[1] = off[2] = 0.0;
+    sg0 = 0;
+  } else {
+    frame_set_translation<T>(f, T(0), T(0), T(0));
+    off[0] = pref[0]; off[1] = pref[1]; off[2] = pref[2];
+    sg0 = rb.ref_seg + 1;
+  }
+
+  // scan the queued items [base, base+n) with one item per lane; route the verdicts back to the owning lanes
+  auto drain = [&](int base, int n) {
+    __syncwarp();
+    const unsigned known = __ballot_sync(FULL, hit);
+    bool h = false;
+    int owner = 0;
+    if (lane < n) {
+      const int info = wq->info[base + lane];
+      owner = info & 31;
+      if (!((known >> owner) & 1u))
+        h = exact_scan(gd, wq->x[base + lane], wq->y[base + lane], wq->z[base + lane], wq->r[base + lane]);
     }
+    const unsigned hm = __reduce_or_sync(FULL, h ? (1u << owner) : 0u);
+    hit |= (hm >> lane) & 1u;
+    __syncwarp();
+  };
 
-    for (int sg = -1; sg < rb.n_seg; ++sg) {
-      if (sg >= sg0) frame_advance<T>(f, rb, sg, q);
-      else if (sg >= 0) continue;
-      const int b = rb.seg_sph_end[sg + 1], e = rb.seg_sph_end[sg + 2];
-      for (int i = b; i < e; ++i) {
+  for (int sg = -1; sg < rb.n_seg; ++sg) {
+    if (sg >= sg0) frame_advance<T>(f, rb, sg, q);
+    else if (sg >= 0) continue;
+    const int b = rb.seg_sph_end[sg + 1], e = rb.seg_sph_end[sg + 2];
+    for (int i0 = b; i0 < e; i0 += K1_BATCH) {
+      double ux[K1_BATCH], uy[K1_BATCH], uz[K1_BATCH];
+      int ev[K1_BATCH];
+      bool need[K1_BATCH];
+#pragma unroll
+      for (int u = 0; u < K1_BATCH; ++u) {  // transform + gather (independent loads, issued back to back)
+        const int i = min(i0 + u, e - 1);
         const T lx = T(rb.sph[i][0]), ly = T(rb.sph[i][1]), lz = T(rb.sph[i][2]);
         const T wx = fma(f.r[0], lx, fma(f.r[1], ly, fma(f.r[2], lz, f.p[0])));
         const T wy = fma(f.r[3], lx, fma(f.r[4], ly, fma(f.r[5], lz, f.p[1])));
         const T wz = fma(f.r[6], lx, fma(f.r[7], ly, fma(f.r[8], lz, f.p[2])));
-        const double cx = double(wx) + off[0], cy = double(wy) + off[1], cz = double(wz) + off[2];
-        if (do_self) {
+        ux[u] = double(wx) + off[0]; uy[u] = double(wy) + off[1]; uz[u] = double(wz) + off[2];
+        if (do_self && i0 + u < e) {
           const int n = rb.n_spheres;
-          s_rel[(0 * n + i) * blockDim.x + threadIdx.x] = float(cx - pref[0]);
-          s_rel[(1 * n + i) * blockDim.x + threadIdx.x] = float(cy - pref[1]);
-          s_rel[(2 * n + i) * blockDim.x + threadIdx.x] = float(cz - pref[2]);
+          s_rel[(0 * n + i) * blockDim.x + threadIdx.x] = float(ux[u] - pref[0]);
+          s_rel[(1 * n + i) * blockDim.x + threadIdx.x] = float(uy[u] - pref[1]);
+          s_rel[(2 * n + i) * blockDim.x + threadIdx.x] = float(uz[u] - pref[2]);
         }
+        // saturating conversions: anything absurdly far lands outside every range test below
+        const int ix = __double2int_rd(ux[u]), iy = __double2int_rd(uy[u]), iz = __double2int_rd(uz[u]);
+        const int pad = rb.sph_ncell[i] + 1;
+        const bool near_grid = unsigned(ix + pad) < unsigned(gd.gx + 2 * pad) &&
+                               unsigned(iy + pad) < unsigned(gd.gy + 2 * pad) &&
+                               unsigned(iz + pad) < unsigned(gd.gz + 2 * pad);
+        const bool inside = unsigned(ix) < unsigned(gd.gx) && unsigned(iy) < unsigned(gd.gy) && unsigned(iz) < unsigned(gd.gz);
         const bool enabled = (MODE == 1) || ((rb.sph_enabled[i >> 5] >> (i & 31)) & 1u);
-        if (do_map && enabled && (MODE == 1 || !hit)) {
-          const bool h = sphere_hits_map(gd, cx, cy, cz, rb.sph[i][3], rb.sph_thr8[i], rb.sph_ncell[i]);
-          hit |= h;
-          if (MODE == 1) sphere_hit[i] = h ? 1 : 0;
+        need[u] = do_map && enabled && near_grid && (i0 + u < e) && (MODE == 1 || !hit);
+        // box-to-box distance of this cell to the nearest occupied cell bounds dist(c, occupied) from below
+        ev[u] = (need[u] && inside) ? int(gd.edt[(size_t(iz) * gd.gy + iy) * gd.gx + ix]) : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < K1_BATCH; ++u) {  // filter verdict; survivors are queued for the exact scan
+        const int i = min(i0 + u, e - 1);
+        const bool nd = need[u] && ev[u] <= int(rb.sph_thr8[i]);
+        if (MODE == 1) {
+          if (nd) sphere_hit[i] = exact_scan(gd, ux[u], uy[u], uz[u], rb.sph[i][3]) ? 1 : 0;
+          continue;
+        }
+        const unsigned m = __ballot_sync(FULL, nd);
+        if (m) {
+          if (nd) {
+            const int pos = qcount + __popc(m & ((1u << lane) - 1u));
+            wq->x[pos] = ux[u]; wq->y[pos] = uy[u]; wq->z[pos] = uz[u]; wq->r[pos] = rb.sph[i][3];
+            wq->info[pos] = (i << 8) | lane;
+          }
+          qcount += __popc(m);
+          if (qcount >= 32) {
+            drain(qcount - 32, 32);
+            qcount -= 32;
+          }
         }
       }
-      if (MODE == 0 && hit) break;  // verdict known (CC:114-115: map before self, first hit wins)
     }
+    // whole warp decided (CC:114-115: map before self, first hit wins) -> stop walking the chain
+    if (MODE == 0 && !do_self && qcount == 0 && __all_sync(FULL, hit)) break;
+  }
+  if (MODE == 0 && qcount > 0) {
+    drain(0, qcount);
+    qcount = 0;
+  }
 
-    // ---- self collision over the enabled cross-group sphere pairs (CC:541-552) ----
-    if (do_self && (MODE == 1 || !hit)) {
-      if (rb.self_const_collision) hit = true;
-      const int n = rb.n_spheres;
-      for (int p = 0; p < n_pairs; ++p) {
-        const SelfPair pr = pairs[p];
-        const float dx = s_rel[(0 * n + pr.a) * blockDim.x + threadIdx.x] - s_rel[(0 * n + pr.b) * blockDim.x + threadIdx.x];
-        const float dy = s_rel[(1 * n + pr.a) * blockDim.x + threadIdx.x] - s_rel[(1 * n + pr.b) * blockDim.x + threadIdx.x];
-        const float dz = s_rel[(2 * n + pr.a) * blockDim.x + threadIdx.x] - s_rel[(2 * n + pr.b) * blockDim.x + threadIdx.x];
-        const bool h = fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= pr.rsum2;
-        hit |= h;
-        if (MODE == 1) pair_hit[p] = h ? 1 : 0;
-        if (MODE == 0 && hit) break;
-      }
+  // ---- self collision over the enabled cross-group sphere pairs (CC:541-552) ----
+  if (do_self && (MODE == 1 || !hit)) {
+    if (rb.self_const_collision) hit = true;
+    const int n = rb.n_spheres;
+    for (int p = 0; p < n_pairs; ++p) {
+      const SelfPair pr = pairs[p];
+      const float dx = s_rel[(0 * n + pr.a) * blockDim.x + threadIdx.x] - s_rel[(0 * n + pr.b) * blockDim.x + threadIdx.x];
+      const float dy = s_rel[(1 * n + pr.a) * blockDim.x + threadIdx.x] - s_rel[(1 * n + pr.b) * blockDim.x + threadIdx.x];
+      const float dz = s_rel[(2 * n + pr.a) * blockDim.x + threadIdx.x] - s_rel[(2 * n + pr.b) * blockDim.x + threadIdx.x];
+      const bool h = fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= pr.rsum2;
+      hit |= h;
+      if (MODE == 1) pair_hit[p] = h ? 1 : 0;
+      if (MODE == 0 && hit) break;
     }
   }
 
   if (MODE == 0) {
-    const unsigned word = __ballot_sync(0xffffffffu, hit);
-    if ((threadIdx.x & 31) == 0 && s < ((S + 31) & ~int64_t(31))) mask_out[s >> 5] = word;
+    const unsigned word = __ballot_sync(FULL, hit && active);
+    if (lane == 0 && s < ((S + 31) & ~int64_t(31))) mask_out[s >> 5] = word;
   }
+}
+
+static size_t k1_smem_bytes(const RobotDev &rb, unsigned flags, int threads) {
+  size_t b = sizeof(WarpQueue) * (K1_THREADS / 32);
+  if (flags & SQMP_CHECK_SELF) b += size_t(3) * rb.n_spheres * threads * sizeof(float);
+  return b;
 }
 
 template <typename T>
 static cudaError_t launch_k1(const RobotDev &rb, const GridDev &gd, const SelfPair *pairs, int n_pairs,
                              const double *d_q, const double *d_q_end, int num_points, int64_t S, unsigned flags,
                              uint32_t *d_mask, cudaStream_t st) {
-  const size_t smem = (flags & SQMP_CHECK_SELF) ? size_t(3) * rb.n_spheres * K1_THREADS * sizeof(float) : 0;
+  const size_t smem = k1_smem_bytes(rb, flags, K1_THREADS);
   const int64_t blocks = (S + K1_THREADS - 1) / K1_THREADS;
   if (blocks <= 0) return cudaSuccess;
   if (blocks > 0x7fffffff) return cudaErrorInvalidValue;
@@ -219,11 +286,11 @@ cudaError_t launch_check_states(const RobotDev &rb, const GridDev &gd, const Sel
 
 cudaError_t launch_get_collisions(const RobotDev &rb, const GridDev &gd, const SelfPair *pairs, int n_pairs,
                                   const double *d_q, uint8_t *d_sphere_hit, uint8_t *d_pair_hit, cudaStream_t st) {
-  const size_t smem = size_t(3) * rb.n_spheres * 32 * sizeof(float);
+  const size_t smem = k1_smem_bytes(rb, SQMP_CHECK_SELF, K1_THREADS);
   auto kern = k1_check_states<double, false, 1>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-  kern<<<1, 32, smem, st>>>(rb, gd, pairs, n_pairs, d_q, nullptr, 0, 1, SQMP_CHECK_MAP | SQMP_CHECK_SELF, nullptr,
-                            d_sphere_hit, d_pair_hit);
+  kern<<<1, K1_THREADS, smem, st>>>(rb, gd, pairs, n_pairs, d_q, nullptr, 0, 1, SQMP_CHECK_MAP | SQMP_CHECK_SELF, nullptr,
+                                    d_sphere_hit, d_pair_hit);
   return cudaGetLastError();
 }
 
