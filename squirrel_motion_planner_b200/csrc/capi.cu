@@ -28,7 +28,8 @@ struct Ctx {
   SelfPair *d_pairs = nullptr;
   std::vector<SelfPair> h_pairs;
   uint32_t *d_occ = nullptr;
-  uint8_t *d_edt = nullptr;
+  uint8_t *d_lb2 = nullptr;
+  uint16_t *d_ft = nullptr;
   TreeDev trees[SQMP_MAX_TREES];
   NNScratch nn;
   size_t nn_part_bytes = 0, nn_hits_bytes = 0;
@@ -95,6 +96,17 @@ static int frame_kind_of(const double *f) {
   return (f[9] == 0.0 && f[10] == 0.0 && f[11] == 0.0) ? 0 : 1;
 }
 
+static void refresh_float_copies(RobotDev &r) {
+  for (int s = 0; s < SQMP_MAX_SEG; ++s) {
+    for (int i = 0; i < 12; ++i) r.seg_pre_f[s][i] = float(r.seg_pre[s][i]);
+    for (int i = 0; i < 3; ++i) r.seg_axis_f[s][i] = float(r.seg_axis[s][i]);
+    r.seg_axis_f[s][3] = 0.0f;
+  }
+  for (int i = 0; i < 12; ++i) r.ee_tip_f[i] = float(r.ee_tip[i]);
+  for (int i = 0; i < SQMP_MAX_SPHERES; ++i)
+    r.sph_f[i] = make_float4(float(r.sph[i][0]), float(r.sph[i][1]), float(r.sph[i][2]), float(r.sph[i][3]));
+}
+
 // Grid-unit copy of the robot for the validity kernel: lengths / res, root offset measured from the grid origin,
 // per-sphere distance-field threshold and scan half-extent, self-pair radii in grid units.  Re-derived whenever
 // the grid (CC:76-88) or the link-disable mask (CC:90-102) changes.
@@ -113,15 +125,19 @@ static int refresh_grid_robot(Ctx *c) {
     for (int k = 0; k < 4; ++k) g.sph[i][k] = rb.sph[i][k] * inv;
     const double r = rb.sph[i][3];
     if (!has) {
-      g.sph_thr8[i] = 255;
+      g.sph_thr[i] = -2;
       g.sph_ncell[i] = 0;
       continue;
     }
-    const double t = std::floor(4.0 * r / c->gd.res);
-    g.sph_thr8[i] = (unsigned char)(t > 255.0 ? 255.0 : t);
+    const double rc = r * inv;  // radius in cells; sqmp_set_voxel_grid guarantees rc <= 13, so rc^2 < 255
+    const double t = std::floor(rc * rc + 1e-9);
+    const bool enabled = (rb.sph_enabled[i >> 5] >> (i & 31)) & 1u;
+    g.sph_thr[i] = enabled ? short(t > 254.0 ? 254.0 : t) : short(-2);
     const double n = std::ceil(r / c->gd.res);
     g.sph_ncell[i] = (unsigned char)(n > 250.0 ? 250.0 : n);
   }
+  refresh_float_copies(g);
+  refresh_float_copies(c->rb);
   for (int p = 0; p < c->n_pairs; ++p) {
     const double rs = (rb.sph[c->h_pairs[p].a][3] + rb.sph[c->h_pairs[p].b][3]) * inv;
     c->h_pairs[p].rsum2 = float(rs * rs);
@@ -357,7 +373,8 @@ void sqmp_destroy(sqmp_ctx *ctx) {
   cudaDeviceSynchronize();
   if (ctx->d_pairs) cudaFree(ctx->d_pairs);
   if (ctx->d_occ) cudaFree(ctx->d_occ);
-  if (ctx->d_edt) cudaFree(ctx->d_edt);
+  if (ctx->d_lb2) cudaFree(ctx->d_lb2);
+  if (ctx->d_ft) cudaFree(ctx->d_ft);
   for (auto &t : ctx->trees)
     if (t.q[0]) cudaFree(t.q[0]);
   if (ctx->nn.part_d) cudaFree(ctx->nn.part_d);
@@ -402,19 +419,23 @@ int sqmp_set_voxel_grid(sqmp_ctx *ctx, const uint32_t *bits, int gx, int gy, int
   if (!bits) return SQMP_OK;  // CC:78-79
   if (gx <= 0 || gy <= 0 || gz <= 0 || !origin || !(res > 0.0)) return fail(c, SQMP_ERR_INVALID, "bad grid");
   const int64_t nvox = int64_t(gx) * gy * gz;
-  if (nvox > (int64_t(1) << 33)) return fail(c, SQMP_ERR_INVALID, "grid too large");
+  if (nvox >= (int64_t(1) << 32)) return fail(c, SQMP_ERR_INVALID, "grid too large (>= 2^32 voxels)");
   double rmax = 0.0;
   for (int i = 0; i < c->rb.n_spheres; ++i) rmax = std::fmax(rmax, c->rb.sph[i][3]);
-  int window = int(std::ceil(rmax / res)) + 2;
-  if (window > 62) return fail(c, SQMP_ERR_INVALID, "sphere radius too large for this resolution (> 60 voxels)");
-  if (window < 4) window = 4;
+  // the 16-bit feature field stores cell offsets in [-15, 15]: every occupied cell within reach of a sphere
+  // (|offset| <= ceil(r/res) + 1 per axis) must be representable
+  if (rmax / res > 13.0) return fail(c, SQMP_ERR_INVALID, "sphere radius too large for this resolution (> 13 voxels)");
+  int window = int(std::ceil(rmax / res)) + 1;
+  if (window < 3) window = 3;
+  if (window > 15) window = 15;
   const int row_words = (gx + 31) / 32 + 1;
   const size_t lin_words = size_t((nvox + 31) / 32) + 1;
   const size_t occ_words = size_t(gy) * gz * row_words;
   CU(cudaDeviceSynchronize());
   uint32_t *d_lin = nullptr, *d_occ = nullptr;
-  uint8_t *d_a = nullptr, *d_edt = nullptr;
-  uint16_t *d_b = nullptr;
+  int8_t *d_a = nullptr;
+  uint8_t *d_lb2 = nullptr;
+  uint16_t *d_b = nullptr, *d_ft = nullptr;
   auto cleanup = [&]() {
     if (d_lin) cudaFree(d_lin);
     if (d_a) cudaFree(d_a);
@@ -426,24 +447,28 @@ int sqmp_set_voxel_grid(sqmp_ctx *ctx, const uint32_t *bits, int gx, int gy, int
   if (e == cudaSuccess) e = cudaMalloc(&d_occ, occ_words * 4);
   if (e == cudaSuccess) e = cudaMalloc(&d_a, size_t(nvox));
   if (e == cudaSuccess) e = cudaMalloc(&d_b, size_t(nvox) * 2);
-  if (e == cudaSuccess) e = cudaMalloc(&d_edt, size_t(nvox));
+  if (e == cudaSuccess) e = cudaMalloc(&d_lb2, size_t(nvox));
+  if (e == cudaSuccess) e = cudaMalloc(&d_ft, size_t(nvox) * 2);
   if (e == cudaSuccess) e = launch_pack_rows(d_lin, gx, gy, gz, row_words, d_occ, nullptr);
   int nl = 1;
-  if (e == cudaSuccess) e = launch_edt_build(d_occ, row_words, gx, gy, gz, window, d_a, d_b, d_edt, nullptr, &nl);
+  if (e == cudaSuccess) e = launch_ft_build(d_occ, row_words, gx, gy, gz, window, d_a, d_b, d_lb2, d_ft, nullptr, &nl);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   cleanup();
   if (e != cudaSuccess) {
     if (d_occ) cudaFree(d_occ);
-    if (d_edt) cudaFree(d_edt);
+    if (d_lb2) cudaFree(d_lb2);
+    if (d_ft) cudaFree(d_ft);
     return fail(c, e == cudaErrorMemoryAllocation ? SQMP_ERR_NOMEM : SQMP_ERR_CUDA, "set_voxel_grid", e);
   }
   c->launches += nl;
   if (c->d_occ) cudaFree(c->d_occ);  // previous collision object deleted (CC:84-85)
-  if (c->d_edt) cudaFree(c->d_edt);
+  if (c->d_lb2) cudaFree(c->d_lb2);
+  if (c->d_ft) cudaFree(c->d_ft);
   c->d_occ = d_occ;
-  c->d_edt = d_edt;
+  c->d_lb2 = d_lb2;
+  c->d_ft = d_ft;
   GridDev &g = c->gd;
-  g.occ = d_occ; g.edt = d_edt;
+  g.occ = d_occ; g.lb2 = d_lb2; g.ft = d_ft;
   g.gx = gx; g.gy = gy; g.gz = gz; g.row_words = row_words;
   g.ox = origin[0]; g.oy = origin[1]; g.oz = origin[2];
   g.res = res; g.inv_res = 1.0 / res;

@@ -76,7 +76,8 @@ __device__ __forceinline__ void fk_one(const RobotDev &rb, const double (&q)[SQM
     sg0 = rb.ref_seg + 1;
   }
   for (int sg = sg0; sg < rb.n_seg; ++sg) frame_advance<T>(f, rb, sg, q);
-  frame_mul_const<T>(f, rb.ee_tip, rb.ee_tip_kind);
+  if (sizeof(T) == 4) frame_mul_const<T>(f, rb.ee_tip_f, rb.ee_tip_kind);
+  else frame_mul_const<T>(f, rb.ee_tip, rb.ee_tip_kind);
   double R[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) R[i] = double(f.r[i]);

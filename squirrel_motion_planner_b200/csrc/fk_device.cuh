@@ -19,8 +19,37 @@ struct Frame {
 
 template <typename T>
 __device__ __forceinline__ void sincos_t(T x, T *s, T *c);
+// fp64 sincos for joint angles: Cody-Waite reduction by pi/2 in three parts (exact for |k| < 2^20, i.e. |x| < 1e5;
+// larger arguments take the library path) + the fdlibm minimax kernels on [-pi/4, pi/4].  <= ~1.5 ulp, about a
+// quarter of the instructions of the general-purpose library routine (no Payne-Hanek set-up, no special cases).
 template <>
-__device__ __forceinline__ void sincos_t<double>(double x, double *s, double *c) { sincos(x, s, c); }
+__device__ __forceinline__ void sincos_t<double>(double x, double *sn, double *cs) {
+  if (!(fabs(x) < 1.0e5)) {
+    sincos(x, sn, cs);
+    return;
+  }
+  const double kd = rint(x * 0.63661977236758138243);  // 2/pi
+  const int k = int(kd);
+  double r = fma(-kd, 1.57079632673412561417e+00, x);  // pi/2 split: 33 + 33 + 53 bits (fdlibm pio2_1, pio2_2, pio2_3)
+  r = fma(-kd, 6.07710050630396597660e-11, r);
+  r = fma(-kd, 2.02226624871116645580e-21, r);
+  const double z = r * r;
+  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  ps = fma(ps, z, 2.75573137070700676789e-06);
+  ps = fma(ps, z, -1.98412698298579493134e-04);
+  ps = fma(ps, z, 8.33333333332248946124e-03);
+  ps = fma(ps, z, -1.66666666666666324348e-01);
+  const double sr = fma(ps * z, r, r);
+  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  pc = fma(pc, z, -2.75573143513906633035e-07);
+  pc = fma(pc, z, 2.48015872894767294178e-05);
+  pc = fma(pc, z, -1.38888888888741095749e-03);
+  pc = fma(pc, z, 4.16666666666666019037e-02);
+  const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+  const double s0 = (k & 1) ? cr : sr, c0 = (k & 1) ? sr : cr;
+  *sn = (k & 2) ? -s0 : s0;
+  *cs = ((k + 1) & 2) ? -c0 : c0;
+}
 template <>
 __device__ __forceinline__ void sincos_t<float>(float x, float *s, float *c) { sincosf(x, s, c); }
 
@@ -33,8 +62,8 @@ __device__ __forceinline__ void frame_set_translation(Frame<T> &f, T x, T y, T z
 }
 
 // f <- f * Frame(R, t) with the constant 12-vector c (R rows, t); kind: 0 identity, 1 translation, 2 general
-template <typename T>
-__device__ __forceinline__ void frame_mul_const(Frame<T> &f, const double *c, int kind) {
+template <typename T, typename C>
+__device__ __forceinline__ void frame_mul_const(Frame<T> &f, const C *c, int kind) {
   if (kind == 0) return;
   const T tx = T(c[9]), ty = T(c[10]), tz = T(c[11]);
 #pragma unroll
@@ -62,8 +91,8 @@ __device__ __forceinline__ void rot_cols(Frame<T> &f, int ca, int cb, T s, T c) 
 }
 
 // f <- f * Motion(axis, q):  KDL::Joint::pose(q) without its origin (already folded into the pre-frame)
-template <typename T>
-__device__ __forceinline__ void frame_joint_motion(Frame<T> &f, int type, int axis_code, const double *axis, T q) {
+template <typename T, typename C>
+__device__ __forceinline__ void frame_joint_motion(Frame<T> &f, int type, int axis_code, const C *axis, T q) {
   if (type == SQMP_JOINT_TRANS) {
     if (axis_code == AX_GENERAL) {
       const T ax = T(axis[0]) * q, ay = T(axis[1]) * q, az = T(axis[2]) * q;
@@ -110,13 +139,18 @@ __device__ __forceinline__ void frame_joint_motion(Frame<T> &f, int type, int ax
 // One chain segment: f <- f * pre[s] * Motion(axis[s], q[qidx[s]])
 template <typename T>
 __device__ __forceinline__ void frame_advance(Frame<T> &f, const RobotDev &rb, int s, const double (&q)[SQMP_DOF]) {
-  frame_mul_const<T>(f, rb.seg_pre[s], rb.seg_pre_kind[s]);
   // q index is warp-uniform; select without dynamic register indexing
   const int qi = rb.seg_qidx[s];
   double qv = q[0];
 #pragma unroll
   for (int j = 1; j < SQMP_DOF; ++j) qv = (qi == j) ? q[j] : qv;
-  frame_joint_motion<T>(f, rb.seg_type[s], rb.seg_axis_code[s], rb.seg_axis[s], T(qv));
+  if (sizeof(T) == 4) {
+    frame_mul_const<T>(f, rb.seg_pre_f[s], rb.seg_pre_kind[s]);
+    frame_joint_motion<T>(f, rb.seg_type[s], rb.seg_axis_code[s], rb.seg_axis_f[s], T(qv));
+  } else {
+    frame_mul_const<T>(f, rb.seg_pre[s], rb.seg_pre_kind[s]);
+    frame_joint_motion<T>(f, rb.seg_type[s], rb.seg_axis_code[s], rb.seg_axis[s], T(qv));
+  }
 }
 
 // KDL::Rotation::GetQuaternion (frames.cpp) — same branch structure so signs match the reference.

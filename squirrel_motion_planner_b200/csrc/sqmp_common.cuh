@@ -37,8 +37,14 @@ struct RobotDev {
   double ee_tip[12];
   int ee_tip_kind;
   double sph[SQMP_MAX_SPHERES][4];        // cx cy cz r in the segment frame
+  // fp32 copies of the constants (made by the host once; saves the F2F conversions in the float chain)
+  float seg_pre_f[SQMP_MAX_SEG][12];
+  float seg_axis_f[SQMP_MAX_SEG][4];
+  float ee_tip_f[12];
+  float4 sph_f[SQMP_MAX_SPHERES];
   // per-grid derived values (recomputed by sqmp_set_voxel_grid)
-  unsigned char sph_thr8[SQMP_MAX_SPHERES];   // distance-field filter threshold, units of res/4
+  short sph_thr[SQMP_MAX_SPHERES];            // floor((r/res)^2): "lb2 > thr" proves the sphere free (integers, exact);
+                                              // -2 while the sphere's link is disabled (sqmp_set_disabled_links)
   unsigned char sph_ncell[SQMP_MAX_SPHERES];  // ceil(r / res)
   // per-request (sqmp_set_disabled_links)
   uint32_t sph_enabled[SQMP_MAX_SPHERES / 32];
@@ -46,7 +52,10 @@ struct RobotDev {
 
 struct GridDev {
   const uint32_t *occ;   // bit-packed rows along x, row_words words per (j,k) row (>= 1 zero pad word)
-  const uint8_t *edt;    // [gz][gy][gx]: floor(4 * box-to-box distance to the nearest occupied voxel / res), <= 255
+  // Feature transform of the occupancy, [gz][gy][gx] each.  For cell C let O* be the occupied cell that minimises the
+  // squared box-to-box distance bb2(C,O) = sum_a max(|o_a|-1,0)^2 (o = O - C; ties: smaller centre distance):
+  const uint8_t *lb2;    //   min(bb2(C,O*), 255); 255 also when nothing is occupied within the build window
+  const uint16_t *ft;    //   (ox+15) | (oy+15)<<5 | (oz+15)<<10 of O*, 0xFFFF when none
   int gx, gy, gz, row_words;
   int has_grid;
   double ox, oy, oz, res, inv_res;
@@ -68,8 +77,9 @@ cudaError_t launch_get_collisions(const RobotDev &rb, const GridDev &gd, const S
                                   const double *d_q, uint8_t *d_sphere_hit, uint8_t *d_pair_hit, cudaStream_t st);
 cudaError_t launch_fk(const RobotDev &rb, const double *d_q, int64_t S, double *d_out, int fk_precision,
                       cudaStream_t st);
-cudaError_t launch_edt_build(const uint32_t *d_occ, int row_words, int gx, int gy, int gz, int window,
-                             uint8_t *d_tmp_a, uint16_t *d_tmp_b, uint8_t *d_edt, cudaStream_t st, int *n_launch);
+cudaError_t launch_ft_build(const uint32_t *d_occ, int row_words, int gx, int gy, int gz, int window,
+                            int8_t *d_tmp_a, uint16_t *d_tmp_b, uint8_t *d_lb2, uint16_t *d_ft, cudaStream_t st,
+                            int *n_launch);
 cudaError_t launch_pack_rows(const uint32_t *d_bits_linear, int gx, int gy, int gz, int row_words, uint32_t *d_occ,
                              cudaStream_t st);
 

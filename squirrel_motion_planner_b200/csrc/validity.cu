@@ -6,8 +6,10 @@
 // The reference walks 39 links and calls fcl::collide per link per state, serially, with early exits.  Here one
 // thread owns one state: it walks the 8 folded chain segments keeping a single frame in registers, transforms the
 // spheres of each rigid group as soon as that group's frame exists, and tests every sphere against
-//   (1) a byte distance field (conservative "certainly free" filter, one L2 gather), then, only if that fails,
-//   (2) the exact test "some occupied voxel AABB within r of the centre" by scanning bit-packed x-rows:
+//   (1) a byte field: squared box-to-box distance from the centre's cell to the nearest occupied cell (exact lower
+//       bound of the point distance: "certainly free", one gather), then, only if that fails,
+//   (2) the offset of that nearest occupied cell (16-bit gather): an exact upper bound ("certainly hit"), then
+//   (3) the exact test "some occupied voxel AABB within r of the centre" by scanning bit-packed x-rows:
 //       per (j,k) row the admissible x-interval is closed-form, so a row costs one (rarely two) word loads.
 // The verdicts of a warp are packed by one ballot into one 32-bit word — the mask layout of the C ABI.
 #include "fk_device.cuh"
@@ -51,12 +53,40 @@ __device__ __forceinline__ bool exact_scan(const GridDev &g, double ux, double u
   return false;
 }
 
+// `count` consecutive rows of the (j,k) scan box of one sphere, starting at row (j0 + jj, k), j fastest.
+__device__ __forceinline__ bool scan_rows(const GridDev &g, double ux, double uy, double uz, double rg, int j0, int nj,
+                                          int k, int jj, int count) {
+  const double r2 = rg * rg;
+  for (int n = 0; n < count; ++n) {
+    const double kd = double(k), jd = double(j0 + jj);
+    const double dz = fmax(fmax(kd - uz, uz - (kd + 1.0)), 0.0);
+    const double dy = fmax(fmax(jd - uy, uy - (jd + 1.0)), 0.0);
+    const double rem = fma(-dy, dy, fma(-dz, dz, r2));
+    if (rem >= 0.0) {
+      const double w = sqrt(rem);
+      int i0 = max(__double2int_ru(ux - w) - 1, 0);
+      const int i1 = min(__double2int_rd(ux + w), g.gx - 1);
+      const uint32_t *row = g.occ + (size_t(k) * g.gy + size_t(j0 + jj)) * g.row_words;
+      while (i0 <= i1) {
+        const int sh = i0 & 31;
+        const int m = min(32 - sh, i1 - i0 + 1);
+        const uint32_t bits = (row[i0 >> 5] >> sh) & (m >= 32 ? ~0u : ((1u << m) - 1u));
+        if (bits) return true;
+        i0 += m;
+      }
+    }
+    if (++jj == nj) { jj = 0; ++k; }
+  }
+  return false;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1
 // ------------------------------------------------------------------------------------------------
 constexpr int K1_THREADS = 128;
 constexpr int K1_QCAP = 64;       // deferred exact-scan items per warp (drained 32 at a time)
-constexpr int K1_BATCH = 4;       // spheres whose distance-field gathers are in flight together
+constexpr int K1_CHUNK = 12;      // rows of an exact scan handed to one lane at a time
+constexpr int K1_BATCH = 4;       // spheres whose field gathers are in flight together
 constexpr unsigned FULL = 0xffffffffu;
 
 struct WarpQueue {   // shared memory, one per warp
@@ -64,16 +94,88 @@ struct WarpQueue {   // shared memory, one per warp
   int info[K1_QCAP];   // sphere index << 8 | owner lane
 };
 
+// round-to-nearest integer of x without F2I: the integer lands in the low mantissa bits of (x + 1.5 * 2^mant)
+__device__ __forceinline__ int rn_int(double x) { return __double2loint(x + 6755399441055744.0); }       // |x| < 2^31
+__device__ __forceinline__ int rn_int(float x) { return __float_as_int(x + 12582912.0f) - 0x4B400000; }   // |x| < 2^22
+
+// gap between coordinate f in [0,1] of the centre's own cell and the unit cube at cell offset o
+__device__ __forceinline__ float axis_gap_off(int o, float f) {
+  return o > 0 ? float(o) - f : (o < 0 ? f - float(o) - 1.0f : 0.0f);
+}
+
+// Decide the queued items [base, base+n); returns the verdicts as a mask over the owning lanes.  Items differ by
+// two orders of magnitude in work (a 1-cell finger sphere scans ~9 rows, the 5-cell head sphere ~150), so the
+// unit handed to a lane is not an item but a chunk of <= K1_CHUNK rows: lane l describes item l, a warp prefix
+// sum numbers the chunks, and every lane finds the item of its chunk by a 5-step shuffle binary search.
+// One copy in the binary (called from the two drain sites of K1): keeps the hot loop inside the instruction cache.
+__device__ __noinline__ unsigned drain_queue(const GridDev &gd, const WarpQueue *wq, int base, int n, unsigned known) {
+  const int lane = threadIdx.x & 31;
+  int nj = 1, j0 = 0, k0 = 0, R = 0, c = 0;
+  if (lane < n) {
+    const int owner = wq->info[base + lane] & 31;
+    if (!((known >> owner) & 1u)) {
+      const double uy = wq->y[base + lane], uz = wq->z[base + lane], rg = wq->r[base + lane];
+      k0 = max(__double2int_rd(uz - rg), 0);
+      j0 = max(__double2int_rd(uy - rg), 0);
+      const int k1 = min(__double2int_rd(uz + rg), gd.gz - 1), j1 = min(__double2int_rd(uy + rg), gd.gy - 1);
+      nj = max(j1 - j0 + 1, 1);
+      R = (j1 >= j0 && k1 >= k0) ? nj * (k1 - k0 + 1) : 0;
+      c = (R + K1_CHUNK - 1) / K1_CHUNK;
+    }
+  }
+  int incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int total = __shfl_sync(FULL, incl, 31);
+  unsigned hm = 0;
+  for (int t0 = 0; t0 < total; t0 += 32) {
+    const int t = t0 + lane;
+    int m = 0;  // first item whose inclusive chunk count exceeds t
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const int v = __shfl_sync(FULL, incl, m + step - 1);
+      if (v <= t) m += step;
+    }
+    const int ex_m = __shfl_sync(FULL, incl - c, m), nj_m = __shfl_sync(FULL, nj, m), j0_m = __shfl_sync(FULL, j0, m),
+              k0_m = __shfl_sync(FULL, k0, m), R_m = __shfl_sync(FULL, R, m);
+    if (t < total) {
+      const double ux = wq->x[base + m], uy = wq->y[base + m], uz = wq->z[base + m], rg = wq->r[base + m];
+      const int r0 = (t - ex_m) * K1_CHUNK, r1 = min(r0 + K1_CHUNK, R_m);
+      const int kk = r0 / nj_m;
+      if (scan_rows(gd, ux, uy, uz, rg, j0_m, nj_m, k0_m + kk, r0 - kk * nj_m, r1 - r0))
+        hm |= 1u << (wq->info[base + m] & 31);
+    }
+  }
+  return __reduce_or_sync(FULL, hm);
+}
+
+template <typename T> struct K1Cfg;
+template <> struct K1Cfg<double> { static constexpr int MIN_BLOCKS = 4; };
+template <> struct K1Cfg<float> { static constexpr int MIN_BLOCKS = 5; };
+
 // MODE 0: verdict bit per state.  MODE 1 (diagnostics, one state): per-sphere / per-pair hits, no early exit.
 //
 // rb is the GRID-UNIT copy of the robot (translations, sphere centres and radii divided by res, root offset
 // measured from the grid origin), so a sphere centre comes out of the chain directly in voxel coordinates.
+// T = double: the whole chain in fp64 in absolute grid coordinates.  T = float: the prismatic base in fp64, the
+// rotating part of the chain in fp32 in coordinates relative to the base's own cell (|values| < ~40 cells, so one
+// float ulp is < 4e-6 cells = 2e-7 m; error budget in DESIGN.md).
 //
-// Divergence control: the cheap filter (one byte gather from the distance field) runs in lockstep for all lanes;
-// the few spheres it cannot clear are NOT scanned on the spot (that left ~4 of 32 lanes active) but pushed, by
-// ballot compaction, on a per-warp queue in shared memory, and scanned 32 at a time with one item per lane.
+// Per sphere, in lockstep for all 32 states of a warp:
+//   1. centre = R l + p, cell index by the round-to-nearest magic-add (no F2I);
+//   2. one byte gather  lb2 = squared box-to-box distance (cells, integer) from the centre's cell to the nearest
+//      occupied cell.  Every point of the cell is at least that far from every occupied cube, so
+//      lb2 > floor(rg^2) proves the sphere free: ~89 % of the spheres end here;
+//   3. otherwise one 16-bit gather = offset of that nearest occupied cell O*: dist(centre, O*) is an upper bound of
+//      the true distance, dist(centre, O*) <= rg proves a hit (all but ~0.1 % of the hits);
+//   4. what is left (lb <= rg < dist(centre,O*): ~1.5 spheres per state) is pushed by ballot compaction on a
+//      per-warp queue in shared memory and decided 32 items at a time by the exact row scan (drain_queue).
+// Steps 3-4 exist once in the code: each lane serialises its own pending spheres of a batch through them.
 template <typename T, bool EDGES, int MODE>
-__global__ void __launch_bounds__(K1_THREADS)
+__global__ void __launch_bounds__(K1_THREADS, K1Cfg<T>::MIN_BLOCKS)
 k1_check_states(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd,
                 const SelfPair *__restrict__ pairs, int n_pairs, const double *__restrict__ q_in,
                 const double *__restrict__ q_end, int num_points, int64_t S, unsigned flags,
@@ -111,9 +213,14 @@ k1_check_states(const __grid_constant__ RobotDev rb, const __grid_constant__ Gri
     q[0] = v0.x; q[1] = v0.y; q[2] = v0.z; q[3] = v0.w;
     q[4] = v1.x; q[5] = v1.y; q[6] = v1.z; q[7] = v1.w;
   }
-  // prismatic joint values are lengths: into grid units with everything else
+  // prismatic joint values are lengths: into grid units with everything else.  A state with a non-finite or
+  // absurd joint value cannot reach the grid (and would break the integer cell arithmetic): map check skipped.
+  bool sane = true;
 #pragma unroll
-  for (int j = 0; j < SQMP_DOF; ++j) q[j] = ((rb.trans_mask >> j) & 1) ? q[j] * rb.len_scale : q[j];
+  for (int j = 0; j < SQMP_DOF; ++j) {
+    q[j] = ((rb.trans_mask >> j) & 1) ? q[j] * rb.len_scale : q[j];
+    sane = sane && (fabs(q[j]) < 1.0e9);
+  }
 
   // ---- base reference point = position after the leading prismatic run ----
   double pref[3] = {rb.root_off[0], rb.root_off[1], rb.root_off[2]};
@@ -128,91 +235,133 @@ k1_check_states(const __grid_constant__ RobotDev rb, const __grid_constant__ Gri
     }
   }
 
-  // ---- chain walk; T = double walks the whole chain, T = float walks the part after the prismatic base
-  //      relative to pref (host guarantees the leading run is translation-only) ----
+  // ---- chain walk.  Working coordinates w: absolute (T = double, bc = 0) or relative to the corner of the
+  //      base's cell bc (T = float; the host guarantees the leading run of the chain is translation-only) ----
   Frame<T> f;
-  double off[3];
+  int bc[3] = {0, 0, 0};
+  T wref[3];   // pref in working coordinates (self-collision offsets are taken relative to it)
   int sg0;
   if (sizeof(T) == 8) {
     frame_set_translation<T>(f, T(rb.root_off[0]), T(rb.root_off[1]), T(rb.root_off[2]));
-    off[0] = off[1] = off[2] = 0.0;
+    wref[0] = T(pref[0]); wref[1] = T(pref[1]); wref[2] = T(pref[2]);
     sg0 = 0;
   } else {
-    frame_set_translation<T>(f, T(0), T(0), T(0));
-    off[0] = pref[0]; off[1] = pref[1]; off[2] = pref[2];
+    if (!sane) pref[0] = pref[1] = pref[2] = 0.0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      bc[a] = rn_int(pref[a] - 0.5);
+      wref[a] = T(pref[a] - double(bc[a]));
+    }
+    frame_set_translation<T>(f, wref[0], wref[1], wref[2]);
     sg0 = rb.ref_seg + 1;
   }
 
-  // scan the queued items [base, base+n) with one item per lane; route the verdicts back to the owning lanes
-  auto drain = [&](int base, int n) {
-    __syncwarp();
-    const unsigned known = __ballot_sync(FULL, hit);
-    bool h = false;
-    int owner = 0;
-    if (lane < n) {
-      const int info = wq->info[base + lane];
-      owner = info & 31;
-      if (!((known >> owner) & 1u))
-        h = exact_scan(gd, wq->x[base + lane], wq->y[base + lane], wq->z[base + lane], wq->r[base + lane]);
-    }
-    const unsigned hm = __reduce_or_sync(FULL, h ? (1u << owner) : 0u);
-    hit |= (hm >> lane) & 1u;
-    __syncwarp();
-  };
-
+  const unsigned plane = unsigned(gd.gy) * unsigned(gd.gx);   // host guarantees gx*gy*gz < 2^32
+  bool live = do_map && sane;   // this lane still needs map tests (MODE 0: until its first hit)
   for (int sg = -1; sg < rb.n_seg; ++sg) {
     if (sg >= sg0) frame_advance<T>(f, rb, sg, q);
     else if (sg >= 0) continue;
     const int b = rb.seg_sph_end[sg + 1], e = rb.seg_sph_end[sg + 2];
+    if (b == e) continue;
+    // translation of this group minus half a cell: round-to-nearest of (w - 0.5) is the cell index floor(w)
+    const T pm0 = f.p[0] - T(0.5), pm1 = f.p[1] - T(0.5), pm2 = f.p[2] - T(0.5);
     for (int i0 = b; i0 < e; i0 += K1_BATCH) {
-      double ux[K1_BATCH], uy[K1_BATCH], uz[K1_BATCH];
-      int ev[K1_BATCH];
-      bool need[K1_BATCH];
+      T wm[K1_BATCH][3];        // centre - 0.5 (working coordinates)
+      int ci[K1_BATCH][3];      // cell of the centre (working coordinates)
+      int lbv[K1_BATCH];
 #pragma unroll
-      for (int u = 0; u < K1_BATCH; ++u) {  // transform + gather (independent loads, issued back to back)
-        const int i = min(i0 + u, e - 1);
-        const T lx = T(rb.sph[i][0]), ly = T(rb.sph[i][1]), lz = T(rb.sph[i][2]);
-        const T wx = fma(f.r[0], lx, fma(f.r[1], ly, fma(f.r[2], lz, f.p[0])));
-        const T wy = fma(f.r[3], lx, fma(f.r[4], ly, fma(f.r[5], lz, f.p[1])));
-        const T wz = fma(f.r[6], lx, fma(f.r[7], ly, fma(f.r[8], lz, f.p[2])));
-        ux[u] = double(wx) + off[0]; uy[u] = double(wy) + off[1]; uz[u] = double(wz) + off[2];
-        if (do_self && i0 + u < e) {
-          const int n = rb.n_spheres;
-          s_rel[(0 * n + i) * blockDim.x + threadIdx.x] = float(ux[u] - pref[0]);
-          s_rel[(1 * n + i) * blockDim.x + threadIdx.x] = float(uy[u] - pref[1]);
-          s_rel[(2 * n + i) * blockDim.x + threadIdx.x] = float(uz[u] - pref[2]);
+      for (int u = 0; u < K1_BATCH; ++u) {  // transform + byte gather (independent loads, issued back to back)
+        const int i = min(i0 + u, e - 1);   // the tail of a group repeats its last sphere (skipped below)
+        T lx, ly, lz;
+        if (sizeof(T) == 8) {
+          lx = T(rb.sph[i][0]); ly = T(rb.sph[i][1]); lz = T(rb.sph[i][2]);
+        } else {
+          const float4 c4 = rb.sph_f[i];
+          lx = T(c4.x); ly = T(c4.y); lz = T(c4.z);
         }
-        // saturating conversions: anything absurdly far lands outside every range test below
-        const int ix = __double2int_rd(ux[u]), iy = __double2int_rd(uy[u]), iz = __double2int_rd(uz[u]);
-        const int pad = rb.sph_ncell[i] + 1;
-        const bool near_grid = unsigned(ix + pad) < unsigned(gd.gx + 2 * pad) &&
-                               unsigned(iy + pad) < unsigned(gd.gy + 2 * pad) &&
-                               unsigned(iz + pad) < unsigned(gd.gz + 2 * pad);
+        wm[u][0] = fma(f.r[0], lx, fma(f.r[1], ly, fma(f.r[2], lz, pm0)));
+        wm[u][1] = fma(f.r[3], lx, fma(f.r[4], ly, fma(f.r[5], lz, pm1)));
+        wm[u][2] = fma(f.r[6], lx, fma(f.r[7], ly, fma(f.r[8], lz, pm2)));
+        ci[u][0] = rn_int(wm[u][0]); ci[u][1] = rn_int(wm[u][1]); ci[u][2] = rn_int(wm[u][2]);
+        const int ix = ci[u][0] + bc[0], iy = ci[u][1] + bc[1], iz = ci[u][2] + bc[2];
         const bool inside = unsigned(ix) < unsigned(gd.gx) && unsigned(iy) < unsigned(gd.gy) && unsigned(iz) < unsigned(gd.gz);
-        const bool enabled = (MODE == 1) || ((rb.sph_enabled[i >> 5] >> (i & 31)) & 1u);
-        need[u] = do_map && enabled && near_grid && (i0 + u < e) && (MODE == 1 || !hit);
-        // box-to-box distance of this cell to the nearest occupied cell bounds dist(c, occupied) from below
-        ev[u] = (need[u] && inside) ? int(gd.edt[(size_t(iz) * gd.gy + iy) * gd.gx + ix]) : 0;
+        // squared box-to-box distance of this cell to the nearest occupied cell: a lower bound of dist(centre, occupied)^2
+        lbv[u] = inside ? int(gd.lb2[unsigned(iz) * plane + unsigned(iy) * unsigned(gd.gx) + unsigned(ix)]) : -1;
       }
+      if (do_self) {
+        const int n = rb.n_spheres;
 #pragma unroll
-      for (int u = 0; u < K1_BATCH; ++u) {  // filter verdict; survivors are queued for the exact scan
-        const int i = min(i0 + u, e - 1);
-        const bool nd = need[u] && ev[u] <= int(rb.sph_thr8[i]);
-        if (MODE == 1) {
-          if (nd) sphere_hit[i] = exact_scan(gd, ux[u], uy[u], uz[u], rb.sph[i][3]) ? 1 : 0;
-          continue;
+        for (int u = 0; u < K1_BATCH; ++u) {
+          const int i = min(i0 + u, e - 1);
+          s_rel[(0 * n + i) * blockDim.x + threadIdx.x] = float(wm[u][0] - wref[0]) + 0.5f;
+          s_rel[(1 * n + i) * blockDim.x + threadIdx.x] = float(wm[u][1] - wref[1]) + 0.5f;
+          s_rel[(2 * n + i) * blockDim.x + threadIdx.x] = float(wm[u][2] - wref[2]) + 0.5f;
         }
-        const unsigned m = __ballot_sync(FULL, nd);
+      }
+      // sph_thr[i] = floor(rg^2), or -2 for a sphere whose link is disabled (lbv is -1 outside the grid): an
+      // integer compare, and ~89 % of the spheres end here
+      unsigned pend = 0;
+#pragma unroll
+      for (int u = 0; u < K1_BATCH; ++u) {
+        const int i = min(i0 + u, e - 1);
+        const int thr = (MODE == 1) ? int(rb.sph[i][3] * rb.sph[i][3] + 1e-9) : int(rb.sph_thr[i]);
+        if (lbv[u] <= thr && (u == 0 || i0 + u < e)) pend |= 1u << u;
+      }
+      if (!live) pend = 0;
+      while (__any_sync(FULL, pend != 0)) {
+        // every lane with pending spheres takes its first one through the single copy of steps 3-4
+        const int u = __ffs(pend) - 1;
+        pend &= pend - 1;
+        T cx = wm[0][0], cy = wm[0][1], cz = wm[0][2];
+        int jx = ci[0][0], jy = ci[0][1], jz = ci[0][2], lb = lbv[0];
+#pragma unroll
+        for (int v = 1; v < K1_BATCH; ++v) {
+          const bool sel = u == v;
+          cx = sel ? wm[v][0] : cx; cy = sel ? wm[v][1] : cy; cz = sel ? wm[v][2] : cz;
+          jx = sel ? ci[v][0] : jx; jy = sel ? ci[v][1] : jy; jz = sel ? ci[v][2] : jz;
+          lb = sel ? lbv[v] : lb;
+        }
+        const int i = min(i0 + max(u, 0), e - 1);
+        const double rg = rb.sph[i][3];
+        bool amb = false;   // neither bound decides: exact scan
+        if (u >= 0 && live) {
+          if (MODE == 1) {
+            sphere_hit[i] = exact_scan(gd, double(cx) + (0.5 + double(bc[0])), double(cy) + (0.5 + double(bc[1])),
+                                       double(cz) + (0.5 + double(bc[2])), rg) ? 1 : 0;
+          } else if (lb >= 0) {
+            const unsigned v = gd.ft[unsigned(jz + bc[2]) * plane + unsigned(jy + bc[1]) * unsigned(gd.gx) + unsigned(jx + bc[0])];
+            const float fx = float(cx - T(jx)) + 0.5f, fy = float(cy - T(jy)) + 0.5f, fz = float(cz - T(jz)) + 0.5f;
+            const float gx_ = axis_gap_off(int(v & 31u) - 15, fx), gy_ = axis_gap_off(int((v >> 5) & 31u) - 15, fy),
+                        gz_ = axis_gap_off(int((v >> 10) & 31u) - 15, fz);
+            const float ub2 = fmaf(gx_, gx_, fmaf(gy_, gy_, gz_ * gz_));
+            const float r2 = float(rg) * float(rg);
+            // float slack 1e-5 rg^2 (~2.5e-7 m at contact, far inside the 1e-5 m band): closer calls go to the scan
+            if (ub2 <= r2 * 0.99999f) { hit = true; live = false; pend = 0; }
+            else amb = true;
+          } else {
+            const int pad = rb.sph_ncell[i] + 1;   // centre outside the grid: can the sphere still reach it?
+            amb = unsigned(jx + bc[0] + pad) < unsigned(gd.gx + 2 * pad) && unsigned(jy + bc[1] + pad) < unsigned(gd.gy + 2 * pad) &&
+                  unsigned(jz + bc[2] + pad) < unsigned(gd.gz + 2 * pad);
+          }
+        }
+        if (MODE == 1) continue;
+        const unsigned m = __ballot_sync(FULL, amb);
         if (m) {
-          if (nd) {
+          if (amb) {
             const int pos = qcount + __popc(m & ((1u << lane) - 1u));
-            wq->x[pos] = ux[u]; wq->y[pos] = uy[u]; wq->z[pos] = uz[u]; wq->r[pos] = rb.sph[i][3];
+            wq->x[pos] = double(cx) + (0.5 + double(bc[0]));
+            wq->y[pos] = double(cy) + (0.5 + double(bc[1]));
+            wq->z[pos] = double(cz) + (0.5 + double(bc[2]));
+            wq->r[pos] = rg;
             wq->info[pos] = (i << 8) | lane;
           }
           qcount += __popc(m);
           if (qcount >= 32) {
-            drain(qcount - 32, 32);
+            __syncwarp();
+            const unsigned hm = drain_queue(gd, wq, qcount - 32, 32, __ballot_sync(FULL, hit));
+            __syncwarp();
             qcount -= 32;
+            if ((hm >> lane) & 1u) { hit = true; live = false; pend = 0; }
           }
         }
       }
@@ -221,7 +370,9 @@ k1_check_states(const __grid_constant__ RobotDev rb, const __grid_constant__ Gri
     if (MODE == 0 && !do_self && qcount == 0 && __all_sync(FULL, hit)) break;
   }
   if (MODE == 0 && qcount > 0) {
-    drain(0, qcount);
+    __syncwarp();
+    const unsigned hm = drain_queue(gd, wq, 0, qcount, __ballot_sync(FULL, hit));
+    hit |= (hm >> lane) & 1u;
     qcount = 0;
   }
 
@@ -347,67 +498,77 @@ cudaError_t launch_pack_rows(const uint32_t *d_bits_linear, int gx, int gy, int 
   return cudaGetLastError();
 }
 
-// Squared box-to-box distance (in cells) from every cell to the nearest occupied cell, separable:
-//   cost of an index offset d along one axis is max(|d|-1, 0)^2  (gap between two unit boxes).
-// Window W caps the search; a cell with nothing inside the window gets the (still valid) lower bound W.
-__global__ void k_edt_x(const uint32_t *__restrict__ occ, int row_words, int gx, int64_t rows, int W,
-                        uint8_t *__restrict__ a) {
+// Feature transform: for every cell the occupied cell O* minimising the squared box-to-box distance
+//   bb2 = sum_a max(|o_a|-1, 0)^2   (gap between two unit boxes per axis), ties: smaller centre distance sum_a o_a^2,
+// found exactly by three separable passes: along one axis both keys are monotone in |o_a|, so the nearest occupied
+// cell of a row (pass x) is the only candidate that row can contribute to any cell of its column (pass y), and the
+// best (ox,oy) of a plane is the only candidate the plane can contribute along z.  Window W caps the search.
+constexpr int FT_NONE8 = -128;
+__device__ __forceinline__ int bbgap2(int d) { const int g = max(abs(d) - 1, 0); return g * g; }
+
+__global__ void k_ft_x(const uint32_t *__restrict__ occ, int row_words, int gx, int64_t rows, int W,
+                       int8_t *__restrict__ a) {
   const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= rows * gx) return;
   const int i = int(idx % gx);
   const uint32_t *row = occ + (idx / gx) * row_words;
-  int best = W;
-  for (int d = 0; d <= W && best == W; ++d) {
+  int best = FT_NONE8;
+  for (int d = 0; d <= W && best == FT_NONE8; ++d) {
     const int l = i - d, r = i + d;
-    const bool hl = l >= 0 && ((row[l >> 5] >> (l & 31)) & 1u);
-    const bool hr = r < gx && ((row[r >> 5] >> (r & 31)) & 1u);
-    if (hl || hr) best = max(d - 1, 0);
+    if (r < gx && ((row[r >> 5] >> (r & 31)) & 1u)) best = d;
+    else if (l >= 0 && ((row[l >> 5] >> (l & 31)) & 1u)) best = -d;
   }
-  a[idx] = uint8_t(best);
+  a[idx] = int8_t(best);
 }
-__global__ void k_edt_y(const uint8_t *__restrict__ a, int gx, int gy, int gz, int W, uint16_t *__restrict__ b) {
+__global__ void k_ft_y(const int8_t *__restrict__ a, int gx, int gy, int gz, int W, uint16_t *__restrict__ b) {
   const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= int64_t(gx) * gy * gz) return;
   const int i = int(idx % gx), j = int((idx / gx) % gy);
   const int64_t k = idx / (int64_t(gx) * gy);
-  int best = W * W;
+  int best = 0x7fffffff, bx = 0, by = 0;
   for (int d = -W; d <= W; ++d) {
     const int jj = j + d;
     if (jj < 0 || jj >= gy) continue;
-    const int g = max(abs(d) - 1, 0);
-    const int av = a[(k * gy + jj) * gx + i];
-    best = min(best, av * av + g * g);
+    const int ox = a[(k * gy + jj) * gx + i];
+    if (ox == FT_NONE8) continue;
+    const int key = (bbgap2(ox) + bbgap2(d)) * 4096 + ox * ox + d * d;
+    if (key < best) { best = key; bx = ox; by = d; }
   }
-  b[idx] = uint16_t(min(best, W * W));
+  b[idx] = best == 0x7fffffff ? uint16_t(0xFFFF) : uint16_t((bx + 128) | ((by + 128) << 8));
 }
-__global__ void k_edt_z(const uint16_t *__restrict__ b, int gx, int gy, int gz, int W, uint8_t *__restrict__ edt) {
+__global__ void k_ft_z(const uint16_t *__restrict__ b, int gx, int gy, int gz, int W, uint8_t *__restrict__ lb2,
+                       uint16_t *__restrict__ ft) {
   const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t plane = int64_t(gx) * gy;
   if (idx >= plane * gz) return;
   const int k = int(idx / plane);
   const int64_t ij = idx % plane;
-  int best = W * W;
+  int best = 0x7fffffff, bx = 0, by = 0, bz = 0;
   for (int d = -W; d <= W; ++d) {
     const int kk = k + d;
     if (kk < 0 || kk >= gz) continue;
-    const int g = max(abs(d) - 1, 0);
-    best = min(best, int(b[kk * plane + ij]) + g * g);
+    const unsigned v = b[kk * plane + ij];
+    if (v == 0xFFFFu) continue;
+    const int ox = int(v & 255u) - 128, oy = int(v >> 8) - 128;
+    const int key = (bbgap2(ox) + bbgap2(oy) + bbgap2(d)) * 4096 + ox * ox + oy * oy + d * d;
+    if (key < best) { best = key; bx = ox; by = oy; bz = d; }
   }
-  best = min(best, W * W);
-  // floor(4 * sqrt(best)) = isqrt(16 * best), exact in integers
-  const int t = 16 * best;
-  int r = int(sqrtf(float(t)));
-  while (r * r > t) --r;
-  while ((r + 1) * (r + 1) <= t) ++r;
-  edt[idx] = uint8_t(min(r, 255));
+  if (best == 0x7fffffff) {
+    lb2[idx] = 255;
+    ft[idx] = 0xFFFF;
+  } else {
+    lb2[idx] = uint8_t(min(best >> 12, 255));
+    ft[idx] = uint16_t((bx + 15) | ((by + 15) << 5) | ((bz + 15) << 10));
+  }
 }
-cudaError_t launch_edt_build(const uint32_t *d_occ, int row_words, int gx, int gy, int gz, int window,
-                             uint8_t *d_tmp_a, uint16_t *d_tmp_b, uint8_t *d_edt, cudaStream_t st, int *n_launch) {
+cudaError_t launch_ft_build(const uint32_t *d_occ, int row_words, int gx, int gy, int gz, int window,
+                            int8_t *d_tmp_a, uint16_t *d_tmp_b, uint8_t *d_lb2, uint16_t *d_ft, cudaStream_t st,
+                            int *n_launch) {
   const int64_t n = int64_t(gx) * gy * gz;
   const unsigned blocks = unsigned((n + 255) / 256);
-  k_edt_x<<<blocks, 256, 0, st>>>(d_occ, row_words, gx, int64_t(gy) * gz, window, d_tmp_a);
-  k_edt_y<<<blocks, 256, 0, st>>>(d_tmp_a, gx, gy, gz, window, d_tmp_b);
-  k_edt_z<<<blocks, 256, 0, st>>>(d_tmp_b, gx, gy, gz, window, d_edt);
+  k_ft_x<<<blocks, 256, 0, st>>>(d_occ, row_words, gx, int64_t(gy) * gz, window, d_tmp_a);
+  k_ft_y<<<blocks, 256, 0, st>>>(d_tmp_a, gx, gy, gz, window, d_tmp_b);
+  k_ft_z<<<blocks, 256, 0, st>>>(d_tmp_b, gx, gy, gz, window, d_lb2, d_ft);
   if (n_launch) *n_launch += 3;
   return cudaGetLastError();
 }
