@@ -24,6 +24,8 @@ struct Ctx {
   RobotDev rb_grid;   // grid units of the current voxel grid (validity kernel); == rb while no grid is set
   GridDev gd;
   int sph_link[SQMP_MAX_SPHERES];
+  int slot_sph[SQMP_MAX_SLOTS];   // K1 slot -> sphere index, -1 for a pad
+  int sph_slot[SQMP_MAX_SPHERES];
   int n_pairs = 0;
   SelfPair *d_pairs = nullptr;
   std::vector<SelfPair> h_pairs;
@@ -103,7 +105,7 @@ static void refresh_float_copies(RobotDev &r) {
     r.seg_axis_f[s][3] = 0.0f;
   }
   for (int i = 0; i < 12; ++i) r.ee_tip_f[i] = float(r.ee_tip[i]);
-  for (int i = 0; i < SQMP_MAX_SPHERES; ++i)
+  for (int i = 0; i < SQMP_MAX_SLOTS; ++i)
     r.sph_f[i] = make_float4(float(r.sph[i][0]), float(r.sph[i][1]), float(r.sph[i][2]), float(r.sph[i][3]));
 }
 
@@ -121,29 +123,48 @@ static int refresh_grid_robot(Ctx *c) {
   for (int s = 0; s < rb.n_seg; ++s)
     for (int i = 9; i < 12; ++i) g.seg_pre[s][i] = rb.seg_pre[s][i] * inv;
   for (int i = 0; i < 3; ++i) g.root_off[i] = (rb.root_off[i] - o[i]) * inv;
-  for (int i = 0; i < rb.n_spheres; ++i) {
-    for (int k = 0; k < 4; ++k) g.sph[i][k] = rb.sph[i][k] * inv;
+  // slots: every group's spheres padded to a multiple of 4 with copies of its last sphere
+  int n_slots = 0;
+  for (int s = 0; s <= SQMP_MAX_SEG; ++s) {   // group s-1 (s = 0: the root) owns spheres [end[s], end[s+1])
+    g.seg_sph_end[s] = n_slots;
+    const int b = rb.seg_sph_end[s], e = rb.seg_sph_end[s + 1];
+    for (int i = b; i < e; ++i) {
+      c->slot_sph[n_slots] = i;
+      c->sph_slot[i] = n_slots++;
+    }
+    while (e > b && (n_slots & 3)) c->slot_sph[n_slots++] = -(e - 1) - 1;   // pad: -(sphere copied)-1
+  }
+  g.seg_sph_end[SQMP_MAX_SEG + 1] = n_slots;
+  g.n_spheres = n_slots;
+  for (int sl = 0; sl < n_slots; ++sl) {
+    const bool pad_slot = c->slot_sph[sl] < 0;
+    const int i = pad_slot ? -c->slot_sph[sl] - 1 : c->slot_sph[sl];
+    if (pad_slot) c->slot_sph[sl] = -1;
+    for (int k = 0; k < 4; ++k) g.sph[sl][k] = rb.sph[i][k] * inv;
     const double r = rb.sph[i][3];
     if (!has) {
-      g.sph_thr[i] = -2;
-      g.sph_ncell[i] = 0;
+      g.sph_thr[sl] = -2;
+      g.sph_ncell[sl] = 0;
       continue;
     }
     const double rc = r * inv;  // radius in cells; sqmp_set_voxel_grid guarantees rc <= 13, so rc^2 < 255
     const double t = std::floor(rc * rc + 1e-9);
-    const bool enabled = (rb.sph_enabled[i >> 5] >> (i & 31)) & 1u;
-    g.sph_thr[i] = enabled ? short(t > 254.0 ? 254.0 : t) : short(-2);
+    const bool enabled = !pad_slot && ((rb.sph_enabled[i >> 5] >> (i & 31)) & 1u);
+    g.sph_thr[sl] = enabled ? short(t > 254.0 ? 254.0 : t) : short(-2);
     const double n = std::ceil(r / c->gd.res);
-    g.sph_ncell[i] = (unsigned char)(n > 250.0 ? 250.0 : n);
+    g.sph_ncell[sl] = (unsigned char)(n > 250.0 ? 250.0 : n);
   }
   refresh_float_copies(g);
   refresh_float_copies(c->rb);
+  std::vector<SelfPair> dev_pairs(c->h_pairs);   // device copy: slot indices, radii in grid units
   for (int p = 0; p < c->n_pairs; ++p) {
     const double rs = (rb.sph[c->h_pairs[p].a][3] + rb.sph[c->h_pairs[p].b][3]) * inv;
-    c->h_pairs[p].rsum2 = float(rs * rs);
+    dev_pairs[p].rsum2 = float(rs * rs);
+    dev_pairs[p].a = (unsigned char)c->sph_slot[c->h_pairs[p].a];
+    dev_pairs[p].b = (unsigned char)c->sph_slot[c->h_pairs[p].b];
   }
   if (c->d_pairs && c->n_pairs > 0) {
-    cudaError_t e = cudaMemcpy(c->d_pairs, c->h_pairs.data(), sizeof(SelfPair) * size_t(c->n_pairs), cudaMemcpyHostToDevice);
+    cudaError_t e = cudaMemcpy(c->d_pairs, dev_pairs.data(), sizeof(SelfPair) * size_t(c->n_pairs), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return fail(c, SQMP_ERR_CUDA, "cudaMemcpy(self pairs)", e);
   }
   return SQMP_OK;
@@ -586,21 +607,21 @@ int sqmp_get_collisions(sqmp_ctx *ctx, const double q[SQMP_DOF], uint8_t *link_m
   void *dq, *ds, *dp;
   int rc;
   if ((rc = ensure(c, 0, SQMP_DOF * 8, &dq))) return rc;
-  if ((rc = ensure(c, 2, SQMP_MAX_SPHERES, &ds))) return rc;
+  if ((rc = ensure(c, 2, SQMP_MAX_SLOTS, &ds))) return rc;
   if ((rc = ensure(c, 3, size_t(c->n_pairs) + 1, &dp))) return rc;
   cudaStream_t st = c->streams[0];
   CU(cudaMemcpyAsync(dq, q, SQMP_DOF * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemsetAsync(ds, 0, SQMP_MAX_SPHERES, st));
+  CU(cudaMemsetAsync(ds, 0, SQMP_MAX_SLOTS, st));
   CU(cudaMemsetAsync(dp, 0, size_t(c->n_pairs) + 1, st));
   CU(launch_get_collisions(c->rb_grid, c->gd, c->d_pairs, c->n_pairs, (const double *)dq, (uint8_t *)ds, (uint8_t *)dp, st));
   c->launches += 1;
-  uint8_t sh[SQMP_MAX_SPHERES];
-  CU(cudaMemcpyAsync(sh, ds, SQMP_MAX_SPHERES, cudaMemcpyDeviceToHost, st));
+  uint8_t sh[SQMP_MAX_SLOTS];
+  CU(cudaMemcpyAsync(sh, ds, SQMP_MAX_SLOTS, cudaMemcpyDeviceToHost, st));
   if (pair_hit && c->n_pairs) CU(cudaMemcpyAsync(pair_hit, dp, size_t(c->n_pairs), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   std::memset(link_map_hit, 0, 64);
-  for (int i = 0; i < c->rb.n_spheres; ++i)
-    if (sh[i]) link_map_hit[c->sph_link[i]] = 1;
+  for (int sl = 0; sl < c->rb_grid.n_spheres; ++sl)
+    if (sh[sl] && c->slot_sph[sl] >= 0) link_map_hit[c->sph_link[c->slot_sph[sl]]] = 1;
   return SQMP_OK;
 }
 

@@ -153,6 +153,20 @@ __device__ __forceinline__ void frame_advance(Frame<T> &f, const RobotDev &rb, i
   }
 }
 
+// Same, with the joint vector parked in shared memory (SoA, q_s[j * pitch + thread]): one LDS instead of a
+// select chain, and 16 registers less per thread for the kernel that keeps many other values live (K1).
+template <typename T>
+__device__ __forceinline__ void frame_advance_smem(Frame<T> &f, const RobotDev &rb, int s, const double *q_mine, int pitch) {
+  const double qv = q_mine[rb.seg_qidx[s] * pitch];
+  if (sizeof(T) == 4) {
+    frame_mul_const<T>(f, rb.seg_pre_f[s], rb.seg_pre_kind[s]);
+    frame_joint_motion<T>(f, rb.seg_type[s], rb.seg_axis_code[s], rb.seg_axis_f[s], T(qv));
+  } else {
+    frame_mul_const<T>(f, rb.seg_pre[s], rb.seg_pre_kind[s]);
+    frame_joint_motion<T>(f, rb.seg_type[s], rb.seg_axis_code[s], rb.seg_axis[s], T(qv));
+  }
+}
+
 // KDL::Rotation::GetQuaternion (frames.cpp) — same branch structure so signs match the reference.
 __device__ __forceinline__ void get_quaternion(const double *R, double &x, double &y, double &z, double &w) {
   const double trace = R[0] + R[4] + R[8];

@@ -11,6 +11,10 @@
 
 namespace sqmp {
 
+// K1 walks "slots": the spheres of every rigid group padded to a multiple of 4 (pads repeat the last sphere and can
+// never test positive), so its 4-wide batches need no bounds logic.
+constexpr int SQMP_MAX_SLOTS = SQMP_MAX_SPHERES + 4 * (SQMP_MAX_SEG + 1);
+
 // axis codes: the joint axes of the reference robot are all signed unit axes (URDF:30-66, 615-759);
 // a general axis takes the Rodrigues path.
 __host__ __device__ __forceinline__ int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
@@ -21,7 +25,7 @@ enum AxisCode : int { AX_GENERAL = 0, AX_PX = 1, AX_NX = 2, AX_PY = 3, AX_NY = 4
 // warp-uniform, so it is served from the constant bank / uniform datapath and never touches the LSU.
 struct RobotDev {
   int n_seg;
-  int n_spheres;
+  int n_spheres;                          // metres copy: spheres; grid-unit copy (K1): slots, see SQMP_MAX_SLOTS
   int ref_seg;                            // last segment of the leading prismatic run (base position)
   int self_const_collision;
   unsigned trans_mask;                    // bit j: q[j] drives a prismatic joint (a length)
@@ -36,16 +40,16 @@ struct RobotDev {
   double root_off[3];
   double ee_tip[12];
   int ee_tip_kind;
-  double sph[SQMP_MAX_SPHERES][4];        // cx cy cz r in the segment frame
+  double sph[SQMP_MAX_SLOTS][4];        // cx cy cz r in the segment frame
   // fp32 copies of the constants (made by the host once; saves the F2F conversions in the float chain)
   float seg_pre_f[SQMP_MAX_SEG][12];
   float seg_axis_f[SQMP_MAX_SEG][4];
   float ee_tip_f[12];
-  float4 sph_f[SQMP_MAX_SPHERES];
+  float4 sph_f[SQMP_MAX_SLOTS];
   // per-grid derived values (recomputed by sqmp_set_voxel_grid)
-  short sph_thr[SQMP_MAX_SPHERES];            // floor((r/res)^2): "lb2 > thr" proves the sphere free (integers, exact);
+  short sph_thr[SQMP_MAX_SLOTS];             // floor((r/res)^2): "lb2 > thr" proves the sphere free (integers, exact);
                                               // -2 while the sphere's link is disabled (sqmp_set_disabled_links)
-  unsigned char sph_ncell[SQMP_MAX_SPHERES];  // ceil(r / res)
+  unsigned char sph_ncell[SQMP_MAX_SLOTS];  // ceil(r / res)
   // per-request (sqmp_set_disabled_links)
   uint32_t sph_enabled[SQMP_MAX_SPHERES / 32];
 };

@@ -174,7 +174,7 @@ template <> struct K1Cfg<float> { static constexpr int MIN_BLOCKS = 5; };
 //   4. what is left (lb <= rg < dist(centre,O*): ~1.5 spheres per state) is pushed by ballot compaction on a
 //      per-warp queue in shared memory and decided 32 items at a time by the exact row scan (drain_queue).
 // Steps 3-4 exist once in the code: each lane serialises its own pending spheres of a batch through them.
-template <typename T, bool EDGES, int MODE>
+template <typename T, bool EDGES, int MODE, bool SELF>
 __global__ void __launch_bounds__(K1_THREADS, K1Cfg<T>::MIN_BLOCKS)
 k1_check_states(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd,
                 const SelfPair *__restrict__ pairs, int n_pairs, const double *__restrict__ q_in,
@@ -182,13 +182,15 @@ k1_check_states(const __grid_constant__ RobotDev rb, const __grid_constant__ Gri
                 uint32_t *__restrict__ mask_out, uint8_t *__restrict__ sphere_hit, uint8_t *__restrict__ pair_hit) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WarpQueue *wq = reinterpret_cast<WarpQueue *>(smem_raw) + (threadIdx.x >> 5);
-  float *s_rel = reinterpret_cast<float *>(smem_raw + sizeof(WarpQueue) * (K1_THREADS / 32));  // [3][n][blockDim]
+  double *q_mine = reinterpret_cast<double *>(smem_raw + sizeof(WarpQueue) * (K1_THREADS / 32)) + threadIdx.x;  // [8][blockDim]
+  float *s_rel = reinterpret_cast<float *>(smem_raw + sizeof(WarpQueue) * (K1_THREADS / 32) +
+                                           sizeof(double) * SQMP_DOF * K1_THREADS);  // [3][n][blockDim]
   const int lane = threadIdx.x & 31;
   const int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool active = s < S;
   const int64_t sl = active ? s : S - 1;  // idle lanes of the last warp shadow the last state (lockstep loops)
   const bool do_map = (flags & SQMP_CHECK_MAP) && gd.has_grid;
-  const bool do_self = (flags & SQMP_CHECK_SELF) != 0;
+  const bool do_self = SELF;   // (flags & SQMP_CHECK_SELF), resolved at launch: the map-only kernel carries no self state
   bool hit = false;
   int qcount = 0;  // warp-uniform
 
@@ -215,21 +217,20 @@ k1_check_states(const __grid_constant__ RobotDev rb, const __grid_constant__ Gri
   }
   // prismatic joint values are lengths: into grid units with everything else.  A state with a non-finite or
   // absurd joint value cannot reach the grid (and would break the integer cell arithmetic): map check skipped.
+  // The vector is parked in shared memory (own column, no sharing): the chain walk picks q[seg_qidx] with one LDS.
   bool sane = true;
 #pragma unroll
   for (int j = 0; j < SQMP_DOF; ++j) {
-    q[j] = ((rb.trans_mask >> j) & 1) ? q[j] * rb.len_scale : q[j];
-    sane = sane && (fabs(q[j]) < 1.0e9);
+    const double v = ((rb.trans_mask >> j) & 1) ? q[j] * rb.len_scale : q[j];
+    sane = sane && (fabs(v) < 1.0e9);
+    q_mine[j * K1_THREADS] = v;
   }
 
   // ---- base reference point = position after the leading prismatic run ----
   double pref[3] = {rb.root_off[0], rb.root_off[1], rb.root_off[2]};
   if (do_self || sizeof(T) == 4) {
     for (int sg = 0; sg <= rb.ref_seg; ++sg) {
-      const int qi = rb.seg_qidx[sg];
-      double qv = q[0];
-#pragma unroll
-      for (int j = 1; j < SQMP_DOF; ++j) qv = (qi == j) ? q[j] : qv;
+      const double qv = q_mine[rb.seg_qidx[sg] * K1_THREADS];
 #pragma unroll
       for (int i = 0; i < 3; ++i) pref[i] += rb.seg_pre[sg][9 + i] + rb.seg_axis[sg][i] * qv;
     }
@@ -259,7 +260,7 @@ k1_check_states(const __grid_constant__ RobotDev rb, const __grid_constant__ Gri
   const unsigned plane = unsigned(gd.gy) * unsigned(gd.gx);   // host guarantees gx*gy*gz < 2^32
   bool live = do_map && sane;   // this lane still needs map tests (MODE 0: until its first hit)
   for (int sg = -1; sg < rb.n_seg; ++sg) {
-    if (sg >= sg0) frame_advance<T>(f, rb, sg, q);
+    if (sg >= sg0) frame_advance_smem<T>(f, rb, sg, q_mine, K1_THREADS);
     else if (sg >= 0) continue;
     const int b = rb.seg_sph_end[sg + 1], e = rb.seg_sph_end[sg + 2];
     if (b == e) continue;
@@ -271,7 +272,7 @@ k1_check_states(const __grid_constant__ RobotDev rb, const __grid_constant__ Gri
       int lbv[K1_BATCH];
 #pragma unroll
       for (int u = 0; u < K1_BATCH; ++u) {  // transform + byte gather (independent loads, issued back to back)
-        const int i = min(i0 + u, e - 1);   // the tail of a group repeats its last sphere (skipped below)
+        const int i = i0 + u;   // slots: groups are padded to a multiple of K1_BATCH (pads never test positive)
         T lx, ly, lz;
         if (sizeof(T) == 8) {
           lx = T(rb.sph[i][0]); ly = T(rb.sph[i][1]); lz = T(rb.sph[i][2]);
@@ -292,20 +293,20 @@ k1_check_states(const __grid_constant__ RobotDev rb, const __grid_constant__ Gri
         const int n = rb.n_spheres;
 #pragma unroll
         for (int u = 0; u < K1_BATCH; ++u) {
-          const int i = min(i0 + u, e - 1);
+          const int i = i0 + u;
           s_rel[(0 * n + i) * blockDim.x + threadIdx.x] = float(wm[u][0] - wref[0]) + 0.5f;
           s_rel[(1 * n + i) * blockDim.x + threadIdx.x] = float(wm[u][1] - wref[1]) + 0.5f;
           s_rel[(2 * n + i) * blockDim.x + threadIdx.x] = float(wm[u][2] - wref[2]) + 0.5f;
         }
       }
-      // sph_thr[i] = floor(rg^2), or -2 for a sphere whose link is disabled (lbv is -1 outside the grid): an
+      // sph_thr[i] = floor(rg^2), or -2 for a pad slot / a sphere whose link is disabled (lbv is -1 outside the grid): an
       // integer compare, and ~89 % of the spheres end here
       unsigned pend = 0;
 #pragma unroll
       for (int u = 0; u < K1_BATCH; ++u) {
-        const int i = min(i0 + u, e - 1);
+        const int i = i0 + u;
         const int thr = (MODE == 1) ? int(rb.sph[i][3] * rb.sph[i][3] + 1e-9) : int(rb.sph_thr[i]);
-        if (lbv[u] <= thr && (u == 0 || i0 + u < e)) pend |= 1u << u;
+        if (lbv[u] <= thr) pend |= 1u << u;
       }
       if (!live) pend = 0;
       while (__any_sync(FULL, pend != 0)) {
@@ -321,7 +322,7 @@ k1_check_states(const __grid_constant__ RobotDev rb, const __grid_constant__ Gri
           jx = sel ? ci[v][0] : jx; jy = sel ? ci[v][1] : jy; jz = sel ? ci[v][2] : jz;
           lb = sel ? lbv[v] : lb;
         }
-        const int i = min(i0 + max(u, 0), e - 1);
+        const int i = i0 + max(u, 0);
         const double rg = rb.sph[i][3];
         bool amb = false;   // neither bound decides: exact scan
         if (u >= 0 && live) {
@@ -399,7 +400,7 @@ k1_check_states(const __grid_constant__ RobotDev rb, const __grid_constant__ Gri
 }
 
 static size_t k1_smem_bytes(const RobotDev &rb, unsigned flags, int threads) {
-  size_t b = sizeof(WarpQueue) * (K1_THREADS / 32);
+  size_t b = sizeof(WarpQueue) * (K1_THREADS / 32) + sizeof(double) * SQMP_DOF * K1_THREADS;
   if (flags & SQMP_CHECK_SELF) b += size_t(3) * rb.n_spheres * threads * sizeof(float);
   return b;
 }
@@ -412,16 +413,18 @@ static cudaError_t launch_k1(const RobotDev &rb, const GridDev &gd, const SelfPa
   const int64_t blocks = (S + K1_THREADS - 1) / K1_THREADS;
   if (blocks <= 0) return cudaSuccess;
   if (blocks > 0x7fffffff) return cudaErrorInvalidValue;
-  if (d_q_end) {
-    auto kern = k1_check_states<T, true, 0>;
+  auto go = [&](auto kern) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    kern<<<unsigned(blocks), K1_THREADS, smem, st>>>(rb, gd, pairs, n_pairs, d_q, d_q_end, num_points, S, flags,
+    kern<<<unsigned(blocks), K1_THREADS, smem, st>>>(rb, gd, pairs, n_pairs, d_q, d_q_end, d_q_end ? num_points : 0, S, flags,
                                                       d_mask, nullptr, nullptr);
+  };
+  const bool self = (flags & SQMP_CHECK_SELF) != 0;
+  if (d_q_end) {
+    if (self) go(k1_check_states<T, true, 0, true>);
+    else go(k1_check_states<T, true, 0, false>);
   } else {
-    auto kern = k1_check_states<T, false, 0>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    kern<<<unsigned(blocks), K1_THREADS, smem, st>>>(rb, gd, pairs, n_pairs, d_q, nullptr, 0, S, flags, d_mask,
-                                                      nullptr, nullptr);
+    if (self) go(k1_check_states<T, false, 0, true>);
+    else go(k1_check_states<T, false, 0, false>);
   }
   return cudaGetLastError();
 }
@@ -438,7 +441,7 @@ cudaError_t launch_check_states(const RobotDev &rb, const GridDev &gd, const Sel
 cudaError_t launch_get_collisions(const RobotDev &rb, const GridDev &gd, const SelfPair *pairs, int n_pairs,
                                   const double *d_q, uint8_t *d_sphere_hit, uint8_t *d_pair_hit, cudaStream_t st) {
   const size_t smem = k1_smem_bytes(rb, SQMP_CHECK_SELF, K1_THREADS);
-  auto kern = k1_check_states<double, false, 1>;
+  auto kern = k1_check_states<double, false, 1, true>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   kern<<<1, K1_THREADS, smem, st>>>(rb, gd, pairs, n_pairs, d_q, nullptr, 0, 1, SQMP_CHECK_MAP | SQMP_CHECK_SELF, nullptr,
                                     d_sphere_hit, d_pair_hit);
