@@ -18,6 +18,7 @@ FLAG_SELF, FLAG_MAP = 1, 2
 DOF = 8
 
 _lib = None
+DOF = 8
 
 
 def build(force: bool = False) -> str:
@@ -34,6 +35,72 @@ def build(force: bool = False) -> str:
 
 def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
+
+
+# ---- oracle/_ref: the reference's OWN distance / sort code (distance_heuristics.cpp, data_structs.h) ----------
+_REF_PATH = os.path.join(_HERE, "_ref", "libsqmp_ref.so")
+REFERENCE_ROOT = "/root/reference"
+_ref = None
+
+
+def build_ref() -> str | None:
+    """Compile oracle/_ref/libsqmp_ref.so from the reference sources where they lie (oracle/Makefile.ref).
+    Only possible where /root/reference exists (the build container); the GPU box uses the prebuilt file."""
+    if os.path.isdir(REFERENCE_ROOT):
+        subprocess.run(["make", "-s", "-C", _HERE, "-f", "Makefile.ref", "REF=" + REFERENCE_ROOT], check=True,
+                       stdout=subprocess.DEVNULL)
+    return _REF_PATH if os.path.exists(_REF_PATH) else None
+
+
+def ref_lib():
+    """ctypes handle of oracle/_ref/libsqmp_ref.so, or None when it has not been built."""
+    global _ref
+    if _ref is not None:
+        return _ref
+    if not os.path.exists(_REF_PATH) and build_ref() is None:
+        return None
+    L = C.CDLL(_REF_PATH)
+    dp, ip, i32p = C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int32)
+    L.ref_joint_space_distance.restype = C.c_double
+    L.ref_joint_space_distance.argtypes = [dp, dp, C.c_int]
+    L.ref_joint_space_distance_chain.argtypes = [ip, C.c_int, dp, dp, C.c_int, dp]
+    L.ref_nearest_batch.argtypes = [dp, C.c_int64, dp, C.c_int64, i32p]
+    L.ref_near_vertices.restype = C.c_int64
+    L.ref_near_vertices.argtypes = [dp, dp, C.c_int64, dp, C.c_int32, C.c_double, i32p, C.c_int64]
+    _ref = L
+    return L
+
+
+def ref_joint_space_distance(a, b):
+    a, b = np.ascontiguousarray(a, np.float64), np.ascontiguousarray(b, np.float64)
+    return ref_lib().ref_joint_space_distance(_p(a, C.c_double), _p(b, C.c_double), a.size)
+
+
+def ref_joint_space_distance_chain(seg_types, a, b):
+    t = np.ascontiguousarray(seg_types, np.int32)
+    a, b = np.ascontiguousarray(a, np.float64), np.ascontiguousarray(b, np.float64)
+    out = np.empty(3)
+    ref_lib().ref_joint_space_distance_chain(_p(t, C.c_int), t.size, _p(a, C.c_double), _p(b, C.c_double), a.size,
+                                             _p(out, C.c_double))
+    return out
+
+
+def ref_nearest(nodes, queries):
+    nodes = np.ascontiguousarray(nodes, np.float64).reshape(-1, DOF)
+    queries = np.ascontiguousarray(queries, np.float64).reshape(-1, DOF)
+    ids = np.empty(queries.shape[0], dtype=np.int32)
+    ref_lib().ref_nearest_batch(_p(nodes, C.c_double), nodes.shape[0], _p(queries, C.c_double), queries.shape[0],
+                                _p(ids, C.c_int32))
+    return ids
+
+
+def ref_near_vertices(nodes, cost, query, exclude_id, r):
+    nodes = np.ascontiguousarray(nodes, np.float64).reshape(-1, DOF)
+    cost, query = np.ascontiguousarray(cost, np.float64), np.ascontiguousarray(query, np.float64)
+    ids = np.empty(nodes.shape[0], dtype=np.int32)
+    n = ref_lib().ref_near_vertices(_p(nodes, C.c_double), _p(cost, C.c_double), nodes.shape[0], _p(query, C.c_double),
+                                    int(exclude_id), float(r), _p(ids, C.c_int32), ids.size)
+    return ids[:n].copy()
 
 
 def lib():

@@ -6,6 +6,9 @@
   collision_numpy.npz sphere-vs-voxel clearances by dense numpy brute force over every occupied voxel
   nn_numpy.npz        nearest / radius results by numpy brute force with the reference's summation order
   interp_numpy.npz    interpolateConfigurations by the numpy formula
+  nn_reference.npz    distances, nearest ids and near-vertex id lists produced by the REFERENCE'S OWN code
+                      (DistanceHeuristics::euclidean_joint_space_distance, Node::operator< + std::sort) compiled
+                      from /root/reference by oracle/Makefile.ref — needs the build container
 
     python tests/golden/make_golden.py
 """
@@ -158,7 +161,34 @@ def interp_numpy():
     np.savez_compressed(os.path.join(HERE, "interp_numpy.npz"), start=a, end=b, states=out)
 
 
+def nn_reference():
+    """Outputs of the reference itself (oracle/_ref): these PIN the near-neighbour rows of the oracle."""
+    import oracle
+    if oracle.build_ref() is None:
+        print("oracle/_ref not buildable here (no /root/reference): nn_reference.npz left as committed")
+        return
+    rng = np.random.default_rng(606)
+    nodes, cost = syn.random_tree(2500, seed=601, cost_seed=602)
+    cost[10] = cost[20] = cost[30]          # cost ties: std::sort is unstable, ids of a tie group are a SET
+    nodes[700] = nodes[7]                   # distance ties: serial '<' keeps the lower id
+    queries = syn.sample_configs(48, seed=603)
+    queries[0] = nodes[7]
+    queries[1] = nodes[700] - 1e-12
+    a, b = rng.normal(size=(256, 8)) * 3.0, rng.normal(size=(256, 8)) * 3.0
+    dist = np.array([oracle.ref_joint_space_distance(x, y) for x, y in zip(a, b)])
+    seg_types = np.array([2, 2, 1, 0, 1, 1, 0, 1, 1, 1], dtype=np.int32)   # chain with fixed segments interleaved
+    dist3 = np.array([oracle.ref_joint_space_distance_chain(seg_types, x, y) for x, y in zip(a, b)])
+    nearest = oracle.ref_nearest(nodes, queries)
+    near = [oracle.ref_near_vertices(nodes, cost, x, -1, 1.5) for x in queries]
+    near_ex = [oracle.ref_near_vertices(nodes, cost, x, int(v[0]) if len(v) else -1, 1.5) for x, v in zip(queries, near)]
+    np.savez_compressed(os.path.join(HERE, "nn_reference.npz"), nodes=nodes, cost=cost, queries=queries, a=a, b=b,
+                        dist=dist, seg_types=seg_types, dist3=dist3, nearest=nearest,
+                        near_count=np.array([len(v) for v in near]), near_flat=np.concatenate(near),
+                        near_ex_count=np.array([len(v) for v in near_ex]), near_ex_flat=np.concatenate(near_ex))
+
+
 if __name__ == "__main__":
+    nn_reference()
     urdf_fk()
     collision_numpy()
     nn_numpy()

@@ -214,6 +214,31 @@ def test_nearest_bit_exact(ctx, variant):
         ctx.set_option("nn_variant", 0)
 
 
+@pytest.mark.parametrize("variant", [1, 2])
+def test_nn_against_reference_golden(ctx, variant):
+    """tests/golden/nn_reference.npz = outputs of the reference's own DistanceHeuristics + Node::operator< / std::sort
+    (compiled from /root/reference by oracle/Makefile.ref): ids bit-exact; within a group of equal cost the reference's
+    unstable sort may order ids either way, the CUDA path orders them by id."""
+    g = np.load(os.path.join(GOLDEN, "nn_reference.npz"))
+    nodes, cost, queries = g["nodes"], g["cost"], g["queries"]
+    ctx.set_option("nn_variant", variant)
+    try:
+        ctx.tree_reset(4)
+        ctx.tree_append_batch(4, nodes, cost)
+        assert np.array_equal(ctx.nn_nearest(4, queries), g["nearest"])
+        low, high, cnt = ctx.nn_radius(4, queries, None, 1.5, 20)
+        assert np.array_equal(cnt, g["near_count"])
+        off = 0
+        for k in range(len(queries)):
+            n = int(cnt[k]); want = g["near_flat"][off:off + n]; off += n
+            got_lo, got_hi = low[k][low[k] >= 0], high[k][high[k] >= 0]
+            assert np.array_equal(cost[got_lo], cost[want[:20]]) and np.array_equal(cost[got_hi], cost[want[::-1][:20]])
+            if n <= 20:
+                assert sorted(got_lo.tolist()) == sorted(want.tolist())
+    finally:
+        ctx.set_option("nn_variant", 0)
+
+
 def test_nearest_quirks_and_tree_mutation(ctx):
     ctx.tree_reset(2)
     assert ctx.nn_nearest(2, np.zeros((3, 8))).tolist() == [0, 0, 0]   # empty tree: id stays 0 (BS:4084)
