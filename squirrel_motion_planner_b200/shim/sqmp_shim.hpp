@@ -1,0 +1,429 @@
+// sqmp_shim.hpp — C++ host side of the drop-in: the reference's collision-check, FK and near-neighbour interfaces,
+// same names, argument meaning and error behaviour, served by the C ABI of libsqmp_b200.so (include/sqmp_b200.h).
+//
+//   reference interface (file:line in /root/reference)                                         here
+//   ----------------------------------------------------------------------------------------------------------------
+//   CollisionChecker (collision_checker.hpp:35-133): isInCollision, setOcTree,                 sqmp_shim::CollisionChecker
+//       setDisabledLinkMapCollisions, getCollisions
+//   BiRRTstarPlanner::isEdgeValid x2 / isConfigValid x2 (birrt_star.cpp:6864-6908)             sqmp_shim::HotPath
+//   BiRRTstarPlanner::find_nearest_neighbour_interpolation (birrt_star.cpp:4076-4133)          sqmp_shim::HotPath
+//   BiRRTstarPlanner::find_near_vertices_interpolation (birrt_star.cpp:4272-4324)              sqmp_shim::HotPath
+//   BiRRTstarPlanner::insertNode and the rewire / cost-update sites (3298-3322, 5173-5193,     sqmp_shim::HotPath
+//       5518-5520) — kept in step with the device mirror of the tree
+//   KDLRobotModel::compute_FK (kdl_kuka_model.cpp:278-305)                                     sqmp_shim::HotPath::compute_FK
+//   Edge / Node / CostsReach / Rrt_star_tree (data_structs.h:11-54)                            the reference's own header when
+//                                                                                              SQMP_SHIM_USE_REFERENCE_STRUCTS
+//                                                                                              is defined, else the mirror below
+//
+// Header-only, C++11 like the reference (birrt_star_algorithm/CMakeLists.txt).  No CPU fallback: if the library or
+// the GPU is missing the checker stays uninitialised and isInCollision answers true (fails closed, CC:106-107).
+#pragma once
+
+#include <cstdint>
+#include <cstdio>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "sqmp_b200.h"
+
+#ifdef SQMP_SHIM_USE_REFERENCE_STRUCTS
+#include <planner_data_structures/data_structs.h>
+#else
+// Mirror of data_structs.h:11-54 — only so that the shim compiles without the reference tree (tests).
+struct Edge {
+  int edge_id;
+  int root_node_id;
+  int child_node_id;
+  std::vector<std::vector<double> > joint_trajectory;
+  std::vector<std::vector<double> > ee_trajectory;
+  double cost_g;
+};
+struct CostsReach {
+  double revolute;
+  double prismatic;
+  double total;
+};
+struct Node {
+  int node_id;
+  int parent_id;
+  std::vector<double> config;
+  std::vector<double> ee_pose;
+  CostsReach cost_h;
+  CostsReach cost_reach;
+  std::vector<Edge> outgoing_edges;
+  bool operator<(const Node &o) const { return cost_reach.total < o.cost_reach.total; }
+};
+struct Rrt_star_tree {
+  std::string name;
+  std::vector<Node> nodes;
+  int num_nodes;
+  int num_edges;
+  int num_rewire_operations;
+};
+#endif
+
+namespace sqmp_shim {
+
+// ---------------------------------------------------------------------------------------------------------------
+// robot description file ("sqmpdesc 1", written by tools/export_robot_desc.py from the reference URDF + SRDF)
+// ---------------------------------------------------------------------------------------------------------------
+struct RobotDescription {
+  sqmp_robot_desc desc;
+  std::vector<std::string> link_names;
+  std::vector<std::string> octomap_disabled;
+  std::vector<int32_t> sph_seg, sph_link, pair_a, pair_b;
+  std::vector<double> sph_center, sph_radius;
+
+  bool load(const std::string &path, std::string *err) {
+    std::ifstream in(path.c_str());
+    if (!in) return fail(err, "cannot open " + path);
+    std::string tok;
+    int version = 0;
+    if (!(in >> tok >> version) || tok != "sqmpdesc" || version != 1) return fail(err, "not a sqmpdesc 1 file");
+    desc = sqmp_robot_desc();
+    int seg = 0;
+    while (in >> tok) {
+      if (tok == "n_seg") {
+        in >> desc.n_seg;
+        if (desc.n_seg < 1 || desc.n_seg > SQMP_MAX_SEG) return fail(err, "n_seg out of range");
+      } else if (tok == "seg") {
+        if (seg >= SQMP_MAX_SEG) return fail(err, "too many segments");
+        in >> desc.seg_type[seg] >> desc.seg_qidx[seg];
+        for (int i = 0; i < 12; ++i) in >> desc.seg_pre[seg][i];
+        for (int i = 0; i < 3; ++i) in >> desc.seg_axis[seg][i];
+        ++seg;
+      } else if (tok == "root_offset") {
+        for (int i = 0; i < 3; ++i) in >> desc.root_offset[i];
+      } else if (tok == "ee_tip") {
+        for (int i = 0; i < 12; ++i) in >> desc.ee_tip[i];
+      } else if (tok == "n_links") {
+        size_t n = 0;
+        in >> n;
+        link_names.assign(n, std::string());
+      } else if (tok == "link") {
+        size_t i = 0;
+        std::string name;
+        in >> i >> name;
+        if (i >= link_names.size()) return fail(err, "link index out of range");
+        link_names[i] = name;
+      } else if (tok == "octomap_disabled") {
+        size_t n = 0;
+        in >> n;
+        octomap_disabled.resize(n);
+        for (size_t i = 0; i < n; ++i) in >> octomap_disabled[i];
+      } else if (tok == "n_spheres") {
+        in >> desc.n_spheres;
+      } else if (tok == "sphere") {
+        int32_t sg = 0, lk = 0;
+        double c[3], r = 0;
+        in >> sg >> lk >> c[0] >> c[1] >> c[2] >> r;
+        sph_seg.push_back(sg);
+        sph_link.push_back(lk);
+        sph_center.insert(sph_center.end(), c, c + 3);
+        sph_radius.push_back(r);
+      } else if (tok == "n_pairs") {
+        in >> desc.n_pairs;
+      } else if (tok == "pair") {
+        int32_t a = 0, b = 0;
+        in >> a >> b;
+        pair_a.push_back(a);
+        pair_b.push_back(b);
+      } else if (tok == "self_const_collision") {
+        in >> desc.self_const_collision;
+      } else {
+        return fail(err, "unknown key " + tok);
+      }
+      if (!in) return fail(err, "truncated value for key " + tok);
+    }
+    if (seg != desc.n_seg || int(sph_radius.size()) != desc.n_spheres || int(pair_a.size()) != desc.n_pairs)
+      return fail(err, "counts do not match their declarations");
+    desc.sph_seg = sph_seg.data();
+    desc.sph_link = sph_link.data();
+    desc.sph_center = sph_center.data();
+    desc.sph_radius = sph_radius.data();
+    desc.pair_a = pair_a.data();
+    desc.pair_b = pair_b.data();
+    return true;
+  }
+
+  int link_index(const std::string &name) const {
+    for (size_t i = 0; i < link_names.size(); ++i)
+      if (link_names[i] == name) return int(i);
+    return -1;
+  }
+
+ private:
+  static bool fail(std::string *err, const std::string &what) {
+    if (err) *err = what;
+    return false;
+  }
+};
+
+// Dense occupancy as the library takes it: bit (k*gy+j)*gx+i = voxel origin + [i,i+1]x[j,j+1]x[k,k+1]*res.
+struct VoxelGrid {
+  std::vector<uint32_t> bits;
+  int gx, gy, gz;
+  double origin[3];
+  double res;
+  VoxelGrid() : gx(0), gy(0), gz(0), res(0.0) { origin[0] = origin[1] = origin[2] = 0.0; }
+  void resize(int nx, int ny, int nz) {
+    gx = nx; gy = ny; gz = nz;
+    bits.assign((size_t(nx) * ny * nz + 31) / 32, 0u);
+  }
+  void set(int i, int j, int k) {
+    const size_t b = (size_t(k) * gy + j) * gx + i;
+    bits[b >> 5] |= 1u << (b & 31);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// CollisionChecker  (collision_checker.hpp:35-133)
+// ---------------------------------------------------------------------------------------------------------------
+class CollisionChecker {
+ public:
+  // CC:66-74 / 156-172: the reference builds its link model from the URDF/SRDF on the parameter server; here the
+  // pre-folded description comes from a file (tools/export_robot_desc.py).  Failure leaves the checker uninitialised.
+  explicit CollisionChecker(const std::string &desc_path, int device = 0) : ctx_(NULL), initialized_(false) {
+    std::string err;
+    if (!robot_.load(desc_path, &err)) {
+      std::fprintf(stderr, "CollisionChecker: %s\n", err.c_str());
+      return;
+    }
+    int code = 0;
+    ctx_ = sqmp_create(device, &robot_.desc, &code);
+    if (!ctx_) {
+      std::fprintf(stderr, "CollisionChecker: sqmp_create failed: %s\n", sqmp_strerror(code));
+      return;
+    }
+    initialized_ = true;
+    setDisabledLinkMapCollisions(std::vector<std::string>());
+  }
+  ~CollisionChecker() { sqmp_destroy(ctx_); }
+
+  bool isInitialized() const { return initialized_; }
+  sqmp_ctx *context() const { return ctx_; }
+  const RobotDescription &robot() const { return robot_; }
+
+  // CC:76-88.  Any octomap-like tree: begin_leafs()/end_leafs() iterators with getX/Y/Z(), getSize(), and
+  // isNodeOccupied(*it); getResolution(); getMetricMin/Max(x,y,z).  NULL is ignored (CC:78-79); deep copy; the
+  // collision object's z = -0.02 offset (CC:87) is folded into the grid origin.
+  template <class OcTreeT>
+  void setOcTree(const OcTreeT *tree) {
+    if (!tree || !initialized_) return;
+    VoxelGrid g;
+    const double res = tree->getResolution();
+    double lo[3], hi[3];
+    tree->getMetricMin(lo[0], lo[1], lo[2]);
+    tree->getMetricMax(hi[0], hi[1], hi[2]);
+    int n[3];
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = res * double((long long)(lo[a] / res) - 1);
+      n[a] = int((hi[a] - lo[a]) / res) + 2;
+      g.origin[a] = lo[a];
+    }
+    g.res = res;
+    g.resize(n[0], n[1], n[2]);
+    for (typename OcTreeT::leaf_iterator it = tree->begin_leafs(), end = tree->end_leafs(); it != end; ++it) {
+      if (!tree->isNodeOccupied(*it)) continue;   // unknown and free space do not collide
+      const double h = 0.5 * it.getSize();        // a pruned leaf covers (size/res)^3 finest voxels
+      const int i0 = int((it.getX() - h - lo[0]) / res + 0.5), i1 = int((it.getX() + h - lo[0]) / res + 0.5);
+      const int j0 = int((it.getY() - h - lo[1]) / res + 0.5), j1 = int((it.getY() + h - lo[1]) / res + 0.5);
+      const int k0 = int((it.getZ() - h - lo[2]) / res + 0.5), k1 = int((it.getZ() + h - lo[2]) / res + 0.5);
+      for (int k = k0; k < k1; ++k)
+        for (int j = j0; j < j1; ++j)
+          for (int i = i0; i < i1; ++i)
+            if (i >= 0 && j >= 0 && k >= 0 && i < g.gx && j < g.gy && k < g.gz) g.set(i, j, k);
+    }
+    setVoxelGrid(g);
+  }
+  // Same, from an occupancy that is already dense (tests, synthetic worlds, .bt ingest).
+  void setVoxelGrid(const VoxelGrid &g) {
+    if (!initialized_ || g.bits.empty()) return;
+    const double origin[3] = {g.origin[0], g.origin[1], g.origin[2] - 0.02};   // CC:87
+    if (sqmp_set_voxel_grid(ctx_, g.bits.data(), g.gx, g.gy, g.gz, origin, g.res) != SQMP_OK)
+      std::fprintf(stderr, "CollisionChecker::setOcTree: %s\n", sqmp_last_error(ctx_));
+  }
+
+  // CC:90-102 (+ the SRDF "octomap" disables, CC:408-416)
+  void setDisabledLinkMapCollisions(const std::vector<std::string> &linksDisabled) {
+    if (!initialized_) return;
+    uint64_t mask = 0;
+    for (size_t i = 0; i < linksDisabled.size(); ++i) add_link(mask, linksDisabled[i]);
+    for (size_t i = 0; i < robot_.octomap_disabled.size(); ++i) add_link(mask, robot_.octomap_disabled[i]);
+    sqmp_set_disabled_links(ctx_, mask);
+  }
+
+  // CC:104-121: true = in collision; true when uninitialised; false when both flags are off.
+  bool isInCollision(const std::vector<double> &jointPositions, const bool checkSelfCollision,
+                     const bool checkMapCollision) {
+    if (!initialized_) return true;
+    if (!checkSelfCollision && !checkMapCollision) return false;
+    if (jointPositions.size() < size_t(SQMP_DOF)) return true;
+    uint32_t word = 0;
+    if (sqmp_check_states(ctx_, jointPositions.data(), 1, flags(checkSelfCollision, checkMapCollision), &word) != SQMP_OK)
+      return true;   // fail closed
+    return (word & 1u) != 0;
+  }
+
+  // CC:123-133, 594-631: names of colliding link pairs (i < j, sorted) and of links hitting the map (sorted).
+  void getCollisions(const std::vector<double> &jointPositions,
+                     std::vector<std::pair<std::string, std::string> > &selfCollisions,
+                     std::vector<std::string> &mapCollisions) {
+    selfCollisions.clear();
+    mapCollisions.clear();
+    if (!initialized_ || jointPositions.size() < size_t(SQMP_DOF)) return;
+    uint8_t link_hit[64];
+    std::vector<uint8_t> pair_hit(size_t(robot_.desc.n_pairs) + 1, 0);
+    if (sqmp_get_collisions(ctx_, jointPositions.data(), link_hit, pair_hit.data()) != SQMP_OK) return;
+    std::map<std::pair<int, int>, bool> seen;
+    for (int p = 0; p < robot_.desc.n_pairs; ++p) {
+      if (!pair_hit[p]) continue;
+      int a = robot_.sph_link[robot_.pair_a[p]], b = robot_.sph_link[robot_.pair_b[p]];
+      if (a > b) std::swap(a, b);
+      seen[std::make_pair(a, b)] = true;
+    }
+    for (std::map<std::pair<int, int>, bool>::const_iterator it = seen.begin(); it != seen.end(); ++it)
+      selfCollisions.push_back(std::make_pair(robot_.link_names[it->first.first], robot_.link_names[it->first.second]));
+    std::map<std::string, bool> names;
+    for (size_t i = 0; i < robot_.link_names.size() && i < 64; ++i)
+      if (link_hit[i]) names[robot_.link_names[i]] = true;
+    for (std::map<std::string, bool>::const_iterator it = names.begin(); it != names.end(); ++it)
+      mapCollisions.push_back(it->first);
+  }
+
+  static unsigned flags(bool self, bool map) { return (self ? SQMP_CHECK_SELF : 0u) | (map ? SQMP_CHECK_MAP : 0u); }
+
+ private:
+  void add_link(uint64_t &mask, const std::string &name) const {
+    const int i = robot_.link_index(name);
+    if (i >= 0 && i < 64) mask |= uint64_t(1) << i;
+  }
+  CollisionChecker(const CollisionChecker &);
+  CollisionChecker &operator=(const CollisionChecker &);
+
+  RobotDescription robot_;
+  sqmp_ctx *ctx_;
+  bool initialized_;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// The members of BiRRTstarPlanner on the hot path (birrt_star.h:103-107, 322-325)
+// ---------------------------------------------------------------------------------------------------------------
+class HotPath {
+ public:
+  HotPath(CollisionChecker *checker, double near_threshold_interpolation = 1.5 /* PY:4 */, int max_near_nodes = 20 /* PY:6 */)
+      : collisionChecker(checker), m_near_threshold_interpolation(near_threshold_interpolation),
+        m_max_near_nodes(max_near_nodes) {}
+
+  // BS:6897-6908
+  bool isConfigValid(const std::vector<double> &config, bool check_self_collision, bool check_map_collision) {
+    return !collisionChecker->isInCollision(config, check_self_collision, check_map_collision);
+  }
+
+  // BS:6864-6876
+  bool isEdgeValid(const Edge &tree_edge, bool check_self_collision, bool check_map_collision) {
+    int unused = 0;
+    return isEdgeValid(tree_edge, unused, check_self_collision, check_map_collision);
+  }
+  // BS:6878-6895: last_valid_node_idx = index of the last state before the first colliding one (0 if none), n-1 if valid.
+  // One library call for the whole trajectory instead of one isInCollision per state.
+  bool isEdgeValid(const Edge &tree_edge, int &last_valid_node_idx, bool check_self_collision, bool check_map_collision) {
+    last_valid_node_idx = 0;
+    const size_t n = tree_edge.joint_trajectory.size();
+    if (n == 0) return true;
+    if (!collisionChecker->isInitialized()) return false;
+    if (!check_self_collision && !check_map_collision) {
+      last_valid_node_idx = int(n) - 1;
+      return true;
+    }
+    scratch_q_.resize(n * SQMP_DOF);
+    for (size_t s = 0; s < n; ++s)
+      for (int i = 0; i < SQMP_DOF; ++i) scratch_q_[s * SQMP_DOF + i] = tree_edge.joint_trajectory[s][i];   // BS:6868-6870
+    scratch_mask_.assign((n + 31) / 32, 0u);
+    if (sqmp_check_states(collisionChecker->context(), scratch_q_.data(), int64_t(n),
+                          CollisionChecker::flags(check_self_collision, check_map_collision), scratch_mask_.data()) != SQMP_OK)
+      return false;
+    for (size_t s = 0; s < n; ++s)
+      if ((scratch_mask_[s >> 5] >> (s & 31)) & 1u) {
+        last_valid_node_idx = s > 0 ? int(s) - 1 : 0;
+        return false;
+      }
+    last_valid_node_idx = int(n) - 1;
+    return true;
+  }
+
+  // Batched form for a planner front-end that submits all candidate edges of an iteration at once: edge e is the
+  // interpolation of q_start[e] -> q_end[e] over num_points+1 states (BS:4461-4478); first_invalid[e] = -1 if valid.
+  bool areEdgesValid(const std::vector<double> &q_start, const std::vector<double> &q_end, int num_points,
+                     bool check_self_collision, bool check_map_collision, std::vector<int32_t> &first_invalid) {
+    const int64_t E = int64_t(q_start.size() / SQMP_DOF);
+    first_invalid.assign(size_t(E), 0);
+    if (!collisionChecker->isInitialized() || q_end.size() != q_start.size()) return false;
+    scratch_mask_.assign(size_t((E * (num_points + 1) + 31) / 32), 0u);
+    return sqmp_check_edges(collisionChecker->context(), q_start.data(), q_end.data(), E, num_points,
+                            CollisionChecker::flags(check_self_collision, check_map_collision), scratch_mask_.data(),
+                            first_invalid.data()) == SQMP_OK;
+  }
+
+  // ---- tree mirror: call next to the reference's own mutation of `tree` ------------------------------------------
+  // `slot` selects the device tree (0 = start tree, 1 = goal tree, ...).
+  bool resetTree(int slot) { return sqmp_tree_reset(collisionChecker->context(), slot) == SQMP_OK; }
+  // BS:3298-3322 insertNode: appends; the id the library returns equals node.node_id (node_id == index invariant).
+  bool insertNode(int slot, const Node &node) {
+    int32_t id = -1;
+    return sqmp_tree_append(collisionChecker->context(), slot, node.config.data(), node.cost_reach.total, &id) == SQMP_OK &&
+           id == node.node_id;
+  }
+  // BS:5173-5193 rewire (config / cost of an existing node change), BS:5518-5520 recursiveNodeCostUpdate
+  bool updateNode(int slot, const Node &node) {
+    return sqmp_tree_update(collisionChecker->context(), slot, node.node_id, node.config.data(), node.cost_reach.total) == SQMP_OK;
+  }
+
+  // BS:4076-4133: returns the Node by value like the reference (id 0 when nothing is closer than 10000.0).
+  Node find_nearest_neighbour_interpolation(Rrt_star_tree *tree, int slot, std::vector<double> x_rand) {
+    int32_t id = 0;
+    if (sqmp_nn_nearest(collisionChecker->context(), slot, x_rand.data(), 1, &id) != SQMP_OK) id = 0;
+    return tree->nodes[size_t(id)];
+  }
+
+  // BS:4272-4324.  The reference returns every near id sorted by cost; its callers only ever walk the first
+  // m_max_near_nodes (BS:4618-4623, 2823) or the last m_max_near_nodes from the end (BS:5075-5089).  The returned
+  // vector has the reference's layout for both walks: if count <= 2*max_near it is the full sorted list, otherwise the
+  // first max_near ids, then (count - 2*max_near) entries of -1 that no caller touches, then the last max_near ids.
+  std::vector<int> find_near_vertices_interpolation(Rrt_star_tree * /*tree*/, int slot, const Node &x_new) {
+    const int k = m_max_near_nodes;
+    std::vector<int32_t> low(size_t(k), -1), high(size_t(k), -1);
+    int32_t count = 0, excl = x_new.node_id;
+    std::vector<int> out;
+    if (sqmp_nn_radius(collisionChecker->context(), slot, x_new.config.data(), &excl, 1, m_near_threshold_interpolation, k,
+                       low.data(), high.data(), &count) != SQMP_OK)
+      return out;
+    out.assign(size_t(count), -1);
+    for (int t = 0; t < k && t < count; ++t) {
+      out[size_t(t)] = low[size_t(t)];
+      out[size_t(count - 1 - t)] = high[size_t(t)];
+    }
+    return out;
+  }
+
+  // KM:278-305: [x y z qx qy qz qw] of the SRDF chain tip (hand_wrist_link).
+  std::vector<double> compute_FK(const std::vector<double> &chain_config) {
+    std::vector<double> pose(7, 0.0);
+    if (chain_config.size() >= size_t(SQMP_DOF)) sqmp_fk(collisionChecker->context(), chain_config.data(), 1, pose.data());
+    return pose;
+  }
+
+  CollisionChecker *collisionChecker;   // same member name as birrt_star.h
+  double m_near_threshold_interpolation;
+  int m_max_near_nodes;
+
+ private:
+  std::vector<double> scratch_q_;
+  std::vector<uint32_t> scratch_mask_;
+};
+
+}  // namespace sqmp_shim

@@ -1,0 +1,160 @@
+// test_shim.cpp — drives the C++ shim (sqmp_shim.hpp) exactly the way birrt_star.cpp drives the reference classes,
+// on inputs written by tests/test_cpp_shim.py, and writes the results back for comparison with the CPU oracle.
+//   usage: test_shim <robot.sqmpdesc> <work_dir>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+
+#include "sqmp_shim.hpp"
+
+template <class T>
+static std::vector<T> read_raw(const std::string &path) {
+  std::ifstream f(path.c_str(), std::ios::binary | std::ios::ate);
+  std::vector<T> v;
+  if (!f) return v;
+  const std::streamsize n = f.tellg();
+  f.seekg(0);
+  v.resize(size_t(n) / sizeof(T));
+  f.read(reinterpret_cast<char *>(v.data()), n);
+  return v;
+}
+template <class T>
+static void write_raw(const std::string &path, const std::vector<T> &v) {
+  std::ofstream f(path.c_str(), std::ios::binary);
+  f.write(reinterpret_cast<const char *>(v.data()), std::streamsize(v.size() * sizeof(T)));
+}
+
+int main(int argc, char **argv) {
+  if (argc < 3) {
+    std::fprintf(stderr, "usage: %s robot.sqmpdesc work_dir\n", argv[0]);
+    return 2;
+  }
+  const std::string dir = std::string(argv[2]) + "/";
+  sqmp_shim::CollisionChecker *collisionChecker = new sqmp_shim::CollisionChecker(argv[1]);   // BS:73
+  if (!collisionChecker->isInitialized()) {
+    // fail-closed behaviour of an uninitialised checker (CC:106-107)
+    std::printf("uninitialised: isInCollision -> %d\n", int(collisionChecker->isInCollision(std::vector<double>(8, 0.0), true, true)));
+    return 3;
+  }
+  sqmp_shim::HotPath planner(collisionChecker);
+
+  // ---- world: before setOcTree the map check reports free (CC:556-557) ----
+  const std::vector<double> states = read_raw<double>(dir + "states.f64");
+  const size_t S = states.size() / 8;
+  std::vector<uint8_t> no_map(S), verdict(S), verdict_map(S);
+  for (size_t s = 0; s < S; ++s)
+    no_map[s] = collisionChecker->isInCollision(std::vector<double>(states.begin() + s * 8, states.begin() + s * 8 + 8), false, true);
+  sqmp_shim::VoxelGrid g;
+  {
+    std::ifstream meta((dir + "grid_meta.txt").c_str());
+    meta >> g.gx >> g.gy >> g.gz >> g.origin[0] >> g.origin[1] >> g.origin[2] >> g.res;
+    g.bits = read_raw<uint32_t>(dir + "grid_bits.u32");
+  }
+  collisionChecker->setVoxelGrid(g);
+  for (size_t s = 0; s < S; ++s) {
+    const std::vector<double> q(states.begin() + s * 8, states.begin() + s * 8 + 8);
+    verdict[s] = collisionChecker->isInCollision(q, true, true);
+    verdict_map[s] = !planner.isConfigValid(q, false, true);
+  }
+  write_raw(dir + "out_no_map.u8", no_map);
+  write_raw(dir + "out_verdict.u8", verdict);
+  write_raw(dir + "out_verdict_map.u8", verdict_map);
+
+  // ---- edges of 21 consecutive states (BS:6864-6895) ----
+  std::vector<int32_t> edge_out;
+  for (size_t e = 0; e + 21 <= S; e += 21) {
+    Edge edge;
+    for (size_t k = 0; k < 21; ++k)
+      edge.joint_trajectory.push_back(std::vector<double>(states.begin() + (e + k) * 8, states.begin() + (e + k) * 8 + 8));
+    int last_valid_node_idx = -7;
+    const bool ok2 = planner.isEdgeValid(edge, last_valid_node_idx, false, true);
+    const bool ok1 = planner.isEdgeValid(edge, false, true);
+    edge_out.push_back(ok1);
+    edge_out.push_back(ok2);
+    edge_out.push_back(last_valid_node_idx);
+  }
+  write_raw(dir + "out_edges.i32", edge_out);
+
+  // ---- disabled links (CC:90-102) ----
+  std::vector<std::string> disabled;
+  {
+    std::ifstream f((dir + "disabled_links.txt").c_str());
+    std::string n;
+    while (f >> n) disabled.push_back(n);
+  }
+  collisionChecker->setDisabledLinkMapCollisions(disabled);
+  std::vector<uint8_t> verdict_dis(S);
+  for (size_t s = 0; s < S; ++s)
+    verdict_dis[s] = collisionChecker->isInCollision(std::vector<double>(states.begin() + s * 8, states.begin() + s * 8 + 8), false, true);
+  write_raw(dir + "out_verdict_disabled.u8", verdict_dis);
+  collisionChecker->setDisabledLinkMapCollisions(std::vector<std::string>());
+
+  // ---- getCollisions of the first colliding state (CC:123-133) ----
+  {
+    std::ofstream f((dir + "out_collisions.txt").c_str());
+    for (size_t s = 0; s < S; ++s) {
+      if (!verdict[s]) continue;
+      std::vector<std::pair<std::string, std::string> > self;
+      std::vector<std::string> map;
+      collisionChecker->getCollisions(std::vector<double>(states.begin() + s * 8, states.begin() + s * 8 + 8), self, map);
+      f << "state " << s << "\n";
+      for (size_t i = 0; i < self.size(); ++i) f << "self " << self[i].first << " " << self[i].second << "\n";
+      for (size_t i = 0; i < map.size(); ++i) f << "map " << map[i] << "\n";
+      break;
+    }
+  }
+
+  // ---- tree + near neighbours (BS:3298-3322, 4076-4133, 4272-4324) ----
+  const std::vector<double> nodes = read_raw<double>(dir + "tree_nodes.f64"), cost = read_raw<double>(dir + "tree_cost.f64");
+  const std::vector<double> queries = read_raw<double>(dir + "queries.f64");
+  Rrt_star_tree tree;
+  tree.name = "START";
+  planner.resetTree(0);
+  for (size_t n = 0; n < cost.size(); ++n) {
+    Node node;
+    node.node_id = int(n);
+    node.parent_id = n ? 0 : -1;
+    node.config.assign(nodes.begin() + n * 8, nodes.begin() + n * 8 + 8);
+    node.cost_reach.total = cost[n];
+    tree.nodes.push_back(node);
+    if (!planner.insertNode(0, node)) {
+      std::fprintf(stderr, "insertNode failed at %zu\n", n);
+      return 4;
+    }
+  }
+  tree.num_nodes = int(tree.nodes.size());
+  std::vector<int32_t> nn_out, near_out;
+  for (size_t k = 0; k * 8 < queries.size(); ++k) {
+    const std::vector<double> x(queries.begin() + k * 8, queries.begin() + k * 8 + 8);
+    const Node nn = planner.find_nearest_neighbour_interpolation(&tree, 0, x);
+    nn_out.push_back(nn.node_id);
+    Node x_new = tree.nodes[size_t(nn.node_id)];   // as after insertNode: x_new is in the tree, its id is excluded
+    const std::vector<int> near = planner.find_near_vertices_interpolation(&tree, 0, x_new);
+    near_out.push_back(int32_t(near.size()));
+    near_out.insert(near_out.end(), near.begin(), near.end());
+  }
+  write_raw(dir + "out_nearest.i32", nn_out);
+  write_raw(dir + "out_near.i32", near_out);
+
+  // rewire moves a node (BS:5173-5193): node 3 jumps onto query 0
+  {
+    Node moved = tree.nodes[3];
+    moved.config.assign(queries.begin(), queries.begin() + 8);
+    tree.nodes[3] = moved;
+    planner.updateNode(0, moved);
+    std::vector<int32_t> after(1, planner.find_nearest_neighbour_interpolation(&tree, 0, moved.config).node_id);
+    write_raw(dir + "out_nearest_after_update.i32", after);
+  }
+
+  // ---- compute_FK (KM:278-305) ----
+  std::vector<double> poses;
+  for (size_t s = 0; s < S && s < 64; ++s) {
+    const std::vector<double> p = planner.compute_FK(std::vector<double>(states.begin() + s * 8, states.begin() + s * 8 + 8));
+    poses.insert(poses.end(), p.begin(), p.end());
+  }
+  write_raw(dir + "out_fk.f64", poses);
+  delete collisionChecker;
+  std::printf("test_shim ok: %zu states, %zu nodes, %zu queries\n", S, cost.size(), queries.size() / 8);
+  return 0;
+}
