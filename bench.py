@@ -325,9 +325,16 @@ def side_metrics(ctx, torch, dev, stream, d_q, S):
     out = {}
     d_mask = torch.zeros((S + 31) // 32, dtype=torch.int32, device=dev)
     d_pose = torch.empty((S, 7), dtype=torch.float64, device=dev)
-    ms = t_ms(lambda: ctx.fk_dev(d_q, S, d_pose, stream))
+    ms = t_ms(lambda: ctx.fk_dev(d_q, S, d_pose, stream), n=20, warm=3)
     out["fk_states_per_s"] = S / ms * 1e3
-    out["fk_hbm_frac"] = S * 120 / (ms * 1e-3) / 1e9 / peak
+    out["fk_hbm_frac"] = S * 120 / (ms * 1e-3) / 1e9 / peak          # K2, fp64 chain (default): 120 B/state
+    ctx.set_option("fk_precision", 32)
+    ms = t_ms(lambda: ctx.fk_dev(d_q, S, d_pose, stream), n=20, warm=3)
+    out["fk_fp32chain_states_per_s"] = S / ms * 1e3
+    out["fk_fp32chain_hbm_frac"] = S * 120 / (ms * 1e-3) / 1e9 / peak  # K2, fp32 chain + fp64 base (<= 2e-6 m error)
+    ms = t_ms(lambda: ctx.check_states_dev(d_q, S, api.CHECK_MAP, d_mask, stream), n=10, warm=2)
+    out["map_fp32chain_states_per_s"] = S / ms * 1e3
+    ctx.set_option("fk_precision", 64)
     ms = t_ms(lambda: ctx.check_states_dev(d_q, S, api.CHECK_MAP | api.CHECK_SELF, d_mask, stream))
     out["map_plus_self_states_per_s"] = S / ms * 1e3
     E = S // 21

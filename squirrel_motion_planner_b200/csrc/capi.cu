@@ -40,6 +40,7 @@ struct Ctx {
   int64_t launches = 0;
   int fk_precision = 64;  // 64 | 32 (validity + FK chain arithmetic)
   int fk_float_ok = 0;
+  int chain_specialization = 1;  // 1: use the compile-time unrolled chain when the description matches a known signature
   int nn_variant = 0;     // 0 auto | 1 QT | 2 WQ
   int64_t nn_hit_pool_bytes = int64_t(1) << 30;
   int64_t pipeline_chunk = 1 << 18;  // states per H2D/kernel/D2H pipeline stage
@@ -418,6 +419,8 @@ int sqmp_set_option(sqmp_ctx *ctx, const char *name, int64_t value) {
     if (value != 32 && value != 64) return fail(c, SQMP_ERR_INVALID, "fk_precision must be 32 or 64");
     if (value == 32 && !c->fk_float_ok) return fail(c, SQMP_ERR_INVALID, "float chain needs a translation-only base");
     c->fk_precision = int(value);
+  } else if (n == "chain_specialization") {
+    c->chain_specialization = value != 0;
   } else if (n == "nn_variant") {
     if (value < 0 || value > 2) return fail(c, SQMP_ERR_INVALID, "nn_variant must be 0, 1 or 2");
     c->nn_variant = int(value);
@@ -630,7 +633,7 @@ int sqmp_fk_dev(sqmp_ctx *ctx, const double *d_q, int64_t S, double *d_out, void
   CHECK_CTX();
   if (S < 0 || (S > 0 && (!d_q || !d_out))) return fail(c, SQMP_ERR_INVALID, "fk_dev: null pointer");
   if (S == 0) return SQMP_OK;
-  CU(launch_fk(c->rb, d_q, S, d_out, c->fk_precision, (cudaStream_t)stream));
+  CU(launch_fk(c->rb, d_q, S, d_out, c->fk_precision, c->chain_specialization != 0, (cudaStream_t)stream));
   c->launches += 1;
   return SQMP_OK;
 }

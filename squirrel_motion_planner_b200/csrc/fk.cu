@@ -16,9 +16,9 @@ namespace sqmp {
 
 constexpr int FK_TILE = 128;  // states per CTA iteration == threads per CTA
 // row pitches in shared memory (doubles).  Input rows keep the global pitch (8) because the bulk copy is a flat
-// byte copy; reading q[j] of row t hits bank pair (16 t + 2 j) mod 32: threads t and t+2 collide (16-way).  The
-// reads are therefore rotated per thread (column (j + t/2) mod 8), which makes the 8-byte accesses of a
-// half-warp hit 16 distinct bank pairs.  Outputs use pitch 7 (odd) and are conflict-free as they are.
+// byte copy; each joint value is read from the tile exactly once, when its chain segment needs it (the 8-way bank
+// conflict of that strided LDS.64 costs ~60 cycles per warp against ~900 instructions of chain arithmetic).
+// Outputs use pitch 7 (odd) and are conflict-free as they are.
 constexpr int FK_IN_PITCH = 8, FK_OUT_PITCH = 7;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -56,28 +56,35 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// The chain for one state: T = double everywhere, or T = float for the rotational part with the prismatic base
-// added in double (see DESIGN.md for the error budget against the 1e-5 m / 1e-5 rad tolerance).
-template <typename T>
-__device__ __forceinline__ void fk_one(const RobotDev &rb, const double (&q)[SQMP_DOF], double *out7) {
+// The chain for one state, its joint vector read straight from the shared-memory tile row (no register copy):
+// T = double everywhere, or T = float for the rotational part with the prismatic base added in double (see DESIGN.md
+// for the error budget against the 1e-5 m / 1e-5 rad tolerance).
+template <typename T, typename SIG>
+__device__ __forceinline__ void fk_one(const RobotDev &rb, const double *q_row, double *out7) {
   Frame<T> f;
   frame_set_translation<T>(f, T(0), T(0), T(0));
   double off[3] = {0.0, 0.0, 0.0};
-  int sg0 = 0;
-  if (sizeof(T) == 4) {
-    for (int sg = 0; sg <= rb.ref_seg; ++sg) {
-      const int qi = rb.seg_qidx[sg];
-      double qv = q[0];
+  if constexpr (SIG::generic) {
+    int sg0 = 0;
+    if (sizeof(T) == 4) {
+      for (int sg = 0; sg <= rb.ref_seg; ++sg) {
+        const double qv = q_row[rb.seg_qidx[sg]];
 #pragma unroll
-      for (int j = 1; j < SQMP_DOF; ++j) qv = (qi == j) ? q[j] : qv;
-#pragma unroll
-      for (int i = 0; i < 3; ++i) off[i] += rb.seg_pre[sg][9 + i] + rb.seg_axis[sg][i] * qv;
+        for (int i = 0; i < 3; ++i) off[i] += rb.seg_pre[sg][9 + i] + rb.seg_axis[sg][i] * qv;
+      }
+      sg0 = rb.ref_seg + 1;
     }
-    sg0 = rb.ref_seg + 1;
+    for (int sg = sg0; sg < rb.n_seg; ++sg) frame_advance_smem<T>(f, rb, sg, q_row, 1);
+    if (sizeof(T) == 4) frame_mul_const<T>(f, rb.ee_tip_f, rb.ee_tip_kind);
+    else frame_mul_const<T>(f, rb.ee_tip, rb.ee_tip_kind);
+  } else {
+    // leading prismatic x, y (identity pre-frames, signature): a plain fp64 offset in both precisions
+    off[0] = q_row[0];
+    off[1] = q_row[1];
+    chain_walk_sig<T, SIG, 2, SIG::n>(f, rb, q_row, 1);
+    if (sizeof(T) == 4) frame_mul_const<T>(f, rb.ee_tip_f, SIG::ee_kind);
+    else frame_mul_const<T>(f, rb.ee_tip, SIG::ee_kind);
   }
-  for (int sg = sg0; sg < rb.n_seg; ++sg) frame_advance<T>(f, rb, sg, q);
-  if (sizeof(T) == 4) frame_mul_const<T>(f, rb.ee_tip_f, rb.ee_tip_kind);
-  else frame_mul_const<T>(f, rb.ee_tip, rb.ee_tip_kind);
   double R[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) R[i] = double(f.r[i]);
@@ -87,7 +94,7 @@ __device__ __forceinline__ void fk_one(const RobotDev &rb, const double (&q)[SQM
   get_quaternion(R, out7[3], out7[4], out7[5], out7[6]);
 }
 
-template <typename T>
+template <typename T, typename SIG>
 __global__ void __launch_bounds__(FK_TILE)
 k2_fk(const __grid_constant__ RobotDev rb, const double *__restrict__ q_in, int64_t S, double *__restrict__ out) {
   __shared__ __align__(128) double s_in[2][FK_TILE * FK_IN_PITCH];
@@ -125,19 +132,8 @@ k2_fk(const __grid_constant__ RobotDev rb, const double *__restrict__ q_in, int6
 
     const int rows = tile_rows(tile);
     if (t < rows) {
-      double q[SQMP_DOF];
-      const double *row = s_in[buf] + t * FK_IN_PITCH;
-      const int rot = (t >> 1) & 7;
-#pragma unroll
-      for (int j = 0; j < SQMP_DOF; ++j) {
-        const double v = row[(j + rot) & 7];  // element (j+rot)&7 -> register slot decided below
-        // scatter v into q[(j+rot)&7] without dynamic register indexing
-#pragma unroll
-        for (int m = 0; m < SQMP_DOF; ++m)
-          if (((j + rot) & 7) == m) q[m] = v;
-      }
       double o[7];
-      fk_one<T>(rb, q, o);
+      fk_one<T, SIG>(rb, s_in[buf] + t * FK_IN_PITCH, o);   // 8 LDS.64 per state (8-way bank conflicts: ~1 % of the work)
       // the previous tile's bulk store must have finished reading s_out before it is overwritten
       // (wait executed by the issuing thread below, made visible to all by the __syncthreads)
       if (rows == FK_TILE) {
@@ -164,18 +160,26 @@ k2_fk(const __grid_constant__ RobotDev rb, const double *__restrict__ q_in, int6
 }
 
 cudaError_t launch_fk(const RobotDev &rb, const double *d_q, int64_t S, double *d_out, int fk_precision,
-                      cudaStream_t st) {
+                      bool allow_specialized, cudaStream_t st) {
   if (S <= 0) return cudaSuccess;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static int sms = 0;   // one device kind per process (B200)
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
   const int64_t n_tiles = (S + FK_TILE - 1) / FK_TILE;
   // persistent CTAs: a multiple of the SM count, enough resident warps to cover the fp64 latency
   const unsigned blocks = unsigned(imin64(n_tiles, int64_t(sms) * 8));
-  if (fk_precision == 32)
-    k2_fk<float><<<blocks, FK_TILE, 0, st>>>(rb, d_q, S, d_out);
-  else
-    k2_fk<double><<<blocks, FK_TILE, 0, st>>>(rb, d_q, S, d_out);
+  const bool robotino = allow_specialized && chain_matches<SigRobotino>(rb);   // structure known at compile time: unrolled chain
+  if (fk_precision == 32) {
+    if (robotino) k2_fk<float, SigRobotino><<<blocks, FK_TILE, 0, st>>>(rb, d_q, S, d_out);
+    else k2_fk<float, SigGeneric><<<blocks, FK_TILE, 0, st>>>(rb, d_q, S, d_out);
+  } else {
+    if (robotino) k2_fk<double, SigRobotino><<<blocks, FK_TILE, 0, st>>>(rb, d_q, S, d_out);
+    else k2_fk<double, SigGeneric><<<blocks, FK_TILE, 0, st>>>(rb, d_q, S, d_out);
+  }
   return cudaGetLastError();
 }
 

@@ -19,6 +19,17 @@ struct Frame {
 
 template <typename T>
 __device__ __forceinline__ void sincos_t(T x, T *s, T *c);
+// Coefficients live in the constant bank so that every Horner step is ONE DFMA with a c[bank][offset] operand; as
+// literals the compiler materialises each 64-bit constant with two UMOVs per use (3 issue slots per step).
+static __constant__ double SQMP_SC64[18] = {
+    0.63661977236758138243,                                   // [0] 2/pi
+    1.57079632673412561417e+00, 6.07710050630396597660e-11, 2.02226624871116645580e-21,   // [1..3] pi/2 in 3 parts
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,  // [4..9] sin kernel S6..S1
+    -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, // [10..15] cos kernel C6..C1
+    2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02,
+    -0.5, 1.0};
+
 // fp64 sincos for joint angles: Cody-Waite reduction by pi/2 in three parts (exact for |k| < 2^20, i.e. |x| < 1e5;
 // larger arguments take the library path) + the fdlibm minimax kernels on [-pi/4, pi/4].  <= ~1.5 ulp, about a
 // quarter of the instructions of the general-purpose library routine (no Payne-Hanek set-up, no special cases).
@@ -28,30 +39,53 @@ __device__ __forceinline__ void sincos_t<double>(double x, double *sn, double *c
     sincos(x, sn, cs);
     return;
   }
-  const double kd = rint(x * 0.63661977236758138243);  // 2/pi
+  const double *C = SQMP_SC64;
+  const double kd = rint(x * C[0]);
   const int k = int(kd);
-  double r = fma(-kd, 1.57079632673412561417e+00, x);  // pi/2 split: 33 + 33 + 53 bits (fdlibm pio2_1, pio2_2, pio2_3)
-  r = fma(-kd, 6.07710050630396597660e-11, r);
-  r = fma(-kd, 2.02226624871116645580e-21, r);
+  double r = fma(-kd, C[1], x);
+  r = fma(-kd, C[2], r);
+  r = fma(-kd, C[3], r);
   const double z = r * r;
-  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-  ps = fma(ps, z, 2.75573137070700676789e-06);
-  ps = fma(ps, z, -1.98412698298579493134e-04);
-  ps = fma(ps, z, 8.33333333332248946124e-03);
-  ps = fma(ps, z, -1.66666666666666324348e-01);
+  double ps = fma(z, C[4], C[5]);
+  ps = fma(ps, z, C[6]);
+  ps = fma(ps, z, C[7]);
+  ps = fma(ps, z, C[8]);
+  ps = fma(ps, z, C[9]);
   const double sr = fma(ps * z, r, r);
-  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-  pc = fma(pc, z, -2.75573143513906633035e-07);
-  pc = fma(pc, z, 2.48015872894767294178e-05);
-  pc = fma(pc, z, -1.38888888888741095749e-03);
-  pc = fma(pc, z, 4.16666666666666019037e-02);
-  const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+  double pc = fma(z, C[10], C[11]);
+  pc = fma(pc, z, C[12]);
+  pc = fma(pc, z, C[13]);
+  pc = fma(pc, z, C[14]);
+  pc = fma(pc, z, C[15]);
+  const double cr = fma(z * z, pc, fma(z, C[16], C[17]));
   const double s0 = (k & 1) ? cr : sr, c0 = (k & 1) ? sr : cr;
   *sn = (k & 2) ? -s0 : s0;
   *cs = ((k + 1) & 2) ? -c0 : c0;
 }
+
+// fp32 counterpart (Cody-Waite in three parts, cephes sinf/cosf kernels on [-pi/4, pi/4]): <= 2 ulp for |x| < 8e3.
 template <>
-__device__ __forceinline__ void sincos_t<float>(float x, float *s, float *c) { sincosf(x, s, c); }
+__device__ __forceinline__ void sincos_t<float>(float x, float *sn, float *cs) {
+  if (!(fabsf(x) < 8.0e3f)) {
+    sincosf(x, sn, cs);
+    return;
+  }
+  const float kf = rintf(x * 0.636619772f);
+  const int k = int(kf);
+  float r = fmaf(-kf, 1.5703125f, x);              // pi/2 = 1.5703125 + 4.837512969970703125e-4 + 7.54978995489188e-8
+  r = fmaf(-kf, 4.837512969970703125e-4f, r);
+  r = fmaf(-kf, 7.54978995489188e-8f, r);
+  const float z = r * r;
+  float ps = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
+  ps = fmaf(ps, z, -1.6666654611e-1f);
+  const float sr = fmaf(ps * z, r, r);
+  float pc = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  pc = fmaf(pc, z, 4.166664568298827e-2f);
+  const float cr = fmaf(z * z, pc, fmaf(z, -0.5f, 1.0f));
+  const float s0 = (k & 1) ? cr : sr, c0 = (k & 1) ? sr : cr;
+  *sn = (k & 2) ? -s0 : s0;
+  *cs = ((k + 1) & 2) ? -c0 : c0;
+}
 
 template <typename T>
 __device__ __forceinline__ void frame_set_translation(Frame<T> &f, T x, T y, T z) {
@@ -167,33 +201,90 @@ __device__ __forceinline__ void frame_advance_smem(Frame<T> &f, const RobotDev &
   }
 }
 
-// KDL::Rotation::GetQuaternion (frames.cpp) — same branch structure so signs match the reference.
+// ---------------------------------------------------------------------------------------------------------------
+// Compile-time chain signatures.  The reference hard-codes its robot (eight named joint links, CC:216-255; 8 DOF,
+// BS:6868-6870), so the structure of the chain — joint types, axis codes, which pre-frames are identity /
+// translation / general — is known when this library is compiled; only the numbers come from the description at
+// run time.  A kernel instantiated on a signature unrolls the chain with no interpreter (no per-segment branches,
+// no jump table, constant-bank operands at fixed offsets); the host uses it only when the loaded description
+// matches the signature exactly and otherwise falls back to the generic interpreter above.
+// ---------------------------------------------------------------------------------------------------------------
+struct SigGeneric {
+  static constexpr bool generic = true;
+};
+struct SigRobotino {   // robotino_plan.urdf: x, y prismatic; theta about z; arm joints -y, +y, +z, -y, +z
+  static constexpr bool generic = false;
+  static constexpr int n = 8;
+  __host__ __device__ static constexpr int type(int s) { return s < 2 ? SQMP_JOINT_TRANS : SQMP_JOINT_ROT; }
+  __host__ __device__ static constexpr int axis(int s) {
+    return s == 0 ? AX_PX : s == 1 ? AX_PY : s == 2 ? AX_PZ : s == 3 ? AX_NY : s == 4 ? AX_PY : s == 5 ? AX_PZ : s == 6 ? AX_NY : AX_PZ;
+  }
+  __host__ __device__ static constexpr int kind(int s) { return s < 3 ? 0 : (s == 3 ? 2 : 1); }
+  static constexpr int ee_kind = 2;
+};
+template <typename SIG>
+inline bool chain_matches(const RobotDev &rb) {
+  if (rb.n_seg != SIG::n || rb.ee_tip_kind != SIG::ee_kind) return false;
+  for (int s = 0; s < SIG::n; ++s)
+    if (rb.seg_type[s] != SIG::type(s) || rb.seg_axis_code[s] != SIG::axis(s) || rb.seg_pre_kind[s] != SIG::kind(s) ||
+        rb.seg_qidx[s] != s)
+      return false;
+  return true;
+}
+
+template <typename T, typename SIG, int S>
+__device__ __forceinline__ void frame_advance_sig(Frame<T> &f, const RobotDev &rb, const double *q_mine, int pitch) {
+  if constexpr (S < SIG::n) {
+    const T qv = T(q_mine[S * pitch]);   // signature guarantees seg_qidx[s] == s
+    if (sizeof(T) == 4) {
+      frame_mul_const<T>(f, rb.seg_pre_f[S], SIG::kind(S));
+      frame_joint_motion<T>(f, SIG::type(S), SIG::axis(S), rb.seg_axis_f[S], qv);
+    } else {
+      frame_mul_const<T>(f, rb.seg_pre[S], SIG::kind(S));
+      frame_joint_motion<T>(f, SIG::type(S), SIG::axis(S), rb.seg_axis[S], qv);
+    }
+  }
+}
+template <typename T, typename SIG, int S0, int S1>
+__device__ __forceinline__ void chain_walk_sig(Frame<T> &f, const RobotDev &rb, const double *q_mine, int pitch) {
+  if constexpr (S0 < S1) {
+    frame_advance_sig<T, SIG, S0>(f, rb, q_mine, pitch);
+    chain_walk_sig<T, SIG, S0 + 1, S1>(f, rb, q_mine, pitch);
+  }
+}
+
+// KDL::Rotation::GetQuaternion (frames.cpp) — same branch structure so signs match the reference.  Every branch
+// needs 1/sqrt(t) and sqrt(t) of one value t: both come from one rsqrt (s = t * rsqrt(t)), no division.
 __device__ __forceinline__ void get_quaternion(const double *R, double &x, double &y, double &z, double &w) {
   const double trace = R[0] + R[4] + R[8];
   if (trace > 1e-12) {
-    const double s = 0.5 / sqrt(trace + 1.0);
-    w = 0.25 / s;
+    const double t = trace + 1.0, rs = rsqrt(t);
+    const double s = 0.5 * rs;          // 0.5 / sqrt(t)
+    w = 0.5 * (t * rs);                 // 0.25 / s
     x = (R[7] - R[5]) * s;
     y = (R[2] - R[6]) * s;
     z = (R[3] - R[1]) * s;
   } else if (R[0] > R[4] && R[0] > R[8]) {
-    const double s = 2.0 * sqrt(1.0 + R[0] - R[4] - R[8]);
-    w = (R[7] - R[5]) / s;
-    x = 0.25 * s;
-    y = (R[1] + R[3]) / s;
-    z = (R[2] + R[6]) / s;
+    const double t = 1.0 + R[0] - R[4] - R[8], rs = rsqrt(t);
+    const double is = 0.5 * rs;         // 1 / s with s = 2 sqrt(t)
+    w = (R[7] - R[5]) * is;
+    x = 0.5 * (t * rs);                 // 0.25 * s
+    y = (R[1] + R[3]) * is;
+    z = (R[2] + R[6]) * is;
   } else if (R[4] > R[8]) {
-    const double s = 2.0 * sqrt(1.0 + R[4] - R[0] - R[8]);
-    w = (R[2] - R[6]) / s;
-    x = (R[1] + R[3]) / s;
-    y = 0.25 * s;
-    z = (R[5] + R[7]) / s;
+    const double t = 1.0 + R[4] - R[0] - R[8], rs = rsqrt(t);
+    const double is = 0.5 * rs;
+    w = (R[2] - R[6]) * is;
+    x = (R[1] + R[3]) * is;
+    y = 0.5 * (t * rs);
+    z = (R[5] + R[7]) * is;
   } else {
-    const double s = 2.0 * sqrt(1.0 + R[8] - R[0] - R[4]);
-    w = (R[3] - R[1]) / s;
-    x = (R[2] + R[6]) / s;
-    y = (R[5] + R[7]) / s;
-    z = 0.25 * s;
+    const double t = 1.0 + R[8] - R[0] - R[4], rs = rsqrt(t);
+    const double is = 0.5 * rs;
+    w = (R[3] - R[1]) * is;
+    x = (R[2] + R[6]) * is;
+    y = (R[5] + R[7]) * is;
+    z = 0.5 * (t * rs);
   }
 }
 

@@ -80,7 +80,7 @@ cudaError_t launch_first_invalid(const uint32_t *d_mask, int64_t E, int P1, int3
 cudaError_t launch_get_collisions(const RobotDev &rb, const GridDev &gd, const SelfPair *pairs, int n_pairs,
                                   const double *d_q, uint8_t *d_sphere_hit, uint8_t *d_pair_hit, cudaStream_t st);
 cudaError_t launch_fk(const RobotDev &rb, const double *d_q, int64_t S, double *d_out, int fk_precision,
-                      cudaStream_t st);
+                      bool allow_specialized, cudaStream_t st);
 cudaError_t launch_ft_build(const uint32_t *d_occ, int row_words, int gx, int gy, int gz, int window,
                             int8_t *d_tmp_a, uint16_t *d_tmp_b, uint8_t *d_lb2, uint16_t *d_ft, cudaStream_t st,
                             int *n_launch);

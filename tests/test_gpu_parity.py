@@ -173,9 +173,12 @@ def _fk_err(a, b):
     return pos, ang
 
 
+@pytest.mark.parametrize("specialized", [1, 0])
 @pytest.mark.parametrize("prec", [64, 32])
-def test_fk_matches_oracle_and_golden(ctx, orc, prec):
+def test_fk_matches_oracle_and_golden(ctx, orc, prec, specialized):
+    """specialized=1: compile-time unrolled chain (signature of the reference's robot); 0: generic chain interpreter."""
     ctx.set_option("fk_precision", prec)
+    ctx.set_option("chain_specialization", specialized)
     try:
         g = np.load(os.path.join(GOLDEN, "fk_scipy.npz"))
         got = ctx.fk(g["q"])
@@ -190,6 +193,7 @@ def test_fk_matches_oracle_and_golden(ctx, orc, prec):
                 assert np.abs(got - ref).max() < 1e-12               # same quaternion sign convention too
     finally:
         ctx.set_option("fk_precision", 64)
+        ctx.set_option("chain_specialization", 1)
 
 
 # --------------------------------------------------------------------------------------- near neighbours
