@@ -171,6 +171,17 @@ static int refresh_grid_robot(Ctx *c) {
   return SQMP_OK;
 }
 
+// |node|^2 bound used by the fp32 pre-filter of K3/K4 (nn.cu); non-finite rows make it +inf (= no filtering)
+static void tree_track_norm(TreeDev &t, const double *q, int64_t n) {
+  double m = t.rmax2;
+  for (int64_t i = 0; i < n; ++i) {
+    double s = 0.0;
+    for (int d = 0; d < SQMP_DOF; ++d) s += q[i * SQMP_DOF + d] * q[i * SQMP_DOF + d];
+    if (!(s <= m)) m = (s == s) ? s : INFINITY;
+  }
+  t.rmax2 = m;
+}
+
 static int tree_reserve(Ctx *c, TreeDev &t, int64_t need) {
   if (need <= t.cap) return SQMP_OK;
   int64_t cap = t.cap > 0 ? t.cap : 4096;
@@ -191,9 +202,31 @@ static int tree_reserve(Ctx *c, TreeDev &t, int64_t need) {
       }
     }
   }
+  // fp32 shadow (float4 + float4 + float per node)
+  float4 *fa = nullptr, *fb = nullptr;
+  float *fn = nullptr;
+  e = cudaMalloc(&fa, size_t(pitch) * sizeof(float4));
+  if (e == cudaSuccess) e = cudaMalloc(&fb, size_t(pitch) * sizeof(float4));
+  if (e == cudaSuccess) e = cudaMalloc(&fn, size_t(pitch) * sizeof(float));
+  if (e == cudaSuccess && t.n > 0) {
+    e = cudaMemcpy(fa, t.fa, size_t(t.n) * sizeof(float4), cudaMemcpyDeviceToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(fb, t.fb, size_t(t.n) * sizeof(float4), cudaMemcpyDeviceToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(fn, t.fn, size_t(t.n) * sizeof(float), cudaMemcpyDeviceToDevice);
+  }
+  if (e != cudaSuccess) {
+    cudaFree(blk);
+    if (fa) cudaFree(fa);
+    if (fb) cudaFree(fb);
+    if (fn) cudaFree(fn);
+    return fail(c, SQMP_ERR_NOMEM, "cudaMalloc(tree fp32 shadow)", e);
+  }
   if (t.q[0]) cudaFree(t.q[0]);
+  if (t.fa) cudaFree(t.fa);
+  if (t.fb) cudaFree(t.fb);
+  if (t.fn) cudaFree(t.fn);
   for (int d = 0; d < SQMP_DOF; ++d) t.q[d] = blk + int64_t(d) * pitch;
   t.cost = blk + int64_t(SQMP_DOF) * pitch;
+  t.fa = fa; t.fb = fb; t.fn = fn;
   t.cap = cap;
   return SQMP_OK;
 }
@@ -208,14 +241,15 @@ static double sumsq_threshold(double r) {
 }
 
 static int pick_variant(const Ctx *c, int64_t Q) {
-  if (c->nn_variant == 1 || c->nn_variant == 2) return c->nn_variant;
-  return Q >= 2048 ? 1 : 2;
+  if (c->nn_variant >= 1 && c->nn_variant <= 3) return c->nn_variant;
+  return Q >= 2048 ? 3 : 2;
 }
 static int pick_chunk_hint(const Ctx *c, int variant, int64_t N, int64_t Q) {
   if (N <= 0) return 1;
   int64_t chunks;
-  if (variant == 1) {
-    const int64_t qtiles = (Q + 127) / 128;
+  if (variant == 1 || variant == 3) {
+    const int64_t per = variant == 3 ? 256 : 128;   // queries per CTA (nn.cu: NN_THREADS * NN_QPT)
+    const int64_t qtiles = (Q + per - 1) / per;
     chunks = (int64_t(c->sm_count) * 16 + qtiles - 1) / qtiles;
     const int64_t maxc = (N + 2047) / 2048;
     if (chunks > maxc) chunks = maxc;
@@ -397,8 +431,12 @@ void sqmp_destroy(sqmp_ctx *ctx) {
   if (ctx->d_occ) cudaFree(ctx->d_occ);
   if (ctx->d_lb2) cudaFree(ctx->d_lb2);
   if (ctx->d_ft) cudaFree(ctx->d_ft);
-  for (auto &t : ctx->trees)
+  for (auto &t : ctx->trees) {
     if (t.q[0]) cudaFree(t.q[0]);
+    if (t.fa) cudaFree(t.fa);
+    if (t.fb) cudaFree(t.fb);
+    if (t.fn) cudaFree(t.fn);
+  }
   if (ctx->nn.part_d) cudaFree(ctx->nn.part_d);
   if (ctx->nn.part_id) cudaFree(ctx->nn.part_id);
   if (ctx->nn.hits) cudaFree(ctx->nn.hits);
@@ -422,7 +460,7 @@ int sqmp_set_option(sqmp_ctx *ctx, const char *name, int64_t value) {
   } else if (n == "chain_specialization") {
     c->chain_specialization = value != 0;
   } else if (n == "nn_variant") {
-    if (value < 0 || value > 2) return fail(c, SQMP_ERR_INVALID, "nn_variant must be 0, 1 or 2");
+    if (value < 0 || value > 3) return fail(c, SQMP_ERR_INVALID, "nn_variant must be 0..3");
     c->nn_variant = int(value);
   } else if (n == "nn_hit_pool_bytes") {
     if (value < 4096) return fail(c, SQMP_ERR_INVALID, "nn_hit_pool_bytes too small");
@@ -664,6 +702,7 @@ int sqmp_tree_reset(sqmp_ctx *ctx, int tree) {
   CHECK_CTX();
   CHECK_TREE();
   t.n = 0;
+  t.rmax2 = 0.0;
   return SQMP_OK;
 }
 int sqmp_tree_size(sqmp_ctx *ctx, int tree, int64_t *n_out) {
@@ -680,6 +719,7 @@ int sqmp_tree_append(sqmp_ctx *ctx, int tree, const double q[SQMP_DOF], double c
   CU(cudaStreamSynchronize(c->streams[0]));
   int rc = tree_reserve(c, t, t.n + 1);
   if (rc) return rc;
+  tree_track_norm(t, q, 1);
   CU(launch_tree_set_one(t, t.n, q, cost, c->streams[0]));
   CU(cudaStreamSynchronize(c->streams[0]));
   c->launches += 1;
@@ -703,6 +743,7 @@ int sqmp_tree_append_batch(sqmp_ctx *ctx, int tree, const double *q, const doubl
   cudaStream_t st = c->streams[0];
   CU(cudaMemcpyAsync(dq, q, size_t(n) * SQMP_DOF * 8, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(dc, cost, size_t(n) * 8, cudaMemcpyHostToDevice, st));
+  tree_track_norm(t, q, n);
   CU(launch_tree_append(t, (const double *)dq, (const double *)dc, t.n, n, st));
   CU(cudaStreamSynchronize(st));
   c->launches += 1;
@@ -713,6 +754,7 @@ int sqmp_tree_update(sqmp_ctx *ctx, int tree, int32_t id, const double q[SQMP_DO
   CHECK_CTX();
   CHECK_TREE();
   if (!q || id < 0 || id >= t.n) return fail(c, SQMP_ERR_INVALID, "tree_update: bad id");
+  tree_track_norm(t, q, 1);
   CU(launch_tree_set_one(t, id, q, cost, c->streams[0]));
   CU(cudaStreamSynchronize(c->streams[0]));
   c->launches += 1;
@@ -780,7 +822,7 @@ int sqmp_nn_radius_dev(sqmp_ctx *ctx, int tree, const double *d_queries, const i
   int rc = nn_prepare(c, Q, hint, true, t.n);
   if (rc) return rc;
   int nl = 0;
-  CU(launch_nn_radius(t, d_queries, d_exclude, Q, sumsq_threshold(r), k, d_low, d_high, d_count, d_overflow, c->nn,
+  CU(launch_nn_radius(t, d_queries, d_exclude, Q, sumsq_threshold(r), r, k, d_low, d_high, d_count, d_overflow, c->nn,
                       hint, variant, st, &nl));
   c->launches += nl;
   return SQMP_OK;

@@ -30,12 +30,28 @@ namespace sqmp {
 struct TreePtrs {
   double *q[SQMP_DOF];
   double *cost;
+  float4 *fa, *fb;
+  float *fn;
 };
 static inline TreePtrs ptrs_of(const TreeDev &t) {
   TreePtrs p;
   for (int d = 0; d < SQMP_DOF; ++d) p.q[d] = t.q[d];
   p.cost = t.cost;
+  p.fa = t.fa; p.fb = t.fb; p.fn = t.fn;
   return p;
+}
+// fp32 shadow of one node (see TreeDev)
+__device__ __forceinline__ void write_shadow(const TreePtrs &t, int64_t i, const double (&v)[SQMP_DOF]) {
+  float f[SQMP_DOF];
+  double n2 = 0.0;
+#pragma unroll
+  for (int d = 0; d < SQMP_DOF; ++d) {
+    f[d] = __double2float_rn(v[d]);
+    n2 += double(f[d]) * double(f[d]);
+  }
+  t.fa[i] = make_float4(f[0], f[1], f[2], f[3]);
+  t.fb[i] = make_float4(f[4], f[5], f[6], f[7]);
+  t.fn[i] = __double2float_rn(n2);
 }
 
 // rows (AoS, n x 8) -> SoA at [first, first+n)
@@ -48,6 +64,8 @@ __global__ void k_tree_append(TreePtrs t, const double *__restrict__ rows, const
   t.q[0][first + i] = a.x; t.q[1][first + i] = a.y; t.q[2][first + i] = a.z; t.q[3][first + i] = a.w;
   t.q[4][first + i] = b.x; t.q[5][first + i] = b.y; t.q[6][first + i] = b.z; t.q[7][first + i] = b.w;
   t.cost[first + i] = cost[i];
+  const double v[SQMP_DOF] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  write_shadow(t, first + i, v);
 }
 struct OneNode {
   double q[SQMP_DOF];
@@ -56,6 +74,7 @@ struct OneNode {
 __global__ void k_tree_set_one(TreePtrs t, int64_t id, OneNode v) {
   if (threadIdx.x < SQMP_DOF) t.q[threadIdx.x][id] = v.q[threadIdx.x];
   if (threadIdx.x == SQMP_DOF) t.cost[id] = v.cost;
+  if (threadIdx.x == SQMP_DOF + 1) write_shadow(t, id, v.q);
 }
 __global__ void k_tree_update_costs(TreePtrs t, const int32_t *__restrict__ ids, const double *__restrict__ cost,
                                     int64_t n, int64_t size) {
@@ -236,6 +255,156 @@ k_nn_wq(TreePtrs t, int64_t N, int64_t chunk_len, int chunks, const double *__re
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// K3/K4 — QT variant with a SOUND fp32 pre-filter.  grid = (ceil(Q / (128 * NN_QPT)), chunks)
+//
+// The exact test costs 24 fp64 instructions per (query, node) pair and the fp64 pipe issues at half rate.  Here every
+// pair first gets an fp32 estimate of the squared distance in the expanded form
+//     s~ = (|q^|^2 + |n^|^2) + sum_i (-2 q^_i) n^_i          (1 FADD + 8 FFMA, q^ = fl32(q), n^ = fl32(n))
+// whose error against the reference's fp64 value s is bounded rigorously:
+//     |s~ - s| <= 2 u R sqrt(s) + 37 u R^2,   u = 2^-23,  R >= max(|q|, |n|)      (input rounding + 18 fp32 roundings of
+//                                                                                  partial sums bounded by 4 R^2)
+// A node can replace the incumbent only if s < s_best, and then s~ < s_best + E with E = 4 u R d_best + 64 u R^2
+// (twice the bound).  Pairs with s~ >= that threshold are skipped — provably without changing the result; the few
+// that pass are evaluated exactly as before (same fp64 operations, same order, same comparisons), so ids stay
+// bit-identical to the CPU's.  Radius mode: s~ + E < s_thr is a proven hit, s~ - E >= s_thr a proven miss, only
+// the band in between is evaluated in fp64.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int NN_GROUP = 4;        // nodes whose estimates are taken before the one (rare) branch
+constexpr int NN_QPT = 2;          // queries per thread: the three LDS of a node are shared by both
+constexpr double NN_U = 1.1920928955078125e-07;   // 2^-23
+
+__device__ __forceinline__ float estimate_s(const float (&m2q)[SQMP_DOF], float qq, const float4 a, const float4 b, float nn) {
+  float s = qq + nn;
+  s = fmaf(m2q[0], a.x, s); s = fmaf(m2q[1], a.y, s); s = fmaf(m2q[2], a.z, s); s = fmaf(m2q[3], a.w, s);
+  s = fmaf(m2q[4], b.x, s); s = fmaf(m2q[5], b.y, s); s = fmaf(m2q[6], b.z, s); s = fmaf(m2q[7], b.w, s);
+  return s;
+}
+// __noinline__: inlined, the compiler hoists its sixteen 64-bit address computations above the (rarely taken) branch
+// and they become a third of all executed instructions.
+__device__ __noinline__ double exact_s(const TreePtrs &t, int64_t n, const double *__restrict__ query) {
+  double node[SQMP_DOF], q[SQMP_DOF];
+#pragma unroll
+  for (int d = 0; d < SQMP_DOF; ++d) { node[d] = t.q[d][n]; q[d] = query[d]; }
+  return sumsq8(node, q);
+}
+
+template <bool RADIUS>
+__global__ void __launch_bounds__(NN_THREADS)
+k_nn_qt_pf(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ queries, int64_t Q, double rmax2,
+           double *__restrict__ part_d, int32_t *__restrict__ part_id,
+           // radius mode
+           const int32_t *__restrict__ exclude, double s_thr, double r, int32_t *__restrict__ count,
+           int32_t *__restrict__ hits, int64_t hit_cap) {
+  __shared__ __align__(16) float tile[NN_TILE][12];   // per node: q0..q7, |n|^2, pad — one base register, immediates
+  int64_t qi[NN_QPT];
+  bool active[NN_QPT];
+  float m2q[NN_QPT][SQMP_DOF], qq[NN_QPT];
+  float thr_lo[NN_QPT];   // nearest: s~ >= thr_lo cannot win.  radius: s~ < thr_lo is a proven hit
+  float thr_hi[NN_QPT];   // radius: s~ >= thr_hi is a proven miss
+  double eR[NN_QPT], eR2[NN_QPT];   // 4 u R and 64 u R^2 of this query
+  Best best[NN_QPT];
+  int32_t excl[NN_QPT];
+#pragma unroll
+  for (int k = 0; k < NN_QPT; ++k) {
+    qi[k] = (int64_t(blockIdx.x) * NN_QPT + k) * NN_THREADS + threadIdx.x;
+    active[k] = qi[k] < Q;
+    const double *qp = queries + (active[k] ? qi[k] : 0) * SQMP_DOF;
+    double qn2 = 0.0, qq_d = 0.0;
+#pragma unroll
+    for (int d = 0; d < SQMP_DOF; ++d) {
+      const double v = qp[d];
+      const float f = __double2float_rn(v);
+      m2q[k][d] = -2.0f * f;
+      qn2 += v * v;
+      qq_d += double(f) * double(f);
+    }
+    qq[k] = __double2float_rn(qq_d);
+    const double R2 = fmax(rmax2, qn2) * 1.000001;
+    eR[k] = 4.0 * NN_U * sqrt(R2);
+    eR2[k] = 64.0 * NN_U * R2;
+    best[k].s = NN_INIT_SUMSQ; best[k].d = NN_INIT_DIST; best[k].id = 0;
+    excl[k] = (RADIUS && active[k] && exclude) ? exclude[qi[k]] : -1;
+    if (RADIUS) {
+      const double E = eR[k] * r + eR2[k];
+      // the "proven hit" direction needs s - 2uR sqrt(s) increasing at s_thr, i.e. r >> u R: otherwise exact only
+      thr_lo[k] = (r > 1.0e3 * NN_U * sqrt(R2)) ? __double2float_rd(s_thr - E) : -CUDART_INF_F;
+      thr_hi[k] = __double2float_ru(s_thr + E);
+    } else {
+      thr_lo[k] = __double2float_ru(NN_INIT_SUMSQ + eR[k] * NN_INIT_DIST + eR2[k]);
+      thr_hi[k] = 0.0f;
+    }
+    if (!active[k]) { thr_lo[k] = -CUDART_INF_F; thr_hi[k] = -CUDART_INF_F; }
+  }
+  const int64_t n0 = int64_t(blockIdx.y) * chunk_len, n1 = min(N, n0 + chunk_len);
+
+  for (int64_t base = n0; base < n1; base += NN_TILE) {
+    const int len = int(imin64(NN_TILE, n1 - base));
+    __syncthreads();
+    for (int i = threadIdx.x; i < NN_TILE; i += NN_THREADS) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      float nn = CUDART_INF_F;   // pad nodes: estimate = +inf, never passes a threshold
+      if (i < len) { a = t.fa[base + i]; b = t.fb[base + i]; nn = t.fn[base + i]; }
+      *reinterpret_cast<float4 *>(&tile[i][0]) = a;
+      *reinterpret_cast<float4 *>(&tile[i][4]) = b;
+      tile[i][8] = nn;
+    }
+    __syncthreads();
+    // whole tile (pad nodes are inert), NN_GROUP nodes at a time: all estimates first, ONE branch per group — the
+    // exact path is re-entered per (node, query) only inside that rarely taken branch
+#pragma unroll 1
+    for (int i0 = 0; i0 < NN_TILE; i0 += NN_GROUP) {
+      float se[NN_GROUP][NN_QPT];
+      bool any = false;
+#pragma unroll
+      for (int u = 0; u < NN_GROUP; ++u) {
+        const float4 a = *reinterpret_cast<const float4 *>(&tile[i0 + u][0]);   // broadcast reads
+        const float4 b = *reinterpret_cast<const float4 *>(&tile[i0 + u][4]);
+        const float nn = tile[i0 + u][8];
+#pragma unroll
+        for (int k = 0; k < NN_QPT; ++k) {
+          se[u][k] = estimate_s(m2q[k], qq[k], a, b, nn);
+          any = any || (se[u][k] < (RADIUS ? thr_hi[k] : thr_lo[k]));
+        }
+      }
+      if (any) {
+#pragma unroll
+        for (int u = 0; u < NN_GROUP; ++u) {
+#pragma unroll
+          for (int k = 0; k < NN_QPT; ++k) {
+            const int64_t n = base + i0 + u;
+            if (RADIUS) {
+              if (se[u][k] < thr_hi[k]) {            // not a proven miss (inactive queries: thr_hi = -inf)
+                bool hit = se[u][k] < thr_lo[k];     // proven hit
+                if (!hit) hit = exact_s(t, n, queries + qi[k] * SQMP_DOF) < s_thr;   // the band: exact
+                if (hit && int32_t(n) != excl[k]) {
+                  const int32_t slot = atomicAdd(&count[qi[k]], 1);
+                  if (slot < hit_cap) hits[qi[k] * hit_cap + slot] = int32_t(n);
+                }
+              }
+            } else {
+              if (se[u][k] < thr_lo[k]) {            // cannot be excluded: exact evaluation, exact comparison
+                const double s = exact_s(t, n, queries + qi[k] * SQMP_DOF);
+                const double before = best[k].s;
+                offer(best[k], s, int32_t(n));
+                if (best[k].s != before) thr_lo[k] = __double2float_ru(best[k].s + eR[k] * best[k].d + eR2[k]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  if (!RADIUS) {
+#pragma unroll
+    for (int k = 0; k < NN_QPT; ++k)
+      if (active[k]) {
+        part_d[int64_t(blockIdx.y) * Q + qi[k]] = best[k].d;
+        part_id[int64_t(blockIdx.y) * Q + qi[k]] = best[k].id;
+      }
+  }
+}
+
 // fold the per-chunk partial results in chunk (= id) order; strict '<' keeps the lowest id on ties (BS:4122)
 __global__ void k_nn_merge(const double *__restrict__ part_d, const int32_t *__restrict__ part_id, int chunks,
                            int64_t Q, int32_t *__restrict__ id_out) {
@@ -338,7 +507,7 @@ static void pick_chunks(int64_t N, int64_t Q, int variant, int chunks_hint, int 
   (void)Q;
   chunks = chunks_hint < 1 ? 1 : chunks_hint;
   chunk_len = (N + chunks - 1) / chunks;
-  const int64_t gran = variant == 2 ? 32 : NN_TILE;
+  const int64_t gran = variant == 2 ? 32 : NN_TILE;   // variants 1 and 3 stream NN_TILE-node tiles
   chunk_len = ((chunk_len + gran - 1) / gran) * gran;
   if (chunk_len < gran) chunk_len = gran;
   chunks = int((N + chunk_len - 1) / chunk_len);
@@ -351,7 +520,11 @@ cudaError_t launch_nn_nearest(const TreeDev &t, const double *d_queries, int64_t
   int chunks;
   int64_t chunk_len;
   pick_chunks(t.n, Q, variant, chunks_hint, chunks, chunk_len);
-  if (variant == 2) {
+  if (variant == 3) {
+    dim3 grid(unsigned((Q + NN_THREADS * NN_QPT - 1) / (NN_THREADS * NN_QPT)), unsigned(chunks));
+    k_nn_qt_pf<false><<<grid, NN_THREADS, 0, st>>>(ptrs_of(t), t.n, chunk_len, d_queries, Q, t.rmax2, sc.part_d,
+                                                   sc.part_id, nullptr, 0.0, 0.0, nullptr, nullptr, 0);
+  } else if (variant == 2) {
     dim3 grid(unsigned(Q), unsigned((chunks + NN_THREADS / 32 - 1) / (NN_THREADS / 32)));
     k_nn_wq<false><<<grid, NN_THREADS, 0, st>>>(ptrs_of(t), t.n, chunk_len, chunks, d_queries, Q, sc.part_d,
                                                 sc.part_id, nullptr, 0.0, nullptr, nullptr, 0);
@@ -366,7 +539,7 @@ cudaError_t launch_nn_nearest(const TreeDev &t, const double *d_queries, int64_t
 }
 
 cudaError_t launch_nn_radius(const TreeDev &t, const double *d_queries, const int32_t *d_exclude, int64_t Q,
-                             double s_thr, int k, int32_t *d_low, int32_t *d_high, int32_t *d_count,
+                             double s_thr, double r, int k, int32_t *d_low, int32_t *d_high, int32_t *d_count,
                              int32_t *d_overflow, NNScratch &sc, int chunks_hint, int variant, cudaStream_t st,
                              int *n_launch) {
   if (Q <= 0) return cudaSuccess;
@@ -375,7 +548,11 @@ cudaError_t launch_nn_radius(const TreeDev &t, const double *d_queries, const in
   pick_chunks(t.n, Q, variant, chunks_hint, chunks, chunk_len);
   cudaError_t e = cudaMemsetAsync(d_count, 0, size_t(Q) * sizeof(int32_t), st);
   if (e != cudaSuccess) return e;
-  if (variant == 2) {
+  if (variant == 3) {
+    dim3 grid(unsigned((Q + NN_THREADS * NN_QPT - 1) / (NN_THREADS * NN_QPT)), unsigned(chunks));
+    k_nn_qt_pf<true><<<grid, NN_THREADS, 0, st>>>(ptrs_of(t), t.n, chunk_len, d_queries, Q, t.rmax2, nullptr, nullptr,
+                                                  d_exclude, s_thr, r, d_count, sc.hits, sc.hit_cap);
+  } else if (variant == 2) {
     dim3 grid(unsigned(Q), unsigned((chunks + NN_THREADS / 32 - 1) / (NN_THREADS / 32)));
     k_nn_wq<true><<<grid, NN_THREADS, 0, st>>>(ptrs_of(t), t.n, chunk_len, chunks, d_queries, Q, nullptr, nullptr,
                                                d_exclude, s_thr, d_count, sc.hits, sc.hit_cap);

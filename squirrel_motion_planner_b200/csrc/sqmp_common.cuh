@@ -90,6 +90,11 @@ cudaError_t launch_pack_rows(const uint32_t *d_bits_linear, int gx, int gy, int 
 struct TreeDev {
   double *q[SQMP_DOF];   // SoA: q[d][n]
   double *cost;
+  // fp32 shadow for the sound pre-filter of K3/K4: fa[n] = (q0..q3), fb[n] = (q4..q7) rounded to float,
+  // fn[n] = |float node|^2 (fp64 sum rounded once)
+  float4 *fa, *fb;
+  float *fn;
+  double rmax2;          // upper bound of |node|^2 over every node written since the last reset (host-tracked)
   int64_t n, cap;
 };
 cudaError_t launch_tree_append(TreeDev &t, const double *d_q_rows, const double *d_cost, int64_t first, int64_t n,
@@ -104,10 +109,11 @@ struct NNScratch {
   int32_t *hits;       // [Q][hit_cap]
   int64_t hit_cap;
 };
+// variant: 1 QT fp64-only, 2 WQ fp64-only, 3 QT with fp32 pre-filter (default for many queries)
 cudaError_t launch_nn_nearest(const TreeDev &t, const double *d_queries, int64_t Q, int32_t *d_id, NNScratch &sc,
                               int chunks, int variant, cudaStream_t st, int *n_launch);
 cudaError_t launch_nn_radius(const TreeDev &t, const double *d_queries, const int32_t *d_exclude, int64_t Q,
-                             double s_thr, int k, int32_t *d_low, int32_t *d_high, int32_t *d_count,
+                             double s_thr, double r, int k, int32_t *d_low, int32_t *d_high, int32_t *d_count,
                              int32_t *d_overflow, NNScratch &sc, int chunks, int variant, cudaStream_t st,
                              int *n_launch);
 

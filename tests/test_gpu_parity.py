@@ -197,7 +197,7 @@ def test_fk_matches_oracle_and_golden(ctx, orc, prec, specialized):
 
 
 # --------------------------------------------------------------------------------------- near neighbours
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_nearest_bit_exact(ctx, variant):
     ctx.set_option("nn_variant", variant)
     try:
@@ -218,7 +218,7 @@ def test_nearest_bit_exact(ctx, variant):
         ctx.set_option("nn_variant", 0)
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_nn_against_reference_golden(ctx, variant):
     """tests/golden/nn_reference.npz = outputs of the reference's own DistanceHeuristics + Node::operator< / std::sort
     (compiled from /root/reference by oracle/Makefile.ref): ids bit-exact; within a group of equal cost the reference's
@@ -261,7 +261,7 @@ def test_nearest_quirks_and_tree_mutation(ctx):
     assert ctx.tree_size(2) == 0
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_radius_topk_bit_exact(ctx, variant):
     ctx.set_option("nn_variant", variant)
     try:
@@ -294,6 +294,34 @@ def test_radius_topk_bit_exact(ctx, variant):
             want = oracle.near_topk(nodes, cost, queries, excl, r, k, nthreads=8)
             for a, b in zip(got, want):
                 assert np.array_equal(a, b)
+    finally:
+        ctx.set_option("nn_variant", 0)
+
+
+def test_fp32_prefilter_is_sound_on_adversarial_trees(ctx):
+    """Variant 3 decides most pairs from an fp32 estimate with a proven error bound; anything inside the bound must fall
+    through to the exact fp64 test.  Trees built to sit inside that bound: clusters whose members differ by 1e-13..1e-7
+    (indistinguishable in fp32), coordinates offset by 1e3 / 1e6 (huge cancellation), radius shells at r +- 1e-12."""
+    rng = np.random.default_rng(77)
+    ctx.set_option("nn_variant", 3)
+    try:
+        for trial, (offset, jitter) in enumerate(((0.0, 1e-13), (0.0, 1e-8), (1.0e3, 1e-9), (1.0e6, 1e-6), (0.0, 1e-4))):
+            centres = syn.sample_configs(40, seed=500 + trial) + offset
+            nodes = np.repeat(centres, 60, axis=0) + rng.normal(size=(2400, 8)) * jitter
+            nodes[::60] = centres                                        # exact duplicates of a later query
+            cost = np.round(rng.uniform(0, 5, len(nodes)), 2)
+            queries = np.concatenate([centres[:20], centres[20:] + rng.normal(size=(20, 8)) * jitter,
+                                      syn.sample_configs(24, seed=600 + trial) + offset])
+            ctx.tree_reset(5)
+            ctx.tree_append_batch(5, nodes, cost)
+            assert np.array_equal(ctx.nn_nearest(5, queries), oracle.nearest(nodes, queries, nthreads=8)), trial
+            # radius placed exactly on shells of nodes: d(node, query) computed like the reference, r = d, d +- ulp-ish
+            d0 = np.sqrt(((nodes[7] - queries[0]) ** 2).sum())
+            for r in (1.5, max(d0, 1e-300), np.nextafter(d0, 1.0) if d0 > 0 else 1e-3, jitter * 2.0 + 1e-15):
+                got = ctx.nn_radius(5, queries, None, float(r), 20)
+                want = oracle.near_topk(nodes, cost, queries, None, float(r), 20, nthreads=8)
+                for a, b, name in zip(got, want, ("low", "high", "count")):
+                    assert np.array_equal(a, b), (trial, r, name)
     finally:
         ctx.set_option("nn_variant", 0)
 
