@@ -1,11 +1,13 @@
 // capi.cu — the C ABI of libsqmp_b200.so (include/sqmp_b200.h): context, device memory, host<->device staging.
 // No CPU fallback anywhere: every entry point either runs the CUDA kernels or returns an error code.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "sqmp_common.cuh"
@@ -27,8 +29,11 @@ struct Ctx {
   int slot_sph[SQMP_MAX_SLOTS];   // K1 slot -> sphere index, -1 for a pad
   int sph_slot[SQMP_MAX_SPHERES];
   int n_pairs = 0;
-  SelfPair *d_pairs = nullptr;
-  std::vector<SelfPair> h_pairs;
+  std::vector<SelfPair> h_pairs;   // the description's pairs: a, b = SPHERE indices, rsum2 in metres^2
+  SelfPair *d_pairs = nullptr, *d_flat = nullptr;   // device: hierarchical order / description order (slots, grid units)
+  SelfA *d_as = nullptr;
+  SelfBlock *d_blocks = nullptr;
+  SelfDev self;
   uint32_t *d_occ = nullptr;
   uint8_t *d_lb2 = nullptr;
   uint16_t *d_ft = nullptr;
@@ -157,16 +162,105 @@ static int refresh_grid_robot(Ctx *c) {
   }
   refresh_float_copies(g);
   refresh_float_copies(c->rb);
-  std::vector<SelfPair> dev_pairs(c->h_pairs);   // device copy: slot indices, radii in grid units
-  for (int p = 0; p < c->n_pairs; ++p) {
-    const double rs = (rb.sph[c->h_pairs[p].a][3] + rb.sph[c->h_pairs[p].b][3]) * inv;
-    dev_pairs[p].rsum2 = float(rs * rs);
-    dev_pairs[p].a = (unsigned char)c->sph_slot[c->h_pairs[p].a];
-    dev_pairs[p].b = (unsigned char)c->sph_slot[c->h_pairs[p].b];
-  }
-  if (c->d_pairs && c->n_pairs > 0) {
-    cudaError_t e = cudaMemcpy(c->d_pairs, dev_pairs.data(), sizeof(SelfPair) * size_t(c->n_pairs), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) return fail(c, SQMP_ERR_CUDA, "cudaMemcpy(self pairs)", e);
+  // ---- self-collision hierarchy (SelfDev): blocks of group pairs -> A-spheres -> partner lists ----
+  {
+    int seg_of[SQMP_MAX_SPHERES];
+    for (int sgi = 0; sgi <= SQMP_MAX_SEG; ++sgi)
+      for (int i = rb.seg_sph_end[sgi]; i < rb.seg_sph_end[sgi + 1]; ++i) seg_of[i] = sgi;   // group index = segment + 1
+    for (int gi = 0; gi <= SQMP_MAX_SEG; ++gi) g.grp_fidx[gi] = -1;
+    g.n_frames = 0;
+    for (int p = 0; p < c->n_pairs; ++p)
+      for (int side = 0; side < 2; ++side) {
+        const int gi = seg_of[side ? c->h_pairs[p].b : c->h_pairs[p].a];
+        if (g.grp_fidx[gi] < 0) g.grp_fidx[gi] = g.n_frames++;
+      }
+    auto bound = [&](const std::vector<int> &sph, double (&cen)[3]) {   // enclosing sphere of a sphere set (metres)
+      cen[0] = cen[1] = cen[2] = 0.0;
+      for (int i : sph)
+        for (int k = 0; k < 3; ++k) cen[k] += rb.sph[i][k] / double(sph.size());
+      double R = 0.0;
+      for (int i : sph) {
+        double d2 = 0.0;
+        for (int k = 0; k < 3; ++k) d2 += (rb.sph[i][k] - cen[k]) * (rb.sph[i][k] - cen[k]);
+        R = std::fmax(R, std::sqrt(d2) + rb.sph[i][3]);
+      }
+      return R;
+    };
+    auto inflate2 = [&](double r_sum) {   // squared culling radius in grid units, padded against fp32 rounding
+      const double v = (r_sum * (1.0 + 1e-4) + 1e-6) * inv;
+      return float(v * v * (1.0 + 1e-6));
+    };
+    std::vector<SelfPair> flat(size_t(c->n_pairs) + 1), hier;
+    std::vector<SelfA> as;
+    std::vector<SelfBlock> blocks;
+    for (int p = 0; p < c->n_pairs; ++p) {
+      const int a = c->h_pairs[p].a, b = c->h_pairs[p].b;
+      const double rs = (rb.sph[a][3] + rb.sph[b][3]) * inv;
+      flat[p].a = (unsigned char)c->sph_slot[a];
+      flat[p].b = (unsigned char)c->sph_slot[b];
+      flat[p].fa = (unsigned char)g.grp_fidx[seg_of[a]];
+      flat[p].fb = (unsigned char)g.grp_fidx[seg_of[b]];
+      flat[p].rsum2 = float(rs * rs);
+    }
+    for (int ga = 0; ga <= SQMP_MAX_SEG; ++ga)
+      for (int gb = 0; gb <= SQMP_MAX_SEG; ++gb) {
+        std::vector<int> members, sa, sb;
+        for (int p = 0; p < c->n_pairs; ++p)
+          if (seg_of[c->h_pairs[p].a] == ga && seg_of[c->h_pairs[p].b] == gb) members.push_back(p);
+        if (members.empty()) continue;
+        for (int p : members) {
+          const int a = c->h_pairs[p].a, b = c->h_pairs[p].b;
+          if (std::find(sa.begin(), sa.end(), a) == sa.end()) sa.push_back(a);
+          if (std::find(sb.begin(), sb.end(), b) == sb.end()) sb.push_back(b);
+        }
+        double cA[3], cB[3];
+        const double RA = bound(sa, cA), RB = bound(sb, cB);
+        SelfBlock blk;
+        blk.fa = g.grp_fidx[ga];
+        blk.fb = g.grp_fidx[gb];
+        blk.a_begin = int(as.size());
+        for (int k = 0; k < 3; ++k) {
+          blk.ca[k] = float(cA[k] * inv);
+          blk.cb[k] = float(cB[k] * inv);
+        }
+        blk.thr2 = inflate2(RA + RB);
+        blk.pad = 0.0f;
+        for (int a : sa) {
+          SelfA ea;
+          ea.a = c->sph_slot[a];
+          ea.p_begin = int(hier.size());
+          for (int p : members)
+            if (c->h_pairs[p].a == a) hier.push_back(flat[p]);
+          ea.p_end = int(hier.size());
+          ea.thr2 = inflate2(rb.sph[a][3] + RB);
+          as.push_back(ea);
+        }
+        blk.a_end = int(as.size());
+        blocks.push_back(blk);
+      }
+    hier.resize(size_t(c->n_pairs) + 1);
+    auto upload = [&](auto *&dptr, const auto &vec, size_t min_count) -> cudaError_t {
+      using E = typename std::remove_reference<decltype(vec)>::type::value_type;
+      const size_t count = vec.size() > min_count ? vec.size() : min_count;
+      if (!dptr) {
+        cudaError_t e = cudaMalloc(&dptr, sizeof(E) * (count + 1));
+        if (e != cudaSuccess) return e;
+      }
+      return vec.empty() ? cudaSuccess : cudaMemcpy(dptr, vec.data(), sizeof(E) * vec.size(), cudaMemcpyHostToDevice);
+    };
+    // sizes depend only on the pair list, which is fixed at sqmp_create: allocated once with that capacity
+    cudaError_t e = upload(c->d_pairs, hier, size_t(c->n_pairs) + 1);
+    if (e == cudaSuccess) e = upload(c->d_flat, flat, size_t(c->n_pairs) + 1);
+    if (e == cudaSuccess) e = upload(c->d_as, as, size_t(c->n_pairs) + 1);
+    if (e == cudaSuccess) e = upload(c->d_blocks, blocks, size_t(SQMP_MAX_SEG + 1) * (SQMP_MAX_SEG + 1));
+    if (e != cudaSuccess) return fail(c, SQMP_ERR_CUDA, "self-collision tables", e);
+    c->self.pairs = c->d_pairs;
+    c->self.flat = c->d_flat;
+    c->self.as = c->d_as;
+    c->self.blocks = c->d_blocks;
+    c->self.n_pairs = c->n_pairs;
+    c->self.n_as = int(as.size());
+    c->self.n_blocks = int(blocks.size());
   }
   return SQMP_OK;
 }
@@ -407,12 +501,10 @@ sqmp_ctx *sqmp_create(int device, const sqmp_robot_desc *d, int *err_out) {
     const double rs = d->sph_radius[a] + d->sph_radius[b];
     c->h_pairs[p].a = (unsigned char)a;
     c->h_pairs[p].b = (unsigned char)b;
-    c->h_pairs[p].pad0 = c->h_pairs[p].pad1 = 0;
+    c->h_pairs[p].fa = c->h_pairs[p].fb = 0;
     c->h_pairs[p].rsum2 = float(rs * rs);
   }
-  bool ok = cudaMalloc(&c->d_pairs, sizeof(SelfPair) * (size_t(d->n_pairs) + 1)) == cudaSuccess;
-  ok = ok && cudaMemcpy(c->d_pairs, c->h_pairs.data(), sizeof(SelfPair) * (size_t(d->n_pairs) + 1),
-                        cudaMemcpyHostToDevice) == cudaSuccess;
+  bool ok = true;
   ok = ok && cudaStreamCreateWithFlags(&c->streams[0], cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&c->streams[1], cudaStreamNonBlocking) == cudaSuccess;
   if (!ok || refresh_grid_robot(c) != SQMP_OK) {
@@ -428,6 +520,9 @@ void sqmp_destroy(sqmp_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   if (ctx->d_pairs) cudaFree(ctx->d_pairs);
+  if (ctx->d_flat) cudaFree(ctx->d_flat);
+  if (ctx->d_as) cudaFree(ctx->d_as);
+  if (ctx->d_blocks) cudaFree(ctx->d_blocks);
   if (ctx->d_occ) cudaFree(ctx->d_occ);
   if (ctx->d_lb2) cudaFree(ctx->d_lb2);
   if (ctx->d_ft) cudaFree(ctx->d_ft);
@@ -559,7 +654,7 @@ int sqmp_check_states_dev(sqmp_ctx *ctx, const double *d_q, int64_t S, unsigned 
     return SQMP_OK;
   }
   int nl = 0;
-  CU(launch_check_states(c->rb_grid, c->gd, c->d_pairs, c->n_pairs, d_q, nullptr, 0, S, flags, d_mask, c->fk_precision,
+  CU(launch_check_states(c->rb_grid, c->gd, c->self, d_q, nullptr, 0, S, flags, d_mask, c->fk_precision,
                          st, &nl));
   c->launches += nl;
   return SQMP_OK;
@@ -578,7 +673,7 @@ int sqmp_check_edges_dev(sqmp_ctx *ctx, const double *d_a, const double *d_b, in
     CU(cudaMemsetAsync(d_mask, 0, size_t((S + 31) / 32) * 4, st));
   } else {
     int nl = 0;
-    CU(launch_check_states(c->rb_grid, c->gd, c->d_pairs, c->n_pairs, d_a, d_b, num_points, S, flags, d_mask,
+    CU(launch_check_states(c->rb_grid, c->gd, c->self, d_a, d_b, num_points, S, flags, d_mask,
                            c->fk_precision, st, &nl));
     c->launches += nl;
   }
@@ -654,7 +749,7 @@ int sqmp_get_collisions(sqmp_ctx *ctx, const double q[SQMP_DOF], uint8_t *link_m
   CU(cudaMemcpyAsync(dq, q, SQMP_DOF * 8, cudaMemcpyHostToDevice, st));
   CU(cudaMemsetAsync(ds, 0, SQMP_MAX_SLOTS, st));
   CU(cudaMemsetAsync(dp, 0, size_t(c->n_pairs) + 1, st));
-  CU(launch_get_collisions(c->rb_grid, c->gd, c->d_pairs, c->n_pairs, (const double *)dq, (uint8_t *)ds, (uint8_t *)dp, st));
+  CU(launch_get_collisions(c->rb_grid, c->gd, c->self, (const double *)dq, (uint8_t *)ds, (uint8_t *)dp, st));
   c->launches += 1;
   uint8_t sh[SQMP_MAX_SLOTS];
   CU(cudaMemcpyAsync(sh, ds, SQMP_MAX_SLOTS, cudaMemcpyDeviceToHost, st));

@@ -35,6 +35,8 @@ struct RobotDev {
   int seg_axis_code[SQMP_MAX_SEG];
   int seg_pre_kind[SQMP_MAX_SEG];         // 0 identity, 1 translation only, 2 general
   int seg_sph_end[SQMP_MAX_SEG + 2];      // spheres of segment s (-1 = root) are [end[s+1-1], end[s+1])
+  int grp_fidx[SQMP_MAX_SEG + 1];         // group (segment + 1) -> slot of its frame in the self-collision scratch, -1: none
+  int n_frames;
   double seg_pre[SQMP_MAX_SEG][12];
   double seg_axis[SQMP_MAX_SEG][3];
   double root_off[3];
@@ -65,19 +67,43 @@ struct GridDev {
   double ox, oy, oz, res, inv_res;
 };
 
+// Self collision (CC:541-552) as a three-level hierarchy over the enabled sphere pairs, all between different rigid
+// groups: block = (group A, group B) with one bounding sphere per side; per block the distinct A-spheres, each with
+// the bounding sphere of its partners; per A-sphere its partner list.  A level is entered only if the level above
+// cannot rule it out, so a state far from self contact costs ~one test per block instead of one per pair.
 struct SelfPair {   // 8 bytes
-  unsigned char a, b, pad0, pad1;
-  float rsum2;      // (ra + rb)^2
+  unsigned char a, b;     // sphere slots
+  unsigned char fa, fb;   // frame slots of their groups (RobotDev::grp_fidx)
+  float rsum2;            // (ra + rb)^2, grid units
+};
+struct SelfA {      // 16 bytes
+  int a;                  // sphere slot
+  int p_begin, p_end;     // its partners in SelfDev::pairs
+  float thr2;             // (ra + RB)^2
+};
+struct SelfBlock {  // 48 bytes
+  int fa, fb;             // frame slots of the two groups
+  int a_begin, a_end;     // its A-spheres in SelfDev::as
+  float ca[3], cb[3];     // bounding-sphere centres in the group frames, grid units
+  float thr2;             // (RA + RB)^2
+  float pad;
+};
+struct SelfDev {
+  const SelfPair *pairs;    // hierarchical order (block, a, b)
+  const SelfA *as;
+  const SelfBlock *blocks;
+  const SelfPair *flat;     // the description's own pair order (diagnostics: one result per pair)
+  int n_pairs, n_as, n_blocks;
 };
 
 // ---- launch helpers (defined in the .cu files) ---------------------------------------------------------
 struct Ctx;
 
-cudaError_t launch_check_states(const RobotDev &rb, const GridDev &gd, const SelfPair *pairs, int n_pairs,
+cudaError_t launch_check_states(const RobotDev &rb, const GridDev &gd, const SelfDev &self,
                                 const double *d_q, const double *d_q_end, int num_points, int64_t S,
                                 unsigned flags, uint32_t *d_mask, int fk_precision, cudaStream_t st, int *n_launch);
 cudaError_t launch_first_invalid(const uint32_t *d_mask, int64_t E, int P1, int32_t *d_first, cudaStream_t st);
-cudaError_t launch_get_collisions(const RobotDev &rb, const GridDev &gd, const SelfPair *pairs, int n_pairs,
+cudaError_t launch_get_collisions(const RobotDev &rb, const GridDev &gd, const SelfDev &self,
                                   const double *d_q, uint8_t *d_sphere_hit, uint8_t *d_pair_hit, cudaStream_t st);
 cudaError_t launch_fk(const RobotDev &rb, const double *d_q, int64_t S, double *d_out, int fk_precision,
                       bool allow_specialized, cudaStream_t st);

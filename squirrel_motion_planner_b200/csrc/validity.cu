@@ -177,14 +177,15 @@ template <> struct K1Cfg<float> { static constexpr int MIN_BLOCKS = 5; };
 template <typename T, bool EDGES, int MODE, bool SELF>
 __global__ void __launch_bounds__(K1_THREADS, K1Cfg<T>::MIN_BLOCKS)
 k1_check_states(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd,
-                const SelfPair *__restrict__ pairs, int n_pairs, const double *__restrict__ q_in,
+                const __grid_constant__ SelfDev self, const double *__restrict__ q_in,
                 const double *__restrict__ q_end, int num_points, int64_t S, unsigned flags,
                 uint32_t *__restrict__ mask_out, uint8_t *__restrict__ sphere_hit, uint8_t *__restrict__ pair_hit) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WarpQueue *wq = reinterpret_cast<WarpQueue *>(smem_raw) + (threadIdx.x >> 5);
   double *q_mine = reinterpret_cast<double *>(smem_raw + sizeof(WarpQueue) * (K1_THREADS / 32)) + threadIdx.x;  // [8][blockDim]
-  float *s_rel = reinterpret_cast<float *>(smem_raw + sizeof(WarpQueue) * (K1_THREADS / 32) +
-                                           sizeof(double) * SQMP_DOF * K1_THREADS);  // [3][n][blockDim]
+  // SELF: the frame of every rigid group (rotation + translation relative to the base reference, fp32), own column
+  float *f_mine = reinterpret_cast<float *>(smem_raw + sizeof(WarpQueue) * (K1_THREADS / 32) +
+                                            sizeof(double) * SQMP_DOF * K1_THREADS) + threadIdx.x;  // [n_frames*12][blockDim]
   const int lane = threadIdx.x & 31;
   const int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool active = s < S;
@@ -266,6 +267,16 @@ k1_check_states(const __grid_constant__ RobotDev rb, const __grid_constant__ Gri
     if (b == e) continue;
     // translation of this group minus half a cell: round-to-nearest of (w - 0.5) is the cell index floor(w)
     const T pm0 = f.p[0] - T(0.5), pm1 = f.p[1] - T(0.5), pm2 = f.p[2] - T(0.5);
+    if (do_self) {
+      const int fi = rb.grp_fidx[sg + 1];
+      if (fi >= 0) {
+        float *dst = f_mine + fi * 12 * K1_THREADS;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) dst[k * K1_THREADS] = float(f.r[k]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) dst[(9 + k) * K1_THREADS] = float(f.p[k] - wref[k]);
+      }
+    }
     for (int i0 = b; i0 < e; i0 += K1_BATCH) {
       T wm[K1_BATCH][3];        // centre - 0.5 (working coordinates)
       int ci[K1_BATCH][3];      // cell of the centre (working coordinates)
@@ -288,16 +299,6 @@ k1_check_states(const __grid_constant__ RobotDev rb, const __grid_constant__ Gri
         const bool inside = unsigned(ix) < unsigned(gd.gx) && unsigned(iy) < unsigned(gd.gy) && unsigned(iz) < unsigned(gd.gz);
         // squared box-to-box distance of this cell to the nearest occupied cell: a lower bound of dist(centre, occupied)^2
         lbv[u] = inside ? int(gd.lb2[unsigned(iz) * plane + unsigned(iy) * unsigned(gd.gx) + unsigned(ix)]) : -1;
-      }
-      if (do_self) {
-        const int n = rb.n_spheres;
-#pragma unroll
-        for (int u = 0; u < K1_BATCH; ++u) {
-          const int i = i0 + u;
-          s_rel[(0 * n + i) * blockDim.x + threadIdx.x] = float(wm[u][0] - wref[0]) + 0.5f;
-          s_rel[(1 * n + i) * blockDim.x + threadIdx.x] = float(wm[u][1] - wref[1]) + 0.5f;
-          s_rel[(2 * n + i) * blockDim.x + threadIdx.x] = float(wm[u][2] - wref[2]) + 0.5f;
-        }
       }
       // sph_thr[i] = floor(rg^2), or -2 for a pad slot / a sphere whose link is disabled (lbv is -1 outside the grid): an
       // integer compare, and ~89 % of the spheres end here
@@ -377,19 +378,62 @@ k1_check_states(const __grid_constant__ RobotDev rb, const __grid_constant__ Gri
     qcount = 0;
   }
 
-  // ---- self collision over the enabled cross-group sphere pairs (CC:541-552) ----
+  // ---- self collision over the enabled cross-group sphere pairs (CC:541-552), hierarchically (SelfDev) ----
   if (do_self && (MODE == 1 || !hit)) {
     if (rb.self_const_collision) hit = true;
-    const int n = rb.n_spheres;
-    for (int p = 0; p < n_pairs; ++p) {
-      const SelfPair pr = pairs[p];
-      const float dx = s_rel[(0 * n + pr.a) * blockDim.x + threadIdx.x] - s_rel[(0 * n + pr.b) * blockDim.x + threadIdx.x];
-      const float dy = s_rel[(1 * n + pr.a) * blockDim.x + threadIdx.x] - s_rel[(1 * n + pr.b) * blockDim.x + threadIdx.x];
-      const float dz = s_rel[(2 * n + pr.a) * blockDim.x + threadIdx.x] - s_rel[(2 * n + pr.b) * blockDim.x + threadIdx.x];
-      const bool h = fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= pr.rsum2;
-      hit |= h;
-      if (MODE == 1) pair_hit[p] = h ? 1 : 0;
-      if (MODE == 0 && hit) break;
+    auto load_frame = [&](int fi, float (&F)[12]) {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) F[k] = f_mine[(fi * 12 + k) * K1_THREADS];
+    };
+    auto xform = [](const float (&F)[12], float cx, float cy, float cz, float &x, float &y, float &z) {
+      x = fmaf(F[0], cx, fmaf(F[1], cy, fmaf(F[2], cz, F[9])));
+      y = fmaf(F[3], cx, fmaf(F[4], cy, fmaf(F[5], cz, F[10])));
+      z = fmaf(F[6], cx, fmaf(F[7], cy, fmaf(F[8], cz, F[11])));
+    };
+    auto dist2 = [](float ax, float ay, float az, float bx, float by, float bz) {
+      const float dx = ax - bx, dy = ay - by, dz = az - bz;
+      return fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+    };
+    if (MODE == 1) {   // diagnostics: every pair of the description, in its order
+      for (int p = 0; p < self.n_pairs; ++p) {
+        const SelfPair pr = self.flat[p];
+        float FA[12], FB[12], ax, ay, az, bx, by, bz;
+        load_frame(pr.fa, FA);
+        load_frame(pr.fb, FB);
+        const float4 ca = rb.sph_f[pr.a], cb = rb.sph_f[pr.b];
+        xform(FA, ca.x, ca.y, ca.z, ax, ay, az);
+        xform(FB, cb.x, cb.y, cb.z, bx, by, bz);
+        const bool h = dist2(ax, ay, az, bx, by, bz) <= pr.rsum2;
+        hit |= h;
+        pair_hit[p] = h ? 1 : 0;
+      }
+    } else {
+      for (int bi = 0; bi < self.n_blocks; ++bi) {
+        if (hit) break;
+        const SelfBlock B = self.blocks[bi];
+        float FA[12], FB[12], ax, ay, az, bx, by, bz;
+        load_frame(B.fa, FA);
+        load_frame(B.fb, FB);
+        xform(FA, B.ca[0], B.ca[1], B.ca[2], ax, ay, az);
+        xform(FB, B.cb[0], B.cb[1], B.cb[2], bx, by, bz);   // bounding sphere of the block's B side
+        if (dist2(ax, ay, az, bx, by, bz) > B.thr2) continue;
+        for (int ai = B.a_begin; ai < B.a_end && !hit; ++ai) {
+          const SelfA A = self.as[ai];
+          const float4 ca = rb.sph_f[A.a];
+          xform(FA, ca.x, ca.y, ca.z, ax, ay, az);
+          if (dist2(ax, ay, az, bx, by, bz) > A.thr2) continue;
+          for (int p = A.p_begin; p < A.p_end; ++p) {
+            const SelfPair pr = self.pairs[p];
+            const float4 cb = rb.sph_f[pr.b];
+            float px, py, pz;
+            xform(FB, cb.x, cb.y, cb.z, px, py, pz);
+            if (dist2(ax, ay, az, px, py, pz) <= pr.rsum2) {
+              hit = true;
+              break;
+            }
+          }
+        }
+      }
     }
   }
 
@@ -401,12 +445,12 @@ k1_check_states(const __grid_constant__ RobotDev rb, const __grid_constant__ Gri
 
 static size_t k1_smem_bytes(const RobotDev &rb, unsigned flags, int threads) {
   size_t b = sizeof(WarpQueue) * (K1_THREADS / 32) + sizeof(double) * SQMP_DOF * K1_THREADS;
-  if (flags & SQMP_CHECK_SELF) b += size_t(3) * rb.n_spheres * threads * sizeof(float);
+  if (flags & SQMP_CHECK_SELF) b += size_t(12) * rb.n_frames * threads * sizeof(float);
   return b;
 }
 
 template <typename T>
-static cudaError_t launch_k1(const RobotDev &rb, const GridDev &gd, const SelfPair *pairs, int n_pairs,
+static cudaError_t launch_k1(const RobotDev &rb, const GridDev &gd, const SelfDev &self,
                              const double *d_q, const double *d_q_end, int num_points, int64_t S, unsigned flags,
                              uint32_t *d_mask, cudaStream_t st) {
   const size_t smem = k1_smem_bytes(rb, flags, K1_THREADS);
@@ -415,35 +459,35 @@ static cudaError_t launch_k1(const RobotDev &rb, const GridDev &gd, const SelfPa
   if (blocks > 0x7fffffff) return cudaErrorInvalidValue;
   auto go = [&](auto kern) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    kern<<<unsigned(blocks), K1_THREADS, smem, st>>>(rb, gd, pairs, n_pairs, d_q, d_q_end, d_q_end ? num_points : 0, S, flags,
+    kern<<<unsigned(blocks), K1_THREADS, smem, st>>>(rb, gd, self, d_q, d_q_end, d_q_end ? num_points : 0, S, flags,
                                                       d_mask, nullptr, nullptr);
   };
-  const bool self = (flags & SQMP_CHECK_SELF) != 0;
+  const bool with_self = (flags & SQMP_CHECK_SELF) != 0;
   if (d_q_end) {
-    if (self) go(k1_check_states<T, true, 0, true>);
+    if (with_self) go(k1_check_states<T, true, 0, true>);
     else go(k1_check_states<T, true, 0, false>);
   } else {
-    if (self) go(k1_check_states<T, false, 0, true>);
+    if (with_self) go(k1_check_states<T, false, 0, true>);
     else go(k1_check_states<T, false, 0, false>);
   }
   return cudaGetLastError();
 }
 
-cudaError_t launch_check_states(const RobotDev &rb, const GridDev &gd, const SelfPair *pairs, int n_pairs,
+cudaError_t launch_check_states(const RobotDev &rb, const GridDev &gd, const SelfDev &self,
                                 const double *d_q, const double *d_q_end, int num_points, int64_t S, unsigned flags,
                                 uint32_t *d_mask, int fk_precision, cudaStream_t st, int *n_launch) {
   if (n_launch) *n_launch += 1;
   if (fk_precision == 32)
-    return launch_k1<float>(rb, gd, pairs, n_pairs, d_q, d_q_end, num_points, S, flags, d_mask, st);
-  return launch_k1<double>(rb, gd, pairs, n_pairs, d_q, d_q_end, num_points, S, flags, d_mask, st);
+    return launch_k1<float>(rb, gd, self, d_q, d_q_end, num_points, S, flags, d_mask, st);
+  return launch_k1<double>(rb, gd, self, d_q, d_q_end, num_points, S, flags, d_mask, st);
 }
 
-cudaError_t launch_get_collisions(const RobotDev &rb, const GridDev &gd, const SelfPair *pairs, int n_pairs,
+cudaError_t launch_get_collisions(const RobotDev &rb, const GridDev &gd, const SelfDev &self,
                                   const double *d_q, uint8_t *d_sphere_hit, uint8_t *d_pair_hit, cudaStream_t st) {
   const size_t smem = k1_smem_bytes(rb, SQMP_CHECK_SELF, K1_THREADS);
   auto kern = k1_check_states<double, false, 1, true>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-  kern<<<1, K1_THREADS, smem, st>>>(rb, gd, pairs, n_pairs, d_q, nullptr, 0, 1, SQMP_CHECK_MAP | SQMP_CHECK_SELF, nullptr,
+  kern<<<1, K1_THREADS, smem, st>>>(rb, gd, self, d_q, nullptr, 0, 1, SQMP_CHECK_MAP | SQMP_CHECK_SELF, nullptr,
                                     d_sphere_hit, d_pair_hit);
   return cudaGetLastError();
 }

@@ -6,6 +6,7 @@
   collision_numpy.npz sphere-vs-voxel clearances by dense numpy brute force over every occupied voxel
   nn_numpy.npz        nearest / radius results by numpy brute force with the reference's summation order
   interp_numpy.npz    interpolateConfigurations by the numpy formula
+  rooms_bt.npz        the reference's room3/4/5.bt octomaps parsed to dense occupancy (counts + bits)
   nn_reference.npz    distances, nearest ids and near-vertex id lists produced by the REFERENCE'S OWN code
                       (DistanceHeuristics::euclidean_joint_space_distance, Node::operator< + std::sort) compiled
                       from /root/reference by oracle/Makefile.ref — needs the build container
@@ -187,7 +188,28 @@ def nn_reference():
                         near_ex_count=np.array([len(v) for v in near_ex]), near_ex_flat=np.concatenate(near_ex))
 
 
+def rooms_bt():
+    """The reference's shipped octomaps (squirrel_8dof_planner/config/room{3,4,5}.bt) parsed to dense grids: node /
+    leaf / voxel counts + the packed occupancy.  Derived data only; needs the build container."""
+    from squirrel_motion_planner_b200 import octomap_io as oio
+    base = "/root/reference/squirrel_8dof_planner/config/"
+    if not os.path.isdir(base):
+        print("no /root/reference: rooms_bt.npz left as committed")
+        return
+    out = {}
+    for name in ("room3", "room4", "room5"):
+        res, occ, free, n = oio.parse_bt(open(base + name + ".bt", "rb").read())
+        w = oio.to_voxel_world(res, occ)
+        out[name + "_counts"] = np.array([n, len(occ), len(free), int((occ[:, 3] ** 3).sum())])
+        out[name + "_bits"] = w.bits
+        out[name + "_dims"] = np.array(w.dims)
+        out[name + "_origin"] = w.origin
+        out[name + "_res"] = res
+    np.savez_compressed(os.path.join(HERE, "rooms_bt.npz"), **out)
+
+
 if __name__ == "__main__":
+    rooms_bt()
     nn_reference()
     urdf_fk()
     collision_numpy()
