@@ -19,9 +19,11 @@
 // the GPU is missing the checker stays uninitialised and isInCollision answers true (fails closed, CC:106-107).
 #pragma once
 
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <fstream>
+#include <iterator>
 #include <map>
 #include <sstream>
 #include <string>
@@ -179,6 +181,87 @@ struct VoxelGrid {
     bits[b >> 5] |= 1u << (b & 31);
   }
 };
+
+// Octomap binary tree (.bt file body = octomap_msgs binary map data) -> dense grid, without liboctomap.
+// Stream format (octomap OcTree::readBinaryNode): per inner node two bytes, 2 bits per child,
+// (bit 2i, bit 2i+1) = (1,0) free leaf, (0,1) occupied leaf, (1,1) inner node, (0,0) unknown; depth-first; child i at
+// x = i&1, y = (i>>1)&1, z = (i>>2)&1; 16 levels; key = floor(coord/res) + 32768.  Pruned leaves are expanded; unknown
+// and free space do not collide (what FCL does with an OcTree).  floor_distance > 0 adds the planner node's floor
+// patch around (pose_x, pose_y) (squirrel_8dof_planner.cpp:886-904).  Same logic as octomap_io.py (tests compare them).
+inline bool read_bt(const std::string &path, VoxelGrid &grid, std::string *err = NULL, bool with_floor = false,
+                    double pose_x = 0.0, double pose_y = 0.0, double floor_distance = 0.0) {
+  std::ifstream in(path.c_str(), std::ios::binary);
+  if (!in) { if (err) *err = "cannot open " + path; return false; }
+  std::string line;
+  double res = 0.0;
+  long size = -1;
+  bool data_seen = false;
+  while (std::getline(in, line)) {
+    if (line == "data") { data_seen = true; break; }
+    std::istringstream ls(line);
+    std::string key;
+    ls >> key;
+    if (key == "res") ls >> res;
+    else if (key == "size") ls >> size;
+    else if (key == "id") { std::string id; ls >> id; if (id != "OcTree") { if (err) *err = "unsupported tree id " + id; return false; } }
+  }
+  if (!data_seen || !(res > 0.0) || size < 0) { if (err) *err = "not an octomap .bt stream"; return false; }
+  std::vector<unsigned char> body((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+  struct Leaf { long k[3]; long size; };
+  struct Item { long k[3]; int depth; };
+  std::vector<Leaf> occ;
+  long n_nodes = size > 0 ? 1 : 0;
+  size_t off = 0;
+  std::vector<Item> stack;
+  if (size > 0) { Item root = {{0, 0, 0}, 0}; stack.push_back(root); }
+  while (!stack.empty()) {
+    const Item it = stack.back();
+    stack.pop_back();
+    if (off + 2 > body.size()) { if (err) *err = "truncated data section"; return false; }
+    const unsigned bits = unsigned(body[off]) | (unsigned(body[off + 1]) << 8);
+    off += 2;
+    const long half = 1L << (16 - it.depth - 1);
+    std::vector<Item> inner;
+    for (int i = 0; i < 8; ++i) {
+      const unsigned b0 = (bits >> (2 * i)) & 1u, b1 = (bits >> (2 * i + 1)) & 1u;
+      if (!b0 && !b1) continue;
+      ++n_nodes;
+      const long cx = it.k[0] + (i & 1) * half, cy = it.k[1] + ((i >> 1) & 1) * half, cz = it.k[2] + ((i >> 2) & 1) * half;
+      if (b0 && b1) {
+        if (it.depth + 1 >= 16) { if (err) *err = "inner node below the finest level"; return false; }
+        Item c = {{cx, cy, cz}, it.depth + 1};
+        inner.push_back(c);
+      } else if (b1) {
+        Leaf l = {{cx, cy, cz}, half};
+        occ.push_back(l);
+      }
+    }
+    for (size_t j = inner.size(); j-- > 0;) stack.push_back(inner[j]);   // depth-first, ascending child order
+  }
+  if (off != body.size() || (size > 0 && n_nodes != size)) { if (err) *err = "tree does not match its header"; return false; }
+  if (with_floor && floor_distance > 0.0) {
+    const long kx = long(std::floor(pose_x / res)) + 32768, ky = long(std::floor(pose_y / res)) + 32768;
+    const long kz = long(std::floor(-0.5)) + 32768, n = long(floor_distance / res);
+    for (long x = kx - n; x <= kx + n; ++x)
+      for (long y = ky - n; y <= ky + n; ++y) { Leaf l = {{x, y, kz}, 1}; occ.push_back(l); }
+  }
+  if (occ.empty()) { if (err) *err = "no occupied leaves"; return false; }
+  long lo[3] = {occ[0].k[0], occ[0].k[1], occ[0].k[2]}, hi[3] = {lo[0], lo[1], lo[2]};
+  for (size_t j = 0; j < occ.size(); ++j)
+    for (int a = 0; a < 3; ++a) {
+      if (occ[j].k[a] < lo[a]) lo[a] = occ[j].k[a];
+      if (occ[j].k[a] + occ[j].size > hi[a]) hi[a] = occ[j].k[a] + occ[j].size;
+    }
+  for (int a = 0; a < 3; ++a) { lo[a] -= 1; hi[a] += 1; }   // one voxel of margin, like octomap_io.to_voxel_world
+  grid.res = res;
+  for (int a = 0; a < 3; ++a) grid.origin[a] = double(lo[a] - 32768) * res;
+  grid.resize(int(hi[0] - lo[0]), int(hi[1] - lo[1]), int(hi[2] - lo[2]));
+  for (size_t j = 0; j < occ.size(); ++j)
+    for (long z = occ[j].k[2]; z < occ[j].k[2] + occ[j].size; ++z)
+      for (long y = occ[j].k[1]; y < occ[j].k[1] + occ[j].size; ++y)
+        for (long x = occ[j].k[0]; x < occ[j].k[0] + occ[j].size; ++x) grid.set(int(x - lo[0]), int(y - lo[1]), int(z - lo[2]));
+  return true;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // CollisionChecker  (collision_checker.hpp:35-133)

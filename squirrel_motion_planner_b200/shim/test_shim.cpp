@@ -26,8 +26,23 @@ static void write_raw(const std::string &path, const std::vector<T> &v) {
 }
 
 int main(int argc, char **argv) {
+  if (argc >= 4 && std::string(argv[1]) == "--bt") {   // test_shim --bt in.bt out_prefix [pose_x pose_y floor_d]
+    sqmp_shim::VoxelGrid g;
+    std::string err;
+    const bool floor = argc >= 7;
+    if (!sqmp_shim::read_bt(argv[2], g, &err, floor, floor ? atof(argv[4]) : 0.0, floor ? atof(argv[5]) : 0.0,
+                            floor ? atof(argv[6]) : 0.0)) {
+      std::fprintf(stderr, "read_bt: %s\n", err.c_str());
+      return 5;
+    }
+    write_raw(std::string(argv[3]) + ".bits.u32", g.bits);
+    std::ofstream meta((std::string(argv[3]) + ".meta.txt").c_str());
+    meta.precision(17);
+    meta << g.gx << " " << g.gy << " " << g.gz << " " << g.origin[0] << " " << g.origin[1] << " " << g.origin[2] << " " << g.res << "\n";
+    return 0;
+  }
   if (argc < 3) {
-    std::fprintf(stderr, "usage: %s robot.sqmpdesc work_dir\n", argv[0]);
+    std::fprintf(stderr, "usage: %s robot.sqmpdesc work_dir | --bt in.bt out_prefix [pose_x pose_y floor_d]\n", argv[0]);
     return 2;
   }
   const std::string dir = std::string(argv[2]) + "/";

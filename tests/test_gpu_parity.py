@@ -118,6 +118,28 @@ def test_grid_partially_covering_the_robot(ctx, orc):
     assert differs.sum() == 0 and 0.02 < got.mean() < 0.98
 
 
+def test_real_scene_room3_with_floor_patch(ctx, orc):
+    """The reference's own room3.bt octomap (tests/golden/rooms_bt.npz), run through the .bt writer/parser, with the
+    planner node's floor patch (squirrel_8dof_planner.cpp:886-904) around the robot: a 202 x 322 x 15 grid (not a cube,
+    not a power of two), thin obstacles, most of the volume unknown = free."""
+    from squirrel_motion_planner_b200 import octomap_io as oio
+    g = np.load(os.path.join(GOLDEN, "rooms_bt.npz"))
+    w0 = syn.VoxelWorld(g["room3_bits"], tuple(int(v) for v in g["room3_dims"]), g["room3_origin"], float(g["room3_res"]))
+    res, occ, _free, _n = oio.parse_bt(oio.write_bt(w0))
+    w = oio.to_voxel_world(res, oio.insert_floor(occ, res, (0.5, -1.0), 3.0))
+    origin = w.origin + np.array([0.0, 0.0, rd.OCTREE_Z_OFFSET])
+    ctx.set_disabled_links(0)
+    orc.set_disabled_links(0)
+    ctx.set_voxel_grid(w.bits, w.dims, origin, w.res)
+    orc.set_grid(w.bits, w.dims, origin, w.res)
+    q = syn.state_batch(21 * 400, seed=29, xy_half=4.5)
+    q[:, 1] *= 1.6                                                      # the room is 10 m x 16 m
+    for flags in (api.CHECK_MAP, api.CHECK_MAP | api.CHECK_SELF):
+        got, ref, clr, differs = _verdict_parity(ctx, orc, q, flags)
+        assert differs.sum() == 0
+    assert 0.02 < got.mean() < 0.98
+
+
 def test_check_edges_matches_oracle_and_states_entry(world_ctx):
     ctx, orc, w, origin = world_ctx
     a, b = syn.edge_batch(777, seed=31, xy_half=2.2)

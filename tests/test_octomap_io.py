@@ -56,3 +56,25 @@ def test_floor_patch_matches_the_planner_node():
     assert w.dims == (2 * n + 1, 2 * n + 1, 1) and abs(w.origin[2] + res) < 1e-12
     cx = (int(np.floor(1.23 / res)) - n) * res
     assert abs(w.origin[0] - cx) < 1e-12
+
+
+def test_cpp_reader_agrees_with_python(tmp_path):
+    """sqmp_shim::read_bt (the C++ side of setOcTree for .bt / binary octomap messages) == octomap_io, bit for bit."""
+    import subprocess
+    from conftest import ROOT
+    shim = os.path.join(ROOT, "squirrel_motion_planner_b200", "shim")
+    subprocess.run(["make", "-s", "-C", shim], check=True)
+    g = np.load(os.path.join(GOLDEN, "rooms_bt.npz"))
+    for name, floor in (("room3", None), ("room5", (0.7, -1.3, 1.5))):
+        w = syn.VoxelWorld(g[name + "_bits"], tuple(int(v) for v in g[name + "_dims"]), g[name + "_origin"], float(g[name + "_res"]))
+        bt = tmp_path / (name + ".bt")
+        bt.write_bytes(oio.write_bt(w))
+        args = [os.path.join(shim, "test_shim"), "--bt", str(bt), str(tmp_path / name)]
+        if floor:
+            args += ["%r" % v for v in floor]
+        subprocess.run(args, check=True)
+        want = oio.load_bt(str(bt), floor[:2] if floor else None, floor[2] if floor else 0.0)
+        meta = open(str(tmp_path / name) + ".meta.txt").read().split()
+        assert tuple(int(v) for v in meta[:3]) == want.dims
+        assert np.allclose([float(v) for v in meta[3:6]], want.origin, atol=1e-12) and float(meta[6]) == want.res
+        assert np.array_equal(np.fromfile(str(tmp_path / name) + ".bits.u32", dtype=np.uint32), want.bits)
