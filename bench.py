@@ -287,7 +287,7 @@ def run_own(args):
                              "field stay resident by design" % (n_rot, n_rot * s_rank * 64 >> 20),
                        "colliding_fraction": n_colliding / s_rank, "entry": "sqmp_check_states_dev"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "k1_check_states<double,false,0>",
+                         "traffic": None, "peak_source": peak_src, "kernel": "k1_check_states<double,false,0,false>",
                          "kernel_ms": kern_ms, "bytes_per_state": BYTES_PER_STATE},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": s_rank * 64, "d2h_bytes_per_step": words * 4,
