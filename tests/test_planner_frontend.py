@@ -1,0 +1,77 @@
+"""The batched BiRRT* front-end (shim/sqmp_birrt.hpp).  The same C++ planner is compiled twice: over
+the CUDA library (product) and over the CPU oracle (test / baseline binary).  Near-neighbour ids are bit-exact and
+collision verdicts equal outside the 1e-5 m band, so with the same seed both must take the SAME decisions: the trace
+hash covers every nearest id, extend verdict, near count, chosen parent, rewire and connection."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from squirrel_motion_planner_b200 import synthetic as syn
+
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import planner_workdir as pw  # noqa: E402
+
+SHIM = os.path.join(ROOT, "squirrel_motion_planner_b200", "shim")
+DESC = os.path.join(ROOT, "squirrel_motion_planner_b200", "data", "robotino_plan.sqmpdesc")
+
+
+def _workdir(tmp_path, fixture_data, world, starts, goals):
+    lt, fx, spheres = fixture_data
+    d = str(tmp_path)
+    pw.write_world(d, world)
+    pw.write_oracle_model(d, lt, spheres)
+    pw.write_queries(d, starts, goals)
+    return d
+
+
+def _run(binary, d, backend, iterations, seed=1):
+    subprocess.run(["make", "-s", "-C", SHIM], check=True)
+    r = subprocess.run([os.path.join(SHIM, binary), DESC, d, backend, str(iterations), str(seed)], capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = [l.split() for l in r.stdout.splitlines() if l and not l.startswith("#")]
+    return rows
+
+
+def test_config1_single_query_on_cpu(tmp_path, fixture_data):
+    """BASELINE.json configs[0]: one BiRRT* query in the synthetic box world on the CPU (reference-checker port)."""
+    world = syn.box_world(g=256, n_boxes=64, seed=1234)
+    d = _workdir(tmp_path, fixture_data, world, *pw.config1_queries(1))
+    a = _run("sqmp_plan_oracle", d, "oracle", 400)
+    b = _run("sqmp_plan_oracle", d, "oracle", 400)
+    assert a == b                                            # seeded: identical decisions, identical trace
+    row = a[0]
+    assert row[1] == "1" and float(row[2]) < 40.0            # solved; path cost well under the 10000 sentinel
+    assert int(row[3]) == 400 and int(row[8]) == 21 * int(row[7])   # 21 states per checked edge
+
+
+def test_invalid_goal_is_rejected_like_init_planner(tmp_path, fixture_data):
+    world = syn.box_world(g=128, n_boxes=8, seed=2)
+    start, goal = pw.config1_queries(1)
+    start[0, :2] = 1.0
+    goal[0, :3] = (1.5, 1.5, 0.0)
+    goal[0, 3:] = (0.29, 2.26, 0.19, -1.17, 0.53)            # hand inside the base: self collision (BS:351-358)
+    d = _workdir(tmp_path, fixture_data, world, start, goal)
+    assert _run("sqmp_plan_oracle", d, "oracle", 10)[0][1] == "invalid_endpoint"
+
+
+@pytest.mark.gpu
+def test_gpu_and_cpu_backends_take_identical_decisions(tmp_path, fixture_data):
+    world = syn.box_world(g=256, n_boxes=64, seed=1234)
+    rng = np.random.default_rng(5)
+    s0, g0 = pw.config1_queries(1)
+    starts = np.repeat(s0, 3, axis=0)
+    goals = np.repeat(g0, 3, axis=0)
+    starts[1, :2] = (3.5, -4.0); goals[1, :2] = (-4.0, 3.0)
+    starts[2, :3] = (0.0, -4.5, 1.0); goals[2, 3:] += rng.uniform(-0.1, 0.1, 5)
+    d = _workdir(tmp_path, fixture_data, world, starts, goals)
+    cpu = _run("sqmp_plan_oracle", d, "oracle", 600)
+    gpu = _run("sqmp_plan", d, "gpu", 600)
+    assert len(cpu) == len(gpu) == 3
+    for c, g in zip(cpu, gpu):
+        assert c == g, "decision traces differ:\\n%s\\n%s" % (c, g)
+    assert sum(r[1] == "1" for r in gpu) >= 2
