@@ -297,7 +297,7 @@ def run_own(args):
             "extra": extra,
         }
         traffic_file = os.path.join(ROOT, "profiles", "k1_traffic.json")
-        if os.path.exists(traffic_file):
+        if os.path.exists(traffic_file) and s_rank == S_CONFIG2:   # the capture is of one 2^20-state launch
             with open(traffic_file) as f:
                 line["roofline"]["traffic"] = json.load(f).get("dram_bytes_per_launch")
         print(json.dumps(line))
@@ -363,18 +363,106 @@ def side_metrics(ctx, torch, dev, stream, d_q, S):
     return out
 
 
+def run_config5(args):
+    """BASELINE.json configs[4]: independent planning queries in a cluttered 512^3 scene, one query stream per GPU, no
+    collective.  Each rank runs the C++ planner front-end (shim/sqmp_plan, GPU backend) over its share of the queries
+    with a fixed iteration budget, so every GPU (and the CPU baseline) does identical work per query."""
+    import subprocess
+    import tempfile
+    import torch
+    import torch.distributed as dist
+    from squirrel_motion_planner_b200 import api, robot_desc as rd, synthetic as syn
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import planner_workdir as pw
+
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world_size > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("gloo")            # only a barrier and a max over ranks: no data-path collective
+    torch.cuda.set_device(local_rank)
+    shim = os.path.join(ROOT, "squirrel_motion_planner_b200", "shim")
+    desc = os.path.join(ROOT, "squirrel_motion_planner_b200", "data", "robotino_plan.sqmpdesc")
+    n_queries, iters = args.queries, args.iterations
+    w = syn.box_world(g=512, n_boxes=2048, seed=4321)                       # W512, SURVEY.md §8d
+    # collision-free (start, goal) pairs: rejection sampling with the CUDA checker itself (self + map), seed 5
+    ctx = api.default_context(local_rank)
+    ctx.set_voxel_grid(w.bits, w.dims, w.origin + np.array([0.0, 0.0, rd.OCTREE_Z_OFFSET]), w.res)
+    cand = syn.sample_configs(8 * n_queries + 64, seed=5, xy_half=11.0)
+    mask = ctx.check_states(cand, api.CHECK_MAP | api.CHECK_SELF)
+    free = cand[~np.unpackbits(mask.view(np.uint8), bitorder="little")[:len(cand)].astype(bool)]
+    ctx.close()
+    if len(free) < 2 * n_queries:
+        raise RuntimeError("not enough collision-free samples for %d queries" % n_queries)
+    starts, goals = free[:n_queries], free[n_queries:2 * n_queries]
+    d = tempfile.mkdtemp(prefix="sqmp_cfg5_")
+    pw.write_world(d, w)
+    pw.write_queries(d, starts, goals)
+    per = (n_queries + world_size - 1) // world_size
+    first, count = rank * per, max(0, min(per, n_queries - rank * per))
+    if world_size > 1:
+        dist.barrier()
+    r = subprocess.run([os.path.join(shim, "sqmp_plan"), desc, d, "gpu", str(iters), "1", str(local_rank), str(first), str(count)],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("sqmp_plan failed: " + r.stderr[-500:])
+    tail = [l for l in r.stdout.splitlines() if l.startswith("# queries")][-1].split()
+    secs, states, its = float(tail[4]), int(tail[6]), int(tail[8])
+    solved = sum(l.split()[1] == "1" for l in r.stdout.splitlines() if l and not l.startswith("#") and "invalid" not in l)
+    agg = torch.tensor([secs, float(states), float(its), float(solved), float(count)], dtype=torch.float64)
+    if world_size > 1:
+        mx = agg.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+        secs = float(mx[0])
+    else:
+        secs = float(agg[0])
+    if rank == 0:
+        cpu = None
+        if world_size == 1 and not args.no_cpu:
+            import oracle  # noqa: F401  (the baseline binary links the oracle library)
+            lt, fx = rd.load_fixture()
+            pw.write_oracle_model(d, lt, [(n, tuple(c), r_) for n, c, r_ in fx["spheres"]])
+            nq_cpu = max(1, min(4, count))
+            t0 = time.perf_counter()
+            rc = subprocess.run([os.path.join(shim, "sqmp_plan_oracle"), desc, d, "oracle", str(iters), "1", "0", "0", str(nq_cpu)],
+                                capture_output=True, text=True)
+            dt = time.perf_counter() - t0
+            if rc.returncode == 0:
+                same = [a for a in rc.stdout.splitlines() if a and not a.startswith("#")] == \
+                       [a for a in r.stdout.splitlines() if a and not a.startswith("#")][:nq_cpu]
+                cpu = {"value": nq_cpu / dt, "unit": "planning queries/s", "cores": 1, "kind": "port",
+                       "sample": "first %d queries, same planner binary over the CPU oracle, %.1f s; decisions identical to the GPU run: %s" % (nq_cpu, dt, same)}
+        total_q = float(agg[4])
+        print(json.dumps({
+            "metric": "planning queries/sec (fixed %d BiRRT* iterations each)" % iters, "value": total_q / secs,
+            "unit": "planning queries/s", "n_gpus": world_size, "steps": 1, "warmup": 0, "ms_per_step": secs * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config5: %d independent planning queries, W512 (512^3 voxels, 2048 boxes), one query stream per GPU, no collective" % n_queries,
+                       "iterations_per_query": iters, "flags": "SELF|MAP"},
+            "checked_states_per_s": float(agg[1]) / secs, "planner_iterations_per_s": float(agg[2]) / secs,
+            "solved": int(agg[3]), "cpu_baseline": cpu, "gpu_launches": None}))
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--workload", default="config2", choices=["config2", "config4"])
+    ap.add_argument("--workload", default="config2", choices=["config2", "config4", "config5"])
+    ap.add_argument("--queries", type=int, default=1024, help="config5: number of planning queries")
+    ap.add_argument("--iterations", type=int, default=1000, help="config5: BiRRT* iterations per query")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "config5":
+        run_config5(args)
     else:
         run_own(args)
 
