@@ -389,13 +389,19 @@ def run_config5(args):
     # collision-free (start, goal) pairs: rejection sampling with the CUDA checker itself (self + map), seed 5
     ctx = api.default_context(local_rank)
     ctx.set_voxel_grid(w.bits, w.dims, w.origin + np.array([0.0, 0.0, rd.OCTREE_Z_OFFSET]), w.res)
-    cand = syn.sample_configs(8 * n_queries + 64, seed=5, xy_half=11.0)
-    mask = ctx.check_states(cand, api.CHECK_MAP | api.CHECK_SELF)
-    free = cand[~np.unpackbits(mask.view(np.uint8), bitorder="little")[:len(cand)].astype(bool)]
+    rng = np.random.default_rng(5)
+    s0, g0 = pw.config1_queries(1)
+
+    def free_samples(arm_pose):      # base anywhere in the scene, arm near a self-collision-free pose
+        cand = syn.sample_configs(64 * n_queries + 256, seed=int(rng.integers(1 << 30)), xy_half=11.0)
+        cand[:, 3:] = arm_pose + rng.uniform(-0.15, 0.15, size=(len(cand), 5))
+        mask = ctx.check_states(cand, api.CHECK_MAP | api.CHECK_SELF)
+        ok = cand[~np.unpackbits(mask.view(np.uint8), bitorder="little")[:len(cand)].astype(bool)]
+        if len(ok) < n_queries:
+            raise RuntimeError("not enough collision-free samples for %d queries (%d found)" % (n_queries, len(ok)))
+        return ok[:n_queries]
+    starts, goals = free_samples(s0[0, 3:]), free_samples(g0[0, 3:])
     ctx.close()
-    if len(free) < 2 * n_queries:
-        raise RuntimeError("not enough collision-free samples for %d queries" % n_queries)
-    starts, goals = free[:n_queries], free[n_queries:2 * n_queries]
     d = tempfile.mkdtemp(prefix="sqmp_cfg5_")
     pw.write_world(d, w)
     pw.write_queries(d, starts, goals)

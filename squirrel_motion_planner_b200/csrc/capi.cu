@@ -41,6 +41,12 @@ struct Ctx {
   NNScratch nn;
   size_t nn_part_bytes = 0, nn_hits_bytes = 0;
   DevBuf scratch[8];  // grow-only staging buffers for the host-pointer entry points
+  // low-latency path of the planner-shaped calls (one query, a few edges): mapped pinned host memory the kernels
+  // read their inputs from and write their answers to — no cudaMemcpy on either side of the launch
+  unsigned char *pin_h = nullptr, *pin_d = nullptr;
+  unsigned *d_ticket = nullptr;     // [0] ticket, [1] hit counter of k_nn_single
+  bool tree_writes_pending = false; // unsynchronised single-node writes are in flight on streams[0]
+  int64_t small_call_states = 4096; // validity calls up to this many states take the low-latency path
   cudaStream_t streams[2] = {nullptr, nullptr};
   int64_t launches = 0;
   int fk_precision = 64;  // 64 | 32 (validity + FK chain arithmetic)
@@ -51,6 +57,13 @@ struct Ctx {
   int64_t pipeline_chunk = 1 << 18;  // states per H2D/kernel/D2H pipeline stage
   std::string err;
 };
+
+// layout of Ctx::pin_h
+constexpr size_t PIN_RESULT = 0;            // int32[2 * 64 + 8]: NN answers
+constexpr size_t PIN_MASK = 4096;           // uint32[...]: validity mask of a small call
+constexpr size_t PIN_QA = 8192;             // doubles: states / edge start points of a small call
+constexpr size_t PIN_BYTES = PIN_QA + 2 * 4096 * SQMP_DOF * sizeof(double);
+constexpr size_t PIN_QB = PIN_QA + 4096 * SQMP_DOF * sizeof(double);
 
 static int fail(Ctx *c, int code, const char *what, cudaError_t e = cudaSuccess) {
   if (c) {
@@ -505,6 +518,9 @@ sqmp_ctx *sqmp_create(int device, const sqmp_robot_desc *d, int *err_out) {
     c->h_pairs[p].rsum2 = float(rs * rs);
   }
   bool ok = true;
+  ok = ok && cudaHostAlloc((void **)&c->pin_h, PIN_BYTES, cudaHostAllocMapped) == cudaSuccess;
+  ok = ok && cudaHostGetDevicePointer((void **)&c->pin_d, c->pin_h, 0) == cudaSuccess;
+  ok = ok && cudaMalloc(&c->d_ticket, 64) == cudaSuccess && cudaMemset(c->d_ticket, 0, 64) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&c->streams[0], cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&c->streams[1], cudaStreamNonBlocking) == cudaSuccess;
   if (!ok || refresh_grid_robot(c) != SQMP_OK) {
@@ -537,6 +553,8 @@ void sqmp_destroy(sqmp_ctx *ctx) {
   if (ctx->nn.hits) cudaFree(ctx->nn.hits);
   for (auto &b : ctx->scratch)
     if (b.p) cudaFree(b.p);
+  if (ctx->pin_h) cudaFreeHost(ctx->pin_h);
+  if (ctx->d_ticket) cudaFree(ctx->d_ticket);
   for (auto &s : ctx->streams)
     if (s) cudaStreamDestroy(s);
   delete ctx;
@@ -560,6 +578,9 @@ int sqmp_set_option(sqmp_ctx *ctx, const char *name, int64_t value) {
   } else if (n == "nn_hit_pool_bytes") {
     if (value < 4096) return fail(c, SQMP_ERR_INVALID, "nn_hit_pool_bytes too small");
     c->nn_hit_pool_bytes = value;
+  } else if (n == "small_call_states") {
+    if (value < 0 || value > 4096) return fail(c, SQMP_ERR_INVALID, "small_call_states must be 0..4096");
+    c->small_call_states = value;
   } else if (n == "pipeline_chunk") {
     if (value < 1024) return fail(c, SQMP_ERR_INVALID, "pipeline_chunk too small");
     c->pipeline_chunk = (value + 31) / 32 * 32;
@@ -688,6 +709,15 @@ int sqmp_check_states(sqmp_ctx *ctx, const double *q, int64_t S, unsigned flags,
   CHECK_CTX();
   if (S < 0 || (S > 0 && (!q || !mask_out))) return fail(c, SQMP_ERR_INVALID, "check_states: null pointer");
   if (S == 0) return SQMP_OK;
+  if (S <= c->small_call_states) {   // planner-shaped call: inputs and mask through mapped pinned memory, one launch
+    std::memcpy(c->pin_h + PIN_QA, q, size_t(S) * SQMP_DOF * sizeof(double));
+    int rc = sqmp_check_states_dev(ctx, (const double *)(c->pin_d + PIN_QA), S, flags, (uint32_t *)(c->pin_d + PIN_MASK),
+                                   c->streams[0]);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->streams[0]));
+    std::memcpy(mask_out, c->pin_h + PIN_MASK, size_t((S + 31) / 32) * 4);
+    return SQMP_OK;
+  }
   // H2D -> kernel -> D2H in stages over two streams so that copies overlap compute for large batches
   const int64_t chunk = c->pipeline_chunk;
   void *dq[2], *dm[2];
@@ -719,6 +749,28 @@ int sqmp_check_edges(sqmp_ctx *ctx, const double *qa, const double *qb, int64_t 
     return fail(c, SQMP_ERR_INVALID, "check_edges: bad argument");
   if (E == 0) return SQMP_OK;
   const int64_t S = E * (num_points + 1);
+  if (S <= c->small_call_states) {   // planner-shaped call (<= ~60 candidate edges of one iteration)
+    std::memcpy(c->pin_h + PIN_QA, qa, size_t(E) * SQMP_DOF * sizeof(double));
+    std::memcpy(c->pin_h + PIN_QB, qb, size_t(E) * SQMP_DOF * sizeof(double));
+    int rc = sqmp_check_edges_dev(ctx, (const double *)(c->pin_d + PIN_QA), (const double *)(c->pin_d + PIN_QB), E, num_points,
+                                  flags, (uint32_t *)(c->pin_d + PIN_MASK), nullptr, c->streams[0]);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->streams[0]));
+    const uint32_t *m = (const uint32_t *)(c->pin_h + PIN_MASK);
+    std::memcpy(mask_out, m, size_t((S + 31) / 32) * 4);
+    if (first_invalid) {   // isEdgeValid's early exit (BS:6866-6874), from the mask
+      const int P1 = num_points + 1;
+      for (int64_t e = 0; e < E; ++e) {
+        int32_t fi = -1;
+        for (int kq = 0; kq < P1; ++kq) {
+          const int64_t b = e * P1 + kq;
+          if ((m[b >> 5] >> (b & 31)) & 1u) { fi = kq; break; }
+        }
+        first_invalid[e] = fi;
+      }
+    }
+    return SQMP_OK;
+  }
   void *da, *db, *dm, *df;
   int rc;
   if ((rc = ensure(c, 0, size_t(E) * SQMP_DOF * 8, &da))) return rc;
@@ -811,12 +863,14 @@ int sqmp_tree_append(sqmp_ctx *ctx, int tree, const double q[SQMP_DOF], double c
   CHECK_TREE();
   if (!q) return fail(c, SQMP_ERR_INVALID, "tree_append: null q");
   if (t.n >= 0x7fffffff) return fail(c, SQMP_ERR_INVALID, "tree full");
-  CU(cudaStreamSynchronize(c->streams[0]));
+  // stream-ordered, not synchronised: the node travels in the kernel parameters, and every later call that reads
+  // the tree runs on (or synchronises with) the same stream.  Growing the buffers synchronises the device itself.
+  if (t.n + 1 > t.cap) CU(cudaDeviceSynchronize());
   int rc = tree_reserve(c, t, t.n + 1);
   if (rc) return rc;
   tree_track_norm(t, q, 1);
   CU(launch_tree_set_one(t, t.n, q, cost, c->streams[0]));
-  CU(cudaStreamSynchronize(c->streams[0]));
+  c->tree_writes_pending = true;
   c->launches += 1;
   if (id_out) *id_out = int32_t(t.n);
   t.n += 1;
@@ -850,8 +904,8 @@ int sqmp_tree_update(sqmp_ctx *ctx, int tree, int32_t id, const double q[SQMP_DO
   CHECK_TREE();
   if (!q || id < 0 || id >= t.n) return fail(c, SQMP_ERR_INVALID, "tree_update: bad id");
   tree_track_norm(t, q, 1);
-  CU(launch_tree_set_one(t, id, q, cost, c->streams[0]));
-  CU(cudaStreamSynchronize(c->streams[0]));
+  CU(launch_tree_set_one(t, id, q, cost, c->streams[0]));   // stream-ordered (see sqmp_tree_append)
+  c->tree_writes_pending = true;
   c->launches += 1;
   return SQMP_OK;
 }
@@ -882,6 +936,10 @@ int sqmp_nn_nearest_dev(sqmp_ctx *ctx, int tree, const double *d_queries, int64_
   if (Q < 0 || (Q > 0 && (!d_queries || !d_id))) return fail(c, SQMP_ERR_INVALID, "nn_nearest_dev: null pointer");
   if (Q == 0) return SQMP_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (c->tree_writes_pending && st != c->streams[0]) {   // single-node writes are ordered on streams[0] only
+    CU(cudaStreamSynchronize(c->streams[0]));
+    c->tree_writes_pending = false;
+  }
   if (t.n == 0) {  // BS:4084: id stays 0 (the reference would then index an empty vector; we report 0)
     CU(cudaMemsetAsync(d_id, 0, size_t(Q) * 4, st));
     return SQMP_OK;
@@ -905,6 +963,10 @@ int sqmp_nn_radius_dev(sqmp_ctx *ctx, int tree, const double *d_queries, const i
     return fail(c, SQMP_ERR_INVALID, "nn_radius_dev: bad argument");
   if (Q == 0) return SQMP_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (c->tree_writes_pending && st != c->streams[0]) {
+    CU(cudaStreamSynchronize(c->streams[0]));
+    c->tree_writes_pending = false;
+  }
   CU(cudaMemsetAsync(d_overflow, 0, 4, st));
   if (t.n == 0) {
     CU(cudaMemsetAsync(d_count, 0, size_t(Q) * 4, st));
@@ -927,6 +989,18 @@ int sqmp_nn_nearest(sqmp_ctx *ctx, int tree, const double *queries, int64_t Q, i
   CHECK_CTX();
   if (Q < 0 || (Q > 0 && (!queries || !id_out))) return fail(c, SQMP_ERR_INVALID, "nn_nearest: null pointer");
   if (Q == 0) return SQMP_OK;
+  if (Q == 1 && c->nn_variant == 0) {   // the planner's call shape: one launch, answer in mapped host memory
+    CHECK_TREE();
+    if (t.n == 0) { id_out[0] = 0; return SQMP_OK; }
+    int rc1 = nn_prepare(c, 1, c->sm_count, false, t.n);
+    if (rc1) return rc1;
+    CU(launch_nn_single(t, queries, false, -1, 0.0, 0, c->nn, c->d_ticket, (int32_t *)(c->d_ticket + 1),
+                        (int32_t *)(c->pin_d + PIN_RESULT), c->sm_count, c->streams[0]));
+    c->launches += 1;
+    CU(cudaStreamSynchronize(c->streams[0]));
+    id_out[0] = ((volatile int32_t *)(c->pin_h + PIN_RESULT))[0];
+    return SQMP_OK;
+  }
   void *dq, *di;
   int rc;
   if ((rc = ensure(c, 0, size_t(Q) * SQMP_DOF * 8, &dq))) return rc;
@@ -975,6 +1049,25 @@ int sqmp_nn_radius(sqmp_ctx *ctx, int tree, const double *queries, const int32_t
   if (Q < 0 || k < 1 || k > 1024 || (Q > 0 && (!queries || !low_ids || !high_ids || !count_out)))
     return fail(c, SQMP_ERR_INVALID, "nn_radius: bad argument");
   if (Q == 0) return SQMP_OK;
+  if (Q == 1 && k <= 64 && c->nn_variant == 0) {   // the planner's call shape (k_nn_single)
+    CHECK_TREE();
+    if (t.n == 0) {
+      count_out[0] = 0;
+      for (int i = 0; i < k; ++i) low_ids[i] = high_ids[i] = -1;
+      return SQMP_OK;
+    }
+    int rc1 = nn_prepare(c, 1, c->sm_count, true, t.n);   // hit buffer = whole tree at Q = 1
+    if (rc1) return rc1;
+    if (c->nn.hit_cap < t.n) return fail(c, SQMP_ERR_OVERFLOW, "nn_radius: hit pool smaller than the tree");
+    CU(launch_nn_single(t, queries, true, exclude_id ? exclude_id[0] : -1, sumsq_threshold(r), k, c->nn, c->d_ticket,
+                        (int32_t *)(c->d_ticket + 1), (int32_t *)(c->pin_d + PIN_RESULT), c->sm_count, c->streams[0]));
+    c->launches += 1;
+    CU(cudaStreamSynchronize(c->streams[0]));
+    const volatile int32_t *res = (volatile int32_t *)(c->pin_h + PIN_RESULT);
+    count_out[0] = res[0];
+    for (int i = 0; i < k; ++i) { low_ids[i] = res[1 + i]; high_ids[i] = res[1 + k + i]; }
+    return SQMP_OK;
+  }
   // The per-query hit buffer shares a fixed pool; if a batch overflows it, halve the batch (the buffer per
   // query doubles) until it fits — at batch size 1 the buffer holds the whole tree.
   int64_t batch = Q;

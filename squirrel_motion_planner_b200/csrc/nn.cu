@@ -501,6 +501,142 @@ k_nn_topk(const double *__restrict__ cost, const int32_t *__restrict__ hits, int
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// The planner's own call shape: ONE query against a tree of 10^2..10^5 nodes (BS:1189, 1226, 1256 call these once
+// per iteration).  One launch does everything: the query arrives in the kernel parameters (no H2D copy), every CTA
+// scans a slice exactly (fp64, reference order), the last CTA to finish (atomic ticket) folds the partial results —
+// for the radius query it also selects the k lowest / k highest (cost, id) — and writes the answer straight into
+// mapped pinned host memory (no D2H copy).  Host cost of a call: one launch + one stream synchronise.
+// ---------------------------------------------------------------------------------------------------------
+struct OneQuery {
+  double q[SQMP_DOF];
+};
+constexpr int NN1_THREADS = 256;
+
+__device__ __forceinline__ Key block_min_key(Key v, Key *sh) {   // all threads get the block minimum
+  v = warp_min_key(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  Key r = sh[0];
+  for (int w = 1; w < NN1_THREADS / 32; ++w)
+    if (key_lt(sh[w], r)) r = sh[w];
+  return r;
+}
+__device__ __forceinline__ Key block_max_key(Key v, Key *sh) {
+  v = warp_max_key(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  Key r = sh[0];
+  for (int w = 1; w < NN1_THREADS / 32; ++w)
+    if (key_lt(r, sh[w])) r = sh[w];
+  return r;
+}
+
+template <bool RADIUS>
+__global__ void __launch_bounds__(NN1_THREADS)
+k_nn_single(TreePtrs t, int64_t N, OneQuery query, int32_t excl, double s_thr, int k, double *__restrict__ part_d,
+            int32_t *__restrict__ part_id, unsigned *__restrict__ ticket, int32_t *__restrict__ hit_count,
+            int32_t *__restrict__ hits, volatile int32_t *__restrict__ out) {
+  __shared__ Key sh[NN1_THREADS / 32];
+  __shared__ bool is_last;
+  Best best = {NN_INIT_SUMSQ, NN_INIT_DIST, 0};
+  for (int64_t n = int64_t(blockIdx.x) * NN1_THREADS + threadIdx.x; n < N; n += int64_t(gridDim.x) * NN1_THREADS) {
+    double node[SQMP_DOF];
+#pragma unroll
+    for (int d = 0; d < SQMP_DOF; ++d) node[d] = t.q[d][n];   // coalesced SoA
+    const double s = sumsq8(node, query.q);
+    if (RADIUS) {
+      if (s < s_thr && int32_t(n) != excl) hits[atomicAdd(hit_count, 1)] = int32_t(n);   // capacity = tree size
+    } else {
+      offer(best, s, int32_t(n));
+    }
+  }
+  if (!RADIUS) {   // (distance, id) lexicographic minimum of the CTA; Key reuses the (double, id) ordering
+    Key v = {best.d, best.id};
+    v = block_min_key(v, sh);
+    if (threadIdx.x == 0) { part_d[blockIdx.x] = v.c; part_id[blockIdx.x] = v.id; }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (!RADIUS) {
+    // a CTA that found nothing below 10000.0 carries (10000.0, 0): it cannot beat a real candidate (d < 10000.0)
+    Key v = {NN_INIT_DIST, 0};
+    for (int b = threadIdx.x; b < int(gridDim.x); b += NN1_THREADS) {
+      const Key c = {__ldcg(part_d + b), __ldcg(part_id + b)};
+      if (key_lt(c, v)) v = c;
+    }
+    v = block_min_key(v, sh);
+    if (threadIdx.x == 0) out[0] = v.id;
+  } else {
+    const int32_t total = __ldcg(hit_count);
+    const Key kmax = {CUDART_INF, 0x7fffffff}, kmin = {-CUDART_INF, -1};
+    Key last = kmin;
+    bool done = false;
+    for (int tsel = 0; tsel < k; ++tsel) {   // t-th lowest = smallest key strictly above the previous pick
+      Key mine = kmax;
+      if (!done)
+        for (int i = threadIdx.x; i < total; i += NN1_THREADS) {
+          Key c;
+          c.id = __ldcg(hits + i);
+          c.c = t.cost[c.id];
+          if (key_lt(last, c) && key_lt(c, mine)) mine = c;
+        }
+      const Key w = block_min_key(mine, sh);
+      const bool found = !done && w.id != kmax.id;
+      if (threadIdx.x == 0) out[1 + tsel] = found ? w.id : -1;
+      if (!found) done = true;
+      last = w;
+    }
+    last = kmax;
+    done = false;
+    for (int tsel = 0; tsel < k; ++tsel) {   // t-th highest = largest key strictly below the previous pick
+      Key mine = kmin;
+      if (!done)
+        for (int i = threadIdx.x; i < total; i += NN1_THREADS) {
+          Key c;
+          c.id = __ldcg(hits + i);
+          c.c = t.cost[c.id];
+          if (key_lt(c, last) && key_lt(mine, c)) mine = c;
+        }
+      const Key w = block_max_key(mine, sh);
+      const bool found = !done && w.id != kmin.id;
+      if (threadIdx.x == 0) out[1 + k + tsel] = found ? w.id : -1;
+      if (!found) done = true;
+      last = w;
+    }
+    if (threadIdx.x == 0) {
+      out[0] = total;
+      *hit_count = 0;
+    }
+  }
+  if (threadIdx.x == 0) *ticket = 0u;   // ready for the next call on this stream
+}
+
+cudaError_t launch_nn_single(const TreeDev &t, const double *h_query, bool radius, int32_t excl, double s_thr, int k,
+                             NNScratch &sc, unsigned *d_ticket, int32_t *d_hit_count, int32_t *d_out_mapped, int sm_count,
+                             cudaStream_t st) {
+  OneQuery q;
+  for (int d = 0; d < SQMP_DOF; ++d) q.q[d] = h_query[d];
+  int blocks = int((t.n + 4 * NN1_THREADS - 1) / (4 * NN1_THREADS));   // >= 4 nodes per thread before adding CTAs
+  if (blocks > sm_count) blocks = sm_count;
+  if (blocks < 1) blocks = 1;
+  if (radius)
+    k_nn_single<true><<<blocks, NN1_THREADS, 0, st>>>(ptrs_of(t), t.n, q, excl, s_thr, k, sc.part_d, sc.part_id, d_ticket,
+                                                      d_hit_count, sc.hits, d_out_mapped);
+  else
+    k_nn_single<false><<<blocks, NN1_THREADS, 0, st>>>(ptrs_of(t), t.n, q, excl, s_thr, k, sc.part_d, sc.part_id, d_ticket,
+                                                       d_hit_count, sc.hits, d_out_mapped);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------------------
 static void pick_chunks(int64_t N, int64_t Q, int variant, int chunks_hint, int &chunks, int64_t &chunk_len) {

@@ -138,6 +138,10 @@ struct NNScratch {
 // variant: 1 QT fp64-only, 2 WQ fp64-only, 3 QT with fp32 pre-filter (default for many queries)
 cudaError_t launch_nn_nearest(const TreeDev &t, const double *d_queries, int64_t Q, int32_t *d_id, NNScratch &sc,
                               int chunks, int variant, cudaStream_t st, int *n_launch);
+// one query, one launch, result in mapped pinned host memory (nn.cu: k_nn_single)
+cudaError_t launch_nn_single(const TreeDev &t, const double *h_query, bool radius, int32_t excl, double s_thr, int k,
+                             NNScratch &sc, unsigned *d_ticket, int32_t *d_hit_count, int32_t *d_out_mapped, int sm_count,
+                             cudaStream_t st);
 cudaError_t launch_nn_radius(const TreeDev &t, const double *d_queries, const int32_t *d_exclude, int64_t Q,
                              double s_thr, double r, int k, int32_t *d_low, int32_t *d_high, int32_t *d_count,
                              int32_t *d_overflow, NNScratch &sc, int chunks, int variant, cudaStream_t st,

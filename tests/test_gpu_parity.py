@@ -348,6 +348,56 @@ def test_fp32_prefilter_is_sound_on_adversarial_trees(ctx):
         ctx.set_option("nn_variant", 0)
 
 
+def test_single_query_fast_path_equals_batched_path(ctx, orc, small_world):
+    """Q = 1 (the planner's call shape) takes the one-launch path (k_nn_single, answers in mapped pinned memory) and
+    validity calls of <= 4096 states take the zero-copy path; both must equal the batched kernels and the oracle."""
+    rng = np.random.default_rng(31)
+    for N in (1, 2, 33, 1025, 40000):
+        nodes, cost = syn.random_tree(N, seed=700 + N, cost_seed=701 + N, xy_half=2.0)
+        cost = np.round(cost, 1)
+        if N > 40:
+            nodes[N // 3] = nodes[5]
+        ctx.tree_reset(6)
+        ctx.tree_append_batch(6, nodes, cost)
+        queries = syn.sample_configs(6, seed=702 + N, xy_half=2.0)
+        queries[0] = nodes[min(5, N - 1)]
+        want_nn = oracle.nearest(nodes, queries)
+        for i, x in enumerate(queries):
+            assert ctx.nn_nearest(6, x[None])[0] == want_nn[i]                       # fast path, one query at a time
+            ex = int(rng.integers(-1, N))
+            for r, k in ((1.5, 20), (3.0, 5), (100.0, 64), (1e-9, 20)):
+                got = ctx.nn_radius(6, x[None], np.array([ex], np.int32), r, k)       # fast path
+                want = oracle.near_topk(nodes, cost, x[None], np.array([ex], np.int32), r, k)
+                for a, b, name in zip(got, want, ("low", "high", "count")):
+                    assert np.array_equal(a, b), (N, i, r, k, name)
+            got = ctx.nn_radius(6, x[None], None, 2.5, 100)                           # k > 64: batched path
+            want = oracle.near_topk(nodes, cost, x[None], None, 2.5, 100)
+            assert all(np.array_equal(a, b) for a, b in zip(got, want))
+        # appends and updates are stream-ordered, not synchronised: the next query must still see them
+        far = np.full(8, 9.0)
+        nid = ctx.tree_append(6, far, 0.5)
+        assert ctx.nn_nearest(6, far[None])[0] == nid
+        ctx.tree_update(6, 0, far + 1e-3, 0.25)
+        assert ctx.nn_nearest(6, (far + 1e-3)[None])[0] == 0
+    w, origin = small_world
+    ctx.set_voxel_grid(w.bits, w.dims, origin, w.res)
+    orc.set_grid(w.bits, w.dims, origin, w.res)
+    q = syn.state_batch(4096, seed=33, xy_half=2.2)
+    for S in (1, 21, 945, 4096):
+        a = unpack(ctx.check_states(q[:S], api.CHECK_MAP | api.CHECK_SELF), S)        # zero-copy path
+        ctx.set_option("small_call_states", 0)
+        b = unpack(ctx.check_states(q[:S], api.CHECK_MAP | api.CHECK_SELF), S)        # staged path
+        ctx.set_option("small_call_states", 4096)
+        assert np.array_equal(a, b)
+    starts, ends = syn.edge_batch(45, seed=34, xy_half=2.2)
+    m1, f1 = ctx.check_edges(starts, ends, 20, api.CHECK_MAP)
+    ctx.set_option("small_call_states", 0)
+    m2, f2 = ctx.check_edges(starts, ends, 20, api.CHECK_MAP)
+    ctx.set_option("small_call_states", 4096)
+    mo, fo = orc.check_edges(starts, ends, 20, oracle.FLAG_MAP)
+    assert np.array_equal(m1, m2) and np.array_equal(f1, f2) and np.array_equal(f1, fo)
+
+
 def test_radius_overflow_retry_is_exact(ctx):
     """A hit pool far too small for the batch: the host entry point halves the batch until it fits."""
     nodes, cost = syn.random_tree(4000, seed=21, cost_seed=22)
