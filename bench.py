@@ -432,7 +432,7 @@ def run_config5(args):
             pw.write_oracle_model(d, lt, [(n, tuple(c), r_) for n, c, r_ in fx["spheres"]])
             nq_cpu = max(1, min(4, count))
             t0 = time.perf_counter()
-            rc = subprocess.run([os.path.join(shim, "sqmp_plan_oracle"), desc, d, "oracle", str(iters), "1", "0", "0", str(nq_cpu)],
+            rc = subprocess.run([os.path.join(ROOT, "oracle", "sqmp_plan_oracle"), desc, d, "oracle", str(iters), "1", "0", "0", str(nq_cpu)],
                                 capture_output=True, text=True)
             dt = time.perf_counter() - t0
             if rc.returncode == 0:

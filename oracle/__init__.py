@@ -33,6 +33,14 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+def build_planner() -> str:
+    """oracle/sqmp_plan_oracle: the package's planner front-end (shim/sqmp_birrt.hpp) over this CPU oracle — the
+    decision-parity twin of shim/sqmp_plan and the CPU arm of config 5.  Needs the package's library to be built."""
+    build()
+    subprocess.run(["make", "-s", "-C", _HERE, "planner"], check=True, stdout=subprocess.DEVNULL)
+    return os.path.join(_HERE, "sqmp_plan_oracle")
+
+
 def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 

@@ -14,5 +14,5 @@ nq = int(os.environ.get("NQ", "4")); iters = os.environ.get("ITERS", "2000")
 s, g = pw.config1_queries(nq); pw.write_queries(d, s, g)
 for binary, backend in (("sqmp_plan", "gpu"), ("sqmp_plan_oracle", "oracle")):
     t = time.time()
-    r = subprocess.run([os.path.join(SHIM, binary), DESC, d, backend, iters, "1"], capture_output=True, text=True)
+    r = subprocess.run([os.path.join(SHIM if backend == "gpu" else os.path.join(ROOT, "oracle"), binary), DESC, d, backend, iters, "1"], capture_output=True, text=True)
     print(backend, "rc", r.returncode, "wall %.2f s" % (time.time() - t)); print(r.stdout[-600:], r.stderr[-300:])
