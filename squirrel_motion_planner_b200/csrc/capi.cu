@@ -35,8 +35,14 @@ struct Ctx {
   SelfBlock *d_blocks = nullptr;
   SelfDev self;
   uint32_t *d_occ = nullptr;
-  uint8_t *d_lb2 = nullptr;
+  uint8_t *d_lb2 = nullptr;     // halo-padded (GridDev)
   uint16_t *d_ft = nullptr;
+  FastDev fast;                 // tables of the fast validity kernel (validity_fast.cu)
+  FastSlot *d_fast_slots = nullptr;
+  double4 *d_fast_sph64 = nullptr;
+  int fast_chain_ok = 0;        // description: translation-only base, then rotations only, spheres on the rotating part
+  double reach_m = 0.0;         // max distance of a sphere centre from the base reference point (metres)
+  int k1_kernel = 0;            // 0 auto (fast when its preconditions hold) | 1 generic | 2 fast (error if not possible)
   TreeDev trees[SQMP_MAX_TREES];
   NNScratch nn;
   size_t nn_part_bytes = 0, nn_hits_bytes = 0;
@@ -175,6 +181,42 @@ static int refresh_grid_robot(Ctx *c) {
   }
   refresh_float_copies(g);
   refresh_float_copies(c->rb);
+  // ---- tables of the fast validity kernel.  Its stage 1 runs on an fp32 copy of the sphere centre; err bounds the
+  //      distance between that copy and the fp64 centre (cells): per axis <= 2^-24 * 13 (reach + 1) from rounding the
+  //      frame, the sphere offset and three FMAs; doubled here, then sqrt(3) for the Euclidean norm.
+  {
+    c->fast.ok = 0;
+    if (has && c->fast_chain_ok && c->gd.halo > 0) {
+      const double reach_c = c->reach_m * inv + 1.0;
+      const double err = std::sqrt(3.0) * std::ldexp(26.0 * (reach_c + 1.0), -24) + 1e-6;
+      std::vector<FastSlot> fs(size_t(n_slots) + 1);
+      std::vector<double4> s64(size_t(n_slots) + 1);
+      for (int sl = 0; sl < n_slots; ++sl) {
+        const double rg = g.sph[sl][3];
+        FastSlot &f = fs[sl];
+        f.x = float(g.sph[sl][0]); f.y = float(g.sph[sl][1]); f.z = float(g.sph[sl][2]);
+        const double t = std::floor((rg + err) * (rg + err) + 1e-9);
+        f.thr = g.sph_thr[sl] < 0 ? -2 : int(t > 254.0 ? 254.0 : t);
+        const double lo = rg > err ? (rg - err) * (rg - err) * (1.0 - 1e-6) : -1.0;
+        float lof = float(lo);
+        if (double(lof) > lo) lof = std::nextafterf(lof, -INFINITY);
+        f.r2_lo = lof;
+        f.ncell = int(g.sph_ncell[sl]) + 1;
+        f.pad0 = f.pad1 = 0.0f;
+        s64[sl] = make_double4(g.sph[sl][0], g.sph[sl][1], g.sph[sl][2], rg);
+      }
+      cudaError_t e = cudaSuccess;
+      if (!c->d_fast_slots) e = cudaMalloc(&c->d_fast_slots, sizeof(FastSlot) * (SQMP_MAX_SLOTS + 1));
+      if (e == cudaSuccess && !c->d_fast_sph64) e = cudaMalloc(&c->d_fast_sph64, sizeof(double4) * (SQMP_MAX_SLOTS + 1));
+      if (e == cudaSuccess) e = cudaMemcpy(c->d_fast_slots, fs.data(), sizeof(FastSlot) * n_slots, cudaMemcpyHostToDevice);
+      if (e == cudaSuccess) e = cudaMemcpy(c->d_fast_sph64, s64.data(), sizeof(double4) * n_slots, cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) return fail(c, SQMP_ERR_CUDA, "fast validity tables", e);
+      c->fast.slots = c->d_fast_slots;
+      c->fast.sph64 = c->d_fast_sph64;
+      c->fast.n_slots = n_slots;
+      c->fast.ok = 1;
+    }
+  }
   // ---- self-collision hierarchy (SelfDev): blocks of group pairs -> A-spheres -> partner lists ----
   {
     int seg_of[SQMP_MAX_SPHERES];
@@ -502,6 +544,22 @@ sqmp_ctx *sqmp_create(int device, const sqmp_robot_desc *d, int *err_out) {
   for (int s = 1; s <= SQMP_MAX_SEG + 1; ++s)
     if (rb.seg_sph_end[s] < rb.seg_sph_end[s - 1]) rb.seg_sph_end[s] = rb.seg_sph_end[s - 1];
   for (int w = 0; w < SQMP_MAX_SPHERES / 32; ++w) rb.sph_enabled[w] = 0xffffffffu;
+  // fast validity kernel: the base is a translation-only run, everything after it rotates (bounded reach), and every
+  // sphere sits on the rotating part.  reach_m bounds |sphere centre - base reference point| over all configurations.
+  c->fast_chain_ok = c->fk_float_ok && rb.ref_seg >= 0;
+  {
+    double cum = 0.0;
+    c->reach_m = 0.0;
+    for (int s = rb.ref_seg + 1; s < rb.n_seg; ++s) {
+      if (rb.seg_type[s] != SQMP_JOINT_ROT) c->fast_chain_ok = 0;
+      cum += std::sqrt(rb.seg_pre[s][9] * rb.seg_pre[s][9] + rb.seg_pre[s][10] * rb.seg_pre[s][10] +
+                       rb.seg_pre[s][11] * rb.seg_pre[s][11]);
+      for (int i = rb.seg_sph_end[s + 1]; i < rb.seg_sph_end[s + 2]; ++i)
+        c->reach_m = std::fmax(c->reach_m, cum + std::sqrt(rb.sph[i][0] * rb.sph[i][0] + rb.sph[i][1] * rb.sph[i][1] +
+                                                            rb.sph[i][2] * rb.sph[i][2]));
+    }
+    if (!(c->reach_m < 1.0e6)) c->fast_chain_ok = 0;
+  }
 
   c->n_pairs = d->n_pairs;
   c->h_pairs.resize(size_t(d->n_pairs) + 1);
@@ -542,6 +600,8 @@ void sqmp_destroy(sqmp_ctx *ctx) {
   if (ctx->d_occ) cudaFree(ctx->d_occ);
   if (ctx->d_lb2) cudaFree(ctx->d_lb2);
   if (ctx->d_ft) cudaFree(ctx->d_ft);
+  if (ctx->d_fast_slots) cudaFree(ctx->d_fast_slots);
+  if (ctx->d_fast_sph64) cudaFree(ctx->d_fast_sph64);
   for (auto &t : ctx->trees) {
     if (t.q[0]) cudaFree(t.q[0]);
     if (t.fa) cudaFree(t.fa);
@@ -570,6 +630,10 @@ int sqmp_set_option(sqmp_ctx *ctx, const char *name, int64_t value) {
     if (value != 32 && value != 64) return fail(c, SQMP_ERR_INVALID, "fk_precision must be 32 or 64");
     if (value == 32 && !c->fk_float_ok) return fail(c, SQMP_ERR_INVALID, "float chain needs a translation-only base");
     c->fk_precision = int(value);
+  } else if (n == "k1_kernel") {
+    if (value < 0 || value > 2) return fail(c, SQMP_ERR_INVALID, "k1_kernel must be 0 (auto), 1 (generic) or 2 (fast)");
+    if (value == 2 && !c->fast_chain_ok) return fail(c, SQMP_ERR_INVALID, "fast validity kernel needs a translation-only base followed by rotations");
+    c->k1_kernel = int(value);
   } else if (n == "chain_specialization") {
     c->chain_specialization = value != 0;
   } else if (n == "nn_variant") {
@@ -606,6 +670,15 @@ int sqmp_set_voxel_grid(sqmp_ctx *ctx, const uint32_t *bits, int gx, int gy, int
   int window = int(std::ceil(rmax / res)) + 1;
   if (window < 3) window = 3;
   if (window > 15) window = 15;
+  // halo of the distance / feature fields: every cell a sphere centre can fall into while the base is inside the grid
+  int halo = 0;
+  if (c->fast_chain_ok) {
+    const double h = std::ceil(c->reach_m / res) + 2.0;
+    const double pn = (gx + 2.0 * h) * (gy + 2.0 * h) * (gz + 2.0 * h);
+    if (h <= 2048.0 && pn < 4294967296.0) halo = int(h);   // else: no halo, generic kernel only
+  }
+  const int64_t PX = gx + 2 * halo, PY = gy + 2 * halo, PZ = gz + 2 * halo;
+  const int64_t pvox = PX * PY * PZ;
   const int row_words = (gx + 31) / 32 + 1;
   const size_t lin_words = size_t((nvox + 31) / 32) + 1;
   const size_t occ_words = size_t(gy) * gz * row_words;
@@ -623,13 +696,13 @@ int sqmp_set_voxel_grid(sqmp_ctx *ctx, const uint32_t *bits, int gx, int gy, int
   if (e == cudaSuccess) e = cudaMemset(d_lin, 0, lin_words * 4);
   if (e == cudaSuccess) e = cudaMemcpy(d_lin, bits, size_t((nvox + 31) / 32) * 4, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(&d_occ, occ_words * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&d_a, size_t(nvox));
-  if (e == cudaSuccess) e = cudaMalloc(&d_b, size_t(nvox) * 2);
-  if (e == cudaSuccess) e = cudaMalloc(&d_lb2, size_t(nvox));
-  if (e == cudaSuccess) e = cudaMalloc(&d_ft, size_t(nvox) * 2);
+  if (e == cudaSuccess) e = cudaMalloc(&d_a, size_t(pvox));
+  if (e == cudaSuccess) e = cudaMalloc(&d_b, size_t(pvox) * 2);
+  if (e == cudaSuccess) e = cudaMalloc(&d_lb2, size_t(pvox));
+  if (e == cudaSuccess) e = cudaMalloc(&d_ft, size_t(pvox) * 2);
   if (e == cudaSuccess) e = launch_pack_rows(d_lin, gx, gy, gz, row_words, d_occ, nullptr);
   int nl = 1;
-  if (e == cudaSuccess) e = launch_ft_build(d_occ, row_words, gx, gy, gz, window, d_a, d_b, d_lb2, d_ft, nullptr, &nl);
+  if (e == cudaSuccess) e = launch_ft_build(d_occ, row_words, gx, gy, gz, halo, window, d_a, d_b, d_lb2, d_ft, nullptr, &nl);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   cleanup();
   if (e != cudaSuccess) {
@@ -646,7 +719,12 @@ int sqmp_set_voxel_grid(sqmp_ctx *ctx, const uint32_t *bits, int gx, int gy, int
   c->d_lb2 = d_lb2;
   c->d_ft = d_ft;
   GridDev &g = c->gd;
-  g.occ = d_occ; g.lb2 = d_lb2; g.ft = d_ft;
+  g.sx = unsigned(PX);
+  g.splane = unsigned(PX * PY);
+  g.org_off = unsigned((int64_t(halo) * PY + halo) * PX + halo);
+  g.halo = halo;
+  g.occ = d_occ; g.lb2_base = d_lb2; g.ft_base = d_ft;
+  g.lb2 = d_lb2 + g.org_off; g.ft = d_ft + g.org_off;
   g.gx = gx; g.gy = gy; g.gz = gz; g.row_words = row_words;
   g.ox = origin[0]; g.oy = origin[1]; g.oz = origin[2];
   g.res = res; g.inv_res = 1.0 / res;
@@ -664,6 +742,12 @@ int sqmp_set_disabled_links(sqmp_ctx *ctx, uint64_t link_mask) {
 }
 
 // ---------------------------------------------------------------------------------------------------- validity
+// The fast kernel decides the same predicate as the generic fp64 kernel (fp32 only where a proven error bound makes it
+// safe, fp64 for everything near contact); it needs a map check against a grid with halo-padded fields.
+static bool use_fast_k1(const Ctx *c, unsigned flags) {
+  if (c->k1_kernel == 1 || c->fk_precision != 64) return false;
+  return c->fast.ok && (flags & SQMP_CHECK_MAP) && c->gd.has_grid;
+}
 int sqmp_check_states_dev(sqmp_ctx *ctx, const double *d_q, int64_t S, unsigned flags, uint32_t *d_mask,
                           void *stream) {
   CHECK_CTX();
@@ -675,8 +759,11 @@ int sqmp_check_states_dev(sqmp_ctx *ctx, const double *d_q, int64_t S, unsigned 
     return SQMP_OK;
   }
   int nl = 0;
-  CU(launch_check_states(c->rb_grid, c->gd, c->self, d_q, nullptr, 0, S, flags, d_mask, c->fk_precision,
-                         st, &nl));
+  if (use_fast_k1(c, flags))
+    CU(launch_check_states_fast(c->rb_grid, c->gd, c->self, c->fast, d_q, nullptr, 0, S, flags, d_mask, st, &nl));
+  else
+    CU(launch_check_states(c->rb_grid, c->gd, c->self, d_q, nullptr, 0, S, flags, d_mask, c->fk_precision,
+                           st, &nl));
   c->launches += nl;
   return SQMP_OK;
 }
@@ -694,8 +781,11 @@ int sqmp_check_edges_dev(sqmp_ctx *ctx, const double *d_a, const double *d_b, in
     CU(cudaMemsetAsync(d_mask, 0, size_t((S + 31) / 32) * 4, st));
   } else {
     int nl = 0;
-    CU(launch_check_states(c->rb_grid, c->gd, c->self, d_a, d_b, num_points, S, flags, d_mask,
-                           c->fk_precision, st, &nl));
+    if (use_fast_k1(c, flags))
+      CU(launch_check_states_fast(c->rb_grid, c->gd, c->self, c->fast, d_a, d_b, num_points, S, flags, d_mask, st, &nl));
+    else
+      CU(launch_check_states(c->rb_grid, c->gd, c->self, d_a, d_b, num_points, S, flags, d_mask,
+                             c->fk_precision, st, &nl));
     c->launches += nl;
   }
   if (d_first) {

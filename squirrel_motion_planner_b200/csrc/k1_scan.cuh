@@ -1,0 +1,145 @@
+// k1_scan.cuh — the exact stage shared by the validity kernels: sphere vs occupied-voxel boxes by bit-row scans, and
+// the per-warp queue that balances those scans over the lanes.  (Reference semantics replaced: fcl::collide of a link
+// shape against the octree, CC:554-592 — here "some occupied voxel AABB within r of the sphere centre".)
+#pragma once
+#include "fk_device.cuh"
+
+namespace sqmp {
+
+// ------------------------------------------------------------------------------------------------
+// exact sphere vs occupied-voxel-boxes test, in GRID UNITS: voxel (i,j,k) is the unit cube [i,i+1]x[j,j+1]x[k,k+1],
+// the sphere has centre u and radius rg = r / res.  true <=> dist(u, some occupied unit cube) <= rg.
+// Per (j,k) row the admissible x-interval is closed-form, so a row costs one (rarely two) word loads.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool exact_scan(const GridDev &g, double ux, double uy, double uz, double rg) {
+  const double r2 = rg * rg;
+  const int k0 = max(__double2int_rd(uz - rg), 0), k1 = min(__double2int_rd(uz + rg), g.gz - 1);
+  const int j0 = max(__double2int_rd(uy - rg), 0), j1 = min(__double2int_rd(uy + rg), g.gy - 1);
+  double kd = double(k0);
+  for (int k = k0; k <= k1; ++k, kd += 1.0) {
+    const double dz = fmax(fmax(kd - uz, uz - (kd + 1.0)), 0.0);
+    const double remz = fma(-dz, dz, r2);
+    if (remz < 0.0) continue;
+    const uint32_t *slab = g.occ + size_t(k) * g.gy * g.row_words;
+    double jd = double(j0);
+    for (int j = j0; j <= j1; ++j, jd += 1.0) {
+      const double dy = fmax(fmax(jd - uy, uy - (jd + 1.0)), 0.0);
+      const double rem = fma(-dy, dy, remz);
+      if (rem < 0.0) continue;
+      const double w = sqrt(rem);  // half-width of the admissible x interval
+      // cube i is within reach  <=>  i + 1 >= ux - w  and  i <= ux + w
+      int i0 = max(__double2int_ru(ux - w) - 1, 0);
+      const int i1 = min(__double2int_rd(ux + w), g.gx - 1);
+      const uint32_t *row = slab + size_t(j) * g.row_words;
+      while (i0 <= i1) {  // at most 2*ceil(rg)+2 wide: one word, two when it straddles a word boundary
+        const int sh = i0 & 31;
+        const int n = min(32 - sh, i1 - i0 + 1);
+        const uint32_t bits = (row[i0 >> 5] >> sh) & (n >= 32 ? ~0u : ((1u << n) - 1u));
+        if (bits) return true;
+        i0 += n;
+      }
+    }
+  }
+  return false;
+}
+
+// `count` consecutive rows of the (j,k) scan box of one sphere, starting at row (j0 + jj, k), j fastest.
+__device__ __forceinline__ bool scan_rows(const GridDev &g, double ux, double uy, double uz, double rg, int j0, int nj,
+                                          int k, int jj, int count) {
+  const double r2 = rg * rg;
+  for (int n = 0; n < count; ++n) {
+    const double kd = double(k), jd = double(j0 + jj);
+    const double dz = fmax(fmax(kd - uz, uz - (kd + 1.0)), 0.0);
+    const double dy = fmax(fmax(jd - uy, uy - (jd + 1.0)), 0.0);
+    const double rem = fma(-dy, dy, fma(-dz, dz, r2));
+    if (rem >= 0.0) {
+      const double w = sqrt(rem);
+      int i0 = max(__double2int_ru(ux - w) - 1, 0);
+      const int i1 = min(__double2int_rd(ux + w), g.gx - 1);
+      const uint32_t *row = g.occ + (size_t(k) * g.gy + size_t(j0 + jj)) * g.row_words;
+      while (i0 <= i1) {
+        const int sh = i0 & 31;
+        const int m = min(32 - sh, i1 - i0 + 1);
+        const uint32_t bits = (row[i0 >> 5] >> sh) & (m >= 32 ? ~0u : ((1u << m) - 1u));
+        if (bits) return true;
+        i0 += m;
+      }
+    }
+    if (++jj == nj) { jj = 0; ++k; }
+  }
+  return false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1
+// ------------------------------------------------------------------------------------------------
+constexpr int K1_THREADS = 128;
+constexpr int K1_QCAP = 64;       // deferred exact-scan items per warp (drained 32 at a time)
+constexpr int K1_CHUNK = 12;      // rows of an exact scan handed to one lane at a time
+constexpr int K1_BATCH = 4;       // spheres whose field gathers are in flight together
+constexpr unsigned FULL = 0xffffffffu;
+
+struct WarpQueue {   // shared memory, one per warp
+  double x[K1_QCAP], y[K1_QCAP], z[K1_QCAP], r[K1_QCAP];
+  int info[K1_QCAP];   // sphere index << 8 | owner lane
+};
+
+// round-to-nearest integer of x without F2I: the integer lands in the low mantissa bits of (x + 1.5 * 2^mant)
+__device__ __forceinline__ int rn_int(double x) { return __double2loint(x + 6755399441055744.0); }       // |x| < 2^31
+__device__ __forceinline__ int rn_int(float x) { return __float_as_int(x + 12582912.0f) - 0x4B400000; }   // |x| < 2^22
+
+// gap between coordinate f in [0,1] of the centre's own cell and the unit cube at cell offset o
+__device__ __forceinline__ float axis_gap_off(int o, float f) {
+  return o > 0 ? float(o) - f : (o < 0 ? f - float(o) - 1.0f : 0.0f);
+}
+
+// Decide the queued items [base, base+n); returns the verdicts as a mask over the owning lanes.  Items differ by
+// two orders of magnitude in work (a 1-cell finger sphere scans ~9 rows, the 5-cell head sphere ~150), so the
+// unit handed to a lane is not an item but a chunk of <= K1_CHUNK rows: lane l describes item l, a warp prefix
+// sum numbers the chunks, and every lane finds the item of its chunk by a 5-step shuffle binary search.
+// One copy in the binary (called from the two drain sites of K1): keeps the hot loop inside the instruction cache.
+static __device__ __noinline__ unsigned drain_queue(const GridDev &gd, const WarpQueue *wq, int base, int n, unsigned known) {
+  const int lane = threadIdx.x & 31;
+  int nj = 1, j0 = 0, k0 = 0, R = 0, c = 0;
+  if (lane < n) {
+    const int owner = wq->info[base + lane] & 31;
+    if (!((known >> owner) & 1u)) {
+      const double uy = wq->y[base + lane], uz = wq->z[base + lane], rg = wq->r[base + lane];
+      k0 = max(__double2int_rd(uz - rg), 0);
+      j0 = max(__double2int_rd(uy - rg), 0);
+      const int k1 = min(__double2int_rd(uz + rg), gd.gz - 1), j1 = min(__double2int_rd(uy + rg), gd.gy - 1);
+      nj = max(j1 - j0 + 1, 1);
+      R = (j1 >= j0 && k1 >= k0) ? nj * (k1 - k0 + 1) : 0;
+      c = (R + K1_CHUNK - 1) / K1_CHUNK;
+    }
+  }
+  int incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int total = __shfl_sync(FULL, incl, 31);
+  unsigned hm = 0;
+  for (int t0 = 0; t0 < total; t0 += 32) {
+    const int t = t0 + lane;
+    int m = 0;  // first item whose inclusive chunk count exceeds t
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const int v = __shfl_sync(FULL, incl, m + step - 1);
+      if (v <= t) m += step;
+    }
+    const int ex_m = __shfl_sync(FULL, incl - c, m), nj_m = __shfl_sync(FULL, nj, m), j0_m = __shfl_sync(FULL, j0, m),
+              k0_m = __shfl_sync(FULL, k0, m), R_m = __shfl_sync(FULL, R, m);
+    if (t < total) {
+      const double ux = wq->x[base + m], uy = wq->y[base + m], uz = wq->z[base + m], rg = wq->r[base + m];
+      const int r0 = (t - ex_m) * K1_CHUNK, r1 = min(r0 + K1_CHUNK, R_m);
+      const int kk = r0 / nj_m;
+      if (scan_rows(gd, ux, uy, uz, rg, j0_m, nj_m, k0_m + kk, r0 - kk * nj_m, r1 - r0))
+        hm |= 1u << (wq->info[base + m] & 31);
+    }
+  }
+  return __reduce_or_sync(FULL, hm);
+}
+
+}  // namespace sqmp

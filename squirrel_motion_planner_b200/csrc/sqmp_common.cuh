@@ -62,9 +62,32 @@ struct GridDev {
   // squared box-to-box distance bb2(C,O) = sum_a max(|o_a|-1,0)^2 (o = O - C; ties: smaller centre distance):
   const uint8_t *lb2;    //   min(bb2(C,O*), 255); 255 also when nothing is occupied within the build window
   const uint16_t *ft;    //   (ox+15) | (oy+15)<<5 | (oz+15)<<10 of O*, 0xFFFF when none
+  // lb2 and ft live in a domain padded by `halo` cells on every side (halo >= reach of any sphere centre from the
+  // base reference + 2): a state whose base lies inside the grid can index them for every sphere with no bounds
+  // test.  lb2 / ft point at in-grid cell (0,0,0); cell (i,j,k) is at [k * splane + j * sx + i], i in [-halo, gx+halo).
+  // lb2_base / ft_base are the allocation starts = cell (-halo,-halo,-halo); org_off = offset of (0,0,0) from them.
+  const uint8_t *lb2_base;
+  const uint16_t *ft_base;
+  unsigned sx, splane, org_off;
+  int halo;
   int gx, gy, gz, row_words;
   int has_grid;
   double ox, oy, oz, res, inv_res;
+};
+
+// Tables of the fast validity kernel (validity_fast.cu), in global memory; rebuilt with the grid-unit robot.
+struct FastSlot {      // 32 bytes per slot, staged in shared memory by every CTA
+  float x, y, z;       // sphere centre in its group frame, grid units, fp32
+  int thr;             // stage-1 threshold: lb2 > thr proves the sphere free even after the fp32 centre error; -2: never test
+  float r2_lo;         // (rg - err)^2 rounded down: ub2 <= r2_lo proves a hit even after the fp32 centre error
+  int ncell;           // ceil(rg) + 1 (reach test of a sphere whose state lies outside the comfortable region)
+  float pad0, pad1;
+};
+struct FastDev {
+  const FastSlot *slots;     // [n_slots]
+  const double4 *sph64;      // [n_slots]: x y z r, grid units, fp64 (exact stage)
+  int n_slots;
+  int ok;                    // the description and the grid satisfy the fast kernel's preconditions
 };
 
 // Self collision (CC:541-552) as a three-level hierarchy over the enabled sphere pairs, all between different rigid
@@ -107,9 +130,12 @@ cudaError_t launch_get_collisions(const RobotDev &rb, const GridDev &gd, const S
                                   const double *d_q, uint8_t *d_sphere_hit, uint8_t *d_pair_hit, cudaStream_t st);
 cudaError_t launch_fk(const RobotDev &rb, const double *d_q, int64_t S, double *d_out, int fk_precision,
                       bool allow_specialized, cudaStream_t st);
-cudaError_t launch_ft_build(const uint32_t *d_occ, int row_words, int gx, int gy, int gz, int window,
+cudaError_t launch_ft_build(const uint32_t *d_occ, int row_words, int gx, int gy, int gz, int halo, int window,
                             int8_t *d_tmp_a, uint16_t *d_tmp_b, uint8_t *d_lb2, uint16_t *d_ft, cudaStream_t st,
                             int *n_launch);
+cudaError_t launch_check_states_fast(const RobotDev &rb, const GridDev &gd, const SelfDev &self, const FastDev &fd,
+                                     const double *d_q, const double *d_q_end, int num_points, int64_t S,
+                                     unsigned flags, uint32_t *d_mask, cudaStream_t st, int *n_launch);
 cudaError_t launch_pack_rows(const uint32_t *d_bits_linear, int gx, int gy, int gz, int row_words, uint32_t *d_occ,
                              cudaStream_t st);
 

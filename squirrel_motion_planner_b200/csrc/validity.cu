@@ -12,145 +12,10 @@
 //   (3) the exact test "some occupied voxel AABB within r of the centre" by scanning bit-packed x-rows:
 //       per (j,k) row the admissible x-interval is closed-form, so a row costs one (rarely two) word loads.
 // The verdicts of a warp are packed by one ballot into one 32-bit word — the mask layout of the C ABI.
-#include "fk_device.cuh"
+#include "k1_scan.cuh"
+#include "k1_self.cuh"
 
 namespace sqmp {
-
-// ------------------------------------------------------------------------------------------------
-// exact sphere vs occupied-voxel-boxes test, in GRID UNITS: voxel (i,j,k) is the unit cube [i,i+1]x[j,j+1]x[k,k+1],
-// the sphere has centre u and radius rg = r / res.  true <=> dist(u, some occupied unit cube) <= rg.
-// Per (j,k) row the admissible x-interval is closed-form, so a row costs one (rarely two) word loads.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool exact_scan(const GridDev &g, double ux, double uy, double uz, double rg) {
-  const double r2 = rg * rg;
-  const int k0 = max(__double2int_rd(uz - rg), 0), k1 = min(__double2int_rd(uz + rg), g.gz - 1);
-  const int j0 = max(__double2int_rd(uy - rg), 0), j1 = min(__double2int_rd(uy + rg), g.gy - 1);
-  double kd = double(k0);
-  for (int k = k0; k <= k1; ++k, kd += 1.0) {
-    const double dz = fmax(fmax(kd - uz, uz - (kd + 1.0)), 0.0);
-    const double remz = fma(-dz, dz, r2);
-    if (remz < 0.0) continue;
-    const uint32_t *slab = g.occ + size_t(k) * g.gy * g.row_words;
-    double jd = double(j0);
-    for (int j = j0; j <= j1; ++j, jd += 1.0) {
-      const double dy = fmax(fmax(jd - uy, uy - (jd + 1.0)), 0.0);
-      const double rem = fma(-dy, dy, remz);
-      if (rem < 0.0) continue;
-      const double w = sqrt(rem);  // half-width of the admissible x interval
-      // cube i is within reach  <=>  i + 1 >= ux - w  and  i <= ux + w
-      int i0 = max(__double2int_ru(ux - w) - 1, 0);
-      const int i1 = min(__double2int_rd(ux + w), g.gx - 1);
-      const uint32_t *row = slab + size_t(j) * g.row_words;
-      while (i0 <= i1) {  // at most 2*ceil(rg)+2 wide: one word, two when it straddles a word boundary
-        const int sh = i0 & 31;
-        const int n = min(32 - sh, i1 - i0 + 1);
-        const uint32_t bits = (row[i0 >> 5] >> sh) & (n >= 32 ? ~0u : ((1u << n) - 1u));
-        if (bits) return true;
-        i0 += n;
-      }
-    }
-  }
-  return false;
-}
-
-// `count` consecutive rows of the (j,k) scan box of one sphere, starting at row (j0 + jj, k), j fastest.
-__device__ __forceinline__ bool scan_rows(const GridDev &g, double ux, double uy, double uz, double rg, int j0, int nj,
-                                          int k, int jj, int count) {
-  const double r2 = rg * rg;
-  for (int n = 0; n < count; ++n) {
-    const double kd = double(k), jd = double(j0 + jj);
-    const double dz = fmax(fmax(kd - uz, uz - (kd + 1.0)), 0.0);
-    const double dy = fmax(fmax(jd - uy, uy - (jd + 1.0)), 0.0);
-    const double rem = fma(-dy, dy, fma(-dz, dz, r2));
-    if (rem >= 0.0) {
-      const double w = sqrt(rem);
-      int i0 = max(__double2int_ru(ux - w) - 1, 0);
-      const int i1 = min(__double2int_rd(ux + w), g.gx - 1);
-      const uint32_t *row = g.occ + (size_t(k) * g.gy + size_t(j0 + jj)) * g.row_words;
-      while (i0 <= i1) {
-        const int sh = i0 & 31;
-        const int m = min(32 - sh, i1 - i0 + 1);
-        const uint32_t bits = (row[i0 >> 5] >> sh) & (m >= 32 ? ~0u : ((1u << m) - 1u));
-        if (bits) return true;
-        i0 += m;
-      }
-    }
-    if (++jj == nj) { jj = 0; ++k; }
-  }
-  return false;
-}
-
-// ------------------------------------------------------------------------------------------------
-// K1
-// ------------------------------------------------------------------------------------------------
-constexpr int K1_THREADS = 128;
-constexpr int K1_QCAP = 64;       // deferred exact-scan items per warp (drained 32 at a time)
-constexpr int K1_CHUNK = 12;      // rows of an exact scan handed to one lane at a time
-constexpr int K1_BATCH = 4;       // spheres whose field gathers are in flight together
-constexpr unsigned FULL = 0xffffffffu;
-
-struct WarpQueue {   // shared memory, one per warp
-  double x[K1_QCAP], y[K1_QCAP], z[K1_QCAP], r[K1_QCAP];
-  int info[K1_QCAP];   // sphere index << 8 | owner lane
-};
-
-// round-to-nearest integer of x without F2I: the integer lands in the low mantissa bits of (x + 1.5 * 2^mant)
-__device__ __forceinline__ int rn_int(double x) { return __double2loint(x + 6755399441055744.0); }       // |x| < 2^31
-__device__ __forceinline__ int rn_int(float x) { return __float_as_int(x + 12582912.0f) - 0x4B400000; }   // |x| < 2^22
-
-// gap between coordinate f in [0,1] of the centre's own cell and the unit cube at cell offset o
-__device__ __forceinline__ float axis_gap_off(int o, float f) {
-  return o > 0 ? float(o) - f : (o < 0 ? f - float(o) - 1.0f : 0.0f);
-}
-
-// Decide the queued items [base, base+n); returns the verdicts as a mask over the owning lanes.  Items differ by
-// two orders of magnitude in work (a 1-cell finger sphere scans ~9 rows, the 5-cell head sphere ~150), so the
-// unit handed to a lane is not an item but a chunk of <= K1_CHUNK rows: lane l describes item l, a warp prefix
-// sum numbers the chunks, and every lane finds the item of its chunk by a 5-step shuffle binary search.
-// One copy in the binary (called from the two drain sites of K1): keeps the hot loop inside the instruction cache.
-__device__ __noinline__ unsigned drain_queue(const GridDev &gd, const WarpQueue *wq, int base, int n, unsigned known) {
-  const int lane = threadIdx.x & 31;
-  int nj = 1, j0 = 0, k0 = 0, R = 0, c = 0;
-  if (lane < n) {
-    const int owner = wq->info[base + lane] & 31;
-    if (!((known >> owner) & 1u)) {
-      const double uy = wq->y[base + lane], uz = wq->z[base + lane], rg = wq->r[base + lane];
-      k0 = max(__double2int_rd(uz - rg), 0);
-      j0 = max(__double2int_rd(uy - rg), 0);
-      const int k1 = min(__double2int_rd(uz + rg), gd.gz - 1), j1 = min(__double2int_rd(uy + rg), gd.gy - 1);
-      nj = max(j1 - j0 + 1, 1);
-      R = (j1 >= j0 && k1 >= k0) ? nj * (k1 - k0 + 1) : 0;
-      c = (R + K1_CHUNK - 1) / K1_CHUNK;
-    }
-  }
-  int incl = c;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(FULL, incl, o);
-    if (lane >= o) incl += v;
-  }
-  const int total = __shfl_sync(FULL, incl, 31);
-  unsigned hm = 0;
-  for (int t0 = 0; t0 < total; t0 += 32) {
-    const int t = t0 + lane;
-    int m = 0;  // first item whose inclusive chunk count exceeds t
-#pragma unroll
-    for (int step = 16; step > 0; step >>= 1) {
-      const int v = __shfl_sync(FULL, incl, m + step - 1);
-      if (v <= t) m += step;
-    }
-    const int ex_m = __shfl_sync(FULL, incl - c, m), nj_m = __shfl_sync(FULL, nj, m), j0_m = __shfl_sync(FULL, j0, m),
-              k0_m = __shfl_sync(FULL, k0, m), R_m = __shfl_sync(FULL, R, m);
-    if (t < total) {
-      const double ux = wq->x[base + m], uy = wq->y[base + m], uz = wq->z[base + m], rg = wq->r[base + m];
-      const int r0 = (t - ex_m) * K1_CHUNK, r1 = min(r0 + K1_CHUNK, R_m);
-      const int kk = r0 / nj_m;
-      if (scan_rows(gd, ux, uy, uz, rg, j0_m, nj_m, k0_m + kk, r0 - kk * nj_m, r1 - r0))
-        hm |= 1u << (wq->info[base + m] & 31);
-    }
-  }
-  return __reduce_or_sync(FULL, hm);
-}
 
 template <typename T> struct K1Cfg;
 template <> struct K1Cfg<double> { static constexpr int MIN_BLOCKS = 4; };
@@ -258,7 +123,7 @@ k1_check_states(const __grid_constant__ RobotDev rb, const __grid_constant__ Gri
     sg0 = rb.ref_seg + 1;
   }
 
-  const unsigned plane = unsigned(gd.gy) * unsigned(gd.gx);   // host guarantees gx*gy*gz < 2^32
+  const unsigned plane = gd.splane, sx = gd.sx;   // strides of the halo-padded fields (host: padded cells < 2^32)
   bool live = do_map && sane;   // this lane still needs map tests (MODE 0: until its first hit)
   for (int sg = -1; sg < rb.n_seg; ++sg) {
     if (sg >= sg0) frame_advance_smem<T>(f, rb, sg, q_mine, K1_THREADS);
@@ -298,7 +163,7 @@ k1_check_states(const __grid_constant__ RobotDev rb, const __grid_constant__ Gri
         const int ix = ci[u][0] + bc[0], iy = ci[u][1] + bc[1], iz = ci[u][2] + bc[2];
         const bool inside = unsigned(ix) < unsigned(gd.gx) && unsigned(iy) < unsigned(gd.gy) && unsigned(iz) < unsigned(gd.gz);
         // squared box-to-box distance of this cell to the nearest occupied cell: a lower bound of dist(centre, occupied)^2
-        lbv[u] = inside ? int(gd.lb2[unsigned(iz) * plane + unsigned(iy) * unsigned(gd.gx) + unsigned(ix)]) : -1;
+        lbv[u] = inside ? int(gd.lb2[unsigned(iz) * plane + unsigned(iy) * sx + unsigned(ix)]) : -1;
       }
       // sph_thr[i] = floor(rg^2), or -2 for a pad slot / a sphere whose link is disabled (lbv is -1 outside the grid): an
       // integer compare, and ~89 % of the spheres end here
@@ -331,7 +196,7 @@ k1_check_states(const __grid_constant__ RobotDev rb, const __grid_constant__ Gri
             sphere_hit[i] = exact_scan(gd, double(cx) + (0.5 + double(bc[0])), double(cy) + (0.5 + double(bc[1])),
                                        double(cz) + (0.5 + double(bc[2])), rg) ? 1 : 0;
           } else if (lb >= 0) {
-            const unsigned v = gd.ft[unsigned(jz + bc[2]) * plane + unsigned(jy + bc[1]) * unsigned(gd.gx) + unsigned(jx + bc[0])];
+            const unsigned v = gd.ft[unsigned(jz + bc[2]) * plane + unsigned(jy + bc[1]) * sx + unsigned(jx + bc[0])];
             const float fx = float(cx - T(jx)) + 0.5f, fy = float(cy - T(jy)) + 0.5f, fz = float(cz - T(jz)) + 0.5f;
             const float gx_ = axis_gap_off(int(v & 31u) - 15, fx), gy_ = axis_gap_off(int((v >> 5) & 31u) - 15, fy),
                         gz_ = axis_gap_off(int((v >> 10) & 31u) - 15, fz);
@@ -381,59 +246,21 @@ k1_check_states(const __grid_constant__ RobotDev rb, const __grid_constant__ Gri
   // ---- self collision over the enabled cross-group sphere pairs (CC:541-552), hierarchically (SelfDev) ----
   if (do_self && (MODE == 1 || !hit)) {
     if (rb.self_const_collision) hit = true;
-    auto load_frame = [&](int fi, float (&F)[12]) {
-#pragma unroll
-      for (int k = 0; k < 12; ++k) F[k] = f_mine[(fi * 12 + k) * K1_THREADS];
-    };
-    auto xform = [](const float (&F)[12], float cx, float cy, float cz, float &x, float &y, float &z) {
-      x = fmaf(F[0], cx, fmaf(F[1], cy, fmaf(F[2], cz, F[9])));
-      y = fmaf(F[3], cx, fmaf(F[4], cy, fmaf(F[5], cz, F[10])));
-      z = fmaf(F[6], cx, fmaf(F[7], cy, fmaf(F[8], cz, F[11])));
-    };
-    auto dist2 = [](float ax, float ay, float az, float bx, float by, float bz) {
-      const float dx = ax - bx, dy = ay - by, dz = az - bz;
-      return fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-    };
     if (MODE == 1) {   // diagnostics: every pair of the description, in its order
       for (int p = 0; p < self.n_pairs; ++p) {
         const SelfPair pr = self.flat[p];
         float FA[12], FB[12], ax, ay, az, bx, by, bz;
-        load_frame(pr.fa, FA);
-        load_frame(pr.fb, FB);
+        self_load_frame(f_mine, K1_THREADS, pr.fa, FA);
+        self_load_frame(f_mine, K1_THREADS, pr.fb, FB);
         const float4 ca = rb.sph_f[pr.a], cb = rb.sph_f[pr.b];
-        xform(FA, ca.x, ca.y, ca.z, ax, ay, az);
-        xform(FB, cb.x, cb.y, cb.z, bx, by, bz);
-        const bool h = dist2(ax, ay, az, bx, by, bz) <= pr.rsum2;
+        self_xform(FA, ca.x, ca.y, ca.z, ax, ay, az);
+        self_xform(FB, cb.x, cb.y, cb.z, bx, by, bz);
+        const bool h = self_dist2(ax, ay, az, bx, by, bz) <= pr.rsum2;
         hit |= h;
         pair_hit[p] = h ? 1 : 0;
       }
-    } else {
-      for (int bi = 0; bi < self.n_blocks; ++bi) {
-        if (hit) break;
-        const SelfBlock B = self.blocks[bi];
-        float FA[12], FB[12], ax, ay, az, bx, by, bz;
-        load_frame(B.fa, FA);
-        load_frame(B.fb, FB);
-        xform(FA, B.ca[0], B.ca[1], B.ca[2], ax, ay, az);
-        xform(FB, B.cb[0], B.cb[1], B.cb[2], bx, by, bz);   // bounding sphere of the block's B side
-        if (dist2(ax, ay, az, bx, by, bz) > B.thr2) continue;
-        for (int ai = B.a_begin; ai < B.a_end && !hit; ++ai) {
-          const SelfA A = self.as[ai];
-          const float4 ca = rb.sph_f[A.a];
-          xform(FA, ca.x, ca.y, ca.z, ax, ay, az);
-          if (dist2(ax, ay, az, bx, by, bz) > A.thr2) continue;
-          for (int p = A.p_begin; p < A.p_end; ++p) {
-            const SelfPair pr = self.pairs[p];
-            const float4 cb = rb.sph_f[pr.b];
-            float px, py, pz;
-            xform(FB, cb.x, cb.y, cb.z, px, py, pz);
-            if (dist2(ax, ay, az, px, py, pz) <= pr.rsum2) {
-              hit = true;
-              break;
-            }
-          }
-        }
-      }
+    } else if (!hit) {
+      hit = self_collision(self, rb, f_mine, K1_THREADS);
     }
   }
 
@@ -553,47 +380,52 @@ cudaError_t launch_pack_rows(const uint32_t *d_bits_linear, int gx, int gy, int 
 constexpr int FT_NONE8 = -128;
 __device__ __forceinline__ int bbgap2(int d) { const int g = max(abs(d) - 1, 0); return g * g; }
 
-__global__ void k_ft_x(const uint32_t *__restrict__ occ, int row_words, int gx, int64_t rows, int W,
+// All three passes run over the HALO-PADDED domain (gx+2H) x (gy+2H) x (gz+2H), occupancy zero outside the grid, so
+// that lb2 / ft are defined for every cell a sphere centre can fall into while the base is inside the grid.
+__global__ void k_ft_x(const uint32_t *__restrict__ occ, int row_words, int gx, int gy, int gz, int H, int W,
                        int8_t *__restrict__ a) {
   const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= rows * gx) return;
-  const int i = int(idx % gx);
-  const uint32_t *row = occ + (idx / gx) * row_words;
+  const int PX = gx + 2 * H, PY = gy + 2 * H, PZ = gz + 2 * H;
+  if (idx >= int64_t(PX) * PY * PZ) return;
+  const int i = int(idx % PX) - H, j = int((idx / PX) % PY) - H, k = int(idx / (int64_t(PX) * PY)) - H;
   int best = FT_NONE8;
-  for (int d = 0; d <= W && best == FT_NONE8; ++d) {
-    const int l = i - d, r = i + d;
-    if (r < gx && ((row[r >> 5] >> (r & 31)) & 1u)) best = d;
-    else if (l >= 0 && ((row[l >> 5] >> (l & 31)) & 1u)) best = -d;
+  if (unsigned(j) < unsigned(gy) && unsigned(k) < unsigned(gz)) {
+    const uint32_t *row = occ + (int64_t(k) * gy + j) * row_words;
+    for (int d = 0; d <= W && best == FT_NONE8; ++d) {
+      const int l = i - d, r = i + d;
+      if (unsigned(r) < unsigned(gx) && ((row[r >> 5] >> (r & 31)) & 1u)) best = d;
+      else if (unsigned(l) < unsigned(gx) && ((row[l >> 5] >> (l & 31)) & 1u)) best = -d;
+    }
   }
   a[idx] = int8_t(best);
 }
-__global__ void k_ft_y(const int8_t *__restrict__ a, int gx, int gy, int gz, int W, uint16_t *__restrict__ b) {
+__global__ void k_ft_y(const int8_t *__restrict__ a, int PX, int PY, int PZ, int W, uint16_t *__restrict__ b) {
   const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= int64_t(gx) * gy * gz) return;
-  const int i = int(idx % gx), j = int((idx / gx) % gy);
-  const int64_t k = idx / (int64_t(gx) * gy);
+  if (idx >= int64_t(PX) * PY * PZ) return;
+  const int i = int(idx % PX), j = int((idx / PX) % PY);
+  const int64_t k = idx / (int64_t(PX) * PY);
   int best = 0x7fffffff, bx = 0, by = 0;
   for (int d = -W; d <= W; ++d) {
     const int jj = j + d;
-    if (jj < 0 || jj >= gy) continue;
-    const int ox = a[(k * gy + jj) * gx + i];
+    if (jj < 0 || jj >= PY) continue;
+    const int ox = a[(k * PY + jj) * PX + i];
     if (ox == FT_NONE8) continue;
     const int key = (bbgap2(ox) + bbgap2(d)) * 4096 + ox * ox + d * d;
     if (key < best) { best = key; bx = ox; by = d; }
   }
   b[idx] = best == 0x7fffffff ? uint16_t(0xFFFF) : uint16_t((bx + 128) | ((by + 128) << 8));
 }
-__global__ void k_ft_z(const uint16_t *__restrict__ b, int gx, int gy, int gz, int W, uint8_t *__restrict__ lb2,
+__global__ void k_ft_z(const uint16_t *__restrict__ b, int PX, int PY, int PZ, int W, uint8_t *__restrict__ lb2,
                        uint16_t *__restrict__ ft) {
   const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int64_t plane = int64_t(gx) * gy;
-  if (idx >= plane * gz) return;
+  const int64_t plane = int64_t(PX) * PY;
+  if (idx >= plane * PZ) return;
   const int k = int(idx / plane);
   const int64_t ij = idx % plane;
   int best = 0x7fffffff, bx = 0, by = 0, bz = 0;
   for (int d = -W; d <= W; ++d) {
     const int kk = k + d;
-    if (kk < 0 || kk >= gz) continue;
+    if (kk < 0 || kk >= PZ) continue;
     const unsigned v = b[kk * plane + ij];
     if (v == 0xFFFFu) continue;
     const int ox = int(v & 255u) - 128, oy = int(v >> 8) - 128;
@@ -608,14 +440,16 @@ __global__ void k_ft_z(const uint16_t *__restrict__ b, int gx, int gy, int gz, i
     ft[idx] = uint16_t((bx + 15) | ((by + 15) << 5) | ((bz + 15) << 10));
   }
 }
-cudaError_t launch_ft_build(const uint32_t *d_occ, int row_words, int gx, int gy, int gz, int window,
+// d_tmp_a / d_tmp_b / d_lb2 / d_ft all hold (gx+2H)(gy+2H)(gz+2H) cells
+cudaError_t launch_ft_build(const uint32_t *d_occ, int row_words, int gx, int gy, int gz, int halo, int window,
                             int8_t *d_tmp_a, uint16_t *d_tmp_b, uint8_t *d_lb2, uint16_t *d_ft, cudaStream_t st,
                             int *n_launch) {
-  const int64_t n = int64_t(gx) * gy * gz;
+  const int PX = gx + 2 * halo, PY = gy + 2 * halo, PZ = gz + 2 * halo;
+  const int64_t n = int64_t(PX) * PY * PZ;
   const unsigned blocks = unsigned((n + 255) / 256);
-  k_ft_x<<<blocks, 256, 0, st>>>(d_occ, row_words, gx, int64_t(gy) * gz, window, d_tmp_a);
-  k_ft_y<<<blocks, 256, 0, st>>>(d_tmp_a, gx, gy, gz, window, d_tmp_b);
-  k_ft_z<<<blocks, 256, 0, st>>>(d_tmp_b, gx, gy, gz, window, d_lb2, d_ft);
+  k_ft_x<<<blocks, 256, 0, st>>>(d_occ, row_words, gx, gy, gz, halo, window, d_tmp_a);
+  k_ft_y<<<blocks, 256, 0, st>>>(d_tmp_a, PX, PY, PZ, window, d_tmp_b);
+  k_ft_z<<<blocks, 256, 0, st>>>(d_tmp_b, PX, PY, PZ, window, d_lb2, d_ft);
   if (n_launch) *n_launch += 3;
   return cudaGetLastError();
 }

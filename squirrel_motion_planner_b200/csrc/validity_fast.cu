@@ -1,0 +1,264 @@
+// validity_fast.cu — K1F: the state-validity kernel the library uses whenever its preconditions hold (sqmp_create /
+// sqmp_set_voxel_grid decide; otherwise the generic K1 of validity.cu runs).  Same predicate, same verdicts.
+//
+// Reference path replaced (file:line in /root/reference): CollisionChecker::isInCollision CC:104-121, updateTransforms
+// CC:519-539, checkMapCollision CC:554-592, checkSelfCollision CC:541-552; BiRRTstarPlanner::interpolateConfigurations
+// BS:4443-4490, isEdgeValid BS:6864-6895.
+//
+// Why a second kernel.  The generic K1 spends ~45 % of its instructions proving "this sphere is nowhere near an
+// obstacle" in fp64 with per-sphere bounds logic.  Here that proof runs in fp32 and is still exact:
+//   * the chain is walked in fp64 (identical frames to K1); per rigid group the frame is rounded ONCE to fp32 in
+//     coordinates relative to the base's own cell, so |fp32 centre - fp64 centre| <= err (host-computed bound, ~5e-5
+//     cells; capi.cu: refresh_grid_robot);
+//   * stage 1 (every sphere): 9 FFMA, 3 magic adds, 2 IMAD, one byte gather from the halo-padded lower-bound field —
+//     no bounds test, because the field covers every cell a sphere can reach while the base is inside the grid.
+//     "lb2 > thr" with thr = floor((rg + err)^2) proves the fp64 centre free as well;
+//   * stage 2 (the ~11 % that stage 1 cannot prove free): the feature-field upper bound in fp32 against
+//     (rg - err)^2 proves a hit for the fp64 centre as well;
+//   * stage 3 (neither bound decides, ~1.5 spheres per state): the fp64 centre is formed from the fp64 frame exactly as
+//     K1 forms it and queued for the same exact bit-row scan (k1_scan.cuh).
+// States whose base lies outside the grid (or is not finite) never use the fp32 path: their spheres go through the
+// reach test and the exact scan only.
+#include "k1_scan.cuh"
+#include "k1_self.cuh"
+
+namespace sqmp {
+
+constexpr int KF_THREADS = 128;
+constexpr int KF_MIN_BLOCKS = 5;
+constexpr float KF_MAGIC = 12582912.0f;          // 1.5 * 2^23: (x + MAGIC) has round-to-nearest-even(x) in its low mantissa bits
+constexpr unsigned KF_MAGIC_BITS = 0x4B400000u;  // bit pattern of MAGIC
+
+__device__ __forceinline__ float kf_gap(int o, float f) {   // gap between coordinate f in [0,1] of the own cell and the unit cube at offset o
+  return o > 0 ? float(o) - f : (o < 0 ? f - float(o) - 1.0f : 0.0f);
+}
+
+template <bool EDGES, bool SELF>
+__global__ void __launch_bounds__(KF_THREADS, KF_MIN_BLOCKS)
+k1_fast(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd, const __grid_constant__ SelfDev self,
+        const __grid_constant__ FastDev fd, const double *__restrict__ q_in, const double *__restrict__ q_end,
+        int num_points, int64_t S, uint32_t *__restrict__ mask_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WarpQueue *wq = reinterpret_cast<WarpQueue *>(smem_raw) + (threadIdx.x >> 5);
+  double *q_mine = reinterpret_cast<double *>(smem_raw + sizeof(WarpQueue) * (KF_THREADS / 32)) + threadIdx.x;  // [8][blockDim]
+  float4 *slots4 = reinterpret_cast<float4 *>(smem_raw + sizeof(WarpQueue) * (KF_THREADS / 32) + sizeof(double) * SQMP_DOF * KF_THREADS);
+  float *f_mine = reinterpret_cast<float *>(slots4 + 2 * fd.n_slots) + threadIdx.x;   // SELF: [n_frames*12][blockDim]
+  const int lane = threadIdx.x & 31;
+  const int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool active = s < S;
+  const int64_t sl = active ? s : S - 1;  // idle lanes of the last warp shadow the last state (lockstep loops)
+
+  // ---- slot table -> shared memory (2 x 16 bytes per slot) ----
+  {
+    const float4 *src = reinterpret_cast<const float4 *>(fd.slots);
+    for (int i = threadIdx.x; i < 2 * fd.n_slots; i += KF_THREADS) slots4[i] = __ldg(src + i);
+  }
+
+  // ---- the state: either given, or interpolated from the edge end points (BS:4461-4462, 4478; no FMA) ----
+  double q[SQMP_DOF];
+  if (EDGES) {
+    const int P1 = num_points + 1;
+    const int64_t e = sl / P1;
+    const int kk = int(sl - e * P1);
+    const double4 *a4 = reinterpret_cast<const double4 *>(q_in + e * SQMP_DOF);
+    const double4 *b4 = reinterpret_cast<const double4 *>(q_end + e * SQMP_DOF);
+    const double4 a0 = a4[0], a1 = a4[1], b0 = b4[0], b1 = b4[1];
+    const double st[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const double en[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const double np = double(num_points), fk = double(kk);
+#pragma unroll
+    for (int j = 0; j < SQMP_DOF; ++j)
+      q[j] = __dadd_rn(st[j], __dmul_rn(fk, __ddiv_rn(__dsub_rn(en[j], st[j]), np)));
+  } else {
+    const double4 *p4 = reinterpret_cast<const double4 *>(q_in + sl * SQMP_DOF);
+    const double4 v0 = p4[0], v1 = p4[1];
+    q[0] = v0.x; q[1] = v0.y; q[2] = v0.z; q[3] = v0.w;
+    q[4] = v1.x; q[5] = v1.y; q[6] = v1.z; q[7] = v1.w;
+  }
+  bool sane = true;   // a non-finite or absurd joint value cannot reach the grid: no map test (as K1)
+#pragma unroll
+  for (int j = 0; j < SQMP_DOF; ++j) {
+    const double v = ((rb.trans_mask >> j) & 1) ? q[j] * rb.len_scale : q[j];
+    sane = sane && (fabs(v) < 1.0e9);
+    q_mine[j * KF_THREADS] = v;
+  }
+
+  // ---- base reference point = position after the leading prismatic run; its cell bc ----
+  double pref[3] = {rb.root_off[0], rb.root_off[1], rb.root_off[2]};
+  for (int sg = 0; sg <= rb.ref_seg; ++sg) {
+    const double qv = q_mine[rb.seg_qidx[sg] * KF_THREADS];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) pref[i] += rb.seg_pre[sg][9 + i] + rb.seg_axis[sg][i] * qv;
+  }
+  Frame<double> f;
+  frame_set_translation<double>(f, pref[0], pref[1], pref[2]);
+  if (!sane) pref[0] = pref[1] = pref[2] = 0.0;
+  int bc[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) bc[a] = rn_int(pref[a] - 0.5);
+  // comfortable: the base lies inside the grid, so every sphere centre lies inside the halo-padded fields
+  const bool comfy = sane && unsigned(bc[0]) < unsigned(gd.gx) && unsigned(bc[1]) < unsigned(gd.gy) && unsigned(bc[2]) < unsigned(gd.gz);
+  const bool forced = sane && !comfy;   // every sphere goes through the reach test + exact scan
+  const unsigned sx = gd.sx, splane = gd.splane;
+  // linear offset of a cell from the raw bits of its three magic sums (all arithmetic mod 2^32; padded cells < 2^32)
+  const unsigned base_off = comfy ? gd.org_off + unsigned(bc[2]) * splane + unsigned(bc[1]) * sx + unsigned(bc[0]) -
+                                        KF_MAGIC_BITS * (splane + sx + 1u)
+                                  : gd.org_off - KF_MAGIC_BITS * (splane + sx + 1u);
+  const double bcd[3] = {double(bc[0]) + 0.5, double(bc[1]) + 0.5, double(bc[2]) + 0.5};
+
+  __syncthreads();   // slot table staged
+
+  bool hit = false;
+  int qcount = 0;  // warp-uniform
+  for (int sg = rb.ref_seg + 1; sg < rb.n_seg; ++sg) {
+    frame_advance_smem<double>(f, rb, sg, q_mine, KF_THREADS);
+    const int b = rb.seg_sph_end[sg + 1], e = rb.seg_sph_end[sg + 2];
+    if (b == e) continue;
+    // the group's frame rounded once to fp32, translation relative to the centre of the base's cell
+    float R[9], pm[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = float(f.r[k]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pm[k] = float(f.p[k] - bcd[k]);
+    if (SELF) {
+      const int fi = rb.grp_fidx[sg + 1];
+      if (fi >= 0) {
+        float *dst = f_mine + fi * 12 * KF_THREADS;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) dst[k * KF_THREADS] = R[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) dst[(9 + k) * KF_THREADS] = pm[k];
+      }
+    }
+    if (!comfy) {   // keep the gathers of a lane that does not use them inside the field: every centre -> cell (0,0,0)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) R[k] = 0.0f;
+      pm[0] = pm[1] = pm[2] = 0.0f;
+    }
+    const uint8_t *__restrict__ lbp = gd.lb2_base;
+    for (int i0 = b; i0 < e; i0 += 8) {
+      const bool two = i0 + 4 < e;   // warp-uniform: slots come in multiples of 4
+      int lbv[8], thr[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        lbv[u] = 255;
+        thr[u] = -2;
+        if (u < 4 || two) {
+          const float4 a = slots4[2 * (i0 + u)];
+          const float cx = fmaf(R[0], a.x, fmaf(R[1], a.y, fmaf(R[2], a.z, pm[0])));
+          const float cy = fmaf(R[3], a.x, fmaf(R[4], a.y, fmaf(R[5], a.z, pm[1])));
+          const float cz = fmaf(R[6], a.x, fmaf(R[7], a.y, fmaf(R[8], a.z, pm[2])));
+          const unsigned bx = __float_as_uint(cx + KF_MAGIC), by = __float_as_uint(cy + KF_MAGIC), bz = __float_as_uint(cz + KF_MAGIC);
+          const unsigned off = bz * splane + by * sx + bx + base_off;
+          lbv[u] = int(lbp[off]);
+          thr[u] = __float_as_int(a.w);
+        }
+      }
+      unsigned pend = 0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (forced ? thr[u] >= 0 : lbv[u] <= thr[u]) pend |= 1u << u;
+      if (hit || !sane) pend = 0;
+      while (__any_sync(FULL, pend != 0)) {
+        bool amb = false;
+        int i = i0;
+        double cx64 = 0.0, cy64 = 0.0, cz64 = 0.0, rg64 = 0.0;
+        auto centre64 = [&]() {   // the fp64 centre exactly as K1 forms it
+          const double2 *lp = reinterpret_cast<const double2 *>(fd.sph64 + i);
+          const double2 l01 = __ldg(lp), l23 = __ldg(lp + 1);
+          const struct { double x, y, z, w; } l = {l01.x, l01.y, l23.x, l23.y};
+          cx64 = fma(f.r[0], l.x, fma(f.r[1], l.y, fma(f.r[2], l.z, f.p[0] - 0.5))) + 0.5;
+          cy64 = fma(f.r[3], l.x, fma(f.r[4], l.y, fma(f.r[5], l.z, f.p[1] - 0.5))) + 0.5;
+          cz64 = fma(f.r[6], l.x, fma(f.r[7], l.y, fma(f.r[8], l.z, f.p[2] - 0.5))) + 0.5;
+          rg64 = l.w;
+        };
+        if (pend != 0) {
+          const int u = __ffs(pend) - 1;
+          pend &= pend - 1;
+          i = i0 + u;
+          if (comfy) {
+            const float4 a = slots4[2 * i];
+            const float r2lo = reinterpret_cast<const float *>(slots4)[8 * i + 4];
+            const float cx = fmaf(R[0], a.x, fmaf(R[1], a.y, fmaf(R[2], a.z, pm[0])));
+            const float cy = fmaf(R[3], a.x, fmaf(R[4], a.y, fmaf(R[5], a.z, pm[1])));
+            const float cz = fmaf(R[6], a.x, fmaf(R[7], a.y, fmaf(R[8], a.z, pm[2])));
+            const float tx = cx + KF_MAGIC, ty = cy + KF_MAGIC, tz = cz + KF_MAGIC;
+            const unsigned off = __float_as_uint(tz) * splane + __float_as_uint(ty) * sx + __float_as_uint(tx) + base_off;
+            const unsigned v = gd.ft_base[off];
+            // position inside the own cell, in [0,1]: (c - n) is exact, c + 0.5 is the centre estimate
+            const float fx = (cx - (tx - KF_MAGIC)) + 0.5f, fy = (cy - (ty - KF_MAGIC)) + 0.5f, fz = (cz - (tz - KF_MAGIC)) + 0.5f;
+            const float gx_ = kf_gap(int(v & 31u) - 15, fx), gy_ = kf_gap(int((v >> 5) & 31u) - 15, fy),
+                        gz_ = kf_gap(int((v >> 10) & 31u) - 15, fz);
+            const float ub2 = fmaf(gx_, gx_, fmaf(gy_, gy_, gz_ * gz_));
+            if (ub2 <= r2lo) { hit = true; pend = 0; }   // dist(fp64 centre, O*) <= rg: certain hit
+            else amb = true;
+          } else {   // base outside the grid: can the sphere still reach it?
+            centre64();
+            const int pad = reinterpret_cast<const int *>(slots4)[8 * i + 5];
+            const int jx = rn_int(cx64 - 0.5), jy = rn_int(cy64 - 0.5), jz = rn_int(cz64 - 0.5);
+            amb = unsigned(jx + pad) < unsigned(gd.gx + 2 * pad) && unsigned(jy + pad) < unsigned(gd.gy + 2 * pad) &&
+                  unsigned(jz + pad) < unsigned(gd.gz + 2 * pad);
+          }
+        }
+        const unsigned m = __ballot_sync(FULL, amb);
+        if (m) {
+          if (amb) {
+            if (comfy) centre64();
+            const int pos = qcount + __popc(m & ((1u << lane) - 1u));
+            wq->x[pos] = cx64;
+            wq->y[pos] = cy64;
+            wq->z[pos] = cz64;
+            wq->r[pos] = rg64;
+            wq->info[pos] = (i << 8) | lane;
+          }
+          qcount += __popc(m);
+          if (qcount >= 32) {
+            __syncwarp();
+            const unsigned hm = drain_queue(gd, wq, qcount - 32, 32, __ballot_sync(FULL, hit));
+            __syncwarp();
+            qcount -= 32;
+            if ((hm >> lane) & 1u) { hit = true; pend = 0; }
+          }
+        }
+      }
+    }
+    // whole warp decided (CC:114-115: map before self, first hit wins) -> stop walking the chain
+    if (!SELF && qcount == 0 && __all_sync(FULL, hit)) break;
+  }
+  if (qcount > 0) {
+    __syncwarp();
+    const unsigned hm = drain_queue(gd, wq, 0, qcount, __ballot_sync(FULL, hit));
+    hit |= (hm >> lane) & 1u;
+  }
+
+  if (SELF && !hit) hit = rb.self_const_collision || self_collision(self, rb, f_mine, KF_THREADS);
+
+  const unsigned word = __ballot_sync(FULL, hit && active);
+  if (lane == 0 && s < ((S + 31) & ~int64_t(31))) mask_out[s >> 5] = word;
+}
+
+cudaError_t launch_check_states_fast(const RobotDev &rb, const GridDev &gd, const SelfDev &self, const FastDev &fd,
+                                     const double *d_q, const double *d_q_end, int num_points, int64_t S,
+                                     unsigned flags, uint32_t *d_mask, cudaStream_t st, int *n_launch) {
+  const bool with_self = (flags & SQMP_CHECK_SELF) != 0;
+  size_t smem = sizeof(WarpQueue) * (KF_THREADS / 32) + sizeof(double) * SQMP_DOF * KF_THREADS + sizeof(FastSlot) * fd.n_slots;
+  if (with_self) smem += size_t(12) * rb.n_frames * KF_THREADS * sizeof(float);
+  const int64_t blocks = (S + KF_THREADS - 1) / KF_THREADS;
+  if (blocks <= 0) return cudaSuccess;
+  if (blocks > 0x7fffffff) return cudaErrorInvalidValue;
+  auto go = [&](auto kern) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    kern<<<unsigned(blocks), KF_THREADS, smem, st>>>(rb, gd, self, fd, d_q, d_q_end, d_q_end ? num_points : 0, S, d_mask);
+  };
+  if (d_q_end) {
+    if (with_self) go(k1_fast<true, true>);
+    else go(k1_fast<true, false>);
+  } else {
+    if (with_self) go(k1_fast<false, true>);
+    else go(k1_fast<false, false>);
+  }
+  if (n_launch) *n_launch += 1;
+  return cudaGetLastError();
+}
+
+}  // namespace sqmp
