@@ -14,7 +14,7 @@ import numpy as np
 from . import robot_desc as rd
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsqmp_b200.so")
+LIB_PATH = os.environ.get("SQMP_B200_LIB") or os.path.join(_HERE, "libsqmp_b200.so")   # override: kernel A/B builds (tools/)
 
 DOF = 8
 CHECK_SELF, CHECK_MAP = 1, 2

@@ -70,6 +70,42 @@ __device__ __forceinline__ bool scan_rows(const GridDev &g, double ux, double uy
   return false;
 }
 
+// Same rows, decided by a CONSERVATIVE fp32 filter in coordinates relative to the sphere's own cell (all magnitudes
+// <= ~15, one float ulp <= 1e-6 cell): per row the admissible x-interval is computed from an inflated radius and an
+// inflated half-width, so it is a superset of the exact one; a row whose superset window holds no occupied bit is
+// free — the common case, because the spheres that reach this stage are mostly free-but-close.  Only a row with a
+// bit in its window is re-decided by the fp64 code above, so the verdict is the fp64 verdict, bit for bit.
+// Cost per row: ~14 fp32/integer instructions and one (rarely two) word loads, against ~27 fp64 + sqrt.f64.
+__device__ __forceinline__ bool scan_rows_filtered(const GridDev &g, double ux, double uy, double uz, double rg, int j0,
+                                                   int nj, int k, int jj, int count) {
+  const int cx = __double2int_rd(ux), cy = __double2int_rd(uy), cz = __double2int_rd(uz);
+  const float fx = float(ux - double(cx)), fy = float(uy - double(cy)), fz = float(uz - double(cz));   // in [0,1]
+  const float rf = float(rg);
+  const float r2 = fmaf(rf * rf, 1.00002f, 2e-5f);   // >= rg^2 + every rounding error below (rg <= 13 cells)
+  for (int n = 0; n < count; ++n) {
+    const int j = j0 + jj;
+    const int oy = j - cy, oz = k - cz;
+    const float gy = oy > 0 ? float(oy) - fy : (oy < 0 ? fy - float(oy + 1) : 0.0f);
+    const float gz = oz > 0 ? float(oz) - fz : (oz < 0 ? fz - float(oz + 1) : 0.0f);
+    const float rem = fmaf(-gy, gy, fmaf(-gz, gz, r2));
+    if (rem >= 0.0f) {
+      const float w = fmaf(rem, rsqrtf(fmaxf(rem, 1e-12f)), 2e-5f);   // >= sqrt(rem) + slack
+      const int i0 = max(cx + __float2int_ru(fx - w) - 1, 0);
+      const int i1 = min(cx + __float2int_rd(fx + w), g.gx - 1);
+      if (i0 <= i1) {   // window of <= 2 * 14 + 1 bits: one funnel shift over two adjacent words (the row has a pad word)
+        const uint32_t *row = g.occ + (size_t(k) * g.gy + size_t(j)) * g.row_words + (i0 >> 5);
+        const int sh = i0 & 31, width = i1 - i0 + 1;
+        const uint32_t w0 = row[0];
+        const uint32_t w1 = (sh + width > 32) ? row[1] : 0u;
+        const uint32_t bits = __funnelshift_r(w0, w1, sh) & (width >= 32 ? ~0u : ((1u << width) - 1u));
+        if (bits && scan_rows(g, ux, uy, uz, rg, j0, nj, k, jj, 1)) return true;
+      }
+    }
+    if (++jj == nj) { jj = 0; ++k; }
+  }
+  return false;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1
 // ------------------------------------------------------------------------------------------------
@@ -135,7 +171,11 @@ static __device__ __noinline__ unsigned drain_queue(const GridDev &gd, const War
       const double ux = wq->x[base + m], uy = wq->y[base + m], uz = wq->z[base + m], rg = wq->r[base + m];
       const int r0 = (t - ex_m) * K1_CHUNK, r1 = min(r0 + K1_CHUNK, R_m);
       const int kk = r0 / nj_m;
+#ifdef SQMP_SCAN_UNFILTERED   // A/B builds only (tools/build_variant.sh): the fp64 scan without the fp32 row filter
       if (scan_rows(gd, ux, uy, uz, rg, j0_m, nj_m, k0_m + kk, r0 - kk * nj_m, r1 - r0))
+#else
+      if (scan_rows_filtered(gd, ux, uy, uz, rg, j0_m, nj_m, k0_m + kk, r0 - kk * nj_m, r1 - r0))
+#endif
         hm |= 1u << (wq->info[base + m] & 31);
     }
   }

@@ -25,7 +25,10 @@
 namespace sqmp {
 
 constexpr int KF_THREADS = 128;
-constexpr int KF_MIN_BLOCKS = 5;
+#ifndef KF_MIN_BLOCKS_DEF
+#define KF_MIN_BLOCKS_DEF 5
+#endif
+constexpr int KF_MIN_BLOCKS = KF_MIN_BLOCKS_DEF;
 constexpr float KF_MAGIC = 12582912.0f;          // 1.5 * 2^23: (x + MAGIC) has round-to-nearest-even(x) in its low mantissa bits
 constexpr unsigned KF_MAGIC_BITS = 0x4B400000u;  // bit pattern of MAGIC
 
