@@ -698,7 +698,8 @@ int sqmp_set_voxel_grid(sqmp_ctx *ctx, const uint32_t *bits, int gx, int gy, int
   if (e == cudaSuccess) e = cudaMalloc(&d_occ, occ_words * 4);
   if (e == cudaSuccess) e = cudaMalloc(&d_a, size_t(pvox));
   if (e == cudaSuccess) e = cudaMalloc(&d_b, size_t(pvox) * 2);
-  if (e == cudaSuccess) e = cudaMalloc(&d_lb2, size_t(pvox));
+  if (e == cudaSuccess) e = cudaMalloc(&d_lb2, size_t(pvox) + 16);   // + a zero byte at [pvox] (GridDev::zero_off)
+  if (e == cudaSuccess) e = cudaMemset(d_lb2 + pvox, 0, 16);
   if (e == cudaSuccess) e = cudaMalloc(&d_ft, size_t(pvox) * 2);
   if (e == cudaSuccess) e = launch_pack_rows(d_lin, gx, gy, gz, row_words, d_occ, nullptr);
   int nl = 1;
@@ -723,6 +724,7 @@ int sqmp_set_voxel_grid(sqmp_ctx *ctx, const uint32_t *bits, int gx, int gy, int
   g.splane = unsigned(PX * PY);
   g.org_off = unsigned((int64_t(halo) * PY + halo) * PX + halo);
   g.halo = halo;
+  g.zero_off = unsigned(pvox);
   g.occ = d_occ; g.lb2_base = d_lb2; g.ft_base = d_ft;
   g.lb2 = d_lb2 + g.org_off; g.ft = d_ft + g.org_off;
   g.gx = gx; g.gy = gy; g.gz = gz; g.row_words = row_words;

@@ -75,33 +75,64 @@ __device__ __forceinline__ bool scan_rows(const GridDev &g, double ux, double uy
 // inflated half-width, so it is a superset of the exact one; a row whose superset window holds no occupied bit is
 // free — the common case, because the spheres that reach this stage are mostly free-but-close.  Only a row with a
 // bit in its window is re-decided by the fp64 code above, so the verdict is the fp64 verdict, bit for bit.
-// Cost per row: ~14 fp32/integer instructions and one (rarely two) word loads, against ~27 fp64 + sqrt.f64.
+// The NR rows of a chunk are handled together: all windows first, then all word loads back to back (one memory
+// round trip per chunk instead of one per row), then the tests.  ~30 fp32/integer instructions per row.
+template <int NR>
 __device__ __forceinline__ bool scan_rows_filtered(const GridDev &g, double ux, double uy, double uz, double rg, int j0,
                                                    int nj, int k, int jj, int count) {
   const int cx = __double2int_rd(ux), cy = __double2int_rd(uy), cz = __double2int_rd(uz);
   const float fx = float(ux - double(cx)), fy = float(uy - double(cy)), fz = float(uz - double(cz));   // in [0,1]
+  const float fy1 = fy - 1.0f, fz1 = fz - 1.0f;
   const float rf = float(rg);
   const float r2 = fmaf(rf * rf, 1.00002f, 2e-5f);   // >= rg^2 + every rounding error below (rg <= 13 cells)
-  for (int n = 0; n < count; ++n) {
-    const int j = j0 + jj;
-    const int oy = j - cy, oz = k - cz;
-    const float gy = oy > 0 ? float(oy) - fy : (oy < 0 ? fy - float(oy + 1) : 0.0f);
-    const float gz = oz > 0 ? float(oz) - fz : (oz < 0 ? fz - float(oz + 1) : 0.0f);
-    const float rem = fmaf(-gy, gy, fmaf(-gz, gz, r2));
-    if (rem >= 0.0f) {
-      const float w = fmaf(rem, rsqrtf(fmaxf(rem, 1e-12f)), 2e-5f);   // >= sqrt(rem) + slack
-      const int i0 = max(cx + __float2int_ru(fx - w) - 1, 0);
-      const int i1 = min(cx + __float2int_rd(fx + w), g.gx - 1);
-      if (i0 <= i1) {   // window of <= 2 * 14 + 1 bits: one funnel shift over two adjacent words (the row has a pad word)
-        const uint32_t *row = g.occ + (size_t(k) * g.gy + size_t(j)) * g.row_words + (i0 >> 5);
-        const int sh = i0 & 31, width = i1 - i0 + 1;
-        const uint32_t w0 = row[0];
-        const uint32_t w1 = (sh + width > 32) ? row[1] : 0u;
-        const uint32_t bits = __funnelshift_r(w0, w1, sh) & (width >= 32 ? ~0u : ((1u << width) - 1u));
-        if (bits && scan_rows(g, ux, uy, uz, rg, j0, nj, k, jj, 1)) return true;
+  const unsigned rw = unsigned(g.row_words);
+  uint32_t w0[NR], w1[NR], msk[NR];
+  int shv[NR];
+  int kq = k, jq = jj;
+  float oyf = float(j0 + jj - cy), ozf = float(k - cz);   // row offsets from the own cell, stepped in float
+  unsigned ridx = (unsigned(k) * unsigned(g.gy) + unsigned(j0 + jj)) * rw;   // occ words < 2^32 (host)
+#pragma unroll
+  for (int n = 0; n < NR; ++n) {
+    w0[n] = w1[n] = msk[n] = 0u;
+    shv[n] = 0;
+    if (n < count) {
+      // gap between f in [0,1] and the unit cube at offset o: max(o - f, (f - 1) - o, 0)
+      const float gy = fmaxf(fmaxf(oyf - fy, fy1 - oyf), 0.0f);
+      const float gz = fmaxf(fmaxf(ozf - fz, fz1 - ozf), 0.0f);
+      const float rem = fmaf(-gy, gy, fmaf(-gz, gz, r2));
+      if (rem >= 0.0f) {
+        const float w = fmaf(rem, rsqrtf(fmaxf(rem, 1e-12f)), 2e-5f);   // >= sqrt(rem) + slack
+        const int i0 = max(cx + __float2int_ru(fx - w) - 1, 0);
+        const int i1 = min(cx + __float2int_rd(fx + w), g.gx - 1);
+        if (i0 <= i1) {   // window of <= 2 * 14 + 1 bits: two adjacent words (the row has a pad word), one funnel shift
+          const uint32_t *p = g.occ + (ridx + unsigned(i0 >> 5));
+          const int sh = i0 & 31, width = i1 - i0 + 1;
+          w0[n] = p[0];
+          if (sh + width > 32) w1[n] = p[1];
+          shv[n] = sh;
+          msk[n] = width >= 32 ? ~0u : ((1u << width) - 1u);
+        }
+      }
+      ridx += rw;
+      oyf += 1.0f;
+      if (++jq == nj) {   // next slab of the scan box
+        jq = 0;
+        ++kq;
+        ozf += 1.0f;
+        oyf = float(j0 - cy);
+        ridx = (unsigned(kq) * unsigned(g.gy) + unsigned(j0)) * rw;
       }
     }
-    if (++jj == nj) { jj = 0; ++k; }
+  }
+  unsigned any = 0;
+#pragma unroll
+  for (int n = 0; n < NR; ++n)
+    if (__funnelshift_r(w0[n], w1[n], shv[n]) & msk[n]) any |= 1u << n;
+  while (any) {   // rare: decide the flagged rows exactly
+    const int n = __ffs(any) - 1;
+    any &= any - 1;
+    const int lin = jj + n, dk = lin / nj;
+    if (scan_rows(g, ux, uy, uz, rg, j0, nj, k + dk, lin - dk * nj, 1)) return true;
   }
   return false;
 }
@@ -111,7 +142,7 @@ __device__ __forceinline__ bool scan_rows_filtered(const GridDev &g, double ux, 
 // ------------------------------------------------------------------------------------------------
 constexpr int K1_THREADS = 128;
 constexpr int K1_QCAP = 64;       // deferred exact-scan items per warp (drained 32 at a time)
-constexpr int K1_CHUNK = 12;      // rows of an exact scan handed to one lane at a time
+constexpr int K1_CHUNK = 4;       // rows of an exact scan handed to one lane at a time (their loads are issued together)
 constexpr int K1_BATCH = 4;       // spheres whose field gathers are in flight together
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -174,7 +205,7 @@ static __device__ __noinline__ unsigned drain_queue(const GridDev &gd, const War
 #ifdef SQMP_SCAN_UNFILTERED   // A/B builds only (tools/build_variant.sh): the fp64 scan without the fp32 row filter
       if (scan_rows(gd, ux, uy, uz, rg, j0_m, nj_m, k0_m + kk, r0 - kk * nj_m, r1 - r0))
 #else
-      if (scan_rows_filtered(gd, ux, uy, uz, rg, j0_m, nj_m, k0_m + kk, r0 - kk * nj_m, r1 - r0))
+      if (scan_rows_filtered<K1_CHUNK>(gd, ux, uy, uz, rg, j0_m, nj_m, k0_m + kk, r0 - kk * nj_m, r1 - r0))
 #endif
         hm |= 1u << (wq->info[base + m] & 31);
     }

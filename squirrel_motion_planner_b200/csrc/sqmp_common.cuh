@@ -69,6 +69,7 @@ struct GridDev {
   const uint8_t *lb2_base;
   const uint16_t *ft_base;
   unsigned sx, splane, org_off;
+  unsigned zero_off;     // lb2_base[zero_off] == 0: where the fast kernel points the gathers of lanes that must not be pruned
   int halo;
   int gx, gy, gz, row_words;
   int has_grid;

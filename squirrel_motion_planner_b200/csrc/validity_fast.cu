@@ -101,12 +101,11 @@ k1_fast(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd,
   for (int a = 0; a < 3; ++a) bc[a] = rn_int(pref[a] - 0.5);
   // comfortable: the base lies inside the grid, so every sphere centre lies inside the halo-padded fields
   const bool comfy = sane && unsigned(bc[0]) < unsigned(gd.gx) && unsigned(bc[1]) < unsigned(gd.gy) && unsigned(bc[2]) < unsigned(gd.gz);
-  const bool forced = sane && !comfy;   // every sphere goes through the reach test + exact scan
   const unsigned sx = gd.sx, splane = gd.splane;
   // linear offset of a cell from the raw bits of its three magic sums (all arithmetic mod 2^32; padded cells < 2^32)
   const unsigned base_off = comfy ? gd.org_off + unsigned(bc[2]) * splane + unsigned(bc[1]) * sx + unsigned(bc[0]) -
                                         KF_MAGIC_BITS * (splane + sx + 1u)
-                                  : gd.org_off - KF_MAGIC_BITS * (splane + sx + 1u);
+                                  : gd.zero_off - KF_MAGIC_BITS * (splane + sx + 1u);   // frame zeroed below: every gather reads the zero byte
   const double bcd[3] = {double(bc[0]) + 0.5, double(bc[1]) + 0.5, double(bc[2]) + 0.5};
 
   __syncthreads();   // slot table staged
@@ -133,7 +132,7 @@ k1_fast(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd,
         for (int k = 0; k < 3; ++k) dst[(9 + k) * KF_THREADS] = pm[k];
       }
     }
-    if (!comfy) {   // keep the gathers of a lane that does not use them inside the field: every centre -> cell (0,0,0)
+    if (!comfy) {   // every centre -> offset 0 -> the zero byte: lb2 = 0 <= thr keeps every enabled sphere pending
 #pragma unroll
       for (int k = 0; k < 9; ++k) R[k] = 0.0f;
       pm[0] = pm[1] = pm[2] = 0.0f;
@@ -145,7 +144,7 @@ k1_fast(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd,
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         lbv[u] = 255;
-        thr[u] = -2;
+        thr[u] = -2;   // absent slot / pad / disabled link: never pending
         if (u < 4 || two) {
           const float4 a = slots4[2 * (i0 + u)];
           const float cx = fmaf(R[0], a.x, fmaf(R[1], a.y, fmaf(R[2], a.z, pm[0])));
@@ -160,7 +159,7 @@ k1_fast(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd,
       unsigned pend = 0;
 #pragma unroll
       for (int u = 0; u < 8; ++u)
-        if (forced ? thr[u] >= 0 : lbv[u] <= thr[u]) pend |= 1u << u;
+        if (lbv[u] <= thr[u]) pend |= 1u << u;
       if (hit || !sane) pend = 0;
       while (__any_sync(FULL, pend != 0)) {
         bool amb = false;

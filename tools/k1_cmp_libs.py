@@ -11,7 +11,8 @@ if len(sys.argv) == 3:
             print(r.stderr); sys.exit(1)
         outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
     same = all(outs[0][k] == outs[1][k] for k in outs[0])
-    print(json.dumps({"equal": same, "a": outs[0], "b": outs[1]}))
+    diff = {k: (outs[0][k], outs[1][k]) for k in outs[0] if outs[0][k] != outs[1][k]}
+    print(json.dumps({"equal": same, "n_keys": len(outs[0]), "diff": diff}))
     sys.exit(0 if same else 2)
 sys.path.insert(0, ROOT)
 import hashlib
