@@ -38,7 +38,8 @@ struct Ctx {
   uint8_t *d_lb2 = nullptr;     // halo-padded (GridDev)
   uint16_t *d_ft = nullptr;
   FastDev fast;                 // tables of the fast validity kernel (validity_fast.cu)
-  FastSlot *d_fast_slots = nullptr;
+  FastPair *d_fast_pairs = nullptr;
+  FastAux *d_fast_aux = nullptr;
   double4 *d_fast_sph64 = nullptr;
   int fast_chain_ok = 0;        // description: translation-only base, then rotations only, spheres on the rotating part
   double reach_m = 0.0;         // max distance of a sphere centre from the base reference point (metres)
@@ -189,29 +190,33 @@ static int refresh_grid_robot(Ctx *c) {
     if (has && c->fast_chain_ok && c->gd.halo > 0) {
       const double reach_c = c->reach_m * inv + 1.0;
       const double err = std::sqrt(3.0) * std::ldexp(26.0 * (reach_c + 1.0), -24) + 1e-6;
-      std::vector<FastSlot> fs(size_t(n_slots) + 1);
+      std::vector<FastPair> fp(size_t(n_slots) / 2 + 1);
+      std::vector<FastAux> fa(size_t(n_slots) + 1);
       std::vector<double4> s64(size_t(n_slots) + 1);
       for (int sl = 0; sl < n_slots; ++sl) {
         const double rg = g.sph[sl][3];
-        FastSlot &f = fs[sl];
-        f.x = float(g.sph[sl][0]); f.y = float(g.sph[sl][1]); f.z = float(g.sph[sl][2]);
+        FastPair &f = fp[sl >> 1];
+        const int h = sl & 1;
+        f.x[h] = float(g.sph[sl][0]); f.y[h] = float(g.sph[sl][1]); f.z[h] = float(g.sph[sl][2]);
         const double t = std::floor((rg + err) * (rg + err) + 1e-9);
-        f.thr = g.sph_thr[sl] < 0 ? -2 : int(t > 254.0 ? 254.0 : t);
+        f.thr[h] = g.sph_thr[sl] < 0 ? -2 : int(t > 254.0 ? 254.0 : t);
         const double lo = rg > err ? (rg - err) * (rg - err) * (1.0 - 1e-6) : -1.0;
         float lof = float(lo);
         if (double(lof) > lo) lof = std::nextafterf(lof, -INFINITY);
-        f.r2_lo = lof;
-        f.ncell = int(g.sph_ncell[sl]) + 1;
-        f.pad0 = f.pad1 = 0.0f;
+        fa[sl].r2_lo = lof;
+        fa[sl].ncell = int(g.sph_ncell[sl]) + 1;
         s64[sl] = make_double4(g.sph[sl][0], g.sph[sl][1], g.sph[sl][2], rg);
       }
       cudaError_t e = cudaSuccess;
-      if (!c->d_fast_slots) e = cudaMalloc(&c->d_fast_slots, sizeof(FastSlot) * (SQMP_MAX_SLOTS + 1));
+      if (!c->d_fast_pairs) e = cudaMalloc(&c->d_fast_pairs, sizeof(FastPair) * (SQMP_MAX_SLOTS / 2 + 1));
+      if (e == cudaSuccess && !c->d_fast_aux) e = cudaMalloc(&c->d_fast_aux, sizeof(FastAux) * (SQMP_MAX_SLOTS + 1));
       if (e == cudaSuccess && !c->d_fast_sph64) e = cudaMalloc(&c->d_fast_sph64, sizeof(double4) * (SQMP_MAX_SLOTS + 1));
-      if (e == cudaSuccess) e = cudaMemcpy(c->d_fast_slots, fs.data(), sizeof(FastSlot) * n_slots, cudaMemcpyHostToDevice);
+      if (e == cudaSuccess) e = cudaMemcpy(c->d_fast_pairs, fp.data(), sizeof(FastPair) * (n_slots / 2), cudaMemcpyHostToDevice);
+      if (e == cudaSuccess) e = cudaMemcpy(c->d_fast_aux, fa.data(), sizeof(FastAux) * n_slots, cudaMemcpyHostToDevice);
       if (e == cudaSuccess) e = cudaMemcpy(c->d_fast_sph64, s64.data(), sizeof(double4) * n_slots, cudaMemcpyHostToDevice);
       if (e != cudaSuccess) return fail(c, SQMP_ERR_CUDA, "fast validity tables", e);
-      c->fast.slots = c->d_fast_slots;
+      c->fast.pairs = c->d_fast_pairs;
+      c->fast.aux = c->d_fast_aux;
       c->fast.sph64 = c->d_fast_sph64;
       c->fast.n_slots = n_slots;
       c->fast.ok = 1;
@@ -600,7 +605,8 @@ void sqmp_destroy(sqmp_ctx *ctx) {
   if (ctx->d_occ) cudaFree(ctx->d_occ);
   if (ctx->d_lb2) cudaFree(ctx->d_lb2);
   if (ctx->d_ft) cudaFree(ctx->d_ft);
-  if (ctx->d_fast_slots) cudaFree(ctx->d_fast_slots);
+  if (ctx->d_fast_pairs) cudaFree(ctx->d_fast_pairs);
+  if (ctx->d_fast_aux) cudaFree(ctx->d_fast_aux);
   if (ctx->d_fast_sph64) cudaFree(ctx->d_fast_sph64);
   for (auto &t : ctx->trees) {
     if (t.q[0]) cudaFree(t.q[0]);

@@ -77,15 +77,17 @@ struct GridDev {
 };
 
 // Tables of the fast validity kernel (validity_fast.cu), in global memory; rebuilt with the grid-unit robot.
-struct FastSlot {      // 32 bytes per slot, staged in shared memory by every CTA
-  float x, y, z;       // sphere centre in its group frame, grid units, fp32
-  int thr;             // stage-1 threshold: lb2 > thr proves the sphere free even after the fp32 centre error; -2: never test
+struct FastPair {      // two consecutive slots (slots come in multiples of 4), laid out for packed fp32x2 arithmetic;
+  float x[2], y[2], z[2];   // sphere centres in their group frame, grid units, fp32
+  int thr[2];          // stage-1 threshold: lb2 > thr proves the sphere free even after the fp32 centre error; -2: never test
+};
+struct FastAux {       // per slot, rare path
   float r2_lo;         // (rg - err)^2 rounded down: ub2 <= r2_lo proves a hit even after the fp32 centre error
   int ncell;           // ceil(rg) + 1 (reach test of a sphere whose state lies outside the comfortable region)
-  float pad0, pad1;
 };
 struct FastDev {
-  const FastSlot *slots;     // [n_slots]
+  const FastPair *pairs;     // [n_slots / 2], staged in shared memory by every CTA
+  const FastAux *aux;        // [n_slots], staged too
   const double4 *sph64;      // [n_slots]: x y z r, grid units, fp64 (exact stage)
   int n_slots;
   int ok;                    // the description and the grid satisfy the fast kernel's preconditions

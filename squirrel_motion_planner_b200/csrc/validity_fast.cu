@@ -32,6 +32,24 @@ constexpr int KF_MIN_BLOCKS = KF_MIN_BLOCKS_DEF;
 constexpr float KF_MAGIC = 12582912.0f;          // 1.5 * 2^23: (x + MAGIC) has round-to-nearest-even(x) in its low mantissa bits
 constexpr unsigned KF_MAGIC_BITS = 0x4B400000u;  // bit pattern of MAGIC
 
+// packed fp32x2 (sm_100 FFMA2 / FADD2): two spheres per instruction; a plain float operand is broadcast (R.F32)
+__device__ __forceinline__ float2 kf_fma2(float a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %2};\n\tmov.b64 rb, {%3, %4};\n\tmov.b64 rc, {%5, %6};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 kf_add2(float2 a, float b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %4};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b));
+  return d;
+}
+
 __device__ __forceinline__ float kf_gap(int o, float f) {   // gap between coordinate f in [0,1] of the own cell and the unit cube at offset o
   return o > 0 ? float(o) - f : (o < 0 ? f - float(o) - 1.0f : 0.0f);
 }
@@ -45,16 +63,21 @@ k1_fast(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd,
   WarpQueue *wq = reinterpret_cast<WarpQueue *>(smem_raw) + (threadIdx.x >> 5);
   double *q_mine = reinterpret_cast<double *>(smem_raw + sizeof(WarpQueue) * (KF_THREADS / 32)) + threadIdx.x;  // [8][blockDim]
   float4 *slots4 = reinterpret_cast<float4 *>(smem_raw + sizeof(WarpQueue) * (KF_THREADS / 32) + sizeof(double) * SQMP_DOF * KF_THREADS);
-  float *f_mine = reinterpret_cast<float *>(slots4 + 2 * fd.n_slots) + threadIdx.x;   // SELF: [n_frames*12][blockDim]
+  // slots4: [n_slots / 2] FastPair (2 x float4 each), then [n_slots] FastAux (8 bytes each)
+  const FastAux *aux_s = reinterpret_cast<const FastAux *>(slots4 + fd.n_slots);
+  float *f_mine = reinterpret_cast<float *>(slots4 + fd.n_slots + (fd.n_slots + 1) / 2) + threadIdx.x;   // SELF: [n_frames*12][blockDim]
   const int lane = threadIdx.x & 31;
   const int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool active = s < S;
   const int64_t sl = active ? s : S - 1;  // idle lanes of the last warp shadow the last state (lockstep loops)
 
-  // ---- slot table -> shared memory (2 x 16 bytes per slot) ----
+  // ---- slot tables -> shared memory (16 + 8 bytes per slot) ----
   {
-    const float4 *src = reinterpret_cast<const float4 *>(fd.slots);
-    for (int i = threadIdx.x; i < 2 * fd.n_slots; i += KF_THREADS) slots4[i] = __ldg(src + i);
+    const float4 *src = reinterpret_cast<const float4 *>(fd.pairs);
+    for (int i = threadIdx.x; i < fd.n_slots; i += KF_THREADS) slots4[i] = __ldg(src + i);
+    const float2 *src2 = reinterpret_cast<const float2 *>(fd.aux);
+    float2 *dst2 = reinterpret_cast<float2 *>(slots4 + fd.n_slots);
+    for (int i = threadIdx.x; i < fd.n_slots; i += KF_THREADS) dst2[i] = __ldg(src2 + i);
   }
 
   // ---- the state: either given, or interpolated from the edge end points (BS:4461-4462, 4478; no FMA) ----
@@ -142,18 +165,22 @@ k1_fast(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd,
       const bool two = i0 + 4 < e;   // warp-uniform: slots come in multiples of 4
       int lbv[8], thr[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        lbv[u] = 255;
-        thr[u] = -2;   // absent slot / pad / disabled link: never pending
-        if (u < 4 || two) {
-          const float4 a = slots4[2 * (i0 + u)];
-          const float cx = fmaf(R[0], a.x, fmaf(R[1], a.y, fmaf(R[2], a.z, pm[0])));
-          const float cy = fmaf(R[3], a.x, fmaf(R[4], a.y, fmaf(R[5], a.z, pm[1])));
-          const float cz = fmaf(R[6], a.x, fmaf(R[7], a.y, fmaf(R[8], a.z, pm[2])));
-          const unsigned bx = __float_as_uint(cx + KF_MAGIC), by = __float_as_uint(cy + KF_MAGIC), bz = __float_as_uint(cz + KF_MAGIC);
-          const unsigned off = bz * splane + by * sx + bx + base_off;
-          lbv[u] = int(lbp[off]);
-          thr[u] = __float_as_int(a.w);
+      for (int v = 0; v < 4; ++v) {   // pairs of slots
+        lbv[2 * v] = lbv[2 * v + 1] = 255;
+        thr[2 * v] = thr[2 * v + 1] = -2;   // absent slot / pad / disabled link: never pending
+        if (v < 2 || two) {
+          const float4 A = slots4[i0 + 2 * v], B = slots4[i0 + 2 * v + 1];   // (x0 x1 y0 y1) (z0 z1 thr0 thr1)
+          const float2 X = make_float2(A.x, A.y), Y = make_float2(A.z, A.w), Z = make_float2(B.x, B.y);
+          const float2 cx = kf_fma2(R[0], X, kf_fma2(R[1], Y, kf_fma2(R[2], Z, make_float2(pm[0], pm[0]))));
+          const float2 cy = kf_fma2(R[3], X, kf_fma2(R[4], Y, kf_fma2(R[5], Z, make_float2(pm[1], pm[1]))));
+          const float2 cz = kf_fma2(R[6], X, kf_fma2(R[7], Y, kf_fma2(R[8], Z, make_float2(pm[2], pm[2]))));
+          const float2 tx = kf_add2(cx, KF_MAGIC), ty = kf_add2(cy, KF_MAGIC), tz = kf_add2(cz, KF_MAGIC);
+          const unsigned off0 = __float_as_uint(tz.x) * splane + __float_as_uint(ty.x) * sx + __float_as_uint(tx.x) + base_off;
+          const unsigned off1 = __float_as_uint(tz.y) * splane + __float_as_uint(ty.y) * sx + __float_as_uint(tx.y) + base_off;
+          lbv[2 * v] = int(lbp[off0]);
+          lbv[2 * v + 1] = int(lbp[off1]);
+          thr[2 * v] = __float_as_int(B.z);
+          thr[2 * v + 1] = __float_as_int(B.w);
         }
       }
       unsigned pend = 0;
@@ -179,8 +206,9 @@ k1_fast(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd,
           pend &= pend - 1;
           i = i0 + u;
           if (comfy) {
-            const float4 a = slots4[2 * i];
-            const float r2lo = reinterpret_cast<const float *>(slots4)[8 * i + 4];
+            const float *sp = reinterpret_cast<const float *>(slots4) + 8 * (i >> 1) + (i & 1);
+            const float3 a = make_float3(sp[0], sp[2], sp[4]);
+            const float r2lo = aux_s[i].r2_lo;
             const float cx = fmaf(R[0], a.x, fmaf(R[1], a.y, fmaf(R[2], a.z, pm[0])));
             const float cy = fmaf(R[3], a.x, fmaf(R[4], a.y, fmaf(R[5], a.z, pm[1])));
             const float cz = fmaf(R[6], a.x, fmaf(R[7], a.y, fmaf(R[8], a.z, pm[2])));
@@ -196,7 +224,7 @@ k1_fast(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd,
             else amb = true;
           } else {   // base outside the grid: can the sphere still reach it?
             centre64();
-            const int pad = reinterpret_cast<const int *>(slots4)[8 * i + 5];
+            const int pad = aux_s[i].ncell;
             const int jx = rn_int(cx64 - 0.5), jy = rn_int(cy64 - 0.5), jz = rn_int(cz64 - 0.5);
             amb = unsigned(jx + pad) < unsigned(gd.gx + 2 * pad) && unsigned(jy + pad) < unsigned(gd.gy + 2 * pad) &&
                   unsigned(jz + pad) < unsigned(gd.gz + 2 * pad);
@@ -243,7 +271,8 @@ cudaError_t launch_check_states_fast(const RobotDev &rb, const GridDev &gd, cons
                                      const double *d_q, const double *d_q_end, int num_points, int64_t S,
                                      unsigned flags, uint32_t *d_mask, cudaStream_t st, int *n_launch) {
   const bool with_self = (flags & SQMP_CHECK_SELF) != 0;
-  size_t smem = sizeof(WarpQueue) * (KF_THREADS / 32) + sizeof(double) * SQMP_DOF * KF_THREADS + sizeof(FastSlot) * fd.n_slots;
+  size_t smem = sizeof(WarpQueue) * (KF_THREADS / 32) + sizeof(double) * SQMP_DOF * KF_THREADS +
+                16 * size_t(fd.n_slots + (fd.n_slots + 1) / 2);   // FastPair: 16 B per slot; FastAux: 8 B per slot
   if (with_self) smem += size_t(12) * rb.n_frames * KF_THREADS * sizeof(float);
   const int64_t blocks = (S + KF_THREADS - 1) / KF_THREADS;
   if (blocks <= 0) return cudaSuccess;
