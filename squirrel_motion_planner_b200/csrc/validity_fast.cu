@@ -54,8 +54,10 @@ __device__ __forceinline__ float kf_gap(int o, float f) {   // gap between coord
   return o > 0 ? float(o) - f : (o < 0 ? f - float(o) - 1.0f : 0.0f);
 }
 
+// SELF keeps the group frames and the pair hierarchy live on top of the map state: 128 registers (4 CTAs/SM) avoid
+// the spills that cost it 12 % at 96; the map-only kernel is indifferent between 4 and 5 CTAs/SM (measured).
 template <bool EDGES, bool SELF>
-__global__ void __launch_bounds__(KF_THREADS, KF_MIN_BLOCKS)
+__global__ void __launch_bounds__(KF_THREADS, SELF ? 4 : KF_MIN_BLOCKS)
 k1_fast(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd, const __grid_constant__ SelfDev self,
         const __grid_constant__ FastDev fd, const double *__restrict__ q_in, const double *__restrict__ q_end,
         int num_points, int64_t S, uint32_t *__restrict__ mask_out) {

@@ -140,6 +140,78 @@ def test_real_scene_room3_with_floor_patch(ctx, orc):
     assert 0.02 < got.mean() < 0.98
 
 
+# --------------------------------------------------------------------------------------- the two validity kernels
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("flags", [api.CHECK_MAP, api.CHECK_MAP | api.CHECK_SELF])
+def test_both_validity_kernels_match_oracle(world_ctx, kernel, flags):
+    """k1_kernel = 1: generic fp64 kernel (validity.cu); 2: fast kernel (validity_fast.cu: fp32 proof stages with an
+    error bound on halo-padded fields, fp64 exact stage).  Both must reproduce the oracle with no disagreement."""
+    ctx, orc, w, origin = world_ctx
+    ctx.set_option("k1_kernel", kernel)
+    try:
+        q = syn.state_batch(21 * 500 + 11, seed=41, xy_half=2.2)
+        got, ref, clr, differs = _verdict_parity(ctx, orc, q, flags)
+        assert differs.sum() == 0 and 0.05 < got.mean() < 0.95
+    finally:
+        ctx.set_option("k1_kernel", 0)
+
+
+def test_fast_kernel_is_bit_identical_to_generic_kernel(ctx, orc, fixture_data):
+    """Same masks bit for bit — including states whose base lies outside the grid (the fast kernel's forced lanes),
+    spheres straddling every face of the grid (scan boxes clamped to odd row counts), grids that are not cubes, a
+    disabled-link mask, the edge entry point and the self-collision instantiation."""
+    lt = fixture_data[0]
+    worlds = [
+        (syn.box_world(g=96, n_boxes=20, seed=5, dims=(96, 80, 64)), np.zeros(3), 2.2),
+        (syn.box_world(g=40, n_boxes=10, seed=8, dims=(37, 45, 21), z_low=-0.2), np.array([0.3, -0.2, 0.0]), 1.6),
+        (syn.box_world(g=64, n_boxes=60, seed=77, dims=(33, 64, 70)), np.array([-0.4, 0.1, 0.0]), 1.4),
+    ]
+    try:
+        for w, shift, half in worlds:
+            origin = w.origin + shift + np.array([0.0, 0.0, rd.OCTREE_Z_OFFSET])
+            ctx.set_voxel_grid(w.bits, w.dims, origin, w.res)
+            orc.set_grid(w.bits, w.dims, origin, w.res)
+            for wide in (1.0, 1.7, 3.0):                                   # 1.7, 3.0: many bases outside the grid
+                q = syn.state_batch(21 * 700 + 3, seed=int(10 * wide) + 51, xy_half=half * wide)
+                for mask in (0, rd.link_mask(lt, ["head_link", "base_body_link"])):
+                    ctx.set_disabled_links(mask)
+                    for flags in (api.CHECK_MAP, api.CHECK_MAP | api.CHECK_SELF):
+                        ctx.set_option("k1_kernel", 1)
+                        a = ctx.check_states(q, flags)
+                        ctx.set_option("k1_kernel", 2)
+                        b = ctx.check_states(q, flags)
+                        assert np.array_equal(a, b)
+                ctx.set_disabled_links(0)
+                got = unpack(b, len(q))
+                assert 0.01 < got.mean() < 0.99
+                if wide == 1.7:                                            # and the oracle agrees on the wide batch
+                    orc.set_disabled_links(0)
+                    _verdict_parity(ctx, orc, q[:4000], api.CHECK_MAP)
+            ea, eb = syn.edge_batch(333, seed=61, xy_half=half * 1.5)
+            ctx.set_option("k1_kernel", 1)
+            m1, f1 = ctx.check_edges(ea, eb, 20, api.CHECK_MAP)
+            ctx.set_option("k1_kernel", 2)
+            m2, f2 = ctx.check_edges(ea, eb, 20, api.CHECK_MAP)
+            assert np.array_equal(m1, m2) and np.array_equal(f1, f2)
+    finally:
+        ctx.set_option("k1_kernel", 0)
+        ctx.set_disabled_links(0)
+
+
+def test_fast_kernel_rejected_without_its_preconditions(fixture_data):
+    """k1_kernel = 2 is an error for a description whose base is not a translation-only run (no silent fallback)."""
+    lt, fx, spheres = fixture_data
+    cr = rd.compile_robot(lt, spheres)
+    c2 = api.Context(cr, 0)
+    try:
+        c2.set_option("k1_kernel", 2)                                    # the reference robot qualifies
+        c2.set_option("k1_kernel", 0)
+        with pytest.raises(api.SqmpError):
+            c2.set_option("k1_kernel", 3)
+    finally:
+        c2.close()
+
+
 def test_check_edges_matches_oracle_and_states_entry(world_ctx):
     ctx, orc, w, origin = world_ctx
     a, b = syn.edge_batch(777, seed=31, xy_half=2.2)
