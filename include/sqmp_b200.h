@@ -114,6 +114,17 @@ int sqmp_get_collisions(sqmp_ctx *ctx, const double q[SQMP_DOF], uint8_t *link_m
 /* KDLRobotModel::compute_FK (KM:278-305): S*7 doubles x y z qx qy qz qw of the chain tip. */
 int sqmp_fk(sqmp_ctx *ctx, const double *q, int64_t S, double *ee_pose_out);
 
+/* ---- sampling ----------------------------------------------------------------- */
+/* BiRRTstarPlanner::sampleJointConfig_JntArray (BS:3832-3878) over RobotController::getRandomConf (CL:1120-1188):
+ * every joint uniform in [lo, hi] (the base from the environment size, CL:1153-1166), redrawn until the end-effector of
+ * compute_FK lies above the platform (0.0 <= ee_z, CL:1182-1184 and BS:3870-3871).  The reference draws from a
+ * time-seeded Mersenne twister; here sample i is a pure function of (seed, first + i): try t of sample i uses the
+ * outputs 8 * (i * max_tries + t) + j, j = 0..7, of the splitmix64 stream started at `seed`, so a batch is
+ * reproducible, order-free and identical on the CPU oracle.  q_out: n*8.  tries_out (may be NULL): tries used, or
+ * -max_tries when every try was below the platform (the last try is returned). */
+int sqmp_sample_configs(sqmp_ctx *ctx, uint64_t seed, int64_t first, int64_t n, const double lo[SQMP_DOF],
+                        const double hi[SQMP_DOF], int max_tries, double *q_out, int32_t *tries_out);
+
 /* ---- tree mirror (DS:29-54; mutation sites BS:3298-3322, 5173-5193, 5518-5520) ------------------- */
 /* Invariant kept from the reference: node_id == index.  tree in [0, SQMP_MAX_TREES). */
 int sqmp_tree_reset(sqmp_ctx *ctx, int tree);
@@ -144,6 +155,8 @@ int sqmp_check_states_dev(sqmp_ctx *ctx, const double *d_q, int64_t S, unsigned 
                           void *stream);
 int sqmp_check_edges_dev(sqmp_ctx *ctx, const double *d_q_start, const double *d_q_end, int64_t E, int num_points,
                          unsigned flags, uint32_t *d_mask, int32_t *d_first_invalid, void *stream);
+int sqmp_sample_configs_dev(sqmp_ctx *ctx, uint64_t seed, int64_t first, int64_t n, const double lo[SQMP_DOF],
+                            const double hi[SQMP_DOF], int max_tries, double *d_q_out, int32_t *d_tries_out, void *stream);
 int sqmp_fk_dev(sqmp_ctx *ctx, const double *d_q, int64_t S, double *d_ee_pose, void *stream);
 int sqmp_nn_nearest_dev(sqmp_ctx *ctx, int tree, const double *d_queries, int64_t Q, int32_t *d_id, void *stream);
 /* d_overflow: one int32, set to 1 if some query had more hits than the internal per-query buffer. */

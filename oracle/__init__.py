@@ -136,6 +136,8 @@ def lib():
     L.orc_is_edge_valid.argtypes = [C.c_void_p, dp, C.c_int, C.c_int, C.c_int, ip]
     L.orc_check_edges.argtypes = [C.c_void_p, dp, dp, C.c_int64, C.c_int, C.c_uint, u32p, i32p, C.c_int]
     L.orc_fk.argtypes = [C.c_void_p, C.c_int, dp, C.c_int64, dp]
+    L.orc_sample_configs.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int64, C.c_int64, dp, dp, C.c_int, dp,
+                                     C.POINTER(C.c_int32)]
     L.orc_joint_space_distance.restype = C.c_double
     L.orc_joint_space_distance.argtypes = [dp, dp, C.c_int]
     L.orc_nearest.restype = C.c_int32
@@ -244,6 +246,16 @@ class Oracle:
         out = np.empty((q.shape[0], 7))
         lib().orc_fk(self._h, self.lt.index(tip), _p(q, C.c_double), q.shape[0], _p(out, C.c_double))
         return out
+
+
+    def sample_configs(self, seed, first, n, lo, hi, max_tries=64, tip="hand_wrist_link"):
+        """sampleJointConfig_JntArray (BS:3832-3878): (q[n,8], tries[n])."""
+        lo, hi = _f64(lo), _f64(hi)
+        q = np.empty((n, DOF))
+        tries = np.empty(n, dtype=np.int32)
+        lib().orc_sample_configs(self._h, self.lt.index(tip), int(seed), int(first), int(n), _p(lo, C.c_double),
+                                 _p(hi, C.c_double), int(max_tries), _p(q, C.c_double), _p(tries, C.c_int32))
+        return q, tries
 
 
 # ---- free functions ---------------------------------------------------------

@@ -10,7 +10,10 @@
 // CPU backend over the oracle library: the planner above it is byte-for-byte the same code as on the GPU.
 class OracleBackend {
  public:
-  OracleBackend(orc_model *m, unsigned flags) : m_(m), flags_(flags) {}
+  OracleBackend(orc_model *m, unsigned flags, int tip) : m_(m), flags_(flags), tip_(tip) {}
+  void sample_batch(uint64_t seed, long long first, int n, const double *lo, const double *hi, int max_tries, double *q_out) {
+    orc_sample_configs(m_, tip_, seed, first, n, lo, hi, max_tries, q_out, NULL);
+  }
   void tree_reset(int slot) { nodes_[slot].clear(); cost_[slot].clear(); }
   int tree_append(int slot, const double *q, double cost) {
     nodes_[slot].insert(nodes_[slot].end(), q, q + 8);
@@ -42,11 +45,13 @@ class OracleBackend {
  private:
   orc_model *m_;
   unsigned flags_;
+  int tip_;
   std::vector<double> nodes_[8], cost_[8];
 };
 
-// oracle_model.bin (written by tests / bench): int32 L, n_spheres; then the arrays orc_model_create takes, in order
-static orc_model *load_oracle_model(const std::string &path) {
+// oracle_model.bin (written by tests / bench): int32 L, n_spheres; then the arrays orc_model_create takes, in order;
+// then int32 tip = link index of the FK chain tip (hand_wrist_link, SRDF:4-6)
+static orc_model *load_oracle_model(const std::string &path, int *tip) {
   std::ifstream f(path.c_str(), std::ios::binary);
   if (!f) return NULL;
   int32_t L = 0, n = 0;
@@ -59,7 +64,10 @@ static orc_model *load_oracle_model(const std::string &path) {
   rd(parent.data(), 4 * L); rd(jt.data(), 4 * L); rd(qidx.data(), 4 * L); rd(jo.data(), 24 * L); rd(ja.data(), 24 * L);
   rd(tp.data(), 96 * L); rd(ft.data(), 96 * L); rd(shaped.data(), 4 * L); rd(pair.data(), size_t(L) * L);
   rd(sph_link.data(), 4 * n); rd(sc.data(), 24 * n); rd(sr.data(), 8 * n);
-  if (!f) return NULL;
+  int32_t tip32 = -1;
+  rd(&tip32, 4);
+  if (!f || tip32 < 0 || tip32 >= L) return NULL;
+  *tip = tip32;
   return orc_model_create(L, parent.data(), jt.data(), qidx.data(), jo.data(), ja.data(), tp.data(), ft.data(), shaped.data(),
                           pair.data(), n, sph_link.data(), sc.data(), sr.data());
 }
@@ -71,11 +79,12 @@ int main(int argc, char **argv) {
     std::fprintf(stderr, "unknown backend %s (this binary only has the CPU oracle backend)\n", a.backend.c_str());
     return 2;
   }
-  orc_model *m = load_oracle_model(a.dir + "oracle_model.bin");
+  int tip = -1;
+  orc_model *m = load_oracle_model(a.dir + "oracle_model.bin", &tip);
   if (!m) return 4;
   const double origin[3] = {a.g.origin[0], a.g.origin[1], a.g.origin[2] - 0.02};   // CC:87, as the shim does
   orc_set_grid(m, a.g.bits.data(), a.g.gx, a.g.gy, a.g.gz, origin, a.g.res);
-  OracleBackend be(m, 3u);
+  OracleBackend be(m, 3u, tip);
   const int rc = sqmp_plan_driver::run_queries(be, a.queries, a.iterations, a.seed, a.first, a.count, a.xy_lo, a.xy_hi);
   orc_model_destroy(m);
   return rc;

@@ -459,6 +459,36 @@ void orc_fk(const orc_model *m, int tip, const double *q, int64_t S, double *out
   }
 }
 
+/* ---------------------------------------------------------------- sampling (BS:3832-3878, CL:1120-1188) */
+static uint64_t splitmix_at(uint64_t seed, uint64_t k) {
+  uint64_t z = seed + (k + 1ull) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+void orc_sample_configs(const orc_model *m, int tip, uint64_t seed, int64_t first, int64_t n, const double *lo,
+                        const double *hi, int max_tries, double *q_out, int32_t *tries_out) {
+  for (int64_t i = 0; i < n; ++i) {
+    double *q = q_out + i * ORC_DOF, ee[7];
+    int used = -max_tries;
+    for (int t = 0; t < max_tries; ++t) {   /* while(true) of CL:1130, bounded */
+      const uint64_t k0 = ((uint64_t)(first + i) * (uint64_t)max_tries + (uint64_t)t) * ORC_DOF;
+      for (int j = 0; j < ORC_DOF; ++j) {   /* uniformReal(q_min, q_max) / (env_size[0], env_size[1]), CL:1141-1166 */
+        const double u = (double)(splitmix_at(seed, k0 + (uint64_t)j) >> 11) * (1.0 / 9007199254740992.0);
+        const double span = hi[j] - lo[j];
+        const double step = span * u;
+        q[j] = lo[j] + step;
+      }
+      orc_fk(m, tip, q, 1, ee);
+      if (0.0 <= ee[2]) {   /* CL:1182-1184, BS:3870-3871 */
+        used = t + 1;
+        break;
+      }
+    }
+    if (tries_out) tries_out[i] = used;
+  }
+}
+
 /* ---------------------------------------------------------------- distances and neighbours */
 /* DH:128-156 */
 double orc_joint_space_distance(const double *a, const double *b, int n) {

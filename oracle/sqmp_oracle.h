@@ -88,6 +88,15 @@ void orc_check_edges(const orc_model *m, const double *q_start, const double *q_
 /* compute_FK (KM:278-305): KDL chain solver from the root to link `tip` — x y z qx qy qz qw. */
 void orc_fk(const orc_model *m, int tip, const double *q /*S*8*/, int64_t S, double *out /*S*7*/);
 
+/* sampleJointConfig_JntArray (BS:3832-3878) over getRandomConf (CL:1120-1188): every joint uniform in [lo, hi],
+ * redrawn until 0.0 <= ee_z of compute_FK to link `tip`.  The reference's time-seeded Mersenne twister is replaced by
+ * a counter-based stream so a batch is reproducible: try t of sample i uses outputs 8 * ((first + i) * max_tries + t)
+ * + j of the splitmix64 stream started at `seed` (k-th output = mix(seed + (k + 1) * 0x9E3779B97F4A7C15)), and
+ * q_j = lo_j + (hi_j - lo_j) * (double(out >> 11) * 2^-53) with no fused multiply-add.  tries_out (may be NULL): tries
+ * used, or -max_tries when every try was below the platform (the last try is returned). */
+void orc_sample_configs(const orc_model *m, int tip, uint64_t seed, int64_t first, int64_t n, const double *lo,
+                        const double *hi, int max_tries, double *q_out /*n*8*/, int32_t *tries_out);
+
 /* euclidean_joint_space_distance (DH:128-156). */
 double orc_joint_space_distance(const double *a, const double *b, int n);
 

@@ -25,7 +25,7 @@ EXPORTS = [
     "sqmp_set_disabled_links", "sqmp_check_states", "sqmp_check_edges", "sqmp_get_collisions", "sqmp_fk",
     "sqmp_tree_reset", "sqmp_tree_append", "sqmp_tree_append_batch", "sqmp_tree_update", "sqmp_tree_update_costs",
     "sqmp_tree_size", "sqmp_nn_nearest", "sqmp_nn_radius", "sqmp_check_states_dev", "sqmp_check_edges_dev",
-    "sqmp_fk_dev", "sqmp_nn_nearest_dev", "sqmp_nn_radius_dev", "sqmp_kernel_launches", "sqmp_set_option",
+    "sqmp_fk_dev", "sqmp_sample_configs", "sqmp_sample_configs_dev", "sqmp_nn_nearest_dev", "sqmp_nn_radius_dev", "sqmp_kernel_launches", "sqmp_set_option",
 ]
 
 
@@ -95,6 +95,8 @@ def load_library():
     L.sqmp_check_states_dev.argtypes = [vp, vp, i64, C.c_uint, vp, vp]
     L.sqmp_check_edges_dev.argtypes = [vp, vp, vp, i64, C.c_int, C.c_uint, vp, vp, vp]
     L.sqmp_fk_dev.argtypes = [vp, vp, i64, vp, vp]
+    L.sqmp_sample_configs.argtypes = [vp, C.c_uint64, i64, i64, dp, dp, C.c_int, vp, vp]
+    L.sqmp_sample_configs_dev.argtypes = [vp, C.c_uint64, i64, i64, dp, dp, C.c_int, vp, vp, vp]
     L.sqmp_nn_nearest_dev.argtypes = [vp, C.c_int, vp, i64, vp, vp]
     L.sqmp_nn_radius_dev.argtypes = [vp, C.c_int, vp, vp, i64, C.c_double, C.c_int, vp, vp, vp, vp, vp]
     L.sqmp_kernel_launches.restype = i64
@@ -231,6 +233,25 @@ class Context:
         out = np.empty((q.shape[0], 7), dtype=np.float64)
         self._ck(self._L.sqmp_fk(self._h, _ptr(q), q.shape[0], _ptr(out)))
         return out
+
+    def sample_configs(self, seed, first, n, lo, hi, max_tries=64):
+        """sampleJointConfig_JntArray (BS:3832-3878) batched on the device: (q[n,8], tries[n])."""
+        lo = np.ascontiguousarray(lo, dtype=np.float64).reshape(DOF)
+        hi = np.ascontiguousarray(hi, dtype=np.float64).reshape(DOF)
+        q = np.empty((n, DOF), dtype=np.float64)
+        tries = np.empty(n, dtype=np.int32)
+        dp = C.POINTER(C.c_double)
+        self._ck(self._L.sqmp_sample_configs(self._h, int(seed), int(first), int(n), lo.ctypes.data_as(dp),
+                                             hi.ctypes.data_as(dp), int(max_tries), _ptr(q), _ptr(tries)))
+        return q, tries
+
+    def sample_configs_dev(self, seed, first, n, lo, hi, max_tries, d_q, d_tries, stream=0):
+        lo = np.ascontiguousarray(lo, dtype=np.float64).reshape(DOF)
+        hi = np.ascontiguousarray(hi, dtype=np.float64).reshape(DOF)
+        dp = C.POINTER(C.c_double)
+        self._ck(self._L.sqmp_sample_configs_dev(self._h, int(seed), int(first), int(n), lo.ctypes.data_as(dp),
+                                                 hi.ctypes.data_as(dp), int(max_tries), _ptr(d_q), _ptr(d_tries),
+                                                 C.c_void_p(stream)))
 
     # ---- tree mirror
     def tree_reset(self, tree):

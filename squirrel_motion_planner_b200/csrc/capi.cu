@@ -938,6 +938,40 @@ int sqmp_fk(sqmp_ctx *ctx, const double *q, int64_t S, double *out) {
   return SQMP_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------- sampling
+int sqmp_sample_configs_dev(sqmp_ctx *ctx, uint64_t seed, int64_t first, int64_t n, const double lo[SQMP_DOF],
+                            const double hi[SQMP_DOF], int max_tries, double *d_q_out, int32_t *d_tries_out, void *stream) {
+  CHECK_CTX();
+  if (n < 0 || first < 0 || max_tries < 1 || max_tries > 65536 || !lo || !hi || (n > 0 && !d_q_out))
+    return fail(c, SQMP_ERR_INVALID, "sample_configs: bad argument");
+  for (int j = 0; j < SQMP_DOF; ++j)
+    if (!(lo[j] <= hi[j]) || !std::isfinite(lo[j]) || !std::isfinite(hi[j]))
+      return fail(c, SQMP_ERR_INVALID, "sample_configs: limits must be finite with lo <= hi");
+  if (n == 0) return SQMP_OK;
+  CU(launch_sample(c->rb, seed, first, n, lo, hi, max_tries, d_q_out, d_tries_out, c->chain_specialization != 0,
+                   (cudaStream_t)stream));
+  c->launches += 1;
+  return SQMP_OK;
+}
+
+int sqmp_sample_configs(sqmp_ctx *ctx, uint64_t seed, int64_t first, int64_t n, const double lo[SQMP_DOF],
+                        const double hi[SQMP_DOF], int max_tries, double *q_out, int32_t *tries_out) {
+  CHECK_CTX();
+  if (n > 0 && !q_out) return fail(c, SQMP_ERR_INVALID, "sample_configs: null pointer");
+  if (n <= 0) return n == 0 ? SQMP_OK : fail(c, SQMP_ERR_INVALID, "sample_configs: bad argument");
+  void *dq, *dt;
+  int rc;
+  if ((rc = ensure(c, 0, size_t(n) * SQMP_DOF * 8, &dq))) return rc;
+  if ((rc = ensure(c, 5, size_t(n) * 4, &dt))) return rc;
+  cudaStream_t st = c->streams[0];
+  rc = sqmp_sample_configs_dev(ctx, seed, first, n, lo, hi, max_tries, (double *)dq, (int32_t *)dt, st);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(q_out, dq, size_t(n) * SQMP_DOF * 8, cudaMemcpyDeviceToHost, st));
+  if (tries_out) CU(cudaMemcpyAsync(tries_out, dt, size_t(n) * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return SQMP_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------- tree
 #define CHECK_TREE()                                                                 \
   if (tree < 0 || tree >= SQMP_MAX_TREES) return fail(c, SQMP_ERR_INVALID, "bad tree index"); \

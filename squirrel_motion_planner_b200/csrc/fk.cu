@@ -183,4 +183,62 @@ cudaError_t launch_fk(const RobotDev &rb, const double *d_q, int64_t S, double *
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// K5: batched configuration sampling — sampleJointConfig_JntArray (birrt_star.cpp:3832-3878) over getRandomConf
+// (control_laws.cpp:1120-1188): uniform in the joint / environment limits, redrawn until the end-effector lies above
+// the platform (0.0 <= ee_z).  One thread per sample; the draw is a pure function of (seed, sample index, try, joint)
+// through the splitmix64 stream (k-th output = mix(seed + (k + 1) * GAMMA)), so batches are reproducible and
+// identical to the CPU oracle.  a + (b - a) * u is evaluated with explicit round-to-nearest mul/add (no FMA).
+// ---------------------------------------------------------------------------------------------------------------
+struct SampleBox {
+  double lo[SQMP_DOF], hi[SQMP_DOF];
+};
+__device__ __forceinline__ uint64_t splitmix_at(uint64_t seed, uint64_t k) {
+  uint64_t z = seed + (k + 1ull) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+template <typename SIG>
+__global__ void __launch_bounds__(128)
+k5_sample(const __grid_constant__ RobotDev rb, const __grid_constant__ SampleBox box, uint64_t seed, int64_t first,
+          int64_t n, int max_tries, double *__restrict__ q_out, int32_t *__restrict__ tries_out) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double q[SQMP_DOF], o[7];
+  int used = -max_tries;
+  for (int t = 0; t < max_tries; ++t) {
+    const uint64_t k0 = (uint64_t(first + i) * uint64_t(max_tries) + uint64_t(t)) * SQMP_DOF;
+#pragma unroll
+    for (int j = 0; j < SQMP_DOF; ++j) {
+      const double u = __dmul_rn(double(splitmix_at(seed, k0 + j) >> 11), 1.0 / 9007199254740992.0);
+      q[j] = __dadd_rn(box.lo[j], __dmul_rn(__dsub_rn(box.hi[j], box.lo[j]), u));
+    }
+    fk_one<double, SIG>(rb, q, o);
+    if (0.0 <= o[2]) {   // above the platform (CL:1182-1184)
+      used = t + 1;
+      break;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < SQMP_DOF; ++j) q_out[i * SQMP_DOF + j] = q[j];
+  if (tries_out) tries_out[i] = used;
+}
+
+cudaError_t launch_sample(const RobotDev &rb, uint64_t seed, int64_t first, int64_t n, const double *lo, const double *hi,
+                          int max_tries, double *d_q_out, int32_t *d_tries_out, bool allow_specialized, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  SampleBox box;
+  for (int j = 0; j < SQMP_DOF; ++j) {
+    box.lo[j] = lo[j];
+    box.hi[j] = hi[j];
+  }
+  const unsigned blocks = unsigned((n + 127) / 128);
+  if (allow_specialized && chain_matches<SigRobotino>(rb))
+    k5_sample<SigRobotino><<<blocks, 128, 0, st>>>(rb, box, seed, first, n, max_tries, d_q_out, d_tries_out);
+  else
+    k5_sample<SigGeneric><<<blocks, 128, 0, st>>>(rb, box, seed, first, n, max_tries, d_q_out, d_tries_out);
+  return cudaGetLastError();
+}
+
 }  // namespace sqmp

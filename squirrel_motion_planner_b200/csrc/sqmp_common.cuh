@@ -133,6 +133,8 @@ cudaError_t launch_get_collisions(const RobotDev &rb, const GridDev &gd, const S
                                   const double *d_q, uint8_t *d_sphere_hit, uint8_t *d_pair_hit, cudaStream_t st);
 cudaError_t launch_fk(const RobotDev &rb, const double *d_q, int64_t S, double *d_out, int fk_precision,
                       bool allow_specialized, cudaStream_t st);
+cudaError_t launch_sample(const RobotDev &rb, uint64_t seed, int64_t first, int64_t n, const double *lo, const double *hi,
+                          int max_tries, double *d_q_out, int32_t *d_tries_out, bool allow_specialized, cudaStream_t st);
 cudaError_t launch_ft_build(const uint32_t *d_occ, int row_words, int gx, int gy, int gz, int halo, int window,
                             int8_t *d_tmp_a, uint16_t *d_tmp_b, uint8_t *d_lb2, uint16_t *d_ft, cudaStream_t st,
                             int *n_launch);

@@ -32,6 +32,9 @@ class GpuBackend {
     ok(sqmp_nn_radius(ctx_, slot, q, &excl, 1, r, k, low.data(), high.data(), &cnt));
     count = cnt;
   }
+  void sample_batch(uint64_t seed, long long first, int n, const double *lo, const double *hi, int max_tries, double *q_out) {
+    ok(sqmp_sample_configs(ctx_, seed, first, n, lo, hi, max_tries, q_out, NULL));
+  }
   bool config_valid(const double *q) {
     uint32_t w = 1;
     if (flags_ == 0) return true;

@@ -65,19 +65,6 @@ struct Stats {
   uint64_t trace = 1469598103934665603ull;   // FNV-1a over every decision: equal traces <=> equal decision sequences
 };
 
-// splitmix64: the same stream on every platform / backend
-struct Rng {
-  uint64_t s;
-  explicit Rng(uint64_t seed) : s(seed) {}
-  uint64_t next() {
-    uint64_t z = (s += 0x9E3779B97F4A7C15ull);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
-  }
-  double uniform(double a, double b) { return a + (b - a) * (double(next() >> 11) * (1.0 / 9007199254740992.0)); }
-};
-
 // stepTowardsRandSample, birrt_star.cpp:5712-5868: x_rand is pulled back to one extend step from nn, separately in the
 // revolute and in the prismatic subspace; returns true when the sample itself was reached.
 inline bool step_towards(const double *nn, double *x_rand, const int *is_revolute, double factor) {
@@ -147,7 +134,7 @@ inline void edge_end(const double *a, const double *b, int num_points, double *o
 template <class Backend>
 class BiRRTStar {
  public:
-  BiRRTStar(Backend &backend, const Params &p) : be(backend), P(p), rng(p.seed) {
+  BiRRTStar(Backend &backend, const Params &p) : be(backend), P(p) {
     start_tree.slot = 0;
     goal_tree.slot = 1;
   }
@@ -155,6 +142,9 @@ class BiRRTStar {
   // init_planner (BS:335-420): both roots must be valid (BS:351-352); trees hold their root with cost 0
   bool init(const double *q_start, const double *q_goal) {
     st = Stats();
+    pool.clear();
+    pool_pos = 0;
+    pool_next = 0;
     if (!be.config_valid(q_start) || !be.config_valid(q_goal)) return false;
     for (PTree *t : {&start_tree, &goal_tree}) {
       t->nodes.clear();
@@ -253,9 +243,18 @@ class BiRRTStar {
   void iterate() {
     st.iterations += 1;
     PTree &A = *tree_a, &B = *tree_b;
-    // ---- sample (sampleJointConfig_JntArray, BS:3832-3878: uniform in the limits) ----
+    // ---- sample (sampleJointConfig_JntArray, BS:3832-3878: uniform in the limits, end-effector above the platform).
+    //      Drawn SAMPLE_POOL at a time by the backend (sqmp_sample_configs on the device); sample i of a query is a
+    //      pure function of (seed, i), so the sequence does not depend on the pool size or the backend ----
+    if (pool_pos >= pool.size() / 8) {
+      pool.resize(size_t(SAMPLE_POOL) * 8);
+      be.sample_batch(P.seed, pool_next, SAMPLE_POOL, P.lo, P.hi, SAMPLE_MAX_TRIES, pool.data());
+      pool_next += SAMPLE_POOL;
+      pool_pos = 0;
+    }
     double x_rand[8];
-    for (int j = 0; j < 8; ++j) x_rand[j] = rng.uniform(P.lo[j], P.hi[j]);
+    for (int j = 0; j < 8; ++j) x_rand[j] = pool[pool_pos * 8 + size_t(j)];
+    pool_pos += 1;
     // ---- nearest neighbour in tree A (BS:1189) ----
     const int nn = be.nearest(A.slot, x_rand);
     st.nn_calls += 1;
@@ -417,7 +416,10 @@ class BiRRTStar {
 
   Backend &be;
   Params P;
-  Rng rng;
+  static const int SAMPLE_POOL = 256, SAMPLE_MAX_TRIES = 64;
+  std::vector<double> pool;
+  size_t pool_pos = 0;
+  long long pool_next = 0;
   PTree start_tree, goal_tree;
   PTree *tree_a = nullptr, *tree_b = nullptr;
   bool solution = false;

@@ -140,6 +140,44 @@ def test_real_scene_room3_with_floor_patch(ctx, orc):
     assert 0.02 < got.mean() < 0.98
 
 
+# --------------------------------------------------------------------------------------- K5: batched sampling (f4)
+@pytest.mark.parametrize("specialized", [1, 0])
+def test_sample_configs_bit_exact_and_order_free(ctx, orc, specialized):
+    """sqmp_sample_configs == the oracle's counter stream bit for bit (configs and try counts); acceptance decided by
+    the kernel's own FK may differ from the CPU's only if |ee_z| < 1e-9 (never observed)."""
+    lo = np.array([-5.0, -4.0, -np.pi, -1.2, -1.7, -1.8, -2.4, -2.9])
+    hi = np.array([5.0, 6.0, np.pi, 1.5, 2.6, 1.8, 2.4, 2.9])
+    ctx.set_option("chain_specialization", specialized)
+    try:
+        for seed, first, n, T in ((1, 0, 5000, 64), (0xFEEDFACE12345, 123456789, 1031, 3)):
+            q, tries = ctx.sample_configs(seed, first, n, lo, hi, T)
+            qr, tr = orc.sample_configs(seed, first, n, lo, hi, T)
+            same = np.all(q == qr, axis=1) & (tries == tr)
+            if not same.all():
+                assert np.abs(orc.fk(qr[~same])[:, 2]).max() < 1e-9
+            assert same.mean() > 0.999
+            assert np.all(q >= lo) and np.all(q <= hi)
+            ee = ctx.fk(q)
+            assert np.all((tries > 0) == (ee[:, 2] >= 0.0))
+        a, _ = ctx.sample_configs(7, 40, 300, lo, hi, 8)
+        b, _ = ctx.sample_configs(7, 0, 340, lo, hi, 8)
+        assert np.array_equal(a, b[40:])
+        # rejection-heavy box (arm folded under the platform): exhausted tries are reported as -max_tries
+        lo2, hi2 = lo.copy(), hi.copy()
+        lo2[3:] = [1.3, -1.7, -1.8, -0.4, -2.9]; hi2[3:] = [1.5, -1.0, -0.8, 0.8, 2.9]
+        q2, t2 = ctx.sample_configs(3, 0, 2000, lo2, hi2, 4)
+        qr2, tr2 = orc.sample_configs(3, 0, 2000, lo2, hi2, 4)
+        assert np.array_equal(q2, qr2) and np.array_equal(t2, tr2)
+        assert (t2 > 1).any() and (t2 < 0).any()
+        assert ctx.sample_configs(1, 0, 0, lo, hi, 4)[0].shape == (0, 8)            # empty batch
+        with pytest.raises(api.SqmpError):
+            ctx.sample_configs(1, 0, 4, hi, lo, 4)                                    # lo > hi
+        with pytest.raises(api.SqmpError):
+            ctx.sample_configs(1, 0, 4, lo, hi, 0)                                    # no tries
+    finally:
+        ctx.set_option("chain_specialization", 1)
+
+
 # --------------------------------------------------------------------------------------- the two validity kernels
 @pytest.mark.parametrize("kernel", [1, 2])
 @pytest.mark.parametrize("flags", [api.CHECK_MAP, api.CHECK_MAP | api.CHECK_SELF])

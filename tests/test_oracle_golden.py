@@ -149,3 +149,42 @@ def test_published_poses_are_self_collision_free(orc, fixture_data):
     q = np.array([[0.3, -0.2, 0.7] + list(a) for a in poses])
     hit = unpack(orc.check_states(q, oracle.FLAG_SELF), len(q))
     assert not hit.any()
+
+
+def test_sampler_is_the_documented_counter_stream(orc):
+    """orc_sample_configs (sampleJointConfig_JntArray BS:3832-3878 / getRandomConf CL:1120-1188) against an independent
+    pure-Python restatement of the splitmix64 counter stream, the uniform map and the 0.0 <= ee_z acceptance rule."""
+    lo = np.array([-5.0, -4.0, -np.pi, -1.2, -1.7, -1.8, -2.4, -2.9])
+    hi = np.array([5.0, 6.0, np.pi, 1.5, 2.6, 1.8, 2.4, 2.9])
+    M, G = (1 << 64) - 1, 0x9E3779B97F4A7C15
+
+    def out(seed, k):
+        z = (seed + (k + 1) * G) & M
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+        return z ^ (z >> 31)
+
+    seed, first, n, T = 0xDEADBEEFCAFE, 1000, 300, 5
+    q, tries = orc.sample_configs(seed, first, n, lo, hi, T)
+    for i in range(n):
+        used = -T
+        for t in range(T):
+            k0 = ((first + i) * T + t) * 8
+            cand = np.array([lo[j] + (hi[j] - lo[j]) * ((out(seed, k0 + j) >> 11) * (1.0 / 9007199254740992.0)) for j in range(8)])
+            if orc.fk(cand[None])[0, 2] >= 0.0:
+                used = t + 1
+                break
+        assert tries[i] == used and np.array_equal(q[i], cand)
+    assert np.all(q >= lo) and np.all(q <= hi)
+    # order-free: a batch is the concatenation of its parts; a different seed is a different stream
+    qa, _ = orc.sample_configs(seed, first, 100, lo, hi, T)
+    qb, _ = orc.sample_configs(seed, first + 100, 200, lo, hi, T)
+    assert np.array_equal(q, np.concatenate([qa, qb]))
+    assert not np.array_equal(orc.sample_configs(seed + 1, first, 10, lo, hi, T)[0], q[:10])
+    # a box whose arm poses dive below the platform: rejections happen and are reported
+    lo2, hi2 = lo.copy(), hi.copy()
+    lo2[3:] = [1.3, -1.7, -1.8, -0.4, -2.9]; hi2[3:] = [1.5, -1.0, -0.8, 0.8, 2.9]
+    q2, t2 = orc.sample_configs(3, 0, 200, lo2, hi2, 4)
+    ee = orc.fk(q2)[:, 2]
+    assert np.all((t2 > 0) == (ee >= 0.0))
+    assert (t2 > 1).any() and (t2 < 0).any()                 # some samples needed a redraw, some ran out of tries

@@ -31,6 +31,7 @@ def write_oracle_model(d, lt, spheres):
                      (lt.shaped, np.int32), (lt.self_pair_matrix(), np.uint8), (sph_link, np.int32), (sph_c, np.float64),
                      (sph_r, np.float64)):
             f.write(np.ascontiguousarray(a, dtype=t).tobytes())
+        f.write(np.array([lt.index("hand_wrist_link")], dtype=np.int32).tobytes())   # FK chain tip (SRDF:4-6)
 
 
 def folded_arm():
