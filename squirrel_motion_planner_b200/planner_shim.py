@@ -158,6 +158,22 @@ class BiRRTstarHotPath:
         last_valid = np.where(first < 0, self.m_num_traj_segments_interp, np.maximum(first - 1, 0))
         return first < 0, last_valid
 
+    # BS:3881-3930 sampleJointConfig_Vector over getRandomConf (CL:1120-1188): uniform in the limits, end-effector
+    # above the platform; drawn `pool` at a time on the device, sample i a pure function of (seed, i)
+    def setSamplingBox(self, q_min, q_max, seed=1, pool=256):
+        self._sample_box = (np.asarray(q_min, dtype=np.float64), np.asarray(q_max, dtype=np.float64), int(seed), int(pool))
+        self._sample_next, self._sample_pool, self._sample_pos = 0, np.zeros((0, 8)), 0
+
+    def sampleJointConfig_Vector(self):
+        lo, hi, seed, pool = self._sample_box
+        if self._sample_pos >= len(self._sample_pool):
+            self._sample_pool, _ = self.ctx.sample_configs(seed, self._sample_next, pool, lo, hi, 64)
+            self._sample_next += pool
+            self._sample_pos = 0
+        q = self._sample_pool[self._sample_pos]
+        self._sample_pos += 1
+        return q.tolist()
+
     # BS:3298-3322 / DS invariant node_id == index
     def insertNode(self, tree: Rrt_star_tree, node: Node):
         nid = self.ctx.tree_append(tree.index, node.config, node.cost_reach_total)

@@ -500,6 +500,34 @@ class HotPath {
     return pose;
   }
 
+  // BS:3881-3930 sampleJointConfig_Vector / BS:3832-3878 sampleJointConfig_JntArray over getRandomConf (CL:1120-1188):
+  // uniform in [q_min, q_max] (base joints from m_env_size_x / m_env_size_y), end-effector above the platform.
+  // Samples are drawn 256 at a time on the device (sqmp_sample_configs) and handed out one by one; sample i of the
+  // stream is a pure function of (seed, i) — call setSamplingBox again to restart the stream.
+  void setSamplingBox(const std::vector<double> &q_min, const std::vector<double> &q_max, uint64_t seed) {
+    for (int j = 0; j < SQMP_DOF; ++j) {
+      sample_lo_[j] = j < int(q_min.size()) ? q_min[size_t(j)] : 0.0;
+      sample_hi_[j] = j < int(q_max.size()) ? q_max[size_t(j)] : 0.0;
+    }
+    sample_seed_ = seed;
+    sample_next_ = 0;
+    sample_pool_.clear();
+    sample_pos_ = 0;
+  }
+  std::vector<double> sampleJointConfig_Vector() {
+    if (sample_pos_ >= sample_pool_.size() / SQMP_DOF) {
+      sample_pool_.assign(size_t(256) * SQMP_DOF, 0.0);
+      if (sqmp_sample_configs(collisionChecker->context(), sample_seed_, sample_next_, 256, sample_lo_, sample_hi_, 64,
+                              sample_pool_.data(), NULL) != SQMP_OK)
+        return std::vector<double>();
+      sample_next_ += 256;
+      sample_pos_ = 0;
+    }
+    const double *q = &sample_pool_[sample_pos_ * SQMP_DOF];
+    sample_pos_ += 1;
+    return std::vector<double>(q, q + SQMP_DOF);
+  }
+
   CollisionChecker *collisionChecker;   // same member name as birrt_star.h
   double m_near_threshold_interpolation;
   int m_max_near_nodes;
@@ -507,6 +535,11 @@ class HotPath {
  private:
   std::vector<double> scratch_q_;
   std::vector<uint32_t> scratch_mask_;
+  double sample_lo_[SQMP_DOF] = {0}, sample_hi_[SQMP_DOF] = {0};
+  uint64_t sample_seed_ = 1;
+  int64_t sample_next_ = 0;
+  std::vector<double> sample_pool_;
+  size_t sample_pos_ = 0;
 };
 
 }  // namespace sqmp_shim

@@ -169,6 +169,18 @@ int main(int argc, char **argv) {
     poses.insert(poses.end(), p.begin(), p.end());
   }
   write_raw(dir + "out_fk.f64", poses);
+
+  // ---- sampleJointConfig_Vector (BS:3881-3930 over CL:1120-1188): 600 draws = three device batches ----
+  {
+    const double lo[8] = {-5.0, -4.0, -3.0, -1.2, -1.7, -1.8, -2.4, -2.9}, hi[8] = {5.0, 6.0, 3.0, 1.5, 2.6, 1.8, 2.4, 2.9};
+    planner.setSamplingBox(std::vector<double>(lo, lo + 8), std::vector<double>(hi, hi + 8), 20240607ull);
+    std::vector<double> samples;
+    for (int i = 0; i < 600; ++i) {
+      const std::vector<double> q = planner.sampleJointConfig_Vector();
+      samples.insert(samples.end(), q.begin(), q.end());
+    }
+    write_raw(dir + "out_samples.f64", samples);
+  }
   delete collisionChecker;
   std::printf("test_shim ok: %zu states, %zu nodes, %zu queries\n", S, cost.size(), queries.size() / 8);
   return 0;

@@ -124,3 +124,8 @@ def test_cpp_shim_against_oracle(tmp_path, fixture_data, orc, small_world):
     ref = orc.fk(q[:len(fk)])
     assert np.abs(fk[:, :3] - ref[:, :3]).max() < 1e-5
     assert np.minimum(np.abs(fk[:, 3:] - ref[:, 3:]).max(1), np.abs(fk[:, 3:] + ref[:, 3:]).max(1)).max() < 1e-5
+
+    samples = np.fromfile(os.path.join(d, "out_samples.f64")).reshape(-1, 8)      # sampleJointConfig_Vector, BS:3881-3930
+    lo = np.array([-5.0, -4.0, -3.0, -1.2, -1.7, -1.8, -2.4, -2.9]); hi = np.array([5.0, 6.0, 3.0, 1.5, 2.6, 1.8, 2.4, 2.9])
+    want, _ = orc.sample_configs(20240607, 0, 600, lo, hi, 64)
+    assert np.array_equal(samples, want)

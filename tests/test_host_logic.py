@@ -175,3 +175,26 @@ def test_mask_allgather_world_size_2_gloo(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=240)
         assert p.returncode == 0, out
+
+
+def test_sphere_fit_covers_every_reference_primitive(fixture_data):
+    """a covering fit of every URDF primitive of the reference (collision_checker.hpp:282-294 shapes) at
+    the authored radius contains the whole shape, stays within one radius of it, and the grading of the authored model
+    reports what it is: complete for the single-sphere cylinders, partial where a link leans on its neighbours."""
+    from squirrel_motion_planner_b200 import sphere_fit as sf
+    lt, fx, spheres = fixture_data
+    rows = {r["link"]: r for r in sf.report(lt, spheres)}
+    assert len(rows) == 27                                            # the 27 shaped links of CC:263-351
+    prim = [r for r in rows.values() if "fit" in r]
+    assert sorted(r["link"] for r in prim) == ["head_link", "hokuyo_link", "kinect_link", "neck_pan_link", "shell_base_link_front"]
+    for r in prim:
+        assert r["fit"]["covered"] == 1.0 and r["fit"]["protrusion"] <= max(r["radii"]) + 1e-12
+    assert rows["head_link"]["authored"]["covered"] > 0.99 and rows["hokuyo_link"]["authored"]["covered"] > 0.99
+    assert all(r["n_spheres"] >= 1 for r in rows.values())            # every shaped link owns a sphere (disable mask, SRDF pairs)
+    # the fit at other radii, a thin box and the parser
+    for shape, r in ((("box", (0.55, 0.55, 0.17)), 0.1), (("cylinder", (0.2, 0.08)), 0.05), (("box", (0.035, 0.18, 0.02)), 0.03)):
+        c = sf.fit_primitive(shape, r)
+        g = sf.grade(shape, c, np.full(len(c), r))
+        assert g["covered"] == 1.0 and g["protrusion"] <= r + 1e-12
+    assert sf.parse_shape("cylinder r=0.23 l=0.25") == ("cylinder", (0.23, 0.25)) and sf.parse_shape("mesh x.stl") is None
+    assert np.allclose(sf.segment_distance([[0, 1, 0.5], [0, 0, 2]], [0, 0, 0], [0, 0, 1]), [1.0, 1.0])
