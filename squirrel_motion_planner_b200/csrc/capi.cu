@@ -1,6 +1,7 @@
 // capi.cu — the C ABI of libsqmp_b200.so (include/sqmp_b200.h): context, device memory, host<->device staging.
 // No CPU fallback anywhere: every entry point either runs the CUDA kernels or returns an error code.
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -30,7 +31,8 @@ struct Ctx {
   int sph_slot[SQMP_MAX_SPHERES];
   int n_pairs = 0;
   std::vector<SelfPair> h_pairs;   // the description's pairs: a, b = SPHERE indices, rsum2 in metres^2
-  SelfPair *d_pairs = nullptr, *d_flat = nullptr;   // device: hierarchical order / description order (slots, grid units)
+  SelfHPair *d_pairs = nullptr;   // device: hierarchical order (grid units)
+  SelfPair *d_flat = nullptr;     // device: description order (slots, grid units)
   SelfA *d_as = nullptr;
   SelfBlock *d_blocks = nullptr;
   SelfDev self;
@@ -250,7 +252,8 @@ static int refresh_grid_robot(Ctx *c) {
       const double v = (r_sum * (1.0 + 1e-4) + 1e-6) * inv;
       return float(v * v * (1.0 + 1e-6));
     };
-    std::vector<SelfPair> flat(size_t(c->n_pairs) + 1), hier;
+    std::vector<SelfPair> flat(size_t(c->n_pairs) + 1);
+    std::vector<SelfHPair> hier;
     std::vector<SelfA> as;
     std::vector<SelfBlock> blocks;
     for (int p = 0; p < c->n_pairs; ++p) {
@@ -273,32 +276,96 @@ static int refresh_grid_robot(Ctx *c) {
           if (std::find(sa.begin(), sa.end(), a) == sa.end()) sa.push_back(a);
           if (std::find(sb.begin(), sb.end(), b) == sb.end()) sb.push_back(b);
         }
-        double cA[3], cB[3];
-        const double RA = bound(sa, cA), RB = bound(sb, cB);
-        SelfBlock blk;
-        blk.fa = g.grp_fidx[ga];
-        blk.fb = g.grp_fidx[gb];
-        blk.a_begin = int(as.size());
-        for (int k = 0; k < 3; ++k) {
-          blk.ca[k] = float(cA[k] * inv);
-          blk.cb[k] = float(cB[k] * inv);
+        // The A side is split into spatial clusters of <= ~5 spheres (farthest-point seeds + a few Lloyd steps on the
+        // sphere centres): the base group spans the whole robot, so one bounding sphere for it never rules a block
+        // out, while a cluster's does.  All clusters of one (group A, group B) share the B-side bound, so the kernel
+        // forms that bound in A's frame once and tests every cluster, and every A-sphere, against it as constants.
+        std::vector<std::vector<int> > clusters;
+        {
+          const int n = int(sa.size());
+          int k = n <= 6 ? 1 : (n + 4) / 5;
+          if (k > 8) k = 8;
+          std::vector<int> seed(1, 0), assign(size_t(n), 0);
+          auto d2 = [&](int i, const double *q) {
+            double v = 0.0;
+            for (int t = 0; t < 3; ++t) v += (rb.sph[sa[size_t(i)]][t] - q[t]) * (rb.sph[sa[size_t(i)]][t] - q[t]);
+            return v;
+          };
+          std::vector<std::array<double, 3> > cen;
+          cen.push_back({rb.sph[sa[0]][0], rb.sph[sa[0]][1], rb.sph[sa[0]][2]});
+          while (int(cen.size()) < k) {   // farthest point from the chosen seeds
+            int best = 0;
+            double bd = -1.0;
+            for (int i = 0; i < n; ++i) {
+              double m = 1e300;
+              for (auto &q : cen) m = std::fmin(m, d2(i, q.data()));
+              if (m > bd) { bd = m; best = i; }
+            }
+            cen.push_back({rb.sph[sa[size_t(best)]][0], rb.sph[sa[size_t(best)]][1], rb.sph[sa[size_t(best)]][2]});
+          }
+          for (int it = 0; it < 8; ++it) {
+            for (int i = 0; i < n; ++i) {
+              int best = 0;
+              for (int q = 1; q < k; ++q)
+                if (d2(i, cen[size_t(q)].data()) < d2(i, cen[size_t(best)].data())) best = q;
+              assign[size_t(i)] = best;
+            }
+            for (int q = 0; q < k; ++q) {
+              double sum[3] = {0, 0, 0};
+              int cnt = 0;
+              for (int i = 0; i < n; ++i)
+                if (assign[size_t(i)] == q) {
+                  for (int t = 0; t < 3; ++t) sum[t] += rb.sph[sa[size_t(i)]][t];
+                  ++cnt;
+                }
+              if (cnt)
+                for (int t = 0; t < 3; ++t) cen[size_t(q)][size_t(t)] = sum[t] / cnt;
+            }
+          }
+          clusters.assign(size_t(k), std::vector<int>());
+          for (int i = 0; i < n; ++i) clusters[size_t(assign[size_t(i)])].push_back(sa[size_t(i)]);
         }
-        blk.thr2 = inflate2(RA + RB);
-        blk.pad = 0.0f;
-        for (int a : sa) {
-          SelfA ea;
-          ea.a = c->sph_slot[a];
-          ea.p_begin = int(hier.size());
-          for (int p : members)
-            if (c->h_pairs[p].a == a) hier.push_back(flat[p]);
-          ea.p_end = int(hier.size());
-          ea.thr2 = inflate2(rb.sph[a][3] + RB);
-          as.push_back(ea);
+        double cB[3];
+        const double RB = bound(sb, cB);
+        for (const std::vector<int> &cl : clusters) {
+          if (cl.empty()) continue;
+          double cA[3];
+          const double RA = bound(cl, cA);
+          SelfBlock blk;
+          blk.fa = g.grp_fidx[ga];
+          blk.fb = g.grp_fidx[gb];
+          blk.a_begin = int(as.size());
+          for (int k = 0; k < 3; ++k) {
+            blk.ca[k] = float(cA[k] * inv);
+            blk.cb[k] = float(cB[k] * inv);
+          }
+          blk.thr2 = inflate2(RA + RB);
+          blk.pad = 0.0f;
+          for (int a : cl) {
+            SelfA ea;
+            ea.a = c->sph_slot[a];
+            ea.pad = 0;
+            ea.cx = float(rb.sph[a][0] * inv); ea.cy = float(rb.sph[a][1] * inv); ea.cz = float(rb.sph[a][2] * inv);
+            ea.p_begin = int(hier.size());
+            for (int p : members)
+              if (c->h_pairs[p].a == a) {
+                const int b = c->h_pairs[p].b;
+                SelfHPair hp;
+                hp.bx = float(rb.sph[b][0] * inv); hp.by = float(rb.sph[b][1] * inv); hp.bz = float(rb.sph[b][2] * inv);
+                hp.rsum2 = flat[p].rsum2;
+                hier.push_back(hp);
+              }
+            ea.p_end = int(hier.size());
+            ea.thr2 = inflate2(rb.sph[a][3] + RB);
+            as.push_back(ea);
+          }
+          blk.a_end = int(as.size());
+          blocks.push_back(blk);
         }
-        blk.a_end = int(as.size());
-        blocks.push_back(blk);
       }
-    hier.resize(size_t(c->n_pairs) + 1);
+    hier.resize(size_t(c->n_pairs) + 4);   // the kernels read partners and A-spheres four at a time (masked)
+    const size_t n_as_real = as.size();
+    as.resize(n_as_real + 4);
     auto upload = [&](auto *&dptr, const auto &vec, size_t min_count) -> cudaError_t {
       using E = typename std::remove_reference<decltype(vec)>::type::value_type;
       const size_t count = vec.size() > min_count ? vec.size() : min_count;
@@ -309,17 +376,17 @@ static int refresh_grid_robot(Ctx *c) {
       return vec.empty() ? cudaSuccess : cudaMemcpy(dptr, vec.data(), sizeof(E) * vec.size(), cudaMemcpyHostToDevice);
     };
     // sizes depend only on the pair list, which is fixed at sqmp_create: allocated once with that capacity
-    cudaError_t e = upload(c->d_pairs, hier, size_t(c->n_pairs) + 1);
+    cudaError_t e = upload(c->d_pairs, hier, size_t(c->n_pairs) + 4);
     if (e == cudaSuccess) e = upload(c->d_flat, flat, size_t(c->n_pairs) + 1);
-    if (e == cudaSuccess) e = upload(c->d_as, as, size_t(c->n_pairs) + 1);
-    if (e == cudaSuccess) e = upload(c->d_blocks, blocks, size_t(SQMP_MAX_SEG + 1) * (SQMP_MAX_SEG + 1));
+    if (e == cudaSuccess) e = upload(c->d_as, as, size_t(c->n_pairs) + 4);
+    if (e == cudaSuccess) e = upload(c->d_blocks, blocks, size_t(SQMP_MAX_SEG + 1) * (SQMP_MAX_SEG + 1) * 8);   // <= 8 clusters per group pair
     if (e != cudaSuccess) return fail(c, SQMP_ERR_CUDA, "self-collision tables", e);
-    c->self.pairs = c->d_pairs;
+    c->self.hpairs = c->d_pairs;
     c->self.flat = c->d_flat;
     c->self.as = c->d_as;
     c->self.blocks = c->d_blocks;
     c->self.n_pairs = c->n_pairs;
-    c->self.n_as = int(as.size());
+    c->self.n_as = int(n_as_real);
     c->self.n_blocks = int(blocks.size());
   }
   return SQMP_OK;

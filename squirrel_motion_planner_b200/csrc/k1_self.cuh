@@ -22,27 +22,57 @@ __device__ __forceinline__ float self_dist2(float ax, float ay, float az, float 
 }
 
 // true <=> some enabled pair of spheres of this state overlaps.  A level of the hierarchy is entered only if the
-// level above cannot rule it out, so a state far from self contact costs ~one test per block.
-__device__ __forceinline__ bool self_collision(const SelfDev &self, const RobotDev &rb, const float *f_mine, int pitch) {
-  for (int bi = 0; bi < self.n_blocks; ++bi) {
-    const SelfBlock B = self.blocks[bi];
-    float FA[12], FB[12], ax, ay, az, bx, by, bz;
-    self_load_frame(f_mine, pitch, B.fa, FA);
-    self_load_frame(f_mine, pitch, B.fb, FB);
-    self_xform(FA, B.ca[0], B.ca[1], B.ca[2], ax, ay, az);
-    self_xform(FB, B.cb[0], B.cb[1], B.cb[2], bx, by, bz);   // bounding sphere of the block's B side
-    if (self_dist2(ax, ay, az, bx, by, bz) > B.thr2) continue;
-    for (int ai = B.a_begin; ai < B.a_end; ++ai) {
-      const SelfA A = self.as[ai];
-      const float4 ca = rb.sph_f[A.a];
-      self_xform(FA, ca.x, ca.y, ca.z, ax, ay, az);
-      if (self_dist2(ax, ay, az, bx, by, bz) > A.thr2) continue;
-      for (int p = A.p_begin; p < A.p_end; ++p) {
-        const SelfPair pr = self.pairs[p];
-        const float4 cb = rb.sph_f[pr.b];
-        float px, py, pz;
-        self_xform(FB, cb.x, cb.y, cb.z, px, py, pz);
-        if (self_dist2(ax, ay, az, px, py, pz) <= pr.rsum2) return true;
+// level above cannot rule it out, so a state far from self contact costs ~one test per block.  `blocks` and `as` may
+// point to shared-memory copies of SelfDev's tables (validity_fast.cu stages them: the loops below are chains of
+// dependent, warp-uniform loads, so their latency is the cost).
+__device__ __forceinline__ bool self_collision(const SelfBlock *blocks, int n_blocks, const SelfA *as, const SelfHPair *hpairs,
+                                               const float *f_mine, int pitch) {
+  int pfa = -1, pfb = -1;
+  float FA[12], FB[12], lx = 0.0f, ly = 0.0f, lz = 0.0f, ax, ay, az;
+  for (int bi = 0; bi < n_blocks; ++bi) {
+    const SelfBlock B = blocks[bi];
+    if (B.fa != pfa || B.fb != pfb) {   // blocks come sorted by group pair (warp-uniform): frames and B bound once per pair
+      pfa = B.fa;
+      pfb = B.fb;
+      self_load_frame(f_mine, pitch, B.fa, FA);
+      self_load_frame(f_mine, pitch, B.fb, FB);
+      float bx, by, bz;
+      self_xform(FB, B.cb[0], B.cb[1], B.cb[2], bx, by, bz);   // bounding sphere of the pair's B side, shared by its blocks
+      // ... expressed in A's frame (R_A^T (b - t_A)): A-side clusters and A-spheres are then tested as the constants
+      // they are, 7 instructions each instead of a 9-FMA transform
+      const float dx = bx - FA[9], dy = by - FA[10], dz = bz - FA[11];
+      lx = fmaf(FA[0], dx, fmaf(FA[3], dy, FA[6] * dz));
+      ly = fmaf(FA[1], dx, fmaf(FA[4], dy, FA[7] * dz));
+      lz = fmaf(FA[2], dx, fmaf(FA[5], dy, FA[8] * dz));
+    }
+    if (self_dist2(B.ca[0], B.ca[1], B.ca[2], lx, ly, lz) > B.thr2) continue;   // this A-side cluster is out of reach
+    // four A-spheres, then four partners, per step: the loops are chains of dependent warp-uniform loads and short
+    // arithmetic, so their cost is latency; batching gives the scheduler four independent chains (tables are padded
+    // by four records, out-of-range records are masked)
+    for (int ai = B.a_begin; ai < B.a_end; ai += 4) {
+      SelfA A[4];
+      unsigned pass = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) A[k] = as[ai + k];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (ai + k < B.a_end && self_dist2(A[k].cx, A[k].cy, A[k].cz, lx, ly, lz) <= A[k].thr2) pass |= 1u << k;
+      while (pass) {
+        const int k = __ffs(pass) - 1;
+        pass &= pass - 1;
+        const SelfA Ak = k == 0 ? A[0] : (k == 1 ? A[1] : (k == 2 ? A[2] : A[3]));
+        self_xform(FA, Ak.cx, Ak.cy, Ak.cz, ax, ay, az);
+        for (int p = Ak.p_begin; p < Ak.p_end; p += 4) {
+          bool h = false;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const SelfHPair pr = hpairs[p + j];
+            float px, py, pz;
+            self_xform(FB, pr.bx, pr.by, pr.bz, px, py, pz);
+            h |= (p + j < Ak.p_end) && self_dist2(ax, ay, az, px, py, pz) <= pr.rsum2;
+          }
+          if (h) return true;
+        }
       }
     }
   }

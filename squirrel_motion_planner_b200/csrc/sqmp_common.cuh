@@ -102,10 +102,16 @@ struct SelfPair {   // 8 bytes
   unsigned char fa, fb;   // frame slots of their groups (RobotDev::grp_fidx)
   float rsum2;            // (ra + rb)^2, grid units
 };
-struct SelfA {      // 16 bytes
-  int a;                  // sphere slot
-  int p_begin, p_end;     // its partners in SelfDev::pairs
+struct SelfA {      // 32 bytes: everything one A-test needs in one record (no dependent second load)
+  float cx, cy, cz;       // the A-sphere's centre in its group frame, grid units
   float thr2;             // (ra + RB)^2
+  int p_begin, p_end;     // its partners in SelfDev::hpairs
+  int a;                  // sphere slot
+  int pad;
+};
+struct SelfHPair {  // 16 bytes: a partner of an A-sphere, hierarchical order (block, a, b)
+  float bx, by, bz;       // the B-sphere's centre in its group frame, grid units
+  float rsum2;            // (ra + rb)^2
 };
 struct SelfBlock {  // 48 bytes
   int fa, fb;             // frame slots of the two groups
@@ -115,7 +121,7 @@ struct SelfBlock {  // 48 bytes
   float pad;
 };
 struct SelfDev {
-  const SelfPair *pairs;    // hierarchical order (block, a, b)
+  const SelfHPair *hpairs;  // hierarchical order (block, a, b)
   const SelfA *as;
   const SelfBlock *blocks;
   const SelfPair *flat;     // the description's own pair order (diagnostics: one result per pair)

@@ -260,7 +260,7 @@ k1_check_states(const __grid_constant__ RobotDev rb, const __grid_constant__ Gri
         pair_hit[p] = h ? 1 : 0;
       }
     } else if (!hit) {
-      hit = self_collision(self, rb, f_mine, K1_THREADS);
+      hit = self_collision(self.blocks, self.n_blocks, self.as, self.hpairs, f_mine, K1_THREADS);
     }
   }
 

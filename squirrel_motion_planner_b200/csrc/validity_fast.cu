@@ -67,7 +67,10 @@ k1_fast(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd,
   float4 *slots4 = reinterpret_cast<float4 *>(smem_raw + sizeof(WarpQueue) * (KF_THREADS / 32) + sizeof(double) * SQMP_DOF * KF_THREADS);
   // slots4: [n_slots / 2] FastPair (2 x float4 each), then [n_slots] FastAux (8 bytes each)
   const FastAux *aux_s = reinterpret_cast<const FastAux *>(slots4 + fd.n_slots);
-  float *f_mine = reinterpret_cast<float *>(slots4 + fd.n_slots + (fd.n_slots + 1) / 2) + threadIdx.x;   // SELF: [n_frames*12][blockDim]
+  // SELF: copies of the block and A-sphere tables of the pair hierarchy, then the group frames [n_frames*12][blockDim]
+  SelfBlock *blocks_s = reinterpret_cast<SelfBlock *>(slots4 + fd.n_slots + (fd.n_slots + 1) / 2);
+  SelfA *as_s = reinterpret_cast<SelfA *>(blocks_s + (SELF ? self.n_blocks : 0));
+  float *f_mine = reinterpret_cast<float *>(as_s + (SELF ? self.n_as : 0)) + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool active = s < S;
@@ -80,6 +83,12 @@ k1_fast(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd,
     const float2 *src2 = reinterpret_cast<const float2 *>(fd.aux);
     float2 *dst2 = reinterpret_cast<float2 *>(slots4 + fd.n_slots);
     for (int i = threadIdx.x; i < fd.n_slots; i += KF_THREADS) dst2[i] = __ldg(src2 + i);
+    if (SELF) {
+      const float4 *sb = reinterpret_cast<const float4 *>(self.blocks), *sa = reinterpret_cast<const float4 *>(self.as);
+      float4 *db = reinterpret_cast<float4 *>(blocks_s), *da = reinterpret_cast<float4 *>(as_s);
+      for (int i = threadIdx.x; i < 3 * self.n_blocks; i += KF_THREADS) db[i] = __ldg(sb + i);
+      for (int i = threadIdx.x; i < 2 * self.n_as; i += KF_THREADS) da[i] = __ldg(sa + i);
+    }
   }
 
   // ---- the state: either given, or interpolated from the edge end points (BS:4461-4462, 4478; no FMA) ----
@@ -263,7 +272,8 @@ k1_fast(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd,
     hit |= (hm >> lane) & 1u;
   }
 
-  if (SELF && !hit) hit = rb.self_const_collision || self_collision(self, rb, f_mine, KF_THREADS);
+  if (SELF && !hit)
+    hit = rb.self_const_collision || self_collision(blocks_s, self.n_blocks, as_s, self.hpairs, f_mine, KF_THREADS);
 
   const unsigned word = __ballot_sync(FULL, hit && active);
   if (lane == 0 && s < ((S + 31) & ~int64_t(31))) mask_out[s >> 5] = word;
@@ -275,7 +285,8 @@ cudaError_t launch_check_states_fast(const RobotDev &rb, const GridDev &gd, cons
   const bool with_self = (flags & SQMP_CHECK_SELF) != 0;
   size_t smem = sizeof(WarpQueue) * (KF_THREADS / 32) + sizeof(double) * SQMP_DOF * KF_THREADS +
                 16 * size_t(fd.n_slots + (fd.n_slots + 1) / 2);   // FastPair: 16 B per slot; FastAux: 8 B per slot
-  if (with_self) smem += size_t(12) * rb.n_frames * KF_THREADS * sizeof(float);
+  if (with_self)
+    smem += size_t(12) * rb.n_frames * KF_THREADS * sizeof(float) + sizeof(SelfBlock) * self.n_blocks + sizeof(SelfA) * self.n_as;
   const int64_t blocks = (S + KF_THREADS - 1) / KF_THREADS;
   if (blocks <= 0) return cudaSuccess;
   if (blocks > 0x7fffffff) return cudaErrorInvalidValue;
