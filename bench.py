@@ -347,6 +347,20 @@ def side_metrics(ctx, torch, dev, stream, d_q, S):
     d_first = torch.empty(E, dtype=torch.int32, device=dev)
     ms = t_ms(lambda: ctx.check_edges_dev(da, db, E, 20, api.CHECK_MAP, d_mask, d_first, stream))
     out["edges_entry_states_per_s"] = E * 21 / ms * 1e3
+    # the same batch through the host-buffer edge entry point: 2 x 64 B per 21 states over PCIe instead of 21 x 64 B
+    ha, hb = torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()
+    for _ in range(2):
+        ctx.check_edges(ha, hb, 20, api.CHECK_MAP)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        ctx.check_edges(ha, hb, 20, api.CHECK_MAP)
+    out["e2e_edges_entry_states_per_s"] = E * 21 * 10 / (time.perf_counter() - t0)
+    d_s = torch.empty((S, 8), dtype=torch.float64, device=dev)
+    d_t = torch.empty(S, dtype=torch.int32, device=dev)
+    lo = np.array([-5.0, -5.0, -np.pi, -1.2, -1.7, -1.8, -2.4, -2.9])
+    hi = np.array([5.0, 5.0, np.pi, 1.5, 2.6, 1.8, 2.4, 2.9])
+    ms = t_ms(lambda: ctx.sample_configs_dev(1, 0, S, lo, hi, 64, d_s, d_t, stream), n=10, warm=2)
+    out["sample_configs_per_s"] = S / ms * 1e3                      # K5: uniform draw + FK rejection (ee above platform)
     N, Q = 1 << 20, 1 << 16
     nodes, cost = syn.random_tree(N, 7, 9)
     ctx.tree_reset(0)

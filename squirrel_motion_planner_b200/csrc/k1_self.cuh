@@ -62,14 +62,17 @@ __device__ __forceinline__ bool self_collision(const SelfBlock *blocks, int n_bl
         pass &= pass - 1;
         const SelfA Ak = k == 0 ? A[0] : (k == 1 ? A[1] : (k == 2 ? A[2] : A[3]));
         self_xform(FA, Ak.cx, Ak.cy, Ak.cz, ax, ay, az);
+        // this A-sphere in B's frame (R_B^T (a - t_B)): its partners are then constants too
+        const float ex = ax - FB[9], ey = ay - FB[10], ez = az - FB[11];
+        const float mx = fmaf(FB[0], ex, fmaf(FB[3], ey, FB[6] * ez));
+        const float my = fmaf(FB[1], ex, fmaf(FB[4], ey, FB[7] * ez));
+        const float mz = fmaf(FB[2], ex, fmaf(FB[5], ey, FB[8] * ez));
         for (int p = Ak.p_begin; p < Ak.p_end; p += 4) {
           bool h = false;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const SelfHPair pr = hpairs[p + j];
-            float px, py, pz;
-            self_xform(FB, pr.bx, pr.by, pr.bz, px, py, pz);
-            h |= (p + j < Ak.p_end) && self_dist2(ax, ay, az, px, py, pz) <= pr.rsum2;
+            h |= (p + j < Ak.p_end) && self_dist2(mx, my, mz, pr.bx, pr.by, pr.bz) <= pr.rsum2;
           }
           if (h) return true;
         }
