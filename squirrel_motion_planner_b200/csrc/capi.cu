@@ -835,7 +835,8 @@ int sqmp_check_states_dev(sqmp_ctx *ctx, const double *d_q, int64_t S, unsigned 
   }
   int nl = 0;
   if (use_fast_k1(c, flags))
-    CU(launch_check_states_fast(c->rb_grid, c->gd, c->self, c->fast, d_q, nullptr, 0, S, flags, d_mask, st, &nl));
+    CU(launch_check_states_fast(c->rb_grid, c->gd, c->self, c->fast, d_q, nullptr, 0, S, flags, d_mask,
+                                c->chain_specialization != 0, st, &nl));
   else
     CU(launch_check_states(c->rb_grid, c->gd, c->self, d_q, nullptr, 0, S, flags, d_mask, c->fk_precision,
                            st, &nl));
@@ -857,7 +858,8 @@ int sqmp_check_edges_dev(sqmp_ctx *ctx, const double *d_a, const double *d_b, in
   } else {
     int nl = 0;
     if (use_fast_k1(c, flags))
-      CU(launch_check_states_fast(c->rb_grid, c->gd, c->self, c->fast, d_a, d_b, num_points, S, flags, d_mask, st, &nl));
+      CU(launch_check_states_fast(c->rb_grid, c->gd, c->self, c->fast, d_a, d_b, num_points, S, flags, d_mask,
+                                  c->chain_specialization != 0, st, &nl));
     else
       CU(launch_check_states(c->rb_grid, c->gd, c->self, d_a, d_b, num_points, S, flags, d_mask,
                              c->fk_precision, st, &nl));

@@ -128,6 +128,24 @@ struct SelfDev {
   int n_pairs, n_as, n_blocks;
 };
 
+// packed fp32x2 (sm_100 FFMA2 / FADD2): two spheres per instruction; a plain float operand is broadcast (R.F32)
+__device__ __forceinline__ float2 f32x2_fma(float a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %2};\n\tmov.b64 rb, {%3, %4};\n\tmov.b64 rc, {%5, %6};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 f32x2_add(float2 a, float b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %4};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b));
+  return d;
+}
+
 // ---- launch helpers (defined in the .cu files) ---------------------------------------------------------
 struct Ctx;
 
@@ -146,7 +164,8 @@ cudaError_t launch_ft_build(const uint32_t *d_occ, int row_words, int gx, int gy
                             int *n_launch);
 cudaError_t launch_check_states_fast(const RobotDev &rb, const GridDev &gd, const SelfDev &self, const FastDev &fd,
                                      const double *d_q, const double *d_q_end, int num_points, int64_t S,
-                                     unsigned flags, uint32_t *d_mask, cudaStream_t st, int *n_launch);
+                                     unsigned flags, uint32_t *d_mask, bool allow_specialized, cudaStream_t st,
+                                     int *n_launch);
 cudaError_t launch_pack_rows(const uint32_t *d_bits_linear, int gx, int gy, int gz, int row_words, uint32_t *d_occ,
                              cudaStream_t st);
 

@@ -32,31 +32,15 @@ constexpr int KF_MIN_BLOCKS = KF_MIN_BLOCKS_DEF;
 constexpr float KF_MAGIC = 12582912.0f;          // 1.5 * 2^23: (x + MAGIC) has round-to-nearest-even(x) in its low mantissa bits
 constexpr unsigned KF_MAGIC_BITS = 0x4B400000u;  // bit pattern of MAGIC
 
-// packed fp32x2 (sm_100 FFMA2 / FADD2): two spheres per instruction; a plain float operand is broadcast (R.F32)
-__device__ __forceinline__ float2 kf_fma2(float a, float2 b, float2 c) {
-  float2 d;
-  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
-      "mov.b64 ra, {%2, %2};\n\tmov.b64 rb, {%3, %4};\n\tmov.b64 rc, {%5, %6};\n\t"
-      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-      : "=f"(d.x), "=f"(d.y) : "f"(a), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-  return d;
-}
-__device__ __forceinline__ float2 kf_add2(float2 a, float b) {
-  float2 d;
-  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
-      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %4};\n\t"
-      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b));
-  return d;
-}
-
 __device__ __forceinline__ float kf_gap(int o, float f) {   // gap between coordinate f in [0,1] of the own cell and the unit cube at offset o
   return o > 0 ? float(o) - f : (o < 0 ? f - float(o) - 1.0f : 0.0f);
 }
 
 // SELF keeps the group frames and the pair hierarchy live on top of the map state: 128 registers (4 CTAs/SM) avoid
 // the spills that cost it 12 % at 96; the map-only kernel is indifferent between 4 and 5 CTAs/SM (measured).
-template <bool EDGES, bool SELF>
+// SIG: compile-time chain signature (fk_device.cuh) — for the reference's robot every segment advance is straight-line
+// code reached through one warp-uniform switch instead of the per-segment interpreter.
+template <bool EDGES, bool SELF, typename SIG>
 __global__ void __launch_bounds__(KF_THREADS, SELF ? 4 : KF_MIN_BLOCKS)
 k1_fast(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd, const __grid_constant__ SelfDev self,
         const __grid_constant__ FastDev fd, const double *__restrict__ q_in, const double *__restrict__ q_end,
@@ -147,7 +131,20 @@ k1_fast(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd,
   bool hit = false;
   int qcount = 0;  // warp-uniform
   for (int sg = rb.ref_seg + 1; sg < rb.n_seg; ++sg) {
-    frame_advance_smem<double>(f, rb, sg, q_mine, KF_THREADS);
+    if constexpr (SIG::generic) {
+      frame_advance_smem<double>(f, rb, sg, q_mine, KF_THREADS);
+    } else {
+      switch (sg) {
+        case 0: frame_advance_sig<double, SIG, 0>(f, rb, q_mine, KF_THREADS); break;
+        case 1: frame_advance_sig<double, SIG, 1>(f, rb, q_mine, KF_THREADS); break;
+        case 2: frame_advance_sig<double, SIG, 2>(f, rb, q_mine, KF_THREADS); break;
+        case 3: frame_advance_sig<double, SIG, 3>(f, rb, q_mine, KF_THREADS); break;
+        case 4: frame_advance_sig<double, SIG, 4>(f, rb, q_mine, KF_THREADS); break;
+        case 5: frame_advance_sig<double, SIG, 5>(f, rb, q_mine, KF_THREADS); break;
+        case 6: frame_advance_sig<double, SIG, 6>(f, rb, q_mine, KF_THREADS); break;
+        default: frame_advance_sig<double, SIG, 7>(f, rb, q_mine, KF_THREADS); break;
+      }
+    }
     const int b = rb.seg_sph_end[sg + 1], e = rb.seg_sph_end[sg + 2];
     if (b == e) continue;
     // the group's frame rounded once to fp32, translation relative to the centre of the base's cell
@@ -182,10 +179,10 @@ k1_fast(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd,
         if (v < 2 || two) {
           const float4 A = slots4[i0 + 2 * v], B = slots4[i0 + 2 * v + 1];   // (x0 x1 y0 y1) (z0 z1 thr0 thr1)
           const float2 X = make_float2(A.x, A.y), Y = make_float2(A.z, A.w), Z = make_float2(B.x, B.y);
-          const float2 cx = kf_fma2(R[0], X, kf_fma2(R[1], Y, kf_fma2(R[2], Z, make_float2(pm[0], pm[0]))));
-          const float2 cy = kf_fma2(R[3], X, kf_fma2(R[4], Y, kf_fma2(R[5], Z, make_float2(pm[1], pm[1]))));
-          const float2 cz = kf_fma2(R[6], X, kf_fma2(R[7], Y, kf_fma2(R[8], Z, make_float2(pm[2], pm[2]))));
-          const float2 tx = kf_add2(cx, KF_MAGIC), ty = kf_add2(cy, KF_MAGIC), tz = kf_add2(cz, KF_MAGIC);
+          const float2 cx = f32x2_fma(R[0], X, f32x2_fma(R[1], Y, f32x2_fma(R[2], Z, make_float2(pm[0], pm[0]))));
+          const float2 cy = f32x2_fma(R[3], X, f32x2_fma(R[4], Y, f32x2_fma(R[5], Z, make_float2(pm[1], pm[1]))));
+          const float2 cz = f32x2_fma(R[6], X, f32x2_fma(R[7], Y, f32x2_fma(R[8], Z, make_float2(pm[2], pm[2]))));
+          const float2 tx = f32x2_add(cx, KF_MAGIC), ty = f32x2_add(cy, KF_MAGIC), tz = f32x2_add(cz, KF_MAGIC);
           const unsigned off0 = __float_as_uint(tz.x) * splane + __float_as_uint(ty.x) * sx + __float_as_uint(tx.x) + base_off;
           const unsigned off1 = __float_as_uint(tz.y) * splane + __float_as_uint(ty.y) * sx + __float_as_uint(tx.y) + base_off;
           lbv[2 * v] = int(lbp[off0]);
@@ -281,7 +278,8 @@ k1_fast(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd,
 
 cudaError_t launch_check_states_fast(const RobotDev &rb, const GridDev &gd, const SelfDev &self, const FastDev &fd,
                                      const double *d_q, const double *d_q_end, int num_points, int64_t S,
-                                     unsigned flags, uint32_t *d_mask, cudaStream_t st, int *n_launch) {
+                                     unsigned flags, uint32_t *d_mask, bool allow_specialized, cudaStream_t st,
+                                     int *n_launch) {
   const bool with_self = (flags & SQMP_CHECK_SELF) != 0;
   size_t smem = sizeof(WarpQueue) * (KF_THREADS / 32) + sizeof(double) * SQMP_DOF * KF_THREADS +
                 16 * size_t(fd.n_slots + (fd.n_slots + 1) / 2);   // FastPair: 16 B per slot; FastAux: 8 B per slot
@@ -294,12 +292,20 @@ cudaError_t launch_check_states_fast(const RobotDev &rb, const GridDev &gd, cons
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     kern<<<unsigned(blocks), KF_THREADS, smem, st>>>(rb, gd, self, fd, d_q, d_q_end, d_q_end ? num_points : 0, S, d_mask);
   };
-  if (d_q_end) {
-    if (with_self) go(k1_fast<true, true>);
-    else go(k1_fast<true, false>);
+  if (allow_specialized && chain_matches<SigRobotino>(rb)) {   // structure of the chain known at compile time (the reference's robot)
+    if (d_q_end) {
+      if (with_self) go(k1_fast<true, true, SigRobotino>);
+      else go(k1_fast<true, false, SigRobotino>);
+    } else {
+      if (with_self) go(k1_fast<false, true, SigRobotino>);
+      else go(k1_fast<false, false, SigRobotino>);
+    }
+  } else if (d_q_end) {
+    if (with_self) go(k1_fast<true, true, SigGeneric>);
+    else go(k1_fast<true, false, SigGeneric>);
   } else {
-    if (with_self) go(k1_fast<false, true>);
-    else go(k1_fast<false, false>);
+    if (with_self) go(k1_fast<false, true, SigGeneric>);
+    else go(k1_fast<false, false, SigGeneric>);
   }
   if (n_launch) *n_launch += 1;
   return cudaGetLastError();

@@ -236,6 +236,24 @@ def test_fast_kernel_is_bit_identical_to_generic_kernel(ctx, orc, fixture_data):
         ctx.set_disabled_links(0)
 
 
+def test_fast_kernel_chain_interpreter_equals_compile_time_chain(world_ctx):
+    """K1F walks the chain through the compile-time signature of the reference's robot when the description matches it
+    and through the per-segment interpreter otherwise: same frames, same masks."""
+    ctx, orc, w, origin = world_ctx
+    q = syn.state_batch(21 * 900 + 7, seed=71, xy_half=2.4)
+    ctx.set_option("k1_kernel", 2)
+    try:
+        for flags in (api.CHECK_MAP, api.CHECK_MAP | api.CHECK_SELF):
+            ctx.set_option("chain_specialization", 1)
+            a = ctx.check_states(q, flags)
+            ctx.set_option("chain_specialization", 0)
+            b = ctx.check_states(q, flags)
+            assert np.array_equal(a, b)
+    finally:
+        ctx.set_option("chain_specialization", 1)
+        ctx.set_option("k1_kernel", 0)
+
+
 def test_fast_kernel_rejected_without_its_preconditions(fixture_data):
     """k1_kernel = 2 is an error for a description whose base is not a translation-only run (no silent fallback)."""
     lt, fx, spheres = fixture_data
