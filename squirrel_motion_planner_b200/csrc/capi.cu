@@ -45,6 +45,7 @@ struct Ctx {
   double4 *d_fast_sph64 = nullptr;
   int fast_chain_ok = 0;        // description: translation-only base, then rotations only, spheres on the rotating part
   double reach_m = 0.0;         // max distance of a sphere centre from the base reference point (metres)
+  int launch_overlap = 1;       // K1F grids may start while the previous grid of the stream drains its last wave (PDL)
   int k1_kernel = 0;            // 0 auto (fast when its preconditions hold) | 1 generic | 2 fast (error if not possible)
   TreeDev trees[SQMP_MAX_TREES];
   NNScratch nn;
@@ -707,6 +708,8 @@ int sqmp_set_option(sqmp_ctx *ctx, const char *name, int64_t value) {
     if (value < 0 || value > 2) return fail(c, SQMP_ERR_INVALID, "k1_kernel must be 0 (auto), 1 (generic) or 2 (fast)");
     if (value == 2 && !c->fast_chain_ok) return fail(c, SQMP_ERR_INVALID, "fast validity kernel needs a translation-only base followed by rotations");
     c->k1_kernel = int(value);
+  } else if (n == "launch_overlap") {
+    c->launch_overlap = value != 0;
   } else if (n == "chain_specialization") {
     c->chain_specialization = value != 0;
   } else if (n == "nn_variant") {
@@ -836,7 +839,7 @@ int sqmp_check_states_dev(sqmp_ctx *ctx, const double *d_q, int64_t S, unsigned 
   int nl = 0;
   if (use_fast_k1(c, flags))
     CU(launch_check_states_fast(c->rb_grid, c->gd, c->self, c->fast, d_q, nullptr, 0, S, flags, d_mask,
-                                c->chain_specialization != 0, st, &nl));
+                                c->chain_specialization != 0, c->launch_overlap != 0, st, &nl));
   else
     CU(launch_check_states(c->rb_grid, c->gd, c->self, d_q, nullptr, 0, S, flags, d_mask, c->fk_precision,
                            st, &nl));
@@ -859,7 +862,7 @@ int sqmp_check_edges_dev(sqmp_ctx *ctx, const double *d_a, const double *d_b, in
     int nl = 0;
     if (use_fast_k1(c, flags))
       CU(launch_check_states_fast(c->rb_grid, c->gd, c->self, c->fast, d_a, d_b, num_points, S, flags, d_mask,
-                                  c->chain_specialization != 0, st, &nl));
+                                  c->chain_specialization != 0, c->launch_overlap != 0, st, &nl));
     else
       CU(launch_check_states(c->rb_grid, c->gd, c->self, d_a, d_b, num_points, S, flags, d_mask,
                              c->fk_precision, st, &nl));

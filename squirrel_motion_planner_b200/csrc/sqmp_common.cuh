@@ -164,8 +164,8 @@ cudaError_t launch_ft_build(const uint32_t *d_occ, int row_words, int gx, int gy
                             int *n_launch);
 cudaError_t launch_check_states_fast(const RobotDev &rb, const GridDev &gd, const SelfDev &self, const FastDev &fd,
                                      const double *d_q, const double *d_q_end, int num_points, int64_t S,
-                                     unsigned flags, uint32_t *d_mask, bool allow_specialized, cudaStream_t st,
-                                     int *n_launch);
+                                     unsigned flags, uint32_t *d_mask, bool allow_specialized, bool overlap,
+                                     cudaStream_t st, int *n_launch);
 cudaError_t launch_pack_rows(const uint32_t *d_bits_linear, int gx, int gy, int gz, int row_words, uint32_t *d_occ,
                              cudaStream_t st);
 

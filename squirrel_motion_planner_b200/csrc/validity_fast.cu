@@ -60,6 +60,10 @@ k1_fast(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd,
   const bool active = s < S;
   const int64_t sl = active ? s : S - 1;  // idle lanes of the last warp shadow the last state (lockstep loops)
 
+  // let the next grid of the stream be scheduled as soon as every CTA of this one has started: its first wave then
+  // fills the SM slots this grid's last wave leaves idle (one CTA lifetime, ~36 us of a 2^20-state launch)
+  asm volatile("griddepcontrol.launch_dependents;");
+
   // ---- slot tables -> shared memory (16 + 8 bytes per slot) ----
   {
     const float4 *src = reinterpret_cast<const float4 *>(fd.pairs);
@@ -273,13 +277,18 @@ k1_fast(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd,
     hit = rb.self_const_collision || self_collision(blocks_s, self.n_blocks, as_s, self.hpairs, f_mine, KF_THREADS);
 
   const unsigned word = __ballot_sync(FULL, hit && active);
+  // Programmatic dependent launch: this grid may have started while the previous grid of the stream was still
+  // draining its last wave (see the launcher).  It reads nothing a predecessor writes; its ONLY write is the mask, so
+  // waiting here — until every prerequisite grid has completed and flushed — keeps back-to-back calls that reuse one
+  // mask buffer equivalent to serial execution.  (A no-op when the grid was launched without the attribute.)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (lane == 0 && s < ((S + 31) & ~int64_t(31))) mask_out[s >> 5] = word;
 }
 
 cudaError_t launch_check_states_fast(const RobotDev &rb, const GridDev &gd, const SelfDev &self, const FastDev &fd,
                                      const double *d_q, const double *d_q_end, int num_points, int64_t S,
-                                     unsigned flags, uint32_t *d_mask, bool allow_specialized, cudaStream_t st,
-                                     int *n_launch) {
+                                     unsigned flags, uint32_t *d_mask, bool allow_specialized, bool overlap,
+                                     cudaStream_t st, int *n_launch) {
   const bool with_self = (flags & SQMP_CHECK_SELF) != 0;
   size_t smem = sizeof(WarpQueue) * (KF_THREADS / 32) + sizeof(double) * SQMP_DOF * KF_THREADS +
                 16 * size_t(fd.n_slots + (fd.n_slots + 1) / 2);   // FastPair: 16 B per slot; FastAux: 8 B per slot
@@ -288,9 +297,20 @@ cudaError_t launch_check_states_fast(const RobotDev &rb, const GridDev &gd, cons
   const int64_t blocks = (S + KF_THREADS - 1) / KF_THREADS;
   if (blocks <= 0) return cudaSuccess;
   if (blocks > 0x7fffffff) return cudaErrorInvalidValue;
+  cudaError_t err = cudaSuccess;
   auto go = [&](auto kern) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    kern<<<unsigned(blocks), KF_THREADS, smem, st>>>(rb, gd, self, fd, d_q, d_q_end, d_q_end ? num_points : 0, S, d_mask);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(blocks));
+    cfg.blockDim = dim3(KF_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // may overlap the tail of the preceding grid
+    attr[0].val.programmaticStreamSerializationAllowed = overlap ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    err = cudaLaunchKernelEx(&cfg, kern, rb, gd, self, fd, d_q, d_q_end, d_q_end ? num_points : 0, S, d_mask);
   };
   if (allow_specialized && chain_matches<SigRobotino>(rb)) {   // structure of the chain known at compile time (the reference's robot)
     if (d_q_end) {
@@ -308,7 +328,7 @@ cudaError_t launch_check_states_fast(const RobotDev &rb, const GridDev &gd, cons
     else go(k1_fast<false, false, SigGeneric>);
   }
   if (n_launch) *n_launch += 1;
-  return cudaGetLastError();
+  return err != cudaSuccess ? err : cudaGetLastError();
 }
 
 }  // namespace sqmp

@@ -254,6 +254,28 @@ def test_fast_kernel_chain_interpreter_equals_compile_time_chain(world_ctx):
         ctx.set_option("k1_kernel", 0)
 
 
+def test_back_to_back_launches_keep_serial_semantics(world_ctx):
+    """K1F grids are launched with programmatic stream serialization: a grid may start while its predecessor drains,
+    but it writes its mask only after the predecessor has completed.  Calls that reuse ONE mask buffer with no
+    synchronisation in between must therefore leave the result of the last call — for one-wave and multi-wave grids."""
+    import torch
+    ctx, orc, w, origin = world_ctx
+    stream = torch.cuda.current_stream().cuda_stream
+    for S in (1 << 11, 1 << 15, 1 << 18):
+        d_q = [torch.from_numpy(syn.state_batch(S, seed=200 + i, xy_half=2.2)).cuda() for i in range(4)]
+        d_m = torch.zeros(S // 32, dtype=torch.int32, device="cuda")
+        want = [ctx.check_states(q.cpu().numpy(), api.CHECK_MAP).view(np.int32) for q in d_q]
+        for overlap in (1, 0):
+            ctx.set_option("launch_overlap", overlap)
+            for trial in range(6):
+                order = np.random.default_rng(trial).permutation(4)
+                for i in order:
+                    ctx.check_states_dev(d_q[i], S, api.CHECK_MAP, d_m, stream)
+                torch.cuda.synchronize()
+                assert np.array_equal(d_m.cpu().numpy(), want[order[-1]])
+    ctx.set_option("launch_overlap", 1)
+
+
 def test_fast_kernel_rejected_without_its_preconditions(fixture_data):
     """k1_kernel = 2 is an error for a description whose base is not a translation-only run (no silent fallback)."""
     lt, fx, spheres = fixture_data
