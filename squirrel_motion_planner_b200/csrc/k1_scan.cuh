@@ -106,6 +106,9 @@ __device__ __forceinline__ bool scan_rows_filtered(const GridDev &g, double ux, 
         const int i1 = min(cx + __float2int_rd(fx + w), g.gx - 1);
         if (i0 <= i1) {   // window of <= 2 * 14 + 1 bits: two adjacent words (the row has a pad word), one funnel shift
           const uint32_t *p = g.occ + (ridx + unsigned(i0 >> 5));
+#ifdef SQMP_BOUNDS_CHECK   // debug builds only: the row word (and its right neighbour) must lie inside the occupancy rows
+          if (kq < 0 || kq >= g.gz || j0 + jq < 0 || j0 + jq >= g.gy || (i0 >> 5) + 1 >= g.row_words) __trap();
+#endif
           const int sh = i0 & 31, width = i1 - i0 + 1;
           w0[n] = p[0];
           if (sh + width > 32) w1[n] = p[1];

@@ -189,6 +189,9 @@ k1_fast(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd,
           const float2 tx = f32x2_add(cx, KF_MAGIC), ty = f32x2_add(cy, KF_MAGIC), tz = f32x2_add(cz, KF_MAGIC);
           const unsigned off0 = __float_as_uint(tz.x) * splane + __float_as_uint(ty.x) * sx + __float_as_uint(tx.x) + base_off;
           const unsigned off1 = __float_as_uint(tz.y) * splane + __float_as_uint(ty.y) * sx + __float_as_uint(tx.y) + base_off;
+#ifdef SQMP_BOUNDS_CHECK   // debug builds only (tools/build_variant.sh): every gather must stay inside the padded field
+          if (off0 > gd.zero_off || off1 > gd.zero_off) __trap();
+#endif
           lbv[2 * v] = int(lbp[off0]);
           lbv[2 * v + 1] = int(lbp[off1]);
           thr[2 * v] = __float_as_int(B.z);
@@ -226,6 +229,9 @@ k1_fast(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd,
             const float cz = fmaf(R[6], a.x, fmaf(R[7], a.y, fmaf(R[8], a.z, pm[2])));
             const float tx = cx + KF_MAGIC, ty = cy + KF_MAGIC, tz = cz + KF_MAGIC;
             const unsigned off = __float_as_uint(tz) * splane + __float_as_uint(ty) * sx + __float_as_uint(tx) + base_off;
+#ifdef SQMP_BOUNDS_CHECK
+            if (off >= gd.zero_off) __trap();
+#endif
             const unsigned v = gd.ft_base[off];
             // position inside the own cell, in [0,1]: (c - n) is exact, c + 0.5 is the centre estimate
             const float fx = (cx - (tx - KF_MAGIC)) + 0.5f, fy = (cy - (ty - KF_MAGIC)) + 0.5f, fz = (cz - (tz - KF_MAGIC)) + 0.5f;
