@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the state-validity hot path (BASELINE.json configs[1]).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload config2|config4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload config2|config3|config4|config5]
 
 One "step" = one pass of the fused FK + collision kernel (K1) over one batch of 2^20 interpolated 8-DOF
 states against the resident 256^3 voxel world W256, map check on.  With N > 1 (torchrun,
@@ -385,6 +385,91 @@ def side_metrics(ctx, torch, dev, stream, d_q, S):
     return out
 
 
+def run_config3(args):
+    """BASELINE.json configs[2]: near-neighbour search over a 2^20-node tree with 2^16 queries.  Multi-GPU per SURVEY.md
+    §8e: the tree is replicated, the queries are sharded, the ids are all-gathered (strong scaling).  A step = nearest
+    (K3) + radius / top-k (K4) for every query of the rank's shard."""
+    import torch
+    import torch.distributed as dist
+    from squirrel_motion_planner_b200 import api, synthetic as syn
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world_size > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = api.default_context(local_rank)
+    N, Q, K = 1 << 20, 1 << 16, 20
+    nodes, cost = syn.random_tree(N, 7, 9)
+    ctx.tree_reset(0)
+    ctx.tree_append_batch(0, nodes, cost)
+    q_rank = Q // world_size
+    d_qs = torch.from_numpy(syn.sample_configs(Q, 8)[rank * q_rank:(rank + 1) * q_rank]).to(dev)
+    d_all = torch.zeros(Q, dtype=torch.int32, device=dev)
+    d_ids = d_all[rank * q_rank:(rank + 1) * q_rank]
+    d_low = torch.empty((q_rank, K), dtype=torch.int32, device=dev)
+    d_high = torch.empty_like(d_low)
+    d_cnt = torch.empty(q_rank, dtype=torch.int32, device=dev)
+    d_ov = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def step():
+        ctx.nn_nearest_dev(0, d_qs, q_rank, d_ids, stream)
+        ctx.nn_radius_dev(0, d_qs, None, q_rank, 1.5, K, d_low, d_high, d_cnt, d_ov, stream)
+        if world_size > 1:
+            dist.all_gather_into_tensor(d_all, d_ids)
+
+    steps, warm = max(1, min(args.steps, 10)), max(3, min(args.warmup, 3))
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    if world_size > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    l0 = ctx.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world_size > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    total_ms = e0.elapsed_time(e1)
+    launches = ctx.kernel_launches - l0
+    if world_size > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        ms = total_ms / steps
+        algo = N * (64 + 72) + Q * (64 + 68) + Q * (4 + (2 * K + 1) * 4)      # SURVEY.md §8d rows K3 + K4
+        print(json.dumps({
+            "metric": "near-neighbour queries/sec (nearest + radius/top-k per query)", "value": Q / (ms * 1e-3),
+            "unit": "queries/s", "n_gpus": world_size, "steps": steps, "warmup": warm, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config3: N=2^20-node tree (replicated), Q=2^16 queries sharded over %d GPU(s), nearest + radius r=1.5 k=20, "
+                                   "ids all-gathered" % world_size,
+                       "l2": "the 72 MiB tree (+36 MiB fp32 shadow) is L2-resident by design and re-read by every query tile"},
+            "pairs_per_s": 2.0 * N * Q / (ms * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": algo / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "k_nn_qt_pf<false> + k_nn_qt_pf<true> (fp32 pre-filter, fp64 exact)", "kernel_ms": ms,
+                         "note": "compute-bound scan (FMA pipe / shared-memory pipe ~60 %): the HBM fraction is tiny by construction"},
+            "gpu_launches": int(launches), "clocks": sampler.summary()}))
+    ctx.close()
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
 def run_config5(args):
     """BASELINE.json configs[4]: independent planning queries in a cluttered 512^3 scene, one query stream per GPU, no
     collective.  Each rank runs the C++ planner front-end (shim/sqmp_plan, GPU backend) over its share of the queries
@@ -481,7 +566,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--workload", default="config2", choices=["config2", "config4", "config5"])
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5"])
     ap.add_argument("--queries", type=int, default=1024, help="config5: number of planning queries")
     ap.add_argument("--iterations", type=int, default=1000, help="config5: BiRRT* iterations per query")
     ap.add_argument("--no-extra", action="store_true")
@@ -491,6 +576,8 @@ def main():
         run_reference(args)
     elif args.workload == "config5":
         run_config5(args)
+    elif args.workload == "config3":
+        run_config3(args)
     else:
         run_own(args)
 

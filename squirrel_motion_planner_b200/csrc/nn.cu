@@ -271,7 +271,10 @@ k_nn_wq(TreePtrs t, int64_t N, int64_t chunk_len, int chunks, const double *__re
 // the band in between is evaluated in fp64.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int NN_GROUP = 4;        // nodes whose estimates are taken before the one (rare) branch
-constexpr int NN_QPT = 2;          // queries per thread: the three LDS of a node are shared by both
+#ifndef NN_QPT_DEF
+#define NN_QPT_DEF 2
+#endif
+constexpr int NN_QPT = NN_QPT_DEF;  // queries per thread (even): the three LDS of a node are shared by all of them
 constexpr double NN_U = 1.1920928955078125e-07;   // 2^-23
 
 // The estimates of the thread's TWO queries against one node, on the packed fp32x2 pipe (FFMA2: the node coordinate is
@@ -279,7 +282,7 @@ constexpr double NN_U = 1.1920928955078125e-07;   // 2^-23
 // 16 FFMA + 2 FADD.  Per lane each operation is the same IEEE fma in the same order as the scalar form, so the
 // estimates — and the error bound above — are unchanged.  The 3-register FFMA issues every other cycle per scheduler
 // on this part; the scan was at ~89 % of that rate.
-static_assert(NN_QPT == 2, "estimate_s2 packs the two queries of a thread");
+static_assert(NN_QPT % 2 == 0, "estimate_s2 packs the queries of a thread in pairs");
 __device__ __forceinline__ float2 estimate_s2(const float2 (&m2q)[SQMP_DOF], float2 qq, const float4 a, const float4 b, float nn) {
   float2 s = f32x2_add(qq, nn);
   s = f32x2_fma(a.x, m2q[0], s); s = f32x2_fma(a.y, m2q[1], s); s = f32x2_fma(a.z, m2q[2], s); s = f32x2_fma(a.w, m2q[3], s);
@@ -305,7 +308,7 @@ k_nn_qt_pf(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ 
   __shared__ __align__(16) float tile[NN_TILE][12];   // per node: q0..q7, |n|^2, pad — one base register, immediates
   int64_t qi[NN_QPT];
   bool active[NN_QPT];
-  float2 m2q[SQMP_DOF], qq2;   // .x: the thread's first query, .y: its second
+  float2 m2q[NN_QPT / 2][SQMP_DOF], qq2[NN_QPT / 2];   // pair p: .x = query 2p of the thread, .y = query 2p + 1
   float qq[NN_QPT];
   float thr_lo[NN_QPT];   // nearest: s~ >= thr_lo cannot win.  radius: s~ < thr_lo is a proven hit
   float thr_hi[NN_QPT];   // radius: s~ >= thr_hi is a proven miss
@@ -322,14 +325,14 @@ k_nn_qt_pf(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ 
     for (int d = 0; d < SQMP_DOF; ++d) {
       const double v = qp[d];
       const float f = __double2float_rn(v);
-      if (k == 0) m2q[d].x = -2.0f * f;
-      else m2q[d].y = -2.0f * f;
+      if ((k & 1) == 0) m2q[k / 2][d].x = -2.0f * f;
+      else m2q[k / 2][d].y = -2.0f * f;
       qn2 += v * v;
       qq_d += double(f) * double(f);
     }
     qq[k] = __double2float_rn(qq_d);
-    if (k == 0) qq2.x = qq[k];
-    else qq2.y = qq[k];
+    if ((k & 1) == 0) qq2[k / 2].x = qq[k];
+    else qq2[k / 2].y = qq[k];
     const double R2 = fmax(rmax2, qn2) * 1.000001;
     eR[k] = 4.0 * NN_U * sqrt(R2);
     eR2[k] = 64.0 * NN_U * R2;
@@ -371,9 +374,12 @@ k_nn_qt_pf(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ 
         const float4 a = *reinterpret_cast<const float4 *>(&tile[i0 + u][0]);   // broadcast reads
         const float4 b = *reinterpret_cast<const float4 *>(&tile[i0 + u][4]);
         const float nn = tile[i0 + u][8];
-        const float2 s2 = estimate_s2(m2q, qq2, a, b, nn);
-        se[u][0] = s2.x;
-        se[u][1] = s2.y;
+#pragma unroll
+        for (int p = 0; p < NN_QPT / 2; ++p) {
+          const float2 s2 = estimate_s2(m2q[p], qq2[p], a, b, nn);
+          se[u][2 * p] = s2.x;
+          se[u][2 * p + 1] = s2.y;
+        }
 #pragma unroll
         for (int k = 0; k < NN_QPT; ++k) any = any || (se[u][k] < (RADIUS ? thr_hi[k] : thr_lo[k]));
       }
