@@ -516,8 +516,13 @@ def run_config5(args):
     first, count = rank * per, max(0, min(per, n_queries - rank * per))
     if world_size > 1:
         dist.barrier()
-    r = subprocess.run([os.path.join(shim, "sqmp_plan"), desc, d, "gpu", str(iters), "1", str(local_rank), str(first), str(count)],
-                       capture_output=True, text=True)
+    # the rank's stream of queries runs `--batch` at a time in lock step (shim/sqmp_multi.hpp: one library call per request
+    # kind and round for the whole batch); --batch 1 is the strictly sequential runner (one query in flight per GPU)
+    if args.batch > 1:
+        cmd = [os.path.join(shim, "sqmp_plan_multi"), desc, d, "gpu", str(iters), "1", str(local_rank), str(first), str(count), str(args.batch)]
+    else:
+        cmd = [os.path.join(shim, "sqmp_plan"), desc, d, "gpu", str(iters), "1", str(local_rank), str(first), str(count)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("sqmp_plan failed: " + r.stderr[-500:])
     tail = [l for l in r.stdout.splitlines() if l.startswith("# queries")][-1].split()
@@ -553,7 +558,7 @@ def run_config5(args):
             "unit": "planning queries/s", "n_gpus": world_size, "steps": 1, "warmup": 0, "ms_per_step": secs * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "config5: %d independent planning queries, W512 (512^3 voxels, 2048 boxes), one query stream per GPU, no collective" % n_queries,
-                       "iterations_per_query": iters, "flags": "SELF|MAP"},
+                       "iterations_per_query": iters, "flags": "SELF|MAP", "queries_in_flight_per_gpu": max(1, args.batch)},
             "checked_states_per_s": float(agg[1]) / secs, "planner_iterations_per_s": float(agg[2]) / secs,
             "solved": int(agg[3]), "cpu_baseline": cpu, "gpu_launches": None}))
     if world_size > 1:
@@ -569,6 +574,7 @@ def main():
     ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5"])
     ap.add_argument("--queries", type=int, default=1024, help="config5: number of planning queries")
     ap.add_argument("--iterations", type=int, default=1000, help="config5: BiRRT* iterations per query")
+    ap.add_argument("--batch", type=int, default=128, help="config5: queries in flight per GPU (1 = sequential runner)")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -30,7 +30,7 @@ extern "C" {
 #define SQMP_MAX_SEG 8
 #define SQMP_MAX_SPHERES 128
 #define SQMP_MAX_PAIRS 4096
-#define SQMP_MAX_TREES 8
+#define SQMP_MAX_TREES 1024   /* two per concurrent planning query (shim/sqmp_multi.hpp) */
 
 #define SQMP_JOINT_ROT 1
 #define SQMP_JOINT_TRANS 2
@@ -147,6 +147,13 @@ int sqmp_nn_nearest(sqmp_ctx *ctx, int tree, const double *queries, int64_t Q, i
  * count_out[q]: number of near vertices.  exclude_id may be NULL (no exclusion). */
 int sqmp_nn_radius(sqmp_ctx *ctx, int tree, const double *queries, const int32_t *exclude_id, int64_t Q, double r,
                    int k, int32_t *low_ids, int32_t *high_ids, int32_t *count_out);
+
+/* Many queries, each against ITS OWN tree (query i searches tree[i]) — the call shape of the lock-step multi-query
+ * planner (shim/sqmp_multi.hpp), where every planning query of a batch owns two small trees.  Same semantics and the
+ * same bit-exact results as Q single calls of sqmp_nn_nearest / sqmp_nn_radius; one launch per call. */
+int sqmp_nn_nearest_multi(sqmp_ctx *ctx, const int32_t *tree, const double *queries, int64_t Q, int32_t *id_out);
+int sqmp_nn_radius_multi(sqmp_ctx *ctx, const int32_t *tree, const double *queries, const int32_t *exclude_id, int64_t Q,
+                         double r, int k, int32_t *low_ids, int32_t *high_ids, int32_t *count_out);
 
 /* ---- device-pointer variants (benchmark harness, multi-GPU sharding) ---------------------------- */
 /* Same semantics; all pointers are device pointers on the context's GPU; work is enqueued on `stream`

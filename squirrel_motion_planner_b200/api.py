@@ -19,13 +19,14 @@ LIB_PATH = os.environ.get("SQMP_B200_LIB") or os.path.join(_HERE, "libsqmp_b200.
 DOF = 8
 CHECK_SELF, CHECK_MAP = 1, 2
 MAX_SEG, MAX_SPHERES = 8, 128
+MAX_TREES = 1024
 
 EXPORTS = [
     "sqmp_create", "sqmp_destroy", "sqmp_last_error", "sqmp_strerror", "sqmp_version", "sqmp_set_voxel_grid",
     "sqmp_set_disabled_links", "sqmp_check_states", "sqmp_check_edges", "sqmp_get_collisions", "sqmp_fk",
     "sqmp_tree_reset", "sqmp_tree_append", "sqmp_tree_append_batch", "sqmp_tree_update", "sqmp_tree_update_costs",
     "sqmp_tree_size", "sqmp_nn_nearest", "sqmp_nn_radius", "sqmp_check_states_dev", "sqmp_check_edges_dev",
-    "sqmp_fk_dev", "sqmp_sample_configs", "sqmp_sample_configs_dev", "sqmp_nn_nearest_dev", "sqmp_nn_radius_dev", "sqmp_kernel_launches", "sqmp_set_option",
+    "sqmp_fk_dev", "sqmp_sample_configs", "sqmp_sample_configs_dev", "sqmp_nn_nearest_multi", "sqmp_nn_radius_multi", "sqmp_nn_nearest_dev", "sqmp_nn_radius_dev", "sqmp_kernel_launches", "sqmp_set_option",
 ]
 
 
@@ -95,6 +96,8 @@ def load_library():
     L.sqmp_check_states_dev.argtypes = [vp, vp, i64, C.c_uint, vp, vp]
     L.sqmp_check_edges_dev.argtypes = [vp, vp, vp, i64, C.c_int, C.c_uint, vp, vp, vp]
     L.sqmp_fk_dev.argtypes = [vp, vp, i64, vp, vp]
+    L.sqmp_nn_nearest_multi.argtypes = [vp, vp, vp, i64, vp]
+    L.sqmp_nn_radius_multi.argtypes = [vp, vp, vp, vp, i64, C.c_double, C.c_int, vp, vp, vp]
     L.sqmp_sample_configs.argtypes = [vp, C.c_uint64, i64, i64, dp, dp, C.c_int, vp, vp]
     L.sqmp_sample_configs_dev.argtypes = [vp, C.c_uint64, i64, i64, dp, dp, C.c_int, vp, vp, vp]
     L.sqmp_nn_nearest_dev.argtypes = [vp, C.c_int, vp, i64, vp, vp]
@@ -233,6 +236,25 @@ class Context:
         out = np.empty((q.shape[0], 7), dtype=np.float64)
         self._ck(self._L.sqmp_fk(self._h, _ptr(q), q.shape[0], _ptr(out)))
         return out
+
+    def nn_nearest_multi(self, trees, queries):
+        """Query i against tree trees[i] (sqmp_nn_nearest_multi)."""
+        q = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, DOF)
+        t = np.ascontiguousarray(trees, dtype=np.int32).reshape(-1)
+        ids = np.empty(q.shape[0], dtype=np.int32)
+        self._ck(self._L.sqmp_nn_nearest_multi(self._h, _ptr(t), _ptr(q), q.shape[0], _ptr(ids)))
+        return ids
+
+    def nn_radius_multi(self, trees, queries, exclude, r, k):
+        q = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, DOF)
+        t = np.ascontiguousarray(trees, dtype=np.int32).reshape(-1)
+        ex = None if exclude is None else np.ascontiguousarray(exclude, dtype=np.int32).reshape(-1)
+        low = np.empty((q.shape[0], k), dtype=np.int32)
+        high = np.empty((q.shape[0], k), dtype=np.int32)
+        cnt = np.empty(q.shape[0], dtype=np.int32)
+        self._ck(self._L.sqmp_nn_radius_multi(self._h, _ptr(t), _ptr(q), _ptr(ex), q.shape[0], float(r), int(k),
+                                              _ptr(low), _ptr(high), _ptr(cnt)))
+        return low, high, cnt
 
     def sample_configs(self, seed, first, n, lo, hi, max_tries=64):
         """sampleJointConfig_JntArray (BS:3832-3878) batched on the device: (q[n,8], tries[n])."""

@@ -54,6 +54,7 @@ struct Ctx {
   // low-latency path of the planner-shaped calls (one query, a few edges): mapped pinned host memory the kernels
   // read their inputs from and write their answers to — no cudaMemcpy on either side of the launch
   unsigned char *pin_h = nullptr, *pin_d = nullptr;
+  unsigned char *pin2_h = nullptr, *pin2_d = nullptr;   // mapped pinned staging of the multi-tree NN calls (lazy)
   unsigned *d_ticket = nullptr;     // [0] ticket, [1] hit counter of k_nn_single
   bool tree_writes_pending = false; // unsynchronised single-node writes are in flight on streams[0]
   int64_t small_call_states = 4096; // validity calls up to this many states take the low-latency path
@@ -688,6 +689,7 @@ void sqmp_destroy(sqmp_ctx *ctx) {
   for (auto &b : ctx->scratch)
     if (b.p) cudaFree(b.p);
   if (ctx->pin_h) cudaFreeHost(ctx->pin_h);
+  if (ctx->pin2_h) cudaFreeHost(ctx->pin2_h);
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
   for (auto &s : ctx->streams)
     if (s) cudaStreamDestroy(s);
@@ -1291,3 +1293,79 @@ int sqmp_nn_radius(sqmp_ctx *ctx, int tree, const double *queries, const int32_t
 }
 
 }  // extern "C"
+
+// ---- every query against its own tree (k_nn_multi) -------------------------------------------------------------
+constexpr int64_t MULTI_MAX_Q = 1024;   // queries per launch; larger calls are split
+constexpr int MULTI_MAX_K = 64;
+static int nn_multi_range(Ctx *c, const int32_t *tree, const double *queries, const int32_t *exclude, int64_t nq,
+                          bool radius, double r, int k, int32_t *out_ids, int32_t *low, int32_t *high, int32_t *count) {
+  const size_t desc_b = nn_multi_desc_bytes();
+  const size_t off_q = size_t(MULTI_MAX_Q) * desc_b, off_out = off_q + size_t(MULTI_MAX_Q) * SQMP_DOF * 8;
+  const size_t total = off_out + size_t(MULTI_MAX_Q) * (2 * MULTI_MAX_K + 2) * 4;
+  if (!c->pin2_h) {
+    CU(cudaHostAlloc((void **)&c->pin2_h, total, cudaHostAllocMapped));
+    CU(cudaHostGetDevicePointer((void **)&c->pin2_d, c->pin2_h, 0));
+  }
+  int64_t nmax = 1;
+  for (int64_t i = 0; i < nq; ++i) {
+    if (tree[i] < 0 || tree[i] >= SQMP_MAX_TREES) return fail(c, SQMP_ERR_INVALID, "nn_multi: bad tree index");
+    const TreeDev &t = c->trees[tree[i]];
+    nn_multi_fill_desc(c->pin2_h + size_t(i) * desc_b, t, (radius && exclude) ? exclude[i] : -1);
+    if (t.n > nmax) nmax = t.n;
+  }
+  std::memcpy(c->pin2_h + off_q, queries, size_t(nq) * SQMP_DOF * 8);
+  if (radius) {
+    int rc = nn_prepare(c, nq, 1, true, nmax);
+    if (rc) return rc;
+  }
+  int32_t *d_out = (int32_t *)(c->pin2_d + off_out);
+  CU(launch_nn_multi(c->pin2_d, (const double *)(c->pin2_d + off_q), nq, radius, radius ? sumsq_threshold(r) : 0.0, k,
+                     c->nn, d_out, c->streams[0]));
+  c->launches += 1;
+  CU(cudaStreamSynchronize(c->streams[0]));
+  const volatile int32_t *res = (volatile int32_t *)(c->pin2_h + off_out);
+  if (!radius) {
+    for (int64_t i = 0; i < nq; ++i) out_ids[i] = res[i];
+    return SQMP_OK;
+  }
+  for (int64_t i = 0; i < nq; ++i) {
+    const volatile int32_t *o = res + i * (2 * k + 2);
+    if (o[1]) {   // this query's hits overflowed its slice of the pool: the single-tree path holds the whole tree
+      int rc = sqmp_nn_radius(static_cast<sqmp_ctx *>(c), tree[i], queries + i * SQMP_DOF, exclude ? exclude + i : nullptr, 1,
+                              r, k, low + i * k, high + i * k, count + i);
+      if (rc) return rc;
+      continue;
+    }
+    count[i] = o[0];
+    for (int j = 0; j < k; ++j) {
+      low[i * k + j] = o[2 + j];
+      high[i * k + j] = o[2 + k + j];
+    }
+  }
+  return SQMP_OK;
+}
+
+int sqmp_nn_nearest_multi(sqmp_ctx *ctx, const int32_t *tree, const double *queries, int64_t Q, int32_t *id_out) {
+  CHECK_CTX();
+  if (Q < 0 || (Q > 0 && (!tree || !queries || !id_out))) return fail(c, SQMP_ERR_INVALID, "nn_nearest_multi: null pointer");
+  for (int64_t q0 = 0; q0 < Q; q0 += MULTI_MAX_Q) {
+    const int64_t nq = Q - q0 < MULTI_MAX_Q ? Q - q0 : MULTI_MAX_Q;
+    int rc = nn_multi_range(c, tree + q0, queries + q0 * SQMP_DOF, nullptr, nq, false, 0.0, 0, id_out + q0, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+  }
+  return SQMP_OK;
+}
+
+int sqmp_nn_radius_multi(sqmp_ctx *ctx, const int32_t *tree, const double *queries, const int32_t *exclude_id, int64_t Q,
+                         double r, int k, int32_t *low_ids, int32_t *high_ids, int32_t *count_out) {
+  CHECK_CTX();
+  if (Q < 0 || k < 1 || k > MULTI_MAX_K || (Q > 0 && (!tree || !queries || !low_ids || !high_ids || !count_out)))
+    return fail(c, SQMP_ERR_INVALID, "nn_radius_multi: bad argument");
+  for (int64_t q0 = 0; q0 < Q; q0 += MULTI_MAX_Q) {
+    const int64_t nq = Q - q0 < MULTI_MAX_Q ? Q - q0 : MULTI_MAX_Q;
+    int rc = nn_multi_range(c, tree + q0, queries + q0 * SQMP_DOF, exclude_id ? exclude_id + q0 : nullptr, nq, true, r, k,
+                            nullptr, low_ids + q0 * k, high_ids + q0 * k, count_out + q0);
+    if (rc) return rc;
+  }
+  return SQMP_OK;
+}

@@ -464,19 +464,9 @@ __device__ __forceinline__ Key warp_max_key(Key v) {
   return v;
 }
 
-__global__ void __launch_bounds__(NN_THREADS)
-k_nn_topk(const double *__restrict__ cost, const int32_t *__restrict__ hits, int64_t hit_cap,
-          const int32_t *__restrict__ count, int64_t Q, int k, int32_t *__restrict__ low, int32_t *__restrict__ high,
-          int32_t *__restrict__ overflow) {
-  const int lane = threadIdx.x & 31;
-  const int64_t qi = int64_t(blockIdx.x) * (NN_THREADS / 32) + (threadIdx.x >> 5);
-  if (qi >= Q) return;
-  const int32_t total = count[qi];
-  if (total > hit_cap) {
-    if (lane == 0) atomicExch(overflow, 1);
-  }
-  const int32_t m = int32_t(imin64(total, hit_cap));
-  const int32_t *h = hits + qi * hit_cap;
+// one warp: the k lowest and the k highest (cost, id) of the m hits h[0..m) -> low[0..k), high[0..k) (-1 padded)
+__device__ __forceinline__ void warp_topk(const double *__restrict__ cost, const int32_t *__restrict__ h, int32_t m, int k,
+                                          int32_t *__restrict__ low, int32_t *__restrict__ high, int lane) {
   const Key kmax = {CUDART_INF, 0x7fffffff}, kmin = {-CUDART_INF, -1};
   Key last = kmin;
   for (int tsel = 0; tsel < k; ++tsel) {   // t-th lowest = smallest key strictly above the previous pick
@@ -489,9 +479,9 @@ k_nn_topk(const double *__restrict__ cost, const int32_t *__restrict__ hits, int
     }
     const Key w = warp_min_key(mine);
     const bool found = w.id != kmax.id;
-    if (lane == 0) low[qi * k + tsel] = found ? w.id : -1;
+    if (lane == 0) low[tsel] = found ? w.id : -1;
     if (!found) {
-      for (int r = tsel + 1 + lane; r < k; r += 32) low[qi * k + r] = -1;
+      for (int r = tsel + 1 + lane; r < k; r += 32) low[r] = -1;
       break;
     }
     last = w;
@@ -507,13 +497,112 @@ k_nn_topk(const double *__restrict__ cost, const int32_t *__restrict__ hits, int
     }
     const Key w = warp_max_key(mine);
     const bool found = w.id != kmin.id;
-    if (lane == 0) high[qi * k + tsel] = found ? w.id : -1;
+    if (lane == 0) high[tsel] = found ? w.id : -1;
     if (!found) {
-      for (int r = tsel + 1 + lane; r < k; r += 32) high[qi * k + r] = -1;
+      for (int r = tsel + 1 + lane; r < k; r += 32) high[r] = -1;
       break;
     }
     last = w;
   }
+}
+
+__global__ void __launch_bounds__(NN_THREADS)
+k_nn_topk(const double *__restrict__ cost, const int32_t *__restrict__ hits, int64_t hit_cap,
+          const int32_t *__restrict__ count, int64_t Q, int k, int32_t *__restrict__ low, int32_t *__restrict__ high,
+          int32_t *__restrict__ overflow) {
+  const int lane = threadIdx.x & 31;
+  const int64_t qi = int64_t(blockIdx.x) * (NN_THREADS / 32) + (threadIdx.x >> 5);
+  if (qi >= Q) return;
+  const int32_t total = count[qi];
+  if (total > hit_cap) {
+    if (lane == 0) atomicExch(overflow, 1);
+  }
+  warp_topk(cost, hits + qi * hit_cap, int32_t(imin64(total, hit_cap)), k, low + qi * k, high + qi * k, lane);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Many queries, EACH AGAINST ITS OWN TREE (the lock-step multi-query planner, shim/sqmp_multi.hpp: every query of
+// a batch owns two small trees).  One warp per query: lanes stride over the nodes (coalesced SoA reads), exact fp64
+// distances in the reference's order, warp argmin over (d, id) for the nearest node; for the near vertices the hits
+// are ballot-compacted into the query's slice of the hit pool and the same warp selects the k lowest / k highest
+// (cost, id).  Inputs and answers live in mapped pinned host memory: one launch + one synchronise per batch.
+// ---------------------------------------------------------------------------------------------------------
+struct MultiQuery {          // 96 bytes, written by the host for every query of a call
+  const double *q[SQMP_DOF];
+  const double *cost;
+  int64_t n;
+  int32_t exclude;
+  int32_t pad;
+};
+template <bool RADIUS>
+__global__ void __launch_bounds__(NN_THREADS)
+k_nn_multi(const MultiQuery *__restrict__ desc, const double *__restrict__ queries, int64_t Q, double s_thr, int k,
+           int32_t *__restrict__ hits, int64_t hit_cap, int32_t *__restrict__ out /* nearest: [Q]; radius: [Q][2k+2] */) {
+  const int lane = threadIdx.x & 31;
+  const int64_t qi = int64_t(blockIdx.x) * (NN_THREADS / 32) + (threadIdx.x >> 5);
+  if (qi >= Q) return;
+  const MultiQuery t = desc[qi];
+  double query[SQMP_DOF];
+#pragma unroll
+  for (int d = 0; d < SQMP_DOF; ++d) query[d] = queries[qi * SQMP_DOF + d];
+  Best best = {NN_INIT_SUMSQ, NN_INIT_DIST, 0};
+  int32_t total = 0;   // warp-uniform
+  int32_t *h = hits + qi * hit_cap;
+  for (int64_t base = 0; base < t.n; base += 32) {
+    const int64_t n = base + lane;
+    bool hit = false;
+    if (n < t.n) {
+      double node[SQMP_DOF];
+#pragma unroll
+      for (int d = 0; d < SQMP_DOF; ++d) node[d] = t.q[d][n];
+      const double s = sumsq8(node, query);
+      if (RADIUS) hit = s < s_thr && int32_t(n) != t.exclude;
+      else offer(best, s, int32_t(n));
+    }
+    if (RADIUS) {
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      const int32_t slot = total + __popc(m & ((1u << lane) - 1u));
+      if (hit && slot < hit_cap) h[slot] = int32_t(n);
+      total += __popc(m);
+    }
+  }
+  if (!RADIUS) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double od = __shfl_xor_sync(0xffffffffu, best.d, o);
+      const int32_t oid = __shfl_xor_sync(0xffffffffu, best.id, o);
+      if (better(od, oid, best.d, best.id)) { best.d = od; best.id = oid; }
+    }
+    if (lane == 0) out[qi] = best.id;
+  } else {
+    __syncwarp();   // the hit list was written by this warp: visible to all its lanes
+    int32_t *o = out + qi * (2 * k + 2);
+    if (lane == 0) {
+      o[0] = total;
+      o[1] = total > hit_cap ? 1 : 0;   // overflow: the host redoes this query through the single-tree path
+    }
+    warp_topk(t.cost, h, int32_t(imin64(total, hit_cap)), k, o + 2, o + 2 + k, lane);
+  }
+}
+cudaError_t launch_nn_multi(const void *d_desc, const double *d_queries, int64_t Q, bool radius, double s_thr, int k,
+                            NNScratch &sc, int32_t *d_out, cudaStream_t st) {
+  if (Q <= 0) return cudaSuccess;
+  const unsigned blocks = unsigned((Q + NN_THREADS / 32 - 1) / (NN_THREADS / 32));
+  if (radius)
+    k_nn_multi<true><<<blocks, NN_THREADS, 0, st>>>((const MultiQuery *)d_desc, d_queries, Q, s_thr, k, sc.hits, sc.hit_cap, d_out);
+  else
+    k_nn_multi<false><<<blocks, NN_THREADS, 0, st>>>((const MultiQuery *)d_desc, d_queries, Q, 0.0, 0, nullptr, 0, d_out);
+  return cudaGetLastError();
+}
+size_t nn_multi_desc_bytes() { return sizeof(MultiQuery); }
+void nn_multi_fill_desc(void *dst, const TreeDev &t, int32_t exclude) {
+  MultiQuery m;
+  for (int d = 0; d < SQMP_DOF; ++d) m.q[d] = t.q[d];
+  m.cost = t.cost;
+  m.n = t.n;
+  m.exclude = exclude;
+  m.pad = 0;
+  *reinterpret_cast<MultiQuery *>(dst) = m;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -1,0 +1,323 @@
+// sqmp_multi.hpp — many planning queries per GPU in lock step (BASELINE.json configs[4]; SURVEY.md §7 item 5: "config 5
+// needs many concurrent queries per GPU to fill 148 SMs").
+//
+// A single BiRRT* query asks the library for ~6 tiny answers per iteration (one nearest node, 21..1000 states, ...), each
+// a synchronous launch: the GPU idles.  Here B queries of a batch run as cooperative fibers (ucontext) over the SAME
+// planner code (sqmp_birrt.hpp, unchanged): a query that needs an answer posts its request and yields; when every live
+// query has posted, the scheduler issues ONE library call per request kind for the whole batch —
+//   nearest node          -> sqmp_nn_nearest_multi   (every query against its own tree)
+//   near vertices         -> sqmp_nn_radius_multi
+//   candidate edges       -> sqmp_check_edges        (all queries' candidate edges concatenated)
+//   isConfigValid         -> sqmp_check_states
+// — hands the answers back and resumes the fibers.  Tree writes need no answer and go straight to the library
+// (stream-ordered).  Every query receives exactly the values it would receive alone, so its decisions — and its trace
+// hash — are those of the sequential run (tests/test_planner_frontend.py).
+#pragma once
+
+#include <ucontext.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "sqmp_birrt.hpp"
+#include "sqmp_shim.hpp"
+
+namespace sqmp_planner {
+
+struct MultiRequest {
+  enum Kind { NONE = 0, NEAREST, NEAR, EDGES, VALID } kind = NONE;
+  // NEAREST / NEAR / VALID
+  int slot = 0;
+  const double *q = nullptr;
+  int exclude = -1;
+  double r = 0.0;
+  int k = 0;
+  // EDGES
+  const std::vector<double> *a = nullptr, *b = nullptr;
+  int num_points = 0;
+  // answers
+  int id = 0;
+  bool valid = false;
+  std::vector<int> *low = nullptr, *high = nullptr, *first_invalid = nullptr;
+  int count = 0;
+};
+
+class MultiScheduler;
+
+// The Backend of BiRRTStar for ONE query of the batch (fiber `index`: tree slots 2*index and 2*index + 1).
+class FiberBackend {
+ public:
+  FiberBackend() : sched_(NULL), ctx_(NULL), index_(0), flags_(0), failed_(false) {}
+  void bind(MultiScheduler *s, sqmp_ctx *ctx, int index, unsigned flags) { sched_ = s; ctx_ = ctx; index_ = index; flags_ = flags; }
+
+  void tree_reset(int slot) { ok(sqmp_tree_reset(ctx_, 2 * index_ + slot)); }
+  int tree_append(int slot, const double *q, double cost) {
+    int32_t id = -1;
+    ok(sqmp_tree_append(ctx_, 2 * index_ + slot, q, cost, &id));
+    return id;
+  }
+  void tree_update(int slot, int id, const double *q, double cost) { ok(sqmp_tree_update(ctx_, 2 * index_ + slot, id, q, cost)); }
+  void sample_batch(uint64_t seed, long long first, int n, const double *lo, const double *hi, int max_tries, double *q_out) {
+    ok(sqmp_sample_configs(ctx_, seed, first, n, lo, hi, max_tries, q_out, NULL));   // once per 256 iterations: not batched
+  }
+  inline int nearest(int slot, const double *q);
+  inline void near(int slot, const double *q, int exclude_id, double r, int k, std::vector<int> &low, std::vector<int> &high, int &count);
+  inline bool config_valid(const double *q);
+  inline void check_edges(const std::vector<double> &a, const std::vector<double> &b, int num_points, std::vector<int> &first_invalid);
+  bool failed() const { return failed_; }
+
+  MultiRequest req;
+
+ private:
+  friend class MultiScheduler;
+  void ok(int rc) {
+    if (rc != SQMP_OK) {
+      failed_ = true;
+      std::fprintf(stderr, "libsqmp_b200: %s (%s)\n", sqmp_strerror(rc), sqmp_last_error(ctx_));
+    }
+  }
+  MultiScheduler *sched_;
+  sqmp_ctx *ctx_;
+  int index_;
+  unsigned flags_;
+  bool failed_;
+};
+
+class MultiScheduler {
+ public:
+  struct Result {
+    bool valid_endpoints = false;
+    Stats stats;
+  };
+
+  MultiScheduler(sqmp_shim::CollisionChecker *checker, bool check_self, bool check_map, int batch)
+      : ctx_(checker->context()), flags_(sqmp_shim::CollisionChecker::flags(check_self, check_map)),
+        batch_(batch < 1 ? 1 : (batch > SQMP_MAX_TREES / 2 ? SQMP_MAX_TREES / 2 : batch)), failed_(false), rounds_(0), calls_(0) {}
+
+  // queries: rows start[8] goal[8]; results in query order.  Returns false on a library error.
+  bool run(const double *queries, size_t n_queries, long iterations, uint64_t seed, size_t first_index, const Params &base,
+           std::vector<Result> &out) {
+    out.assign(n_queries, Result());
+    for (size_t g0 = 0; g0 < n_queries && !failed_; g0 += size_t(batch_)) {
+      const size_t nb = n_queries - g0 < size_t(batch_) ? n_queries - g0 : size_t(batch_);
+      fibers_.assign(nb, Fiber());
+      for (size_t i = 0; i < nb; ++i) {
+        Fiber &f = fibers_[i];
+        f.owner = this;
+        f.be.bind(this, ctx_, int(i), flags_);
+        f.P = base;
+        f.P.seed = seed + first_index + g0 + i;
+        f.q = queries + (g0 + i) * 16;
+        f.iterations = iterations;
+        f.stack.resize(STACK_BYTES);
+        getcontext(&f.uc);
+        f.uc.uc_stack.ss_sp = f.stack.data();
+        f.uc.uc_stack.ss_size = f.stack.size();
+        f.uc.uc_link = &main_;
+        const uintptr_t p = reinterpret_cast<uintptr_t>(&f);
+        makecontext(&f.uc, reinterpret_cast<void (*)()>(&MultiScheduler::entry), 2, unsigned(p & 0xffffffffu), unsigned(p >> 32));
+      }
+      size_t alive = nb;
+      while (alive > 0 && !failed_) {
+        for (size_t i = 0; i < nb; ++i) {   // run every live query up to its next request
+          Fiber &f = fibers_[i];
+          if (f.done) continue;
+          current_ = &f;
+          swapcontext(&main_, &f.uc);
+          if (f.done) {
+            --alive;
+            failed_ = failed_ || f.be.failed();
+          }
+        }
+        serve(nb);
+        rounds_ += 1;
+      }
+      for (size_t i = 0; i < nb; ++i) {
+        out[g0 + i].valid_endpoints = fibers_[i].valid_endpoints;
+        out[g0 + i].stats = fibers_[i].stats;
+      }
+    }
+    return !failed_;
+  }
+  void yield() { swapcontext(&current_->uc, &main_); }   // called on a fiber's stack
+  long rounds() const { return rounds_; }
+  long library_calls() const { return calls_; }
+
+ private:
+  struct Fiber {
+    MultiScheduler *owner = NULL;
+    ucontext_t uc;
+    std::vector<char> stack;
+    FiberBackend be;
+    Params P;
+    const double *q = NULL;
+    long iterations = 0;
+    bool done = false, valid_endpoints = false;
+    Stats stats;
+  };
+  static const size_t STACK_BYTES = 256 * 1024;
+
+  static void entry(unsigned lo, unsigned hi) {
+    Fiber *f = reinterpret_cast<Fiber *>(uintptr_t(lo) | (uintptr_t(hi) << 32));
+    {
+      BiRRTStar<FiberBackend> planner(f->be, f->P);
+      f->valid_endpoints = planner.init(f->q, f->q + 8);
+      if (f->valid_endpoints) f->stats = planner.run(f->iterations);
+    }
+    f->be.req.kind = MultiRequest::NONE;
+    f->done = true;   // returning resumes uc_link = the scheduler
+  }
+
+  void ok(int rc) {
+    if (rc != SQMP_OK) {
+      failed_ = true;
+      std::fprintf(stderr, "libsqmp_b200: %s (%s)\n", sqmp_strerror(rc), sqmp_last_error(ctx_));
+    }
+  }
+
+  // one library call per request kind present in this round
+  void serve(size_t nb) {
+    // ---- nearest ----
+    idx_.clear(); trees_.clear(); qs_.clear();
+    for (size_t i = 0; i < nb; ++i) {
+      MultiRequest &r = fibers_[i].be.req;
+      if (fibers_[i].done || r.kind != MultiRequest::NEAREST) continue;
+      idx_.push_back(int(i));
+      trees_.push_back(2 * int(i) + r.slot);
+      qs_.insert(qs_.end(), r.q, r.q + 8);
+    }
+    if (!idx_.empty()) {
+      ids_.assign(idx_.size(), 0);
+      ok(sqmp_nn_nearest_multi(ctx_, trees_.data(), qs_.data(), int64_t(idx_.size()), ids_.data()));
+      calls_ += 1;
+      for (size_t j = 0; j < idx_.size(); ++j) fibers_[size_t(idx_[j])].be.req.id = ids_[j];
+    }
+    // ---- near vertices (r and k are planner parameters: equal for the whole batch) ----
+    idx_.clear(); trees_.clear(); qs_.clear(); excl_.clear();
+    double rr = 0.0;
+    int kk = 0;
+    for (size_t i = 0; i < nb; ++i) {
+      MultiRequest &r = fibers_[i].be.req;
+      if (fibers_[i].done || r.kind != MultiRequest::NEAR) continue;
+      idx_.push_back(int(i));
+      trees_.push_back(2 * int(i) + r.slot);
+      qs_.insert(qs_.end(), r.q, r.q + 8);
+      excl_.push_back(r.exclude);
+      rr = r.r;
+      kk = r.k;
+    }
+    if (!idx_.empty()) {
+      low_.assign(idx_.size() * size_t(kk), -1);
+      high_.assign(idx_.size() * size_t(kk), -1);
+      cnt_.assign(idx_.size(), 0);
+      ok(sqmp_nn_radius_multi(ctx_, trees_.data(), qs_.data(), excl_.data(), int64_t(idx_.size()), rr, kk, low_.data(),
+                              high_.data(), cnt_.data()));
+      calls_ += 1;
+      for (size_t j = 0; j < idx_.size(); ++j) {
+        MultiRequest &r = fibers_[size_t(idx_[j])].be.req;
+        r.low->assign(low_.begin() + long(j) * kk, low_.begin() + long(j + 1) * kk);
+        r.high->assign(high_.begin() + long(j) * kk, high_.begin() + long(j + 1) * kk);
+        r.count = cnt_[j];
+      }
+    }
+    // ---- candidate edges ----
+    idx_.clear(); ea_.clear(); eb_.clear();
+    int np = 0;
+    for (size_t i = 0; i < nb; ++i) {
+      MultiRequest &r = fibers_[i].be.req;
+      if (fibers_[i].done || r.kind != MultiRequest::EDGES) continue;
+      idx_.push_back(int(i));
+      ea_.insert(ea_.end(), r.a->begin(), r.a->end());
+      eb_.insert(eb_.end(), r.b->begin(), r.b->end());
+      np = r.num_points;
+    }
+    if (!idx_.empty()) {
+      const int64_t E = int64_t(ea_.size() / 8);
+      first_.assign(size_t(E), -1);
+      if (flags_ != 0) {
+        mask_.assign(size_t((E * (np + 1) + 31) / 32), 0u);
+        ok(sqmp_check_edges(ctx_, ea_.data(), eb_.data(), E, np, flags_, mask_.data(), first_.data()));
+        calls_ += 1;
+      }
+      size_t off = 0;
+      for (size_t j = 0; j < idx_.size(); ++j) {
+        MultiRequest &r = fibers_[size_t(idx_[j])].be.req;
+        const size_t e = r.a->size() / 8;
+        r.first_invalid->assign(first_.begin() + long(off), first_.begin() + long(off + e));
+        off += e;
+      }
+    }
+    // ---- isConfigValid ----
+    idx_.clear(); qs_.clear();
+    for (size_t i = 0; i < nb; ++i) {
+      MultiRequest &r = fibers_[i].be.req;
+      if (fibers_[i].done || r.kind != MultiRequest::VALID) continue;
+      idx_.push_back(int(i));
+      qs_.insert(qs_.end(), r.q, r.q + 8);
+    }
+    if (!idx_.empty()) {
+      mask_.assign((idx_.size() + 31) / 32, 0u);
+      if (flags_ != 0) {
+        ok(sqmp_check_states(ctx_, qs_.data(), int64_t(idx_.size()), flags_, mask_.data()));
+        calls_ += 1;
+      }
+      for (size_t j = 0; j < idx_.size(); ++j)
+        fibers_[size_t(idx_[j])].be.req.valid = ((mask_[j >> 5] >> (j & 31)) & 1u) == 0;
+    }
+    for (size_t i = 0; i < nb; ++i) fibers_[i].be.req.kind = MultiRequest::NONE;
+  }
+
+  sqmp_ctx *ctx_;
+  unsigned flags_;
+  int batch_;
+  bool failed_;
+  long rounds_, calls_;
+  ucontext_t main_;
+  Fiber *current_ = NULL;
+  std::vector<Fiber> fibers_;
+  std::vector<int> idx_;
+  std::vector<int32_t> trees_, excl_, ids_, low_, high_, cnt_, first_;
+  std::vector<double> qs_, ea_, eb_;
+  std::vector<uint32_t> mask_;
+};
+
+inline int FiberBackend::nearest(int slot, const double *q) {
+  req.kind = MultiRequest::NEAREST;
+  req.slot = slot;
+  req.q = q;
+  sched_->yield();
+  return req.id;
+}
+inline void FiberBackend::near(int slot, const double *q, int exclude_id, double r, int k, std::vector<int> &low,
+                               std::vector<int> &high, int &count) {
+  req.kind = MultiRequest::NEAR;
+  req.slot = slot;
+  req.q = q;
+  req.exclude = exclude_id;
+  req.r = r;
+  req.k = k;
+  req.low = &low;
+  req.high = &high;
+  sched_->yield();
+  count = req.count;
+}
+inline bool FiberBackend::config_valid(const double *q) {
+  if (flags_ == 0) return true;
+  req.kind = MultiRequest::VALID;
+  req.q = q;
+  sched_->yield();
+  return req.valid;
+}
+inline void FiberBackend::check_edges(const std::vector<double> &a, const std::vector<double> &b, int num_points,
+                                      std::vector<int> &first_invalid) {
+  req.kind = MultiRequest::EDGES;
+  req.a = &a;
+  req.b = &b;
+  req.num_points = num_points;
+  req.first_invalid = &first_invalid;
+  sched_->yield();
+}
+
+}  // namespace sqmp_planner

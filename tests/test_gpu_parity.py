@@ -470,6 +470,51 @@ def test_radius_topk_bit_exact(ctx, variant):
         ctx.set_option("nn_variant", 0)
 
 
+def test_multi_tree_queries_equal_single_tree_calls(ctx):
+    """sqmp_nn_nearest_multi / sqmp_nn_radius_multi (query i against tree[i], one launch) == the oracle on every tree:
+    trees of very different sizes incl. an empty one and a one-node tree, duplicated nodes (ties -> lowest id), equal
+    costs (ties -> lowest id), exclusions, more hits than k, and a pool small enough to force the overflow fall-back."""
+    rng = np.random.default_rng(3)
+    sizes = [0, 1, 7, 33, 500, 3000, 64, 1025]
+    trees, costs = [], []
+    for t, n in enumerate(sizes):
+        ctx.tree_reset(10 + t)
+        nodes, cost = syn.random_tree(max(n, 1), seed=300 + t, cost_seed=400 + t, xy_half=1.0)
+        nodes, cost = nodes[:n], cost[:n]
+        if n >= 33:
+            nodes[5] = nodes[20]; nodes[31] = nodes[20]            # exact duplicates
+            cost[::4] = cost[3]                                     # equal costs
+        if n:
+            ctx.tree_append_batch(10 + t, nodes, cost)
+        trees.append(nodes); costs.append(cost)
+    Q = 400
+    which = rng.integers(0, len(sizes), Q)
+    queries = syn.sample_configs(Q, seed=77, xy_half=1.0)
+    for i in range(0, Q, 9):                                        # some queries ARE nodes (distance 0, exclusion)
+        if sizes[which[i]] >= 33:
+            queries[i] = trees[which[i]][20]
+    excl = np.where(rng.random(Q) < 0.5, 20, -1).astype(np.int32)
+    ids = ctx.nn_nearest_multi(10 + which, queries)
+    for i in range(Q):
+        n = sizes[which[i]]
+        want = 0 if n == 0 else int(oracle.nearest(trees[which[i]], queries[i:i + 1])[0])
+        assert ids[i] == want
+    for pool in (1 << 30, 1 << 16):                                 # 2^16 bytes / 400 queries: 40-hit slices overflow
+        ctx.set_option("nn_hit_pool_bytes", pool)
+        low, high, cnt = ctx.nn_radius_multi(10 + which, queries, excl, 3.0, 20)
+        for i in range(Q):
+            n = sizes[which[i]]
+            if n == 0:
+                assert cnt[i] == 0 and (low[i] == -1).all() and (high[i] == -1).all()
+                continue
+            rl, rh, rc = oracle.near_topk(trees[which[i]], costs[which[i]], queries[i:i + 1], excl[i:i + 1], 3.0, 20)
+            assert cnt[i] == rc[0] and np.array_equal(low[i], rl[0]) and np.array_equal(high[i], rh[0])
+    ctx.set_option("nn_hit_pool_bytes", 1 << 30)
+    assert cnt.max() > 40                                           # the small pool really overflowed somewhere
+    with pytest.raises(api.SqmpError):
+        ctx.nn_nearest_multi(np.array([5000], dtype=np.int32), queries[:1])
+
+
 def test_fp32_prefilter_is_sound_on_adversarial_trees(ctx):
     """Variant 3 decides most pairs from an fp32 estimate with a proven error bound; anything inside the bound must fall
     through to the exact fp64 test.  Trees built to sit inside that bound: clusters whose members differ by 1e-13..1e-7

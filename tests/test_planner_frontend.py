@@ -83,3 +83,28 @@ def test_gpu_and_cpu_backends_take_identical_decisions(tmp_path, fixture_data):
     for c, g in zip(cpu, gpu):
         assert c == g, "decision traces differ:\\n%s\\n%s" % (c, g)
     assert sum(r[1] == "1" for r in gpu) >= 2
+
+
+@pytest.mark.gpu
+def test_lockstep_multi_query_runner_repeats_the_sequential_decisions(tmp_path, fixture_data):
+    """shim/sqmp_plan_multi (B queries per GPU as fibers over the same planner code, one library call per request kind
+    and round) must print the sequential runner's lines: same decisions, same trace hashes — for batch sizes that do and
+    do not divide the number of queries, and with an invalid goal in the middle of a batch."""
+    world = syn.box_world(g=256, n_boxes=64, seed=1234)
+    rng = np.random.default_rng(11)
+    s0, g0 = pw.config1_queries(1)
+    n = 11
+    starts, goals = np.repeat(s0, n, axis=0), np.repeat(g0, n, axis=0)
+    starts[:, :2] += rng.uniform(-0.4, 0.4, size=(n, 2))
+    goals[:, :2] += rng.uniform(-0.4, 0.4, size=(n, 2))
+    goals[4, 3:] = (0.29, 2.26, 0.19, -1.17, 0.53)          # self collision: init_planner rejects it (BS:351-358)
+    d = _workdir(tmp_path, fixture_data, world, starts, goals)
+    seq = _run("sqmp_plan", d, "gpu", 300)
+    assert len(seq) == n and seq[4][1] == "invalid_endpoint"
+    for batch in (4, 11, 128):
+        subprocess.run(["make", "-s", "-C", SHIM], check=True)
+        r = subprocess.run([os.path.join(SHIM, "sqmp_plan_multi"), DESC, d, "gpu", "300", "1", "0", "0", str(n), str(batch)],
+                           capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout + r.stderr
+        rows = [l.split() for l in r.stdout.splitlines() if l and not l.startswith("#")]
+        assert rows == seq, "batch %d" % batch
