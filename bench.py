@@ -574,7 +574,7 @@ def main():
     ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5"])
     ap.add_argument("--queries", type=int, default=1024, help="config5: number of planning queries")
     ap.add_argument("--iterations", type=int, default=1000, help="config5: BiRRT* iterations per query")
-    ap.add_argument("--batch", type=int, default=128, help="config5: queries in flight per GPU (1 = sequential runner)")
+    ap.add_argument("--batch", type=int, default=512, help="config5: queries in flight per GPU (1 = sequential runner)")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
