@@ -201,19 +201,40 @@ def run_own(args):
         wl = "config2: 2^20 interpolated 8-DOF states per GPU vs W256 (256^3 voxels, res 0.05), map check"
     d_q = [torch.from_numpy(b).to(dev) for b in batches]
     words = (s_rank + 31) // 32
-    d_all = torch.zeros(world_size * words, dtype=torch.int32, device=dev)   # gathered mask, every rank
-    d_mine = d_all[rank * words:(rank + 1) * words]                          # kernel writes straight into its slot
+    # gathered mask, every rank; double-buffered so that the all-gather of step i (comm stream) overlaps the kernel of
+    # step i + 1 (compute stream).  The kernel writes straight into the rank's slot of the gather buffer.
+    NBUF = 2 if world_size > 1 else 1
+    d_all = [torch.zeros(world_size * words, dtype=torch.int32, device=dev) for _ in range(NBUF)]
+    d_mine = [a[rank * words:(rank + 1) * words] for a in d_all]
     flags = api.CHECK_MAP
+    comm = torch.cuda.Stream(device=dev) if world_size > 1 else None
+    kernel_done = [torch.cuda.Event() for _ in range(NBUF)]
+    gather_done = [torch.cuda.Event() for _ in range(NBUF)]
+    gathers_issued = [False] * NBUF
 
     def step(i):
-        ctx.check_states_dev(d_q[i % n_rot], s_rank, flags, d_mine, stream)
+        b = i % NBUF
+        cur = torch.cuda.current_stream()
+        if world_size > 1 and gathers_issued[b]:
+            cur.wait_event(gather_done[b])            # buffer b is free again once its previous all-gather has finished
+        ctx.check_states_dev(d_q[i % n_rot], s_rank, flags, d_mine[b], stream)
         if world_size > 1:
-            dist.all_gather_into_tensor(d_all, d_mine)
+            kernel_done[b].record(cur)
+            with torch.cuda.stream(comm):
+                comm.wait_event(kernel_done[b])
+                dist.all_gather_into_tensor(d_all[b], d_mine[b])
+                gather_done[b].record(comm)
+            gathers_issued[b] = True
+
+    def drain():                                      # every all-gather issued so far has completed
+        if world_size > 1:
+            torch.cuda.current_stream().wait_stream(comm)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
     for i in range(max(args.warmup, 3)):
         step(i)
+    drain()
     torch.cuda.synchronize()
     if world_size > 1:
         dist.barrier()
@@ -223,6 +244,7 @@ def run_own(args):
     e_start.record()
     for i in range(args.steps):                       # the timed region: nothing but the steps (no events in between,
         step(i)                                       # so consecutive K1F grids may overlap their tails as in production)
+    drain()                                           # the region ends when the last mask has reached every rank
     e_stop.record()
     torch.cuda.synchronize()
     if world_size > 1:
@@ -234,7 +256,7 @@ def run_own(args):
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k0.record()
         for i in range(args.steps):
-            ctx.check_states_dev(d_q[i % n_rot], s_rank, flags, d_mine, stream)
+            ctx.check_states_dev(d_q[i % n_rot], s_rank, flags, d_mine[0], stream)
         k1.record()
         torch.cuda.synchronize()
         kern_ms = k0.elapsed_time(k1) / args.steps
