@@ -1,8 +1,10 @@
 // plan_oracle.cpp — TEST INFRASTRUCTURE / CPU BASELINE ONLY (like everything under oracle/).
 // The planner front-end of the package (shim/sqmp_birrt.hpp, byte-for-byte the code the CUDA build runs) instantiated
 // over the CPU oracle library, so that tests can compare per-iteration decisions and bench.py can time the CPU arm.
-//   sqmp_plan_oracle <robot.sqmpdesc (unused)> <work_dir> oracle <iterations> <seed> [device (unused)] [first_query] [n_queries]
+//   sqmp_plan_oracle <robot.sqmpdesc (unused)> <work_dir> oracle <iterations> <seed> [device (unused)] [first_query] [n_queries] [batch]
+// With [batch] the queries run through the lock-step scheduler of shim/sqmp_multi.hpp over the oracle.
 // work_dir additionally holds oracle_model.bin (written by tools/planner_workdir.py).
+#include "sqmp_multi.hpp"
 #include "sqmp_plan_driver.hpp"
 
 #include "sqmp_oracle.h"
@@ -49,6 +51,62 @@ class OracleBackend {
   std::vector<double> nodes_[8], cost_[8];
 };
 
+// The "library" of the lock-step scheduler (shim/sqmp_multi.hpp) over the CPU oracle: the batched calls are loops over
+// the oracle's single-tree functions.  Lets the scheduler's host logic be tested without a GPU: its lines must equal
+// the sequential runner's.
+class OracleService {
+ public:
+  OracleService(orc_model *m, unsigned flags, int tip) : m_(m), flags_(flags), tip_(tip), nodes_(2048), cost_(2048) {}
+  static int max_batch() { return 1024; }
+  unsigned flags() const { return flags_; }
+  int tree_reset(int t) { nodes_[size_t(t)].clear(); cost_[size_t(t)].clear(); return 0; }
+  int tree_append(int t, const double *q, double cost, int32_t *id) {
+    nodes_[size_t(t)].insert(nodes_[size_t(t)].end(), q, q + 8);
+    cost_[size_t(t)].push_back(cost);
+    *id = int32_t(cost_[size_t(t)].size()) - 1;
+    return 0;
+  }
+  int tree_update(int t, int id, const double *q, double cost) {
+    std::memcpy(&nodes_[size_t(t)][size_t(id) * 8], q, 64);
+    cost_[size_t(t)][size_t(id)] = cost;
+    return 0;
+  }
+  int sample(uint64_t seed, long long first, int n, const double *lo, const double *hi, int max_tries, double *q_out) {
+    orc_sample_configs(m_, tip_, seed, first, n, lo, hi, max_tries, q_out, NULL);
+    return 0;
+  }
+  int nearest_multi(const int32_t *tree, const double *q, int64_t n, int32_t *ids) {
+    for (int64_t i = 0; i < n; ++i)
+      ids[i] = orc_nearest(nodes_[size_t(tree[i])].data(), int64_t(cost_[size_t(tree[i])].size()), q + i * 8);
+    return 0;
+  }
+  int radius_multi(const int32_t *tree, const double *q, const int32_t *excl, int64_t n, double r, int k, int32_t *low,
+                   int32_t *high, int32_t *cnt) {
+    for (int64_t i = 0; i < n; ++i)
+      orc_near_topk_batch(nodes_[size_t(tree[i])].data(), cost_[size_t(tree[i])].data(), int64_t(cost_[size_t(tree[i])].size()),
+                          q + i * 8, excl + i, 1, r, k, low + i * k, high + i * k, cnt + i, 1);
+    return 0;
+  }
+  int check_edges(const double *a, const double *b, int64_t E, int num_points, uint32_t *mask, int32_t *first) {
+    orc_check_edges(m_, a, b, E, num_points, flags_, mask, first, 1);
+    return 0;
+  }
+  int check_states(const double *q, int64_t n, uint32_t *mask) {
+    for (int64_t i = 0; i < n; ++i) {
+      if ((i & 31) == 0) mask[i >> 5] = 0u;
+      if (orc_is_in_collision(m_, q + i * 8, (flags_ & 1u) != 0, (flags_ & 2u) != 0)) mask[i >> 5] |= 1u << (i & 31);
+    }
+    return 0;
+  }
+  void report(int) const {}
+
+ private:
+  orc_model *m_;
+  unsigned flags_;
+  int tip_;
+  std::vector<std::vector<double> > nodes_, cost_;
+};
+
 // oracle_model.bin (written by tests / bench): int32 L, n_spheres; then the arrays orc_model_create takes, in order;
 // then int32 tip = link index of the FK chain tip (hand_wrist_link, SRDF:4-6)
 static orc_model *load_oracle_model(const std::string &path, int *tip) {
@@ -84,8 +142,31 @@ int main(int argc, char **argv) {
   if (!m) return 4;
   const double origin[3] = {a.g.origin[0], a.g.origin[1], a.g.origin[2] - 0.02};   // CC:87, as the shim does
   orc_set_grid(m, a.g.bits.data(), a.g.gx, a.g.gy, a.g.gz, origin, a.g.res);
-  OracleBackend be(m, 3u, tip);
-  const int rc = sqmp_plan_driver::run_queries(be, a.queries, a.iterations, a.seed, a.first, a.count, a.xy_lo, a.xy_hi);
+  int rc = 0;
+  if (argc > 9) {   // [batch]: the lock-step scheduler over the oracle (same output lines as the sequential runner)
+    OracleService svc(m, 3u, tip);
+    sqmp_planner::MultiSchedulerT<OracleService> sched(&svc, atoi(argv[9]));
+    sqmp_planner::Params P;
+    P.lo[0] = a.xy_lo[0]; P.lo[1] = a.xy_lo[1]; P.hi[0] = a.xy_hi[0]; P.hi[1] = a.xy_hi[1];
+    size_t count = a.count;
+    if ((a.first + count) * 16 > a.queries.size()) count = a.queries.size() / 16 > a.first ? a.queries.size() / 16 - a.first : 0;
+    std::vector<sqmp_planner::MultiSchedulerT<OracleService>::Result> res;
+    if (!sched.run(a.queries.data() + a.first * 16, count, a.iterations, a.seed, a.first, P, res)) rc = 6;
+    for (size_t k = 0; k < res.size() && rc == 0; ++k) {
+      if (!res[k].valid_endpoints) {
+        std::printf("%zu invalid_endpoint\n", a.first + k);
+        continue;
+      }
+      const sqmp_planner::Stats &s = res[k].stats;
+      std::printf("%zu %d %.17g %ld %ld %ld %ld %ld %ld %ld %ld %ld %ld %llu\n", a.first + k, int(s.solved), s.best_cost,
+                  s.iterations, s.nn_calls, s.near_calls, s.edge_batches, s.edges_checked, s.states_checked, s.rewires,
+                  s.parents_chosen, s.nodes_start, s.nodes_goal, (unsigned long long)s.trace);
+    }
+    std::printf("# queries %zu rounds %ld service_calls %ld\n", count, sched.rounds(), sched.library_calls());
+  } else {
+    OracleBackend be(m, 3u, tip);
+    rc = sqmp_plan_driver::run_queries(be, a.queries, a.iterations, a.seed, a.first, a.count, a.xy_lo, a.xy_hi);
+  }
   orc_model_destroy(m);
   return rc;
 }

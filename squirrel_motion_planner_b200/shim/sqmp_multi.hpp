@@ -44,23 +44,56 @@ struct MultiRequest {
   int count = 0;
 };
 
-class MultiScheduler;
+// What the scheduler needs from "the library": the batched calls and the tree writes.  GpuService is the product (the
+// C ABI of libsqmp_b200.so); the test twin over the CPU oracle lives outside the package (oracle/plan_oracle.cpp).
+// Every method returns 0 on success.
+class GpuService {
+ public:
+  GpuService(sqmp_shim::CollisionChecker *checker, bool check_self, bool check_map)
+      : ctx_(checker->context()), flags_(sqmp_shim::CollisionChecker::flags(check_self, check_map)) {}
+  static int max_batch() { return SQMP_MAX_TREES / 2; }
+  unsigned flags() const { return flags_; }
+  int tree_reset(int tree) { return sqmp_tree_reset(ctx_, tree); }
+  int tree_append(int tree, const double *q, double cost, int32_t *id) { return sqmp_tree_append(ctx_, tree, q, cost, id); }
+  int tree_update(int tree, int id, const double *q, double cost) { return sqmp_tree_update(ctx_, tree, id, q, cost); }
+  int sample(uint64_t seed, long long first, int n, const double *lo, const double *hi, int max_tries, double *q_out) {
+    return sqmp_sample_configs(ctx_, seed, first, n, lo, hi, max_tries, q_out, NULL);
+  }
+  int nearest_multi(const int32_t *tree, const double *q, int64_t n, int32_t *ids) { return sqmp_nn_nearest_multi(ctx_, tree, q, n, ids); }
+  int radius_multi(const int32_t *tree, const double *q, const int32_t *excl, int64_t n, double r, int k, int32_t *low,
+                   int32_t *high, int32_t *cnt) {
+    return sqmp_nn_radius_multi(ctx_, tree, q, excl, n, r, k, low, high, cnt);
+  }
+  int check_edges(const double *a, const double *b, int64_t E, int num_points, uint32_t *mask, int32_t *first) {
+    return sqmp_check_edges(ctx_, a, b, E, num_points, flags_, mask, first);
+  }
+  int check_states(const double *q, int64_t n, uint32_t *mask) { return sqmp_check_states(ctx_, q, n, flags_, mask); }
+  void report(int rc) const { std::fprintf(stderr, "libsqmp_b200: %s (%s)\n", sqmp_strerror(rc), sqmp_last_error(ctx_)); }
+
+ private:
+  sqmp_ctx *ctx_;
+  unsigned flags_;
+};
+
+template <class Service>
+class MultiSchedulerT;
 
 // The Backend of BiRRTStar for ONE query of the batch (fiber `index`: tree slots 2*index and 2*index + 1).
-class FiberBackend {
+template <class Service>
+class FiberBackendT {
  public:
-  FiberBackend() : sched_(NULL), ctx_(NULL), index_(0), flags_(0), failed_(false) {}
-  void bind(MultiScheduler *s, sqmp_ctx *ctx, int index, unsigned flags) { sched_ = s; ctx_ = ctx; index_ = index; flags_ = flags; }
+  FiberBackendT() : sched_(NULL), svc_(NULL), index_(0), flags_(0), failed_(false) {}
+  void bind(MultiSchedulerT<Service> *s, Service *svc, int index) { sched_ = s; svc_ = svc; index_ = index; flags_ = svc->flags(); }
 
-  void tree_reset(int slot) { ok(sqmp_tree_reset(ctx_, 2 * index_ + slot)); }
+  void tree_reset(int slot) { ok(svc_->tree_reset(2 * index_ + slot)); }
   int tree_append(int slot, const double *q, double cost) {
     int32_t id = -1;
-    ok(sqmp_tree_append(ctx_, 2 * index_ + slot, q, cost, &id));
+    ok(svc_->tree_append(2 * index_ + slot, q, cost, &id));
     return id;
   }
-  void tree_update(int slot, int id, const double *q, double cost) { ok(sqmp_tree_update(ctx_, 2 * index_ + slot, id, q, cost)); }
+  void tree_update(int slot, int id, const double *q, double cost) { ok(svc_->tree_update(2 * index_ + slot, id, q, cost)); }
   void sample_batch(uint64_t seed, long long first, int n, const double *lo, const double *hi, int max_tries, double *q_out) {
-    ok(sqmp_sample_configs(ctx_, seed, first, n, lo, hi, max_tries, q_out, NULL));   // once per 256 iterations: not batched
+    ok(svc_->sample(seed, first, n, lo, hi, max_tries, q_out));   // once per 256 iterations: not batched
   }
   inline int nearest(int slot, const double *q);
   inline void near(int slot, const double *q, int exclude_id, double r, int k, std::vector<int> &low, std::vector<int> &high, int &count);
@@ -71,30 +104,32 @@ class FiberBackend {
   MultiRequest req;
 
  private:
-  friend class MultiScheduler;
+  friend class MultiSchedulerT<Service>;
   void ok(int rc) {
-    if (rc != SQMP_OK) {
+    if (rc != 0) {
       failed_ = true;
-      std::fprintf(stderr, "libsqmp_b200: %s (%s)\n", sqmp_strerror(rc), sqmp_last_error(ctx_));
+      svc_->report(rc);
     }
   }
-  MultiScheduler *sched_;
-  sqmp_ctx *ctx_;
+  MultiSchedulerT<Service> *sched_;
+  Service *svc_;
   int index_;
   unsigned flags_;
   bool failed_;
 };
 
-class MultiScheduler {
+template <class Service>
+class MultiSchedulerT {
  public:
+  typedef FiberBackendT<Service> FiberBackend;
   struct Result {
     bool valid_endpoints = false;
     Stats stats;
   };
 
-  MultiScheduler(sqmp_shim::CollisionChecker *checker, bool check_self, bool check_map, int batch)
-      : ctx_(checker->context()), flags_(sqmp_shim::CollisionChecker::flags(check_self, check_map)),
-        batch_(batch < 1 ? 1 : (batch > SQMP_MAX_TREES / 2 ? SQMP_MAX_TREES / 2 : batch)), failed_(false), rounds_(0), calls_(0) {}
+  MultiSchedulerT(Service *service, int batch)
+      : svc_(service), flags_(service->flags()),
+        batch_(batch < 1 ? 1 : (batch > Service::max_batch() ? Service::max_batch() : batch)), failed_(false), rounds_(0), calls_(0) {}
 
   // queries: rows start[8] goal[8]; results in query order.  Returns false on a library error.
   bool run(const double *queries, size_t n_queries, long iterations, uint64_t seed, size_t first_index, const Params &base,
@@ -106,7 +141,7 @@ class MultiScheduler {
       for (size_t i = 0; i < nb; ++i) {
         Fiber &f = fibers_[i];
         f.owner = this;
-        f.be.bind(this, ctx_, int(i), flags_);
+        f.be.bind(this, svc_, int(i));
         f.P = base;
         f.P.seed = seed + first_index + g0 + i;
         f.q = queries + (g0 + i) * 16;
@@ -117,7 +152,7 @@ class MultiScheduler {
         f.uc.uc_stack.ss_size = f.stack.size();
         f.uc.uc_link = &main_;
         const uintptr_t p = reinterpret_cast<uintptr_t>(&f);
-        makecontext(&f.uc, reinterpret_cast<void (*)()>(&MultiScheduler::entry), 2, unsigned(p & 0xffffffffu), unsigned(p >> 32));
+        makecontext(&f.uc, reinterpret_cast<void (*)()>(&MultiSchedulerT<Service>::entry), 2, unsigned(p & 0xffffffffu), unsigned(p >> 32));
       }
       size_t alive = nb;
       while (alive > 0 && !failed_) {
@@ -147,7 +182,7 @@ class MultiScheduler {
 
  private:
   struct Fiber {
-    MultiScheduler *owner = NULL;
+    MultiSchedulerT<Service> *owner = NULL;
     ucontext_t uc;
     std::vector<char> stack;
     FiberBackend be;
@@ -171,9 +206,9 @@ class MultiScheduler {
   }
 
   void ok(int rc) {
-    if (rc != SQMP_OK) {
+    if (rc != 0) {
       failed_ = true;
-      std::fprintf(stderr, "libsqmp_b200: %s (%s)\n", sqmp_strerror(rc), sqmp_last_error(ctx_));
+      svc_->report(rc);
     }
   }
 
@@ -190,7 +225,7 @@ class MultiScheduler {
     }
     if (!idx_.empty()) {
       ids_.assign(idx_.size(), 0);
-      ok(sqmp_nn_nearest_multi(ctx_, trees_.data(), qs_.data(), int64_t(idx_.size()), ids_.data()));
+      ok(svc_->nearest_multi(trees_.data(), qs_.data(), int64_t(idx_.size()), ids_.data()));
       calls_ += 1;
       for (size_t j = 0; j < idx_.size(); ++j) fibers_[size_t(idx_[j])].be.req.id = ids_[j];
     }
@@ -212,8 +247,8 @@ class MultiScheduler {
       low_.assign(idx_.size() * size_t(kk), -1);
       high_.assign(idx_.size() * size_t(kk), -1);
       cnt_.assign(idx_.size(), 0);
-      ok(sqmp_nn_radius_multi(ctx_, trees_.data(), qs_.data(), excl_.data(), int64_t(idx_.size()), rr, kk, low_.data(),
-                              high_.data(), cnt_.data()));
+      ok(svc_->radius_multi(trees_.data(), qs_.data(), excl_.data(), int64_t(idx_.size()), rr, kk, low_.data(), high_.data(),
+                              cnt_.data()));
       calls_ += 1;
       for (size_t j = 0; j < idx_.size(); ++j) {
         MultiRequest &r = fibers_[size_t(idx_[j])].be.req;
@@ -238,7 +273,7 @@ class MultiScheduler {
       first_.assign(size_t(E), -1);
       if (flags_ != 0) {
         mask_.assign(size_t((E * (np + 1) + 31) / 32), 0u);
-        ok(sqmp_check_edges(ctx_, ea_.data(), eb_.data(), E, np, flags_, mask_.data(), first_.data()));
+        ok(svc_->check_edges(ea_.data(), eb_.data(), E, np, mask_.data(), first_.data()));
         calls_ += 1;
       }
       size_t off = 0;
@@ -260,7 +295,7 @@ class MultiScheduler {
     if (!idx_.empty()) {
       mask_.assign((idx_.size() + 31) / 32, 0u);
       if (flags_ != 0) {
-        ok(sqmp_check_states(ctx_, qs_.data(), int64_t(idx_.size()), flags_, mask_.data()));
+        ok(svc_->check_states(qs_.data(), int64_t(idx_.size()), mask_.data()));
         calls_ += 1;
       }
       for (size_t j = 0; j < idx_.size(); ++j)
@@ -269,7 +304,7 @@ class MultiScheduler {
     for (size_t i = 0; i < nb; ++i) fibers_[i].be.req.kind = MultiRequest::NONE;
   }
 
-  sqmp_ctx *ctx_;
+  Service *svc_;
   unsigned flags_;
   int batch_;
   bool failed_;
@@ -283,14 +318,16 @@ class MultiScheduler {
   std::vector<uint32_t> mask_;
 };
 
-inline int FiberBackend::nearest(int slot, const double *q) {
+template <class Service>
+inline int FiberBackendT<Service>::nearest(int slot, const double *q) {
   req.kind = MultiRequest::NEAREST;
   req.slot = slot;
   req.q = q;
   sched_->yield();
   return req.id;
 }
-inline void FiberBackend::near(int slot, const double *q, int exclude_id, double r, int k, std::vector<int> &low,
+template <class Service>
+inline void FiberBackendT<Service>::near(int slot, const double *q, int exclude_id, double r, int k, std::vector<int> &low,
                                std::vector<int> &high, int &count) {
   req.kind = MultiRequest::NEAR;
   req.slot = slot;
@@ -303,14 +340,16 @@ inline void FiberBackend::near(int slot, const double *q, int exclude_id, double
   sched_->yield();
   count = req.count;
 }
-inline bool FiberBackend::config_valid(const double *q) {
+template <class Service>
+inline bool FiberBackendT<Service>::config_valid(const double *q) {
   if (flags_ == 0) return true;
   req.kind = MultiRequest::VALID;
   req.q = q;
   sched_->yield();
   return req.valid;
 }
-inline void FiberBackend::check_edges(const std::vector<double> &a, const std::vector<double> &b, int num_points,
+template <class Service>
+inline void FiberBackendT<Service>::check_edges(const std::vector<double> &a, const std::vector<double> &b, int num_points,
                                       std::vector<int> &first_invalid) {
   req.kind = MultiRequest::EDGES;
   req.a = &a;
@@ -319,5 +358,7 @@ inline void FiberBackend::check_edges(const std::vector<double> &a, const std::v
   req.first_invalid = &first_invalid;
   sched_->yield();
 }
+
+typedef MultiSchedulerT<GpuService> MultiScheduler;   // the product instantiation
 
 }  // namespace sqmp_planner

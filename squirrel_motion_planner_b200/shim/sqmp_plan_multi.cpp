@@ -20,7 +20,8 @@ int main(int argc, char **argv) {
   if ((a.first + count) * 16 > a.queries.size()) count = a.queries.size() / 16 > a.first ? a.queries.size() / 16 - a.first : 0;
   sqmp_planner::Params P;
   P.lo[0] = a.xy_lo[0]; P.lo[1] = a.xy_lo[1]; P.hi[0] = a.xy_hi[0]; P.hi[1] = a.xy_hi[1];
-  sqmp_planner::MultiScheduler sched(&checker, true, true, batch);
+  sqmp_planner::GpuService service(&checker, true, true);
+  sqmp_planner::MultiScheduler sched(&service, batch);
   std::vector<sqmp_planner::MultiScheduler::Result> res;
   const auto t0 = std::chrono::steady_clock::now();
   const bool ok = sched.run(a.queries.data() + a.first * 16, count, a.iterations, a.seed, a.first, P, res);

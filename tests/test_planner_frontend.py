@@ -85,6 +85,29 @@ def test_gpu_and_cpu_backends_take_identical_decisions(tmp_path, fixture_data):
     assert sum(r[1] == "1" for r in gpu) >= 2
 
 
+def test_lockstep_scheduler_host_logic_on_the_cpu(tmp_path, fixture_data):
+    """The lock-step scheduler (shim/sqmp_multi.hpp: fibers, request gathering, answer scatter) instantiated over the CPU
+    oracle must print the sequential oracle runner's lines — batch sizes that do and do not divide the number of queries,
+    an invalid goal in the middle of a batch."""
+    world = syn.box_world(g=128, n_boxes=16, seed=21)
+    rng = np.random.default_rng(13)
+    s0, g0 = pw.config1_queries(1)
+    n = 7
+    starts, goals = np.repeat(s0, n, axis=0), np.repeat(g0, n, axis=0)
+    starts[:, :2] = rng.uniform(-2.0, -1.0, size=(n, 2))
+    goals[:, :2] = rng.uniform(1.0, 2.0, size=(n, 2))
+    goals[3, 3:] = (0.29, 2.26, 0.19, -1.17, 0.53)          # self collision: rejected like BS:351-358
+    d = _workdir(tmp_path, fixture_data, world, starts, goals)
+    seq = _run("sqmp_plan_oracle", d, "oracle", 120)
+    assert len(seq) == n and seq[3][1] == "invalid_endpoint"
+    for batch in (3, 7, 64):
+        r = subprocess.run([os.path.join(ORACLE_DIR, "sqmp_plan_oracle"), DESC, d, "oracle", "120", "1", "0", "0", str(n), str(batch)],
+                           capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout + r.stderr
+        rows = [l.split() for l in r.stdout.splitlines() if l and not l.startswith("#")]
+        assert rows == seq, "batch %d" % batch
+
+
 @pytest.mark.gpu
 def test_lockstep_multi_query_runner_repeats_the_sequential_decisions(tmp_path, fixture_data):
     """shim/sqmp_plan_multi (B queries per GPU as fibers over the same planner code, one library call per request kind
