@@ -41,6 +41,30 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def bind_to_gpu_numa(index):
+    """Run this process on the CPU cores local to GPU `index` (sysfs local_cpulist of its PCI function) so that pinned host
+    buffers are allocated on the GPU's own NUMA node: the host-buffer (e2e) path is PCIe-bound and a remote node costs up to
+    25 % of it.  Returns the cpulist string, or None when it cannot be determined."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        path = "/sys/bus/pci/devices/%s/local_cpulist" % bus[-12:].lower()
+        cpulist = open(path).read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpulist
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons through NVML while the timed regions run."""
 
@@ -180,6 +204,7 @@ def run_own(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     stream = torch.cuda.current_stream().cuda_stream
+    numa = bind_to_gpu_numa(local_rank)
 
     ctx = api.default_context(local_rank)      # raises if libsqmp_b200.so or the GPU is missing
     w, origin = make_world()
@@ -321,7 +346,7 @@ def run_own(args):
                          "kernel_ms": kern_ms, "bytes_per_state": BYTES_PER_STATE},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": s_rank * 64, "d2h_bytes_per_step": words * 4,
-                    "entry": "sqmp_check_states (pinned host buffers)", "steps": e2e_steps},
+                    "entry": "sqmp_check_states (pinned host buffers)", "steps": e2e_steps, "host_cpus": numa},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "extra": extra,
