@@ -10,13 +10,16 @@
 //   * the chain is walked in fp64 (identical frames to K1); per rigid group the frame is rounded ONCE to fp32 in
 //     coordinates relative to the base's own cell, so |fp32 centre - fp64 centre| <= err (host-computed bound, ~5e-5
 //     cells; capi.cu: refresh_grid_robot);
-//   * stage 1 (every sphere): 9 FFMA, 3 magic adds, 2 IMAD, one byte gather from the halo-padded lower-bound field —
-//     no bounds test, because the field covers every cell a sphere can reach while the base is inside the grid.
+//   * stage 1 (every sphere): two spheres per packed fp32x2 instruction (9 FFMA2 + 3 FADD2 per pair), 2 IMAD + 1 add per
+//     sphere for the cell offset, one byte gather from the halo-padded lower-bound field — no bounds test, because the
+//     field covers every cell a sphere can reach while the base is inside the grid.
 //     "lb2 > thr" with thr = floor((rg + err)^2) proves the fp64 centre free as well;
 //   * stage 2 (the ~11 % that stage 1 cannot prove free): the feature-field upper bound in fp32 against
 //     (rg - err)^2 proves a hit for the fp64 centre as well;
-//   * stage 3 (neither bound decides, ~1.5 spheres per state): the fp64 centre is formed from the fp64 frame exactly as
-//     K1 forms it and queued for the same exact bit-row scan (k1_scan.cuh).
+//   * stage 3 (neither bound decides, ~0.4 spheres per state after the early exits): the fp64 centre is formed from the
+//     fp64 frame exactly as K1 forms it and queued for the same exact bit-row scan (k1_scan.cuh).
+// Grids are launched with programmatic stream serialization (see the launcher): the next grid of the stream may start
+// while this one drains, and writes its mask only after this one has completed.
 // States whose base lies outside the grid (or is not finite) never use the fp32 path: their spheres go through the
 // reach test and the exact scan only.
 #include "k1_scan.cuh"
