@@ -566,7 +566,7 @@ def run_config5(args):
     # the rank's stream of queries runs `--batch` at a time in lock step (shim/sqmp_multi.hpp: one library call per request
     # kind and round for the whole batch); --batch 1 is the strictly sequential runner (one query in flight per GPU)
     if args.batch > 1:
-        cmd = [os.path.join(shim, "sqmp_plan_multi"), desc, d, "gpu", str(iters), "1", str(local_rank), str(first), str(count), str(args.batch)]
+        cmd = [os.path.join(shim, "sqmp_plan_multi"), desc, d, "gpu", str(iters), "1", str(local_rank), str(first), str(count), str(args.batch), str(args.threads)]
     else:
         cmd = [os.path.join(shim, "sqmp_plan"), desc, d, "gpu", str(iters), "1", str(local_rank), str(first), str(count)]
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -605,7 +605,8 @@ def run_config5(args):
             "unit": "planning queries/s", "n_gpus": world_size, "steps": 1, "warmup": 0, "ms_per_step": secs * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "config5: %d independent planning queries, W512 (512^3 voxels, 2048 boxes), one query stream per GPU, no collective" % n_queries,
-                       "iterations_per_query": iters, "flags": "SELF|MAP", "queries_in_flight_per_gpu": max(1, args.batch)},
+                       "iterations_per_query": iters, "flags": "SELF|MAP", "queries_in_flight_per_gpu": max(1, args.batch) * (args.threads if args.batch > 1 else 1),
+                       "host_threads_per_gpu": args.threads if args.batch > 1 else 1},
             "checked_states_per_s": float(agg[1]) / secs, "planner_iterations_per_s": float(agg[2]) / secs,
             "solved": int(agg[3]), "cpu_baseline": cpu, "gpu_launches": None}))
     if world_size > 1:
@@ -621,6 +622,7 @@ def main():
     ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5"])
     ap.add_argument("--queries", type=int, default=1024, help="config5: number of planning queries")
     ap.add_argument("--iterations", type=int, default=1000, help="config5: BiRRT* iterations per query")
+    ap.add_argument("--threads", type=int, default=2, help="config5: host threads per GPU, each with its own context")
     ap.add_argument("--batch", type=int, default=512, help="config5: queries in flight per GPU (1 = sequential runner)")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -93,6 +93,11 @@ const char *sqmp_version(void);
 int sqmp_set_voxel_grid(sqmp_ctx *ctx, const uint32_t *bits, int gx, int gy, int gz, const double origin[3],
                         double res);
 /* CollisionChecker::setDisabledLinkMapCollisions (CC:90-102): bit i = link i is skipped by the map check. */
+/* Second and further contexts on the SAME device (one planner thread each, e.g. shim/sqmp_plan_multi --threads) can use
+ * the voxel fields of a context that already holds the grid instead of building their own copy: dst references src's
+ * device memory (src keeps ownership and must outlive dst or dst's next sqmp_set_voxel_grid).  Both contexts must
+ * have been created from the same robot description (the halo of the fields depends on it). */
+int sqmp_share_voxel_grid(sqmp_ctx *dst, const sqmp_ctx *src);
 int sqmp_set_disabled_links(sqmp_ctx *ctx, uint64_t link_mask);
 
 /* ---- state validity ---------------------------------------------------------------------------- */

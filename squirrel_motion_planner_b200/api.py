@@ -23,7 +23,7 @@ MAX_TREES = 1024
 
 EXPORTS = [
     "sqmp_create", "sqmp_destroy", "sqmp_last_error", "sqmp_strerror", "sqmp_version", "sqmp_set_voxel_grid",
-    "sqmp_set_disabled_links", "sqmp_check_states", "sqmp_check_edges", "sqmp_get_collisions", "sqmp_fk",
+    "sqmp_share_voxel_grid", "sqmp_set_disabled_links", "sqmp_check_states", "sqmp_check_edges", "sqmp_get_collisions", "sqmp_fk",
     "sqmp_tree_reset", "sqmp_tree_append", "sqmp_tree_append_batch", "sqmp_tree_update", "sqmp_tree_update_costs",
     "sqmp_tree_size", "sqmp_nn_nearest", "sqmp_nn_radius", "sqmp_check_states_dev", "sqmp_check_edges_dev",
     "sqmp_fk_dev", "sqmp_sample_configs", "sqmp_sample_configs_dev", "sqmp_nn_nearest_multi", "sqmp_nn_radius_multi", "sqmp_nn_nearest_dev", "sqmp_nn_radius_dev", "sqmp_kernel_launches", "sqmp_set_option",
@@ -255,6 +255,11 @@ class Context:
         self._ck(self._L.sqmp_nn_radius_multi(self._h, _ptr(t), _ptr(q), _ptr(ex), q.shape[0], float(r), int(k),
                                               _ptr(low), _ptr(high), _ptr(cnt)))
         return low, high, cnt
+
+    def share_voxel_grid(self, other: "Context"):
+        """Use the voxel fields of `other` (same device, same robot) instead of building an own copy."""
+        self._L.sqmp_share_voxel_grid.argtypes = [C.c_void_p, C.c_void_p]
+        self._ck(self._L.sqmp_share_voxel_grid(self._h, other._h))
 
     def sample_configs(self, seed, first, n, lo, hi, max_tries=64):
         """sampleJointConfig_JntArray (BS:3832-3878) batched on the device: (q[n,8], tries[n])."""

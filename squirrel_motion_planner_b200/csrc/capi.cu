@@ -36,6 +36,7 @@ struct Ctx {
   SelfA *d_as = nullptr;
   SelfBlock *d_blocks = nullptr;
   SelfDev self;
+  bool grid_borrowed = false;   // the grid fields belong to another context (sqmp_share_voxel_grid): never freed here
   uint32_t *d_occ = nullptr;
   uint8_t *d_lb2 = nullptr;     // halo-padded (GridDev)
   uint16_t *d_ft = nullptr;
@@ -671,9 +672,11 @@ void sqmp_destroy(sqmp_ctx *ctx) {
   if (ctx->d_flat) cudaFree(ctx->d_flat);
   if (ctx->d_as) cudaFree(ctx->d_as);
   if (ctx->d_blocks) cudaFree(ctx->d_blocks);
-  if (ctx->d_occ) cudaFree(ctx->d_occ);
-  if (ctx->d_lb2) cudaFree(ctx->d_lb2);
-  if (ctx->d_ft) cudaFree(ctx->d_ft);
+  if (!ctx->grid_borrowed) {
+    if (ctx->d_occ) cudaFree(ctx->d_occ);
+    if (ctx->d_lb2) cudaFree(ctx->d_lb2);
+    if (ctx->d_ft) cudaFree(ctx->d_ft);
+  }
   if (ctx->d_fast_pairs) cudaFree(ctx->d_fast_pairs);
   if (ctx->d_fast_aux) cudaFree(ctx->d_fast_aux);
   if (ctx->d_fast_sph64) cudaFree(ctx->d_fast_sph64);
@@ -791,9 +794,12 @@ int sqmp_set_voxel_grid(sqmp_ctx *ctx, const uint32_t *bits, int gx, int gy, int
     return fail(c, e == cudaErrorMemoryAllocation ? SQMP_ERR_NOMEM : SQMP_ERR_CUDA, "set_voxel_grid", e);
   }
   c->launches += nl;
-  if (c->d_occ) cudaFree(c->d_occ);  // previous collision object deleted (CC:84-85)
-  if (c->d_lb2) cudaFree(c->d_lb2);
-  if (c->d_ft) cudaFree(c->d_ft);
+  if (!c->grid_borrowed) {
+    if (c->d_occ) cudaFree(c->d_occ);  // previous collision object deleted (CC:84-85)
+    if (c->d_lb2) cudaFree(c->d_lb2);
+    if (c->d_ft) cudaFree(c->d_ft);
+  }
+  c->grid_borrowed = false;
   c->d_occ = d_occ;
   c->d_lb2 = d_lb2;
   c->d_ft = d_ft;
@@ -809,6 +815,27 @@ int sqmp_set_voxel_grid(sqmp_ctx *ctx, const uint32_t *bits, int gx, int gy, int
   g.ox = origin[0]; g.oy = origin[1]; g.oz = origin[2];
   g.res = res; g.inv_res = 1.0 / res;
   g.has_grid = 1;
+  return refresh_grid_robot(c);
+}
+
+int sqmp_share_voxel_grid(sqmp_ctx *ctx, const sqmp_ctx *src) {
+  CHECK_CTX();
+  if (!src || src == ctx) return fail(c, SQMP_ERR_INVALID, "share_voxel_grid: bad source");
+  const Ctx *o = src;
+  if (o->device != c->device || !o->gd.has_grid) return fail(c, SQMP_ERR_INVALID, "share_voxel_grid: source has no grid on this device");
+  if (o->reach_m != c->reach_m || o->fast_chain_ok != c->fast_chain_ok)
+    return fail(c, SQMP_ERR_INVALID, "share_voxel_grid: contexts were created from different robot descriptions");
+  CU(cudaDeviceSynchronize());
+  if (!c->grid_borrowed) {
+    if (c->d_occ) cudaFree(c->d_occ);
+    if (c->d_lb2) cudaFree(c->d_lb2);
+    if (c->d_ft) cudaFree(c->d_ft);
+  }
+  c->d_occ = o->d_occ;
+  c->d_lb2 = o->d_lb2;
+  c->d_ft = o->d_ft;
+  c->grid_borrowed = true;
+  c->gd = o->gd;
   return refresh_grid_robot(c);
 }
 

@@ -323,6 +323,10 @@ class CollisionChecker {
     }
     setVoxelGrid(g);
   }
+  // A further checker on the same device (one per planner thread) borrows the voxel fields of `other` (CC:76-88 done once).
+  bool shareOcTreeWith(const CollisionChecker &other) {
+    return initialized_ && other.initialized_ && sqmp_share_voxel_grid(ctx_, other.ctx_) == SQMP_OK;
+  }
   // Same, from an occupancy that is already dense (tests, synthetic worlds, .bt ingest).
   void setVoxelGrid(const VoxelGrid &g) {
     if (!initialized_ || g.bits.empty()) return;

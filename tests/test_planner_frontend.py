@@ -131,3 +131,8 @@ def test_lockstep_multi_query_runner_repeats_the_sequential_decisions(tmp_path, 
         assert r.returncode == 0, r.stdout + r.stderr
         rows = [l.split() for l in r.stdout.splitlines() if l and not l.startswith("#")]
         assert rows == seq, "batch %d" % batch
+    # several host threads, each with its own context on the same GPU and the voxel fields shared (sqmp_share_voxel_grid)
+    r = subprocess.run([os.path.join(SHIM, "sqmp_plan_multi"), DESC, d, "gpu", "300", "1", "0", "0", str(n), "3", "3"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert [l.split() for l in r.stdout.splitlines() if l and not l.startswith("#")] == seq
