@@ -270,7 +270,10 @@ k_nn_wq(TreePtrs t, int64_t N, int64_t chunk_len, int chunks, const double *__re
 // bit-identical to the CPU's.  Radius mode: s~ + E < s_thr is a proven hit, s~ - E >= s_thr a proven miss, only
 // the band in between is evaluated in fp64.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int NN_GROUP = 4;        // nodes whose estimates are taken before the one (rare) branch
+#ifndef NN_GROUP_DEF
+#define NN_GROUP_DEF 8
+#endif
+constexpr int NN_GROUP = NN_GROUP_DEF;   // nodes whose estimates are taken before the one (rare) branch
 #ifndef NN_QPT_DEF
 #define NN_QPT_DEF 2
 #endif
