@@ -656,6 +656,49 @@ def test_full_size_config2_properties(ctx, orc):
     assert not np.any((unpack(ref, len(sel)) != unpack(m_states, S)[sel]) & (np.abs(cm) > BAND))
 
 
+def test_full_size_config4_sharding_invariance(ctx, orc):
+    """2^26 states vs W256 (BASELINE.json configs[3]), generated on the device (K5) so that no 4 GiB host array is
+    needed: the mask of the whole batch equals the concatenation of the masks of its 8 rank shards (what the multi-GPU
+    run all-gathers), both kernels agree on a 2^22 slice, and a seeded sample agrees with the oracle."""
+    import torch
+    w = syn.box_world(g=256, n_boxes=64, seed=1234)
+    origin = w.origin + np.array([0, 0, rd.OCTREE_Z_OFFSET])
+    ctx.set_voxel_grid(w.bits, w.dims, origin, w.res)
+    orc.set_grid(w.bits, w.dims, origin, w.res)
+    S, R = 1 << 26, 8
+    stream = torch.cuda.current_stream().cuda_stream
+    lo = np.array([-5.0, -5.0, -np.pi, -1.2, -1.7, -1.8, -2.4, -2.9])
+    hi = np.array([5.0, 5.0, np.pi, 1.5, 2.6, 1.8, 2.4, 2.9])
+    d_q = torch.empty((S, 8), dtype=torch.float64, device="cuda")
+    ctx.sample_configs_dev(2026, 0, S, lo, hi, 8, d_q, None, stream)
+    d_whole = torch.zeros(S // 32, dtype=torch.int32, device="cuda")
+    d_parts = torch.zeros(S // 32, dtype=torch.int32, device="cuda")
+    ctx.check_states_dev(d_q, S, api.CHECK_MAP, d_whole, stream)
+    for r in range(R):                                                   # rank r's shard, written into its slot
+        lo_s, n = r * (S // R), S // R
+        ctx.check_states_dev(d_q[lo_s:], n, api.CHECK_MAP, d_parts[lo_s // 32:], stream)
+    torch.cuda.synchronize()
+    assert torch.equal(d_whole, d_parts)
+    frac = float(torch.sum(torch.bitwise_count(d_whole).to(torch.int64)).item()) / S if hasattr(torch, "bitwise_count") else \
+        float(np.unpackbits(d_whole[: 1 << 16].cpu().numpy().view(np.uint8)).mean())
+    assert 0.05 < frac < 0.95
+    n_slice = 1 << 22
+    d_a = torch.zeros(n_slice // 32, dtype=torch.int32, device="cuda")
+    ctx.set_option("k1_kernel", 1)
+    ctx.check_states_dev(d_q[S // 2:], n_slice, api.CHECK_MAP, d_a, stream)
+    ctx.set_option("k1_kernel", 0)
+    torch.cuda.synchronize()
+    assert torch.equal(d_a, d_whole[S // 64: S // 64 + n_slice // 32])
+    sel = np.random.default_rng(1).choice(S, 20000, replace=False)
+    sel.sort()
+    q_sel = d_q[torch.from_numpy(sel).cuda()].cpu().numpy()
+    got = unpack(d_whole.cpu().numpy(), S)[sel]
+    ref, cm, _ = orc.check_states(q_sel, oracle.FLAG_MAP, clearance=True, nthreads=8)
+    assert not np.any((unpack(ref, len(sel)) != got) & (np.abs(cm) > BAND))
+    del d_q, d_whole, d_parts
+    torch.cuda.empty_cache()
+
+
 def test_full_size_config3_properties(ctx):
     """2^20-node tree (configs[2]): a seeded subset of queries against the oracle, bit-exact, both mappings."""
     N = 1 << 20
