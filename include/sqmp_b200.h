@@ -163,6 +163,11 @@ int sqmp_nn_radius_multi(sqmp_ctx *ctx, const int32_t *tree, const double *queri
 /* ---- device-pointer variants (benchmark harness, multi-GPU sharding) ---------------------------- */
 /* Same semantics; all pointers are device pointers on the context's GPU; work is enqueued on `stream`
  * (a cudaStream_t, NULL = default stream) and NOT synchronised. */
+/* Ordering contract of the validity *_dev calls: consecutive calls on one stream may overlap (a grid starts while its
+ * predecessor drains; it writes its mask only after the predecessor has completed, so reusing one mask buffer is safe).
+ * A grid reads its states BEFORE that point, so the operation enqueued on the stream immediately before a validity call
+ * must not be a foreign kernel that produces those states; the library's own kernels never are (they break the overlap
+ * chain).  sqmp_set_option(ctx, "launch_overlap", 0) restores plain stream order. */
 int sqmp_check_states_dev(sqmp_ctx *ctx, const double *d_q, int64_t S, unsigned flags, uint32_t *d_mask,
                           void *stream);
 int sqmp_check_edges_dev(sqmp_ctx *ctx, const double *d_q_start, const double *d_q_end, int64_t E, int num_points,

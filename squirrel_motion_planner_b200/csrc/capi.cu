@@ -46,7 +46,9 @@ struct Ctx {
   double4 *d_fast_sph64 = nullptr;
   int fast_chain_ok = 0;        // description: translation-only base, then rotations only, spheres on the rotating part
   double reach_m = 0.0;         // max distance of a sphere centre from the base reference point (metres)
-  int launch_overlap = 1;       // K1F grids may start while the previous grid of the stream drains its last wave (PDL)
+  int launch_overlap = 1;       // K1F grids may start while the previous K1F grid of the stream drains its last wave (PDL)
+  int64_t k1f_seq = -1;         // value of `launches` right after the last K1F launch, and the stream it went to:
+  cudaStream_t k1f_stream = nullptr;   // overlap is requested only when nothing else was launched by this context since
   int k1_kernel = 0;            // 0 auto (fast when its preconditions hold) | 1 generic | 2 fast (error if not possible)
   TreeDev trees[SQMP_MAX_TREES];
   NNScratch nn;
@@ -851,6 +853,18 @@ int sqmp_set_disabled_links(sqmp_ctx *ctx, uint64_t link_mask) {
 // ---------------------------------------------------------------------------------------------------- validity
 // The fast kernel decides the same predicate as the generic fp64 kernel (fp32 only where a proven error bound makes it
 // safe, fp64 for everything near contact); it needs a map check against a grid with halo-padded fields.
+// Programmatic overlap is requested only for a K1F launch that directly follows another K1F launch of this context on
+// the same stream: K1F reads its inputs before it waits for its predecessor, so the predecessor must not be their
+// producer.  K1F never writes states, the library's own producers (the sampler, ...) break the chain here, and a
+// caller who enqueues a foreign producer of the states between two validity calls on one stream must set
+// launch_overlap = 0 (include/sqmp_b200.h).
+static bool k1f_may_overlap(const Ctx *c, cudaStream_t st) {
+  return c->launch_overlap != 0 && c->k1f_seq == c->launches && c->k1f_stream == st;
+}
+static void k1f_launched(Ctx *c, cudaStream_t st) {
+  c->k1f_seq = c->launches;
+  c->k1f_stream = st;
+}
 static bool use_fast_k1(const Ctx *c, unsigned flags) {
   if (c->k1_kernel == 1 || c->fk_precision != 64) return false;
   return c->fast.ok && (flags & SQMP_CHECK_MAP) && c->gd.has_grid;
@@ -866,13 +880,15 @@ int sqmp_check_states_dev(sqmp_ctx *ctx, const double *d_q, int64_t S, unsigned 
     return SQMP_OK;
   }
   int nl = 0;
-  if (use_fast_k1(c, flags))
+  const bool fast = use_fast_k1(c, flags);
+  if (fast)
     CU(launch_check_states_fast(c->rb_grid, c->gd, c->self, c->fast, d_q, nullptr, 0, S, flags, d_mask,
-                                c->chain_specialization != 0, c->launch_overlap != 0, st, &nl));
+                                c->chain_specialization != 0, k1f_may_overlap(c, st), st, &nl));
   else
     CU(launch_check_states(c->rb_grid, c->gd, c->self, d_q, nullptr, 0, S, flags, d_mask, c->fk_precision,
                            st, &nl));
   c->launches += nl;
+  if (fast) k1f_launched(c, st);
   return SQMP_OK;
 }
 
@@ -889,13 +905,15 @@ int sqmp_check_edges_dev(sqmp_ctx *ctx, const double *d_a, const double *d_b, in
     CU(cudaMemsetAsync(d_mask, 0, size_t((S + 31) / 32) * 4, st));
   } else {
     int nl = 0;
-    if (use_fast_k1(c, flags))
+    const bool fast = use_fast_k1(c, flags);
+    if (fast)
       CU(launch_check_states_fast(c->rb_grid, c->gd, c->self, c->fast, d_a, d_b, num_points, S, flags, d_mask,
-                                  c->chain_specialization != 0, c->launch_overlap != 0, st, &nl));
+                                  c->chain_specialization != 0, k1f_may_overlap(c, st), st, &nl));
     else
       CU(launch_check_states(c->rb_grid, c->gd, c->self, d_a, d_b, num_points, S, flags, d_mask,
                              c->fk_precision, st, &nl));
     c->launches += nl;
+    if (fast && !d_first) k1f_launched(c, st);
   }
   if (d_first) {
     CU(launch_first_invalid(d_mask, E, P1, d_first, st));
