@@ -94,69 +94,72 @@ __device__ __forceinline__ void fk_one(const RobotDev &rb, const double *q_row, 
   get_quaternion(R, out7[3], out7[4], out7[5], out7[6]);
 }
 
+// Warp-private tiles: every warp of the CTA streams its own 32-state tiles (2 KB in, 1.75 KB out) through its own
+// double-buffered shared-memory slice with its own pair of mbarriers — no __syncthreads anywhere, so a warp never waits
+// for the slowest warp of its CTA (the CTA-wide barriers of the previous version held ~14 % of the stall samples).
+constexpr int FK_WARP_TILE = 32;
 template <typename T, typename SIG>
-__global__ void __launch_bounds__(FK_TILE)
+__global__ void __launch_bounds__(FK_TILE, 8)
 k2_fk(const __grid_constant__ RobotDev rb, const double *__restrict__ q_in, int64_t S, double *__restrict__ out) {
-  __shared__ __align__(128) double s_in[2][FK_TILE * FK_IN_PITCH];
-  __shared__ __align__(128) double s_out[FK_TILE * FK_OUT_PITCH];
-  __shared__ __align__(8) uint64_t bar[2];
-  const int t = threadIdx.x;
-  const int64_t n_tiles = (S + FK_TILE - 1) / FK_TILE;
-  if (t == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
+  constexpr int WARPS = FK_TILE / 32;
+  __shared__ __align__(128) double s_in[WARPS][2][FK_WARP_TILE * FK_IN_PITCH];
+  __shared__ __align__(128) double s_out[WARPS][FK_WARP_TILE * FK_OUT_PITCH];
+  __shared__ __align__(8) uint64_t bar[WARPS][2];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t n_tiles = (S + FK_WARP_TILE - 1) / FK_WARP_TILE;
+  const int64_t stride = int64_t(gridDim.x) * WARPS;
+  if (lane == 0) {
+    mbar_init(&bar[w][0], 1);
+    mbar_init(&bar[w][1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
+  __syncwarp();
 
-  auto tile_rows = [&](int64_t tile) { return int(imin64(FK_TILE, S - tile * FK_TILE)); };
-  int64_t tile = blockIdx.x;
-  if (t == 0 && tile < n_tiles) {
+  auto tile_rows = [&](int64_t tile) { return int(imin64(FK_WARP_TILE, S - tile * FK_WARP_TILE)); };
+  int64_t tile = int64_t(blockIdx.x) * WARPS + w;
+  if (lane == 0 && tile < n_tiles) {
     const uint32_t bytes = uint32_t(tile_rows(tile)) * SQMP_DOF * sizeof(double);
-    mbar_expect_tx(&bar[0], bytes);
-    bulk_g2s(s_in[0], q_in + tile * FK_TILE * SQMP_DOF, bytes, &bar[0]);
+    mbar_expect_tx(&bar[w][0], bytes);
+    bulk_g2s(s_in[w][0], q_in + tile * FK_WARP_TILE * SQMP_DOF, bytes, &bar[w][0]);
   }
   uint32_t phase[2] = {0, 0};
   int buf = 0;
-  for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
-    // prefetch the next tile of this CTA into the other buffer (its previous contents were consumed one
-    // iteration ago, before the __syncthreads at the end of that iteration)
-    const int64_t next = tile + gridDim.x;
-    if (t == 0 && next < n_tiles) {
+  for (; tile < n_tiles; tile += stride, buf ^= 1) {
+    // prefetch this warp's next tile into its other buffer (consumed one iteration ago, before the __syncwarp below)
+    const int64_t next = tile + stride;
+    if (lane == 0 && next < n_tiles) {
       const uint32_t bytes = uint32_t(tile_rows(next)) * SQMP_DOF * sizeof(double);
-      mbar_expect_tx(&bar[buf ^ 1], bytes);
-      bulk_g2s(s_in[buf ^ 1], q_in + next * FK_TILE * SQMP_DOF, bytes, &bar[buf ^ 1]);
+      mbar_expect_tx(&bar[w][buf ^ 1], bytes);
+      bulk_g2s(s_in[w][buf ^ 1], q_in + next * FK_WARP_TILE * SQMP_DOF, bytes, &bar[w][buf ^ 1]);
     }
-    mbar_wait(&bar[buf], phase[buf]);
+    mbar_wait(&bar[w][buf], phase[buf]);
     phase[buf] ^= 1;
 
     const int rows = tile_rows(tile);
-    if (t < rows) {
+    if (lane < rows) {
       double o[7];
-      fk_one<T, SIG>(rb, s_in[buf] + t * FK_IN_PITCH, o);   // 8 LDS.64 per state (8-way bank conflicts: ~1 % of the work)
-      // the previous tile's bulk store must have finished reading s_out before it is overwritten
-      // (wait executed by the issuing thread below, made visible to all by the __syncthreads)
-      if (rows == FK_TILE) {
-        double *orow = s_out + t * FK_OUT_PITCH;
+      fk_one<T, SIG>(rb, s_in[w][buf] + lane * FK_IN_PITCH, o);
+      if (rows == FK_WARP_TILE) {
+        double *orow = s_out[w] + lane * FK_OUT_PITCH;
 #pragma unroll
         for (int j = 0; j < 7; ++j) orow[j] = o[j];
       } else {
         // ragged last tile: its byte count need not be a multiple of 16, which bulk copies require
-        double *orow = out + (tile * FK_TILE + t) * 7;
+        double *orow = out + (tile * FK_WARP_TILE + lane) * 7;
 #pragma unroll
         for (int j = 0; j < 7; ++j) orow[j] = o[j];
       }
     }
     fence_async_smem();  // make the generic-proxy writes to s_out visible to the async (bulk copy) proxy
-    __syncthreads();
-    if (t == 0 && rows == FK_TILE) {
-      bulk_s2g(out + tile * FK_TILE * 7, s_out, uint32_t(FK_TILE) * 7 * sizeof(double));
+    __syncwarp();
+    if (lane == 0 && rows == FK_WARP_TILE) {
+      bulk_s2g(out + tile * FK_WARP_TILE * 7, s_out[w], uint32_t(FK_WARP_TILE) * 7 * sizeof(double));
       bulk_commit();
-      bulk_wait_read0();  // s_out may be rewritten once the copy engine has read it
+      bulk_wait_read0();  // s_out[w] may be rewritten once the copy engine has read it
     }
-    __syncthreads();
+    __syncwarp();
   }
-  if (t == 0) bulk_wait0();
+  if (lane == 0) bulk_wait0();
 }
 
 cudaError_t launch_fk(const RobotDev &rb, const double *d_q, int64_t S, double *d_out, int fk_precision,
@@ -169,7 +172,7 @@ cudaError_t launch_fk(const RobotDev &rb, const double *d_q, int64_t S, double *
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
   }
-  const int64_t n_tiles = (S + FK_TILE - 1) / FK_TILE;
+  const int64_t n_tiles = (S + FK_TILE - 1) / FK_TILE;   // CTAs needed if every warp took one 32-state tile
   // persistent CTAs: a multiple of the SM count, enough resident warps to cover the fp64 latency
   const unsigned blocks = unsigned(imin64(n_tiles, int64_t(sms) * 8));
   const bool robotino = allow_specialized && chain_matches<SigRobotino>(rb);   // structure known at compile time: unrolled chain
