@@ -276,6 +276,29 @@ def test_back_to_back_launches_keep_serial_semantics(world_ctx):
     ctx.set_option("launch_overlap", 1)
 
 
+def test_shared_voxel_grid_between_contexts(world_ctx, fixture_data):
+    """sqmp_share_voxel_grid: a second context on the same device borrows the owner's fields (one copy in HBM) and
+    returns the same masks; its own disable mask and a later grid of its own do not disturb the owner."""
+    ctx, orc, w, origin = world_ctx
+    lt, fx, spheres = fixture_data
+    q = syn.state_batch(21 * 300, seed=81, xy_half=2.2)
+    want = ctx.check_states(q, api.CHECK_MAP | api.CHECK_SELF)
+    c2 = api.Context(rd.compile_robot(lt, spheres), 0)
+    try:
+        with pytest.raises(api.SqmpError):
+            ctx.share_voxel_grid(ctx)                                      # a context cannot borrow from itself
+        c2.share_voxel_grid(ctx)
+        assert np.array_equal(c2.check_states(q, api.CHECK_MAP | api.CHECK_SELF), want)
+        c2.set_disabled_links(rd.link_mask(lt, ["head_link"]))             # per-context, the fields stay shared
+        assert np.array_equal(ctx.check_states(q, api.CHECK_MAP | api.CHECK_SELF), want)
+        w2 = syn.box_world(g=48, n_boxes=4, seed=2)
+        c2.set_voxel_grid(w2.bits, w2.dims, w2.origin, w2.res)            # an own grid replaces the borrowed one
+        assert np.array_equal(ctx.check_states(q, api.CHECK_MAP | api.CHECK_SELF), want)
+    finally:
+        c2.close()
+    assert np.array_equal(ctx.check_states(q, api.CHECK_MAP | api.CHECK_SELF), want)   # the owner outlives the borrower
+
+
 def test_fast_kernel_rejected_without_its_preconditions(fixture_data):
     """k1_kernel = 2 is an error for a description whose base is not a translation-only run (no silent fallback)."""
     lt, fx, spheres = fixture_data
