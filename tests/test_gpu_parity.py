@@ -118,6 +118,26 @@ def test_grid_partially_covering_the_robot(ctx, orc):
     assert differs.sum() == 0 and 0.02 < got.mean() < 0.98
 
 
+@pytest.mark.parametrize("res,dims", [(0.025, (150, 170, 90)), (0.08, (60, 45, 30)), (0.1, (40, 52, 25))])
+def test_other_resolutions_match_oracle(ctx, orc, res, dims):
+    """Grid resolution other than the reference's 0.05 m (sphere radii between 0.1 and 10 cells, other halo widths,
+    other integer thresholds): both kernels against the oracle, no disagreement outside the band."""
+    w = syn.box_world(g=64, res=res, n_boxes=14, seed=int(res * 1000), dims=dims, z_low=-0.3)
+    origin = w.origin + np.array([0.07, -0.11, rd.OCTREE_Z_OFFSET])
+    ctx.set_disabled_links(0)
+    orc.set_disabled_links(0)
+    ctx.set_voxel_grid(w.bits, w.dims, origin, w.res)
+    orc.set_grid(w.bits, w.dims, origin, w.res)
+    q = syn.state_batch(21 * 250, seed=97, xy_half=min(dims[0], dims[1]) * res / 2.0 * 1.2)
+    try:
+        for kernel in (1, 2):
+            ctx.set_option("k1_kernel", kernel)
+            got, ref, clr, differs = _verdict_parity(ctx, orc, q, api.CHECK_MAP)
+            assert differs.sum() == 0 and 0.02 < got.mean() < 0.98
+    finally:
+        ctx.set_option("k1_kernel", 0)
+
+
 def test_real_scene_room3_with_floor_patch(ctx, orc):
     """The reference's own room3.bt octomap (tests/golden/rooms_bt.npz), run through the .bt writer/parser, with the
     planner node's floor patch (squirrel_8dof_planner.cpp:886-904) around the robot: a 202 x 322 x 15 grid (not a cube,
