@@ -198,3 +198,19 @@ def test_sphere_fit_covers_every_reference_primitive(fixture_data):
         assert g["covered"] == 1.0 and g["protrusion"] <= r + 1e-12
     assert sf.parse_shape("cylinder r=0.23 l=0.25") == ("cylinder", (0.23, 0.25)) and sf.parse_shape("mesh x.stl") is None
     assert np.allclose(sf.segment_distance([[0, 1, 0.5], [0, 0, 2]], [0, 0, 0], [0, 0, 1]), [1.0, 1.0])
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) needs no GPU: one JSON line with the
+    contract's keys, the oracle port as `cpu_baseline`, zero-byte `e2e`."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "configs/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"] and line["gpu_launches"] == 0
