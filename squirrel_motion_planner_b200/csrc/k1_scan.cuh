@@ -216,4 +216,43 @@ static __device__ __noinline__ unsigned drain_queue(const GridDev &gd, const War
   return __reduce_or_sync(FULL, hm);
 }
 
+// ------------------------------------------------------------------------------------------------
+// the state of one thread: either given (row sl of q_in), or interpolated from the end points of edge sl / (P + 1)
+// with the reference's exact operation order (BS:4461-4462, 4478; no FMA); then parked in shared memory, prismatic
+// values converted to grid units.  Returns false for a non-finite or absurd joint value (no map test for that state).
+// ------------------------------------------------------------------------------------------------
+template <bool EDGES>
+__device__ __forceinline__ void k1_load_state(const double *__restrict__ q_in, const double *__restrict__ q_end, int num_points,
+                                              int64_t sl, double (&q)[SQMP_DOF]) {
+  if (EDGES) {
+    const int P1 = num_points + 1;
+    const int64_t e = sl / P1;
+    const int kk = int(sl - e * P1);
+    const double4 *a4 = reinterpret_cast<const double4 *>(q_in + e * SQMP_DOF);
+    const double4 *b4 = reinterpret_cast<const double4 *>(q_end + e * SQMP_DOF);
+    const double4 a0 = a4[0], a1 = a4[1], b0 = b4[0], b1 = b4[1];
+    const double st[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const double en[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const double np = double(num_points), fk = double(kk);
+#pragma unroll
+    for (int j = 0; j < SQMP_DOF; ++j)
+      q[j] = __dadd_rn(st[j], __dmul_rn(fk, __ddiv_rn(__dsub_rn(en[j], st[j]), np)));
+  } else {
+    const double4 *p4 = reinterpret_cast<const double4 *>(q_in + sl * SQMP_DOF);
+    const double4 v0 = p4[0], v1 = p4[1];
+    q[0] = v0.x; q[1] = v0.y; q[2] = v0.z; q[3] = v0.w;
+    q[4] = v1.x; q[5] = v1.y; q[6] = v1.z; q[7] = v1.w;
+  }
+}
+__device__ __forceinline__ bool k1_park_state(const RobotDev &rb, const double (&q)[SQMP_DOF], double *q_mine, int pitch) {
+  bool sane = true;
+#pragma unroll
+  for (int j = 0; j < SQMP_DOF; ++j) {
+    const double v = ((rb.trans_mask >> j) & 1) ? q[j] * rb.len_scale : q[j];
+    sane = sane && (fabs(v) < 1.0e9);
+    q_mine[j * pitch] = v;
+  }
+  return sane;
+}
+
 }  // namespace sqmp

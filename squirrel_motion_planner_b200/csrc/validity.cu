@@ -60,37 +60,11 @@ k1_check_states(const __grid_constant__ RobotDev rb, const __grid_constant__ Gri
   bool hit = false;
   int qcount = 0;  // warp-uniform
 
-  // ---- the state: either given, or interpolated from the edge end points (BS:4461-4462, 4478; no FMA) ----
+  // ---- the state (given, or interpolated from the edge end points), parked in shared memory (own column): the chain
+  //      walk picks q[seg_qidx] with one LDS ----
   double q[SQMP_DOF];
-  if (EDGES) {
-    const int P1 = num_points + 1;
-    const int64_t e = sl / P1;
-    const int kk = int(sl - e * P1);
-    const double4 *a4 = reinterpret_cast<const double4 *>(q_in + e * SQMP_DOF);
-    const double4 *b4 = reinterpret_cast<const double4 *>(q_end + e * SQMP_DOF);
-    const double4 a0 = a4[0], a1 = a4[1], b0 = b4[0], b1 = b4[1];
-    const double st[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const double en[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    const double np = double(num_points), fk = double(kk);
-#pragma unroll
-    for (int j = 0; j < SQMP_DOF; ++j)
-      q[j] = __dadd_rn(st[j], __dmul_rn(fk, __ddiv_rn(__dsub_rn(en[j], st[j]), np)));
-  } else {
-    const double4 *p4 = reinterpret_cast<const double4 *>(q_in + sl * SQMP_DOF);
-    const double4 v0 = p4[0], v1 = p4[1];
-    q[0] = v0.x; q[1] = v0.y; q[2] = v0.z; q[3] = v0.w;
-    q[4] = v1.x; q[5] = v1.y; q[6] = v1.z; q[7] = v1.w;
-  }
-  // prismatic joint values are lengths: into grid units with everything else.  A state with a non-finite or
-  // absurd joint value cannot reach the grid (and would break the integer cell arithmetic): map check skipped.
-  // The vector is parked in shared memory (own column, no sharing): the chain walk picks q[seg_qidx] with one LDS.
-  bool sane = true;
-#pragma unroll
-  for (int j = 0; j < SQMP_DOF; ++j) {
-    const double v = ((rb.trans_mask >> j) & 1) ? q[j] * rb.len_scale : q[j];
-    sane = sane && (fabs(v) < 1.0e9);
-    q_mine[j * K1_THREADS] = v;
-  }
+  k1_load_state<EDGES>(q_in, q_end, num_points, sl, q);
+  const bool sane = k1_park_state(rb, q, q_mine, K1_THREADS);   // false: non-finite / absurd joint value, no map test
 
   // ---- base reference point = position after the leading prismatic run ----
   double pref[3] = {rb.root_off[0], rb.root_off[1], rb.root_off[2]};
