@@ -226,9 +226,11 @@ def run_own(args):
         wl = "config2: 2^20 interpolated 8-DOF states per GPU vs W256 (256^3 voxels, res 0.05), map check"
     d_q = [torch.from_numpy(b).to(dev) for b in batches]
     words = (s_rank + 31) // 32
-    # gathered mask, every rank; double-buffered so that the all-gather of step i (comm stream) overlaps the kernel of
-    # step i + 1 (compute stream).  The kernel writes straight into the rank's slot of the gather buffer.
-    NBUF = 2 if world_size > 1 else 1
+    # gathered mask, every rank; NBUF buffers in rotation so that the gather of step i (comm stream) overlaps the kernels
+    # of the following steps (compute stream).  The kernel writes straight into the rank's slot of the gather buffer.
+    # Buffer reuse is throttled on the HOST (the launch of step i blocks until the gather of step i - NBUF has completed):
+    # a stream-side wait on the other stream's event between two validity launches would cancel their launch overlap.
+    NBUF = 4 if world_size > 1 else 1
     d_all = [torch.zeros(world_size * words, dtype=torch.int32, device=dev) for _ in range(NBUF)]
     d_mine = [a[rank * words:(rank + 1) * words] for a in d_all]
     flags = api.CHECK_MAP
@@ -237,11 +239,47 @@ def run_own(args):
     gather_done = [torch.cuda.Event() for _ in range(NBUF)]
     gathers_issued = [False] * NBUF
 
+    # --gather p2p (default when it can be set up): the all-gather is fused into the validity kernel — every rank's
+    # kernel stores its mask words straight into every rank's gather buffer through peer-mapped pointers (CUDA IPC, NVLink
+    # stores); on the communication stream, behind the kernel, a one-warp kernel publishes the step in every rank's flag
+    # array and another waits for all ranks' flags (= the mask of the step has reached this rank).
+    # --gather nccl: one ncclAllGather per step.
+    pg, gather_mode, d_status = None, "nccl", None
+    if world_size > 1 and args.gather in ("auto", "p2p"):
+        try:
+            from squirrel_motion_planner_b200.peer_gather import PeerGather
+            pg = PeerGather(rank, world_size, words, NBUF)
+            d_status = torch.zeros(1, dtype=torch.int32, device=dev)
+            gather_mode = "p2p-fused"
+        except Exception as e:                        # e.g. CUDA IPC not permitted in this container
+            if args.gather == "p2p":
+                raise
+            if rank == 0:
+                print("bench: fused peer gather unavailable (%s), using NCCL" % e, file=sys.stderr)
+            pg = None
+        ok = torch.tensor([1 if pg is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)     # all ranks or none
+        if int(ok.item()) == 0 and pg is not None:
+            pg.close()
+            pg, gather_mode = None, "nccl"
+    step_no = [0]
+
     def step(i):
         b = i % NBUF
         cur = torch.cuda.current_stream()
         if world_size > 1 and gathers_issued[b]:
-            cur.wait_event(gather_done[b])            # buffer b is free again once its previous all-gather has finished
+            gather_done[b].synchronize()              # buffer b is free again once its previous gather has finished
+        if pg is not None:
+            step_no[0] += 1
+            ctx.check_states_gather_dev(d_q[i % n_rot], s_rank, flags, pg.structs[b], stream)
+            kernel_done[b].record(cur)
+            with torch.cuda.stream(comm):             # behind the kernel: publish the step, then wait for every rank's
+                comm.wait_event(kernel_done[b])
+                ctx.gather_signal_dev(pg.structs[b], step_no[0], comm.cuda_stream)
+                ctx.gather_wait_dev(pg.flags_ptr, world_size, step_no[0], d_status, comm.cuda_stream)
+                gather_done[b].record(comm)
+            gathers_issued[b] = True
+            return
         ctx.check_states_dev(d_q[i % n_rot], s_rank, flags, d_mine[b], stream)
         if world_size > 1:
             kernel_done[b].record(cur)
@@ -250,6 +288,19 @@ def run_own(args):
                 dist.all_gather_into_tensor(d_all[b], d_mine[b])
                 gather_done[b].record(comm)
             gathers_issued[b] = True
+
+    if pg is not None:                                # the fused gather must deliver what ncclAllGather delivers
+        ctx.check_states_dev(d_q[0], s_rank, flags, d_mine[0], stream)
+        dist.all_gather_into_tensor(d_all[0], d_mine[0])
+        step(0)
+        torch.cuda.current_stream().wait_stream(comm)
+        torch.cuda.synchronize()
+        got = torch.empty_like(d_all[0])
+        pg.copy_buffer_to(0, got)
+        same = torch.tensor([1 if (torch.equal(got, d_all[0]) and int(d_status.item()) == 0) else 0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        if int(same.item()) == 0:
+            raise RuntimeError("fused peer gather does not reproduce the NCCL all-gather")
 
     def drain():                                      # every all-gather issued so far has completed
         if world_size > 1:
@@ -277,6 +328,8 @@ def run_own(args):
         torch.cuda.synchronize()
     launches = ctx.kernel_launches - l0
     total_ms = e_start.elapsed_time(e_stop)
+    if pg is not None and int(d_status.item()) != 0:
+        raise RuntimeError("fused peer gather: a rank's flags did not arrive (timeout)")
     if world_size > 1:                                # the kernel alone (roofline): same launches without the collective
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k0.record()
@@ -338,7 +391,9 @@ def run_own(args):
             "config": {"workload": wl, "states_per_gpu": s_rank, "flags": "MAP",
                        "l2": "inputs rotate over %d distinct batches (%d MiB > 126 MiB L2); the 18 MiB grid + distance "
                              "field stay resident by design" % (n_rot, n_rot * s_rank * 64 >> 20),
-                       "colliding_fraction": n_colliding / s_rank, "entry": "sqmp_check_states_dev",
+                       "colliding_fraction": n_colliding / s_rank,
+                       "entry": "sqmp_check_states_gather_dev" if pg is not None else "sqmp_check_states_dev",
+                       "mask_gather": gather_mode if world_size > 1 else "none (1 GPU)",
                        "kernel": "K1F (fp32 proof stages with a proven error bound, fp64 exact stage; verdicts identical "
                                  "to the all-fp64 kernel)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -356,6 +411,10 @@ def run_own(args):
             with open(traffic_file) as f:
                 line["roofline"]["traffic"] = json.load(f).get("dram_bytes_per_launch")
         print(json.dumps(line))
+    if pg is not None:
+        torch.cuda.synchronize()
+        dist.barrier()
+        pg.close()
     ctx.close()
     if world_size > 1:
         dist.destroy_process_group()
@@ -624,6 +683,8 @@ def main():
     ap.add_argument("--iterations", type=int, default=1000, help="config5: BiRRT* iterations per query")
     ap.add_argument("--threads", type=int, default=2, help="config5: host threads per GPU, each with its own context")
     ap.add_argument("--batch", type=int, default=512, help="config5: queries in flight per GPU (1 = sequential runner)")
+    ap.add_argument("--gather", default="nccl", choices=["auto", "p2p", "nccl"],
+                    help="N > 1: mask all-gather fused into the kernel over peer memory (p2p) or ncclAllGather (nccl)")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -30,6 +30,7 @@ extern "C" {
 #define SQMP_MAX_SEG 8
 #define SQMP_MAX_SPHERES 128
 #define SQMP_MAX_PAIRS 4096
+#define SQMP_MAX_PEERS 8       /* GPUs of one node in the fused mask all-gather */
 #define SQMP_MAX_TREES 1024   /* two per concurrent planning query (shim/sqmp_multi.hpp) */
 
 #define SQMP_JOINT_ROT 1
@@ -172,6 +173,25 @@ int sqmp_check_states_dev(sqmp_ctx *ctx, const double *d_q, int64_t S, unsigned 
                           void *stream);
 int sqmp_check_edges_dev(sqmp_ctx *ctx, const double *d_q_start, const double *d_q_end, int64_t E, int num_points,
                          unsigned flags, uint32_t *d_mask, int32_t *d_first_invalid, void *stream);
+/* Multi-GPU (states sharded over the ranks of one node, masks gathered on every rank) with the gather
+ * fused into the validity kernel: every rank's kernel writes its mask words straight into the gather buffer of every
+ * rank through peer-mapped device pointers (CUDA IPC + NVLink stores) — no collective launch in the step.  `mask[p]` /
+ * `flag[p]` are rank p's gather buffer and flag array (uint32[n_peers], zero-initialised) as mapped into this process;
+ * this rank's words go to mask[p][word_offset ...].  The kernel only stores; sqmp_gather_signal_dev, enqueued AFTER it
+ * in stream order (same stream, or another stream behind an event), publishes `step` (use 1, 2, 3, ...) in flag[p][rank]
+ * of every rank — the completed validity grid orders its stores before that.  sqmp_gather_wait_dev enqueues a one-warp
+ * kernel that returns once this rank's flag array shows `step` for all n_peers ranks (status 0) or ~2 s have passed (1):
+ * work enqueued behind it sees the complete gathered mask of the step. */
+typedef struct sqmp_peer_gather {
+  int32_t n_peers, rank;
+  uint32_t *mask[SQMP_MAX_PEERS];
+  uint32_t *flag[SQMP_MAX_PEERS];
+  int64_t word_offset;
+} sqmp_peer_gather;
+int sqmp_check_states_gather_dev(sqmp_ctx *ctx, const double *d_q, int64_t S, unsigned flags, const sqmp_peer_gather *g,
+                                 void *stream);
+int sqmp_gather_signal_dev(sqmp_ctx *ctx, const sqmp_peer_gather *g, uint32_t step, void *stream);
+int sqmp_gather_wait_dev(sqmp_ctx *ctx, const uint32_t *d_flags, int n_peers, uint32_t step, int32_t *d_status, void *stream);
 int sqmp_sample_configs_dev(sqmp_ctx *ctx, uint64_t seed, int64_t first, int64_t n, const double lo[SQMP_DOF],
                             const double hi[SQMP_DOF], int max_tries, double *d_q_out, int32_t *d_tries_out, void *stream);
 int sqmp_fk_dev(sqmp_ctx *ctx, const double *d_q, int64_t S, double *d_ee_pose, void *stream);

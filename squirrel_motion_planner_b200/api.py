@@ -26,7 +26,7 @@ EXPORTS = [
     "sqmp_share_voxel_grid", "sqmp_set_disabled_links", "sqmp_check_states", "sqmp_check_edges", "sqmp_get_collisions", "sqmp_fk",
     "sqmp_tree_reset", "sqmp_tree_append", "sqmp_tree_append_batch", "sqmp_tree_update", "sqmp_tree_update_costs",
     "sqmp_tree_size", "sqmp_nn_nearest", "sqmp_nn_radius", "sqmp_check_states_dev", "sqmp_check_edges_dev",
-    "sqmp_fk_dev", "sqmp_sample_configs", "sqmp_sample_configs_dev", "sqmp_nn_nearest_multi", "sqmp_nn_radius_multi", "sqmp_nn_nearest_dev", "sqmp_nn_radius_dev", "sqmp_kernel_launches", "sqmp_set_option",
+    "sqmp_fk_dev", "sqmp_sample_configs", "sqmp_sample_configs_dev", "sqmp_check_states_gather_dev", "sqmp_gather_signal_dev", "sqmp_gather_wait_dev", "sqmp_nn_nearest_multi", "sqmp_nn_radius_multi", "sqmp_nn_nearest_dev", "sqmp_nn_radius_dev", "sqmp_kernel_launches", "sqmp_set_option",
 ]
 
 
@@ -54,6 +54,20 @@ class RobotDescC(C.Structure):
         ("pair_a", C.POINTER(C.c_int32)),
         ("pair_b", C.POINTER(C.c_int32)),
         ("self_const_collision", C.c_int32),
+    ]
+
+
+MAX_PEERS = 8
+
+
+class PeerGatherC(C.Structure):
+    """sqmp_peer_gather (include/sqmp_b200.h): peer-mapped gather buffers / flag arrays of the ranks of one node."""
+    _fields_ = [
+        ("n_peers", C.c_int32),
+        ("rank", C.c_int32),
+        ("mask", C.c_void_p * MAX_PEERS),
+        ("flag", C.c_void_p * MAX_PEERS),
+        ("word_offset", C.c_int64),
     ]
 
 
@@ -96,6 +110,9 @@ def load_library():
     L.sqmp_check_states_dev.argtypes = [vp, vp, i64, C.c_uint, vp, vp]
     L.sqmp_check_edges_dev.argtypes = [vp, vp, vp, i64, C.c_int, C.c_uint, vp, vp, vp]
     L.sqmp_fk_dev.argtypes = [vp, vp, i64, vp, vp]
+    L.sqmp_check_states_gather_dev.argtypes = [vp, vp, i64, C.c_uint, C.POINTER(PeerGatherC), vp]
+    L.sqmp_gather_signal_dev.argtypes = [vp, C.POINTER(PeerGatherC), C.c_uint32, vp]
+    L.sqmp_gather_wait_dev.argtypes = [vp, vp, C.c_int, C.c_uint32, vp, vp]
     L.sqmp_nn_nearest_multi.argtypes = [vp, vp, vp, i64, vp]
     L.sqmp_nn_radius_multi.argtypes = [vp, vp, vp, vp, i64, C.c_double, C.c_int, vp, vp, vp]
     L.sqmp_sample_configs.argtypes = [vp, C.c_uint64, i64, i64, dp, dp, C.c_int, vp, vp]
@@ -339,6 +356,17 @@ class Context:
     def check_edges_dev(self, d_a, d_b, E, num_points, flags, d_mask, d_first=None, stream=0):
         self._ck(self._L.sqmp_check_edges_dev(self._h, _ptr(d_a), _ptr(d_b), int(E), int(num_points), flags,
                                               _ptr(d_mask), _ptr(d_first), C.c_void_p(stream)))
+
+    def check_states_gather_dev(self, d_q, S, flags, peers: "PeerGatherC", stream=0):
+        """Validity kernel with the mask all-gather fused in: words go straight to every rank's gather buffer."""
+        self._ck(self._L.sqmp_check_states_gather_dev(self._h, _ptr(d_q), int(S), flags, C.byref(peers), C.c_void_p(stream)))
+
+    def gather_signal_dev(self, peers: "PeerGatherC", step, stream=0):
+        self._ck(self._L.sqmp_gather_signal_dev(self._h, C.byref(peers), int(step), C.c_void_p(stream)))
+
+    def gather_wait_dev(self, d_flags_ptr, n_peers, step, d_status, stream=0):
+        self._ck(self._L.sqmp_gather_wait_dev(self._h, C.c_void_p(int(d_flags_ptr)), int(n_peers), int(step), _ptr(d_status),
+                                              C.c_void_p(stream)))
 
     def fk_dev(self, d_q, S, d_out, stream=0):
         self._ck(self._L.sqmp_fk_dev(self._h, _ptr(d_q), int(S), _ptr(d_out), C.c_void_p(stream)))

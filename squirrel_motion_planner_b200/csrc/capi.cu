@@ -892,6 +892,57 @@ int sqmp_check_states_dev(sqmp_ctx *ctx, const double *d_q, int64_t S, unsigned 
   return SQMP_OK;
 }
 
+static int fill_peer_dev(Ctx *c, const sqmp_peer_gather *g, uint32_t step, PeerDev &pd) {
+  if (!g || g->n_peers < 1 || g->n_peers > SQMP_MAX_PEERS || g->rank < 0 || g->rank >= g->n_peers || g->word_offset < 0)
+    return fail(c, SQMP_ERR_INVALID, "peer gather: bad descriptor");
+  std::memset(&pd, 0, sizeof(pd));
+  for (int p = 0; p < g->n_peers; ++p) {
+    if (!g->mask[p] || !g->flag[p]) return fail(c, SQMP_ERR_INVALID, "peer gather: null peer pointer");
+    pd.mask[p] = g->mask[p];
+    pd.flag[p] = g->flag[p];
+  }
+  pd.word_offset = g->word_offset;
+  pd.n = g->n_peers;
+  pd.rank = g->rank;
+  pd.step = step;
+  return SQMP_OK;
+}
+
+int sqmp_check_states_gather_dev(sqmp_ctx *ctx, const double *d_q, int64_t S, unsigned flags, const sqmp_peer_gather *g,
+                                 void *stream) {
+  CHECK_CTX();
+  if (S <= 0 || !d_q) return fail(c, SQMP_ERR_INVALID, "check_states_gather_dev: bad argument");
+  if (!use_fast_k1(c, flags)) return fail(c, SQMP_ERR_INVALID, "check_states_gather_dev: needs the fast validity kernel (map check)");
+  PeerDev pd;
+  int rc = fill_peer_dev(c, g, 0, pd);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  int nl = 0;
+  CU(launch_check_states_fast(c->rb_grid, c->gd, c->self, c->fast, d_q, nullptr, 0, S, flags, nullptr,
+                              c->chain_specialization != 0, k1f_may_overlap(c, st), st, &nl, &pd));
+  c->launches += nl;
+  k1f_launched(c, st);
+  return SQMP_OK;
+}
+
+int sqmp_gather_signal_dev(sqmp_ctx *ctx, const sqmp_peer_gather *g, uint32_t step, void *stream) {
+  CHECK_CTX();
+  PeerDev pd;
+  int rc = fill_peer_dev(c, g, step, pd);
+  if (rc) return rc;
+  CU(launch_gather_signal(pd, (cudaStream_t)stream));
+  // (like the wait kernel) not counted in `launches`: issued on the communication stream, outside the overlap chain
+  return SQMP_OK;
+}
+
+int sqmp_gather_wait_dev(sqmp_ctx *ctx, const uint32_t *d_flags, int n_peers, uint32_t step, int32_t *d_status, void *stream) {
+  CHECK_CTX();
+  if (!d_flags || n_peers < 1 || n_peers > SQMP_MAX_PEERS) return fail(c, SQMP_ERR_INVALID, "gather_wait_dev: bad argument");
+  CU(launch_gather_wait(d_flags, n_peers, step, d_status, (cudaStream_t)stream));
+  // not counted in `launches`: it may run on another stream and must not break the overlap chain of the validity kernel
+  return SQMP_OK;
+}
+
 int sqmp_check_edges_dev(sqmp_ctx *ctx, const double *d_a, const double *d_b, int64_t E, int num_points,
                          unsigned flags, uint32_t *d_mask, int32_t *d_first, void *stream) {
   CHECK_CTX();

@@ -76,6 +76,17 @@ struct GridDev {
   double ox, oy, oz, res, inv_res;
 };
 
+// Fused mask all-gather (validity_fast.cu): instead of writing its mask words to one local buffer, a rank's kernel
+// writes them straight into the gather buffer of EVERY rank of the node through peer-mapped pointers (NVLink stores);
+// a one-warp signal kernel ordered after it publishes the step number in every rank's flag array.  n == 0: plain local store.
+struct PeerDev {
+  uint32_t *mask[SQMP_MAX_PEERS];   // every rank's gather buffer (identical layout), as mapped into this process
+  uint32_t *flag[SQMP_MAX_PEERS];   // every rank's flag array [n]: flag[p][rank] = step once this rank's words of `step` have landed
+  int64_t word_offset;              // first word of this rank's slot inside a gather buffer
+  int n, rank;
+  unsigned step;
+};
+
 // Tables of the fast validity kernel (validity_fast.cu), in global memory; rebuilt with the grid-unit robot.
 struct FastPair {      // two consecutive slots (slots come in multiples of 4), laid out for packed fp32x2 arithmetic;
   float x[2], y[2], z[2];   // sphere centres in their group frame, grid units, fp32
@@ -165,7 +176,9 @@ cudaError_t launch_ft_build(const uint32_t *d_occ, int row_words, int gx, int gy
 cudaError_t launch_check_states_fast(const RobotDev &rb, const GridDev &gd, const SelfDev &self, const FastDev &fd,
                                      const double *d_q, const double *d_q_end, int num_points, int64_t S,
                                      unsigned flags, uint32_t *d_mask, bool allow_specialized, bool overlap,
-                                     cudaStream_t st, int *n_launch);
+                                     cudaStream_t st, int *n_launch, const PeerDev *peers = nullptr);
+cudaError_t launch_gather_signal(const PeerDev &peer, cudaStream_t st);
+cudaError_t launch_gather_wait(const uint32_t *d_flags, int n, unsigned step, int32_t *d_status, cudaStream_t st);
 cudaError_t launch_pack_rows(const uint32_t *d_bits_linear, int gx, int gy, int gz, int row_words, uint32_t *d_occ,
                              cudaStream_t st);
 

@@ -22,6 +22,8 @@
 // while this one drains, and writes its mask only after this one has completed.
 // States whose base lies outside the grid (or is not finite) never use the fp32 path: their spheres go through the
 // reach test and the exact scan only.
+#include <cstring>
+
 #include "k1_scan.cuh"
 #include "k1_self.cuh"
 
@@ -50,8 +52,8 @@ __device__ __forceinline__ float kf_gap(int o, float f) {   // gap between coord
 template <bool EDGES, bool SELF, typename SIG>
 __global__ void __launch_bounds__(KF_THREADS, SELF ? (512 / KF_THREADS) : KF_MIN_BLOCKS)
 k1_fast(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd, const __grid_constant__ SelfDev self,
-        const __grid_constant__ FastDev fd, const double *__restrict__ q_in, const double *__restrict__ q_end,
-        int num_points, int64_t S, uint32_t *__restrict__ mask_out) {
+        const __grid_constant__ FastDev fd, const __grid_constant__ PeerDev peer, const double *__restrict__ q_in,
+        const double *__restrict__ q_end, int num_points, int64_t S, uint32_t *__restrict__ mask_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WarpQueue *wq = reinterpret_cast<WarpQueue *>(smem_raw) + (threadIdx.x >> 5);
   double *q_mine = reinterpret_cast<double *>(smem_raw + sizeof(WarpQueue) * (KF_THREADS / 32)) + threadIdx.x;  // [8][blockDim]
@@ -272,13 +274,50 @@ k1_fast(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd,
   // waiting here — until every prerequisite grid has completed and flushed — keeps back-to-back calls that reuse one
   // mask buffer equivalent to serial execution.  (A no-op when the grid was launched without the attribute.)
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (lane == 0 && s < ((S + 31) & ~int64_t(31))) mask_out[s >> 5] = word;
+  if (peer.n == 0) {
+    if (lane == 0 && s < ((S + 31) & ~int64_t(31))) mask_out[s >> 5] = word;
+    return;
+  }
+  // ---- fused all-gather: lane p stores the warp's word into rank p's gather buffer (one store instruction, n peers).
+  //      Plain stores, no fence here: the completion of this grid orders them before the signal kernel that follows it ----
+  if (lane < peer.n && s < ((S + 31) & ~int64_t(31))) peer.mask[lane][peer.word_offset + (s >> 5)] = word;
+}
+
+// after the validity kernel of a step (stream order, possibly through an event): publish the step in every rank's flags
+__global__ void k_gather_signal(PeerDev peer) {
+  __threadfence_system();
+  if (threadIdx.x < peer.n) *reinterpret_cast<volatile uint32_t *>(peer.flag[threadIdx.x] + peer.rank) = peer.step;
+}
+cudaError_t launch_gather_signal(const PeerDev &peer, cudaStream_t st) {
+  k_gather_signal<<<1, 32, 0, st>>>(peer);
+  return cudaGetLastError();
+}
+
+// one warp: lane p waits until flags[p] has reached `step` (wrap-safe), bounded by ~2 s of SM clock
+__global__ void k_gather_wait(const uint32_t *__restrict__ flags, int n, unsigned step, int32_t *__restrict__ status) {
+  const int lane = threadIdx.x;
+  bool ok = true;
+  if (lane < n) {
+    const long long t0 = clock64();
+    const volatile uint32_t *f = flags + lane;
+    while (int32_t(*f - step) < 0) {
+      if (clock64() - t0 > 4000000000ll) { ok = false; break; }
+      __nanosleep(200);
+    }
+  }
+  __threadfence_system();   // acquire: the peers' mask words are visible to whatever follows on this stream
+  const unsigned bad = __ballot_sync(0xffffffffu, !ok);
+  if (lane == 0 && status) *status = bad ? 1 : 0;
+}
+cudaError_t launch_gather_wait(const uint32_t *d_flags, int n, unsigned step, int32_t *d_status, cudaStream_t st) {
+  k_gather_wait<<<1, 32, 0, st>>>(d_flags, n, step, d_status);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_check_states_fast(const RobotDev &rb, const GridDev &gd, const SelfDev &self, const FastDev &fd,
                                      const double *d_q, const double *d_q_end, int num_points, int64_t S,
                                      unsigned flags, uint32_t *d_mask, bool allow_specialized, bool overlap,
-                                     cudaStream_t st, int *n_launch) {
+                                     cudaStream_t st, int *n_launch, const PeerDev *peers) {
   const bool with_self = (flags & SQMP_CHECK_SELF) != 0;
   size_t smem = sizeof(WarpQueue) * (KF_THREADS / 32) + sizeof(double) * SQMP_DOF * KF_THREADS +
                 16 * size_t(fd.n_slots + (fd.n_slots + 1) / 2);   // FastPair: 16 B per slot; FastAux: 8 B per slot
@@ -288,6 +327,9 @@ cudaError_t launch_check_states_fast(const RobotDev &rb, const GridDev &gd, cons
   if (blocks <= 0) return cudaSuccess;
   if (blocks > 0x7fffffff) return cudaErrorInvalidValue;
   cudaError_t err = cudaSuccess;
+  PeerDev pd;
+  std::memset(&pd, 0, sizeof(pd));
+  if (peers) pd = *peers;
   auto go = [&](auto kern) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     cudaLaunchConfig_t cfg = {};
@@ -300,7 +342,7 @@ cudaError_t launch_check_states_fast(const RobotDev &rb, const GridDev &gd, cons
     attr[0].val.programmaticStreamSerializationAllowed = overlap ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    err = cudaLaunchKernelEx(&cfg, kern, rb, gd, self, fd, d_q, d_q_end, d_q_end ? num_points : 0, S, d_mask);
+    err = cudaLaunchKernelEx(&cfg, kern, rb, gd, self, fd, pd, d_q, d_q_end, d_q_end ? num_points : 0, S, d_mask);
   };
   if (allow_specialized && chain_matches<SigRobotino>(rb)) {   // structure of the chain known at compile time (the reference's robot)
     if (d_q_end) {

@@ -319,6 +319,42 @@ def test_shared_voxel_grid_between_contexts(world_ctx, fixture_data):
     assert np.array_equal(ctx.check_states(q, api.CHECK_MAP | api.CHECK_SELF), want)   # the owner outlives the borrower
 
 
+def test_fused_gather_entry_point_single_rank(world_ctx):
+    """sqmp_check_states_gather_dev / sqmp_gather_signal_dev / sqmp_gather_wait_dev with one "peer" (this GPU itself): the
+    words land at word_offset of the gather buffer, the flag shows the step, the wait kernel reports success; a step
+    that was never signalled makes the wait time out (status 1) instead of hanging.  (The 2- and 8-GPU runs of bench.py
+    --gather p2p check the peer-mapped case against ncclAllGather.)"""
+    import ctypes as C
+    import torch
+    ctx, orc, w, origin = world_ctx
+    stream = torch.cuda.current_stream().cuda_stream
+    S = 21 * 1000 + 13
+    q = syn.state_batch(S, seed=91, xy_half=2.2)
+    d_q = torch.from_numpy(q).cuda()
+    words = (S + 31) // 32
+    off = 17
+    d_buf = torch.zeros(off + words + 5, dtype=torch.int32, device="cuda")
+    d_flags = torch.zeros(8, dtype=torch.int32, device="cuda")
+    d_status = torch.full((1,), -1, dtype=torch.int32, device="cuda")
+    g = api.PeerGatherC()
+    g.n_peers, g.rank, g.word_offset = 1, 0, off
+    g.mask[0], g.flag[0] = d_buf.data_ptr(), d_flags.data_ptr()
+    ctx.check_states_gather_dev(d_q, S, api.CHECK_MAP, g, stream)
+    ctx.gather_signal_dev(g, 5, stream)
+    ctx.gather_wait_dev(d_flags.data_ptr(), 1, 5, d_status, stream)
+    torch.cuda.synchronize()
+    want = ctx.check_states(q, api.CHECK_MAP).view(np.int32)
+    got = d_buf.cpu().numpy()
+    assert np.array_equal(got[off:off + words], want) and not got[:off].any() and not got[off + words:].any()
+    assert int(d_flags[0].item()) == 5 and int(d_status.item()) == 0
+    ctx.gather_wait_dev(d_flags.data_ptr(), 1, 6, d_status, stream)          # step 6 is never signalled
+    torch.cuda.synchronize()
+    assert int(d_status.item()) == 1
+    with pytest.raises(api.SqmpError):
+        g.n_peers = 9
+        ctx.check_states_gather_dev(d_q, S, api.CHECK_MAP, g, stream)
+
+
 def test_fast_kernel_rejected_without_its_preconditions(fixture_data):
     """k1_kernel = 2 is an error for a description whose base is not a translation-only run (no silent fallback)."""
     lt, fx, spheres = fixture_data

@@ -11,7 +11,12 @@ S = 1 << 20
 dq = [torch.from_numpy(syn.state_batch(S, seed=100 + i)).cuda() for i in range(4)]
 dm = torch.zeros(S // 32, dtype=torch.int32, device="cuda")
 out = {}
-for mode in ("plain", "event_between", "overlap_off"):
+side = torch.cuda.Stream()
+ev_done = torch.cuda.Event()
+with torch.cuda.stream(side):
+    ev_done.record(side)
+torch.cuda.synchronize()
+for mode in ("plain", "event_between", "wait_between", "wait_every_4", "overlap_off"):
     ctx.set_option("launch_overlap", 0 if mode == "overlap_off" else 1)
     evs = [torch.cuda.Event() for _ in range(64)]
     for i in range(5): ctx.check_states_dev(dq[i % 4], S, 2, dm, st)
@@ -20,6 +25,8 @@ for mode in ("plain", "event_between", "overlap_off"):
     for i in range(60):
         ctx.check_states_dev(dq[i % 4], S, 2, dm, st)
         if mode == "event_between": evs[i].record()
+        if mode == "wait_between" or (mode == "wait_every_4" and i % 4 == 3):
+            torch.cuda.current_stream().wait_event(ev_done)     # an (already completed) event of another stream
     b.record(); torch.cuda.synchronize()
     out[mode] = round(a.elapsed_time(b) / 60 * 1e3, 1)
 print(json.dumps(out))
