@@ -3,11 +3,13 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload config2|config3|config4|config5]
 
-One "step" = one pass of the fused FK + collision kernel (K1) over one batch of 2^20 interpolated 8-DOF
+One "step" = one pass of the fused FK + collision kernel (K1F) over one batch of 2^20 interpolated 8-DOF
 states against the resident 256^3 voxel world W256, map check on.  With N > 1 (torchrun,
-one rank per GPU) every rank checks its own 2^20-state shard, writes its mask straight into its slot of the
-gathered buffer, and one NCCL all-gather completes the step (weak scaling).  `--workload config4` runs the
-2^26-state batch of configs[3] sharded over the ranks instead (strong scaling).
+one rank per GPU) every rank checks its own 2^20-state shard, writes its mask straight into its slot of a
+gather buffer, and the mask is gathered on every rank — `--gather nccl` (default): one ncclAllGather per step
+on a communication stream; `--gather p2p`: fused into the kernel over peer memory (weak scaling).
+`--workload config4` runs the 2^26-state batch of configs[3] sharded over the ranks instead (strong scaling),
+`config3` the near-neighbour queries, `config5` the planning queries.
 
 Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port (the reference itself cannot be
 built here: ROS/KDL/FCL/octomap are absent — DESIGN.md) on the host cores.

@@ -3,7 +3,8 @@
 States are independent, so rank r owns the contiguous, 32-aligned range [r*S/R, (r+1)*S/R); the voxel grid and
 the robot description are replicated; every rank writes its packed verdict bits straight into its slot of
 the gather buffer and ONE all-gather (NCCL over NVLink on the GPU box, gloo in the CPU tests) gives every rank
-the full mask.  No other collective exists on this path; planning-query batches are replicas only.
+the full mask — or the kernel stores the words into every rank's buffer itself (peer_gather.py, `sqmp_check_states_
+gather_dev`).  No other collective exists on this path; planning-query batches are replicas only.
 """
 from __future__ import annotations
 
