@@ -130,6 +130,16 @@ def make_world():
     return w, origin
 
 
+def host_threads():
+    """All the host threads this process may use.  torchrun exports OMP_NUM_THREADS=1 to every rank, which would make the
+    CPU arm single-threaded under the driver's multi-GPU launches: the oracle takes its thread count as an argument
+    (num_threads clause), so the affinity mask is what counts."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline_sample(n_threads, target_s=12.0):
     """Oracle port of the reference checker (early-exit path) on a bounded sample of the same workload."""
     import oracle
@@ -165,7 +175,7 @@ def run_reference(args):
     if rank != 0:
         return
     import oracle
-    threads = max(1, min(oracle.max_threads(), os.cpu_count() or 1))
+    threads = host_threads()
     orc, rate, n_probe, _ = cpu_baseline_sample(threads, target_s=3.0)
     budget_s = 150.0 / max(1, args.steps + args.warmup)
     n = int(min(S_CONFIG2, max(2100, rate * min(budget_s, 8.0))))
@@ -381,7 +391,7 @@ def run_own(args):
         cpu = None
         if world_size == 1 and not args.no_cpu:
             import oracle
-            threads = max(1, min(oracle.max_threads(), os.cpu_count() or 1))
+            threads = host_threads()
             _, rate, n, dt = cpu_baseline_sample(threads, target_s=12.0)
             cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": "first %d of the 2^20 config-2 states (repeated), W256, map check, oracle early-exit path, "
