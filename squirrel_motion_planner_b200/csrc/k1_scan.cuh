@@ -145,7 +145,10 @@ __device__ __forceinline__ bool scan_rows_filtered(const GridDev &g, double ux, 
 // ------------------------------------------------------------------------------------------------
 constexpr int K1_THREADS = 128;
 constexpr int K1_QCAP = 64;       // deferred exact-scan items per warp (drained 32 at a time)
-constexpr int K1_CHUNK = 4;       // rows of an exact scan handed to one lane at a time (their loads are issued together)
+#ifndef K1_CHUNK_DEF
+#define K1_CHUNK_DEF 3
+#endif
+constexpr int K1_CHUNK = K1_CHUNK_DEF;   // rows of an exact scan handed to one lane at a time (their loads are issued together); 3 measured best (2, 4, 6, 8 tried)       // rows of an exact scan handed to one lane at a time (their loads are issued together)
 constexpr int K1_BATCH = 4;       // spheres whose field gathers are in flight together
 constexpr unsigned FULL = 0xffffffffu;
 
