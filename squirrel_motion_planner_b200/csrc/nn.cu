@@ -136,7 +136,10 @@ __device__ __forceinline__ bool better(double d1, int32_t id1, double d2, int32_
 }
 
 constexpr int NN_THREADS = 128;
-constexpr int NN_TILE = 256;  // nodes per shared-memory tile (QT)
+#ifndef NN_TILE_DEF
+#define NN_TILE_DEF 256
+#endif
+constexpr int NN_TILE = NN_TILE_DEF;  // nodes per shared-memory tile (QT)
 
 // ---------------------------------------------------------------------------------------------------------
 // K3 nearest — QT variant.  grid = (ceil(Q/128), chunks)
