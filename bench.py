@@ -693,7 +693,7 @@ def main():
     ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5"])
     ap.add_argument("--queries", type=int, default=1024, help="config5: number of planning queries")
     ap.add_argument("--iterations", type=int, default=1000, help="config5: BiRRT* iterations per query")
-    ap.add_argument("--threads", type=int, default=2, help="config5: host threads per GPU, each with its own context")
+    ap.add_argument("--threads", type=int, default=1, help="config5: host threads per GPU, each with its own context")
     ap.add_argument("--batch", type=int, default=512, help="config5: queries in flight per GPU (1 = sequential runner)")
     ap.add_argument("--gather", default="nccl", choices=["auto", "p2p", "nccl"],
                     help="N > 1: mask all-gather fused into the kernel over peer memory (p2p) or ncclAllGather (nccl)")

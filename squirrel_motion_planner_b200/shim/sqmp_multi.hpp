@@ -14,7 +14,11 @@
 // hash — are those of the sequential run (tests/test_planner_frontend.py).
 #pragma once
 
+#if defined(__x86_64__) && defined(__linux__) && !defined(SQMP_FIBER_UCONTEXT)
+#define SQMP_FIBER_ASM 1
+#else
 #include <ucontext.h>
+#endif
 
 #include <cstdint>
 #include <cstdio>
@@ -24,7 +28,55 @@
 #include "sqmp_birrt.hpp"
 #include "sqmp_shim.hpp"
 
+#ifdef SQMP_FIBER_ASM
+// Fiber switch for x86-64 System V: the callee-saved registers, MXCSR and the x87 control word go on the old stack, the
+// stack pointers are exchanged, the same state comes off the new stack.  ~10 ns; glibc's swapcontext also saves and
+// restores the signal mask with two system calls (~300 ns), which was the largest host cost of a scheduler round.
+// (-DSQMP_FIBER_UCONTEXT selects the portable ucontext version.)
+extern "C" void sqmp_fiber_switch(void **from_sp, void *to_sp);
+extern "C" void sqmp_fiber_boot();
+asm(".text\n"
+    ".weak sqmp_fiber_switch\n"
+    ".type sqmp_fiber_switch,@function\n"
+    "sqmp_fiber_switch:\n"
+    "  pushq %rbp\n  pushq %rbx\n  pushq %r12\n  pushq %r13\n  pushq %r14\n  pushq %r15\n"
+    "  subq $8, %rsp\n  stmxcsr (%rsp)\n  fnstcw 4(%rsp)\n"
+    "  movq %rsp, (%rdi)\n"
+    "  movq %rsi, %rsp\n"
+    "  ldmxcsr (%rsp)\n  fldcw 4(%rsp)\n  addq $8, %rsp\n"
+    "  popq %r15\n  popq %r14\n  popq %r13\n  popq %r12\n  popq %rbx\n  popq %rbp\n"
+    "  ret\n"
+    ".size sqmp_fiber_switch,.-sqmp_fiber_switch\n"
+    // first activation of a fiber: rbx = argument, r12 = entry function (placed in the initial frame)
+    ".weak sqmp_fiber_boot\n"
+    ".type sqmp_fiber_boot,@function\n"
+    "sqmp_fiber_boot:\n"
+    "  movq %rbx, %rdi\n"
+    "  subq $8, %rsp\n"
+    "  callq *%r12\n"
+    "  ud2\n"
+    ".size sqmp_fiber_boot,.-sqmp_fiber_boot\n");
+#endif
+
 namespace sqmp_planner {
+
+#ifdef SQMP_FIBER_ASM
+// initial frame of a fiber on its own stack: [mxcsr | x87 cw][r15][r14][r13][r12 = entry][rbx = arg][rbp][ret = boot][pad]
+inline void *fiber_prepare(char *stack, size_t bytes, void (*entry)(void *), void *arg) {
+  uintptr_t top = (reinterpret_cast<uintptr_t>(stack) + bytes) & ~uintptr_t(15);
+  uint64_t *sp = reinterpret_cast<uint64_t *>(top);
+  *--sp = 0;                                              // pad: after boot's `ret` slot is popped, rsp % 16 == 8
+  *--sp = reinterpret_cast<uint64_t>(&sqmp_fiber_boot);   // return address of the first switch
+  *--sp = 0;                                              // rbp
+  *--sp = reinterpret_cast<uint64_t>(arg);                // rbx
+  *--sp = reinterpret_cast<uint64_t>(entry);              // r12
+  *--sp = 0;                                              // r13
+  *--sp = 0;                                              // r14
+  *--sp = 0;                                              // r15
+  *--sp = 0x0000037F00001F80ull;                          // MXCSR = 0x1F80 (low 4 bytes), x87 control word = 0x037F
+  return sp;
+}
+#endif
 
 struct MultiRequest {
   enum Kind { NONE = 0, NEAREST, NEAR, EDGES, VALID } kind = NONE;
@@ -147,12 +199,16 @@ class MultiSchedulerT {
         f.q = queries + (g0 + i) * 16;
         f.iterations = iterations;
         f.stack.resize(STACK_BYTES);
+#ifdef SQMP_FIBER_ASM
+        f.sp = fiber_prepare(f.stack.data(), f.stack.size(), &MultiSchedulerT<Service>::entry_ptr, &f);
+#else
         getcontext(&f.uc);
         f.uc.uc_stack.ss_sp = f.stack.data();
         f.uc.uc_stack.ss_size = f.stack.size();
         f.uc.uc_link = &main_;
         const uintptr_t p = reinterpret_cast<uintptr_t>(&f);
         makecontext(&f.uc, reinterpret_cast<void (*)()>(&MultiSchedulerT<Service>::entry), 2, unsigned(p & 0xffffffffu), unsigned(p >> 32));
+#endif
       }
       size_t alive = nb;
       while (alive > 0 && !failed_) {
@@ -160,7 +216,11 @@ class MultiSchedulerT {
           Fiber &f = fibers_[i];
           if (f.done) continue;
           current_ = &f;
+#ifdef SQMP_FIBER_ASM
+          sqmp_fiber_switch(&main_sp_, f.sp);
+#else
           swapcontext(&main_, &f.uc);
+#endif
           if (f.done) {
             --alive;
             failed_ = failed_ || f.be.failed();
@@ -176,14 +236,22 @@ class MultiSchedulerT {
     }
     return !failed_;
   }
+#ifdef SQMP_FIBER_ASM
+  void yield() { sqmp_fiber_switch(&current_->sp, main_sp_); }   // called on a fiber's stack
+#else
   void yield() { swapcontext(&current_->uc, &main_); }   // called on a fiber's stack
+#endif
   long rounds() const { return rounds_; }
   long library_calls() const { return calls_; }
 
  private:
   struct Fiber {
     MultiSchedulerT<Service> *owner = NULL;
+#ifdef SQMP_FIBER_ASM
+    void *sp = NULL;
+#else
     ucontext_t uc;
+#endif
     std::vector<char> stack;
     FiberBackend be;
     Params P;
@@ -194,15 +262,25 @@ class MultiSchedulerT {
   };
   static const size_t STACK_BYTES = 256 * 1024;
 
+#ifdef SQMP_FIBER_ASM
+  static void entry_ptr(void *p) {
+    Fiber *f = static_cast<Fiber *>(p);
+    run_query(f);
+    sqmp_fiber_switch(&f->sp, f->owner->main_sp_);   // never resumed: the scheduler skips finished fibers
+  }
+#else
   static void entry(unsigned lo, unsigned hi) {
-    Fiber *f = reinterpret_cast<Fiber *>(uintptr_t(lo) | (uintptr_t(hi) << 32));
+    run_query(reinterpret_cast<Fiber *>(uintptr_t(lo) | (uintptr_t(hi) << 32)));   // returning resumes uc_link = the scheduler
+  }
+#endif
+  static void run_query(Fiber *f) {
     {
       BiRRTStar<FiberBackend> planner(f->be, f->P);
       f->valid_endpoints = planner.init(f->q, f->q + 8);
       if (f->valid_endpoints) f->stats = planner.run(f->iterations);
     }
     f->be.req.kind = MultiRequest::NONE;
-    f->done = true;   // returning resumes uc_link = the scheduler
+    f->done = true;
   }
 
   void ok(int rc) {
@@ -309,7 +387,11 @@ class MultiSchedulerT {
   int batch_;
   bool failed_;
   long rounds_, calls_;
+#ifdef SQMP_FIBER_ASM
+  void *main_sp_ = NULL;
+#else
   ucontext_t main_;
+#endif
   Fiber *current_ = NULL;
   std::vector<Fiber> fibers_;
   std::vector<int> idx_;
