@@ -144,7 +144,8 @@ int main(int argc, char **argv) {
   orc_set_grid(m, a.g.bits.data(), a.g.gx, a.g.gy, a.g.gz, origin, a.g.res);
   int rc = 0;
   if (argc > 9) {   // [batch]: the lock-step scheduler over the oracle (same output lines as the sequential runner)
-    OracleService svc(m, 3u, tip);
+    const char *fl = getenv("SQMP_ORACLE_FLAGS");   // profiling aid: 0 = no collision checks (host logic only)
+    OracleService svc(m, fl ? unsigned(atoi(fl)) : 3u, tip);
     sqmp_planner::MultiSchedulerT<OracleService> sched(&svc, atoi(argv[9]));
     sqmp_planner::Params P;
     P.lo[0] = a.xy_lo[0]; P.lo[1] = a.xy_lo[1]; P.hi[0] = a.xy_hi[0]; P.hi[1] = a.xy_hi[1];
