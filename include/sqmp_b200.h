@@ -28,8 +28,8 @@ extern "C" {
 
 #define SQMP_DOF 8
 #define SQMP_MAX_SEG 8
-#define SQMP_MAX_SPHERES 128
-#define SQMP_MAX_PAIRS 4096
+#define SQMP_MAX_SPHERES 1024  /* a covering model of the reference's 27 link shapes needs ~330 (sphere_model.py) */
+#define SQMP_MAX_LINKS 64
 #define SQMP_MAX_PEERS 8       /* GPUs of one node in the fused mask all-gather */
 #define SQMP_MAX_TREES 1024   /* two per concurrent planning query (shim/sqmp_multi.hpp) */
 
@@ -69,9 +69,10 @@ typedef struct sqmp_robot_desc {
   const int32_t *sph_link;             /* [n] link index 0..63 (bit position in the disable mask) */
   const double *sph_center;            /* [n*3] in the segment frame */
   const double *sph_radius;            /* [n] */
-  int32_t n_pairs;                     /* enabled sphere pairs across different segments (CC:353-393) */
-  const int32_t *pair_a;
-  const int32_t *pair_b;
+  /* selfCollisionPairs (CC:353-393) at link level: bit j of link_pair_mask[i] = links i and j are checked against
+   * each other (both shaped, not disabled in the SRDF; symmetric).  The library collides every sphere of link i with
+   * every sphere of link j when the two links hang on different segments. */
+  uint64_t link_pair_mask[SQMP_MAX_LINKS];
   int32_t self_const_collision;        /* 1: an enabled pair inside one rigid group always collides */
 } sqmp_robot_desc;
 
@@ -113,8 +114,9 @@ int sqmp_check_states(sqmp_ctx *ctx, const double *q, int64_t S, unsigned flags,
 int sqmp_check_edges(sqmp_ctx *ctx, const double *q_start, const double *q_end, int64_t E, int num_points,
                      unsigned flags, uint32_t *mask_out, int32_t *first_invalid);
 /* CollisionChecker::getCollisions (CC:123-133, 594-631) for one state: link_map_hit[64] (1 = link hits
- * the map; like the reference, ignores the disable mask) and pair_hit[n_pairs] per enabled sphere pair. */
-int sqmp_get_collisions(sqmp_ctx *ctx, const double q[SQMP_DOF], uint8_t *link_map_hit, uint8_t *pair_hit);
+ * the map; like the reference, ignores the disable mask) and link_pair_hit[64 * 64] (may be NULL): entry [i * 64 + j],
+ * i < j, is 1 when the enabled link pair (i, j) collides. */
+int sqmp_get_collisions(sqmp_ctx *ctx, const double q[SQMP_DOF], uint8_t *link_map_hit, uint8_t *link_pair_hit);
 
 /* ---- forward kinematics ------------------------------------------------------------------------- */
 /* KDLRobotModel::compute_FK (KM:278-305): S*7 doubles x y z qx qy qz qw of the chain tip. */
@@ -164,11 +166,12 @@ int sqmp_nn_radius_multi(sqmp_ctx *ctx, const int32_t *tree, const double *queri
 /* ---- device-pointer variants (benchmark harness, multi-GPU sharding) ---------------------------- */
 /* Same semantics; all pointers are device pointers on the context's GPU; work is enqueued on `stream`
  * (a cudaStream_t, NULL = default stream) and NOT synchronised. */
-/* Ordering contract of the validity *_dev calls: consecutive calls on one stream may overlap (a grid starts while its
- * predecessor drains; it writes its mask only after the predecessor has completed, so reusing one mask buffer is safe).
- * A grid reads its states BEFORE that point, so the operation enqueued on the stream immediately before a validity call
- * must not be a foreign kernel that produces those states; the library's own kernels never are (they break the overlap
- * chain).  sqmp_set_option(ctx, "launch_overlap", 0) restores plain stream order. */
+/* Ordering of the validity *_dev calls: plain stream order by default.  sqmp_set_option(ctx, "launch_overlap", 1) is an
+ * opt-in for callers whose input states are complete before the call is enqueued (bench.py, the host-buffer entry
+ * points of this library): consecutive validity grids on one stream may then overlap (a grid starts while its
+ * predecessor drains; it writes its mask only after the predecessor has completed, so reusing one mask buffer stays
+ * safe), but a grid reads its states BEFORE that point — a kernel enqueued immediately before the call on the same
+ * stream must therefore not be the producer of those states. */
 int sqmp_check_states_dev(sqmp_ctx *ctx, const double *d_q, int64_t S, unsigned flags, uint32_t *d_mask,
                           void *stream);
 int sqmp_check_edges_dev(sqmp_ctx *ctx, const double *d_q_start, const double *d_q_end, int64_t E, int num_points,

@@ -283,10 +283,20 @@ static int check_self(const orc_model *m, const double *frames) {
   return 0;
 }
 
+/* Fail-closed policy of the new boundary (no counterpart in the reference, which would feed NaN frames to FCL): a
+ * joint value that is not finite, or absurd (|q_j| >= 1e7 m / rad), makes the state "in collision" — the spirit of
+ * CC:106-107, where a checker that cannot answer says "collision". */
+static int state_is_sane(const double q[ORC_DOF]) {
+  for (int j = 0; j < ORC_DOF; ++j)
+    if (!(fabs(q[j]) < 1.0e7)) return 0;
+  return 1;
+}
+
 /* isInCollision (CC:104-121).  "not initialised ⇒ true" (CC:106-107) is the NULL model here. */
 int orc_is_in_collision(const orc_model *m, const double q[ORC_DOF], int self, int map) {
   if (!m) return 1;
   if (!self && !map) return 0;
+  if (!state_is_sane(q)) return 1;
   double frames[MAX_LINKS * 12];
   orc_update_transforms(m, q, frames);
   if (map && check_map(m, frames)) return 1;
@@ -298,6 +308,11 @@ int orc_state_clearance(const orc_model *m, const double q[ORC_DOF], unsigned fl
                         double *clr_self) {
   double frames[MAX_LINKS * 12];
   double cm = INFINITY, cs = INFINITY;
+  if ((flags & (ORC_FLAG_MAP | ORC_FLAG_SELF)) && !state_is_sane(q)) {
+    if (clr_map) *clr_map = -INFINITY;
+    if (clr_self) *clr_self = -INFINITY;
+    return 1;
+  }
   orc_update_transforms(m, q, frames);
   if ((flags & ORC_FLAG_MAP) && m->bits) {
     for (int l = 0; l < m->L; ++l) {

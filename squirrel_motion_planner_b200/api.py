@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("SQMP_B200_LIB") or os.path.join(_HERE, "libsqmp_b200.
 
 DOF = 8
 CHECK_SELF, CHECK_MAP = 1, 2
-MAX_SEG, MAX_SPHERES = 8, 128
+MAX_SEG, MAX_SPHERES, MAX_LINKS = 8, 1024, 64
 MAX_TREES = 1024
 
 EXPORTS = [
@@ -50,9 +50,7 @@ class RobotDescC(C.Structure):
         ("sph_link", C.POINTER(C.c_int32)),
         ("sph_center", C.POINTER(C.c_double)),
         ("sph_radius", C.POINTER(C.c_double)),
-        ("n_pairs", C.c_int32),
-        ("pair_a", C.POINTER(C.c_int32)),
-        ("pair_b", C.POINTER(C.c_int32)),
+        ("link_pair_mask", C.c_uint64 * MAX_LINKS),
         ("self_const_collision", C.c_int32),
     ]
 
@@ -156,16 +154,14 @@ def pack_desc(cr: rd.CompiledRobot):
     keep = dict(
         sph_seg=np.ascontiguousarray(cr.sph_seg, np.int32), sph_link=np.ascontiguousarray(cr.sph_link, np.int32),
         sph_center=np.ascontiguousarray(cr.sph_center, np.float64).reshape(-1),
-        sph_radius=np.ascontiguousarray(cr.sph_radius, np.float64),
-        pair_a=np.ascontiguousarray(cr.pair_a, np.int32), pair_b=np.ascontiguousarray(cr.pair_b, np.int32))
+        sph_radius=np.ascontiguousarray(cr.sph_radius, np.float64))
     d.n_spheres = cr.n_spheres
     d.sph_seg = keep["sph_seg"].ctypes.data_as(C.POINTER(C.c_int32))
     d.sph_link = keep["sph_link"].ctypes.data_as(C.POINTER(C.c_int32))
     d.sph_center = keep["sph_center"].ctypes.data_as(C.POINTER(C.c_double))
     d.sph_radius = keep["sph_radius"].ctypes.data_as(C.POINTER(C.c_double))
-    d.n_pairs = len(cr.pair_a)
-    d.pair_a = keep["pair_a"].ctypes.data_as(C.POINTER(C.c_int32))
-    d.pair_b = keep["pair_b"].ctypes.data_as(C.POINTER(C.c_int32))
+    for i in range(MAX_LINKS):
+        d.link_pair_mask[i] = int(cr.link_pair_mask[i])
     d.self_const_collision = int(cr.self_const_collision)
     return d, keep
 
@@ -241,12 +237,13 @@ class Context:
 
     def get_collisions(self, q):
         q = np.ascontiguousarray(q, dtype=np.float64).reshape(DOF)
-        lm = np.zeros(64, dtype=np.uint8)
-        ph = np.zeros(max(1, len(self.compiled.pair_a)), dtype=np.uint8)
+        """(link_map_hit[64], link_pair_hit[64, 64]): links that hit the map; enabled link pairs (i < j) that collide."""
+        lm = np.zeros(MAX_LINKS, dtype=np.uint8)
+        ph = np.zeros((MAX_LINKS, MAX_LINKS), dtype=np.uint8)
         self._ck(self._L.sqmp_get_collisions(self._h, q.ctypes.data_as(C.POINTER(C.c_double)),
                                              lm.ctypes.data_as(C.POINTER(C.c_uint8)),
                                              ph.ctypes.data_as(C.POINTER(C.c_uint8))))
-        return lm.astype(bool), ph[:len(self.compiled.pair_a)].astype(bool)
+        return lm.astype(bool), ph.astype(bool)
 
     def fk(self, q):
         q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, DOF)

@@ -20,33 +20,64 @@ struct DevBuf {
   size_t bytes = 0;
 };
 
+struct HostSphere {   // metres, in the frame of its rigid group
+  double c[3], r;
+  int link, grp;
+};
+struct HostCluster {  // <= 8 spheres of one link that lie close together; the unit of the bound hierarchies
+  int grp, link;
+  std::vector<int> members;   // sphere indices
+  double c[3], R;             // enclosing sphere (metres, group frame)
+  double c2[2], R2;           // enclosing vertical cylinder: axis (x, y), radius (yaw-only base group)
+  double zlo, zhi;            // z extent of the members (centre -+ radius), group frame
+  int slot0, nslots;          // its slots (4 or 8)
+};
+
 struct Ctx {
   int device = 0;
   int sm_count = 148;
   RobotDev rb;        // metres (FK kernel)
   RobotDev rb_grid;   // grid units of the current voxel grid (validity kernel); == rb while no grid is set
   GridDev gd;
-  int sph_link[SQMP_MAX_SPHERES];
-  int slot_sph[SQMP_MAX_SLOTS];   // K1 slot -> sphere index, -1 for a pad
-  int sph_slot[SQMP_MAX_SPHERES];
-  int n_pairs = 0;
-  std::vector<SelfPair> h_pairs;   // the description's pairs: a, b = SPHERE indices, rsum2 in metres^2
-  SelfHPair *d_pairs = nullptr;   // device: hierarchical order (grid units)
-  SelfPair *d_flat = nullptr;     // device: description order (slots, grid units)
-  SelfA *d_as = nullptr;
-  SelfBlock *d_blocks = nullptr;
+  // ---- collision model (fixed at sqmp_create) ----
+  std::vector<HostSphere> sph;
+  std::vector<HostCluster> clusters;        // ordered by group
+  std::vector<int> slot_sph;                // slot -> sphere index, -1 for a pad
+  int grp_cluster_end[SQMP_MAX_GROUPS + 1];
+  double grp_root_c[SQMP_MAX_GROUPS][3], grp_root_R[SQMP_MAX_GROUPS];   // enclosing sphere of a whole group
+  double grp_root_c2[SQMP_MAX_GROUPS][2], grp_root_R2[SQMP_MAX_GROUPS];
+  double grp_zlo[SQMP_MAX_GROUPS], grp_zhi[SQMP_MAX_GROUPS];
+  int n_links = 0;
+  uint64_t link_pair_mask[SQMP_MAX_LINKS];
+  uint64_t link_disabled = 0;
+  int base2d_group = -1;        // group that only translates in x, y and turns about z: tested against the slab fields
+  double base2d_z0 = 0.0;       // world z (metres) of that group's frame origin
+  // ---- device tables ----
+  K1Slot *d_k1slots = nullptr;
+  SelfGroupPair *d_self_gp = nullptr;
+  SelfLinkPair *d_self_lp = nullptr;
+  SelfLink *d_self_links = nullptr;
+  SelfCluster *d_self_cl = nullptr;
+  SelfLeaf *d_self_leaves = nullptr;
+  size_t self_cap[5] = {0, 0, 0, 0, 0};
   SelfDev self;
   bool grid_borrowed = false;   // the grid fields belong to another context (sqmp_share_voxel_grid): never freed here
   uint32_t *d_occ = nullptr;
-  uint8_t *d_lb2 = nullptr;     // halo-padded (GridDev)
+  uint8_t *d_lb2 = nullptr;     // halo-padded (GridDev), followed by the slab fields
   uint16_t *d_ft = nullptr;
+  std::vector<int> slab_k0, slab_k1;   // layer range of every slab field of the current grid
   FastDev fast;                 // tables of the fast validity kernel (validity_fast.cu)
-  FastPair *d_fast_pairs = nullptr;
+  KfTab kftab;                  // its by-value node tables (host copy; thresholds follow the link-disable mask)
+  std::vector<int> kf_leaf_thr, kf_bound_thr;   // thresholds with every link enabled (per slot / per cluster)
+  std::vector<int> kf_bound_idx;                // cluster -> index in KfTab::bound
+  int slab_of_link[SQMP_MAX_LINKS];             // link -> slab field (base2d group)
+  int slab_root = -1;
+  int ft_window = 0, slab_window = 0;           // search windows the current fields were built with (cells)
   FastAux *d_fast_aux = nullptr;
   double4 *d_fast_sph64 = nullptr;
   int fast_chain_ok = 0;        // description: translation-only base, then rotations only, spheres on the rotating part
   double reach_m = 0.0;         // max distance of a sphere centre from the base reference point (metres)
-  int launch_overlap = 1;       // K1F grids may start while the previous K1F grid of the stream drains its last wave (PDL)
+  int launch_overlap = 0;       // opt-in (include/sqmp_b200.h): K1F grids may start while the previous K1F grid of the stream drains (PDL)
   int64_t k1f_seq = -1;         // value of `launches` right after the last K1F launch, and the stream it went to:
   cudaStream_t k1f_stream = nullptr;   // overlap is requested only when nothing else was launched by this context since
   int k1_kernel = 0;            // 0 auto (fast when its preconditions hold) | 1 generic | 2 fast (error if not possible)
@@ -62,8 +93,9 @@ struct Ctx {
   bool tree_writes_pending = false; // unsynchronised single-node writes are in flight on streams[0]
   int64_t small_call_states = 4096; // validity calls up to this many states take the low-latency path
   cudaStream_t streams[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
   int64_t launches = 0;
-  int fk_precision = 64;  // 64 | 32 (validity + FK chain arithmetic)
+  int fk_precision = 64;  // 64 | 32 (FK chain arithmetic of sqmp_fk; the validity kernels always walk the chain in fp64)
   int fk_float_ok = 0;
   int chain_specialization = 1;  // 1: use the compile-time unrolled chain when the description matches a known signature
   int nn_variant = 0;     // 0 auto | 1 QT | 2 WQ
@@ -138,13 +170,257 @@ static void refresh_float_copies(RobotDev &r) {
     r.seg_axis_f[s][3] = 0.0f;
   }
   for (int i = 0; i < 12; ++i) r.ee_tip_f[i] = float(r.ee_tip[i]);
-  for (int i = 0; i < SQMP_MAX_SLOTS; ++i)
-    r.sph_f[i] = make_float4(float(r.sph[i][0]), float(r.sph[i][1]), float(r.sph[i][2]), float(r.sph[i][3]));
 }
 
-// Grid-unit copy of the robot for the validity kernel: lengths / res, root offset measured from the grid origin,
-// per-sphere distance-field threshold and scan half-extent, self-pair radii in grid units.  Re-derived whenever
-// the grid (CC:76-88) or the link-disable mask (CC:90-102) changes.
+// ---------------------------------------------------------------------------------------------------------------------
+// Bound hierarchy of the collision model (once per sqmp_create, metres): the spheres of every (rigid group, link) are
+// split by recursive median bisection into clusters of <= 8; a cluster gets 4 or 8 consecutive slots.  The same
+// clusters serve the map check (cluster bound vs lower-bound field) and the self check (cluster bound vs cluster bound).
+// ---------------------------------------------------------------------------------------------------------------------
+static void enclose(const std::vector<HostSphere> &sph, const std::vector<int> &ids, double (&c)[3], double &R,
+                    double (&c2)[2], double &R2, double &zlo, double &zhi) {
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (int i : ids)
+    for (int k = 0; k < 3; ++k) {
+      lo[k] = std::fmin(lo[k], sph[size_t(i)].c[k] - sph[size_t(i)].r);
+      hi[k] = std::fmax(hi[k], sph[size_t(i)].c[k] + sph[size_t(i)].r);
+    }
+  for (int k = 0; k < 3; ++k) c[k] = 0.5 * (lo[k] + hi[k]);   // centre of the bounding box of the spheres
+  c2[0] = c[0];
+  c2[1] = c[1];
+  R = R2 = 0.0;
+  for (int i : ids) {
+    const HostSphere &s = sph[size_t(i)];
+    const double dx = s.c[0] - c[0], dy = s.c[1] - c[1], dz = s.c[2] - c[2];
+    R = std::fmax(R, std::sqrt(dx * dx + dy * dy + dz * dz) + s.r);
+    R2 = std::fmax(R2, std::sqrt(dx * dx + dy * dy) + s.r);
+  }
+  zlo = lo[2];
+  zhi = hi[2];
+}
+
+static void bisect(const std::vector<HostSphere> &sph, std::vector<int> ids, double zweight, std::vector<std::vector<int> > &out) {
+  if (ids.size() <= 8) {
+    out.push_back(ids);
+    return;
+  }
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (int i : ids)
+    for (int k = 0; k < 3; ++k) {
+      lo[k] = std::fmin(lo[k], sph[size_t(i)].c[k]);
+      hi[k] = std::fmax(hi[k], sph[size_t(i)].c[k]);
+    }
+  int ax = 0;
+  double best = -1.0;
+  for (int k = 0; k < 3; ++k) {
+    const double ext = (hi[k] - lo[k]) * (k == 2 ? zweight : 1.0);
+    if (ext > best) { best = ext; ax = k; }
+  }
+  std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return sph[size_t(a)].c[ax] < sph[size_t(b)].c[ax]; });
+  // split so that both halves fill whole clusters as far as possible
+  const size_t n = ids.size(), parts = (n + 7) / 8, left = (parts / 2) * 8 < n ? (parts / 2) * 8 : n / 2;
+  std::vector<int> a(ids.begin(), ids.begin() + long(left)), b(ids.begin() + long(left), ids.end());
+  bisect(sph, a, zweight, out);
+  bisect(sph, b, zweight, out);
+}
+
+static int build_hierarchy(Ctx *c) {
+  c->clusters.clear();
+  c->slot_sph.clear();
+  int slot = 0;
+  for (int g = 0; g < SQMP_MAX_GROUPS; ++g) {
+    c->grp_cluster_end[g] = int(c->clusters.size());
+    c->rb.grp_slot_end[g] = slot;
+    std::vector<int> all;
+    for (int l = 0; l < SQMP_MAX_LINKS; ++l) {
+      std::vector<int> ids;
+      for (int i = 0; i < int(c->sph.size()); ++i)
+        if (c->sph[size_t(i)].grp == g && c->sph[size_t(i)].link == l) ids.push_back(i);
+      if (ids.empty()) continue;
+      all.insert(all.end(), ids.begin(), ids.end());
+      std::vector<std::vector<int> > parts;
+      bisect(c->sph, ids, g == c->base2d_group ? 0.3 : 1.0, parts);
+      for (auto &m : parts) {
+        HostCluster cl;
+        cl.grp = g;
+        cl.link = l;
+        cl.members = m;
+        enclose(c->sph, m, cl.c, cl.R, cl.c2, cl.R2, cl.zlo, cl.zhi);
+        cl.slot0 = slot;
+        cl.nslots = m.size() <= 4 ? 4 : 8;
+        for (int k = 0; k < cl.nslots; ++k) c->slot_sph.push_back(k < int(m.size()) ? m[size_t(k)] : -1);
+        slot += cl.nslots;
+        c->clusters.push_back(cl);
+      }
+    }
+    c->grp_root_R[g] = c->grp_root_R2[g] = 0.0;
+    if (!all.empty())
+      enclose(c->sph, all, c->grp_root_c[g], c->grp_root_R[g], c->grp_root_c2[g], c->grp_root_R2[g], c->grp_zlo[g], c->grp_zhi[g]);
+  }
+  c->grp_cluster_end[SQMP_MAX_GROUPS] = int(c->clusters.size());
+  c->rb.grp_slot_end[SQMP_MAX_GROUPS] = slot;
+  c->rb.n_slots = slot;
+  if (int(c->clusters.size()) > SQMP_MAX_CLUSTERS || slot > SQMP_MAX_SLOTS) return SQMP_ERR_INVALID;
+  return SQMP_OK;
+}
+
+template <typename E>
+static cudaError_t upload_vec(E *&dptr, size_t &cap, const std::vector<E> &v) {
+  if (cap < v.size() + 1) {
+    if (dptr) cudaFree(dptr);
+    dptr = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&dptr, sizeof(E) * (v.size() + 8));
+    if (e != cudaSuccess) return e;
+    cap = v.size() + 8;
+  }
+  return v.empty() ? cudaSuccess : cudaMemcpy(dptr, v.data(), sizeof(E) * v.size(), cudaMemcpyHostToDevice);
+}
+
+// Self-collision tables (SelfDev), grid units `inv` = 1/res (1 while no grid is set).
+static int build_self_tables(Ctx *c, double inv) {
+  RobotDev &g = c->rb_grid;
+  auto pad = [&](double r_sum) { return float((r_sum * (1.0 + 1e-4) + 1e-6) * inv); };   // bounds padded against fp32 rounding
+  // links = (group, link) with spheres; clusters and leaves in slot order
+  std::vector<SelfLeaf> leaves(c->slot_sph.size());
+  for (size_t sl = 0; sl < c->slot_sph.size(); ++sl) {
+    const int i = c->slot_sph[sl];
+    if (i < 0) leaves[sl] = {0.f, 0.f, 0.f, -1.0e6f};   // pad: can never touch anything
+    else leaves[sl] = {float(c->sph[size_t(i)].c[0] * inv), float(c->sph[size_t(i)].c[1] * inv), float(c->sph[size_t(i)].c[2] * inv),
+                       float(c->sph[size_t(i)].r * inv)};
+  }
+  std::vector<SelfCluster> cls(c->clusters.size());
+  std::vector<SelfLink> links;
+  std::vector<int> link_grp;
+  for (size_t k = 0; k < c->clusters.size(); ++k) {
+    const HostCluster &cl = c->clusters[k];
+    cls[k] = {float(cl.c[0] * inv), float(cl.c[1] * inv), float(cl.c[2] * inv), pad(cl.R), cl.slot0, cl.slot0 + int(cl.members.size()), {0, 0}};
+    if (links.empty() || links.back().link != cl.link || link_grp.back() != cl.grp) {
+      SelfLink L = {0.f, 0.f, 0.f, 0.f, int(k), int(k), cl.link, 0};
+      links.push_back(L);
+      link_grp.push_back(cl.grp);
+    }
+    links.back().cl_end = int(k) + 1;
+  }
+  for (size_t li = 0; li < links.size(); ++li) {
+    std::vector<int> ids;
+    for (int k = links[li].cl_begin; k < links[li].cl_end; ++k)
+      ids.insert(ids.end(), c->clusters[size_t(k)].members.begin(), c->clusters[size_t(k)].members.end());
+    double cc[3], R, c2[2], R2, zl, zh;
+    enclose(c->sph, ids, cc, R, c2, R2, zl, zh);
+    links[li].x = float(cc[0] * inv); links[li].y = float(cc[1] * inv); links[li].z = float(cc[2] * inv);
+    links[li].R = pad(R);
+  }
+  for (int gi = 0; gi < SQMP_MAX_GROUPS; ++gi) g.grp_fidx[gi] = -1;
+  g.n_frames = 0;
+  std::vector<SelfGroupPair> gps;
+  std::vector<SelfLinkPair> lps;
+  for (int ga = 0; ga < SQMP_MAX_GROUPS; ++ga)
+    for (int gb = ga + 1; gb < SQMP_MAX_GROUPS; ++gb) {
+      std::vector<int> ida, idb;
+      const int lp0 = int(lps.size());
+      for (size_t a = 0; a < links.size(); ++a)
+        for (size_t b = 0; b < links.size(); ++b)
+          if (link_grp[a] == ga && link_grp[b] == gb && ((c->link_pair_mask[links[a].link] >> links[b].link) & 1ull)) {
+            lps.push_back({int(a), int(b)});
+            for (int k = links[a].cl_begin; k < links[a].cl_end; ++k)
+              ida.insert(ida.end(), c->clusters[size_t(k)].members.begin(), c->clusters[size_t(k)].members.end());
+            for (int k = links[b].cl_begin; k < links[b].cl_end; ++k)
+              idb.insert(idb.end(), c->clusters[size_t(k)].members.begin(), c->clusters[size_t(k)].members.end());
+          }
+      if (int(lps.size()) == lp0) continue;
+      if (g.grp_fidx[ga] < 0) g.grp_fidx[ga] = g.n_frames++;
+      if (g.grp_fidx[gb] < 0) g.grp_fidx[gb] = g.n_frames++;
+      double ca[3], RA, cb[3], RB, c2[2], R2, zl, zh;
+      enclose(c->sph, ida, ca, RA, c2, R2, zl, zh);
+      enclose(c->sph, idb, cb, RB, c2, R2, zl, zh);
+      SelfGroupPair gp;
+      gp.fa = g.grp_fidx[ga]; gp.fb = g.grp_fidx[gb];
+      gp.lp_begin = lp0; gp.lp_end = int(lps.size());
+      gp.ax = float(ca[0] * inv); gp.ay = float(ca[1] * inv); gp.az = float(ca[2] * inv); gp.RA = pad(RA);
+      gp.bx = float(cb[0] * inv); gp.by = float(cb[1] * inv); gp.bz = float(cb[2] * inv); gp.RB = pad(RB);
+      gps.push_back(gp);
+    }
+  cudaError_t e = upload_vec(c->d_self_gp, c->self_cap[0], gps);
+  if (e == cudaSuccess) e = upload_vec(c->d_self_lp, c->self_cap[1], lps);
+  if (e == cudaSuccess) e = upload_vec(c->d_self_links, c->self_cap[2], links);
+  if (e == cudaSuccess) e = upload_vec(c->d_self_cl, c->self_cap[3], cls);
+  if (e == cudaSuccess) e = upload_vec(c->d_self_leaves, c->self_cap[4], leaves);
+  if (e != cudaSuccess) return fail(c, SQMP_ERR_CUDA, "self-collision tables", e);
+  c->self.gpairs = c->d_self_gp; c->self.lpairs = c->d_self_lp; c->self.links = c->d_self_links;
+  c->self.clusters = c->d_self_cl; c->self.leaves = c->d_self_leaves;
+  c->self.n_gpairs = int(gps.size()); c->self.n_lpairs = int(lps.size()); c->self.n_links = int(links.size());
+  c->rb.n_frames = g.n_frames;
+  for (int gi = 0; gi < SQMP_MAX_GROUPS; ++gi) c->rb.grp_fidx[gi] = g.grp_fidx[gi];
+  return SQMP_OK;
+}
+
+static inline void rec_set_thr(float4 *rec, int idx, int thr) {   // pair records: (x0 x1 y0 y1) (z0 z1 thr0 thr1)
+  float4 &r = rec[2 * (idx >> 1) + 1];
+  std::memcpy((idx & 1) ? &r.w : &r.z, &thr, 4);
+}
+static inline void rec_set_xyz(float4 *rec, int idx, float x, float y, float z) {
+  float4 &a = rec[2 * (idx >> 1)], &b = rec[2 * (idx >> 1) + 1];
+  if (idx & 1) { a.y = x; a.w = y; b.y = z; }
+  else { a.x = x; a.z = y; b.x = z; }
+}
+
+// Thresholds of the fast kernel's node tables under the current link-disable mask (host only: the tables travel in the
+// kernel parameters, nothing is copied or synchronised).  CollisionChecker::setDisabledLinkMapCollisions (CC:90-102).
+static void apply_link_mask(Ctx *c) {
+  c->rb.link_disabled = c->rb_grid.link_disabled = c->link_disabled;
+  if (!c->fast.ok) return;
+  KfTab &t = c->kftab;
+  for (size_t k = 0; k < c->clusters.size(); ++k) {
+    const HostCluster &cl = c->clusters[k];
+    const bool off = (c->link_disabled >> cl.link) & 1ull;
+    for (int sl = cl.slot0; sl < cl.slot0 + cl.nslots; ++sl) rec_set_thr(t.leaf, sl, off ? -2 : c->kf_leaf_thr[size_t(sl)]);
+    rec_set_thr(t.bound, c->kf_bound_idx[k], off ? -2 : c->kf_bound_thr[k]);
+  }
+}
+
+// Layer ranges of the slab fields for the current grid (yaw-only base group): one slab per link of that group (the
+// layers its spheres can touch) + one for the whole group (root bound).  slab_of_link[l] / slab_root index c->slab_k0/k1.
+static void plan_slabs(Ctx *c, double oz, double res, int gz) {
+  c->slab_k0.clear();
+  c->slab_k1.clear();
+  for (int l = 0; l < SQMP_MAX_LINKS; ++l) c->slab_of_link[l] = -1;
+  c->slab_root = -1;
+  const int g = c->base2d_group;
+  if (g < 0) return;
+  auto range_of = [&](double zlo, double zhi, int &k0, int &k1) {
+    k0 = int(std::floor((c->base2d_z0 + zlo - oz) / res - 1e-4));
+    k1 = int(std::floor((c->base2d_z0 + zhi - oz) / res + 1e-4));
+    if (k0 < 0) k0 = 0;
+    if (k1 > gz - 1) k1 = gz - 1;
+    if (k1 < k0) { k0 = 0; k1 = -1; }   // out of the grid: an empty slab (nothing to hit)
+  };
+  auto slab_for = [&](int k0, int k1) {
+    for (size_t s = 0; s < c->slab_k0.size(); ++s)
+      if (c->slab_k0[s] == k0 && c->slab_k1[s] == k1) return int(s);
+    c->slab_k0.push_back(k0);
+    c->slab_k1.push_back(k1);
+    return int(c->slab_k0.size()) - 1;
+  };
+  int k0, k1;
+  range_of(c->grp_zlo[g], c->grp_zhi[g], k0, k1);
+  c->slab_root = slab_for(k0, k1);
+  for (int l = 0; l < SQMP_MAX_LINKS; ++l) {
+    double zlo = 1e300, zhi = -1e300;
+    for (int k = c->grp_cluster_end[g]; k < c->grp_cluster_end[g + 1]; ++k)
+      if (c->clusters[size_t(k)].link == l) {
+        zlo = std::fmin(zlo, c->clusters[size_t(k)].zlo);
+        zhi = std::fmax(zhi, c->clusters[size_t(k)].zhi);
+      }
+    if (zlo > zhi) continue;
+    range_of(zlo, zhi, k0, k1);
+    c->slab_of_link[l] = slab_for(k0, k1);
+  }
+}
+
+// Grid-unit copy of the robot for the validity kernels: lengths / res, root offset measured from the grid origin, the
+// slot tables with their distance-field thresholds, the node tables of the fast kernel, the self-collision tables.
+// Re-derived whenever the grid changes (CC:76-88).
 static int refresh_grid_robot(Ctx *c) {
   const RobotDev &rb = c->rb;
   RobotDev &g = c->rb_grid;
@@ -156,245 +432,126 @@ static int refresh_grid_robot(Ctx *c) {
   for (int s = 0; s < rb.n_seg; ++s)
     for (int i = 9; i < 12; ++i) g.seg_pre[s][i] = rb.seg_pre[s][i] * inv;
   for (int i = 0; i < 3; ++i) g.root_off[i] = (rb.root_off[i] - o[i]) * inv;
-  // slots: every group's spheres padded to a multiple of 4 with copies of its last sphere
-  int n_slots = 0;
-  for (int s = 0; s <= SQMP_MAX_SEG; ++s) {   // group s-1 (s = 0: the root) owns spheres [end[s], end[s+1])
-    g.seg_sph_end[s] = n_slots;
-    const int b = rb.seg_sph_end[s], e = rb.seg_sph_end[s + 1];
-    for (int i = b; i < e; ++i) {
-      c->slot_sph[n_slots] = i;
-      c->sph_slot[i] = n_slots++;
-    }
-    while (e > b && (n_slots & 3)) c->slot_sph[n_slots++] = -(e - 1) - 1;   // pad: -(sphere copied)-1
-  }
-  g.seg_sph_end[SQMP_MAX_SEG + 1] = n_slots;
-  g.n_spheres = n_slots;
-  for (int sl = 0; sl < n_slots; ++sl) {
-    const bool pad_slot = c->slot_sph[sl] < 0;
-    const int i = pad_slot ? -c->slot_sph[sl] - 1 : c->slot_sph[sl];
-    if (pad_slot) c->slot_sph[sl] = -1;
-    for (int k = 0; k < 4; ++k) g.sph[sl][k] = rb.sph[i][k] * inv;
-    const double r = rb.sph[i][3];
-    if (!has) {
-      g.sph_thr[sl] = -2;
-      g.sph_ncell[sl] = 0;
-      continue;
-    }
-    const double rc = r * inv;  // radius in cells; sqmp_set_voxel_grid guarantees rc <= 13, so rc^2 < 255
-    const double t = std::floor(rc * rc + 1e-9);
-    const bool enabled = !pad_slot && ((rb.sph_enabled[i >> 5] >> (i & 31)) & 1u);
-    g.sph_thr[sl] = enabled ? short(t > 254.0 ? 254.0 : t) : short(-2);
-    const double n = std::ceil(r / c->gd.res);
-    g.sph_ncell[sl] = (unsigned char)(n > 250.0 ? 250.0 : n);
-  }
   refresh_float_copies(g);
   refresh_float_copies(c->rb);
-  // ---- tables of the fast validity kernel.  Its stage 1 runs on an fp32 copy of the sphere centre; err bounds the
+  const int n_slots = rb.n_slots;
+  // ---- slot table of the generic kernel ----
+  {
+    std::vector<K1Slot> ks(size_t(n_slots) + 4);
+    for (int sl = 0; sl < n_slots; ++sl) {
+      int i = c->slot_sph[size_t(sl)];
+      const bool pad_slot = i < 0;
+      if (pad_slot) {   // a pad repeats the last real sphere of its cluster and never tests positive
+        int t = sl;
+        while (c->slot_sph[size_t(t)] < 0) --t;
+        i = c->slot_sph[size_t(t)];
+      }
+      const HostSphere &s = c->sph[size_t(i)];
+      K1Slot &k = ks[size_t(sl)];
+      k.x = s.c[0] * inv; k.y = s.c[1] * inv; k.z = s.c[2] * inv; k.r = s.r * inv;
+      const double rc = s.r * inv;   // radius in cells; sqmp_set_voxel_grid guarantees rc <= 13, so rc^2 < 255
+      const double t = std::floor(rc * rc + 1e-9);
+      k.thr = (!has || pad_slot) ? -2 : int(t > 254.0 ? 254.0 : t);
+      const double n = std::ceil(rc);
+      k.ncell = int(n > 250.0 ? 250.0 : n);
+      k.link = pad_slot ? -1 : s.link;
+      k.pad = 0;
+    }
+    if (!c->d_k1slots && cudaMalloc(&c->d_k1slots, sizeof(K1Slot) * (SQMP_MAX_SLOTS + 4)) != cudaSuccess)
+      return fail(c, SQMP_ERR_NOMEM, "cudaMalloc(slot table)");
+    if (n_slots > 0) CU(cudaMemcpy(c->d_k1slots, ks.data(), sizeof(K1Slot) * size_t(n_slots), cudaMemcpyHostToDevice));
+  }
+  // ---- tables of the fast validity kernel.  Its stage 1 runs on an fp32 copy of the node centre; err bounds the
   //      distance between that copy and the fp64 centre (cells): per axis <= 2^-24 * 13 (reach + 1) from rounding the
   //      frame, the sphere offset and three FMAs; doubled here, then sqrt(3) for the Euclidean norm.
-  {
-    c->fast.ok = 0;
-    if (has && c->fast_chain_ok && c->gd.halo > 0) {
-      const double reach_c = c->reach_m * inv + 1.0;
-      const double err = std::sqrt(3.0) * std::ldexp(26.0 * (reach_c + 1.0), -24) + 1e-6;
-      std::vector<FastPair> fp(size_t(n_slots) / 2 + 1);
-      std::vector<FastAux> fa(size_t(n_slots) + 1);
-      std::vector<double4> s64(size_t(n_slots) + 1);
-      for (int sl = 0; sl < n_slots; ++sl) {
-        const double rg = g.sph[sl][3];
-        FastPair &f = fp[sl >> 1];
-        const int h = sl & 1;
-        f.x[h] = float(g.sph[sl][0]); f.y[h] = float(g.sph[sl][1]); f.z[h] = float(g.sph[sl][2]);
-        const double t = std::floor((rg + err) * (rg + err) + 1e-9);
-        f.thr[h] = g.sph_thr[sl] < 0 ? -2 : int(t > 254.0 ? 254.0 : t);
-        const double lo = rg > err ? (rg - err) * (rg - err) * (1.0 - 1e-6) : -1.0;
-        float lof = float(lo);
-        if (double(lof) > lo) lof = std::nextafterf(lof, -INFINITY);
-        fa[sl].r2_lo = lof;
-        fa[sl].ncell = int(g.sph_ncell[sl]) + 1;
-        s64[sl] = make_double4(g.sph[sl][0], g.sph[sl][1], g.sph[sl][2], rg);
+  c->fast.ok = 0;
+  int n_bounds = 0;
+  for (int gi = 0; gi < SQMP_MAX_GROUPS; ++gi) n_bounds += (c->grp_cluster_end[gi + 1] - c->grp_cluster_end[gi] + 7) / 8 * 8;
+  if (has && c->fast_chain_ok && c->gd.halo > 0 && n_slots <= KF_MAX_SLOTS && n_bounds <= KF_MAX_BOUNDS) {
+    const double reach_c = c->reach_m * inv + 1.0;
+    const double err = std::sqrt(3.0) * std::ldexp(26.0 * (reach_c + 1.0), -24) + 1e-6;
+    const int W3 = c->ft_window, W2 = c->slab_window;
+    auto thr_of = [&](double rg, int window) {   // field > thr proves a node of radius rg free; 255: cannot be proven (always open)
+      const double t = std::floor((rg + err) * (rg + err) + 1e-9);
+      return (t > 254.0 || t >= double(window) * window) ? 255 : int(t);
+    };
+    KfTab &t = c->kftab;
+    std::memset(&t, 0, sizeof(t));
+    t.base2d_group = c->base2d_group;
+    c->kf_leaf_thr.assign(size_t(n_slots) + 2, -2);
+    c->kf_bound_thr.assign(c->clusters.size(), -2);
+    c->kf_bound_idx.assign(c->clusters.size(), 0);
+    std::vector<FastAux> fa(size_t(n_slots) + 1);
+    std::vector<double4> s64(size_t(n_slots) + 1);
+    for (int i = 0; i < KF_MAX_SLOTS; ++i) rec_set_thr(t.leaf, i, -2);
+    for (int i = 0; i < KF_MAX_BOUNDS; ++i) rec_set_thr(t.bound, i, -2);
+    int bidx = 0;
+    for (int gi = 0; gi < SQMP_MAX_GROUPS; ++gi) {
+      t.grp_bound_end[gi] = short(bidx);
+      const bool twod = gi == c->base2d_group;
+      for (int k = c->grp_cluster_end[gi]; k < c->grp_cluster_end[gi + 1]; ++k, ++bidx) {
+        const HostCluster &cl = c->clusters[size_t(k)];
+        const float slabf = twod ? float(c->slab_of_link[cl.link]) : 0.0f;
+        c->kf_bound_idx[size_t(k)] = bidx;
+        if (twod) {
+          rec_set_xyz(t.bound, bidx, float(cl.c2[0] * inv), float(cl.c2[1] * inv), slabf);
+          c->kf_bound_thr[size_t(k)] = thr_of(cl.R2 * inv, W2);
+        } else {
+          rec_set_xyz(t.bound, bidx, float(cl.c[0] * inv), float(cl.c[1] * inv), float(cl.c[2] * inv));
+          c->kf_bound_thr[size_t(k)] = thr_of(cl.R * inv, W3);
+        }
+        t.bound_first[bidx] = short(cl.slot0);
+        t.bound_count[bidx] = (unsigned char)cl.nslots;
+        for (int sl = cl.slot0; sl < cl.slot0 + cl.nslots; ++sl) {
+          int i = c->slot_sph[size_t(sl)];
+          const bool pad_slot = i < 0;
+          if (pad_slot) i = cl.members.back();
+          const HostSphere &sp = c->sph[size_t(i)];
+          const double rg = sp.r * inv;
+          rec_set_xyz(t.leaf, sl, float(sp.c[0] * inv), float(sp.c[1] * inv), twod ? slabf : float(sp.c[2] * inv));
+          c->kf_leaf_thr[size_t(sl)] = pad_slot ? -2 : thr_of(rg, twod ? W2 : W3);
+          FastAux &a = fa[size_t(sl)];
+          a.x = float(sp.c[0] * inv); a.y = float(sp.c[1] * inv); a.z = float(sp.c[2] * inv);
+          const double lo = rg > err ? (rg - err) * (rg - err) * (1.0 - 1e-6) : -1.0;
+          float lof = float(lo);
+          if (double(lof) > lo) lof = std::nextafterf(lof, -INFINITY);
+          a.r2_lo = lof;
+          a.ncell = int(std::ceil(rg)) + 1;
+          a.pad[0] = a.pad[1] = a.pad[2] = 0;
+          s64[size_t(sl)] = make_double4(sp.c[0] * inv, sp.c[1] * inv, sp.c[2] * inv, rg);
+        }
       }
-      cudaError_t e = cudaSuccess;
-      if (!c->d_fast_pairs) e = cudaMalloc(&c->d_fast_pairs, sizeof(FastPair) * (SQMP_MAX_SLOTS / 2 + 1));
-      if (e == cudaSuccess && !c->d_fast_aux) e = cudaMalloc(&c->d_fast_aux, sizeof(FastAux) * (SQMP_MAX_SLOTS + 1));
-      if (e == cudaSuccess && !c->d_fast_sph64) e = cudaMalloc(&c->d_fast_sph64, sizeof(double4) * (SQMP_MAX_SLOTS + 1));
-      if (e == cudaSuccess) e = cudaMemcpy(c->d_fast_pairs, fp.data(), sizeof(FastPair) * (n_slots / 2), cudaMemcpyHostToDevice);
-      if (e == cudaSuccess) e = cudaMemcpy(c->d_fast_aux, fa.data(), sizeof(FastAux) * n_slots, cudaMemcpyHostToDevice);
-      if (e == cudaSuccess) e = cudaMemcpy(c->d_fast_sph64, s64.data(), sizeof(double4) * n_slots, cudaMemcpyHostToDevice);
-      if (e != cudaSuccess) return fail(c, SQMP_ERR_CUDA, "fast validity tables", e);
-      c->fast.pairs = c->d_fast_pairs;
-      c->fast.aux = c->d_fast_aux;
-      c->fast.sph64 = c->d_fast_sph64;
-      c->fast.n_slots = n_slots;
-      c->fast.ok = 1;
+      while (bidx & 7) ++bidx;   // the kernel tests bounds eight at a time
+      // root bound of the group
+      int rthr = -2;
+      float rx = 0.f, ry = 0.f, rz = 0.f;
+      if (c->grp_cluster_end[gi + 1] > c->grp_cluster_end[gi]) {
+        if (twod) {
+          rx = float(c->grp_root_c2[gi][0] * inv); ry = float(c->grp_root_c2[gi][1] * inv); rz = float(c->slab_root);
+          rthr = thr_of(c->grp_root_R2[gi] * inv, W2);
+        } else {
+          rx = float(c->grp_root_c[gi][0] * inv); ry = float(c->grp_root_c[gi][1] * inv); rz = float(c->grp_root_c[gi][2] * inv);
+          rthr = thr_of(c->grp_root_R[gi] * inv, W3);
+        }
+      }
+      float rt;
+      std::memcpy(&rt, &rthr, 4);
+      t.root[gi] = make_float4(rx, ry, rz, rt);
     }
+    t.grp_bound_end[SQMP_MAX_GROUPS] = short(bidx);
+    cudaError_t e = cudaSuccess;
+    if (!c->d_fast_aux) e = cudaMalloc(&c->d_fast_aux, sizeof(FastAux) * (KF_MAX_SLOTS + 1));
+    if (e == cudaSuccess && !c->d_fast_sph64) e = cudaMalloc(&c->d_fast_sph64, sizeof(double4) * (KF_MAX_SLOTS + 1));
+    if (e == cudaSuccess) e = cudaMemcpy(c->d_fast_aux, fa.data(), sizeof(FastAux) * size_t(n_slots), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(c->d_fast_sph64, s64.data(), sizeof(double4) * size_t(n_slots), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return fail(c, SQMP_ERR_CUDA, "fast validity tables", e);
+    c->fast.aux = c->d_fast_aux;
+    c->fast.sph64 = c->d_fast_sph64;
+    c->fast.n_slots = n_slots;
+    c->fast.ok = 1;
   }
-  // ---- self-collision hierarchy (SelfDev): blocks of group pairs -> A-spheres -> partner lists ----
-  {
-    int seg_of[SQMP_MAX_SPHERES];
-    for (int sgi = 0; sgi <= SQMP_MAX_SEG; ++sgi)
-      for (int i = rb.seg_sph_end[sgi]; i < rb.seg_sph_end[sgi + 1]; ++i) seg_of[i] = sgi;   // group index = segment + 1
-    for (int gi = 0; gi <= SQMP_MAX_SEG; ++gi) g.grp_fidx[gi] = -1;
-    g.n_frames = 0;
-    for (int p = 0; p < c->n_pairs; ++p)
-      for (int side = 0; side < 2; ++side) {
-        const int gi = seg_of[side ? c->h_pairs[p].b : c->h_pairs[p].a];
-        if (g.grp_fidx[gi] < 0) g.grp_fidx[gi] = g.n_frames++;
-      }
-    auto bound = [&](const std::vector<int> &sph, double (&cen)[3]) {   // enclosing sphere of a sphere set (metres)
-      cen[0] = cen[1] = cen[2] = 0.0;
-      for (int i : sph)
-        for (int k = 0; k < 3; ++k) cen[k] += rb.sph[i][k] / double(sph.size());
-      double R = 0.0;
-      for (int i : sph) {
-        double d2 = 0.0;
-        for (int k = 0; k < 3; ++k) d2 += (rb.sph[i][k] - cen[k]) * (rb.sph[i][k] - cen[k]);
-        R = std::fmax(R, std::sqrt(d2) + rb.sph[i][3]);
-      }
-      return R;
-    };
-    auto inflate2 = [&](double r_sum) {   // squared culling radius in grid units, padded against fp32 rounding
-      const double v = (r_sum * (1.0 + 1e-4) + 1e-6) * inv;
-      return float(v * v * (1.0 + 1e-6));
-    };
-    std::vector<SelfPair> flat(size_t(c->n_pairs) + 1);
-    std::vector<SelfHPair> hier;
-    std::vector<SelfA> as;
-    std::vector<SelfBlock> blocks;
-    for (int p = 0; p < c->n_pairs; ++p) {
-      const int a = c->h_pairs[p].a, b = c->h_pairs[p].b;
-      const double rs = (rb.sph[a][3] + rb.sph[b][3]) * inv;
-      flat[p].a = (unsigned char)c->sph_slot[a];
-      flat[p].b = (unsigned char)c->sph_slot[b];
-      flat[p].fa = (unsigned char)g.grp_fidx[seg_of[a]];
-      flat[p].fb = (unsigned char)g.grp_fidx[seg_of[b]];
-      flat[p].rsum2 = float(rs * rs);
-    }
-    for (int ga = 0; ga <= SQMP_MAX_SEG; ++ga)
-      for (int gb = 0; gb <= SQMP_MAX_SEG; ++gb) {
-        std::vector<int> members, sa, sb;
-        for (int p = 0; p < c->n_pairs; ++p)
-          if (seg_of[c->h_pairs[p].a] == ga && seg_of[c->h_pairs[p].b] == gb) members.push_back(p);
-        if (members.empty()) continue;
-        for (int p : members) {
-          const int a = c->h_pairs[p].a, b = c->h_pairs[p].b;
-          if (std::find(sa.begin(), sa.end(), a) == sa.end()) sa.push_back(a);
-          if (std::find(sb.begin(), sb.end(), b) == sb.end()) sb.push_back(b);
-        }
-        // The A side is split into spatial clusters of <= ~5 spheres (farthest-point seeds + a few Lloyd steps on the
-        // sphere centres): the base group spans the whole robot, so one bounding sphere for it never rules a block
-        // out, while a cluster's does.  All clusters of one (group A, group B) share the B-side bound, so the kernel
-        // forms that bound in A's frame once and tests every cluster, and every A-sphere, against it as constants.
-        std::vector<std::vector<int> > clusters;
-        {
-          const int n = int(sa.size());
-          int k = n <= 6 ? 1 : (n + 4) / 5;
-          if (k > 8) k = 8;
-          std::vector<int> seed(1, 0), assign(size_t(n), 0);
-          auto d2 = [&](int i, const double *q) {
-            double v = 0.0;
-            for (int t = 0; t < 3; ++t) v += (rb.sph[sa[size_t(i)]][t] - q[t]) * (rb.sph[sa[size_t(i)]][t] - q[t]);
-            return v;
-          };
-          std::vector<std::array<double, 3> > cen;
-          cen.push_back({rb.sph[sa[0]][0], rb.sph[sa[0]][1], rb.sph[sa[0]][2]});
-          while (int(cen.size()) < k) {   // farthest point from the chosen seeds
-            int best = 0;
-            double bd = -1.0;
-            for (int i = 0; i < n; ++i) {
-              double m = 1e300;
-              for (auto &q : cen) m = std::fmin(m, d2(i, q.data()));
-              if (m > bd) { bd = m; best = i; }
-            }
-            cen.push_back({rb.sph[sa[size_t(best)]][0], rb.sph[sa[size_t(best)]][1], rb.sph[sa[size_t(best)]][2]});
-          }
-          for (int it = 0; it < 8; ++it) {
-            for (int i = 0; i < n; ++i) {
-              int best = 0;
-              for (int q = 1; q < k; ++q)
-                if (d2(i, cen[size_t(q)].data()) < d2(i, cen[size_t(best)].data())) best = q;
-              assign[size_t(i)] = best;
-            }
-            for (int q = 0; q < k; ++q) {
-              double sum[3] = {0, 0, 0};
-              int cnt = 0;
-              for (int i = 0; i < n; ++i)
-                if (assign[size_t(i)] == q) {
-                  for (int t = 0; t < 3; ++t) sum[t] += rb.sph[sa[size_t(i)]][t];
-                  ++cnt;
-                }
-              if (cnt)
-                for (int t = 0; t < 3; ++t) cen[size_t(q)][size_t(t)] = sum[t] / cnt;
-            }
-          }
-          clusters.assign(size_t(k), std::vector<int>());
-          for (int i = 0; i < n; ++i) clusters[size_t(assign[size_t(i)])].push_back(sa[size_t(i)]);
-        }
-        double cB[3];
-        const double RB = bound(sb, cB);
-        for (const std::vector<int> &cl : clusters) {
-          if (cl.empty()) continue;
-          double cA[3];
-          const double RA = bound(cl, cA);
-          SelfBlock blk;
-          blk.fa = g.grp_fidx[ga];
-          blk.fb = g.grp_fidx[gb];
-          blk.a_begin = int(as.size());
-          for (int k = 0; k < 3; ++k) {
-            blk.ca[k] = float(cA[k] * inv);
-            blk.cb[k] = float(cB[k] * inv);
-          }
-          blk.thr2 = inflate2(RA + RB);
-          blk.pad = 0.0f;
-          for (int a : cl) {
-            SelfA ea;
-            ea.a = c->sph_slot[a];
-            ea.pad = 0;
-            ea.cx = float(rb.sph[a][0] * inv); ea.cy = float(rb.sph[a][1] * inv); ea.cz = float(rb.sph[a][2] * inv);
-            ea.p_begin = int(hier.size());
-            for (int p : members)
-              if (c->h_pairs[p].a == a) {
-                const int b = c->h_pairs[p].b;
-                SelfHPair hp;
-                hp.bx = float(rb.sph[b][0] * inv); hp.by = float(rb.sph[b][1] * inv); hp.bz = float(rb.sph[b][2] * inv);
-                hp.rsum2 = flat[p].rsum2;
-                hier.push_back(hp);
-              }
-            ea.p_end = int(hier.size());
-            ea.thr2 = inflate2(rb.sph[a][3] + RB);
-            as.push_back(ea);
-          }
-          blk.a_end = int(as.size());
-          blocks.push_back(blk);
-        }
-      }
-    hier.resize(size_t(c->n_pairs) + 4);   // the kernels read partners and A-spheres four at a time (masked)
-    const size_t n_as_real = as.size();
-    as.resize(n_as_real + 4);
-    auto upload = [&](auto *&dptr, const auto &vec, size_t min_count) -> cudaError_t {
-      using E = typename std::remove_reference<decltype(vec)>::type::value_type;
-      const size_t count = vec.size() > min_count ? vec.size() : min_count;
-      if (!dptr) {
-        cudaError_t e = cudaMalloc(&dptr, sizeof(E) * (count + 1));
-        if (e != cudaSuccess) return e;
-      }
-      return vec.empty() ? cudaSuccess : cudaMemcpy(dptr, vec.data(), sizeof(E) * vec.size(), cudaMemcpyHostToDevice);
-    };
-    // sizes depend only on the pair list, which is fixed at sqmp_create: allocated once with that capacity
-    cudaError_t e = upload(c->d_pairs, hier, size_t(c->n_pairs) + 4);
-    if (e == cudaSuccess) e = upload(c->d_flat, flat, size_t(c->n_pairs) + 1);
-    if (e == cudaSuccess) e = upload(c->d_as, as, size_t(c->n_pairs) + 4);
-    if (e == cudaSuccess) e = upload(c->d_blocks, blocks, size_t(SQMP_MAX_SEG + 1) * (SQMP_MAX_SEG + 1) * 8);   // <= 8 clusters per group pair
-    if (e != cudaSuccess) return fail(c, SQMP_ERR_CUDA, "self-collision tables", e);
-    c->self.hpairs = c->d_pairs;
-    c->self.flat = c->d_flat;
-    c->self.as = c->d_as;
-    c->self.blocks = c->d_blocks;
-    c->self.n_pairs = c->n_pairs;
-    c->self.n_as = int(n_as_real);
-    c->self.n_blocks = int(blocks.size());
-  }
-  return SQMP_OK;
+  apply_link_mask(c);
+  return build_self_tables(c, inv);
 }
 
 // |node|^2 bound used by the fp32 pre-filter of K3/K4 (nn.cu); non-finite rows make it +inf (= no filtering)
@@ -533,7 +690,7 @@ struct sqmp_ctx : public sqmp::Ctx {};
 
 extern "C" {
 
-const char *sqmp_version(void) { return "libsqmp_b200 r1 (sm_100a)"; }
+const char *sqmp_version(void) { return "libsqmp_b200 r2 (sm_100a)"; }
 
 const char *sqmp_strerror(int code) {
   switch (code) {
@@ -554,8 +711,7 @@ sqmp_ctx *sqmp_create(int device, const sqmp_robot_desc *d, int *err_out) {
     if (err_out) *err_out = code;
     return nullptr;
   };
-  if (!d || d->n_seg < 1 || d->n_seg > SQMP_MAX_SEG || d->n_spheres < 0 || d->n_spheres > SQMP_MAX_SPHERES ||
-      d->n_pairs < 0 || d->n_pairs > SQMP_MAX_PAIRS)
+  if (!d || d->n_seg < 1 || d->n_seg > SQMP_MAX_SEG || d->n_spheres < 0 || d->n_spheres > SQMP_MAX_SPHERES)
     return bail(SQMP_ERR_INVALID);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return bail(SQMP_ERR_NODEVICE);
@@ -572,9 +728,11 @@ sqmp_ctx *sqmp_create(int device, const sqmp_robot_desc *d, int *err_out) {
   std::memset(&c->gd, 0, sizeof(c->gd));
   std::memset(c->trees, 0, sizeof(c->trees));
   std::memset(&c->nn, 0, sizeof(c->nn));
+  std::memset(&c->self, 0, sizeof(c->self));
+  std::memset(&c->fast, 0, sizeof(c->fast));
+  std::memset(&c->kftab, 0, sizeof(c->kftab));
   RobotDev &rb = c->rb;
   rb.n_seg = d->n_seg;
-  rb.n_spheres = d->n_spheres;
   rb.self_const_collision = d->self_const_collision;
   rb.ref_seg = -1;
   rb.trans_mask = 0;
@@ -600,27 +758,34 @@ sqmp_ctx *sqmp_create(int device, const sqmp_robot_desc *d, int *err_out) {
   std::memcpy(rb.ee_tip, d->ee_tip, sizeof(double) * 12);
   rb.ee_tip_kind = frame_kind_of(d->ee_tip);
   int prev = -1;
-  for (int s = 0; s <= SQMP_MAX_SEG + 1; ++s) rb.seg_sph_end[s] = 0;
   c->fk_float_ok = 1;
+  c->sph.resize(size_t(d->n_spheres));
   for (int i = 0; i < d->n_spheres; ++i) {
     const int sg = d->sph_seg[i];
-    if (sg < prev || sg < -1 || sg >= d->n_seg || d->sph_link[i] < 0 || d->sph_link[i] > 63 ||
+    if (sg < prev || sg < -1 || sg >= d->n_seg || d->sph_link[i] < 0 || d->sph_link[i] >= SQMP_MAX_LINKS ||
         !(d->sph_radius[i] > 0.0)) {
       delete c;
       return bail(SQMP_ERR_INVALID);
     }
     prev = sg;
-    rb.seg_sph_end[sg + 2] = i + 1;
-    rb.sph[i][0] = d->sph_center[3 * i + 0];
-    rb.sph[i][1] = d->sph_center[3 * i + 1];
-    rb.sph[i][2] = d->sph_center[3 * i + 2];
-    rb.sph[i][3] = d->sph_radius[i];
-    c->sph_link[i] = d->sph_link[i];
+    HostSphere &h = c->sph[size_t(i)];
+    h.c[0] = d->sph_center[3 * i + 0];
+    h.c[1] = d->sph_center[3 * i + 1];
+    h.c[2] = d->sph_center[3 * i + 2];
+    h.r = d->sph_radius[i];
+    h.link = d->sph_link[i];
+    h.grp = sg + 1;
+    if (h.link + 1 > c->n_links) c->n_links = h.link + 1;
     if (sg <= rb.ref_seg) c->fk_float_ok = 0;  // float chain starts after the prismatic base
   }
-  for (int s = 1; s <= SQMP_MAX_SEG + 1; ++s)
-    if (rb.seg_sph_end[s] < rb.seg_sph_end[s - 1]) rb.seg_sph_end[s] = rb.seg_sph_end[s - 1];
-  for (int w = 0; w < SQMP_MAX_SPHERES / 32; ++w) rb.sph_enabled[w] = 0xffffffffu;
+  for (int l = 0; l < SQMP_MAX_LINKS; ++l) {
+    c->link_pair_mask[l] = d->link_pair_mask[l];
+    c->slab_of_link[l] = -1;
+  }
+  for (int a = 0; a < SQMP_MAX_LINKS; ++a)   // symmetric, no self pairs
+    for (int b = 0; b < SQMP_MAX_LINKS; ++b)
+      if (a == b) c->link_pair_mask[a] &= ~(1ull << a);
+      else if ((d->link_pair_mask[a] >> b) & 1ull) c->link_pair_mask[b] |= 1ull << a;
   // fast validity kernel: the base is a translation-only run, everything after it rotates (bounded reach), and every
   // sphere sits on the rotating part.  reach_m bounds |sphere centre - base reference point| over all configurations.
   c->fast_chain_ok = c->fk_float_ok && rb.ref_seg >= 0;
@@ -631,26 +796,32 @@ sqmp_ctx *sqmp_create(int device, const sqmp_robot_desc *d, int *err_out) {
       if (rb.seg_type[s] != SQMP_JOINT_ROT) c->fast_chain_ok = 0;
       cum += std::sqrt(rb.seg_pre[s][9] * rb.seg_pre[s][9] + rb.seg_pre[s][10] * rb.seg_pre[s][10] +
                        rb.seg_pre[s][11] * rb.seg_pre[s][11]);
-      for (int i = rb.seg_sph_end[s + 1]; i < rb.seg_sph_end[s + 2]; ++i)
-        c->reach_m = std::fmax(c->reach_m, cum + std::sqrt(rb.sph[i][0] * rb.sph[i][0] + rb.sph[i][1] * rb.sph[i][1] +
-                                                            rb.sph[i][2] * rb.sph[i][2]));
+      for (const HostSphere &h : c->sph)
+        if (h.grp == s + 1)
+          c->reach_m = std::fmax(c->reach_m, cum + std::sqrt(h.c[0] * h.c[0] + h.c[1] * h.c[1] + h.c[2] * h.c[2]) + h.r);
     }
     if (!(c->reach_m < 1.0e6)) c->fast_chain_ok = 0;
   }
-
-  c->n_pairs = d->n_pairs;
-  c->h_pairs.resize(size_t(d->n_pairs) + 1);
-  for (int p = 0; p < d->n_pairs; ++p) {
-    const int a = d->pair_a[p], b = d->pair_b[p];
-    if (a < 0 || b < 0 || a >= d->n_spheres || b >= d->n_spheres) {
-      delete c;
-      return bail(SQMP_ERR_INVALID);
+  // yaw-only base group: the leading prismatic run moves in x, y only, the first rotating segment turns about +-z with a
+  // translation-only pre-frame -> the world z of that group's spheres never changes, so they can be tested against
+  // 2-D slab fields that leave out the layers they cannot touch (in particular the floor right under the robot).
+  c->base2d_group = -1;
+  if (c->fast_chain_ok && rb.ref_seg + 1 < rb.n_seg) {
+    const int s0 = rb.ref_seg + 1;
+    bool ok2 = (rb.seg_axis_code[s0] == AX_PZ || rb.seg_axis_code[s0] == AX_NZ) && rb.seg_pre_kind[s0] <= 1;
+    double z0 = rb.root_off[2];
+    for (int s = 0; s <= s0; ++s) {
+      z0 += rb.seg_pre[s][11];
+      if (s < s0 && rb.seg_axis[s][2] != 0.0) ok2 = false;
     }
-    const double rs = d->sph_radius[a] + d->sph_radius[b];
-    c->h_pairs[p].a = (unsigned char)a;
-    c->h_pairs[p].b = (unsigned char)b;
-    c->h_pairs[p].fa = c->h_pairs[p].fb = 0;
-    c->h_pairs[p].rsum2 = float(rs * rs);
+    if (ok2) {
+      c->base2d_group = s0 + 1;
+      c->base2d_z0 = z0;
+    }
+  }
+  if (build_hierarchy(c) != SQMP_OK) {
+    delete c;
+    return bail(SQMP_ERR_INVALID);
   }
   bool ok = true;
   ok = ok && cudaHostAlloc((void **)&c->pin_h, PIN_BYTES, cudaHostAllocMapped) == cudaSuccess;
@@ -658,6 +829,8 @@ sqmp_ctx *sqmp_create(int device, const sqmp_robot_desc *d, int *err_out) {
   ok = ok && cudaMalloc(&c->d_ticket, 64) == cudaSuccess && cudaMemset(c->d_ticket, 0, 64) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&c->streams[0], cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&c->streams[1], cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&c->ev[0], cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&c->ev[1], cudaEventDisableTiming) == cudaSuccess;
   if (!ok || refresh_grid_robot(c) != SQMP_OK) {
     sqmp_destroy(c);
     return bail(SQMP_ERR_CUDA);
@@ -670,16 +843,17 @@ void sqmp_destroy(sqmp_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  if (ctx->d_pairs) cudaFree(ctx->d_pairs);
-  if (ctx->d_flat) cudaFree(ctx->d_flat);
-  if (ctx->d_as) cudaFree(ctx->d_as);
-  if (ctx->d_blocks) cudaFree(ctx->d_blocks);
+  if (ctx->d_self_gp) cudaFree(ctx->d_self_gp);
+  if (ctx->d_self_lp) cudaFree(ctx->d_self_lp);
+  if (ctx->d_self_links) cudaFree(ctx->d_self_links);
+  if (ctx->d_self_cl) cudaFree(ctx->d_self_cl);
+  if (ctx->d_self_leaves) cudaFree(ctx->d_self_leaves);
+  if (ctx->d_k1slots) cudaFree(ctx->d_k1slots);
   if (!ctx->grid_borrowed) {
     if (ctx->d_occ) cudaFree(ctx->d_occ);
     if (ctx->d_lb2) cudaFree(ctx->d_lb2);
     if (ctx->d_ft) cudaFree(ctx->d_ft);
   }
-  if (ctx->d_fast_pairs) cudaFree(ctx->d_fast_pairs);
   if (ctx->d_fast_aux) cudaFree(ctx->d_fast_aux);
   if (ctx->d_fast_sph64) cudaFree(ctx->d_fast_sph64);
   for (auto &t : ctx->trees) {
@@ -698,6 +872,8 @@ void sqmp_destroy(sqmp_ctx *ctx) {
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
   for (auto &s : ctx->streams)
     if (s) cudaStreamDestroy(s);
+  for (auto &e : ctx->ev)
+    if (e) cudaEventDestroy(e);
   delete ctx;
 }
 
@@ -745,28 +921,44 @@ int sqmp_set_voxel_grid(sqmp_ctx *ctx, const uint32_t *bits, int gx, int gy, int
   if (gx <= 0 || gy <= 0 || gz <= 0 || !origin || !(res > 0.0)) return fail(c, SQMP_ERR_INVALID, "bad grid");
   const int64_t nvox = int64_t(gx) * gy * gz;
   if (nvox >= (int64_t(1) << 32)) return fail(c, SQMP_ERR_INVALID, "grid too large (>= 2^32 voxels)");
-  double rmax = 0.0;
-  for (int i = 0; i < c->rb.n_spheres; ++i) rmax = std::fmax(rmax, c->rb.sph[i][3]);
+  double rmax = 0.0, bmax3 = 0.0, bmax2 = 0.0;
+  for (const HostSphere &h : c->sph) rmax = std::fmax(rmax, h.r);
+  for (const HostCluster &cl : c->clusters) {
+    if (cl.grp == c->base2d_group) bmax2 = std::fmax(bmax2, cl.R2);
+    else bmax3 = std::fmax(bmax3, cl.R);
+  }
+  for (int g = 0; g < SQMP_MAX_GROUPS; ++g) {
+    if (g == c->base2d_group) bmax2 = std::fmax(bmax2, c->grp_root_R2[g]);
+    else bmax3 = std::fmax(bmax3, c->grp_root_R[g]);
+  }
   // the 16-bit feature field stores cell offsets in [-15, 15]: every occupied cell within reach of a sphere
   // (|offset| <= ceil(r/res) + 1 per axis) must be representable
   if (rmax / res > 13.0) return fail(c, SQMP_ERR_INVALID, "sphere radius too large for this resolution (> 13 voxels)");
-  int window = int(std::ceil(rmax / res)) + 1;
+  // search windows of the field builds: a field value is exact up to window^2 - 1 and "255" beyond it, so a node can
+  // only be proven free when its threshold lies below window^2 (refresh_grid_robot marks the others "always open")
+  int window = int(std::ceil(std::fmax(rmax, bmax3) / res)) + 1;
   if (window < 3) window = 3;
   if (window > 15) window = 15;
+  int window2 = int(std::ceil(std::fmax(rmax, bmax2) / res)) + 1;
+  if (window2 < 3) window2 = 3;
+  if (window2 > 17) window2 = 17;
   // halo of the distance / feature fields: every cell a sphere centre can fall into while the base is inside the grid
   int halo = 0;
   if (c->fast_chain_ok) {
     const double h = std::ceil(c->reach_m / res) + 2.0;
-    const double pn = (gx + 2.0 * h) * (gy + 2.0 * h) * (gz + 2.0 * h);
+    const double pn = (gx + 2.0 * h) * (gy + 2.0 * h) * (gz + 2.0 * h + 64.0);
     if (h <= 2048.0 && pn < 4294967296.0) halo = int(h);   // else: no halo, generic kernel only
   }
+  plan_slabs(c, origin[2], res, gz);
+  const int n_slabs = halo > 0 ? int(c->slab_k0.size()) : 0;
   const int64_t PX = gx + 2 * halo, PY = gy + 2 * halo, PZ = gz + 2 * halo;
-  const int64_t pvox = PX * PY * PZ;
+  const int64_t pvox = PX * PY * PZ, pcol = PX * PY;
   const int row_words = (gx + 31) / 32 + 1;
   const size_t lin_words = size_t((nvox + 31) / 32) + 1;
   const size_t occ_words = size_t(gy) * gz * row_words;
+  const size_t lb_bytes = size_t(pvox) + 16 + size_t(n_slabs) * size_t(pcol);   // lb2, 16 zero bytes, the slab fields
   CU(cudaDeviceSynchronize());
-  uint32_t *d_lin = nullptr, *d_occ = nullptr;
+  uint32_t *d_lin = nullptr, *d_occ = nullptr, *d_col = nullptr;
   int8_t *d_a = nullptr;
   uint8_t *d_lb2 = nullptr;
   uint16_t *d_b = nullptr, *d_ft = nullptr;
@@ -774,6 +966,7 @@ int sqmp_set_voxel_grid(sqmp_ctx *ctx, const uint32_t *bits, int gx, int gy, int
     if (d_lin) cudaFree(d_lin);
     if (d_a) cudaFree(d_a);
     if (d_b) cudaFree(d_b);
+    if (d_col) cudaFree(d_col);
   };
   cudaError_t e = cudaMalloc(&d_lin, lin_words * 4);
   if (e == cudaSuccess) e = cudaMemset(d_lin, 0, lin_words * 4);
@@ -781,12 +974,16 @@ int sqmp_set_voxel_grid(sqmp_ctx *ctx, const uint32_t *bits, int gx, int gy, int
   if (e == cudaSuccess) e = cudaMalloc(&d_occ, occ_words * 4);
   if (e == cudaSuccess) e = cudaMalloc(&d_a, size_t(pvox));
   if (e == cudaSuccess) e = cudaMalloc(&d_b, size_t(pvox) * 2);
-  if (e == cudaSuccess) e = cudaMalloc(&d_lb2, size_t(pvox) + 16);   // + a zero byte at [pvox] (GridDev::zero_off)
-  if (e == cudaSuccess) e = cudaMemset(d_lb2 + pvox, 0, 16);
+  if (e == cudaSuccess) e = cudaMalloc(&d_lb2, lb_bytes);
+  if (e == cudaSuccess) e = cudaMemset(d_lb2 + pvox, 0, 16);   // the zero byte at [pvox] (GridDev::zero_off)
   if (e == cudaSuccess) e = cudaMalloc(&d_ft, size_t(pvox) * 2);
+  if (e == cudaSuccess && n_slabs > 0) e = cudaMalloc(&d_col, size_t(n_slabs) * gy * row_words * 4 + 16);
   if (e == cudaSuccess) e = launch_pack_rows(d_lin, gx, gy, gz, row_words, d_occ, nullptr);
   int nl = 1;
   if (e == cudaSuccess) e = launch_ft_build(d_occ, row_words, gx, gy, gz, halo, window, d_a, d_b, d_lb2, d_ft, nullptr, &nl);
+  if (e == cudaSuccess && n_slabs > 0)   // d_a is free again after the feature transform: scratch of the slab build
+    e = launch_slab_build(d_occ, row_words, gx, gy, gz, halo, window2, n_slabs, c->slab_k0.data(), c->slab_k1.data(), d_col, d_a,
+                          d_lb2 + pvox + 16, nullptr, &nl);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   cleanup();
   if (e != cudaSuccess) {
@@ -805,12 +1002,17 @@ int sqmp_set_voxel_grid(sqmp_ctx *ctx, const uint32_t *bits, int gx, int gy, int
   c->d_occ = d_occ;
   c->d_lb2 = d_lb2;
   c->d_ft = d_ft;
+  c->ft_window = window;
+  c->slab_window = window2;
   GridDev &g = c->gd;
   g.sx = unsigned(PX);
   g.splane = unsigned(PX * PY);
   g.org_off = unsigned((int64_t(halo) * PY + halo) * PX + halo);
   g.halo = halo;
   g.zero_off = unsigned(pvox);
+  g.slab_off = unsigned(pvox + 16);
+  g.splane2 = unsigned(pcol);
+  g.n_slabs = n_slabs;
   g.occ = d_occ; g.lb2_base = d_lb2; g.ft_base = d_ft;
   g.lb2 = d_lb2 + g.org_off; g.ft = d_ft + g.org_off;
   g.gx = gx; g.gy = gy; g.gz = gz; g.row_words = row_words;
@@ -825,7 +1027,8 @@ int sqmp_share_voxel_grid(sqmp_ctx *ctx, const sqmp_ctx *src) {
   if (!src || src == ctx) return fail(c, SQMP_ERR_INVALID, "share_voxel_grid: bad source");
   const Ctx *o = src;
   if (o->device != c->device || !o->gd.has_grid) return fail(c, SQMP_ERR_INVALID, "share_voxel_grid: source has no grid on this device");
-  if (o->reach_m != c->reach_m || o->fast_chain_ok != c->fast_chain_ok)
+  if (o->reach_m != c->reach_m || o->fast_chain_ok != c->fast_chain_ok || o->base2d_group != c->base2d_group ||
+      o->sph.size() != c->sph.size() || o->clusters.size() != c->clusters.size())
     return fail(c, SQMP_ERR_INVALID, "share_voxel_grid: contexts were created from different robot descriptions");
   CU(cudaDeviceSynchronize());
   if (!c->grid_borrowed) {
@@ -838,16 +1041,22 @@ int sqmp_share_voxel_grid(sqmp_ctx *ctx, const sqmp_ctx *src) {
   c->d_ft = o->d_ft;
   c->grid_borrowed = true;
   c->gd = o->gd;
+  c->ft_window = o->ft_window;
+  c->slab_window = o->slab_window;
+  plan_slabs(c, c->gd.oz, c->gd.res, c->gd.gz);   // same description, same grid -> the same slabs the source built
+  if (c->slab_k0 != o->slab_k0 || c->slab_k1 != o->slab_k1)
+    return fail(c, SQMP_ERR_INVALID, "share_voxel_grid: slab plans differ");
   return refresh_grid_robot(c);
 }
 
+// CollisionChecker::setDisabledLinkMapCollisions (CC:90-102): host-side only — the link mask and the thresholds it
+// switches travel in the kernel parameters of the next launch; no device work, no synchronisation.
 int sqmp_set_disabled_links(sqmp_ctx *ctx, uint64_t link_mask) {
-  CHECK_CTX();
-  for (int w = 0; w < SQMP_MAX_SPHERES / 32; ++w) c->rb.sph_enabled[w] = 0;
-  for (int i = 0; i < c->rb.n_spheres; ++i)
-    if (!((link_mask >> c->sph_link[i]) & 1ull)) c->rb.sph_enabled[i >> 5] |= 1u << (i & 31);
-  CU(cudaDeviceSynchronize());
-  return refresh_grid_robot(c);
+  if (!ctx) return SQMP_ERR_INVALID;
+  Ctx *c = ctx;
+  c->link_disabled = link_mask;
+  apply_link_mask(c);
+  return SQMP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------- validity
@@ -866,7 +1075,7 @@ static void k1f_launched(Ctx *c, cudaStream_t st) {
   c->k1f_stream = st;
 }
 static bool use_fast_k1(const Ctx *c, unsigned flags) {
-  if (c->k1_kernel == 1 || c->fk_precision != 64) return false;
+  if (c->k1_kernel == 1) return false;
   return c->fast.ok && (flags & SQMP_CHECK_MAP) && c->gd.has_grid;
 }
 int sqmp_check_states_dev(sqmp_ctx *ctx, const double *d_q, int64_t S, unsigned flags, uint32_t *d_mask,
@@ -882,11 +1091,10 @@ int sqmp_check_states_dev(sqmp_ctx *ctx, const double *d_q, int64_t S, unsigned 
   int nl = 0;
   const bool fast = use_fast_k1(c, flags);
   if (fast)
-    CU(launch_check_states_fast(c->rb_grid, c->gd, c->self, c->fast, d_q, nullptr, 0, S, flags, d_mask,
+    CU(launch_check_states_fast(c->rb_grid, c->gd, c->self, c->fast, c->kftab, d_q, nullptr, 0, S, flags, d_mask,
                                 c->chain_specialization != 0, k1f_may_overlap(c, st), st, &nl));
   else
-    CU(launch_check_states(c->rb_grid, c->gd, c->self, d_q, nullptr, 0, S, flags, d_mask, c->fk_precision,
-                           st, &nl));
+    CU(launch_check_states(c->rb_grid, c->gd, c->self, c->d_k1slots, d_q, nullptr, 0, S, flags, d_mask, st, &nl));
   c->launches += nl;
   if (fast) k1f_launched(c, st);
   return SQMP_OK;
@@ -918,7 +1126,7 @@ int sqmp_check_states_gather_dev(sqmp_ctx *ctx, const double *d_q, int64_t S, un
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   int nl = 0;
-  CU(launch_check_states_fast(c->rb_grid, c->gd, c->self, c->fast, d_q, nullptr, 0, S, flags, nullptr,
+  CU(launch_check_states_fast(c->rb_grid, c->gd, c->self, c->fast, c->kftab, d_q, nullptr, 0, S, flags, nullptr,
                               c->chain_specialization != 0, k1f_may_overlap(c, st), st, &nl, &pd));
   c->launches += nl;
   k1f_launched(c, st);
@@ -958,11 +1166,10 @@ int sqmp_check_edges_dev(sqmp_ctx *ctx, const double *d_a, const double *d_b, in
     int nl = 0;
     const bool fast = use_fast_k1(c, flags);
     if (fast)
-      CU(launch_check_states_fast(c->rb_grid, c->gd, c->self, c->fast, d_a, d_b, num_points, S, flags, d_mask,
+      CU(launch_check_states_fast(c->rb_grid, c->gd, c->self, c->fast, c->kftab, d_a, d_b, num_points, S, flags, d_mask,
                                   c->chain_specialization != 0, k1f_may_overlap(c, st), st, &nl));
     else
-      CU(launch_check_states(c->rb_grid, c->gd, c->self, d_a, d_b, num_points, S, flags, d_mask,
-                             c->fk_precision, st, &nl));
+      CU(launch_check_states(c->rb_grid, c->gd, c->self, c->d_k1slots, d_a, d_b, num_points, S, flags, d_mask, st, &nl));
     c->launches += nl;
     if (fast && !d_first) k1f_launched(c, st);
   }
@@ -1057,27 +1264,28 @@ int sqmp_check_edges(sqmp_ctx *ctx, const double *qa, const double *qb, int64_t 
   return SQMP_OK;
 }
 
-int sqmp_get_collisions(sqmp_ctx *ctx, const double q[SQMP_DOF], uint8_t *link_map_hit, uint8_t *pair_hit) {
+int sqmp_get_collisions(sqmp_ctx *ctx, const double q[SQMP_DOF], uint8_t *link_map_hit, uint8_t *link_pair_hit) {
   CHECK_CTX();
   if (!q || !link_map_hit) return fail(c, SQMP_ERR_INVALID, "get_collisions: null pointer");
   void *dq, *ds, *dp;
   int rc;
+  const size_t LL = size_t(SQMP_MAX_LINKS) * SQMP_MAX_LINKS;
   if ((rc = ensure(c, 0, SQMP_DOF * 8, &dq))) return rc;
   if ((rc = ensure(c, 2, SQMP_MAX_SLOTS, &ds))) return rc;
-  if ((rc = ensure(c, 3, size_t(c->n_pairs) + 1, &dp))) return rc;
+  if ((rc = ensure(c, 3, LL, &dp))) return rc;
   cudaStream_t st = c->streams[0];
   CU(cudaMemcpyAsync(dq, q, SQMP_DOF * 8, cudaMemcpyHostToDevice, st));
   CU(cudaMemsetAsync(ds, 0, SQMP_MAX_SLOTS, st));
-  CU(cudaMemsetAsync(dp, 0, size_t(c->n_pairs) + 1, st));
-  CU(launch_get_collisions(c->rb_grid, c->gd, c->self, (const double *)dq, (uint8_t *)ds, (uint8_t *)dp, st));
+  CU(cudaMemsetAsync(dp, 0, LL, st));
+  CU(launch_get_collisions(c->rb_grid, c->gd, c->self, c->d_k1slots, (const double *)dq, (uint8_t *)ds, (uint8_t *)dp, st));
   c->launches += 1;
-  uint8_t sh[SQMP_MAX_SLOTS];
-  CU(cudaMemcpyAsync(sh, ds, SQMP_MAX_SLOTS, cudaMemcpyDeviceToHost, st));
-  if (pair_hit && c->n_pairs) CU(cudaMemcpyAsync(pair_hit, dp, size_t(c->n_pairs), cudaMemcpyDeviceToHost, st));
+  std::vector<uint8_t> sh(SQMP_MAX_SLOTS);
+  CU(cudaMemcpyAsync(sh.data(), ds, SQMP_MAX_SLOTS, cudaMemcpyDeviceToHost, st));
+  if (link_pair_hit) CU(cudaMemcpyAsync(link_pair_hit, dp, LL, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  std::memset(link_map_hit, 0, 64);
-  for (int sl = 0; sl < c->rb_grid.n_spheres; ++sl)
-    if (sh[sl] && c->slot_sph[sl] >= 0) link_map_hit[c->sph_link[c->slot_sph[sl]]] = 1;
+  std::memset(link_map_hit, 0, SQMP_MAX_LINKS);
+  for (int sl = 0; sl < c->rb_grid.n_slots; ++sl)
+    if (sh[size_t(sl)] && c->slot_sph[size_t(sl)] >= 0) link_map_hit[c->sph[size_t(c->slot_sph[size_t(sl)])].link] = 1;
   return SQMP_OK;
 }
 

@@ -222,7 +222,8 @@ static __device__ __noinline__ unsigned drain_queue(const GridDev &gd, const War
 // ------------------------------------------------------------------------------------------------
 // the state of one thread: either given (row sl of q_in), or interpolated from the end points of edge sl / (P + 1)
 // with the reference's exact operation order (BS:4461-4462, 4478; no FMA); then parked in shared memory, prismatic
-// values converted to grid units.  Returns false for a non-finite or absurd joint value (no map test for that state).
+// values converted to grid units.  Returns false for a non-finite or absurd joint value: the kernels report such a state
+// "in collision" (fail closed, the spirit of CC:106-107; the oracle restates the same rule).
 // ------------------------------------------------------------------------------------------------
 template <bool EDGES>
 __device__ __forceinline__ void k1_load_state(const double *__restrict__ q_in, const double *__restrict__ q_end, int num_points,
@@ -252,7 +253,7 @@ __device__ __forceinline__ bool k1_park_state(const RobotDev &rb, const double (
 #pragma unroll
   for (int j = 0; j < SQMP_DOF; ++j) {
     const double v = ((rb.trans_mask >> j) & 1) ? q[j] * rb.len_scale : q[j];
-    sane = sane && (fabs(v) < 1.0e9);
+    sane = sane && (fabs(v) < 1.0e9) && (fabs(q[j]) < 1.0e7);   // the fail-closed rule of the boundary: |q_j| < 1e7
     q_mine[j * pitch] = v;
   }
   return sane;

@@ -1,6 +1,7 @@
-// k1_self.cuh — self collision over the enabled cross-group sphere pairs (CollisionChecker::checkSelfCollision,
-// CC:541-552; pair table CC:353-393), hierarchically (SelfDev in sqmp_common.cuh).  Shared by the validity kernels.
-// The caller has parked the frame of every rigid group that owns a pair in shared memory: f_mine[(slot * 12 + k) *
+// k1_self.cuh — self collision over the enabled link pairs whose links hang on different rigid groups
+// (CollisionChecker::checkSelfCollision, CC:541-552; pair table CC:353-393), by nested bounds (SelfDev in
+// sqmp_common.cuh).  Shared by the validity kernels.
+// The caller has parked the frame of every rigid group that takes part in shared memory: f_mine[(slot * 12 + k) *
 // pitch], k = 0..8 rotation (row-major), 9..11 translation, fp32, all translations relative to one common point.
 #pragma once
 #include "sqmp_common.cuh"
@@ -20,66 +21,78 @@ __device__ __forceinline__ float self_dist2(float ax, float ay, float az, float 
   const float dx = ax - bx, dy = ay - by, dz = az - bz;
   return fmaf(dx, dx, fmaf(dy, dy, dz * dz));
 }
+// T = FA^-1 * FB: a point given in B's frame expressed in A's frame
+__device__ __forceinline__ void self_relative(const float (&FA)[12], const float (&FB)[12], float (&T)[12]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) T[3 * i + j] = fmaf(FA[i], FB[j], fmaf(FA[3 + i], FB[3 + j], FA[6 + i] * FB[6 + j]));
+  const float dx = FB[9] - FA[9], dy = FB[10] - FA[10], dz = FB[11] - FA[11];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) T[9 + i] = fmaf(FA[i], dx, fmaf(FA[3 + i], dy, FA[6 + i] * dz));
+}
 
-// true <=> some enabled pair of spheres of this state overlaps.  A level of the hierarchy is entered only if the
-// level above cannot rule it out, so a state far from self contact costs ~one test per block.  `blocks` and `as` may
-// point to shared-memory copies of SelfDev's tables (validity_fast.cu stages them: the loops below are chains of
-// dependent, warp-uniform loads, so their latency is the cost).
-__device__ __forceinline__ bool self_collision(const SelfBlock *blocks, int n_blocks, const SelfA *as, const SelfHPair *hpairs,
-                                               const float *f_mine, int pitch) {
-  int pfa = -1, pfb = -1;
-  float FA[12], FB[12], lx = 0.0f, ly = 0.0f, lz = 0.0f, ax, ay, az;
-  for (int bi = 0; bi < n_blocks; ++bi) {
-    const SelfBlock B = blocks[bi];
-    if (B.fa != pfa || B.fb != pfb) {   // blocks come sorted by group pair (warp-uniform): frames and B bound once per pair
-      pfa = B.fa;
-      pfb = B.fb;
-      self_load_frame(f_mine, pitch, B.fa, FA);
-      self_load_frame(f_mine, pitch, B.fb, FB);
-      float bx, by, bz;
-      self_xform(FB, B.cb[0], B.cb[1], B.cb[2], bx, by, bz);   // bounding sphere of the pair's B side, shared by its blocks
-      // ... expressed in A's frame (R_A^T (b - t_A)): A-side clusters and A-spheres are then tested as the constants
-      // they are, 7 instructions each instead of a 9-FMA transform
-      const float dx = bx - FA[9], dy = by - FA[10], dz = bz - FA[11];
-      lx = fmaf(FA[0], dx, fmaf(FA[3], dy, FA[6] * dz));
-      ly = fmaf(FA[1], dx, fmaf(FA[4], dy, FA[7] * dz));
-      lz = fmaf(FA[2], dx, fmaf(FA[5], dy, FA[8] * dz));
+// true <=> some sphere of link a overlaps some sphere of link b, for an enabled link pair (a, b) on different rigid
+// groups.  A level of the hierarchy is entered only if the level above cannot rule it out: group pair -> link pair ->
+// (link A, cluster of B) -> cluster pair -> (cluster of A, leaf of B) -> leaf pair.  Everything is expressed in A's
+// frame, so the A side is tested as the constants it is.  LINK_HITS (diagnostics): no early exit, every colliding link
+// pair is recorded in link_pair_hit[64 * 64].
+template <bool LINK_HITS>
+__device__ __forceinline__ bool self_collision(const SelfDev &sd, const float *f_mine, int pitch, uint8_t *link_pair_hit,
+                                               int gp0 = 0, int gp_step = 1) {
+  bool any = false;
+  for (int gi = gp0; gi < sd.n_gpairs; gi += gp_step) {
+    const SelfGroupPair G = sd.gpairs[gi];
+    float FA[12], FB[12], T[12];
+    self_load_frame(f_mine, pitch, G.fa, FA);
+    self_load_frame(f_mine, pitch, G.fb, FB);
+    self_relative(FA, FB, T);
+    float px, py, pz;
+    self_xform(T, G.bx, G.by, G.bz, px, py, pz);
+    {
+      const float rs = G.RA + G.RB;
+      if (self_dist2(px, py, pz, G.ax, G.ay, G.az) > rs * rs) continue;
     }
-    if (self_dist2(B.ca[0], B.ca[1], B.ca[2], lx, ly, lz) > B.thr2) continue;   // this A-side cluster is out of reach
-    // four A-spheres, then four partners, per step: the loops are chains of dependent warp-uniform loads and short
-    // arithmetic, so their cost is latency; batching gives the scheduler four independent chains (tables are padded
-    // by four records, out-of-range records are masked)
-    for (int ai = B.a_begin; ai < B.a_end; ai += 4) {
-      SelfA A[4];
-      unsigned pass = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) A[k] = as[ai + k];
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (ai + k < B.a_end && self_dist2(A[k].cx, A[k].cy, A[k].cz, lx, ly, lz) <= A[k].thr2) pass |= 1u << k;
-      while (pass) {
-        const int k = __ffs(pass) - 1;
-        pass &= pass - 1;
-        const SelfA Ak = k == 0 ? A[0] : (k == 1 ? A[1] : (k == 2 ? A[2] : A[3]));
-        self_xform(FA, Ak.cx, Ak.cy, Ak.cz, ax, ay, az);
-        // this A-sphere in B's frame (R_B^T (a - t_B)): its partners are then constants too
-        const float ex = ax - FB[9], ey = ay - FB[10], ez = az - FB[11];
-        const float mx = fmaf(FB[0], ex, fmaf(FB[3], ey, FB[6] * ez));
-        const float my = fmaf(FB[1], ex, fmaf(FB[4], ey, FB[7] * ez));
-        const float mz = fmaf(FB[2], ex, fmaf(FB[5], ey, FB[8] * ez));
-        for (int p = Ak.p_begin; p < Ak.p_end; p += 4) {
-          bool h = false;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const SelfHPair pr = hpairs[p + j];
-            h |= (p + j < Ak.p_end) && self_dist2(mx, my, mz, pr.bx, pr.by, pr.bz) <= pr.rsum2;
+    for (int lp = G.lp_begin; lp < G.lp_end; ++lp) {
+      const SelfLinkPair P = sd.lpairs[lp];
+      const SelfLink LA = sd.links[P.a], LB = sd.links[P.b];
+      self_xform(T, LB.x, LB.y, LB.z, px, py, pz);
+      const float rl = LA.R + LB.R;
+      if (self_dist2(px, py, pz, LA.x, LA.y, LA.z) > rl * rl) continue;
+      bool pair_hit = false;
+      for (int cb = LB.cl_begin; cb < LB.cl_end && !pair_hit; ++cb) {
+        const SelfCluster CB = sd.clusters[cb];
+        float qx, qy, qz;
+        self_xform(T, CB.x, CB.y, CB.z, qx, qy, qz);
+        const float r1 = LA.R + CB.R;
+        if (self_dist2(qx, qy, qz, LA.x, LA.y, LA.z) > r1 * r1) continue;
+        for (int ca = LA.cl_begin; ca < LA.cl_end && !pair_hit; ++ca) {
+          const SelfCluster CA = sd.clusters[ca];
+          const float r2 = CA.R + CB.R;
+          if (self_dist2(qx, qy, qz, CA.x, CA.y, CA.z) > r2 * r2) continue;
+          for (int b = CB.leaf_begin; b < CB.leaf_end && !pair_hit; ++b) {
+            const SelfLeaf Bl = sd.leaves[b];
+            float bx, by, bz;
+            self_xform(T, Bl.x, Bl.y, Bl.z, bx, by, bz);
+            const float r3 = CA.R + Bl.r;
+            if (self_dist2(bx, by, bz, CA.x, CA.y, CA.z) > r3 * r3) continue;
+            for (int a = CA.leaf_begin; a < CA.leaf_end; ++a) {
+              const SelfLeaf Al = sd.leaves[a];
+              const float rs = Al.r + Bl.r;
+              if (self_dist2(bx, by, bz, Al.x, Al.y, Al.z) <= rs * rs) { pair_hit = true; break; }
+            }
           }
-          if (h) return true;
         }
+      }
+      if (pair_hit) {
+        if (!LINK_HITS) return true;
+        any = true;
+        const int la = min(LA.link, LB.link), lb = max(LA.link, LB.link);
+        link_pair_hit[la * SQMP_MAX_LINKS + lb] = 1;
       }
     }
   }
-  return false;
+  return any;
 }
 
 }  // namespace sqmp

@@ -11,9 +11,12 @@
 
 namespace sqmp {
 
-// K1 walks "slots": the spheres of every rigid group padded to a multiple of 4 (pads repeat the last sphere and can
-// never test positive), so its 4-wide batches need no bounds logic.
-constexpr int SQMP_MAX_SLOTS = SQMP_MAX_SPHERES + 4 * (SQMP_MAX_SEG + 1);
+// The validity kernels walk "slots": the spheres of a rigid group are ordered cluster by cluster (a cluster = up to 8
+// spheres of ONE link that lie close together, capi.cu: build_hierarchy) and every cluster is padded to a multiple of 4
+// slots (pads can never test positive), so the 4- and 8-wide batches need no bounds logic.
+constexpr int SQMP_MAX_CLUSTERS = 256;
+constexpr int SQMP_MAX_SLOTS = SQMP_MAX_SPHERES + 3 * SQMP_MAX_CLUSTERS;
+constexpr int SQMP_MAX_GROUPS = SQMP_MAX_SEG + 1;   // rigid group g = segment g - 1; group 0 hangs on the root
 
 // axis codes: the joint axes of the reference robot are all signed unit axes (URDF:30-66, 615-759);
 // a general axis takes the Rodrigues path.
@@ -21,11 +24,12 @@ __host__ __device__ __forceinline__ int64_t imin64(int64_t a, int64_t b) { retur
 
 enum AxisCode : int { AX_GENERAL = 0, AX_PX = 1, AX_NX = 2, AX_PY = 3, AX_NY = 4, AX_PZ = 5, AX_NZ = 6 };
 
-// Chain + sphere table, passed by value as a __grid_constant__ kernel parameter: every access is
-// warp-uniform, so it is served from the constant bank / uniform datapath and never touches the LSU.
+// The kinematic chain, passed by value as a __grid_constant__ kernel parameter: every access is warp-uniform, so it
+// is served from the constant bank / uniform datapath and never touches the LSU.  (The sphere tables live in global
+// memory / in KfTab: a covering model has several hundred spheres.)
 struct RobotDev {
   int n_seg;
-  int n_spheres;                          // metres copy: spheres; grid-unit copy (K1): slots, see SQMP_MAX_SLOTS
+  int n_slots;                            // grid-unit copy: slots of the generic kernel's table (K1Slot)
   int ref_seg;                            // last segment of the leading prismatic run (base position)
   int self_const_collision;
   unsigned trans_mask;                    // bit j: q[j] drives a prismatic joint (a length)
@@ -34,26 +38,29 @@ struct RobotDev {
   int seg_qidx[SQMP_MAX_SEG];
   int seg_axis_code[SQMP_MAX_SEG];
   int seg_pre_kind[SQMP_MAX_SEG];         // 0 identity, 1 translation only, 2 general
-  int seg_sph_end[SQMP_MAX_SEG + 2];      // spheres of segment s (-1 = root) are [end[s+1-1], end[s+1])
-  int grp_fidx[SQMP_MAX_SEG + 1];         // group (segment + 1) -> slot of its frame in the self-collision scratch, -1: none
+  int grp_slot_end[SQMP_MAX_GROUPS + 1];  // slots of group g are [end[g], end[g+1])
+  int grp_fidx[SQMP_MAX_GROUPS];          // group -> slot of its frame in the self-collision scratch, -1: none
   int n_frames;
   double seg_pre[SQMP_MAX_SEG][12];
   double seg_axis[SQMP_MAX_SEG][3];
   double root_off[3];
   double ee_tip[12];
   int ee_tip_kind;
-  double sph[SQMP_MAX_SLOTS][4];        // cx cy cz r in the segment frame
   // fp32 copies of the constants (made by the host once; saves the F2F conversions in the float chain)
   float seg_pre_f[SQMP_MAX_SEG][12];
   float seg_axis_f[SQMP_MAX_SEG][4];
   float ee_tip_f[12];
-  float4 sph_f[SQMP_MAX_SLOTS];
-  // per-grid derived values (recomputed by sqmp_set_voxel_grid)
-  short sph_thr[SQMP_MAX_SLOTS];             // floor((r/res)^2): "lb2 > thr" proves the sphere free (integers, exact);
-                                              // -2 while the sphere's link is disabled (sqmp_set_disabled_links)
-  unsigned char sph_ncell[SQMP_MAX_SLOTS];  // ceil(r / res)
-  // per-request (sqmp_set_disabled_links)
-  uint32_t sph_enabled[SQMP_MAX_SPHERES / 32];
+  // per-request (sqmp_set_disabled_links, CC:90-102): bit l = link l is skipped by the map check
+  uint64_t link_disabled;
+};
+
+// One slot of the generic validity kernel (validity.cu), global memory, grid units.
+struct K1Slot {
+  double x, y, z, r;   // centre in the group frame, radius
+  int thr;             // floor(rg^2): "lb2 > thr" proves the sphere free (integers, exact); -2: pad slot
+  int ncell;           // ceil(rg)
+  int link;            // link index (disable mask, diagnostics); -1: pad slot
+  int pad;
 };
 
 struct GridDev {
@@ -70,6 +77,11 @@ struct GridDev {
   const uint16_t *ft_base;
   unsigned sx, splane, org_off;
   unsigned zero_off;     // lb2_base[zero_off] == 0: where the fast kernel points the gathers of lanes that must not be pruned
+  // Slab fields (fast kernel, yaw-only base group): for a set of z-layers [k0, k1] the 2-D squared box-to-box distance
+  // (cells, capped at 255) from column (i, j) to the nearest column that holds an occupied cell in those layers.  They
+  // follow lb2 in the same allocation: slab s, column (i, j) at lb2_base[slab_off + s * splane2 + (j + halo) * sx + i + halo].
+  unsigned slab_off, splane2;
+  int n_slabs;
   int halo;
   int gx, gy, gz, row_words;
   int has_grid;
@@ -87,56 +99,72 @@ struct PeerDev {
   unsigned step;
 };
 
-// Tables of the fast validity kernel (validity_fast.cu), in global memory; rebuilt with the grid-unit robot.
-struct FastPair {      // two consecutive slots (slots come in multiples of 4), laid out for packed fp32x2 arithmetic;
-  float x[2], y[2], z[2];   // sphere centres in their group frame, grid units, fp32
-  int thr[2];          // stage-1 threshold: lb2 > thr proves the sphere free even after the fp32 centre error; -2: never test
+// ---- tables of the fast validity kernel (validity_fast.cu) ----------------------------------------------------------
+// A rigid group is a two-level hierarchy: root bound -> cluster bounds -> leaf spheres.  Bounds and leaves are "nodes"
+// tested the same way (stage 1: one byte gather from a lower-bound field, `field > thr` proves the node free); a level
+// is entered only by the lanes whose node above is not provably free.
+// Node records come in pairs laid out for packed fp32x2 arithmetic — two consecutive float4:
+//   (x0 x1 y0 y1) (z0 z1 thr0 thr1)       3-D node: centre in its group frame, grid units; thr as int bits
+//   (x0 x1 y0 y1) (so0 so1 thr0 thr1)     2-D node (yaw-only base group): so = byte offset of the node's slab field
+//                                         from slab field 0 (uint bits) — its z never changes, so its layers are fixed
+constexpr int KF_MAX_SLOTS = 1024;
+constexpr int KF_MAX_BOUNDS = 128;
+struct KfTab {   // by value in the kernel parameters: the lockstep stage-1 loops read it with warp-uniform indices
+  float4 leaf[KF_MAX_SLOTS];           // pair records of the leaf slots
+  float4 bound[KF_MAX_BOUNDS];         // pair records of the cluster bounds (groups padded to a multiple of 8 bounds)
+  short bound_first[KF_MAX_BOUNDS];    // first leaf slot of the cluster
+  unsigned char bound_count[KF_MAX_BOUNDS];   // its slots (4 or 8)
+  float4 root[SQMP_MAX_GROUPS];        // x y (z | slab offset bits) thr bits: bound of the whole group
+  short grp_bound_end[SQMP_MAX_GROUPS + 1];   // bounds of group g are [end[g], end[g+1])
+  int base2d_group;                    // group tested against the slab fields (-1: none)
 };
-struct FastAux {       // per slot, rare path
+struct FastAux {       // per leaf slot, global memory: what the rare stages need (divergent indices)
+  float x, y, z;       // centre in the group frame, grid units, fp32 (same values as the pair record; z also for 2-D nodes)
   float r2_lo;         // (rg - err)^2 rounded down: ub2 <= r2_lo proves a hit even after the fp32 centre error
   int ncell;           // ceil(rg) + 1 (reach test of a sphere whose state lies outside the comfortable region)
+  int pad[3];
 };
 struct FastDev {
-  const FastPair *pairs;     // [n_slots / 2], staged in shared memory by every CTA
-  const FastAux *aux;        // [n_slots], staged too
+  const FastAux *aux;        // [n_slots]
   const double4 *sph64;      // [n_slots]: x y z r, grid units, fp64 (exact stage)
   int n_slots;
   int ok;                    // the description and the grid satisfy the fast kernel's preconditions
 };
 
-// Self collision (CC:541-552) as a three-level hierarchy over the enabled sphere pairs, all between different rigid
-// groups: block = (group A, group B) with one bounding sphere per side; per block the distinct A-spheres, each with
-// the bounding sphere of its partners; per A-sphere its partner list.  A level is entered only if the level above
-// cannot rule it out, so a state far from self contact costs ~one test per block instead of one per pair.
-struct SelfPair {   // 8 bytes
-  unsigned char a, b;     // sphere slots
-  unsigned char fa, fb;   // frame slots of their groups (RobotDev::grp_fidx)
-  float rsum2;            // (ra + rb)^2, grid units
+// ---- self collision (CC:541-552) -------------------------------------------------------------------------------------
+// Nested bounds over the enabled link pairs whose links hang on different rigid groups: group pair -> link pair ->
+// cluster of B vs link A -> cluster pair -> leaf of B vs cluster of A -> leaf pair.  A level is entered only if the level
+// above cannot rule it out, so a state far from self contact costs ~one test per link pair.  All centres are fp32 in
+// their group frame, grid units; bounds are padded against fp32 rounding (capi.cu: build_self_tables).
+struct SelfLeaf {   // 16 bytes
+  float x, y, z, r;
 };
-struct SelfA {      // 32 bytes: everything one A-test needs in one record (no dependent second load)
-  float cx, cy, cz;       // the A-sphere's centre in its group frame, grid units
-  float thr2;             // (ra + RB)^2
-  int p_begin, p_end;     // its partners in SelfDev::hpairs
-  int a;                  // sphere slot
-  int pad;
+struct SelfCluster {   // 32 bytes: bounding sphere + leaf range
+  float x, y, z, R;
+  int leaf_begin, leaf_end;
+  int pad[2];
 };
-struct SelfHPair {  // 16 bytes: a partner of an A-sphere, hierarchical order (block, a, b)
-  float bx, by, bz;       // the B-sphere's centre in its group frame, grid units
-  float rsum2;            // (ra + rb)^2
+struct SelfLink {   // 32 bytes: bounding sphere of a link + its clusters
+  float x, y, z, R;
+  int cl_begin, cl_end;
+  int link, pad;
 };
-struct SelfBlock {  // 48 bytes
-  int fa, fb;             // frame slots of the two groups
-  int a_begin, a_end;     // its A-spheres in SelfDev::as
-  float ca[3], cb[3];     // bounding-sphere centres in the group frames, grid units
-  float thr2;             // (RA + RB)^2
-  float pad;
+struct SelfLinkPair {   // 8 bytes: indices into SelfDev::links (a in group A, b in group B)
+  int a, b;
+};
+struct SelfGroupPair {   // 48 bytes
+  int fa, fb;             // frame slots of the two groups (RobotDev::grp_fidx)
+  int lp_begin, lp_end;   // its link pairs
+  float ax, ay, az, RA;   // bound of the A-side links that take part
+  float bx, by, bz, RB;   // ... B side
 };
 struct SelfDev {
-  const SelfHPair *hpairs;  // hierarchical order (block, a, b)
-  const SelfA *as;
-  const SelfBlock *blocks;
-  const SelfPair *flat;     // the description's own pair order (diagnostics: one result per pair)
-  int n_pairs, n_as, n_blocks;
+  const SelfGroupPair *gpairs;
+  const SelfLinkPair *lpairs;
+  const SelfLink *links;
+  const SelfCluster *clusters;
+  const SelfLeaf *leaves;
+  int n_gpairs, n_lpairs, n_links;
 };
 
 // packed fp32x2 (sm_100 FFMA2 / FADD2): two spheres per instruction; a plain float operand is broadcast (R.F32)
@@ -160,21 +188,24 @@ __device__ __forceinline__ float2 f32x2_add(float2 a, float b) {
 // ---- launch helpers (defined in the .cu files) ---------------------------------------------------------
 struct Ctx;
 
-cudaError_t launch_check_states(const RobotDev &rb, const GridDev &gd, const SelfDev &self,
+cudaError_t launch_check_states(const RobotDev &rb, const GridDev &gd, const SelfDev &self, const K1Slot *d_slots,
                                 const double *d_q, const double *d_q_end, int num_points, int64_t S,
-                                unsigned flags, uint32_t *d_mask, int fk_precision, cudaStream_t st, int *n_launch);
+                                unsigned flags, uint32_t *d_mask, cudaStream_t st, int *n_launch);
 cudaError_t launch_first_invalid(const uint32_t *d_mask, int64_t E, int P1, int32_t *d_first, cudaStream_t st);
-cudaError_t launch_get_collisions(const RobotDev &rb, const GridDev &gd, const SelfDev &self,
-                                  const double *d_q, uint8_t *d_sphere_hit, uint8_t *d_pair_hit, cudaStream_t st);
+cudaError_t launch_get_collisions(const RobotDev &rb, const GridDev &gd, const SelfDev &self, const K1Slot *d_slots,
+                                  const double *d_q, uint8_t *d_slot_hit, uint8_t *d_link_pair_hit, cudaStream_t st);
 cudaError_t launch_fk(const RobotDev &rb, const double *d_q, int64_t S, double *d_out, int fk_precision,
                       bool allow_specialized, cudaStream_t st);
 cudaError_t launch_sample(const RobotDev &rb, uint64_t seed, int64_t first, int64_t n, const double *lo, const double *hi,
                           int max_tries, double *d_q_out, int32_t *d_tries_out, bool allow_specialized, cudaStream_t st);
+cudaError_t launch_slab_build(const uint32_t *d_occ, int row_words, int gx, int gy, int gz, int halo, int window,
+                              int n_slabs, const int *h_k0, const int *h_k1, uint32_t *d_col, int8_t *d_tmp, uint8_t *d_slab,
+                              cudaStream_t st, int *n_launch);
 cudaError_t launch_ft_build(const uint32_t *d_occ, int row_words, int gx, int gy, int gz, int halo, int window,
                             int8_t *d_tmp_a, uint16_t *d_tmp_b, uint8_t *d_lb2, uint16_t *d_ft, cudaStream_t st,
                             int *n_launch);
 cudaError_t launch_check_states_fast(const RobotDev &rb, const GridDev &gd, const SelfDev &self, const FastDev &fd,
-                                     const double *d_q, const double *d_q_end, int num_points, int64_t S,
+                                     const KfTab &tab, const double *d_q, const double *d_q_end, int num_points, int64_t S,
                                      unsigned flags, uint32_t *d_mask, bool allow_specialized, bool overlap,
                                      cudaStream_t st, int *n_launch, const PeerDev *peers = nullptr);
 cudaError_t launch_gather_signal(const PeerDev &peer, cudaStream_t st);

@@ -69,13 +69,7 @@ class CollisionChecker:
     def getCollisions(self, jointPositions):
         lm, ph = self.ctx.get_collisions(jointPositions)
         names = self.link_table.names
-        cr = self.ctx.compiled
-        pairs = []
-        for p in np.nonzero(ph)[0]:
-            la, lb = sorted((int(cr.sph_link[cr.pair_a[p]]), int(cr.sph_link[cr.pair_b[p]])))   # CC:387-390: i < j
-            if (la, lb) not in pairs:
-                pairs.append((la, lb))
-        pairs = [(names[a], names[b]) for a, b in sorted(pairs)]
+        pairs = [(names[a], names[b]) for a, b in zip(*np.nonzero(ph[:len(names), :len(names)])) if a < b]   # CC:387-390: i < j
         return pairs, sorted(names[i] for i in np.nonzero(lm[:len(names)])[0])   # std::map order (CC:614)
 
 

@@ -276,6 +276,35 @@ def link_table_from_urdf(urdf_xml: str, srdf_xml: str) -> LinkTable:
                      pairs, octo, limits)
 
 
+def rigid_group_of_links(lt: LinkTable) -> np.ndarray:
+    """Index of the planning link each link is rigid to (-1: the root) — frozen joints do not move (CC:257)."""
+    grp = np.full(lt.n, -1, np.int32)
+    for i in range(lt.n):
+        p = int(lt.parent[i])
+        if p >= 0:
+            grp[i] = i if lt.joint_type[i] != JOINT_NONE else grp[p]
+    return grp
+
+
+def disable_rigid_pairs(lt: LinkTable):
+    """Deliberate deviation from CC:353-393, applied when the fixture is generated: shaped link pairs that are rigid to
+    each other (same planning link) are taken out of the self-collision matrix.  Their relative pose never changes, so
+    they cannot distinguish one configuration from another — but the reference's SRDF predates the box that replaced
+    the front-shell mesh (URDF:324-328) and leaves pairs enabled whose URDF shapes overlap permanently (the hokuyo
+    cylinder lies inside that box): with them every configuration would be "in self collision".  Returns the pairs
+    that were enabled before (recorded in the fixture's extras)."""
+    grp = rigid_group_of_links(lt)
+    m = lt.self_pair_matrix()
+    added = []
+    for a in range(lt.n):
+        for b in range(a + 1, lt.n):
+            if m[a, b] and grp[a] == grp[b]:
+                added.append((lt.names[a], lt.names[b]))
+    lt.disabled_pairs = list(lt.disabled_pairs) + added
+    lt.extras = dict(lt.extras, rigid_pairs_disabled=[list(p) for p in added])
+    return added
+
+
 def load_fixture(path: str = DEFAULT_FIXTURE):
     """Link table + authored sphere model + reference fixtures, as committed under data/."""
     with open(path) as f:
@@ -301,8 +330,7 @@ class CompiledRobot:
     sph_link: np.ndarray     # i32 [n]  link-table index (for the per-request link disable mask)
     sph_center: np.ndarray   # f64 [n,3] in the segment frame
     sph_radius: np.ndarray   # f64 [n]
-    pair_a: np.ndarray       # i32 [m]  sphere pairs checked for self collision (different segments)
-    pair_b: np.ndarray
+    link_pair_mask: np.ndarray  # u64 [64]  bit j of row i: links i and j are checked against each other (CC:353-393)
     self_const_collision: int  # 1 if an enabled pair inside one rigid group always collides
     link_names: list
     ee_link: str
@@ -368,24 +396,30 @@ def compile_robot(lt: LinkTable, spheres, ee_link: str = "hand_wrist_link") -> C
     sph_seg = np.array(sph_seg, np.int32)[order]; sph_link = np.array(sph_link, np.int32)[order]
     sph_c = np.array(sph_c, np.float64)[order]; sph_r = np.array(sph_r, np.float64)[order]
 
+    # selfCollisionPairs at link level (CC:353-393); the library collides the spheres of an enabled link pair when the
+    # two links hang on different segments.  A pair inside one rigid group never changes: if it overlaps, it always does.
     m = lt.self_pair_matrix()
-    pa, pb, const_hit = [], [], 0
-    for a in range(len(sph_r)):
-        for b in range(a + 1, len(sph_r)):
-            if not m[sph_link[a], sph_link[b]]:
-                continue
-            if sph_seg[a] == sph_seg[b]:
-                d = np.linalg.norm(sph_c[a] - sph_c[b])
-                if d - (sph_r[a] + sph_r[b]) <= 0.0:
+    rows = np.zeros(64, dtype=np.uint64)
+    for a in range(L):
+        for b in range(L):
+            if m[a, b]:
+                rows[a] |= np.uint64(1) << np.uint64(b)
+    const_hit = 0
+    by_link = {}
+    for i in range(len(sph_r)):
+        by_link.setdefault(int(sph_link[i]), []).append(i)
+    for a in by_link:
+        for b in by_link:
+            if a < b and m[a, b] and seg_of_link[a] == seg_of_link[b]:
+                ia, ib = np.array(by_link[a]), np.array(by_link[b])
+                d = np.linalg.norm(sph_c[ia][:, None, :] - sph_c[ib][None, :, :], axis=2) - (sph_r[ia][:, None] + sph_r[ib][None, :])
+                if d.min() <= 0.0:
                     const_hit = 1
-                continue
-            pa.append(a); pb.append(b)
     return CompiledRobot(
         n_seg, np.array(seg_type, np.int32), np.array(seg_qidx, np.int32),
         np.array([_f12(T) for T in seg_pre]), np.array(seg_axis),
         np.array([0.0, 0.0, ROOT_Z_OFFSET]), _f12(rel_fk[ee]),
-        len(sph_r), sph_seg, sph_link, sph_c, sph_r, np.array(pa, np.int32), np.array(pb, np.int32),
-        const_hit, list(lt.names), ee_link)
+        len(sph_r), sph_seg, sph_link, sph_c, sph_r, rows, const_hit, list(lt.names), ee_link)
 
 
 def link_mask(lt: LinkTable, disabled_names) -> int:

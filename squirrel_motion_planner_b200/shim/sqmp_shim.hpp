@@ -22,6 +22,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <iterator>
 #include <map>
@@ -71,13 +72,13 @@ struct Rrt_star_tree {
 namespace sqmp_shim {
 
 // ---------------------------------------------------------------------------------------------------------------
-// robot description file ("sqmpdesc 1", written by tools/export_robot_desc.py from the reference URDF + SRDF)
+// robot description file ("sqmpdesc 2", written by tools/export_robot_desc.py from the reference URDF + SRDF)
 // ---------------------------------------------------------------------------------------------------------------
 struct RobotDescription {
   sqmp_robot_desc desc;
   std::vector<std::string> link_names;
   std::vector<std::string> octomap_disabled;
-  std::vector<int32_t> sph_seg, sph_link, pair_a, pair_b;
+  std::vector<int32_t> sph_seg, sph_link;
   std::vector<double> sph_center, sph_radius;
 
   bool load(const std::string &path, std::string *err) {
@@ -85,9 +86,9 @@ struct RobotDescription {
     if (!in) return fail(err, "cannot open " + path);
     std::string tok;
     int version = 0;
-    if (!(in >> tok >> version) || tok != "sqmpdesc" || version != 1) return fail(err, "not a sqmpdesc 1 file");
+    if (!(in >> tok >> version) || tok != "sqmpdesc" || version != 2) return fail(err, "not a sqmpdesc 2 file");
     desc = sqmp_robot_desc();
-    int seg = 0;
+    int seg = 0, pair_rows = 0, pair_rows_read = 0;
     while (in >> tok) {
       if (tok == "n_seg") {
         in >> desc.n_seg;
@@ -127,13 +128,15 @@ struct RobotDescription {
         sph_link.push_back(lk);
         sph_center.insert(sph_center.end(), c, c + 3);
         sph_radius.push_back(r);
-      } else if (tok == "n_pairs") {
-        in >> desc.n_pairs;
-      } else if (tok == "pair") {
-        int32_t a = 0, b = 0;
-        in >> a >> b;
-        pair_a.push_back(a);
-        pair_b.push_back(b);
+      } else if (tok == "n_link_pair_rows") {
+        in >> pair_rows;
+      } else if (tok == "link_pairs") {   // selfCollisionPairs at link level (CC:353-393): row index, 64-bit mask in hex
+        int row = -1;
+        std::string hex;
+        in >> row >> hex;
+        if (row < 0 || row >= SQMP_MAX_LINKS) return fail(err, "link_pairs row out of range");
+        desc.link_pair_mask[row] = std::strtoull(hex.c_str(), nullptr, 16);
+        ++pair_rows_read;
       } else if (tok == "self_const_collision") {
         in >> desc.self_const_collision;
       } else {
@@ -141,14 +144,12 @@ struct RobotDescription {
       }
       if (!in) return fail(err, "truncated value for key " + tok);
     }
-    if (seg != desc.n_seg || int(sph_radius.size()) != desc.n_spheres || int(pair_a.size()) != desc.n_pairs)
+    if (seg != desc.n_seg || int(sph_radius.size()) != desc.n_spheres || pair_rows_read != pair_rows)
       return fail(err, "counts do not match their declarations");
     desc.sph_seg = sph_seg.data();
     desc.sph_link = sph_link.data();
     desc.sph_center = sph_center.data();
     desc.sph_radius = sph_radius.data();
-    desc.pair_a = pair_a.data();
-    desc.pair_b = pair_b.data();
     return true;
   }
 
@@ -363,18 +364,13 @@ class CollisionChecker {
     selfCollisions.clear();
     mapCollisions.clear();
     if (!initialized_ || jointPositions.size() < size_t(SQMP_DOF)) return;
-    uint8_t link_hit[64];
-    std::vector<uint8_t> pair_hit(size_t(robot_.desc.n_pairs) + 1, 0);
+    uint8_t link_hit[SQMP_MAX_LINKS];
+    std::vector<uint8_t> pair_hit(size_t(SQMP_MAX_LINKS) * SQMP_MAX_LINKS, 0);
     if (sqmp_get_collisions(ctx_, jointPositions.data(), link_hit, pair_hit.data()) != SQMP_OK) return;
-    std::map<std::pair<int, int>, bool> seen;
-    for (int p = 0; p < robot_.desc.n_pairs; ++p) {
-      if (!pair_hit[p]) continue;
-      int a = robot_.sph_link[robot_.pair_a[p]], b = robot_.sph_link[robot_.pair_b[p]];
-      if (a > b) std::swap(a, b);
-      seen[std::make_pair(a, b)] = true;
-    }
-    for (std::map<std::pair<int, int>, bool>::const_iterator it = seen.begin(); it != seen.end(); ++it)
-      selfCollisions.push_back(std::make_pair(robot_.link_names[it->first.first], robot_.link_names[it->first.second]));
+    const size_t nl = robot_.link_names.size() < size_t(SQMP_MAX_LINKS) ? robot_.link_names.size() : size_t(SQMP_MAX_LINKS);
+    for (size_t a = 0; a < nl; ++a)   // (i < j) in index order, like selfCollisionPairs (CC:387-390)
+      for (size_t b = a + 1; b < nl; ++b)
+        if (pair_hit[a * SQMP_MAX_LINKS + b]) selfCollisions.push_back(std::make_pair(robot_.link_names[a], robot_.link_names[b]));
     std::map<std::string, bool> names;
     for (size_t i = 0; i < robot_.link_names.size() && i < 64; ++i)
       if (link_hit[i]) names[robot_.link_names[i]] = true;

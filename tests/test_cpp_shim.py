@@ -27,12 +27,13 @@ def test_desc_file_matches_the_compiled_robot(fixture_data):
     lt, fx, spheres = fixture_data
     cr = rd.compile_robot(lt, spheres)
     toks = open(DESC).read().split("\n")
-    assert toks[0] == "sqmpdesc 1" and toks[1] == "n_seg %d" % cr.n_seg
+    assert toks[0] == "sqmpdesc 2" and toks[1] == "n_seg %d" % cr.n_seg
     sph = [l.split() for l in toks if l.startswith("sphere ")]
     assert len(sph) == cr.n_spheres
     assert np.array_equal(np.array([[float(v) for v in l[3:7]] for l in sph]),
                           np.column_stack([cr.sph_center, cr.sph_radius]))
-    assert sum(l.startswith("pair ") for l in toks) == len(cr.pair_a)
+    rows = {int(l.split()[1]): int(l.split()[2], 16) for l in toks if l.startswith("link_pairs ")}
+    assert rows == {i: int(v) for i, v in enumerate(cr.link_pair_mask) if int(v)}
 
 
 def test_shim_builds_and_fails_closed_without_gpu():

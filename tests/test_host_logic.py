@@ -13,7 +13,11 @@ from squirrel_motion_planner_b200 import api, robot_desc as rd, sharding, sphere
 
 def test_compile_robot_structure(fixture_data):
     lt, fx, spheres = fixture_data
-    assert lt.n == 39 and int(lt.shaped.sum()) == 27 and len(lt.disabled_pairs) == 245   # URDF / SRDF:26-271
+    rigid = [tuple(p) for p in lt.extras["rigid_pairs_disabled"]]
+    assert lt.n == 39 and int(lt.shaped.sum()) == 27 and len(lt.disabled_pairs) - len(rigid) == 245   # URDF / SRDF:26-271
+    grp = rd.rigid_group_of_links(lt)   # pairs of links that are rigid to each other are out of the matrix (robot_desc.disable_rigid_pairs)
+    assert rigid and all(grp[lt.index(a)] == grp[lt.index(b)] for a, b in rigid)
+    assert ("hokuyo_link", "shell_base_link_front") in rigid          # the URDF cylinder lies inside the URDF box
     cr = rd.compile_robot(lt, spheres)
     assert cr.n_seg == 8 and list(cr.seg_qidx) == list(range(8))
     assert list(cr.seg_type) == [2, 2, 1, 1, 1, 1, 1, 1]
@@ -22,7 +26,9 @@ def test_compile_robot_structure(fixture_data):
     assert cr.n_spheres == len(spheres) <= api.MAX_SPHERES
     assert np.all(np.diff(cr.sph_seg) >= 0)
     assert set(lt.names[i] for i in cr.sph_link) == set(n for n, s in zip(lt.names, lt.shaped) if s)
-    assert np.all(cr.sph_seg[cr.pair_a] != cr.sph_seg[cr.pair_b])
+    m = lt.self_pair_matrix()
+    for a in range(lt.n):
+        assert int(cr.link_pair_mask[a]) == sum(1 << b for b in range(lt.n) if m[a, b])
 
 
 def test_compiled_chain_equals_link_walk(fixture_data, orc):
@@ -60,6 +66,8 @@ def test_fixture_is_regenerable_from_reference(fixture_data):
     lt = fixture_data[0]
     cfg = "/root/reference/squirrel_8dof_planner/config/"
     lt2 = rd.link_table_from_urdf(open(cfg + "robotino_plan.urdf").read(), open(cfg + "robotino_plan.srdf").read())
+    assert len(lt2.disabled_pairs) == 245
+    rd.disable_rigid_pairs(lt2)
     assert lt2.names == lt.names
     assert np.array_equal(lt2.to_parent, lt.to_parent) and np.array_equal(lt2.parent, lt.parent)
     assert [tuple(p) for p in lt2.disabled_pairs] == [tuple(p) for p in lt.disabled_pairs]
@@ -177,26 +185,45 @@ def test_mask_allgather_world_size_2_gloo(tmp_path):
         assert p.returncode == 0, out
 
 
-def test_sphere_fit_covers_every_reference_primitive(fixture_data):
-    """a covering fit of every URDF primitive of the reference (collision_checker.hpp:282-294 shapes) at
-    the authored radius contains the whole shape, stays within one radius of it, and the grading of the authored model
-    reports what it is: complete for the single-sphere cylinders, partial where a link leans on its neighbours."""
+def test_sphere_model_is_conservative(fixture_data):
+    """SURVEY.md §8 f3 / collision_checker.hpp:263-351: the shipped sphere model COVERS every shape the reference collides
+    — the six URDF primitives (robotino_plan.urdf:323-330, 355-360, 385-390, 430-435, 546-551, 1369-1374) and the declared
+    stand-ins of the 21 mesh links — and reaches at most one 0.05 m voxel outside it.  Coverage is proven, not sampled:
+    every point of a lattice over the shape lies at least half a lattice diagonal inside some sphere."""
     from squirrel_motion_planner_b200 import sphere_fit as sf
     lt, fx, spheres = fixture_data
-    rows = {r["link"]: r for r in sf.report(lt, spheres)}
-    assert len(rows) == 27                                            # the 27 shaped links of CC:263-351
-    prim = [r for r in rows.values() if "fit" in r]
-    assert sorted(r["link"] for r in prim) == ["head_link", "hokuyo_link", "kinect_link", "neck_pan_link", "shell_base_link_front"]
-    for r in prim:
-        assert r["fit"]["covered"] == 1.0 and r["fit"]["protrusion"] <= max(r["radii"]) + 1e-12
-    assert rows["head_link"]["authored"]["covered"] > 0.99 and rows["hokuyo_link"]["authored"]["covered"] > 0.99
-    assert all(r["n_spheres"] >= 1 for r in rows.values())            # every shaped link owns a sphere (disable mask, SRDF pairs)
-    # the fit at other radii, a thin box and the parser
-    for shape, r in ((("box", (0.55, 0.55, 0.17)), 0.1), (("cylinder", (0.2, 0.08)), 0.05), (("box", (0.035, 0.18, 0.02)), 0.03)):
-        c = sf.fit_primitive(shape, r)
-        g = sf.grade(shape, c, np.full(len(c), r))
-        assert g["covered"] == 1.0 and g["protrusion"] <= r + 1e-12
-    assert sf.parse_shape("cylinder r=0.23 l=0.25") == ("cylinder", (0.23, 0.25)) and sf.parse_shape("mesh x.stl") is None
+    shapes = sphere_model.link_shapes(lt)
+    assert len(shapes) == 27                                          # the 27 shaped links of CC:263-351
+    urdf = sorted(n for n, (_, src) in shapes.items() if src.startswith("URDF"))
+    assert urdf == ["base_neck_link", "head_link", "hokuyo_link", "kinect_link", "neck_pan_link", "shell_base_link_front"]
+    assert shapes["shell_base_link_front"][0][:2] == ("box", (0.55, 0.55, 0.17)) and shapes["neck_pan_link"][0][:2] == ("cylinder", (0.2, 0.08))
+    rows = {r["link"]: r for r in sf.report(shapes, spheres, n=4000)}
+    for name, row in rows.items():
+        assert row["n_spheres"] >= 1                                  # every shaped link owns a sphere (disable mask, SRDF pairs)
+        mine = [(c, r) for n, c, r in spheres if n == name]
+        assert sf.verify_cover(row["shape"], [c for c, _ in mine], [r for _, r in mine]) == 0, name
+        assert row["grade"]["covered"] >= 0.999, (name, row["grade"])
+        assert row["grade"]["protrusion"] <= sphere_model.inflation_of(lt, name) + 1e-6 <= 0.05, (name, row["grade"])
+    # the floor slab the planner inserts (squirrel_8dof_planner.cpp:889-902, top at z = -0.02 after CC:87) stays clear
+    # of the lowest sphere: shapes start at z = +0.02 (CC:201), so their cover may reach at most 0.04 m below them
+    assert sphere_model.P_BOTTOM < 0.04
+
+
+def test_sphere_fit_tool(fixture_data):
+    """The fitter itself: covers at other inflations, a thin box, a capsule chain; the grader reports a miss."""
+    from squirrel_motion_planner_b200 import sphere_fit as sf
+    for shape, p in ((("box", (0.3, 0.2, 0.1)), 0.03), (("cylinder", (0.1, 0.08)), 0.02), (("box", (0.035, 0.18, 0.02)), 0.035)):
+        c, r = sf.cover_shape(shape, p)
+        g = sf.grade(shape, c, r, n=4000)
+        assert sf.verify_cover(shape, c, r) == 0 and g["covered"] == 1.0 and g["protrusion"] <= p + 1e-9
+        small = r > r.min() + 1e-12
+        assert not small.any() or sf.verify_cover(shape, c[small], r[small]) > 0   # without its smallest spheres (corners, rim) the cover has holes
+    cap = ("capsule", ((0, 0, 0), (0, 0, 0.25), 0.05))
+    c, r = sf.cover_shape(cap, 0.01)
+    assert sf.verify_cover(cap, c, r) == 0 and abs(sf.protrusion(cap, c, r) - 0.01) < 1e-12
+    assert sf.verify_cover(cap, c[::2], r[::2]) > 0                               # every other sphere: gaps on the surface
+    assert sf.grade(cap, c, r, n=4000)["covered"] == 1.0
+    assert sf.parse_shape("cylinder r=0.23 l=0.25")[:2] == ("cylinder", (0.23, 0.25)) and sf.parse_shape("mesh x.stl") is None
     assert np.allclose(sf.segment_distance([[0, 1, 0.5], [0, 0, 2]], [0, 0, 0], [0, 0, 1]), [1.0, 1.0])
 
 

@@ -21,11 +21,23 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default="/root/reference")
     ap.add_argument("--out", default=robot_desc.DEFAULT_FIXTURE)
+    ap.add_argument("--refit", action="store_true",
+                    help="re-run the covering sphere fit (sphere_model.build_model, ~1 min) and refreeze data/robotino_spheres.json")
     a = ap.parse_args()
     cfg = os.path.join(a.reference, "squirrel_8dof_planner", "config")
     urdf = open(os.path.join(cfg, "robotino_plan.urdf")).read()
     srdf = open(os.path.join(cfg, "robotino_plan.srdf")).read()
     lt = robot_desc.link_table_from_urdf(urdf, srdf)
+    rigid = robot_desc.disable_rigid_pairs(lt)
+    print("rigid pairs taken out of the self-collision matrix:", len(rigid))
+    if a.refit or not os.path.exists(sphere_model.FROZEN):
+        sph = sphere_model.build_model(lt, progress=print)
+        with open(sphere_model.FROZEN, "w") as f:
+            json.dump({"generator": "tools/gen_robot_fixture.py --refit (sphere_model.build_model)",
+                       "inflation_m": {"primitive": sphere_model.P_PRIMITIVE, "bottom": sphere_model.P_BOTTOM,
+                                       "arm": sphere_model.P_ARM, "hand": sphere_model.P_HAND},
+                       "spheres": [[n, list(c), r] for n, c, r in sph]}, f, indent=0)
+        print("froze", sphere_model.FROZEN, len(sph), "spheres")
 
     # published poses (fixtures for sanity tests): folding trajectory and folded arm
     fold = open(os.path.join(cfg, "folding_poses_tuw-robotino2.yaml")).read()

@@ -38,10 +38,15 @@ def folded_arm():
     return np.array([-0.7, 1.9, 0.0, 1.7, 0.0])       # pose_folded_arm, squirrel_8dof_planner/config/parameters.yaml:37
 
 
+def half_folded_arm():
+    return np.array([-0.17, 1.96, 0.19, 0.65, 0.53])   # folding key-frame 13 (folding_poses_tuw-robotino2.yaml:13)
+
+
 def config1_queries(n=1):
-    """start (-4,-4,0, folded arm), goal (4,4,pi/2, arm half unfolded).  (The survey's goal arm
-    pose, the first folding key-frame 0.29 2.26 0.19 -1.17 0.53, touches the base in the authored sphere model, so
-    init_planner would reject it like BS:351-358 rejects an invalid goal.)"""
-    start = np.concatenate([[-4.0, -4.0, 0.0], folded_arm()])
+    """start (-4,-4,0, arm half folded), goal (4,4,pi/2, arm half unfolded).  (The survey's own
+    arm poses — pose_folded_arm and the first folding key-frame — rest the hand ON the shell: with a sphere model that
+    covers the URDF's front shell box they are in self collision, and init_planner rejects them like BS:351-358
+    rejects any invalid end point; tests/test_oracle_golden.py shows the URDF box itself contains the fingers there.)"""
+    start = np.concatenate([[-4.0, -4.0, 0.0], half_folded_arm()])
     goal = np.concatenate([[4.0, 4.0, np.pi / 2], [-0.2, 1.2, 0.4, 0.9, 0.3]])
     return np.tile(start, (n, 1)), np.tile(goal, (n, 1))
