@@ -74,6 +74,7 @@ struct Ctx {
   int slab_root = -1;
   int ft_window = 0, slab_window = 0;           // search windows the current fields were built with (cells)
   FastAux *d_fast_aux = nullptr;
+  float4 *d_fast_leaf = nullptr;
   double4 *d_fast_sph64 = nullptr;
   int fast_chain_ok = 0;        // description: translation-only base, then rotations only, spheres on the rotating part
   double reach_m = 0.0;         // max distance of a sphere centre from the base reference point (metres)
@@ -374,8 +375,7 @@ static void apply_link_mask(Ctx *c) {
   for (size_t k = 0; k < c->clusters.size(); ++k) {
     const HostCluster &cl = c->clusters[k];
     const bool off = (c->link_disabled >> cl.link) & 1ull;
-    for (int sl = cl.slot0; sl < cl.slot0 + cl.nslots; ++sl) rec_set_thr(t.leaf, sl, off ? -2 : c->kf_leaf_thr[size_t(sl)]);
-    rec_set_thr(t.bound, c->kf_bound_idx[k], off ? -2 : c->kf_bound_thr[k]);
+    rec_set_thr(t.bound, c->kf_bound_idx[k], off ? -2 : c->kf_bound_thr[k]);   // a cluster belongs to one link: its spheres are only reached through it
   }
 }
 
@@ -483,7 +483,8 @@ static int refresh_grid_robot(Ctx *c) {
     c->kf_bound_idx.assign(c->clusters.size(), 0);
     std::vector<FastAux> fa(size_t(n_slots) + 1);
     std::vector<double4> s64(size_t(n_slots) + 1);
-    for (int i = 0; i < KF_MAX_SLOTS; ++i) rec_set_thr(t.leaf, i, -2);
+    std::vector<float4> leaf(size_t(KF_MAX_SLOTS), make_float4(0.f, 0.f, 0.f, 0.f));
+    for (int i = 0; i < KF_MAX_SLOTS; ++i) rec_set_thr(leaf.data(), i, -2);
     for (int i = 0; i < KF_MAX_BOUNDS; ++i) rec_set_thr(t.bound, i, -2);
     int bidx = 0;
     for (int gi = 0; gi < SQMP_MAX_GROUPS; ++gi) {
@@ -508,8 +509,9 @@ static int refresh_grid_robot(Ctx *c) {
           if (pad_slot) i = cl.members.back();
           const HostSphere &sp = c->sph[size_t(i)];
           const double rg = sp.r * inv;
-          rec_set_xyz(t.leaf, sl, float(sp.c[0] * inv), float(sp.c[1] * inv), twod ? slabf : float(sp.c[2] * inv));
+          rec_set_xyz(leaf.data(), sl, float(sp.c[0] * inv), float(sp.c[1] * inv), twod ? slabf : float(sp.c[2] * inv));
           c->kf_leaf_thr[size_t(sl)] = pad_slot ? -2 : thr_of(rg, twod ? W2 : W3);
+          rec_set_thr(leaf.data(), sl, c->kf_leaf_thr[size_t(sl)]);
           FastAux &a = fa[size_t(sl)];
           a.x = float(sp.c[0] * inv); a.y = float(sp.c[1] * inv); a.z = float(sp.c[2] * inv);
           const double lo = rg > err ? (rg - err) * (rg - err) * (1.0 - 1e-6) : -1.0;
@@ -541,10 +543,13 @@ static int refresh_grid_robot(Ctx *c) {
     t.grp_bound_end[SQMP_MAX_GROUPS] = short(bidx);
     cudaError_t e = cudaSuccess;
     if (!c->d_fast_aux) e = cudaMalloc(&c->d_fast_aux, sizeof(FastAux) * (KF_MAX_SLOTS + 1));
+    if (e == cudaSuccess && !c->d_fast_leaf) e = cudaMalloc(&c->d_fast_leaf, sizeof(float4) * KF_MAX_SLOTS);
+    if (e == cudaSuccess) e = cudaMemcpy(c->d_fast_leaf, leaf.data(), sizeof(float4) * KF_MAX_SLOTS, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && !c->d_fast_sph64) e = cudaMalloc(&c->d_fast_sph64, sizeof(double4) * (KF_MAX_SLOTS + 1));
     if (e == cudaSuccess) e = cudaMemcpy(c->d_fast_aux, fa.data(), sizeof(FastAux) * size_t(n_slots), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(c->d_fast_sph64, s64.data(), sizeof(double4) * size_t(n_slots), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return fail(c, SQMP_ERR_CUDA, "fast validity tables", e);
+    c->fast.leafrec = c->d_fast_leaf;
     c->fast.aux = c->d_fast_aux;
     c->fast.sph64 = c->d_fast_sph64;
     c->fast.n_slots = n_slots;
@@ -855,6 +860,7 @@ void sqmp_destroy(sqmp_ctx *ctx) {
     if (ctx->d_ft) cudaFree(ctx->d_ft);
   }
   if (ctx->d_fast_aux) cudaFree(ctx->d_fast_aux);
+  if (ctx->d_fast_leaf) cudaFree(ctx->d_fast_leaf);
   if (ctx->d_fast_sph64) cudaFree(ctx->d_fast_sph64);
   for (auto &t : ctx->trees) {
     if (t.q[0]) cudaFree(t.q[0]);

@@ -109,8 +109,7 @@ struct PeerDev {
 //                                         from slab field 0 (uint bits) — its z never changes, so its layers are fixed
 constexpr int KF_MAX_SLOTS = 1024;
 constexpr int KF_MAX_BOUNDS = 128;
-struct KfTab {   // by value in the kernel parameters: the lockstep stage-1 loops read it with warp-uniform indices
-  float4 leaf[KF_MAX_SLOTS];           // pair records of the leaf slots
+struct KfTab {   // by value in the kernel parameters: the lockstep bound loops read it with warp-uniform indices
   float4 bound[KF_MAX_BOUNDS];         // pair records of the cluster bounds (groups padded to a multiple of 8 bounds)
   short bound_first[KF_MAX_BOUNDS];    // first leaf slot of the cluster
   unsigned char bound_count[KF_MAX_BOUNDS];   // its slots (4 or 8)
@@ -125,6 +124,7 @@ struct FastAux {       // per leaf slot, global memory: what the rare stages nee
   int pad[3];
 };
 struct FastDev {
+  const float4 *leafrec;     // [n_slots]: pair records of the leaf slots (read per queued (cluster, state) item: divergent indices)
   const FastAux *aux;        // [n_slots]
   const double4 *sph64;      // [n_slots]: x y z r, grid units, fp64 (exact stage)
   int n_slots;

@@ -50,6 +50,19 @@ constexpr int KF_MIN_BLOCKS = KF_MIN_BLOCKS_DEF;
 constexpr float KF_MAGIC = 12582912.0f;          // 1.5 * 2^23: (x + MAGIC) has round-to-nearest-even(x) in its low mantissa bits
 constexpr unsigned KF_MAGIC_BITS = 0x4B400000u;  // bit pattern of MAGIC
 
+#ifdef SQMP_KF_STATS   // development builds only (tools/k1f_stats.py): where the work of the hierarchy goes
+__device__ unsigned long long kf_stats[16];
+#define KF_COUNT(slot, n) atomicAdd(&kf_stats[slot], (unsigned long long)(n))
+#else
+#define KF_COUNT(slot, n)
+#endif
+
+constexpr int KF_PQ_CAP = 32 + 8 * 32;   // a batch adds at most 8 x 32 entries to fewer than 32 left over
+__host__ __device__ constexpr size_t kf_smem_base() {   // everything but the SELF frames
+  return sizeof(WarpQueue) * (KF_THREADS / 32) + sizeof(double) * (SQMP_DOF + 12) * KF_THREADS + sizeof(float) * 12 * KF_THREADS +
+         2 * sizeof(unsigned short) * KF_PQ_CAP * (KF_THREADS / 32);
+}
+
 __device__ __forceinline__ float kf_gap(int o, float f) {   // gap between coordinate f in [0,1] of the own cell and the unit cube at offset o
   return o > 0 ? float(o) - f : (o < 0 ? f - float(o) - 1.0f : 0.0f);
 }
@@ -96,11 +109,20 @@ k1_fast(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd,
         const double *__restrict__ q_in, const double *__restrict__ q_end, int num_points, int64_t S,
         uint32_t *__restrict__ mask_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  WarpQueue *wq = reinterpret_cast<WarpQueue *>(smem_raw) + (threadIdx.x >> 5);
-  double *q_mine = reinterpret_cast<double *>(smem_raw + sizeof(WarpQueue) * (KF_THREADS / 32)) + threadIdx.x;  // [8][blockDim]
+  constexpr int NW = KF_THREADS / 32;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  WarpQueue *wq = reinterpret_cast<WarpQueue *>(smem_raw) + wid;
+  double *q_mine = reinterpret_cast<double *>(smem_raw + sizeof(WarpQueue) * NW) + threadIdx.x;  // [8][blockDim]
+  // frames of the group the warp is working on, one column per lane: fp64 [12][32] (exact centres), fp32 [12][32] (stage 2)
+  double *fr64 = reinterpret_cast<double *>(smem_raw + sizeof(WarpQueue) * NW + sizeof(double) * SQMP_DOF * KF_THREADS) + wid * (12 * 32);
+  float *fr32 = reinterpret_cast<float *>(smem_raw + sizeof(WarpQueue) * NW + sizeof(double) * (SQMP_DOF + 12) * KF_THREADS) + wid * (12 * 32);
+  // spheres stage 1 could not prove free, waiting for stage 2: (slot << 5 | owner lane), decided 32 at a time
+  unsigned short *pq = reinterpret_cast<unsigned short *>(smem_raw + sizeof(WarpQueue) * NW + sizeof(double) * (SQMP_DOF + 12) * KF_THREADS +
+                                                          sizeof(float) * 12 * KF_THREADS) + wid * KF_PQ_CAP;
+  // clusters some state has to look into, waiting for stage 1 of their spheres: (first slot / 4) << 6 | eight slots << 5 | owner lane
+  unsigned short *cq = pq + NW * KF_PQ_CAP;
   // SELF: the group frames [n_frames*12][blockDim]
-  float *f_mine = reinterpret_cast<float *>(smem_raw + sizeof(WarpQueue) * (KF_THREADS / 32) + sizeof(double) * SQMP_DOF * KF_THREADS) + threadIdx.x;
-  const int lane = threadIdx.x & 31;
+  float *f_mine = reinterpret_cast<float *>(smem_raw + kf_smem_base()) + threadIdx.x;
   const int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool active = s < S;
   const int64_t sl = active ? s : S - 1;  // idle lanes of the last warp shadow the last state (lockstep loops)
@@ -205,109 +227,217 @@ k1_fast(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd,
 #endif
       open = !hit && int(lbp[off]) <= __float_as_int(rt.w);
     }
+    KF_COUNT(0, lane == 0);                                  // [0] group root tests (warp level)
+    KF_COUNT(1, open);                                       // [1] open roots (lanes)
     if (!__any_sync(FULL, open)) continue;
+    KF_COUNT(2, lane == 0);                                  // [2] groups entered (warp level)
 
-    for (int b0 = bb; b0 < be; b0 += 8) {
-      // ---- cluster bounds, eight at a time (a group with a single cluster: its root is that cluster's bound) ----
-      unsigned ob;
-      if (be - bb == 8 && tab.bound_count[bb + 1] == 0) {
-        ob = open ? 1u : 0u;
-      } else {
-        int lbv[8], thr[8];
-        kf_stage1(tab.bound + 2 * (b0 >> 1) * 1, true, F, sx, spl, base_off, lbp, open, lbv, thr);
-        ob = 0;
+    // park this group's frames where any lane can read them (stages 2-3 are decided by whichever lane is free)
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          if (lbv[u] <= thr[u]) ob |= 1u << u;
-        if (!open) ob = 0;
+    for (int k = 0; k < 9; ++k) {
+      fr64[k * 32 + lane] = f.r[k];
+      fr32[k * 32 + lane] = R[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      fr64[(9 + k) * 32 + lane] = f.p[k];
+      fr32[(9 + k) * 32 + lane] = pm[k];
+    }
+    __syncwarp();
+    const unsigned comfy_mask = __ballot_sync(FULL, comfy);
+    int pcount = 0;   // entries in pq (warp-uniform)
+
+    // Stages 2-3 for 32 queued spheres at once, one per lane whatever state it belongs to: upper bound from the feature
+    // field (certain hit), else the fp64 centre goes to the exact-scan queue.  Returns the owners proven in collision.
+    auto resolve = [&](int base, int n) -> unsigned {
+      const unsigned known = __ballot_sync(FULL, hit);
+      bool amb = false, h2 = false;
+      int i = 0, owner = lane;
+      if (lane < n) {
+        const unsigned e = pq[base + lane];
+        owner = int(e & 31u);
+        i = int(e >> 5);
       }
-      unsigned todo = __reduce_or_sync(FULL, ob);
-      while (todo) {   // warp-uniform: every cluster some lane has to look into
-        const int cb = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int i0 = tab.bound_first[b0 + cb];
-        const bool two = tab.bound_count[b0 + cb] > 4;
-        const bool mine = ((ob >> cb) & 1u) && !hit;
-        int lbv[8], thr[8];
-        kf_stage1(tab.leaf + 2 * (i0 >> 1), two, F, sx, spl, base_off, lbp, mine, lbv, thr);
-        unsigned pend = 0;
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-          if (lbv[u] <= thr[u]) pend |= 1u << u;
-        if (!mine) pend = 0;
-        while (__any_sync(FULL, pend != 0)) {
-          bool amb = false;
-          int i = i0;
-          double cx64 = 0.0, cy64 = 0.0, cz64 = 0.0, rg64 = 0.0;
-          auto centre64 = [&]() {   // the fp64 centre exactly as K1 forms it
-            const double2 *lp = reinterpret_cast<const double2 *>(fd.sph64 + i);
-            const double2 l01 = __ldg(lp), l23 = __ldg(lp + 1);
-            cx64 = fma(f.r[0], l01.x, fma(f.r[1], l01.y, fma(f.r[2], l23.x, f.p[0] - 0.5))) + 0.5;
-            cy64 = fma(f.r[3], l01.x, fma(f.r[4], l01.y, fma(f.r[5], l23.x, f.p[1] - 0.5))) + 0.5;
-            cz64 = fma(f.r[6], l01.x, fma(f.r[7], l01.y, fma(f.r[8], l23.x, f.p[2] - 0.5))) + 0.5;
-            rg64 = l23.y;
-          };
-          if (pend != 0) {
-            const int u = __ffs(pend) - 1;
-            pend &= pend - 1;
-            i = i0 + u;
-            if (comfy) {   // stage 2: the true 3-D centre (fp32) against the feature field
-              const float4 a = __ldg(reinterpret_cast<const float4 *>(fd.aux + i));   // x y z r2_lo
-              const float cx = fmaf(R[0], a.x, fmaf(R[1], a.y, fmaf(R[2], a.z, pm[0])));
-              const float cy = fmaf(R[3], a.x, fmaf(R[4], a.y, fmaf(R[5], a.z, pm[1])));
-              const float cz = fmaf(R[6], a.x, fmaf(R[7], a.y, fmaf(R[8], a.z, pm[2])));
-              const float tx = cx + KF_MAGIC, ty = cy + KF_MAGIC, tz = cz + KF_MAGIC;
-              const unsigned off = __float_as_uint(tz) * splane + __float_as_uint(ty) * sx + __float_as_uint(tx) + base_off3;
+      const unsigned ob3 = __shfl_sync(FULL, base_off3, owner);   // the owner's field offset (its base cell)
+      if (lane < n) {
+        if (!((known >> owner) & 1u)) {
+          if ((comfy_mask >> owner) & 1u) {   // stage 2: the true 3-D centre (fp32) against the feature field
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(fd.aux + i));   // x y z r2_lo
+            const float *fo = fr32 + owner;
+            const float cx = fmaf(fo[0 * 32], a.x, fmaf(fo[1 * 32], a.y, fmaf(fo[2 * 32], a.z, fo[9 * 32])));
+            const float cy = fmaf(fo[3 * 32], a.x, fmaf(fo[4 * 32], a.y, fmaf(fo[5 * 32], a.z, fo[10 * 32])));
+            const float cz = fmaf(fo[6 * 32], a.x, fmaf(fo[7 * 32], a.y, fmaf(fo[8 * 32], a.z, fo[11 * 32])));
+            const float tx = cx + KF_MAGIC, ty = cy + KF_MAGIC, tz = cz + KF_MAGIC;
+            const unsigned off = __float_as_uint(tz) * splane + __float_as_uint(ty) * sx + __float_as_uint(tx) + ob3;
 #ifdef SQMP_BOUNDS_CHECK
-              if (off >= gd.zero_off) __trap();
+            if (off >= gd.zero_off) __trap();
 #endif
-              const unsigned v = gd.ft_base[off];
-              // position inside the own cell, in [0,1]: (c - n) is exact, c + 0.5 is the centre estimate
-              const float fx = (cx - (tx - KF_MAGIC)) + 0.5f, fy = (cy - (ty - KF_MAGIC)) + 0.5f, fz = (cz - (tz - KF_MAGIC)) + 0.5f;
-              const float gx_ = kf_gap(int(v & 31u) - 15, fx), gy_ = kf_gap(int((v >> 5) & 31u) - 15, fy),
-                          gz_ = kf_gap(int((v >> 10) & 31u) - 15, fz);
-              const float ub2 = fmaf(gx_, gx_, fmaf(gy_, gy_, gz_ * gz_));
-              if (ub2 <= a.w) { hit = true; pend = 0; }   // dist(fp64 centre, O*) <= rg: certain hit
-              else amb = true;
-            } else {   // base outside the grid: can the sphere still reach it?
-              centre64();
-              const int pad = __ldg(&fd.aux[i].ncell);
-              const int jx = rn_int(cx64 - 0.5), jy = rn_int(cy64 - 0.5), jz = rn_int(cz64 - 0.5);
-              amb = unsigned(jx + pad) < unsigned(gd.gx + 2 * pad) && unsigned(jy + pad) < unsigned(gd.gy + 2 * pad) &&
-                    unsigned(jz + pad) < unsigned(gd.gz + 2 * pad);
-            }
-          }
-          const unsigned m = __ballot_sync(FULL, amb);
-          if (m) {
-            if (amb) {
-              if (comfy) centre64();
-              const int pos = qcount + __popc(m & ((1u << lane) - 1u));
-              wq->x[pos] = cx64;
-              wq->y[pos] = cy64;
-              wq->z[pos] = cz64;
-              wq->r[pos] = rg64;
-              wq->info[pos] = (i << 8) | lane;
-            }
-            qcount += __popc(m);
-            if (qcount >= 32) {
-              __syncwarp();
-              const unsigned hm = drain_queue(gd, wq, qcount - 32, 32, __ballot_sync(FULL, hit));
-              __syncwarp();
-              qcount -= 32;
-              if ((hm >> lane) & 1u) { hit = true; pend = 0; }
-            }
+            const unsigned v = gd.ft_base[off];
+            // position inside the own cell, in [0,1]: (c - n) is exact, c + 0.5 is the centre estimate
+            const float fx = (cx - (tx - KF_MAGIC)) + 0.5f, fy = (cy - (ty - KF_MAGIC)) + 0.5f, fz = (cz - (tz - KF_MAGIC)) + 0.5f;
+            const float gx_ = kf_gap(int(v & 31u) - 15, fx), gy_ = kf_gap(int((v >> 5) & 31u) - 15, fy),
+                        gz_ = kf_gap(int((v >> 10) & 31u) - 15, fz);
+            const float ub2 = fmaf(gx_, gx_, fmaf(gy_, gy_, gz_ * gz_));
+            KF_COUNT(8, 1);                                  // [8] stage-2 tests (lanes)
+            if (ub2 <= a.w) h2 = true;   // dist(fp64 centre, O*) <= rg: certain hit
+            else amb = true;
+          } else {
+            amb = true;   // base outside the grid: reach test below, on the fp64 centre
           }
         }
       }
+      double cx64 = 0.0, cy64 = 0.0, cz64 = 0.0, rg64 = 0.0;
+      if (amb) {   // the fp64 centre exactly as K1 forms it, from the owner's fp64 frame
+        const double2 *lp = reinterpret_cast<const double2 *>(fd.sph64 + i);
+        const double2 l01 = __ldg(lp), l23 = __ldg(lp + 1);
+        const double *fo = fr64 + owner;
+        cx64 = fma(fo[0 * 32], l01.x, fma(fo[1 * 32], l01.y, fma(fo[2 * 32], l23.x, fo[9 * 32] - 0.5))) + 0.5;
+        cy64 = fma(fo[3 * 32], l01.x, fma(fo[4 * 32], l01.y, fma(fo[5 * 32], l23.x, fo[10 * 32] - 0.5))) + 0.5;
+        cz64 = fma(fo[6 * 32], l01.x, fma(fo[7 * 32], l01.y, fma(fo[8 * 32], l23.x, fo[11 * 32] - 0.5))) + 0.5;
+        rg64 = l23.y;
+        if (!((comfy_mask >> owner) & 1u)) {   // can the sphere still reach the grid?
+          const int pad = __ldg(&fd.aux[i].ncell);
+          const int jx = rn_int(cx64 - 0.5), jy = rn_int(cy64 - 0.5), jz = rn_int(cz64 - 0.5);
+          amb = unsigned(jx + pad) < unsigned(gd.gx + 2 * pad) && unsigned(jy + pad) < unsigned(gd.gy + 2 * pad) &&
+                unsigned(jz + pad) < unsigned(gd.gz + 2 * pad);
+        }
+      }
+      unsigned hm = __reduce_or_sync(FULL, h2 ? (1u << owner) : 0u);
+      const unsigned m = __ballot_sync(FULL, amb);
+      if (m) {
+        if (amb) {
+          const int pos = qcount + __popc(m & ((1u << lane) - 1u));
+          wq->x[pos] = cx64;
+          wq->y[pos] = cy64;
+          wq->z[pos] = cz64;
+          wq->r[pos] = rg64;
+          wq->info[pos] = (i << 8) | owner;
+        }
+        qcount += __popc(m);
+        KF_COUNT(9, lane == 0 ? __popc(m) : 0);              // [9] exact-scan items
+        if (qcount >= 32) {
+          __syncwarp();
+          KF_COUNT(10, lane == 0);                           // [10] queue drains
+          hm |= drain_queue(gd, wq, qcount - 32, 32, known | hm);
+          __syncwarp();
+          qcount -= 32;
+        }
+      }
+      return hm;
+    };
+
+    int ccount = 0;   // entries in cq (warp-uniform)
+    // Stage 1 of the spheres of 32 queued clusters at once, one (cluster, state) per lane whatever state it belongs to:
+    // the owner's frame comes from shared memory, the sphere records from global memory.  Undecided spheres go to pq.
+    auto leaves_round = [&](int base, int n) {
+      const unsigned known = __ballot_sync(FULL, hit);
+      int owner = lane, i0 = 0;
+      bool two = false, valid = false;
+      if (lane < n) {
+        const unsigned e = cq[base + lane];
+        owner = int(e & 31u);
+        two = (e >> 5) & 1u;
+        i0 = int(e >> 6) << 2;
+        valid = !((known >> owner) & 1u);
+      }
+      const unsigned boff = __shfl_sync(FULL, base_off, owner);   // the owner's field offset (its base cell; zero byte when not comfortable)
+      unsigned pend = 0;
+      if (valid) {
+        const bool oc = (comfy_mask >> owner) & 1u;
+        const float *fo = fr32 + owner;
+        KfFrame G;   // the owner's stage-1 frame (see F above)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) G.r[k] = oc ? fo[k * 32] : 0.0f;
+        G.r[6] = (oc && !twod) ? fo[6 * 32] : 0.0f;
+        G.r[7] = (oc && !twod) ? fo[7 * 32] : 0.0f;
+        G.r[8] = oc ? (twod ? 1.0f : fo[8 * 32]) : 0.0f;
+        G.p[0] = oc ? fo[9 * 32] : 0.0f;
+        G.p[1] = oc ? fo[10 * 32] : 0.0f;
+        G.p[2] = (oc && !twod) ? fo[11 * 32] : 0.0f;
+        int lbv[8], thr[8];
+        kf_stage1(fd.leafrec + 2 * (i0 >> 1), two, G, sx, spl, boff, lbp, true, lbv, thr);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (lbv[u] <= thr[u]) pend |= 1u << u;
+      }
+      if (!__any_sync(FULL, pend != 0)) return;
+      const int cnt = __popc(pend);
+      KF_COUNT(6, cnt);                                      // [6] spheres stage 1 cannot prove free (lanes)
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+      }
+      int pos = pcount + incl - cnt;
+      while (pend) {
+        const int u = __ffs(pend) - 1;
+        pend &= pend - 1;
+        pq[pos++] = (unsigned short)(((i0 + u) << 5) | owner);
+      }
+      pcount += __shfl_sync(FULL, incl, 31);
+      __syncwarp();
+    };
+
+    // a group with a single cluster: its root is that cluster's bound
+    const bool single = be - bb == 8 && tab.bound_count[bb + 1] == 0;
+    for (int b0 = bb; b0 < be; b0 += 8) {
+      // ---- cluster bounds, eight at a time ----
+      unsigned ob;
+      {
+        int lbv[8], thr[8];
+        kf_stage1(tab.bound + 2 * (b0 >> 1), true, F, sx, spl, base_off, lbp, open && !hit && !single, lbv, thr);
+        ob = 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if ((single ? 0 : lbv[u]) <= thr[u]) ob |= 1u << u;   // (thr = -2: pad bound or disabled link)
+        if (!open || hit) ob = 0;
+      }
+      unsigned todo = __reduce_or_sync(FULL, ob);
+      KF_COUNT(3, lane == 0);                                // [3] bound batches (warp level)
+      KF_COUNT(4, __popc(ob));                               // [4] open clusters (lanes)
+      KF_COUNT(5, lane == 0 ? __popc(todo) : 0);             // [5] clusters entered (warp level)
+      while (todo) {   // warp-uniform: queue (cluster, state) for every state that has to look into the cluster
+        const int cb = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const unsigned entry = (unsigned(tab.bound_first[b0 + cb]) >> 2) << 6 | (tab.bound_count[b0 + cb] > 4 ? 32u : 0u);
+        const bool mine = (ob >> cb) & 1u;
+        const unsigned m = __ballot_sync(FULL, mine);
+        if (mine) cq[ccount + __popc(m & ((1u << lane) - 1u))] = (unsigned short)(entry | unsigned(lane));
+        ccount += __popc(m);
+      }
+      __syncwarp();
+      // decide full rounds of 32; after the group's last bound batch whatever is left (the frames change with the next group)
+      const bool last = b0 + 8 >= be;
+      while (ccount >= 32 || (last && (ccount | pcount) != 0)) {
+        const int n = min(ccount, 32);
+        if (n > 0) {
+          KF_COUNT(13, lane == 0);                           // [13] cluster rounds (warp level)
+          leaves_round(ccount - n, n);
+          ccount -= n;
+        }
+        const bool flush = last && ccount == 0;
+        while (pcount >= 32 || (flush && pcount > 0)) {
+          KF_COUNT(7, lane == 0);                            // [7] stage-2 rounds (warp level)
+          const int np = min(pcount, 32);
+          const unsigned hm = resolve(pcount - np, np);
+          pcount -= np;
+          if ((hm >> lane) & 1u) hit = true;
+        }
+      }
     }
+    __syncwarp();
     // whole warp decided (CC:114-115: map before self, first hit wins) -> stop walking the chain
     if (!SELF && qcount == 0 && __all_sync(FULL, hit)) break;
   }
   if (qcount > 0) {
     __syncwarp();
+    KF_COUNT(10, lane == 0);
     const unsigned hm = drain_queue(gd, wq, 0, qcount, __ballot_sync(FULL, hit));
     hit |= (hm >> lane) & 1u;
   }
+  KF_COUNT(11, lane == 0);                                   // [11] warps
+  KF_COUNT(12, hit);                                         // [12] colliding states
 
   if (SELF && !hit) hit = rb.self_const_collision || self_collision<false>(self, f_mine, KF_THREADS, nullptr);
 
@@ -357,12 +487,24 @@ cudaError_t launch_gather_wait(const uint32_t *d_flags, int n, unsigned step, in
   return cudaGetLastError();
 }
 
+#ifdef SQMP_KF_STATS
+extern "C" int sqmp_debug_kf_stats(unsigned long long *out, int reset) {
+  cudaDeviceSynchronize();
+  cudaError_t e = cudaMemcpyFromSymbol(out, kf_stats, sizeof(kf_stats));
+  if (e == cudaSuccess && reset) {
+    unsigned long long z[16] = {0};
+    e = cudaMemcpyToSymbol(kf_stats, z, sizeof(z));
+  }
+  return e == cudaSuccess ? 0 : -2;
+}
+#endif
+
 cudaError_t launch_check_states_fast(const RobotDev &rb, const GridDev &gd, const SelfDev &self, const FastDev &fd,
                                      const KfTab &tab, const double *d_q, const double *d_q_end, int num_points, int64_t S,
                                      unsigned flags, uint32_t *d_mask, bool allow_specialized, bool overlap,
                                      cudaStream_t st, int *n_launch, const PeerDev *peers) {
   const bool with_self = (flags & SQMP_CHECK_SELF) != 0;
-  size_t smem = sizeof(WarpQueue) * (KF_THREADS / 32) + sizeof(double) * SQMP_DOF * KF_THREADS;
+  size_t smem = kf_smem_base();
   if (with_self) smem += size_t(12) * rb.n_frames * KF_THREADS * sizeof(float);
   const int64_t blocks = (S + KF_THREADS - 1) / KF_THREADS;
   if (blocks <= 0) return cudaSuccess;
