@@ -33,6 +33,7 @@ S_CONFIG4 = 1 << 26
 BYTES_PER_STATE = 64.125          # 8 x f64 in + 1 bit out
 METRIC = "collision-checked 8-DOF configs/sec"
 UNIT = "configs/s"
+WORKLOAD = "config2: 2^20 interpolated 8-DOF states per GPU vs W256 (256^3 voxels, res 0.05), map check, conservative 326-sphere model"
 
 
 def measured_peaks():
@@ -123,6 +124,18 @@ def build_inputs(n_states, seed):
     return syn.state_batch(n_states, seed=seed)
 
 
+def device_states(torch, dev, n_states, seed):
+    """n_states interpolated edge states (the config-2 generator) in device memory, built 2^20 at a time so that the host
+    never holds more than one 64 MiB chunk."""
+    from squirrel_motion_planner_b200 import synthetic as syn
+    out = torch.empty((n_states, 8), dtype=torch.float64, device=dev)
+    chunk = 1 << 20
+    for i, s0 in enumerate(range(0, n_states, chunk)):
+        n = min(chunk, n_states - s0)
+        out[s0:s0 + n].copy_(torch.from_numpy(syn.state_batch(n, seed=seed + 104729 * i)))
+    return out
+
+
 def make_world():
     from squirrel_motion_planner_b200 import robot_desc as rd, synthetic as syn
     w = syn.box_world(g=256, n_boxes=64, seed=1234)
@@ -192,7 +205,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "config2: 2^20 interpolated 8-DOF states vs W256 (256^3 voxels, res 0.05), map check",
+        "config": {"workload": WORKLOAD,
                    "note": "CPU oracle port of CollisionChecker::isInCollision on host cores; the reference itself "
                            "needs ROS/KDL/FCL/octomap, absent here"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
@@ -228,16 +241,19 @@ def run_own(args):
         s_rank = total // world_size
         scaling = "strong"
         n_rot = 1                                  # 2^26/8 states x 64 B = 512 MiB per rank > 126 MiB L2
-        batches = [syn.state_batch(total, seed=42)[rank * s_rank:(rank + 1) * s_rank]] if world_size == 1 else \
-            [syn.state_batch(s_rank, seed=42 + rank)]
+        batches = None
         wl = "config4: 2^26 interpolated states sharded over %d GPU(s), W256, map check, NCCL mask all-gather" % world_size
     else:
         s_rank = S_CONFIG2
         scaling = "weak"
         n_rot = 4                                  # 4 x 64 MiB distinct batches = 256 MiB > 126 MiB L2
         batches = [build_inputs(s_rank, 42 + 7919 * (rank * n_rot + i)) for i in range(n_rot)]
-        wl = "config2: 2^20 interpolated 8-DOF states per GPU vs W256 (256^3 voxels, res 0.05), map check"
-    d_q = [torch.from_numpy(b).to(dev) for b in batches]
+        wl = WORKLOAD
+    if batches is None:
+        d_q = [device_states(torch, dev, s_rank, 42 + 15485863 * rank)]
+        batches = [d_q[0][:S_CONFIG2].cpu().numpy()]          # the e2e leg below times one 2^20-state host batch
+    else:
+        d_q = [torch.from_numpy(b).to(dev) for b in batches]
     words = (s_rank + 31) // 32
     # gathered mask, every rank; NBUF buffers in rotation so that the gather of step i (comm stream) overlaps the kernels
     # of the following steps (compute stream).  The kernel writes straight into the rank's slot of the gather buffer.
@@ -360,8 +376,9 @@ def run_own(args):
     value = s_rank * world_size * args.steps / (total_ms * 1e-3)
 
     # ---- e2e: the host-buffer C-ABI call (pinned host memory in, mask back on the host), same workload ----
+    s_e2e = len(batches[0])
     h_q = torch.from_numpy(batches[0]).pin_memory()
-    h_mask = torch.zeros(words, dtype=torch.int32).pin_memory()
+    h_mask = torch.zeros((s_e2e + 31) // 32, dtype=torch.int32).pin_memory()
     e2e_steps = max(3, min(args.steps, 20))
     for _ in range(2):
         ctx.check_states(h_q, flags, out=h_mask)
@@ -377,12 +394,32 @@ def run_own(args):
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = s_rank * world_size * e2e_steps / e2e_s
+    e2e_value = s_e2e * world_size * e2e_steps / e2e_s
     n_colliding = int(np.unpackbits(h_mask.numpy().view(np.uint8)).sum())
+    # the ceiling of that leg: what the host -> device copy of the same pinned batch reaches with all ranks copying at once
+    d_tmp = torch.empty_like(d_q[0][:s_e2e])
+    if world_size > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        d_tmp.copy_(h_q, non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_s = (time.perf_counter() - t0) / 5
+    if world_size > 1:
+        t = torch.tensor([h2d_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        h2d_s = float(t.item())
+    h2d_gbs = s_e2e * 64 / h2d_s / 1e9
+    del d_tmp
 
     extra = {}
+    if not args.no_extra and world_size > 1 and args.workload != "config4":
+        extra.update(multi_gpu_extras(ctx, torch, dist, dev, stream, rank, world_size, args))   # collective: every rank takes part
     if rank == 0 and not args.no_extra:
-        extra = side_metrics(ctx, torch, dev, stream, d_q[0], s_rank)
+        extra.update(side_metrics(ctx, torch, dev, stream, d_q, min(s_rank, S_CONFIG2)))
+    extra["h2d_gbs_per_gpu_all_ranks_copying"] = h2d_gbs
+    extra["e2e_frac_of_h2d_ceiling"] = (e2e_value / world_size) * 64 / 1e9 / h2d_gbs
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
 
@@ -393,10 +430,16 @@ def run_own(args):
         if world_size == 1 and not args.no_cpu:
             import oracle
             threads = host_threads()
-            _, rate, n, dt = cpu_baseline_sample(threads, target_s=12.0)
+            orc_, rate, n, dt = cpu_baseline_sample(threads, target_s=12.0)
+            q1 = build_inputs(S_CONFIG2, 42)[:21 * 400]
+            t0 = time.perf_counter()
+            orc_.check_states(q1, oracle.FLAG_MAP, nthreads=1)
+            single = len(q1) / (time.perf_counter() - t0)
             cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": "first %d of the 2^20 config-2 states (repeated), W256, map check, oracle early-exit path, "
-                             "%.1f s of CPU work timed" % (n, dt)}
+                             "%.1f s of CPU work timed" % (n, dt),
+                   "single_thread": {"value": single, "unit": UNIT, "sample": "first %d states, one thread (the reference's "
+                                     "checker is single-threaded: CC:141-142)" % len(q1)}}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -407,11 +450,12 @@ def run_own(args):
                        "colliding_fraction": n_colliding / s_rank,
                        "entry": "sqmp_check_states_gather_dev" if pg is not None else "sqmp_check_states_dev",
                        "mask_gather": gather_mode if world_size > 1 else "none (1 GPU)",
-                       "kernel": "K1F (fp32 proof stages with a proven error bound, fp64 exact stage; verdicts identical "
-                                 "to the all-fp64 kernel)"},
+                       "kernel": "K1F (bound hierarchy + slab fields, fp32 proof stages with a proven error bound, fp64 exact "
+                                 "stage; verdicts identical to the all-fp64 flat kernel)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "k1_fast<false,false> (K1F)",
-                         "kernel_ms": kern_ms, "bytes_per_state": BYTES_PER_STATE},
+                         "traffic": None, "traffic_source": None, "peak_source": peak_src,
+                         "kernel": "k1_fast<false,false,SigRobotino> (K1F)", "kernel_ms": kern_ms,
+                         "bytes_per_state": BYTES_PER_STATE},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": s_rank * 64, "d2h_bytes_per_step": words * 4,
                     "entry": "sqmp_check_states (pinned host buffers)", "steps": e2e_steps, "host_cpus": numa},
@@ -419,10 +463,15 @@ def run_own(args):
             "clocks": sampler.summary(),
             "extra": extra,
         }
-        traffic_file = os.path.join(ROOT, "profiles", "k1_traffic.json")
-        if os.path.exists(traffic_file) and s_rank == S_CONFIG2:   # the capture is of one 2^20-state launch
+        # dram bytes of ONE 2^20-state launch of this kernel from the round's `ncu --set full` capture (profiles/, written
+        # by tools/ncu_traffic.py from the .ncu-rep; the build tag must match, else the key stays null)
+        traffic_file = os.path.join(ROOT, "profiles", "r2_k1f_traffic.json")
+        if os.path.exists(traffic_file) and s_rank == S_CONFIG2:
             with open(traffic_file) as f:
-                line["roofline"]["traffic"] = json.load(f).get("dram_bytes_per_launch")
+                tr = json.load(f)
+            if tr.get("library") == api.load_library().sqmp_version().decode():
+                line["roofline"]["traffic"] = tr.get("dram_bytes_per_launch")
+                line["roofline"]["traffic_source"] = tr.get("source")
         print(json.dumps(line))
     if pg is not None:
         torch.cuda.synchronize()
@@ -433,8 +482,71 @@ def run_own(args):
         dist.destroy_process_group()
 
 
-def side_metrics(ctx, torch, dev, stream, d_q, S):
+def multi_gpu_extras(ctx, torch, dist, dev, stream, rank, world_size, args):
+    """N > 1, same run: (1) BASELINE.json configs[3] — the 2^26-state batch sharded over the ranks (strong scaling), every
+    rank's mask all-gathered with NCCL; (2) configs[2] — the 2^16 queries sharded over the ranks against the replicated
+    2^20-node tree, ids all-gathered.  Device-timed, max over ranks."""
+    from squirrel_motion_planner_b200 import api, synthetic as syn
+    out = {}
+    s_rank = S_CONFIG4 // world_size
+    d_q = device_states(torch, dev, s_rank, 42 + 15485863 * rank)
+    words = s_rank // 32
+    d_all = torch.zeros(world_size * words, dtype=torch.int32, device=dev)
+    d_mine = d_all[rank * words:(rank + 1) * words]
+
+    def timed(fn, n, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / n], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step4():
+        ctx.check_states_dev(d_q, s_rank, api.CHECK_MAP, d_mine, stream)
+        dist.all_gather_into_tensor(d_all, d_mine)
+    ms = timed(step4, 5, 2)
+    out["config4_states_per_s"] = S_CONFIG4 / ms * 1e3
+    out["config4_ms_per_batch"] = ms
+    out["config4_workload"] = "2^26 interpolated states sharded over %d GPUs (strong), W256, map check, ncclAllGather of the %d MiB mask" % (
+        world_size, S_CONFIG4 // 8 >> 20)
+    del d_q, d_all
+    torch.cuda.empty_cache()
+    N, Q, K = 1 << 20, 1 << 16, 20
+    nodes, cost = syn.random_tree(N, 7, 9)
+    ctx.tree_reset(0)
+    ctx.tree_append_batch(0, nodes, cost)
+    q_rank = Q // world_size
+    d_qs = torch.from_numpy(syn.sample_configs(Q, 8)[rank * q_rank:(rank + 1) * q_rank]).to(dev)
+    d_ids_all = torch.zeros(Q, dtype=torch.int32, device=dev)
+    d_ids = d_ids_all[rank * q_rank:(rank + 1) * q_rank]
+    d_low = torch.empty((q_rank, K), dtype=torch.int32, device=dev)
+    d_high = torch.empty_like(d_low)
+    d_cnt = torch.empty(q_rank, dtype=torch.int32, device=dev)
+    d_ov = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def step3():
+        ctx.nn_nearest_dev(0, d_qs, q_rank, d_ids, stream)
+        ctx.nn_radius_dev(0, d_qs, None, q_rank, 1.5, K, d_low, d_high, d_cnt, d_ov, stream)
+        dist.all_gather_into_tensor(d_ids_all, d_ids)
+    ms = timed(step3, 3, 1)
+    out["nn_sharded_queries_per_s"] = Q / ms * 1e3
+    out["nn_sharded_workload"] = "config3: 2^20-node tree replicated, 2^16 queries sharded over %d GPUs, nearest + radius/top-k per query, ids all-gathered" % world_size
+    ctx.tree_reset(0)
+    return out
+
+
+def side_metrics(ctx, torch, dev, stream, d_qs_rot, S):
     """Secondary numbers of the same run (not the headline): FK-only, self-collision, edges entry, NN."""
+    d_q = d_qs_rot[0][:S]
     from squirrel_motion_planner_b200 import api, synthetic as syn
     peak, _ = measured_peaks()
 
@@ -451,12 +563,23 @@ def side_metrics(ctx, torch, dev, stream, d_q, S):
 
     out = {}
     d_mask = torch.zeros((S + 31) // 32, dtype=torch.int32, device=dev)
-    d_pose = torch.empty((S, 7), dtype=torch.float64, device=dev)
-    ms = t_ms(lambda: ctx.fk_dev(d_q, S, d_pose, stream), n=20, warm=3)
+    # K2 is the HBM-bound kernel: its inputs and outputs rotate over a working set larger than L2 (>= 4 x 64 MiB in, 4 x 56 MiB out)
+    ins = [t[:S] for t in d_qs_rot]
+    while len(ins) < 4:
+        ins.append(ins[0].clone())
+    outs = [torch.empty((S, 7), dtype=torch.float64, device=dev) for _ in range(4)]
+    d_pose = outs[0]
+    k2i = [0]
+
+    def k2():
+        ctx.fk_dev(ins[k2i[0] % len(ins)], S, outs[k2i[0] % 4], stream)
+        k2i[0] += 1
+    ms = t_ms(k2, n=24, warm=4)
     out["fk_states_per_s"] = S / ms * 1e3
     out["fk_hbm_frac"] = S * 120 / (ms * 1e-3) / 1e9 / peak          # K2, fp64 chain (default): 120 B/state
+    out["fk_working_set"] = "%d MiB in + %d MiB out, rotating (> 126 MiB L2)" % (len(ins) * S * 64 >> 20, 4 * S * 56 >> 20)
     ctx.set_option("fk_precision", 32)
-    ms = t_ms(lambda: ctx.fk_dev(d_q, S, d_pose, stream), n=20, warm=3)
+    ms = t_ms(k2, n=24, warm=4)
     out["fk_fp32chain_states_per_s"] = S / ms * 1e3
     out["fk_fp32chain_hbm_frac"] = S * 120 / (ms * 1e-3) / 1e9 / peak  # K2, fp32 chain + fp64 base (<= 2e-6 m error)
     ctx.set_option("fk_precision", 64)

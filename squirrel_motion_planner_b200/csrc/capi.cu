@@ -55,11 +55,12 @@ struct Ctx {
   // ---- device tables ----
   K1Slot *d_k1slots = nullptr;
   SelfGroupPair *d_self_gp = nullptr;
-  SelfLinkPair *d_self_lp = nullptr;
+  int *d_self_lp = nullptr;
+  SelfALink *d_self_al = nullptr;
   SelfLink *d_self_links = nullptr;
   SelfCluster *d_self_cl = nullptr;
   SelfLeaf *d_self_leaves = nullptr;
-  size_t self_cap[5] = {0, 0, 0, 0, 0};
+  size_t self_cap[6] = {0, 0, 0, 0, 0, 0};
   SelfDev self;
   bool grid_borrowed = false;   // the grid fields belong to another context (sqmp_share_voxel_grid): never freed here
   uint32_t *d_occ = nullptr;
@@ -315,21 +316,28 @@ static int build_self_tables(Ctx *c, double inv) {
   for (int gi = 0; gi < SQMP_MAX_GROUPS; ++gi) g.grp_fidx[gi] = -1;
   g.n_frames = 0;
   std::vector<SelfGroupPair> gps;
-  std::vector<SelfLinkPair> lps;
+  std::vector<SelfALink> als;
+  std::vector<int> lps;
   for (int ga = 0; ga < SQMP_MAX_GROUPS; ++ga)
     for (int gb = ga + 1; gb < SQMP_MAX_GROUPS; ++gb) {
       std::vector<int> ida, idb;
-      const int lp0 = int(lps.size());
-      for (size_t a = 0; a < links.size(); ++a)
+      const int al0 = int(als.size());
+      for (size_t a = 0; a < links.size(); ++a) {
+        if (link_grp[a] != ga) continue;
+        const int lp0 = int(lps.size());
         for (size_t b = 0; b < links.size(); ++b)
-          if (link_grp[a] == ga && link_grp[b] == gb && ((c->link_pair_mask[links[a].link] >> links[b].link) & 1ull)) {
-            lps.push_back({int(a), int(b)});
-            for (int k = links[a].cl_begin; k < links[a].cl_end; ++k)
-              ida.insert(ida.end(), c->clusters[size_t(k)].members.begin(), c->clusters[size_t(k)].members.end());
+          if (link_grp[b] == gb && ((c->link_pair_mask[links[a].link] >> links[b].link) & 1ull)) {
+            lps.push_back(int(b));
             for (int k = links[b].cl_begin; k < links[b].cl_end; ++k)
               idb.insert(idb.end(), c->clusters[size_t(k)].members.begin(), c->clusters[size_t(k)].members.end());
           }
-      if (int(lps.size()) == lp0) continue;
+        if (int(lps.size()) == lp0) continue;
+        for (int k = links[a].cl_begin; k < links[a].cl_end; ++k)
+          ida.insert(ida.end(), c->clusters[size_t(k)].members.begin(), c->clusters[size_t(k)].members.end());
+        SelfALink al = {links[a].x, links[a].y, links[a].z, links[a].R, lp0, int(lps.size()), int(a), 0};
+        als.push_back(al);
+      }
+      if (int(als.size()) == al0) continue;
       if (g.grp_fidx[ga] < 0) g.grp_fidx[ga] = g.n_frames++;
       if (g.grp_fidx[gb] < 0) g.grp_fidx[gb] = g.n_frames++;
       double ca[3], RA, cb[3], RB, c2[2], R2, zl, zh;
@@ -337,18 +345,19 @@ static int build_self_tables(Ctx *c, double inv) {
       enclose(c->sph, idb, cb, RB, c2, R2, zl, zh);
       SelfGroupPair gp;
       gp.fa = g.grp_fidx[ga]; gp.fb = g.grp_fidx[gb];
-      gp.lp_begin = lp0; gp.lp_end = int(lps.size());
+      gp.al_begin = al0; gp.al_end = int(als.size());
       gp.ax = float(ca[0] * inv); gp.ay = float(ca[1] * inv); gp.az = float(ca[2] * inv); gp.RA = pad(RA);
       gp.bx = float(cb[0] * inv); gp.by = float(cb[1] * inv); gp.bz = float(cb[2] * inv); gp.RB = pad(RB);
       gps.push_back(gp);
     }
   cudaError_t e = upload_vec(c->d_self_gp, c->self_cap[0], gps);
   if (e == cudaSuccess) e = upload_vec(c->d_self_lp, c->self_cap[1], lps);
+  if (e == cudaSuccess) e = upload_vec(c->d_self_al, c->self_cap[5], als);
   if (e == cudaSuccess) e = upload_vec(c->d_self_links, c->self_cap[2], links);
   if (e == cudaSuccess) e = upload_vec(c->d_self_cl, c->self_cap[3], cls);
   if (e == cudaSuccess) e = upload_vec(c->d_self_leaves, c->self_cap[4], leaves);
   if (e != cudaSuccess) return fail(c, SQMP_ERR_CUDA, "self-collision tables", e);
-  c->self.gpairs = c->d_self_gp; c->self.lpairs = c->d_self_lp; c->self.links = c->d_self_links;
+  c->self.gpairs = c->d_self_gp; c->self.alinks = c->d_self_al; c->self.lpairs = c->d_self_lp; c->self.links = c->d_self_links;
   c->self.clusters = c->d_self_cl; c->self.leaves = c->d_self_leaves;
   c->self.n_gpairs = int(gps.size()); c->self.n_lpairs = int(lps.size()); c->self.n_links = int(links.size());
   c->rb.n_frames = g.n_frames;
@@ -572,6 +581,14 @@ static void tree_track_norm(TreeDev &t, const double *q, int64_t n) {
 
 static int tree_reserve(Ctx *c, TreeDev &t, int64_t need) {
   if (need <= t.cap) return SQMP_OK;
+  // growing copies the old buffers with blocking copies on the legacy stream, which does not order against the
+  // non-blocking streams[0]: single-node writes still in flight there (sqmp_tree_append / sqmp_tree_update) must land
+  // in the OLD buffers before they are copied
+  if (c->streams[0]) {
+    cudaError_t es = cudaStreamSynchronize(c->streams[0]);
+    if (es != cudaSuccess) return fail(c, SQMP_ERR_CUDA, "cudaStreamSynchronize(tree grow)", es);
+  }
+  c->tree_writes_pending = false;
   int64_t cap = t.cap > 0 ? t.cap : 4096;
   while (cap < need) cap *= 2;
   // one allocation for the 8 coordinate columns + cost; columns 256-byte aligned
@@ -850,6 +867,7 @@ void sqmp_destroy(sqmp_ctx *ctx) {
   cudaDeviceSynchronize();
   if (ctx->d_self_gp) cudaFree(ctx->d_self_gp);
   if (ctx->d_self_lp) cudaFree(ctx->d_self_lp);
+  if (ctx->d_self_al) cudaFree(ctx->d_self_al);
   if (ctx->d_self_links) cudaFree(ctx->d_self_links);
   if (ctx->d_self_cl) cudaFree(ctx->d_self_cl);
   if (ctx->d_self_leaves) cudaFree(ctx->d_self_leaves);
@@ -1381,8 +1399,7 @@ int sqmp_tree_append(sqmp_ctx *ctx, int tree, const double q[SQMP_DOF], double c
   if (t.n >= 0x7fffffff) return fail(c, SQMP_ERR_INVALID, "tree full");
   // stream-ordered, not synchronised: the node travels in the kernel parameters, and every later call that reads
   // the tree runs on (or synchronises with) the same stream.  Growing the buffers synchronises the device itself.
-  if (t.n + 1 > t.cap) CU(cudaDeviceSynchronize());
-  int rc = tree_reserve(c, t, t.n + 1);
+  int rc = tree_reserve(c, t, t.n + 1);   // (synchronises streams[0] itself when it has to grow)
   if (rc) return rc;
   tree_track_norm(t, q, 1);
   CU(launch_tree_set_one(t, t.n, q, cost, c->streams[0]));

@@ -33,8 +33,10 @@ __device__ __forceinline__ void self_relative(const float (&FA)[12], const float
 }
 
 // true <=> some sphere of link a overlaps some sphere of link b, for an enabled link pair (a, b) on different rigid
-// groups.  A level of the hierarchy is entered only if the level above cannot rule it out: group pair -> link pair ->
-// (link A, cluster of B) -> cluster pair -> (cluster of A, leaf of B) -> leaf pair.  Everything is expressed in A's
+// groups.  A level of the hierarchy is entered only if the level above cannot rule it out: group pair -> (link of A,
+// group B) -> (cluster of A, group B) -> (cluster of A, link of B) -> cluster pair -> (cluster of A, leaf of B) -> leaf
+// pair: the A side (the base: twelve links, ~45 clusters) is narrowed down against the small bound of the whole B
+// group before the B side's many links are looked at.  Everything is expressed in A's
 // frame, so the A side is tested as the constants it is.  LINK_HITS (diagnostics): no early exit, every colliding link
 // pair is recorded in link_pair_hit[64 * 64].
 template <bool LINK_HITS>
@@ -47,48 +49,58 @@ __device__ __forceinline__ bool self_collision(const SelfDev &sd, const float *f
     self_load_frame(f_mine, pitch, G.fa, FA);
     self_load_frame(f_mine, pitch, G.fb, FB);
     self_relative(FA, FB, T);
-    float px, py, pz;
-    self_xform(T, G.bx, G.by, G.bz, px, py, pz);
+    float gx, gy, gz;   // bound of the B-side links, in A's frame
+    self_xform(T, G.bx, G.by, G.bz, gx, gy, gz);
     {
       const float rs = G.RA + G.RB;
-      if (self_dist2(px, py, pz, G.ax, G.ay, G.az) > rs * rs) continue;
+      if (self_dist2(gx, gy, gz, G.ax, G.ay, G.az) > rs * rs) continue;
     }
-    for (int lp = G.lp_begin; lp < G.lp_end; ++lp) {
-      const SelfLinkPair P = sd.lpairs[lp];
-      const SelfLink LA = sd.links[P.a], LB = sd.links[P.b];
-      self_xform(T, LB.x, LB.y, LB.z, px, py, pz);
-      const float rl = LA.R + LB.R;
-      if (self_dist2(px, py, pz, LA.x, LA.y, LA.z) > rl * rl) continue;
-      bool pair_hit = false;
-      for (int cb = LB.cl_begin; cb < LB.cl_end && !pair_hit; ++cb) {
-        const SelfCluster CB = sd.clusters[cb];
-        float qx, qy, qz;
-        self_xform(T, CB.x, CB.y, CB.z, qx, qy, qz);
-        const float r1 = LA.R + CB.R;
-        if (self_dist2(qx, qy, qz, LA.x, LA.y, LA.z) > r1 * r1) continue;
-        for (int ca = LA.cl_begin; ca < LA.cl_end && !pair_hit; ++ca) {
-          const SelfCluster CA = sd.clusters[ca];
-          const float r2 = CA.R + CB.R;
-          if (self_dist2(qx, qy, qz, CA.x, CA.y, CA.z) > r2 * r2) continue;
-          for (int b = CB.leaf_begin; b < CB.leaf_end && !pair_hit; ++b) {
-            const SelfLeaf Bl = sd.leaves[b];
-            float bx, by, bz;
-            self_xform(T, Bl.x, Bl.y, Bl.z, bx, by, bz);
-            const float r3 = CA.R + Bl.r;
-            if (self_dist2(bx, by, bz, CA.x, CA.y, CA.z) > r3 * r3) continue;
-            for (int a = CA.leaf_begin; a < CA.leaf_end; ++a) {
-              const SelfLeaf Al = sd.leaves[a];
-              const float rs = Al.r + Bl.r;
-              if (self_dist2(bx, by, bz, Al.x, Al.y, Al.z) <= rs * rs) { pair_hit = true; break; }
+    for (int al = G.al_begin; al < G.al_end; ++al) {
+      const SelfALink AL = sd.alinks[al];
+      {
+        const float ra = AL.R + G.RB;
+        if (self_dist2(gx, gy, gz, AL.x, AL.y, AL.z) > ra * ra) continue;   // this A link is out of reach of all of B
+      }
+      const SelfLink LA = sd.links[AL.a];
+      for (int ca = LA.cl_begin; ca < LA.cl_end; ++ca) {
+        const SelfCluster CA = sd.clusters[ca];
+        {
+          const float rc = CA.R + G.RB;
+          if (self_dist2(gx, gy, gz, CA.x, CA.y, CA.z) > rc * rc) continue;   // ... and so is this cluster of it
+        }
+        for (int lp = AL.lp_begin; lp < AL.lp_end; ++lp) {
+          const SelfLink LB = sd.links[sd.lpairs[lp]];
+          if (LINK_HITS && link_pair_hit[min(LA.link, LB.link) * SQMP_MAX_LINKS + max(LA.link, LB.link)]) continue;
+          float px, py, pz;
+          self_xform(T, LB.x, LB.y, LB.z, px, py, pz);
+          const float rl = CA.R + LB.R;
+          if (self_dist2(px, py, pz, CA.x, CA.y, CA.z) > rl * rl) continue;
+          bool pair_hit = false;
+          for (int cb = LB.cl_begin; cb < LB.cl_end && !pair_hit; ++cb) {
+            const SelfCluster CB = sd.clusters[cb];
+            float qx, qy, qz;
+            self_xform(T, CB.x, CB.y, CB.z, qx, qy, qz);
+            const float r2 = CA.R + CB.R;
+            if (self_dist2(qx, qy, qz, CA.x, CA.y, CA.z) > r2 * r2) continue;
+            for (int b = CB.leaf_begin; b < CB.leaf_end && !pair_hit; ++b) {
+              const SelfLeaf Bl = sd.leaves[b];
+              float bx, by, bz;
+              self_xform(T, Bl.x, Bl.y, Bl.z, bx, by, bz);
+              const float r3 = CA.R + Bl.r;
+              if (self_dist2(bx, by, bz, CA.x, CA.y, CA.z) > r3 * r3) continue;
+              for (int a = CA.leaf_begin; a < CA.leaf_end; ++a) {
+                const SelfLeaf Al = sd.leaves[a];
+                const float rs = Al.r + Bl.r;
+                if (self_dist2(bx, by, bz, Al.x, Al.y, Al.z) <= rs * rs) { pair_hit = true; break; }
+              }
             }
           }
+          if (pair_hit) {
+            if (!LINK_HITS) return true;
+            any = true;
+            link_pair_hit[min(LA.link, LB.link) * SQMP_MAX_LINKS + max(LA.link, LB.link)] = 1;
+          }
         }
-      }
-      if (pair_hit) {
-        if (!LINK_HITS) return true;
-        any = true;
-        const int la = min(LA.link, LB.link), lb = max(LA.link, LB.link);
-        link_pair_hit[la * SQMP_MAX_LINKS + lb] = 1;
       }
     }
   }

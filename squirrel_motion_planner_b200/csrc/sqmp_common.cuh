@@ -132,8 +132,8 @@ struct FastDev {
 };
 
 // ---- self collision (CC:541-552) -------------------------------------------------------------------------------------
-// Nested bounds over the enabled link pairs whose links hang on different rigid groups: group pair -> link pair ->
-// cluster of B vs link A -> cluster pair -> leaf of B vs cluster of A -> leaf pair.  A level is entered only if the level
+// Nested bounds over the enabled link pairs whose links hang on different rigid groups: group pair -> link of A vs the
+// bound of group B -> link pair -> cluster of B vs link A -> cluster pair -> leaf of B vs cluster of A -> leaf pair.  A level is entered only if the level
 // above cannot rule it out, so a state far from self contact costs ~one test per link pair.  All centres are fp32 in
 // their group frame, grid units; bounds are padded against fp32 rounding (capi.cu: build_self_tables).
 struct SelfLeaf {   // 16 bytes
@@ -149,18 +149,22 @@ struct SelfLink {   // 32 bytes: bounding sphere of a link + its clusters
   int cl_begin, cl_end;
   int link, pad;
 };
-struct SelfLinkPair {   // 8 bytes: indices into SelfDev::links (a in group A, b in group B)
-  int a, b;
+struct SelfALink {   // 32 bytes: a link of group A within one group pair, with the B-side links it is checked against
+  float x, y, z, R;       // the link's bound (A frame)
+  int lp_begin, lp_end;   // its partners in SelfDev::lpairs
+  int a;                  // its record in SelfDev::links (clusters)
+  int pad;
 };
 struct SelfGroupPair {   // 48 bytes
   int fa, fb;             // frame slots of the two groups (RobotDev::grp_fidx)
-  int lp_begin, lp_end;   // its link pairs
+  int al_begin, al_end;   // the A-side links that take part (SelfDev::alinks)
   float ax, ay, az, RA;   // bound of the A-side links that take part
   float bx, by, bz, RB;   // ... B side
 };
 struct SelfDev {
   const SelfGroupPair *gpairs;
-  const SelfLinkPair *lpairs;
+  const SelfALink *alinks;
+  const int *lpairs;          // B-side link (index into links) of every enabled link pair, grouped by A-side link
   const SelfLink *links;
   const SelfCluster *clusters;
   const SelfLeaf *leaves;
