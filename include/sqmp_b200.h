@@ -133,6 +133,29 @@ int sqmp_fk(sqmp_ctx *ctx, const double *q, int64_t S, double *ee_pose_out);
 int sqmp_sample_configs(sqmp_ctx *ctx, uint64_t seed, int64_t first, int64_t n, const double lo[SQMP_DOF],
                         const double hi[SQMP_DOF], int max_tries, double *q_out, int32_t *tries_out);
 
+/* BiRRTstarPlanner::sampleJointConfigfromEllipse_JntArray (BS:3607-3829): the informed sampler the planner switches to
+ * once a solution exists (BS:1168).  The ellipse comes from jointConfigEllipseInitialization (BS:3472-3604), per joint
+ * class (revolute / prismatic): centre = midpoint of start and goal, rotation C with first column (goal - start) / c_min,
+ * and the diagonal L = (c_best / 2, sqrt(c_best^2 - c_min^2) / 2, ...) of BS:3709-3752 (the caller refreshes l_rev /
+ * l_pri whenever the best solution cost changes).  One try: a joint vector uniform in [lo, hi] (getRandomConf), split by
+ * class, each part normalised and scaled by ONE uniform number in [0, 1); x = C (L ball) + centre, written back prismatic
+ * joints first, then revolute ones (BS:3773-3785); redrawn until the end-effector lies above the platform (0.0 <= ee_z) and
+ * the first two joints lie strictly inside env_x / env_y (all four zero: unconfined; BS:3800-3806).  Try t of sample i
+ * uses outputs 9 * ((first + i) * max_tries + t) + j, j = 0..8 (j = 8: the scale), of the splitmix64 stream of
+ * sqmp_sample_configs.  Products and sums are evaluated in index order with round-to-nearest operations, so the device
+ * and the CPU oracle produce the same doubles. */
+typedef struct sqmp_informed {
+  int32_t n_rev, n_pri;              /* joints per class (n_rev + n_pri = 8) */
+  int32_t rev_idx[SQMP_DOF], pri_idx[SQMP_DOF];   /* which entries of the joint vector belong to the class, ascending */
+  double c_rev[SQMP_DOF * SQMP_DOF], c_pri[SQMP_DOF * SQMP_DOF];   /* rotation C, row-major n x n */
+  double center_rev[SQMP_DOF], center_pri[SQMP_DOF];
+  double l_rev[2], l_pri[2];         /* L = diag(l[0], l[1], ..., l[1]) */
+  double env_x[2], env_y[2];
+} sqmp_informed;
+int sqmp_sample_informed(sqmp_ctx *ctx, uint64_t seed, int64_t first, int64_t n, const double lo[SQMP_DOF],
+                         const double hi[SQMP_DOF], int max_tries, const sqmp_informed *ellipse, double *q_out,
+                         int32_t *tries_out);
+
 /* ---- tree mirror (DS:29-54; mutation sites BS:3298-3322, 5173-5193, 5518-5520) ------------------- */
 /* Invariant kept from the reference: node_id == index.  tree in [0, SQMP_MAX_TREES). */
 int sqmp_tree_reset(sqmp_ctx *ctx, int tree);
@@ -197,6 +220,9 @@ int sqmp_gather_signal_dev(sqmp_ctx *ctx, const sqmp_peer_gather *g, uint32_t st
 int sqmp_gather_wait_dev(sqmp_ctx *ctx, const uint32_t *d_flags, int n_peers, uint32_t step, int32_t *d_status, void *stream);
 int sqmp_sample_configs_dev(sqmp_ctx *ctx, uint64_t seed, int64_t first, int64_t n, const double lo[SQMP_DOF],
                             const double hi[SQMP_DOF], int max_tries, double *d_q_out, int32_t *d_tries_out, void *stream);
+int sqmp_sample_informed_dev(sqmp_ctx *ctx, uint64_t seed, int64_t first, int64_t n, const double lo[SQMP_DOF],
+                             const double hi[SQMP_DOF], int max_tries, const sqmp_informed *ellipse, double *d_q_out,
+                             int32_t *d_tries_out, void *stream);
 int sqmp_fk_dev(sqmp_ctx *ctx, const double *d_q, int64_t S, double *d_ee_pose, void *stream);
 int sqmp_nn_nearest_dev(sqmp_ctx *ctx, int tree, const double *d_queries, int64_t Q, int32_t *d_id, void *stream);
 /* d_overflow: one int32, set to 1 if some query had more hits than the internal per-query buffer. */

@@ -138,6 +138,8 @@ def lib():
     L.orc_fk.argtypes = [C.c_void_p, C.c_int, dp, C.c_int64, dp]
     L.orc_sample_configs.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int64, C.c_int64, dp, dp, C.c_int, dp,
                                      C.POINTER(C.c_int32)]
+    L.orc_sample_informed.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int64, C.c_int64, dp, dp, C.c_int, C.c_void_p, dp,
+                                      C.POINTER(C.c_int32)]
     L.orc_joint_space_distance.restype = C.c_double
     L.orc_joint_space_distance.argtypes = [dp, dp, C.c_int]
     L.orc_nearest.restype = C.c_int32
@@ -255,6 +257,17 @@ class Oracle:
         tries = np.empty(n, dtype=np.int32)
         lib().orc_sample_configs(self._h, self.lt.index(tip), int(seed), int(first), int(n), _p(lo, C.c_double),
                                  _p(hi, C.c_double), int(max_tries), _p(q, C.c_double), _p(tries, C.c_int32))
+        return q, tries
+
+
+    def sample_informed(self, seed, first, n, lo, hi, ellipse, max_tries=64, tip="hand_wrist_link"):
+        """sampleJointConfigfromEllipse_JntArray (BS:3607-3829); ellipse: squirrel_motion_planner_b200.informed.InformedC."""
+        lo, hi = _f64(lo), _f64(hi)
+        q = np.empty((n, DOF))
+        tries = np.empty(n, dtype=np.int32)
+        lib().orc_sample_informed(self._h, self.lt.index(tip), C.c_uint64(int(seed)), C.c_int64(int(first)), C.c_int64(int(n)),
+                                  _p(lo, C.c_double), _p(hi, C.c_double), int(max_tries), C.byref(ellipse), _p(q, C.c_double),
+                                  _p(tries, C.c_int32))
         return q, tries
 
 

@@ -16,6 +16,11 @@ class OracleBackend {
   void sample_batch(uint64_t seed, long long first, int n, const double *lo, const double *hi, int max_tries, double *q_out) {
     orc_sample_configs(m_, tip_, seed, first, n, lo, hi, max_tries, q_out, NULL);
   }
+  void sample_informed_batch(uint64_t seed, long long first, int n, const double *lo, const double *hi, int max_tries,
+                             const sqmp_informed &el, double *q_out) {
+    static_assert(sizeof(sqmp_informed) == sizeof(orc_informed), "orc_informed mirrors sqmp_informed");
+    orc_sample_informed(m_, tip_, seed, first, n, lo, hi, max_tries, reinterpret_cast<const orc_informed *>(&el), q_out, NULL);
+  }
   void tree_reset(int slot) { nodes_[slot].clear(); cost_[slot].clear(); }
   int tree_append(int slot, const double *q, double cost) {
     nodes_[slot].insert(nodes_[slot].end(), q, q + 8);
@@ -73,6 +78,11 @@ class OracleService {
   }
   int sample(uint64_t seed, long long first, int n, const double *lo, const double *hi, int max_tries, double *q_out) {
     orc_sample_configs(m_, tip_, seed, first, n, lo, hi, max_tries, q_out, NULL);
+    return 0;
+  }
+  int sample_informed(uint64_t seed, long long first, int n, const double *lo, const double *hi, int max_tries, const sqmp_informed &el,
+                      double *q_out) {
+    orc_sample_informed(m_, tip_, seed, first, n, lo, hi, max_tries, reinterpret_cast<const orc_informed *>(&el), q_out, NULL);
     return 0;
   }
   int nearest_multi(const int32_t *tree, const double *q, int64_t n, int32_t *ids) {
@@ -159,9 +169,9 @@ int main(int argc, char **argv) {
         continue;
       }
       const sqmp_planner::Stats &s = res[k].stats;
-      std::printf("%zu %d %.17g %ld %ld %ld %ld %ld %ld %ld %ld %ld %ld %llu\n", a.first + k, int(s.solved), s.best_cost,
+      std::printf("%zu %d %.17g %ld %ld %ld %ld %ld %ld %ld %ld %ld %ld %llu %.17g %.17g %ld %ld\n", a.first + k, int(s.solved), s.best_cost,
                   s.iterations, s.nn_calls, s.near_calls, s.edge_batches, s.edges_checked, s.states_checked, s.rewires,
-                  s.parents_chosen, s.nodes_start, s.nodes_goal, (unsigned long long)s.trace);
+                  s.parents_chosen, s.nodes_start, s.nodes_goal, (unsigned long long)s.trace, s.best_cost_rev, s.best_cost_pri, s.informed_samples, s.solution_rewires);
     }
     std::printf("# queries %zu rounds %ld service_calls %ld\n", count, sched.rounds(), sched.library_calls());
   } else {

@@ -504,6 +504,65 @@ void orc_sample_configs(const orc_model *m, int tip, uint64_t seed, int64_t firs
   }
 }
 
+/* sampleJointConfigfromEllipse_JntArray (BS:3607-3829) over the counter stream of orc_sample_configs, nine outputs per
+ * try (eight joint draws for getRandomConf, BS:3633, + the point scale, BS:3690).  The ellipse (centres, rotations C,
+ * diagonal L) is prepared by the caller like jointConfigEllipseInitialization (BS:3472-3604) / BS:3709-3752 do. */
+void orc_sample_informed(const orc_model *m, int tip, uint64_t seed, int64_t first, int64_t n, const double *lo,
+                         const double *hi, int max_tries, const orc_informed *el, double *q_out, int32_t *tries_out) {
+  const int unconfined = el->env_x[0] == 0.0 && el->env_x[1] == 0.0 && el->env_y[0] == 0.0 && el->env_y[1] == 0.0;
+  for (int64_t i = 0; i < n; ++i) {
+    double *rand_conf_array = q_out + i * ORC_DOF, ee_pose[7];
+    int used = -max_tries;
+    for (int t = 0; t < max_tries; ++t) {   /* while (collision_free == false || above_platform == false || ...), bounded */
+      const uint64_t k0 = ((uint64_t)(first + i) * (uint64_t)max_tries + (uint64_t)t) * 9ull;
+      double ball_conf_array[ORC_DOF];
+      for (int j = 0; j < ORC_DOF; ++j) {   /* getRandomConf (BS:3633) */
+        const double u = (double)(splitmix_at(seed, k0 + (uint64_t)j) >> 11) * (1.0 / 9007199254740992.0);
+        const double span = hi[j] - lo[j];
+        const double step = span * u;
+        ball_conf_array[j] = lo[j] + step;
+      }
+      const double point_scale = (double)(splitmix_at(seed, k0 + 8ull) >> 11) * (1.0 / 9007199254740992.0);   /* BS:3690 */
+      int joint_index = 0;
+      for (int cls = 0; cls < 2; ++cls) {   /* BS:3773-3785: prismatic joints first, then revolute ones */
+        const int nc = cls == 0 ? el->n_pri : el->n_rev;
+        const int32_t *idx = cls == 0 ? el->pri_idx : el->rev_idx;
+        const double *C = cls == 0 ? el->c_pri : el->c_rev;
+        const double *center = cls == 0 ? el->center_pri : el->center_rev;
+        const double *L = cls == 0 ? el->l_pri : el->l_rev;
+        double sum_squares = 0.0, y[ORC_DOF];
+        for (int a = 0; a < nc; ++a) {   /* BS:3676-3683 */
+          const double sq = ball_conf_array[idx[a]] * ball_conf_array[idx[a]];
+          sum_squares += sq;
+        }
+        const double conf_norm = sqrt(sum_squares);
+        for (int a = 0; a < nc; ++a) {   /* BS:3697-3704, then the diagonal L of BS:3709-3752 */
+          const double unit = ball_conf_array[idx[a]] / conf_norm;
+          const double ball = point_scale * unit;
+          y[a] = (a == 0 ? L[0] : L[1]) * ball;
+        }
+        for (int r = 0; r < nc; ++r) {   /* BS:3759-3763: C * L * ball + centre */
+          double acc = 0.0;
+          for (int a = 0; a < nc; ++a) {
+            const double prod = C[r * nc + a] * y[a];
+            acc += prod;
+          }
+          rand_conf_array[joint_index++] = acc + center[r];
+        }
+      }
+      orc_fk(m, tip, rand_conf_array, 1, ee_pose);
+      const int above_platform = 0.0 <= ee_pose[2];   /* BS:3792-3795 */
+      const int inside_environment = unconfined || (rand_conf_array[0] < el->env_x[1] && rand_conf_array[0] > el->env_x[0] &&
+                                                    rand_conf_array[1] < el->env_y[1] && rand_conf_array[1] > el->env_y[0]);   /* BS:3810-3816 */
+      if (above_platform && inside_environment) {
+        used = t + 1;
+        break;
+      }
+    }
+    if (tries_out) tries_out[i] = used;
+  }
+}
+
 /* ---------------------------------------------------------------- distances and neighbours */
 /* DH:128-156 */
 double orc_joint_space_distance(const double *a, const double *b, int n) {

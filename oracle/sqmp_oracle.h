@@ -96,6 +96,17 @@ void orc_fk(const orc_model *m, int tip, const double *q /*S*8*/, int64_t S, dou
  * used, or -max_tries when every try was below the platform (the last try is returned). */
 void orc_sample_configs(const orc_model *m, int tip, uint64_t seed, int64_t first, int64_t n, const double *lo,
                         const double *hi, int max_tries, double *q_out /*n*8*/, int32_t *tries_out);
+/* layout of sqmp_informed (include/sqmp_b200.h) */
+typedef struct orc_informed {
+  int32_t n_rev, n_pri;
+  int32_t rev_idx[ORC_DOF], pri_idx[ORC_DOF];
+  double c_rev[ORC_DOF * ORC_DOF], c_pri[ORC_DOF * ORC_DOF];
+  double center_rev[ORC_DOF], center_pri[ORC_DOF];
+  double l_rev[2], l_pri[2];
+  double env_x[2], env_y[2];
+} orc_informed;
+void orc_sample_informed(const orc_model *m, int tip, uint64_t seed, int64_t first, int64_t n, const double *lo,
+                         const double *hi, int max_tries, const orc_informed *el, double *q_out, int32_t *tries_out);
 
 /* euclidean_joint_space_distance (DH:128-156). */
 double orc_joint_space_distance(const double *a, const double *b, int n);

@@ -26,7 +26,7 @@ EXPORTS = [
     "sqmp_share_voxel_grid", "sqmp_set_disabled_links", "sqmp_check_states", "sqmp_check_edges", "sqmp_get_collisions", "sqmp_fk",
     "sqmp_tree_reset", "sqmp_tree_append", "sqmp_tree_append_batch", "sqmp_tree_update", "sqmp_tree_update_costs",
     "sqmp_tree_size", "sqmp_nn_nearest", "sqmp_nn_radius", "sqmp_check_states_dev", "sqmp_check_edges_dev",
-    "sqmp_fk_dev", "sqmp_sample_configs", "sqmp_sample_configs_dev", "sqmp_check_states_gather_dev", "sqmp_gather_signal_dev", "sqmp_gather_wait_dev", "sqmp_nn_nearest_multi", "sqmp_nn_radius_multi", "sqmp_nn_nearest_dev", "sqmp_nn_radius_dev", "sqmp_kernel_launches", "sqmp_set_option",
+    "sqmp_fk_dev", "sqmp_sample_configs", "sqmp_sample_configs_dev", "sqmp_sample_informed", "sqmp_sample_informed_dev", "sqmp_check_states_gather_dev", "sqmp_gather_signal_dev", "sqmp_gather_wait_dev", "sqmp_nn_nearest_multi", "sqmp_nn_radius_multi", "sqmp_nn_nearest_dev", "sqmp_nn_radius_dev", "sqmp_kernel_launches", "sqmp_set_option",
 ]
 
 
@@ -115,6 +115,8 @@ def load_library():
     L.sqmp_nn_radius_multi.argtypes = [vp, vp, vp, vp, i64, C.c_double, C.c_int, vp, vp, vp]
     L.sqmp_sample_configs.argtypes = [vp, C.c_uint64, i64, i64, dp, dp, C.c_int, vp, vp]
     L.sqmp_sample_configs_dev.argtypes = [vp, C.c_uint64, i64, i64, dp, dp, C.c_int, vp, vp, vp]
+    L.sqmp_sample_informed.argtypes = [vp, C.c_uint64, i64, i64, dp, dp, C.c_int, vp, vp, vp]
+    L.sqmp_sample_informed_dev.argtypes = [vp, C.c_uint64, i64, i64, dp, dp, C.c_int, vp, vp, vp, vp]
     L.sqmp_nn_nearest_dev.argtypes = [vp, C.c_int, vp, i64, vp, vp]
     L.sqmp_nn_radius_dev.argtypes = [vp, C.c_int, vp, vp, i64, C.c_double, C.c_int, vp, vp, vp, vp, vp]
     L.sqmp_kernel_launches.restype = i64
@@ -226,12 +228,18 @@ class Context:
         self._ck(self._L.sqmp_check_states(self._h, _ptr(q), S, flags, _ptr(mask)))
         return mask
 
-    def check_edges(self, q_start, q_end, num_points=20, flags=CHECK_MAP, want_first=True):
-        a = np.ascontiguousarray(q_start, dtype=np.float64).reshape(-1, DOF)
-        b = np.ascontiguousarray(q_end, dtype=np.float64).reshape(-1, DOF)
-        E = a.shape[0]
-        mask = np.zeros((E * (num_points + 1) + 31) // 32, dtype=np.uint32)
-        first = np.empty(E, dtype=np.int32) if want_first else None
+    def check_edges(self, q_start, q_end, num_points=20, flags=CHECK_MAP, want_first=True, out_mask=None, out_first=None):
+        """q_start / q_end: numpy arrays or pinned torch tensors [E, 8]; out_mask / out_first: optional pinned torch tensors
+        (int32) the results are written to — with pageable outputs every stage of the pipeline waits for its copies."""
+        if isinstance(q_start, np.ndarray) or not hasattr(q_start, "data_ptr"):
+            a = np.ascontiguousarray(q_start, dtype=np.float64).reshape(-1, DOF)
+            b = np.ascontiguousarray(q_end, dtype=np.float64).reshape(-1, DOF)
+            E = a.shape[0]
+        else:
+            a, b = q_start, q_end
+            E = a.numel() // DOF
+        mask = out_mask if out_mask is not None else np.zeros((E * (num_points + 1) + 31) // 32, dtype=np.uint32)
+        first = out_first if out_first is not None else (np.empty(E, dtype=np.int32) if want_first else None)
         self._ck(self._L.sqmp_check_edges(self._h, _ptr(a), _ptr(b), E, num_points, flags, _ptr(mask), _ptr(first)))
         return mask, first
 
@@ -284,6 +292,18 @@ class Context:
         dp = C.POINTER(C.c_double)
         self._ck(self._L.sqmp_sample_configs(self._h, int(seed), int(first), int(n), lo.ctypes.data_as(dp),
                                              hi.ctypes.data_as(dp), int(max_tries), _ptr(q), _ptr(tries)))
+        return q, tries
+
+    def sample_informed(self, seed, first, n, lo, hi, ellipse, max_tries=64):
+        """sampleJointConfigfromEllipse_JntArray (BS:3607-3829) batched on the device; ellipse: informed.InformedC."""
+        lo = np.ascontiguousarray(lo, dtype=np.float64).reshape(DOF)
+        hi = np.ascontiguousarray(hi, dtype=np.float64).reshape(DOF)
+        q = np.empty((n, DOF), dtype=np.float64)
+        tries = np.empty(n, dtype=np.int32)
+        dp = C.POINTER(C.c_double)
+        self._ck(self._L.sqmp_sample_informed(self._h, C.c_uint64(int(seed)), C.c_int64(int(first)), C.c_int64(int(n)),
+                                              lo.ctypes.data_as(dp), hi.ctypes.data_as(dp), int(max_tries), C.byref(ellipse),
+                                              _ptr(q), _ptr(tries)))
         return q, tries
 
     def sample_configs_dev(self, seed, first, n, lo, hi, max_tries, d_q, d_tries, stream=0):

@@ -1186,21 +1186,25 @@ int sqmp_check_edges_dev(sqmp_ctx *ctx, const double *d_a, const double *d_b, in
   const int64_t S = E * P1;
   if (!(flags & (SQMP_CHECK_SELF | SQMP_CHECK_MAP))) {
     CU(cudaMemsetAsync(d_mask, 0, size_t((S + 31) / 32) * 4, st));
+    if (d_first) CU(cudaMemsetAsync(d_first, 0xFF, size_t(E) * 4, st));   // -1: every edge valid
+    return SQMP_OK;
+  }
+  int nl = 0;
+  const bool fast = use_fast_k1(c, flags);
+  if (fast) {
+    // the fast kernel lowers first_invalid[e] itself (atomicMin on the unsigned view): preset to 0xFFFFFFFF = -1
+    if (d_first) CU(cudaMemsetAsync(d_first, 0xFF, size_t(E) * 4, st));
+    CU(launch_check_states_fast(c->rb_grid, c->gd, c->self, c->fast, c->kftab, d_a, d_b, num_points, S, flags, d_mask,
+                                c->chain_specialization != 0, !d_first && k1f_may_overlap(c, st), st, &nl, nullptr, d_first));
   } else {
-    int nl = 0;
-    const bool fast = use_fast_k1(c, flags);
-    if (fast)
-      CU(launch_check_states_fast(c->rb_grid, c->gd, c->self, c->fast, c->kftab, d_a, d_b, num_points, S, flags, d_mask,
-                                  c->chain_specialization != 0, k1f_may_overlap(c, st), st, &nl));
-    else
-      CU(launch_check_states(c->rb_grid, c->gd, c->self, c->d_k1slots, d_a, d_b, num_points, S, flags, d_mask, st, &nl));
-    c->launches += nl;
-    if (fast && !d_first) k1f_launched(c, st);
+    CU(launch_check_states(c->rb_grid, c->gd, c->self, c->d_k1slots, d_a, d_b, num_points, S, flags, d_mask, st, &nl));
+    if (d_first) {
+      CU(launch_first_invalid(d_mask, E, P1, d_first, st));
+      nl += 1;
+    }
   }
-  if (d_first) {
-    CU(launch_first_invalid(d_mask, E, P1, d_first, st));
-    c->launches += 1;
-  }
+  c->launches += nl;
+  if (fast && !d_first) k1f_launched(c, st);
   return SQMP_OK;
 }
 
@@ -1270,21 +1274,34 @@ int sqmp_check_edges(sqmp_ctx *ctx, const double *qa, const double *qb, int64_t 
     }
     return SQMP_OK;
   }
-  void *da, *db, *dm, *df;
-  int rc;
-  if ((rc = ensure(c, 0, size_t(E) * SQMP_DOF * 8, &da))) return rc;
-  if ((rc = ensure(c, 1, size_t(E) * SQMP_DOF * 8, &db))) return rc;
-  if ((rc = ensure(c, 2, size_t((S + 31) / 32) * 4, &dm))) return rc;
-  if ((rc = ensure(c, 3, size_t(E) * 4, &df))) return rc;
-  cudaStream_t st = c->streams[0];
-  CU(cudaMemcpyAsync(da, qa, size_t(E) * SQMP_DOF * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(db, qb, size_t(E) * SQMP_DOF * 8, cudaMemcpyHostToDevice, st));
-  rc = sqmp_check_edges_dev(ctx, (const double *)da, (const double *)db, E, num_points, flags, (uint32_t *)dm,
-                            first_invalid ? (int32_t *)df : nullptr, st);
-  if (rc) return rc;
-  CU(cudaMemcpyAsync(mask_out, dm, size_t((S + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
-  if (first_invalid) CU(cudaMemcpyAsync(first_invalid, df, size_t(E) * 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  // H2D -> kernel (+ first_invalid in its epilogue) -> D2H in stages over two streams: the copies of one stage overlap
+  // the kernel of the other.  A stage holds a multiple of 32 edges, so its first state starts a mask word.
+  const int P1 = num_points + 1;
+  int64_t ce = (c->pipeline_chunk / P1) / 32 * 32;
+  if (ce < 32) ce = 32;
+  if (ce > E) ce = (E + 31) / 32 * 32;
+  void *da[2], *db[2], *dm[2], *df[2];
+  for (int b = 0; b < 2; ++b) {
+    int rc;
+    if ((rc = ensure(c, b, size_t(ce) * 2 * SQMP_DOF * 8, &da[b]))) return rc;
+    db[b] = (char *)da[b] + size_t(ce) * SQMP_DOF * 8;
+    if ((rc = ensure(c, 2 + b, size_t(ce * P1 / 32 + 1) * 4, &dm[b]))) return rc;
+    if ((rc = ensure(c, 4 + b, size_t(ce) * 4, &df[b]))) return rc;
+  }
+  int b = 0;
+  for (int64_t e0 = 0; e0 < E; e0 += ce, b ^= 1) {
+    const int64_t n = E - e0 < ce ? E - e0 : ce;
+    cudaStream_t st = c->streams[b];
+    CU(cudaMemcpyAsync(da[b], qa + e0 * SQMP_DOF, size_t(n) * SQMP_DOF * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(db[b], qb + e0 * SQMP_DOF, size_t(n) * SQMP_DOF * 8, cudaMemcpyHostToDevice, st));
+    int rc = sqmp_check_edges_dev(ctx, (const double *)da[b], (const double *)db[b], n, num_points, flags, (uint32_t *)dm[b],
+                                  first_invalid ? (int32_t *)df[b] : nullptr, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(mask_out + e0 * P1 / 32, dm[b], size_t((n * P1 + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
+    if (first_invalid) CU(cudaMemcpyAsync(first_invalid + e0, df[b], size_t(n) * 4, cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(c->streams[0]));
+  CU(cudaStreamSynchronize(c->streams[1]));
   return SQMP_OK;
 }
 
@@ -1367,6 +1384,53 @@ int sqmp_sample_configs(sqmp_ctx *ctx, uint64_t seed, int64_t first, int64_t n, 
   if ((rc = ensure(c, 5, size_t(n) * 4, &dt))) return rc;
   cudaStream_t st = c->streams[0];
   rc = sqmp_sample_configs_dev(ctx, seed, first, n, lo, hi, max_tries, (double *)dq, (int32_t *)dt, st);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(q_out, dq, size_t(n) * SQMP_DOF * 8, cudaMemcpyDeviceToHost, st));
+  if (tries_out) CU(cudaMemcpyAsync(tries_out, dt, size_t(n) * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return SQMP_OK;
+}
+
+static bool informed_ok(const sqmp_informed *el) {
+  if (!el || el->n_rev < 0 || el->n_pri < 0 || el->n_rev + el->n_pri != SQMP_DOF) return false;
+  bool seen[SQMP_DOF] = {false};
+  for (int cls = 0; cls < 2; ++cls) {
+    const int n = cls ? el->n_rev : el->n_pri;
+    const int32_t *idx = cls ? el->rev_idx : el->pri_idx;
+    for (int a = 0; a < n; ++a) {
+      if (idx[a] < 0 || idx[a] >= SQMP_DOF || seen[idx[a]]) return false;
+      seen[idx[a]] = true;
+    }
+  }
+  return true;
+}
+int sqmp_sample_informed_dev(sqmp_ctx *ctx, uint64_t seed, int64_t first, int64_t n, const double lo[SQMP_DOF],
+                             const double hi[SQMP_DOF], int max_tries, const sqmp_informed *ellipse, double *d_q_out,
+                             int32_t *d_tries_out, void *stream) {
+  CHECK_CTX();
+  if (n < 0 || first < 0 || max_tries < 1 || max_tries > 65536 || !lo || !hi || (n > 0 && !d_q_out) || !informed_ok(ellipse))
+    return fail(c, SQMP_ERR_INVALID, "sample_informed: bad argument");
+  for (int j = 0; j < SQMP_DOF; ++j)
+    if (!(lo[j] <= hi[j]) || !std::isfinite(lo[j]) || !std::isfinite(hi[j]))
+      return fail(c, SQMP_ERR_INVALID, "sample_informed: limits must be finite with lo <= hi");
+  if (n == 0) return SQMP_OK;
+  CU(launch_sample_informed(c->rb, seed, first, n, lo, hi, max_tries, *ellipse, d_q_out, d_tries_out, c->chain_specialization != 0,
+                            (cudaStream_t)stream));
+  c->launches += 1;
+  return SQMP_OK;
+}
+int sqmp_sample_informed(sqmp_ctx *ctx, uint64_t seed, int64_t first, int64_t n, const double lo[SQMP_DOF],
+                         const double hi[SQMP_DOF], int max_tries, const sqmp_informed *ellipse, double *q_out,
+                         int32_t *tries_out) {
+  CHECK_CTX();
+  if (n > 0 && !q_out) return fail(c, SQMP_ERR_INVALID, "sample_informed: null pointer");
+  if (n <= 0) return n == 0 ? SQMP_OK : fail(c, SQMP_ERR_INVALID, "sample_informed: bad argument");
+  void *dq, *dt;
+  int rc;
+  if ((rc = ensure(c, 0, size_t(n) * SQMP_DOF * 8, &dq))) return rc;
+  if ((rc = ensure(c, 5, size_t(n) * 4, &dt))) return rc;
+  cudaStream_t st = c->streams[0];
+  rc = sqmp_sample_informed_dev(ctx, seed, first, n, lo, hi, max_tries, ellipse, (double *)dq, (int32_t *)dt, st);
   if (rc) return rc;
   CU(cudaMemcpyAsync(q_out, dq, size_t(n) * SQMP_DOF * 8, cudaMemcpyDeviceToHost, st));
   if (tries_out) CU(cudaMemcpyAsync(tries_out, dt, size_t(n) * 4, cudaMemcpyDeviceToHost, st));

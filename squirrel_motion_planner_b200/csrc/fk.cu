@@ -228,6 +228,74 @@ k5_sample(const __grid_constant__ RobotDev rb, const __grid_constant__ SampleBox
   if (tries_out) tries_out[i] = used;
 }
 
+// sampleJointConfigfromEllipse_JntArray (BS:3607-3829), one thread per sample; same counter stream as k5_sample with nine
+// outputs per try (eight joint draws + the scale).  Arithmetic order documented in include/sqmp_b200.h.
+template <typename SIG>
+__global__ void __launch_bounds__(128)
+k5_sample_informed(const __grid_constant__ RobotDev rb, const __grid_constant__ SampleBox box, const __grid_constant__ sqmp_informed el,
+                   uint64_t seed, int64_t first, int64_t n, int max_tries, double *__restrict__ q_out,
+                   int32_t *__restrict__ tries_out) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double q[SQMP_DOF], o[7];
+  int used = -max_tries;
+  const bool unconfined = el.env_x[0] == 0.0 && el.env_x[1] == 0.0 && el.env_y[0] == 0.0 && el.env_y[1] == 0.0;
+  for (int t = 0; t < max_tries; ++t) {
+    const uint64_t k0 = (uint64_t(first + i) * uint64_t(max_tries) + uint64_t(t)) * 9ull;
+    double ball[SQMP_DOF];
+#pragma unroll
+    for (int j = 0; j < SQMP_DOF; ++j) {
+      const double u = __dmul_rn(double(splitmix_at(seed, k0 + j) >> 11), 1.0 / 9007199254740992.0);
+      ball[j] = __dadd_rn(box.lo[j], __dmul_rn(__dsub_rn(box.hi[j], box.lo[j]), u));
+    }
+    const double scale = __dmul_rn(double(splitmix_at(seed, k0 + 8) >> 11), 1.0 / 9007199254740992.0);
+    int out_idx = 0;
+    for (int cls = 0; cls < 2; ++cls) {   // prismatic joints first, then revolute ones (BS:3773-3785)
+      const int nc = cls == 0 ? el.n_pri : el.n_rev;
+      const int *idx = cls == 0 ? el.pri_idx : el.rev_idx;
+      const double *Cm = cls == 0 ? el.c_pri : el.c_rev;
+      const double *cen = cls == 0 ? el.center_pri : el.center_rev;
+      const double *L = cls == 0 ? el.l_pri : el.l_rev;
+      double sum = 0.0, y[SQMP_DOF];
+      for (int a = 0; a < nc; ++a) sum = __dadd_rn(sum, __dmul_rn(ball[idx[a]], ball[idx[a]]));
+      const double norm = sqrt(sum);
+      for (int a = 0; a < nc; ++a)   // L (scale * v / |v|)
+        y[a] = __dmul_rn(a == 0 ? L[0] : L[1], __dmul_rn(scale, __ddiv_rn(ball[idx[a]], norm)));
+      for (int r = 0; r < nc; ++r) {
+        double acc = 0.0;
+        for (int a = 0; a < nc; ++a) acc = __dadd_rn(acc, __dmul_rn(Cm[r * nc + a], y[a]));
+        q[out_idx++] = __dadd_rn(acc, cen[r]);
+      }
+    }
+    fk_one<double, SIG>(rb, q, o);
+    const bool inside = unconfined || (q[0] < el.env_x[1] && q[0] > el.env_x[0] && q[1] < el.env_y[1] && q[1] > el.env_y[0]);
+    if (0.0 <= o[2] && inside) {
+      used = t + 1;
+      break;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < SQMP_DOF; ++j) q_out[i * SQMP_DOF + j] = q[j];
+  if (tries_out) tries_out[i] = used;
+}
+
+cudaError_t launch_sample_informed(const RobotDev &rb, uint64_t seed, int64_t first, int64_t n, const double *lo, const double *hi,
+                                   int max_tries, const sqmp_informed &el, double *d_q_out, int32_t *d_tries_out,
+                                   bool allow_specialized, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  SampleBox box;
+  for (int j = 0; j < SQMP_DOF; ++j) {
+    box.lo[j] = lo[j];
+    box.hi[j] = hi[j];
+  }
+  const unsigned blocks = unsigned((n + 127) / 128);
+  if (allow_specialized && chain_matches<SigRobotino>(rb))
+    k5_sample_informed<SigRobotino><<<blocks, 128, 0, st>>>(rb, box, el, seed, first, n, max_tries, d_q_out, d_tries_out);
+  else
+    k5_sample_informed<SigGeneric><<<blocks, 128, 0, st>>>(rb, box, el, seed, first, n, max_tries, d_q_out, d_tries_out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_sample(const RobotDev &rb, uint64_t seed, int64_t first, int64_t n, const double *lo, const double *hi,
                           int max_tries, double *d_q_out, int32_t *d_tries_out, bool allow_specialized, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;

@@ -202,6 +202,9 @@ cudaError_t launch_fk(const RobotDev &rb, const double *d_q, int64_t S, double *
                       bool allow_specialized, cudaStream_t st);
 cudaError_t launch_sample(const RobotDev &rb, uint64_t seed, int64_t first, int64_t n, const double *lo, const double *hi,
                           int max_tries, double *d_q_out, int32_t *d_tries_out, bool allow_specialized, cudaStream_t st);
+cudaError_t launch_sample_informed(const RobotDev &rb, uint64_t seed, int64_t first, int64_t n, const double *lo, const double *hi,
+                                   int max_tries, const sqmp_informed &el, double *d_q_out, int32_t *d_tries_out,
+                                   bool allow_specialized, cudaStream_t st);
 cudaError_t launch_slab_build(const uint32_t *d_occ, int row_words, int gx, int gy, int gz, int halo, int window,
                               int n_slabs, const int *h_k0, const int *h_k1, uint32_t *d_col, int8_t *d_tmp, uint8_t *d_slab,
                               cudaStream_t st, int *n_launch);
@@ -211,7 +214,8 @@ cudaError_t launch_ft_build(const uint32_t *d_occ, int row_words, int gx, int gy
 cudaError_t launch_check_states_fast(const RobotDev &rb, const GridDev &gd, const SelfDev &self, const FastDev &fd,
                                      const KfTab &tab, const double *d_q, const double *d_q_end, int num_points, int64_t S,
                                      unsigned flags, uint32_t *d_mask, bool allow_specialized, bool overlap,
-                                     cudaStream_t st, int *n_launch, const PeerDev *peers = nullptr);
+                                     cudaStream_t st, int *n_launch, const PeerDev *peers = nullptr,
+                                     int32_t *d_first_invalid = nullptr);
 cudaError_t launch_gather_signal(const PeerDev &peer, cudaStream_t st);
 cudaError_t launch_gather_wait(const uint32_t *d_flags, int n, unsigned step, int32_t *d_status, cudaStream_t st);
 cudaError_t launch_pack_rows(const uint32_t *d_bits_linear, int gx, int gy, int gz, int row_words, uint32_t *d_occ,

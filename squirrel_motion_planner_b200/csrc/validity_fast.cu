@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(KF_THREADS, SELF ? (512 / KF_THREADS) : KF_MIN
 k1_fast(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd, const __grid_constant__ SelfDev self,
         const __grid_constant__ FastDev fd, const __grid_constant__ KfTab tab, const __grid_constant__ PeerDev peer,
         const double *__restrict__ q_in, const double *__restrict__ q_end, int num_points, int64_t S,
-        uint32_t *__restrict__ mask_out) {
+        uint32_t *__restrict__ mask_out, uint32_t *__restrict__ first_invalid) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NW = KF_THREADS / 32;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -447,6 +447,17 @@ k1_fast(const __grid_constant__ RobotDev rb, const __grid_constant__ GridDev gd,
   // waiting here — until every prerequisite grid has completed and flushed — keeps back-to-back calls that reuse one
   // mask buffer equivalent to serial execution.  (A no-op when the grid was launched without the attribute.)
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (EDGES && first_invalid != nullptr && word != 0) {
+    // isEdgeValid's early exit (BS:6866-6874) in the same pass: lane j looks at the j-th edge that overlaps this warp's 32
+    // states and lowers first_invalid[e] (preset to 0xFFFFFFFF = -1 by the host) to the first colliding state it sees
+    const int P1 = num_points + 1;
+    const int64_t s0 = s - lane, e = s0 / P1 + lane;
+    const int64_t b0 = max(e * P1, s0) - s0, b1 = min((e + 1) * P1, s0 + 32) - s0;
+    if (b0 < b1) {
+      const unsigned m = word & (b1 - b0 >= 32 ? ~0u : (((1u << int(b1 - b0)) - 1u) << int(b0)));
+      if (m) atomicMin(first_invalid + e, unsigned(s0 + (__ffs(m) - 1) - e * P1));
+    }
+  }
   if (peer.n == 0) {
     if (lane == 0 && s < ((S + 31) & ~int64_t(31))) mask_out[s >> 5] = word;
     return;
@@ -502,7 +513,7 @@ extern "C" int sqmp_debug_kf_stats(unsigned long long *out, int reset) {
 cudaError_t launch_check_states_fast(const RobotDev &rb, const GridDev &gd, const SelfDev &self, const FastDev &fd,
                                      const KfTab &tab, const double *d_q, const double *d_q_end, int num_points, int64_t S,
                                      unsigned flags, uint32_t *d_mask, bool allow_specialized, bool overlap,
-                                     cudaStream_t st, int *n_launch, const PeerDev *peers) {
+                                     cudaStream_t st, int *n_launch, const PeerDev *peers, int32_t *d_first_invalid) {
   const bool with_self = (flags & SQMP_CHECK_SELF) != 0;
   size_t smem = kf_smem_base();
   if (with_self) smem += size_t(12) * rb.n_frames * KF_THREADS * sizeof(float);
@@ -525,7 +536,8 @@ cudaError_t launch_check_states_fast(const RobotDev &rb, const GridDev &gd, cons
     attr[0].val.programmaticStreamSerializationAllowed = overlap ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    err = cudaLaunchKernelEx(&cfg, kern, rb, gd, self, fd, tab, pd, d_q, d_q_end, d_q_end ? num_points : 0, S, d_mask);
+    err = cudaLaunchKernelEx(&cfg, kern, rb, gd, self, fd, tab, pd, d_q, d_q_end, d_q_end ? num_points : 0, S, d_mask,
+                             reinterpret_cast<uint32_t *>(d_first_invalid));
   };
   if (allow_specialized && chain_matches<SigRobotino>(rb)) {   // structure of the chain known at compile time (the reference's robot)
     if (d_q_end) {

@@ -35,6 +35,10 @@ class GpuBackend {
   void sample_batch(uint64_t seed, long long first, int n, const double *lo, const double *hi, int max_tries, double *q_out) {
     ok(sqmp_sample_configs(ctx_, seed, first, n, lo, hi, max_tries, q_out, NULL));
   }
+  void sample_informed_batch(uint64_t seed, long long first, int n, const double *lo, const double *hi, int max_tries,
+                             const sqmp_informed &el, double *q_out) {
+    ok(sqmp_sample_informed(ctx_, seed, first, n, lo, hi, max_tries, &el, q_out, NULL));
+  }
   bool config_valid(const double *q) {
     uint32_t w = 1;
     if (flags_ == 0) return true;

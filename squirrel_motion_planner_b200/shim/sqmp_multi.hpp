@@ -111,6 +111,10 @@ class GpuService {
   int sample(uint64_t seed, long long first, int n, const double *lo, const double *hi, int max_tries, double *q_out) {
     return sqmp_sample_configs(ctx_, seed, first, n, lo, hi, max_tries, q_out, NULL);
   }
+  int sample_informed(uint64_t seed, long long first, int n, const double *lo, const double *hi, int max_tries, const sqmp_informed &el,
+                      double *q_out) {
+    return sqmp_sample_informed(ctx_, seed, first, n, lo, hi, max_tries, &el, q_out, NULL);
+  }
   int nearest_multi(const int32_t *tree, const double *q, int64_t n, int32_t *ids) { return sqmp_nn_nearest_multi(ctx_, tree, q, n, ids); }
   int radius_multi(const int32_t *tree, const double *q, const int32_t *excl, int64_t n, double r, int k, int32_t *low,
                    int32_t *high, int32_t *cnt) {
@@ -146,6 +150,10 @@ class FiberBackendT {
   void tree_update(int slot, int id, const double *q, double cost) { ok(svc_->tree_update(2 * index_ + slot, id, q, cost)); }
   void sample_batch(uint64_t seed, long long first, int n, const double *lo, const double *hi, int max_tries, double *q_out) {
     ok(svc_->sample(seed, first, n, lo, hi, max_tries, q_out));   // once per 256 iterations: not batched
+  }
+  void sample_informed_batch(uint64_t seed, long long first, int n, const double *lo, const double *hi, int max_tries,
+                             const sqmp_informed &el, double *q_out) {
+    ok(svc_->sample_informed(seed, first, n, lo, hi, max_tries, el, q_out));   // redrawn when the best cost changes: not batched
   }
   inline int nearest(int slot, const double *q);
   inline void near(int slot, const double *q, int exclude_id, double r, int k, std::vector<int> &low, std::vector<int> &high, int &count);

@@ -66,9 +66,9 @@ int main(int argc, char **argv) {
         continue;
       }
       const sqmp_planner::Stats &s = res[size_t(t)][j].stats;
-      std::printf("%zu %d %.17g %ld %ld %ld %ld %ld %ld %ld %ld %ld %ld %llu\n", a.first + k, int(s.solved), s.best_cost, s.iterations,
+      std::printf("%zu %d %.17g %ld %ld %ld %ld %ld %ld %ld %ld %ld %ld %llu %.17g %.17g %ld %ld\n", a.first + k, int(s.solved), s.best_cost, s.iterations,
                   s.nn_calls, s.near_calls, s.edge_batches, s.edges_checked, s.states_checked, s.rewires, s.parents_chosen,
-                  s.nodes_start, s.nodes_goal, (unsigned long long)s.trace);
+                  s.nodes_start, s.nodes_goal, (unsigned long long)s.trace, s.best_cost_rev, s.best_cost_pri, s.informed_samples, s.solution_rewires);
       total_states += s.states_checked;
       total_iter += s.iterations;
     }

@@ -32,6 +32,7 @@
 #include <vector>
 
 #include "sqmp_b200.h"
+#include "sqmp_informed.hpp"
 
 #ifdef SQMP_SHIM_USE_REFERENCE_STRUCTS
 #include <planner_data_structures/data_structs.h>
@@ -271,7 +272,26 @@ class CollisionChecker {
  public:
   // CC:66-74 / 156-172: the reference builds its link model from the URDF/SRDF on the parameter server; here the
   // pre-folded description comes from a file (tools/export_robot_desc.py).  Failure leaves the checker uninitialised.
-  explicit CollisionChecker(const std::string &desc_path, int device = 0) : ctx_(NULL), initialized_(false) {
+  // CC:66-74 as the reference calls it — `new CollisionChecker()` (BS:73): the description path comes from
+  // setDescriptionPath() (the analogue of the robot_description ROS parameter the reference reads, CC:178) or the
+  // SQMP_ROBOT_DESC environment variable, the device from SQMP_DEVICE (default 0).
+  CollisionChecker() : ctx_(NULL), initialized_(false) {
+    const char *env = std::getenv("SQMP_ROBOT_DESC"), *dev = std::getenv("SQMP_DEVICE");
+    const std::string path = !description_path().empty() ? description_path() : std::string(env ? env : "");
+    if (path.empty()) {
+      std::fprintf(stderr, "CollisionChecker: no robot description (CollisionChecker::setDescriptionPath / SQMP_ROBOT_DESC)\n");
+      return;
+    }
+    open(path, dev ? std::atoi(dev) : 0);
+  }
+  static void setDescriptionPath(const std::string &path) { description_path() = path; }
+  explicit CollisionChecker(const std::string &desc_path, int device = 0) : ctx_(NULL), initialized_(false) { open(desc_path, device); }
+ private:
+  static std::string &description_path() {
+    static std::string p;
+    return p;
+  }
+  void open(const std::string &desc_path, int device) {
     std::string err;
     if (!robot_.load(desc_path, &err)) {
       std::fprintf(stderr, "CollisionChecker: %s\n", err.c_str());
@@ -286,6 +306,7 @@ class CollisionChecker {
     initialized_ = true;
     setDisabledLinkMapCollisions(std::vector<std::string>());
   }
+ public:
   ~CollisionChecker() { sqmp_destroy(ctx_); }
 
   bool isInitialized() const { return initialized_; }
@@ -407,6 +428,38 @@ class HotPath {
     return !collisionChecker->isInCollision(config, check_self_collision, check_map_collision);
   }
 
+  // BS:6901-6908: the KDL::JntArray overload — any array type with rows() and operator()(i) (SP:763-839 call sites)
+  template <class JntArrayT>
+  auto isConfigValid(const JntArrayT &config, bool check_self_collision, bool check_map_collision)
+      -> decltype(config.rows(), config(0), bool()) {
+    std::vector<double> v(size_t(config.rows()));
+    for (size_t i = 0; i < v.size(); ++i) v[i] = config(static_cast<unsigned int>(i));
+    return isConfigValid(v, check_self_collision, check_map_collision);
+  }
+
+  // BS:4162-4242 compute_edge_cost_interpolation: {total, revolute, prismatic}; the total weights every squared
+  // coordinate difference with m_edge_cost_weights (BS:109-113: all 1.0 unless set), the other two do not.
+  // m_joint_is_revolute stands for the reference's getTypeName() == "RotAxis" test on the KDL chain (BS:4193, 4203).
+  std::vector<double> compute_edge_cost_interpolation(const std::vector<std::vector<double> > &joint_traj) const {
+    std::vector<double> cost_list(3, 0.0);
+    for (size_t wp = 0; wp + 1 < joint_traj.size(); ++wp) {
+      double wp_dist_total = 0.0, wp_dist_rot = 0.0, wp_dist_prism = 0.0;
+      for (size_t joint_idx = 0; joint_idx < joint_traj[wp].size() && joint_idx < size_t(SQMP_DOF); ++joint_idx) {
+        const double coordinate_dist = (joint_traj[wp + 1][joint_idx] - joint_traj[wp][joint_idx]) *
+                                       (joint_traj[wp + 1][joint_idx] - joint_traj[wp][joint_idx]);
+        wp_dist_total += coordinate_dist * m_edge_cost_weights[joint_idx];
+        if (m_joint_is_revolute[joint_idx]) wp_dist_rot += coordinate_dist;
+        else wp_dist_prism += coordinate_dist;
+      }
+      cost_list[0] += std::sqrt(wp_dist_total);
+      cost_list[1] += std::sqrt(wp_dist_rot);
+      cost_list[2] += std::sqrt(wp_dist_prism);
+    }
+    return cost_list;
+  }
+  double m_edge_cost_weights[SQMP_DOF] = {1, 1, 1, 1, 1, 1, 1, 1};
+  int m_joint_is_revolute[SQMP_DOF] = {0, 0, 1, 1, 1, 1, 1, 1};   // x, y prismatic; theta and the five arm joints revolute (URDF:30-66, 615-759)
+
   // BS:6864-6876
   bool isEdgeValid(const Edge &tree_edge, bool check_self_collision, bool check_map_collision) {
     int unused = 0;
@@ -493,6 +546,61 @@ class HotPath {
     return out;
   }
 
+  // ---- the two search functions with the reference's EXACT signatures (birrt_star.h:322-325): no slot argument and no
+  //      mirror calls at insertNode / rewire / recursiveNodeCostUpdate.  The device mirror of `tree` is brought up to
+  //      date lazily, right before the search, from a host shadow of what it holds: nodes appended since the last call
+  //      go up in one batch, nodes whose config or cost_reach.total changed (rewire, BS:5173-5193; cost propagation,
+  //      BS:5518-5520) are rewritten, a tree that shrank (reset_planner, BS:1411-1619) is rebuilt.  The scan is one
+  //      pass over the host tree — less work than the reference's own O(N) distance loop it replaces.
+  Node find_nearest_neighbour_interpolation(Rrt_star_tree *tree, std::vector<double> x_rand) {
+    const int slot = sync_mirror(tree);
+    if (slot < 0) return tree->nodes.empty() ? Node() : tree->nodes[0];
+    return find_nearest_neighbour_interpolation(tree, slot, x_rand);
+  }
+  std::vector<int> find_near_vertices_interpolation(Rrt_star_tree *tree, Node x_new) {
+    const int slot = sync_mirror(tree);
+    if (slot < 0) return std::vector<int>();
+    return find_near_vertices_interpolation(tree, slot, x_new);
+  }
+  // device tree slot of a host tree (assigned on first use), or -1 when the mirror could not be updated
+  int sync_mirror(const Rrt_star_tree *tree) {
+    Mirror &m = mirrors_[tree];
+    if (m.slot < 0) m.slot = next_slot_++;
+    sqmp_ctx *c = collisionChecker->context();
+    const size_t n = tree->nodes.size();
+    if (n < m.cost.size()) {   // the planner was reset: start over
+      if (sqmp_tree_reset(c, m.slot) != SQMP_OK) return -1;
+      m.q.clear();
+      m.cost.clear();
+    }
+    for (size_t i = 0; i < m.cost.size(); ++i) {   // rewired nodes / propagated costs
+      const Node &nd = tree->nodes[i];
+      bool same = nd.cost_reach.total == m.cost[i];
+      for (int j = 0; same && j < SQMP_DOF; ++j) same = nd.config[size_t(j)] == m.q[i * SQMP_DOF + size_t(j)];
+      if (same) continue;
+      if (sqmp_tree_update(c, m.slot, int32_t(i), nd.config.data(), nd.cost_reach.total) != SQMP_OK) return -1;
+      for (int j = 0; j < SQMP_DOF; ++j) m.q[i * SQMP_DOF + size_t(j)] = nd.config[size_t(j)];
+      m.cost[i] = nd.cost_reach.total;
+    }
+    if (n > m.cost.size()) {   // appended nodes (insertNode, BS:3298-3322), one batch
+      const size_t first = m.cost.size();
+      m.q.resize(n * SQMP_DOF);
+      m.cost.resize(n);
+      for (size_t i = first; i < n; ++i) {
+        for (int j = 0; j < SQMP_DOF; ++j) m.q[i * SQMP_DOF + size_t(j)] = tree->nodes[i].config[size_t(j)];
+        m.cost[i] = tree->nodes[i].cost_reach.total;
+      }
+      int32_t first_id = -1;
+      if (sqmp_tree_append_batch(c, m.slot, &m.q[first * SQMP_DOF], &m.cost[first], int64_t(n - first), &first_id) != SQMP_OK ||
+          first_id != int32_t(first)) {
+        m.q.resize(first * SQMP_DOF);
+        m.cost.resize(first);
+        return -1;
+      }
+    }
+    return m.slot;
+  }
+
   // KM:278-305: [x y z qx qy qz qw] of the SRDF chain tip (hand_wrist_link).
   std::vector<double> compute_FK(const std::vector<double> &chain_config) {
     std::vector<double> pose(7, 0.0);
@@ -528,11 +636,36 @@ class HotPath {
     return std::vector<double>(q, q + SQMP_DOF);
   }
 
+  // BS:3607-3829 sampleJointConfigfromEllipse (informed sampling once a solution exists, BS:1168): the ellipse is set up
+  // from start and goal like jointConfigEllipseInitialization (BS:3472-3604); samples are drawn on the device.
+  void jointConfigEllipseInitialization(const std::vector<double> &config_start, const std::vector<double> &config_goal) {
+    ellipse_.init(config_start.data(), config_goal.data(), m_joint_is_revolute);
+    informed_next_ = 0;
+  }
+  std::vector<double> sampleJointConfigfromEllipse_Vector(double cost_best_revolute, double cost_best_prismatic) {
+    sqmp_informed el;
+    ellipse_.fill(el, cost_best_revolute, cost_best_prismatic, sample_lo_, sample_hi_);
+    std::vector<double> q(SQMP_DOF, 0.0);
+    if (sqmp_sample_informed(collisionChecker->context(), sample_seed_ + 0x5851f42d4c957f2dull, informed_next_, 1, sample_lo_, sample_hi_,
+                             64, &el, q.data(), NULL) != SQMP_OK)
+      return std::vector<double>();
+    informed_next_ += 1;
+    return q;
+  }
+
   CollisionChecker *collisionChecker;   // same member name as birrt_star.h
   double m_near_threshold_interpolation;
   int m_max_near_nodes;
 
  private:
+  struct Mirror {   // what the device tree of one host tree holds
+    int slot = -1;
+    std::vector<double> q, cost;
+  };
+  std::map<const Rrt_star_tree *, Mirror> mirrors_;
+  int next_slot_ = 0;
+  InformedEllipse ellipse_;
+  int64_t informed_next_ = 0;
   std::vector<double> scratch_q_;
   std::vector<uint32_t> scratch_mask_;
   double sample_lo_[SQMP_DOF] = {0}, sample_hi_[SQMP_DOF] = {0};

@@ -46,7 +46,8 @@ int main(int argc, char **argv) {
     return 2;
   }
   const std::string dir = std::string(argv[2]) + "/";
-  sqmp_shim::CollisionChecker *collisionChecker = new sqmp_shim::CollisionChecker(argv[1]);   // BS:73
+  sqmp_shim::CollisionChecker::setDescriptionPath(argv[1]);
+  sqmp_shim::CollisionChecker *collisionChecker = new sqmp_shim::CollisionChecker();   // BS:73, literally
   if (!collisionChecker->isInitialized()) {
     // fail-closed behaviour of an uninitialised checker (CC:106-107)
     std::printf("uninitialised: isInCollision -> %d\n", int(collisionChecker->isInCollision(std::vector<double>(8, 0.0), true, true)));
@@ -160,6 +161,68 @@ int main(int argc, char **argv) {
     planner.updateNode(0, moved);
     std::vector<int32_t> after(1, planner.find_nearest_neighbour_interpolation(&tree, 0, moved.config).node_id);
     write_raw(dir + "out_nearest_after_update.i32", after);
+  }
+
+  // ---- the reference's exact signatures (BH:322-325): no slot, no mirror calls; the host tree is mutated like the
+  //      planner mutates it (append = insertNode, move = rewire, cost change = recursiveNodeCostUpdate, clear = reset) ----
+  {
+    Rrt_star_tree t2;
+    t2.name = "GOAL";
+    std::vector<int32_t> lit;
+    auto query_all = [&]() {
+      for (size_t k = 0; k * 8 < queries.size() && k < 24; ++k) {
+        const std::vector<double> x(queries.begin() + k * 8, queries.begin() + k * 8 + 8);
+        const Node nn = planner.find_nearest_neighbour_interpolation(&t2, x);
+        lit.push_back(nn.node_id);
+        const std::vector<int> near = planner.find_near_vertices_interpolation(&t2, t2.nodes[size_t(nn.node_id)]);
+        lit.push_back(int32_t(near.size()));
+        lit.insert(lit.end(), near.begin(), near.end());
+      }
+    };
+    for (size_t n = 0; n < cost.size() / 2; ++n) t2.nodes.push_back(tree.nodes[n]);
+    query_all();                                                        // phase 0: first half of the tree
+    for (size_t n = cost.size() / 2; n < cost.size(); ++n) t2.nodes.push_back(tree.nodes[n]);
+    query_all();                                                        // phase 1: appended nodes
+    for (size_t n = 5; n < t2.nodes.size(); n += 7) {                   // phase 2: rewires + cost propagation
+      t2.nodes[n].config.assign(queries.begin() + (n % 16) * 8, queries.begin() + (n % 16) * 8 + 8);
+      t2.nodes[n].cost_reach.total *= 0.5;
+    }
+    query_all();
+    t2.nodes.resize(40);                                                // phase 3: planner reset, a shorter tree
+    query_all();
+    write_raw(dir + "out_literal.i32", lit);
+    // isConfigValid(JntArray-like) (BS:6901-6908) and compute_edge_cost_interpolation (BS:4162-4242)
+    struct JntArrayLike {
+      std::vector<double> d;
+      unsigned int rows() const { return static_cast<unsigned int>(d.size()); }
+      double operator()(unsigned int i) const { return d[i]; }
+    };
+    std::vector<uint8_t> jv;
+    std::vector<double> ec;
+    planner.m_edge_cost_weights[1] = 0.5;
+    planner.m_edge_cost_weights[4] = 3.0;
+    for (size_t s = 0; s + 21 <= S && s < 21 * 40; s += 21) {
+      JntArrayLike ja;
+      ja.d.assign(states.begin() + s * 8, states.begin() + s * 8 + 8);
+      jv.push_back(planner.isConfigValid(ja, true, true) ? 1 : 0);
+      std::vector<std::vector<double> > traj;
+      for (size_t k = 0; k < 21; ++k) traj.push_back(std::vector<double>(states.begin() + (s + k) * 8, states.begin() + (s + k) * 8 + 8));
+      const std::vector<double> c3 = planner.compute_edge_cost_interpolation(traj);
+      ec.insert(ec.end(), c3.begin(), c3.end());
+    }
+    write_raw(dir + "out_jntarray_valid.u8", jv);
+    write_raw(dir + "out_edge_cost.f64", ec);
+    // informed sampler through the reference-named members
+    const double ilo[8] = {-5.0, -4.0, -3.0, -1.2, -1.7, -1.8, -2.4, -2.9}, ihi[8] = {5.0, 6.0, 3.0, 1.5, 2.6, 1.8, 2.4, 2.9};
+    planner.setSamplingBox(std::vector<double>(ilo, ilo + 8), std::vector<double>(ihi, ihi + 8), 424242ull);
+    planner.jointConfigEllipseInitialization(std::vector<double>(states.begin(), states.begin() + 8),
+                                             std::vector<double>(states.begin() + 8 * 500, states.begin() + 8 * 501));
+    std::vector<double> inf;
+    for (int i = 0; i < 40; ++i) {
+      const std::vector<double> q = planner.sampleJointConfigfromEllipse_Vector(9.0, 14.0);
+      inf.insert(inf.end(), q.begin(), q.end());
+    }
+    write_raw(dir + "out_informed.f64", inf);
   }
 
   // ---- compute_FK (KM:278-305) ----

@@ -130,3 +130,41 @@ def test_cpp_shim_against_oracle(tmp_path, fixture_data, orc, small_world):
     lo = np.array([-5.0, -4.0, -3.0, -1.2, -1.7, -1.8, -2.4, -2.9]); hi = np.array([5.0, 6.0, 3.0, 1.5, 2.6, 1.8, 2.4, 2.9])
     want, _ = orc.sample_configs(20240607, 0, 600, lo, hi, 64)
     assert np.array_equal(samples, want)
+
+    # ---- the reference's exact signatures over a lazily mirrored host tree (BH:322-325; no slot, no mirror calls) ----
+    lit = np.fromfile(os.path.join(d, "out_literal.i32"), dtype=np.int32)
+    half = len(cost) // 2
+    t_nodes, t_cost = nodes.copy(), cost.copy()
+    phases = [(t_nodes[:half].copy(), t_cost[:half].copy()), (t_nodes.copy(), t_cost.copy())]
+    for n in range(5, len(cost), 7):                                            # the rewires + cost changes of test_shim.cpp
+        t_nodes[n] = queries[n % 16]
+        t_cost[n] *= 0.5
+    phases += [(t_nodes.copy(), t_cost.copy()), (t_nodes[:40].copy(), t_cost[:40].copy())]
+    off = 0
+    for pn, pc in phases:
+        for k in range(24):
+            want_nn = int(oracle.nearest(pn, queries[k:k + 1])[0])
+            assert lit[off] == want_nn
+            n = int(lit[off + 1]); got = lit[off + 2:off + 2 + n]; off += 2 + n
+            want = oracle.near_vertices(pn, pc, pn[want_nn], want_nn, 1.5)
+            assert n == len(want) and np.array_equal(got[:20], want[:20]) and np.array_equal(got[-20:], want[-20:])
+    assert off == len(lit)
+    # isConfigValid(JntArray-like) (BS:6901-6908), compute_edge_cost_interpolation with weights (BS:4162-4242)
+    jv = rd_u8("out_jntarray_valid.u8")
+    first = q[0:21 * 40:21]
+    ref_mask, cm, cs = orc.check_states(first, oracle.FLAG_MAP | oracle.FLAG_SELF, clearance=True)
+    ref = np.unpackbits(ref_mask.view(np.uint8), bitorder="little")[:len(first)].astype(bool)
+    assert not np.any((jv[:len(first)] == ref) & (np.abs(np.minimum(cm, cs)) > BAND))      # valid == not in collision
+    ec = np.fromfile(os.path.join(d, "out_edge_cost.f64")).reshape(-1, 3)
+    wts = np.ones(8); wts[1] = 0.5; wts[4] = 3.0
+    for e in range(len(ec)):
+        assert np.array_equal(ec[e], oracle.edge_cost(q[e * 21:(e + 1) * 21], syn.IS_REVOLUTE, wts))       # bit for bit
+    # informed sampler through jointConfigEllipseInitialization / sampleJointConfigfromEllipse_Vector
+    from squirrel_motion_planner_b200 import informed
+    el = informed.ellipse_init(q[0], q[500], syn.IS_REVOLUTE)
+    lo[2], hi[2] = -3.0, 3.0
+    es = informed.ctypes_struct(el, 9.0, 14.0, (lo[0], hi[0]), (lo[1], hi[1]))
+    want_inf, _ = orc.sample_informed((424242 + 0x5851f42d4c957f2d) & ((1 << 64) - 1), 0, 40, lo, hi, es, 64)
+    got_inf = np.fromfile(os.path.join(d, "out_informed.f64")).reshape(-1, 8)
+    assert np.array_equal(got_inf, want_inf)
+

@@ -228,6 +228,39 @@ def test_sample_configs_bit_exact_and_order_free(ctx, orc, specialized):
         ctx.set_option("chain_specialization", 1)
 
 
+@pytest.mark.parametrize("specialized", [1, 0])
+def test_informed_sampler_bit_exact(ctx, orc, specialized):
+    """sqmp_sample_informed (sampleJointConfigfromEllipse_JntArray, BS:3607-3829) == the oracle's restatement, double for
+    double: same counter stream, same operation order; narrow and wide ellipses, a confined and an unconfined environment."""
+    from squirrel_motion_planner_b200 import informed
+    lo = np.array([-5.0, -4.0, -np.pi, -1.2, -1.7, -1.8, -2.4, -2.9])
+    hi = np.array([5.0, 6.0, np.pi, 1.5, 2.6, 1.8, 2.4, 2.9])
+    start = np.array([-2.0, -1.5, 0.3, -0.17, 1.96, 0.19, 0.65, 0.53])
+    goal = np.array([1.5, 1.0, 1.2, -0.2, 1.2, 0.4, 0.9, 0.3])
+    el = informed.ellipse_init(start, goal, syn.IS_REVOLUTE)
+    ctx.set_option("chain_specialization", specialized)
+    try:
+        for k_rev, k_pri, env in ((1.0001, 1.0001, True), (1.5, 1.2, True), (4.0, 3.0, True), (2.0, 2.0, False)):
+            es = informed.ctypes_struct(el, k_rev * el["rev"]["c_min"], k_pri * el["pri"]["c_min"],
+                                        (lo[0], hi[0]) if env else (0.0, 0.0), (lo[1], hi[1]) if env else (0.0, 0.0))
+            for seed, first, n, T in ((3, 0, 4000, 64), (0xC0FFEE1234, 987654321, 777, 2)):
+                q, t = ctx.sample_informed(seed, first, n, lo, hi, es, T)
+                qr, tr = orc.sample_informed(seed, first, n, lo, hi, es, T)
+                same = np.all(q == qr, axis=1) & (t == tr)
+                if not same.all():                                  # only where the acceptance test sits on its boundary
+                    assert np.abs(orc.fk(qr[~same])[:, 2]).max() < 1e-9
+                assert same.mean() > 0.999
+        a, _ = ctx.sample_informed(9, 10, 90, lo, hi, es, 8)
+        b, _ = ctx.sample_informed(9, 0, 100, lo, hi, es, 8)
+        assert np.array_equal(a, b[10:])
+        bad = informed.ctypes_struct(el, 3.0, 3.0)
+        bad.n_rev = 7
+        with pytest.raises(api.SqmpError):
+            ctx.sample_informed(1, 0, 4, lo, hi, bad, 4)
+    finally:
+        ctx.set_option("chain_specialization", 1)
+
+
 # --------------------------------------------------------------------------------------- the two validity kernels
 @pytest.mark.parametrize("kernel", [1, 2])
 @pytest.mark.parametrize("flags", [api.CHECK_MAP, api.CHECK_MAP | api.CHECK_SELF])

@@ -200,3 +200,84 @@ def test_sampler_is_the_documented_counter_stream(orc):
     ee = orc.fk(q2)[:, 2]
     assert np.all((t2 > 0) == (ee >= 0.0))
     assert (t2 > 1).any() and (t2 < 0).any()                 # some samples needed a redraw, some ran out of tries
+
+
+def test_informed_sampler_is_the_documented_rule(orc):
+    """orc_sample_informed (sampleJointConfigfromEllipse_JntArray BS:3607-3829 over the ellipse of BS:3472-3604) against a
+    pure-Python restatement of the counter stream and of the map ball -> ellipse, and against the geometry it must have:
+    every sample lies inside the ellipse of its joint class, above the platform, inside the environment."""
+    from squirrel_motion_planner_b200 import informed
+    is_rev = [0, 0, 1, 1, 1, 1, 1, 1]
+    start = np.array([-2.0, -1.5, 0.3, -0.17, 1.96, 0.19, 0.65, 0.53])
+    goal = np.array([1.5, 1.0, 1.2, -0.2, 1.2, 0.4, 0.9, 0.3])
+    el = informed.ellipse_init(start, goal, is_rev)
+    for cls in ("rev", "pri"):                               # the rotation C: orthogonal, det +1, first column (goal - start) / c_min
+        Cm, e = el[cls]["C"], el[cls]
+        assert np.abs(Cm @ Cm.T - np.eye(len(Cm))).max() < 1e-15 and abs(np.linalg.det(Cm) - 1.0) < 1e-14
+        assert np.abs(Cm[:, 0] * e["c_min"] - (goal - start)[e["idx"]]).max() < 1e-15
+        assert np.array_equal(e["center"], ((start + goal) / 2.0)[e["idx"]])
+    th = np.arctan2(goal[1] - start[1], goal[0] - start[0])   # two joints: THE rotation by the heading start -> goal
+    assert np.abs(el["pri"]["C"] - np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])).max() < 1e-15
+    c_rev, c_pri = 1.6 * el["rev"]["c_min"], 1.25 * el["pri"]["c_min"]
+    lo = np.array([-5.0, -4.0, -np.pi, -1.2, -1.7, -1.8, -2.4, -2.9])
+    hi = np.array([5.0, 6.0, np.pi, 1.5, 2.6, 1.8, 2.4, 2.9])
+    es = informed.ctypes_struct(el, c_rev, c_pri, (lo[0], hi[0]), (lo[1], hi[1]))
+    M, G = (1 << 64) - 1, 0x9E3779B97F4A7C15
+
+    def out(seed, k):
+        z = (seed + (k + 1) * G) & M
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+        return z ^ (z >> 31)
+
+    seed, first, n, T = 0xABCDEF987654, 77, 200, 6
+    q, tries = orc.sample_informed(seed, first, n, lo, hi, es, T)
+    for i in range(n):
+        used = -T
+        for t in range(T):
+            k0 = ((first + i) * T + t) * 9
+            ball = np.array([lo[j] + (hi[j] - lo[j]) * ((out(seed, k0 + j) >> 11) * (1.0 / 9007199254740992.0)) for j in range(8)])
+            scale = (out(seed, k0 + 8) >> 11) * (1.0 / 9007199254740992.0)
+            cand = []
+            for cls, cb in (("pri", c_pri), ("rev", c_rev)):
+                e = el[cls]
+                v = ball[e["idx"]]
+                s2 = 0.0
+                for x in v:
+                    s2 += float(x) * float(x)
+                l0, l1 = informed.ellipse_L(cb, e["c_min"])
+                y = [(l0 if a == 0 else l1) * (scale * (float(v[a]) / np.sqrt(s2))) for a in range(len(v))]
+                for r in range(len(v)):
+                    acc = 0.0
+                    for a in range(len(v)):
+                        acc += float(e["C"][r, a]) * y[a]
+                    cand.append(acc + float(e["center"][r]))
+            cand = np.array(cand)
+            if orc.fk(cand[None])[0, 2] >= 0.0 and lo[0] < cand[0] < hi[0] and lo[1] < cand[1] < hi[1]:
+                used = t + 1
+                break
+        assert tries[i] == used and np.array_equal(q[i], cand)
+    ok = tries > 0
+    assert ok.mean() > 0.9
+    for cls, cb in (("rev", c_rev), ("pri", c_pri)):         # inside the ellipse: |L^-1 C^T (x - centre)| <= 1
+        e = el[cls]
+        l0, l1 = informed.ellipse_L(cb, e["c_min"])
+        u = (q[ok][:, e["idx"]] - e["center"]) @ e["C"] / np.array([l0] + [l1] * (len(e["idx"]) - 1))
+        assert np.linalg.norm(u, axis=1).max() <= 1.0 + 1e-12
+    assert (orc.fk(q[ok])[:, 2] >= 0.0).all()
+    qa, _ = orc.sample_informed(seed, first, 50, lo, hi, es, T)   # order-free like the uniform stream
+    qb, _ = orc.sample_informed(seed, first + 50, 150, lo, hi, es, T)
+    assert np.array_equal(q, np.concatenate([qa, qb]))
+
+
+def test_edge_cost_three_way_with_weights():
+    """compute_edge_cost_interpolation (BS:4162-4242): total uses m_edge_cost_weights, the other two do not."""
+    from squirrel_motion_planner_b200 import synthetic as syn
+    a, b = syn.edge_batch(20, seed=3)
+    w = np.array([2.0, 0.5, 1.0, 3.0, 1.0, 0.25, 1.0, 4.0])
+    for i in range(20):
+        traj = oracle.interpolate(a[i], b[i], 20)
+        c = oracle.edge_cost(traj, syn.IS_REVOLUTE, w)
+        seg = np.diff(traj, axis=0)
+        assert abs(c[0] - np.sqrt((seg ** 2 * w).sum(1)).sum()) < 1e-12
+        assert abs(c[1] - np.sqrt((seg[:, 2:] ** 2).sum(1)).sum()) < 1e-12 and abs(c[2] - np.sqrt((seg[:, :2] ** 2).sum(1)).sum()) < 1e-12

@@ -136,3 +136,45 @@ def test_lockstep_multi_query_runner_repeats_the_sequential_decisions(tmp_path, 
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout + r.stderr
     assert [l.split() for l in r.stdout.splitlines() if l and not l.startswith("#")] == seq
+
+
+def test_cpp_front_end_equals_independent_python_restatement(tmp_path, fixture_data, orc):
+    """the decisions of shim/sqmp_birrt.hpp pinned by a SECOND restatement of the reference's iteration
+    (tests/birrt_restatement.py: Python, one edge at a time with the reference's early exits, its own tree structure, the
+    numpy twin of the ellipse set-up).  Three queries with different seeds, each long enough to find a solution and to
+    spend most of its iterations in the optimisation phase (informed samples, choose-parent, rewires, rewires ON the
+    solution path): decision trace, node counts, solution costs (total / revolute / prismatic) and counters must agree."""
+    import birrt_restatement as br
+    import oracle
+    from squirrel_motion_planner_b200 import robot_desc as rd
+    world = syn.box_world(g=160, n_boxes=14, seed=99, dims=(160, 160, 48))
+    origin = world.origin + np.array([0.0, 0.0, rd.OCTREE_Z_OFFSET])
+    arm_a, arm_b = pw.half_folded_arm(), np.array([-0.2, 1.2, 0.4, 0.9, 0.3])
+    orc.set_disabled_links(0)
+    orc.set_grid(world.bits, world.dims, origin, world.res)
+    cand = syn.sample_configs(200, seed=5, xy_half=2.8)      # collision-free end points: the first six valid candidates
+    cand[0::2, 3:], cand[1::2, 3:] = arm_a, arm_b
+    ok = cand[~np.unpackbits(orc.check_states(cand, oracle.FLAG_SELF | oracle.FLAG_MAP).view(np.uint8), bitorder="little")[:len(cand)].astype(bool)]
+    starts, goals = ok[0:3], ok[3:6]
+    d = _workdir(tmp_path, fixture_data, world, starts, goals)
+    iters, seed = 160, 11
+    rows = _run("sqmp_plan_oracle", d, "oracle", iters, seed)
+    lo = np.array([world.origin[0] + 1.0, world.origin[1] + 1.0, -3.14159265358979323846, -1.2, -1.7, -1.8, -2.4, -2.9])
+    hi = np.array([world.origin[0] + world.dims[0] * world.res - 1.0, world.origin[1] + world.dims[1] * world.res - 1.0,
+                   3.14159265358979323846, 1.5, 2.6, 1.8, 2.4, 2.9])
+    phases = 0
+    for k, row in enumerate(rows):
+        p = br.Planner(orc, oracle.FLAG_SELF | oracle.FLAG_MAP, lo, hi, seed + k)
+        assert p.init(starts[k], goals[k]) and row[1] != "invalid_endpoint"
+        for _ in range(iters):
+            p.iterate()
+        s = p.stats
+        assert int(row[1]) == int(p.solution) and int(row[13]) == p.trace, "query %d: decision traces differ" % k
+        assert int(row[3]) == s["iterations"] and int(row[4]) == s["nn_calls"] and int(row[5]) == s["near_calls"]
+        assert int(row[9]) == s["rewires"] and int(row[10]) == s["parents_chosen"]
+        assert int(row[11]) == len(p.start_tree.nodes) and int(row[12]) == len(p.goal_tree.nodes)
+        assert float(row[2]) == p.best[0] and float(row[14]) == p.best[1] and float(row[15]) == p.best[2]   # bit for bit
+        assert int(row[16]) == s["informed_samples"] and int(row[17]) == s["solution_rewires"]
+        if p.solution and s["rewires"] > 0 and s["informed_samples"] > iters // 3:
+            phases += 1
+    assert phases >= 2                                       # the comparison covers the optimisation phase, not only the search
