@@ -738,18 +738,10 @@ def run_config5(args):
     # collision-free (start, goal) pairs: rejection sampling with the CUDA checker itself (self + map), seed 5
     ctx = api.default_context(local_rank)
     ctx.set_voxel_grid(w.bits, w.dims, w.origin + np.array([0.0, 0.0, rd.OCTREE_Z_OFFSET]), w.res)
-    rng = np.random.default_rng(5)
-    s0, g0 = pw.config1_queries(1)
-
-    def free_samples(arm_pose):      # base anywhere in the scene, arm near a self-collision-free pose
-        cand = syn.sample_configs(64 * n_queries + 256, seed=int(rng.integers(1 << 30)), xy_half=11.0)
-        cand[:, 3:] = arm_pose + rng.uniform(-0.15, 0.15, size=(len(cand), 5))
-        mask = ctx.check_states(cand, api.CHECK_MAP | api.CHECK_SELF)
-        ok = cand[~np.unpackbits(mask.view(np.uint8), bitorder="little")[:len(cand)].astype(bool)]
-        if len(ok) < n_queries:
-            raise RuntimeError("not enough collision-free samples for %d queries (%d found)" % (n_queries, len(ok)))
-        return ok[:n_queries]
-    starts, goals = free_samples(s0[0, 3:]), free_samples(g0[0, 3:])
+    def in_collision(q):
+        mask = ctx.check_states(q, api.CHECK_MAP | api.CHECK_SELF)
+        return np.unpackbits(mask.view(np.uint8), bitorder="little")[:len(q)].astype(bool)
+    starts, goals = pw.config5_queries(in_collision, n_queries, seed=5)
     ctx.close()
     d = tempfile.mkdtemp(prefix="sqmp_cfg5_")
     pw.write_world(d, w)
@@ -769,8 +761,12 @@ def run_config5(args):
         raise RuntimeError("sqmp_plan failed: " + r.stderr[-500:])
     tail = [l for l in r.stdout.splitlines() if l.startswith("# queries")][-1].split()
     secs, states, its = float(tail[4]), int(tail[6]), int(tail[8])
-    solved = sum(l.split()[1] == "1" for l in r.stdout.splitlines() if l and not l.startswith("#") and "invalid" not in l)
-    agg = torch.tensor([secs, float(states), float(its), float(solved), float(count)], dtype=torch.float64)
+    rows = [l.split() for l in r.stdout.splitlines() if l and not l.startswith("#") and "invalid" not in l]
+    solved = sum(row[1] == "1" for row in rows)
+    near_calls, rewires, informed_n = sum(int(row[5]) for row in rows), sum(int(row[9]) for row in rows), sum(int(row[16]) for row in rows)
+    optimising = sum(int(row[5]) > 0 for row in rows)            # queries that reached the optimisation phase
+    agg = torch.tensor([secs, float(states), float(its), float(solved), float(count), float(near_calls), float(rewires), float(informed_n),
+                        float(optimising)], dtype=torch.float64)
     if world_size > 1:
         mx = agg.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -803,7 +799,8 @@ def run_config5(args):
                        "iterations_per_query": iters, "flags": "SELF|MAP", "queries_in_flight_per_gpu": max(1, args.batch) * (args.threads if args.batch > 1 else 1),
                        "host_threads_per_gpu": args.threads if args.batch > 1 else 1},
             "checked_states_per_s": float(agg[1]) / secs, "planner_iterations_per_s": float(agg[2]) / secs,
-            "solved": int(agg[3]), "cpu_baseline": cpu, "gpu_launches": None}))
+            "solved": int(agg[3]), "queries_in_optimisation_phase": int(agg[8]), "near_calls": int(agg[5]), "rewires": int(agg[6]),
+            "informed_samples": int(agg[7]), "cpu_baseline": cpu, "gpu_launches": None}))
     if world_size > 1:
         dist.destroy_process_group()
 

@@ -565,8 +565,12 @@ class HotPath {
   // device tree slot of a host tree (assigned on first use), or -1 when the mirror could not be updated
   int sync_mirror(const Rrt_star_tree *tree) {
     Mirror &m = mirrors_[tree];
-    if (m.slot < 0) m.slot = next_slot_++;
     sqmp_ctx *c = collisionChecker->context();
+    if (m.slot < 0) {   // first use: a slot of its own, counted down from the top (explicit slots count up from 0)
+      if (next_slot_ >= SQMP_MAX_TREES) return -1;
+      m.slot = SQMP_MAX_TREES - 1 - next_slot_++;
+      if (sqmp_tree_reset(c, m.slot) != SQMP_OK) return -1;
+    }
     const size_t n = tree->nodes.size();
     if (n < m.cost.size()) {   // the planner was reset: start over
       if (sqmp_tree_reset(c, m.slot) != SQMP_OK) return -1;

@@ -135,6 +135,7 @@ def test_cpp_shim_against_oracle(tmp_path, fixture_data, orc, small_world):
     lit = np.fromfile(os.path.join(d, "out_literal.i32"), dtype=np.int32)
     half = len(cost) // 2
     t_nodes, t_cost = nodes.copy(), cost.copy()
+    t_nodes[3] = queries[0]                                                     # (node 3 was moved by the update test above)
     phases = [(t_nodes[:half].copy(), t_cost[:half].copy()), (t_nodes.copy(), t_cost.copy())]
     for n in range(5, len(cost), 7):                                            # the rewires + cost changes of test_shim.cpp
         t_nodes[n] = queries[n % 16]

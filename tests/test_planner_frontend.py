@@ -138,6 +138,41 @@ def test_lockstep_multi_query_runner_repeats_the_sequential_decisions(tmp_path, 
     assert [l.split() for l in r.stdout.splitlines() if l and not l.startswith("#")] == seq
 
 
+@pytest.mark.gpu
+def test_config5_scene_queries_reach_the_optimisation_phase(tmp_path, fixture_data):
+    """BASELINE.json configs[4] in small: planning queries in W512 (512^3 voxels, 2048 boxes, seed 4321) whose start / goal
+    pairs come from the bench's own generator.  GPU backend and CPU twin must print the same lines (decision trace, costs,
+    counters), the lock-step runner must repeat them, and the batch must exercise the whole path: at least half of the
+    queries reach the optimisation phase (near-vertex search, choose-parent, rewire, informed samples)."""
+    from squirrel_motion_planner_b200 import api, robot_desc as rd
+    world = syn.box_world(g=512, n_boxes=2048, seed=4321)
+    ctx = api.default_context(0)
+    ctx.set_voxel_grid(world.bits, world.dims, world.origin + np.array([0.0, 0.0, rd.OCTREE_Z_OFFSET]), world.res)
+
+    def in_collision(q):
+        return np.unpackbits(ctx.check_states(q, api.CHECK_MAP | api.CHECK_SELF).view(np.uint8), bitorder="little")[:len(q)].astype(bool)
+    n = 12
+    starts, goals = pw.config5_queries(in_collision, n, seed=5)
+    ctx.close()
+    d = _workdir(tmp_path, fixture_data, world, starts, goals)
+    iters = 250
+    gpu = _run("sqmp_plan", d, "gpu", iters)
+    r = subprocess.run([os.path.join(SHIM, "sqmp_plan_multi"), DESC, d, "gpu", str(iters), "1", "0", "0", str(n), "8"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert [l.split() for l in r.stdout.splitlines() if l and not l.startswith("#")] == gpu
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR, "planner"], check=True)
+    r = subprocess.run([os.path.join(ORACLE_DIR, "sqmp_plan_oracle"), DESC, d, "oracle", str(iters), "1", "0", "0", "4"],
+                       capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout + r.stderr
+    cpu = [l.split() for l in r.stdout.splitlines() if l and not l.startswith("#")]
+    assert cpu == gpu[:4], "decision traces differ"
+    assert all(row[1] != "invalid_endpoint" for row in gpu)
+    optimising = [row for row in gpu if int(row[5]) > 0]                    # near_calls > 0 <=> a solution existed
+    assert len(optimising) >= n // 2 and sum(int(row[9]) for row in gpu) > 0 and sum(int(row[16]) for row in gpu) > 0
+    assert all(row[1] == "1" for row in optimising)
+
+
 def test_cpp_front_end_equals_independent_python_restatement(tmp_path, fixture_data, orc):
     """the decisions of shim/sqmp_birrt.hpp pinned by a SECOND restatement of the reference's iteration
     (tests/birrt_restatement.py: Python, one edge at a time with the reference's early exits, its own tree structure, the

@@ -50,3 +50,43 @@ def config1_queries(n=1):
     start = np.concatenate([[-4.0, -4.0, 0.0], half_folded_arm()])
     goal = np.concatenate([[4.0, 4.0, np.pi / 2], [-0.2, 1.2, 0.4, 0.9, 0.3]])
     return np.tile(start, (n, 1)), np.tile(goal, (n, 1))
+
+
+def config5_queries(check_states, n_queries, seed=5, xy_half=11.0, goal_dist=(1.0, 2.5)):
+    """collision-free (start, goal) pairs in W512 by rejection sampling with the checker that is
+    handed in (`check_states(q) -> bool[n]`, True = in collision; self + map).  2048 boxes leave ~1 % of uniformly drawn
+    base poses free, and free space falls into pockets: a goal is drawn 1 - 2.5 m from its start and kept when it is
+    free and the straight base motion between them is free for the start's arm pose — so that most queries are solvable
+    within their iteration budget and spend it in the optimisation phase (near-vertex search, choose-parent, rewire),
+    which is what the configuration is meant to exercise."""
+    from squirrel_motion_planner_b200 import synthetic as syn
+    rng = np.random.default_rng(seed)
+    s0, g0 = config1_queries(1)
+    starts, goals = [], []
+    for _ in range(400):
+        cand = syn.sample_configs(1 << 15, seed=int(rng.integers(1 << 30)), xy_half=xy_half)
+        cand[:, 3:] = s0[0, 3:] + rng.uniform(-0.15, 0.15, size=(len(cand), 5))
+        free = cand[~check_states(cand)]
+        if len(free) == 0:
+            continue
+        ang, dist = rng.uniform(-np.pi, np.pi, len(free)), rng.uniform(goal_dist[0], goal_dist[1], len(free))
+        g = free.copy()
+        g[:, 0] += dist * np.cos(ang)
+        g[:, 1] += dist * np.sin(ang)
+        g[:, 2] = rng.uniform(-np.pi, np.pi, len(free))
+        g[:, 3:] = g0[0, 3:] + rng.uniform(-0.15, 0.15, size=(len(free), 5))
+        keep = ~check_states(g) & (np.abs(g[:, 0]) < xy_half) & (np.abs(g[:, 1]) < xy_half)
+        free, g = free[keep], g[keep]
+        if len(free) == 0:
+            continue
+        mid = np.repeat(free, 9, axis=0)                      # the straight base motion, sampled every ~12 % of the way
+        t = np.tile(np.linspace(0.1, 0.9, 9), len(free))[:, None]
+        mid[:, :2] = mid[:, :2] + t * (np.repeat(g, 9, axis=0)[:, :2] - mid[:, :2])
+        clear = ~check_states(mid).reshape(-1, 9).any(axis=1)
+        starts += list(free[clear])
+        goals += list(g[clear])
+        if len(starts) >= n_queries:
+            break
+    if len(starts) < n_queries:
+        raise RuntimeError("not enough collision-free query pairs (%d of %d)" % (len(starts), n_queries))
+    return np.array(starts[:n_queries]), np.array(goals[:n_queries])
