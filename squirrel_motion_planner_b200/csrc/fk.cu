@@ -59,7 +59,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // The chain for one state, its joint vector read straight from the shared-memory tile row (no register copy):
 // T = double everywhere, or T = float for the rotational part with the prismatic base added in double (see DESIGN.md
 // for the error budget against the 1e-5 m / 1e-5 rad tolerance).
-template <typename T, typename SIG>
+template <typename T, typename SIG, bool SMALL = false>
 __device__ __forceinline__ void fk_one(const RobotDev &rb, const double *q_row, double *out7) {
   Frame<T> f;
   frame_set_translation<T>(f, T(0), T(0), T(0));
@@ -81,7 +81,7 @@ __device__ __forceinline__ void fk_one(const RobotDev &rb, const double *q_row, 
     // leading prismatic x, y (identity pre-frames, signature): a plain fp64 offset in both precisions
     off[0] = q_row[0];
     off[1] = q_row[1];
-    chain_walk_sig<T, SIG, 2, SIG::n>(f, rb, q_row, 1);
+    chain_walk_sig<T, SIG, 2, SIG::n, SMALL>(f, rb, q_row, 1);
     if (sizeof(T) == 4) frame_mul_const<T>(f, rb.ee_tip_f, SIG::ee_kind);
     else frame_mul_const<T>(f, rb.ee_tip, SIG::ee_kind);
   }
@@ -97,9 +97,16 @@ __device__ __forceinline__ void fk_one(const RobotDev &rb, const double *q_row, 
 // Warp-private tiles: every warp of the CTA streams its own 32-state tiles (2 KB in, 1.75 KB out) through its own
 // double-buffered shared-memory slice with its own pair of mbarriers — no __syncthreads anywhere, so a warp never waits
 // for the slowest warp of its CTA (the CTA-wide barriers of the previous version held ~14 % of the stall samples).
-constexpr int FK_WARP_TILE = 32;
+#ifndef FK_ROWS_PER_LANE_DEF
+#define FK_ROWS_PER_LANE_DEF 2
+#endif
+constexpr int FK_RPL = FK_ROWS_PER_LANE_DEF;   // states per lane: two independent chains per thread keep the fp64 pipe fed
+constexpr int FK_WARP_TILE = 32 * FK_RPL;
+#ifndef FK_MIN_BLOCKS_DEF
+#define FK_MIN_BLOCKS_DEF 4
+#endif
 template <typename T, typename SIG>
-__global__ void __launch_bounds__(FK_TILE, 8)
+__global__ void __launch_bounds__(FK_TILE, FK_MIN_BLOCKS_DEF)
 k2_fk(const __grid_constant__ RobotDev rb, const double *__restrict__ q_in, int64_t S, double *__restrict__ out) {
   constexpr int WARPS = FK_TILE / 32;
   __shared__ __align__(128) double s_in[WARPS][2][FK_WARP_TILE * FK_IN_PITCH];
@@ -136,16 +143,45 @@ k2_fk(const __grid_constant__ RobotDev rb, const double *__restrict__ q_in, int6
     phase[buf] ^= 1;
 
     const int rows = tile_rows(tile);
-    if (lane < rows) {
-      double o[7];
-      fk_one<T, SIG>(rb, s_in[w][buf] + lane * FK_IN_PITCH, o);
-      if (rows == FK_WARP_TILE) {
-        double *orow = s_out[w] + lane * FK_OUT_PITCH;
+    if (rows == FK_WARP_TILE) {
+      // full tile: every lane owns FK_RPL rows (lane, lane + 32, ...).  When all their joint values are small enough for
+      // the branch-free sincos the chains are straight-line code and interleave; otherwise row by row.
+      const double *rows_in = s_in[w][buf];
+      bool small = true;
+      if constexpr (!SIG::generic && sizeof(T) == 8) {
 #pragma unroll
-        for (int j = 0; j < 7; ++j) orow[j] = o[j];
+        for (int r = 0; r < FK_RPL; ++r)
+#pragma unroll
+          for (int j = 2; j < SQMP_DOF; ++j) small = small && fabs(rows_in[(lane + 32 * r) * FK_IN_PITCH + j]) < 1.0e5;
       } else {
-        // ragged last tile: its byte count need not be a multiple of 16, which bulk copies require
-        double *orow = out + (tile * FK_WARP_TILE + lane) * 7;
+        small = false;
+      }
+      if (small) {
+        double o[FK_RPL][7];
+#pragma unroll
+        for (int r = 0; r < FK_RPL; ++r) fk_one<T, SIG, true>(rb, rows_in + (lane + 32 * r) * FK_IN_PITCH, o[r]);
+#pragma unroll
+        for (int r = 0; r < FK_RPL; ++r) {
+          double *orow = s_out[w] + (lane + 32 * r) * FK_OUT_PITCH;
+#pragma unroll
+          for (int j = 0; j < 7; ++j) orow[j] = o[r][j];
+        }
+      } else {
+#pragma unroll 1
+        for (int r = 0; r < FK_RPL; ++r) {
+          double o[7];
+          fk_one<T, SIG>(rb, rows_in + (lane + 32 * r) * FK_IN_PITCH, o);
+          double *orow = s_out[w] + (lane + 32 * r) * FK_OUT_PITCH;
+#pragma unroll
+          for (int j = 0; j < 7; ++j) orow[j] = o[j];
+        }
+      }
+    } else {
+      // ragged last tile: its byte count need not be a multiple of 16, which bulk copies require
+      for (int row = lane; row < rows; row += 32) {
+        double o[7];
+        fk_one<T, SIG>(rb, s_in[w][buf] + row * FK_IN_PITCH, o);
+        double *orow = out + (tile * FK_WARP_TILE + row) * 7;
 #pragma unroll
         for (int j = 0; j < 7; ++j) orow[j] = o[j];
       }
@@ -172,9 +208,9 @@ cudaError_t launch_fk(const RobotDev &rb, const double *d_q, int64_t S, double *
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
   }
-  const int64_t n_tiles = (S + FK_TILE - 1) / FK_TILE;   // CTAs needed if every warp took one 32-state tile
+  const int64_t n_tiles = (S + FK_TILE * FK_RPL - 1) / (FK_TILE * FK_RPL);   // CTAs needed if every warp took one tile
   // persistent CTAs: a multiple of the SM count, enough resident warps to cover the fp64 latency
-  const unsigned blocks = unsigned(imin64(n_tiles, int64_t(sms) * 8));
+  const unsigned blocks = unsigned(imin64(n_tiles, int64_t(sms) * FK_MIN_BLOCKS_DEF));
   const bool robotino = allow_specialized && chain_matches<SigRobotino>(rb);   // structure known at compile time: unrolled chain
   if (fk_precision == 32) {
     if (robotino) k2_fk<float, SigRobotino><<<blocks, FK_TILE, 0, st>>>(rb, d_q, S, d_out);

@@ -33,12 +33,18 @@ static __constant__ double SQMP_SC64[18] = {
 // fp64 sincos for joint angles: Cody-Waite reduction by pi/2 in three parts (exact for |k| < 2^20, i.e. |x| < 1e5;
 // larger arguments take the library path) + the fdlibm minimax kernels on [-pi/4, pi/4].  <= ~1.5 ulp, about a
 // quarter of the instructions of the general-purpose library routine (no Payne-Hanek set-up, no special cases).
+// the body without the large-argument test (callers that have checked |x| < 1e5 for all their angles up front run it as
+// straight-line code, which lets the compiler interleave independent chains)
+__device__ __forceinline__ void sincos64_small(double x, double *sn, double *cs);
 template <>
 __device__ __forceinline__ void sincos_t<double>(double x, double *sn, double *cs) {
   if (!(fabs(x) < 1.0e5)) {
     sincos(x, sn, cs);
     return;
   }
+  sincos64_small(x, sn, cs);
+}
+__device__ __forceinline__ void sincos64_small(double x, double *sn, double *cs) {
   const double *C = SQMP_SC64;
   const double kd = rint(x * C[0]);
   const int k = int(kd);
@@ -125,7 +131,8 @@ __device__ __forceinline__ void rot_cols(Frame<T> &f, int ca, int cb, T s, T c) 
 }
 
 // f <- f * Motion(axis, q):  KDL::Joint::pose(q) without its origin (already folded into the pre-frame)
-template <typename T, typename C>
+// SMALL: the caller guarantees |q| < 1e5 for rotations in fp64 (no large-argument branch in the sincos)
+template <typename T, typename C, bool SMALL = false>
 __device__ __forceinline__ void frame_joint_motion(Frame<T> &f, int type, int axis_code, const C *axis, T q) {
   if (type == SQMP_JOINT_TRANS) {
     if (axis_code == AX_GENERAL) {
@@ -144,7 +151,14 @@ __device__ __forceinline__ void frame_joint_motion(Frame<T> &f, int type, int ax
     return;
   }
   T s, c;
-  sincos_t<T>(q, &s, &c);
+  if constexpr (SMALL && sizeof(T) == 8) {
+    double sd, cd;
+    sincos64_small(double(q), &sd, &cd);
+    s = T(sd);
+    c = T(cd);
+  } else {
+    sincos_t<T>(q, &s, &c);
+  }
   switch (axis_code) {
     case AX_PX: rot_cols(f, 1, 2, s, c); break;
     case AX_NX: rot_cols(f, 1, 2, -s, c); break;
@@ -232,24 +246,24 @@ inline bool chain_matches(const RobotDev &rb) {
   return true;
 }
 
-template <typename T, typename SIG, int S>
+template <typename T, typename SIG, int S, bool SMALL = false>
 __device__ __forceinline__ void frame_advance_sig(Frame<T> &f, const RobotDev &rb, const double *q_mine, int pitch) {
   if constexpr (S < SIG::n) {
     const T qv = T(q_mine[S * pitch]);   // signature guarantees seg_qidx[s] == s
     if (sizeof(T) == 4) {
       frame_mul_const<T>(f, rb.seg_pre_f[S], SIG::kind(S));
-      frame_joint_motion<T>(f, SIG::type(S), SIG::axis(S), rb.seg_axis_f[S], qv);
+      frame_joint_motion<T, float, SMALL>(f, SIG::type(S), SIG::axis(S), rb.seg_axis_f[S], qv);
     } else {
       frame_mul_const<T>(f, rb.seg_pre[S], SIG::kind(S));
-      frame_joint_motion<T>(f, SIG::type(S), SIG::axis(S), rb.seg_axis[S], qv);
+      frame_joint_motion<T, double, SMALL>(f, SIG::type(S), SIG::axis(S), rb.seg_axis[S], qv);
     }
   }
 }
-template <typename T, typename SIG, int S0, int S1>
+template <typename T, typename SIG, int S0, int S1, bool SMALL = false>
 __device__ __forceinline__ void chain_walk_sig(Frame<T> &f, const RobotDev &rb, const double *q_mine, int pitch) {
   if constexpr (S0 < S1) {
-    frame_advance_sig<T, SIG, S0>(f, rb, q_mine, pitch);
-    chain_walk_sig<T, SIG, S0 + 1, S1>(f, rb, q_mine, pitch);
+    frame_advance_sig<T, SIG, S0, SMALL>(f, rb, q_mine, pitch);
+    chain_walk_sig<T, SIG, S0 + 1, S1, SMALL>(f, rb, q_mine, pitch);
   }
 }
 
