@@ -207,7 +207,12 @@ int sqmp_check_edges_dev(sqmp_ctx *ctx, const double *d_q_start, const double *d
  * in stream order (same stream, or another stream behind an event), publishes `step` (use 1, 2, 3, ...) in flag[p][rank]
  * of every rank — the completed validity grid orders its stores before that.  sqmp_gather_wait_dev enqueues a one-warp
  * kernel that returns once this rank's flag array shows `step` for all n_peers ranks (status 0) or ~2 s have passed (1):
- * work enqueued behind it sees the complete gathered mask of the step. */
+ * work enqueued behind it sees the complete gathered mask of the step.
+ * REUSE RULE: the protocol has no consumer acknowledgement.  A peer may store the words of a later step into a gather
+ * buffer as soon as it has been told to; a buffer may therefore be handed out again (for step i + NBUF) only after EVERY
+ * rank's consumer of step i has finished reading it — the caller provides that hand-shake (a host barrier, an
+ * all-reduce, or a second flag array the consumers publish and the producers wait on).  bench.py rotates four buffers
+ * and never reads them inside its timed loop. */
 typedef struct sqmp_peer_gather {
   int32_t n_peers, rank;
   uint32_t *mask[SQMP_MAX_PEERS];

@@ -11,8 +11,8 @@ import torch
 from squirrel_motion_planner_b200 import api, robot_desc as rd, synthetic as syn
 
 NAMES = ["group root tests (warp)", "open roots (lanes)", "groups entered (warp)", "bound batches (warp)", "open clusters (lanes)",
-         "clusters entered (warp)", "spheres pending after stage 1 (lanes)", "serialised stage-2 rounds (warp)", "stage-2 tests (lanes)",
-         "exact-scan items", "queue drains (warp)", "warps", "colliding states"]
+         "clusters some lane opens (warp)", "spheres pending after stage 1", "stage-2 rounds (warp)", "stage-2 tests",
+         "exact-scan items", "queue drains (warp)", "warps", "colliding states", "cluster rounds (warp)"]
 
 
 def main():
