@@ -607,10 +607,13 @@ static int tree_reserve(Ctx *c, TreeDev &t, int64_t need) {
       }
     }
   }
-  // fp32 shadow (float4 + float4 + float per node)
+  // row-major copy + fp32 shadow (float4 + float4 + float per node)
+  double *aos = nullptr;
   float4 *fa = nullptr, *fb = nullptr;
   float *fn = nullptr;
-  e = cudaMalloc(&fa, size_t(pitch) * sizeof(float4));
+  e = cudaMalloc(&aos, size_t(pitch) * SQMP_DOF * sizeof(double));
+  if (e == cudaSuccess && t.n > 0) e = cudaMemcpy(aos, t.aos, size_t(t.n) * SQMP_DOF * sizeof(double), cudaMemcpyDeviceToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&fa, size_t(pitch) * sizeof(float4));
   if (e == cudaSuccess) e = cudaMalloc(&fb, size_t(pitch) * sizeof(float4));
   if (e == cudaSuccess) e = cudaMalloc(&fn, size_t(pitch) * sizeof(float));
   if (e == cudaSuccess && t.n > 0) {
@@ -620,12 +623,15 @@ static int tree_reserve(Ctx *c, TreeDev &t, int64_t need) {
   }
   if (e != cudaSuccess) {
     cudaFree(blk);
+    if (aos) cudaFree(aos);
     if (fa) cudaFree(fa);
     if (fb) cudaFree(fb);
     if (fn) cudaFree(fn);
     return fail(c, SQMP_ERR_NOMEM, "cudaMalloc(tree fp32 shadow)", e);
   }
   if (t.q[0]) cudaFree(t.q[0]);
+  if (t.aos) cudaFree(t.aos);
+  t.aos = aos;
   if (t.fa) cudaFree(t.fa);
   if (t.fb) cudaFree(t.fb);
   if (t.fn) cudaFree(t.fn);
@@ -882,6 +888,7 @@ void sqmp_destroy(sqmp_ctx *ctx) {
   if (ctx->d_fast_sph64) cudaFree(ctx->d_fast_sph64);
   for (auto &t : ctx->trees) {
     if (t.q[0]) cudaFree(t.q[0]);
+    if (t.aos) cudaFree(t.aos);
     if (t.fa) cudaFree(t.fa);
     if (t.fb) cudaFree(t.fb);
     if (t.fn) cudaFree(t.fn);

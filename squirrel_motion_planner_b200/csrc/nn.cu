@@ -30,6 +30,7 @@ namespace sqmp {
 struct TreePtrs {
   double *q[SQMP_DOF];
   double *cost;
+  double *aos;
   float4 *fa, *fb;
   float *fn;
 };
@@ -37,6 +38,7 @@ static inline TreePtrs ptrs_of(const TreeDev &t) {
   TreePtrs p;
   for (int d = 0; d < SQMP_DOF; ++d) p.q[d] = t.q[d];
   p.cost = t.cost;
+  p.aos = t.aos;
   p.fa = t.fa; p.fb = t.fb; p.fn = t.fn;
   return p;
 }
@@ -64,6 +66,9 @@ __global__ void k_tree_append(TreePtrs t, const double *__restrict__ rows, const
   t.q[0][first + i] = a.x; t.q[1][first + i] = a.y; t.q[2][first + i] = a.z; t.q[3][first + i] = a.w;
   t.q[4][first + i] = b.x; t.q[5][first + i] = b.y; t.q[6][first + i] = b.z; t.q[7][first + i] = b.w;
   t.cost[first + i] = cost[i];
+  double4 *row = reinterpret_cast<double4 *>(t.aos + (first + i) * SQMP_DOF);
+  row[0] = a;
+  row[1] = b;
   const double v[SQMP_DOF] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
   write_shadow(t, first + i, v);
 }
@@ -72,7 +77,10 @@ struct OneNode {
   double cost;
 };
 __global__ void k_tree_set_one(TreePtrs t, int64_t id, OneNode v) {
-  if (threadIdx.x < SQMP_DOF) t.q[threadIdx.x][id] = v.q[threadIdx.x];
+  if (threadIdx.x < SQMP_DOF) {
+    t.q[threadIdx.x][id] = v.q[threadIdx.x];
+    t.aos[id * SQMP_DOF + threadIdx.x] = v.q[threadIdx.x];
+  }
   if (threadIdx.x == SQMP_DOF) t.cost[id] = v.cost;
   if (threadIdx.x == SQMP_DOF + 1) write_shadow(t, id, v.q);
 }
@@ -298,9 +306,11 @@ __device__ __forceinline__ float2 estimate_s2(const float2 (&m2q)[SQMP_DOF], flo
 // __noinline__: inlined, the compiler hoists its sixteen 64-bit address computations above the (rarely taken) branch
 // and they become a third of all executed instructions.
 __device__ __noinline__ double exact_s(const TreePtrs &t, int64_t n, const double *__restrict__ query) {
-  double node[SQMP_DOF], q[SQMP_DOF];
-#pragma unroll
-  for (int d = 0; d < SQMP_DOF; ++d) { node[d] = t.q[d][n]; q[d] = query[d]; }
+  // node and query are 64-byte rows: four 16-byte loads each, all independent (the SoA columns would be eight L2 round trips)
+  const double2 *np = reinterpret_cast<const double2 *>(t.aos + n * SQMP_DOF), *qp = reinterpret_cast<const double2 *>(query);
+  const double2 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3], q0 = __ldg(qp), q1 = __ldg(qp + 1), q2 = __ldg(qp + 2), q3 = __ldg(qp + 3);
+  const double node[SQMP_DOF] = {n0.x, n0.y, n1.x, n1.y, n2.x, n2.y, n3.x, n3.y};
+  const double q[SQMP_DOF] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y};
   return sumsq8(node, q);
 }
 
@@ -311,7 +321,9 @@ k_nn_qt_pf(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ 
            // radius mode
            const int32_t *__restrict__ exclude, double s_thr, double r, int32_t *__restrict__ count,
            int32_t *__restrict__ hits, int64_t hit_cap) {
-  __shared__ __align__(16) float tile[NN_TILE][12];   // per node: q0..q7, |n|^2, pad — one base register, immediates
+  // per node: q0..q7, |n|^2, pad — one base register, immediates.  Two buffers: the next tile is on its way (cp.async)
+  // while this one is scanned
+  __shared__ __align__(16) float tiles[2][NN_TILE][12];
   int64_t qi[NN_QPT];
   bool active[NN_QPT];
   float2 m2q[NN_QPT / 2][SQMP_DOF], qq2[NN_QPT / 2];   // pair p: .x = query 2p of the thread, .y = query 2p + 1
@@ -357,18 +369,34 @@ k_nn_qt_pf(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ 
   }
   const int64_t n0 = int64_t(blockIdx.y) * chunk_len, n1 = min(N, n0 + chunk_len);
 
-  for (int64_t base = n0; base < n1; base += NN_TILE) {
+  auto fetch = [&](int buf, int64_t base) {   // asynchronous copies global -> shared; pad nodes: |n|^2 = +inf, never pass a threshold
     const int len = int(imin64(NN_TILE, n1 - base));
-    __syncthreads();
     for (int i = threadIdx.x; i < NN_TILE; i += NN_THREADS) {
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-      float nn = CUDART_INF_F;   // pad nodes: estimate = +inf, never passes a threshold
-      if (i < len) { a = t.fa[base + i]; b = t.fb[base + i]; nn = t.fn[base + i]; }
-      *reinterpret_cast<float4 *>(&tile[i][0]) = a;
-      *reinterpret_cast<float4 *>(&tile[i][4]) = b;
-      tile[i][8] = nn;
+      float *dst = &tiles[buf][i][0];
+      if (i < len) {
+        const unsigned d = unsigned(__cvta_generic_to_shared(dst));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(t.fa + base + i) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d + 16u), "l"(t.fb + base + i) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 32u), "l"(t.fn + base + i) : "memory");
+      } else {
+        *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4 *>(dst + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        dst[8] = CUDART_INF_F;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (n0 < n1) fetch(0, n0);
+  int buf = 0;
+  for (int64_t base = n0; base < n1; base += NN_TILE, buf ^= 1) {
+    if (base + NN_TILE < n1) {
+      fetch(buf ^ 1, base + NN_TILE);   // (its buffer was released by the barrier at the end of the previous iteration)
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    float (*tile)[12] = tiles[buf];
     // whole tile (pad nodes are inert), NN_GROUP nodes at a time: all estimates first, ONE branch per group — the
     // exact path is re-entered per (node, query) only inside that rarely taken branch
 #pragma unroll 1
@@ -416,6 +444,7 @@ k_nn_qt_pf(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ 
         }
       }
     }
+    __syncthreads();   // everyone is done with this buffer: the fetch two tiles ahead may overwrite it
   }
   if (!RADIUS) {
 #pragma unroll

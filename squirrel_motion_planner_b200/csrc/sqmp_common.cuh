@@ -224,6 +224,8 @@ cudaError_t launch_pack_rows(const uint32_t *d_bits_linear, int gx, int gy, int 
 struct TreeDev {
   double *q[SQMP_DOF];   // SoA: q[d][n]
   double *cost;
+  double *aos;           // the same nodes row-major [n][8]: one 64-byte line per node for the exact re-evaluation of the
+                         // few pairs that survive the fp32 pre-filter (eight SoA columns cost eight L2 round trips)
   // fp32 shadow for the sound pre-filter of K3/K4: fa[n] = (q0..q3), fb[n] = (q4..q7) rounded to float,
   // fn[n] = |float node|^2 (fp64 sum rounded once)
   float4 *fa, *fb;
