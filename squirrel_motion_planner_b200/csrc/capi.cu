@@ -291,12 +291,30 @@ static int build_self_tables(Ctx *c, double inv) {
     else leaves[sl] = {float(c->sph[size_t(i)].c[0] * inv), float(c->sph[size_t(i)].c[1] * inv), float(c->sph[size_t(i)].c[2] * inv),
                        float(c->sph[size_t(i)].r * inv)};
   }
+  // bounding box of a sphere set (group frame, grid units), padded like the radii
+  auto box_of = [&](const std::vector<int> &ids, float (&lo)[3], float (&hi)[3]) {
+    for (int k = 0; k < 3; ++k) {
+      double l = 1e300, h = -1e300;
+      for (int i : ids) {
+        l = std::fmin(l, c->sph[size_t(i)].c[k] - c->sph[size_t(i)].r);
+        h = std::fmax(h, c->sph[size_t(i)].c[k] + c->sph[size_t(i)].r);
+      }
+      const double m = 1e-4 * std::fmax(std::fabs(l), std::fabs(h)) + 1e-6;
+      lo[k] = float((l - m) * inv);
+      hi[k] = float((h + m) * inv);
+      lo[k] = std::nextafterf(lo[k], -INFINITY);
+      hi[k] = std::nextafterf(hi[k], INFINITY);
+    }
+  };
   std::vector<SelfCluster> cls(c->clusters.size());
   std::vector<SelfLink> links;
   std::vector<int> link_grp;
   for (size_t k = 0; k < c->clusters.size(); ++k) {
     const HostCluster &cl = c->clusters[k];
-    cls[k] = {float(cl.c[0] * inv), float(cl.c[1] * inv), float(cl.c[2] * inv), pad(cl.R), cl.slot0, cl.slot0 + int(cl.members.size()), {0, 0}};
+    cls[k].x = float(cl.c[0] * inv); cls[k].y = float(cl.c[1] * inv); cls[k].z = float(cl.c[2] * inv); cls[k].R = pad(cl.R);
+    box_of(cl.members, cls[k].lo, cls[k].hi);
+    cls[k].leaf_begin = cl.slot0;
+    cls[k].leaf_end = cl.slot0 + int(cl.members.size());
     if (links.empty() || links.back().link != cl.link || link_grp.back() != cl.grp) {
       SelfLink L = {0.f, 0.f, 0.f, 0.f, int(k), int(k), cl.link, 0};
       links.push_back(L);
@@ -334,7 +352,15 @@ static int build_self_tables(Ctx *c, double inv) {
         if (int(lps.size()) == lp0) continue;
         for (int k = links[a].cl_begin; k < links[a].cl_end; ++k)
           ida.insert(ida.end(), c->clusters[size_t(k)].members.begin(), c->clusters[size_t(k)].members.end());
-        SelfALink al = {links[a].x, links[a].y, links[a].z, links[a].R, lp0, int(lps.size()), int(a), 0};
+        SelfALink al;
+        std::vector<int> own;
+        for (int k = links[a].cl_begin; k < links[a].cl_end; ++k)
+          own.insert(own.end(), c->clusters[size_t(k)].members.begin(), c->clusters[size_t(k)].members.end());
+        box_of(own, al.lo, al.hi);
+        al.lp_begin = lp0;
+        al.lp_end = int(lps.size());
+        al.a = int(a);
+        al.pad[0] = al.pad[1] = al.pad[2] = 0;
         als.push_back(al);
       }
       if (int(als.size()) == al0) continue;

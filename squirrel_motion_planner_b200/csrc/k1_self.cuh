@@ -21,6 +21,12 @@ __device__ __forceinline__ float self_dist2(float ax, float ay, float az, float 
   const float dx = ax - bx, dy = ay - by, dz = az - bz;
   return fmaf(dx, dx, fmaf(dy, dy, dz * dz));
 }
+// squared distance from a point to an axis-aligned box
+__device__ __forceinline__ float self_box_dist2(float px, float py, float pz, const float (&lo)[3], const float (&hi)[3]) {
+  const float dx = fmaxf(fmaxf(lo[0] - px, px - hi[0]), 0.0f), dy = fmaxf(fmaxf(lo[1] - py, py - hi[1]), 0.0f),
+              dz = fmaxf(fmaxf(lo[2] - pz, pz - hi[2]), 0.0f);
+  return fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+}
 // T = FA^-1 * FB: a point given in B's frame expressed in A's frame
 __device__ __forceinline__ void self_relative(const float (&FA)[12], const float (&FB)[12], float (&T)[12]) {
 #pragma unroll
@@ -36,7 +42,9 @@ __device__ __forceinline__ void self_relative(const float (&FA)[12], const float
 // groups.  A level of the hierarchy is entered only if the level above cannot rule it out: group pair -> (link of A,
 // group B) -> (cluster of A, group B) -> (cluster of A, link of B) -> cluster pair -> (cluster of A, leaf of B) -> leaf
 // pair: the A side (the base: twelve links, ~45 clusters) is narrowed down against the small bound of the whole B
-// group before the B side's many links are looked at.  Everything is expressed in A's
+// group before the B side's many links are looked at.  A-side bounds are axis-aligned BOXES in A's frame (they are
+// constants there, and flat shapes like the shell box or the drum fill a box far better than a sphere), B-side bounds
+// are spheres (they travel through the relative transform as points).  Everything is expressed in A's
 // frame, so the A side is tested as the constants it is.  LINK_HITS (diagnostics): no early exit, every colliding link
 // pair is recorded in link_pair_hit[64 * 64].
 template <bool LINK_HITS>
@@ -57,37 +65,28 @@ __device__ __forceinline__ bool self_collision(const SelfDev &sd, const float *f
     }
     for (int al = G.al_begin; al < G.al_end; ++al) {
       const SelfALink AL = sd.alinks[al];
-      {
-        const float ra = AL.R + G.RB;
-        if (self_dist2(gx, gy, gz, AL.x, AL.y, AL.z) > ra * ra) continue;   // this A link is out of reach of all of B
-      }
+      if (self_box_dist2(gx, gy, gz, AL.lo, AL.hi) > G.RB * G.RB) continue;   // this A link is out of reach of all of B
       const SelfLink LA = sd.links[AL.a];
       for (int ca = LA.cl_begin; ca < LA.cl_end; ++ca) {
         const SelfCluster CA = sd.clusters[ca];
-        {
-          const float rc = CA.R + G.RB;
-          if (self_dist2(gx, gy, gz, CA.x, CA.y, CA.z) > rc * rc) continue;   // ... and so is this cluster of it
-        }
+        if (self_box_dist2(gx, gy, gz, CA.lo, CA.hi) > G.RB * G.RB) continue;   // ... and so is this cluster of it
         for (int lp = AL.lp_begin; lp < AL.lp_end; ++lp) {
           const SelfLink LB = sd.links[sd.lpairs[lp]];
           if (LINK_HITS && link_pair_hit[min(LA.link, LB.link) * SQMP_MAX_LINKS + max(LA.link, LB.link)]) continue;
           float px, py, pz;
           self_xform(T, LB.x, LB.y, LB.z, px, py, pz);
-          const float rl = CA.R + LB.R;
-          if (self_dist2(px, py, pz, CA.x, CA.y, CA.z) > rl * rl) continue;
+          if (self_box_dist2(px, py, pz, CA.lo, CA.hi) > LB.R * LB.R) continue;
           bool pair_hit = false;
           for (int cb = LB.cl_begin; cb < LB.cl_end && !pair_hit; ++cb) {
             const SelfCluster CB = sd.clusters[cb];
             float qx, qy, qz;
             self_xform(T, CB.x, CB.y, CB.z, qx, qy, qz);
-            const float r2 = CA.R + CB.R;
-            if (self_dist2(qx, qy, qz, CA.x, CA.y, CA.z) > r2 * r2) continue;
+            if (self_box_dist2(qx, qy, qz, CA.lo, CA.hi) > CB.R * CB.R) continue;
             for (int b = CB.leaf_begin; b < CB.leaf_end && !pair_hit; ++b) {
               const SelfLeaf Bl = sd.leaves[b];
               float bx, by, bz;
               self_xform(T, Bl.x, Bl.y, Bl.z, bx, by, bz);
-              const float r3 = CA.R + Bl.r;
-              if (self_dist2(bx, by, bz, CA.x, CA.y, CA.z) > r3 * r3) continue;
+              if (self_box_dist2(bx, by, bz, CA.lo, CA.hi) > Bl.r * Bl.r) continue;
               for (int a = CA.leaf_begin; a < CA.leaf_end; ++a) {
                 const SelfLeaf Al = sd.leaves[a];
                 const float rs = Al.r + Bl.r;

@@ -139,21 +139,22 @@ struct FastDev {
 struct SelfLeaf {   // 16 bytes
   float x, y, z, r;
 };
-struct SelfCluster {   // 32 bytes: bounding sphere + leaf range
+struct SelfCluster {   // 48 bytes: bounding sphere (its role on the B side), bounding box (its role on the A side), leaf range
   float x, y, z, R;
+  float lo[3], hi[3];     // axis-aligned box of its spheres in the group frame, padded like R: flat shapes (the shell box,
+                          // the drum) fill a box far better than a sphere, and the A side is tested as constants anyway
   int leaf_begin, leaf_end;
-  int pad[2];
 };
 struct SelfLink {   // 32 bytes: bounding sphere of a link + its clusters
   float x, y, z, R;
   int cl_begin, cl_end;
   int link, pad;
 };
-struct SelfALink {   // 32 bytes: a link of group A within one group pair, with the B-side links it is checked against
-  float x, y, z, R;       // the link's bound (A frame)
+struct SelfALink {   // 48 bytes: a link of group A within one group pair, with the B-side links it is checked against
+  float lo[3], hi[3];     // the link's bounding box (A frame), padded against fp32 rounding
   int lp_begin, lp_end;   // its partners in SelfDev::lpairs
   int a;                  // its record in SelfDev::links (clusters)
-  int pad;
+  int pad[3];
 };
 struct SelfGroupPair {   // 48 bytes
   int fa, fb;             // frame slots of the two groups (RobotDev::grp_fidx)
