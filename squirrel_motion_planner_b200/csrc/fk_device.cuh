@@ -36,6 +36,23 @@ static __constant__ double SQMP_SC64[18] = {
 // the body without the large-argument test (callers that have checked |x| < 1e5 for all their angles up front run it as
 // straight-line code, which lets the compiler interleave independent chains)
 __device__ __forceinline__ void sincos64_small(double x, double *sn, double *cs);
+#ifdef SQMP_SINCOS_NOINLINE
+// One copy per kernel instead of one per chain segment (validity_fast.cu): with every segment's sincos inlined the
+// validity kernel grows past the instruction cache (no_instruction became its top stall reason).  Values travel in
+// registers (double2 / float2 by value), not through the stack.
+static __device__ __noinline__ double2 sincos64_call(double x) {
+  double s, c;
+  if (!(fabs(x) < 1.0e5)) sincos(x, &s, &c);
+  else sincos64_small(x, &s, &c);
+  return make_double2(s, c);
+}
+template <>
+__device__ __forceinline__ void sincos_t<double>(double x, double *sn, double *cs) {
+  const double2 v = sincos64_call(x);
+  *sn = v.x;
+  *cs = v.y;
+}
+#else
 template <>
 __device__ __forceinline__ void sincos_t<double>(double x, double *sn, double *cs) {
   if (!(fabs(x) < 1.0e5)) {
@@ -44,6 +61,7 @@ __device__ __forceinline__ void sincos_t<double>(double x, double *sn, double *c
   }
   sincos64_small(x, sn, cs);
 }
+#endif
 __device__ __forceinline__ void sincos64_small(double x, double *sn, double *cs) {
   const double *C = SQMP_SC64;
   const double kd = rint(x * C[0]);
@@ -70,8 +88,24 @@ __device__ __forceinline__ void sincos64_small(double x, double *sn, double *cs)
 }
 
 // fp32 counterpart (Cody-Waite in three parts, cephes sinf/cosf kernels on [-pi/4, pi/4]): <= 2 ulp for |x| < 8e3.
+#ifdef SQMP_SINCOS_NOINLINE
+__device__ __forceinline__ void sincos32_body(float x, float *sn, float *cs);
+static __device__ __noinline__ float2 sincos32_call(float x) {
+  float s, c;
+  sincos32_body(x, &s, &c);
+  return make_float2(s, c);
+}
 template <>
 __device__ __forceinline__ void sincos_t<float>(float x, float *sn, float *cs) {
+  const float2 v = sincos32_call(x);
+  *sn = v.x;
+  *cs = v.y;
+}
+__device__ __forceinline__ void sincos32_body(float x, float *sn, float *cs) {
+#else
+template <>
+__device__ __forceinline__ void sincos_t<float>(float x, float *sn, float *cs) {
+#endif
   if (!(fabsf(x) < 8.0e3f)) {
     sincosf(x, sn, cs);
     return;
@@ -229,6 +263,7 @@ struct SigGeneric {
 struct SigRobotino {   // robotino_plan.urdf: x, y prismatic; theta about z; arm joints -y, +y, +z, -y, +z
   static constexpr bool generic = false;
   static constexpr int n = 8;
+  static constexpr int first_rot = 2;   // segments 0, 1 are the prismatic base
   __host__ __device__ static constexpr int type(int s) { return s < 2 ? SQMP_JOINT_TRANS : SQMP_JOINT_ROT; }
   __host__ __device__ static constexpr int axis(int s) {
     return s == 0 ? AX_PX : s == 1 ? AX_PY : s == 2 ? AX_PZ : s == 3 ? AX_NY : s == 4 ? AX_PY : s == 5 ? AX_PZ : s == 6 ? AX_NY : AX_PZ;

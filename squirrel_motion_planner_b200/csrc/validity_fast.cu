@@ -34,6 +34,11 @@
 // non-finite or absurd joint value is reported in collision (fail closed).
 #include <cstring>
 
+#ifndef SQMP_KF_INLINE_SINCOS
+// one sincos body per kernel instead of one per chain segment: 4000 -> 2900 instructions.  ncu had no_instructions (instruction
+// cache misses) as the top stall of the fully inlined kernel; out of line it is 4 % faster (0.378 -> 0.363 ms per 2^20 states)
+#define SQMP_SINCOS_NOINLINE
+#endif
 #include "k1_scan.cuh"
 #include "k1_self.cuh"
 
