@@ -100,7 +100,7 @@ struct Ctx {
   int fk_precision = 64;  // 64 | 32 (FK chain arithmetic of sqmp_fk; the validity kernels always walk the chain in fp64)
   int fk_float_ok = 0;
   int chain_specialization = 1;  // 1: use the compile-time unrolled chain when the description matches a known signature
-  int nn_variant = 0;     // 0 auto | 1 QT | 2 WQ
+  int nn_variant = 0;     // 0 auto | 1 QT | 2 WQ | 3 QT + fp32 pre-filter | 4 tensor-core pre-filter
   int64_t nn_hit_pool_bytes = int64_t(1) << 30;
   int64_t pipeline_chunk = 1 << 18;  // states per H2D/kernel/D2H pipeline stage
   std::string err;
@@ -637,15 +637,21 @@ static int tree_reserve(Ctx *c, TreeDev &t, int64_t need) {
   double *aos = nullptr;
   float4 *fa = nullptr, *fb = nullptr;
   float *fn = nullptr;
+  float4 *img = nullptr;
   e = cudaMalloc(&aos, size_t(pitch) * SQMP_DOF * sizeof(double));
   if (e == cudaSuccess && t.n > 0) e = cudaMemcpy(aos, t.aos, size_t(t.n) * SQMP_DOF * sizeof(double), cudaMemcpyDeviceToDevice);
   if (e == cudaSuccess) e = cudaMalloc(&fa, size_t(pitch) * sizeof(float4));
   if (e == cudaSuccess) e = cudaMalloc(&fb, size_t(pitch) * sizeof(float4));
   if (e == cudaSuccess) e = cudaMalloc(&fn, size_t(pitch) * sizeof(float));
+  // (cap is a multiple of 128: whole tiles; rows past n are never trusted by the scan, zero keeps them finite)
+  const size_t img_bytes = size_t((pitch + 127) / 128) * 12288;
+  if (e == cudaSuccess) e = cudaMalloc(&img, img_bytes);
+  if (e == cudaSuccess) e = cudaMemset(img, 0, img_bytes);
   if (e == cudaSuccess && t.n > 0) {
     e = cudaMemcpy(fa, t.fa, size_t(t.n) * sizeof(float4), cudaMemcpyDeviceToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(fb, t.fb, size_t(t.n) * sizeof(float4), cudaMemcpyDeviceToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(fn, t.fn, size_t(t.n) * sizeof(float), cudaMemcpyDeviceToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(img, t.img, size_t((t.n + 127) / 128) * 12288, cudaMemcpyDeviceToDevice);
   }
   if (e != cudaSuccess) {
     cudaFree(blk);
@@ -653,6 +659,7 @@ static int tree_reserve(Ctx *c, TreeDev &t, int64_t need) {
     if (fa) cudaFree(fa);
     if (fb) cudaFree(fb);
     if (fn) cudaFree(fn);
+    if (img) cudaFree(img);
     return fail(c, SQMP_ERR_NOMEM, "cudaMalloc(tree fp32 shadow)", e);
   }
   if (t.q[0]) cudaFree(t.q[0]);
@@ -661,6 +668,8 @@ static int tree_reserve(Ctx *c, TreeDev &t, int64_t need) {
   if (t.fa) cudaFree(t.fa);
   if (t.fb) cudaFree(t.fb);
   if (t.fn) cudaFree(t.fn);
+  if (t.img) cudaFree(t.img);
+  t.img = img;
   for (int d = 0; d < SQMP_DOF; ++d) t.q[d] = blk + int64_t(d) * pitch;
   t.cost = blk + int64_t(SQMP_DOF) * pitch;
   t.fa = fa; t.fb = fb; t.fn = fn;
@@ -678,13 +687,24 @@ static double sumsq_threshold(double r) {
 }
 
 static int pick_variant(const Ctx *c, int64_t Q) {
-  if (c->nn_variant >= 1 && c->nn_variant <= 3) return c->nn_variant;
+  if (c->nn_variant >= 1 && c->nn_variant <= 4) return c->nn_variant;
   return Q >= 2048 ? 3 : 2;
 }
 static int pick_chunk_hint(const Ctx *c, int variant, int64_t N, int64_t Q) {
   if (N <= 0) return 1;
   int64_t chunks;
-  if (variant == 1 || variant == 3) {
+  if (variant == 4) {
+    // one 320-thread CTA per SM: the fewest chunks (each restarts the search for the best) that fill whole waves
+    const int64_t qtiles = (Q + 255) / 256;
+    const int64_t maxc = (N + 4095) / 4096;
+    chunks = 1;
+    double best_eff = 0.0;
+    for (int64_t k = 1; k <= 16 && k <= maxc; ++k) {
+      const int64_t ctas = qtiles * k, waves = (ctas + c->sm_count - 1) / c->sm_count;
+      const double eff = double(ctas) / double(waves * c->sm_count);
+      if (eff > best_eff + 0.02) { best_eff = eff; chunks = k; }
+    }
+  } else if (variant == 1 || variant == 3) {
     const int64_t per = variant == 3 ? 256 : 128;   // queries per CTA (nn.cu: NN_THREADS * NN_QPT)
     const int64_t qtiles = (Q + per - 1) / per;
     chunks = (int64_t(c->sm_count) * 16 + qtiles - 1) / qtiles;
@@ -918,6 +938,7 @@ void sqmp_destroy(sqmp_ctx *ctx) {
     if (t.fa) cudaFree(t.fa);
     if (t.fb) cudaFree(t.fb);
     if (t.fn) cudaFree(t.fn);
+    if (t.img) cudaFree(t.img);
   }
   if (ctx->nn.part_d) cudaFree(ctx->nn.part_d);
   if (ctx->nn.part_id) cudaFree(ctx->nn.part_id);
@@ -953,7 +974,7 @@ int sqmp_set_option(sqmp_ctx *ctx, const char *name, int64_t value) {
   } else if (n == "chain_specialization") {
     c->chain_specialization = value != 0;
   } else if (n == "nn_variant") {
-    if (value < 0 || value > 3) return fail(c, SQMP_ERR_INVALID, "nn_variant must be 0..3");
+    if (value < 0 || value > 4) return fail(c, SQMP_ERR_INVALID, "nn_variant must be 0..4");
     c->nn_variant = int(value);
   } else if (n == "nn_hit_pool_bytes") {
     if (value < 4096) return fail(c, SQMP_ERR_INVALID, "nn_hit_pool_bytes too small");

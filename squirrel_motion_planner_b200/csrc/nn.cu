@@ -21,6 +21,7 @@
 #include <math_constants.h>
 
 #include "sqmp_common.cuh"
+#include "tc_umma.cuh"
 
 namespace sqmp {
 
@@ -33,6 +34,7 @@ struct TreePtrs {
   double *aos;
   float4 *fa, *fb;
   float *fn;
+  float4 *img;
 };
 static inline TreePtrs ptrs_of(const TreeDev &t) {
   TreePtrs p;
@@ -40,6 +42,7 @@ static inline TreePtrs ptrs_of(const TreeDev &t) {
   p.cost = t.cost;
   p.aos = t.aos;
   p.fa = t.fa; p.fb = t.fb; p.fn = t.fn;
+  p.img = t.img;
   return p;
 }
 // fp32 shadow of one node (see TreeDev)
@@ -54,6 +57,7 @@ __device__ __forceinline__ void write_shadow(const TreePtrs &t, int64_t i, const
   t.fa[i] = make_float4(f[0], f[1], f[2], f[3]);
   t.fb[i] = make_float4(f[4], f[5], f[6], f[7]);
   t.fn[i] = __double2float_rn(n2);
+  tc_write_node_row(t.img + (i >> 7) * TC_TILE_FLOAT4, int(i & 127), v);   // tf32 operand image (tc_umma.cuh)
 }
 
 // rows (AoS, n x 8) -> SoA at [first, first+n)
@@ -456,6 +460,208 @@ k_nn_qt_pf(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// TC ("tensor-core pre-filter", many queries): the estimate of every (query, node) pair comes out of tcgen05.mma
+// instead of nine FFMA2 per pair.  A CTA keeps TC_QTILES x 128 queries as the A operand in shared memory and streams
+// its node chunk through a ring of 12 KB tile images (bulk async copies, one elected thread); one elected thread issues
+// four K = 8 MMAs per (query tile, node tile) into a double-buffered TMEM accumulator (tc_umma.cuh); the epilogue
+// warps read their query's row of it (one TMEM lane per thread, 32 columns per tcgen05.ld), take the minimum of the 32
+// estimates with three-input min and only look at individual columns when that minimum passes the thread's threshold.
+// Everything that passes is re-evaluated exactly (exact_s) and compared exactly — the same contract as QT/PF, so the
+// answers are bit-identical; the band is wider (tf32 pieces: NN_TC_EPS R^2 instead of a few fp32 ulps) and still
+// admits < 0.1 extra exact evaluations per query on the benchmark's tree.
+//
+// Error bound of the estimate v = D[query][node] against t = |n|^2 - 2 q.n in real arithmetic, R >= |q|, |n|:
+//   operands:      q = qh + qm + eq, n = nh + nm + en with |eq| <= 2^-21 |q_d|, |en| <= 2^-21 |n_d| (fp32 rounding of the
+//                  fp64 value + two tf32 roundings); the dropped terms qm.nm, eq.n, q.en add up to <= 2.5 * 2^-21 R^2 in 2 q.n
+//   |n|^2 pieces:  <= 2^-30 R^2
+//   accumulation:  25 exact products of magnitude <= R^2 summed by the tensor core over four instructions; budgeted
+//                  2^-15 R^2 (a per-addition error of 2^-22 of the running magnitude 4 R^2, i.e. two fp32 ulps, 32 times).
+//                  The hardware's accumulation order is not documented, which is why the budget is 60 times the error the
+//                  probe (tools/tc_probe.cu) and the parity tests observe (2^-21 R^2).
+//   total          < 2^-14 R^2 = NN_TC_EPS R^2.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TC_QTILES = 2;                       // query tiles per CTA: every node tile is multiplied by both
+constexpr int TC_STAGES = 4;                       // node tiles in flight
+constexpr int TC_EPI_WARPS = 4 * TC_QTILES;        // one warp per (query tile, TMEM lane quarter)
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS; // warp 0: copies, warp 1: MMA issue + TMEM allocation, then the epilogue warps
+constexpr int TC_TMEM_COLS = 2 * TC_QTILES * TC_ROWS;   // two accumulator buffers x query tiles x 128 columns = 512
+constexpr int TC_SMEM_BYTES = (TC_QTILES + TC_STAGES) * TC_TILE_BYTES + 128;
+constexpr double NN_TC_EPS = 1.0 / 16384.0;
+
+struct TcQuery {          // one epilogue thread = one query
+  const double *q;        // its row (nullptr: inactive)
+  int64_t qi;
+  double qq, E;           // |q|^2 and the estimate's error bound
+  Best best;
+  int32_t excl;
+};
+// nearest: exact evaluation of a surviving pair; returns the new threshold
+__device__ __noinline__ float tc_offer(const TreePtrs &t, TcQuery &me, int64_t n, float thr) {
+  const double s = exact_s(t, n, me.q);
+  const double before = me.best.s;
+  offer(me.best, s, int32_t(n));
+  return me.best.s != before ? __double2float_ru(me.best.s + me.E - me.qq) : thr;
+}
+// radius: proven hit, or exact evaluation inside the band
+__device__ __noinline__ void tc_hit(const TreePtrs &t, const TcQuery &me, int64_t n, bool proven, double s_thr,
+                                    int32_t *__restrict__ count, int32_t *__restrict__ hits, int64_t hit_cap) {
+  if (!proven) proven = exact_s(t, n, me.q) < s_thr;
+  if (proven && int32_t(n) != me.excl) {
+    const int32_t slot = atomicAdd(&count[me.qi], 1);
+    if (slot < hit_cap) hits[me.qi * hit_cap + slot] = int32_t(n);
+  }
+}
+
+template <bool RADIUS>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ queries, int64_t Q, double rmax2,
+        double *__restrict__ part_d, int32_t *__restrict__ part_id,
+        const int32_t *__restrict__ exclude, double s_thr, int32_t *__restrict__ count, int32_t *__restrict__ hits,
+        int64_t hit_cap) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char *sA = smem, *sB = smem + TC_QTILES * TC_TILE_BYTES;
+  uint64_t *full = reinterpret_cast<uint64_t *>(sB + TC_STAGES * TC_TILE_BYTES);   // node tile landed
+  uint64_t *empty = full + TC_STAGES;                                               // its MMAs are done
+  uint64_t *acc_full = empty + TC_STAGES;                                           // [2] accumulator buffer written
+  uint64_t *acc_empty = acc_full + 2;                                               // [2] ... and read by every epilogue warp
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n0 = int64_t(blockIdx.y) * chunk_len, n1 = min(N, n0 + chunk_len);
+  const int n_tiles = n0 < n1 ? int((n1 - n0 + TC_ROWS - 1) / TC_ROWS) : 0;
+  const float4 *img = t.img + (n0 / TC_ROWS) * TC_TILE_FLOAT4;
+
+  // ---- set-up: barriers, TMEM, the queries as the A operand
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TC_STAGES; ++i) { tc_mbar_init(&full[i], 1); tc_mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc_mbar_init(&acc_full[i], 1); tc_mbar_init(&acc_empty[i], TC_EPI_WARPS); }
+    tc_fence_mbar_init();
+  }
+  if (warp == 1) tc_tmem_alloc(tmem_slot, TC_TMEM_COLS);
+  TcQuery me;
+  float thr = -CUDART_INF_F, thr_lo = -CUDART_INF_F;   // inactive: nothing passes
+  const int qt = (warp - 2) >> 2, quarter = warp & 3;   // a warp may only read TMEM lanes [32 (warp % 4), +32)
+  if (warp >= 2) {
+    const int row = quarter * 32 + lane;
+    me.qi = (int64_t(blockIdx.x) * TC_QTILES + qt) * TC_ROWS + row;
+    me.q = me.qi < Q ? queries + me.qi * SQMP_DOF : nullptr;
+    double v[SQMP_DOF];
+    me.qq = 0.0;
+#pragma unroll
+    for (int d = 0; d < SQMP_DOF; ++d) {
+      v[d] = me.q ? me.q[d] : 0.0;
+      me.qq += v[d] * v[d];
+    }
+    tc_write_query_row(reinterpret_cast<float4 *>(sA + qt * TC_TILE_BYTES), row, v);
+    me.E = NN_TC_EPS * fmax(rmax2, me.qq) * 1.000001;
+    me.best.s = NN_INIT_SUMSQ; me.best.d = NN_INIT_DIST; me.best.id = 0;
+    me.excl = (RADIUS && me.q && exclude) ? exclude[me.qi] : -1;
+    if (me.q) {
+      if (RADIUS) {
+        thr = __double2float_ru(s_thr + me.E - me.qq);      // v >= thr: proven miss
+        thr_lo = __double2float_rd(s_thr - me.E - me.qq);   // v <  thr_lo: proven hit
+      } else {
+        thr = __double2float_ru(NN_INIT_SUMSQ + me.E - me.qq);
+      }
+    }
+    tc_fence_async_smem();   // the A operand was written through the generic proxy; the tensor core reads through the async one
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ---- copies: one thread keeps TC_STAGES node tiles in flight
+    if (lane == 0) {
+      for (int it = 0; it < n_tiles; ++it) {
+        const int s = it % TC_STAGES;
+        tc_mbar_wait(&empty[s], ((it / TC_STAGES) & 1) ^ 1);
+        tc_mbar_expect_tx(&full[s], TC_TILE_BYTES);
+        tc_bulk_g2s(sB + s * TC_TILE_BYTES, img + int64_t(it) * TC_TILE_FLOAT4, TC_TILE_BYTES, &full[s]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---- MMA issue: one thread
+    if (lane == 0) {
+      const uint32_t a_base = tc_smem_u32(sA), b_base = tc_smem_u32(sB);
+      for (int it = 0; it < n_tiles; ++it) {
+        const int s = it % TC_STAGES, buf = it & 1;
+        tc_mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+        tc_mbar_wait(&full[s], (it / TC_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t b = b_base + s * TC_TILE_BYTES;
+        const uint64_t b_hi = tc_desc(b), b_mid = tc_desc(b + 2 * TC_CHUNK_BYTES), b_nrm = tc_desc(b + 4 * TC_CHUNK_BYTES);
+#pragma unroll
+        for (int k = 0; k < TC_QTILES; ++k) {
+          const uint32_t a = a_base + k * TC_TILE_BYTES, d = tmem + uint32_t((buf * TC_QTILES + k) * TC_ROWS);
+          const uint64_t a_hi = tc_desc(a), a_mid = tc_desc(a + 2 * TC_CHUNK_BYTES), a_one = tc_desc(a + 4 * TC_CHUNK_BYTES);
+          tc_mma_tf32(d, a_hi, b_hi, false);
+          tc_mma_tf32(d, a_mid, b_hi, true);
+          tc_mma_tf32(d, a_hi, b_mid, true);
+          tc_mma_tf32(d, a_one, b_nrm, true);
+        }
+        tc_commit(&empty[s]);        // the tile's slot may be refilled
+        tc_commit(&acc_full[buf]);   // the accumulators may be read
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---- epilogue: this thread's query against every node of the chunk
+    for (int it = 0; it < n_tiles; ++it) {
+      const int buf = it & 1;
+      const int64_t base = n0 + int64_t(it) * TC_ROWS;
+      tc_mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem + (uint32_t(quarter * 32) << 16) + uint32_t((buf * TC_QTILES + qt) * TC_ROWS);
+      float va[32], vb[32];
+      tc_tmem_ld32(taddr, va);
+      tc_tmem_ld_wait();
+      auto group = [&](const float (&v)[32], int c) {
+        float m = tc_min3(v[0], v[1], v[2]);
+#pragma unroll
+        for (int j = 3; j + 1 < 32; j += 2) m = tc_min3(m, v[j], v[j + 1]);
+        m = fminf(m, v[31]);
+        if (m < thr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int64_t n = base + c + j;
+            if (v[j] < thr && n < n1) {
+              if (RADIUS) tc_hit(t, me, n, v[j] < thr_lo, s_thr, count, hits, hit_cap);
+              else thr = tc_offer(t, me, n, thr);
+            }
+          }
+        }
+      };
+      // the next 32 columns are on their way while these are scanned
+      tc_tmem_ld32(taddr + 32, vb);
+      group(va, 0);
+      tc_tmem_ld_wait();
+      tc_tmem_ld32(taddr + 64, va);
+      group(vb, 32);
+      tc_tmem_ld_wait();
+      tc_tmem_ld32(taddr + 96, vb);
+      group(va, 64);
+      tc_tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc_mbar_arrive(&acc_empty[buf]);   // the buffer's columns are in registers: it may be overwritten
+      group(vb, 96);
+    }
+    if (!RADIUS && me.q) {
+      part_d[int64_t(blockIdx.y) * Q + me.qi] = me.best.d;
+      part_id[int64_t(blockIdx.y) * Q + me.qi] = me.best.id;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_tmem_free(tmem, TC_TMEM_COLS);
+  }
+}
+
 // fold the per-chunk partial results in chunk (= id) order; strict '<' keeps the lowest id on ties (BS:4122)
 __global__ void k_nn_merge(const double *__restrict__ part_d, const int32_t *__restrict__ part_id, int chunks,
                            int64_t Q, int32_t *__restrict__ id_out) {
@@ -779,11 +985,17 @@ cudaError_t launch_nn_single(const TreeDev &t, const double *h_query, bool radiu
 // ---------------------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------------------
+// the tensor-core scan needs more dynamic shared memory than the default limit (a per-device attribute: set per launch)
+static cudaError_t tc_prepare() {
+  cudaError_t e = cudaFuncSetAttribute(k_nn_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_nn_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  return e;
+}
 static void pick_chunks(int64_t N, int64_t Q, int variant, int chunks_hint, int &chunks, int64_t &chunk_len) {
   (void)Q;
   chunks = chunks_hint < 1 ? 1 : chunks_hint;
   chunk_len = (N + chunks - 1) / chunks;
-  const int64_t gran = variant == 2 ? 32 : NN_TILE;   // variants 1 and 3 stream NN_TILE-node tiles
+  const int64_t gran = variant == 2 ? 32 : NN_TILE;   // variants 1, 3 and 4 stream NN_TILE-node tiles (two TC tiles)
   chunk_len = ((chunk_len + gran - 1) / gran) * gran;
   if (chunk_len < gran) chunk_len = gran;
   chunks = int((N + chunk_len - 1) / chunk_len);
@@ -796,7 +1008,13 @@ cudaError_t launch_nn_nearest(const TreeDev &t, const double *d_queries, int64_t
   int chunks;
   int64_t chunk_len;
   pick_chunks(t.n, Q, variant, chunks_hint, chunks, chunk_len);
-  if (variant == 3) {
+  if (variant == 4) {
+    cudaError_t ea = tc_prepare();
+    if (ea != cudaSuccess) return ea;
+    dim3 grid(unsigned((Q + TC_QTILES * TC_ROWS - 1) / (TC_QTILES * TC_ROWS)), unsigned(chunks));
+    k_nn_tc<false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ptrs_of(t), t.n, chunk_len, d_queries, Q, t.rmax2, sc.part_d,
+                                                           sc.part_id, nullptr, 0.0, nullptr, nullptr, 0);
+  } else if (variant == 3) {
     dim3 grid(unsigned((Q + NN_THREADS * NN_QPT - 1) / (NN_THREADS * NN_QPT)), unsigned(chunks));
     k_nn_qt_pf<false><<<grid, NN_THREADS, 0, st>>>(ptrs_of(t), t.n, chunk_len, d_queries, Q, t.rmax2, sc.part_d,
                                                    sc.part_id, nullptr, 0.0, 0.0, nullptr, nullptr, 0);
@@ -824,7 +1042,13 @@ cudaError_t launch_nn_radius(const TreeDev &t, const double *d_queries, const in
   pick_chunks(t.n, Q, variant, chunks_hint, chunks, chunk_len);
   cudaError_t e = cudaMemsetAsync(d_count, 0, size_t(Q) * sizeof(int32_t), st);
   if (e != cudaSuccess) return e;
-  if (variant == 3) {
+  if (variant == 4) {
+    cudaError_t ea = tc_prepare();
+    if (ea != cudaSuccess) return ea;
+    dim3 grid(unsigned((Q + TC_QTILES * TC_ROWS - 1) / (TC_QTILES * TC_ROWS)), unsigned(chunks));
+    k_nn_tc<true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ptrs_of(t), t.n, chunk_len, d_queries, Q, t.rmax2, nullptr, nullptr,
+                                                          d_exclude, s_thr, d_count, sc.hits, sc.hit_cap);
+  } else if (variant == 3) {
     dim3 grid(unsigned((Q + NN_THREADS * NN_QPT - 1) / (NN_THREADS * NN_QPT)), unsigned(chunks));
     k_nn_qt_pf<true><<<grid, NN_THREADS, 0, st>>>(ptrs_of(t), t.n, chunk_len, d_queries, Q, t.rmax2, nullptr, nullptr,
                                                   d_exclude, s_thr, r, d_count, sc.hits, sc.hit_cap);

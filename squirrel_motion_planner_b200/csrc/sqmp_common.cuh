@@ -231,6 +231,8 @@ struct TreeDev {
   // fn[n] = |float node|^2 (fp64 sum rounded once)
   float4 *fa, *fb;
   float *fn;
+  // tf32 operand image of the nodes for the tensor-core scan (tc_umma.cuh): one 12 KB record per 128-node tile
+  float4 *img;
   double rmax2;          // upper bound of |node|^2 over every node written since the last reset (host-tracked)
   int64_t n, cap;
 };
@@ -246,7 +248,7 @@ struct NNScratch {
   int32_t *hits;       // [Q][hit_cap]
   int64_t hit_cap;
 };
-// variant: 1 QT fp64-only, 2 WQ fp64-only, 3 QT with fp32 pre-filter (default for many queries)
+// variant: 1 QT fp64-only, 2 WQ fp64-only, 3 QT with fp32 pre-filter, 4 tensor-core pre-filter (default for many queries)
 cudaError_t launch_nn_nearest(const TreeDev &t, const double *d_queries, int64_t Q, int32_t *d_id, NNScratch &sc,
                               int chunks, int variant, cudaStream_t st, int *n_launch);
 // one query, one launch, result in mapped pinned host memory (nn.cu: k_nn_single)

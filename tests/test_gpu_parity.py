@@ -516,7 +516,7 @@ def test_fk_matches_oracle_and_golden(ctx, orc, prec, specialized):
 
 
 # --------------------------------------------------------------------------------------- near neighbours
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 def test_nearest_bit_exact(ctx, variant):
     ctx.set_option("nn_variant", variant)
     try:
@@ -537,7 +537,7 @@ def test_nearest_bit_exact(ctx, variant):
         ctx.set_option("nn_variant", 0)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 def test_nn_against_reference_golden(ctx, variant):
     """tests/golden/nn_reference.npz = outputs of the reference's own DistanceHeuristics + Node::operator< / std::sort
     (compiled from /root/reference by oracle/Makefile.ref): ids bit-exact; within a group of equal cost the reference's
@@ -580,7 +580,7 @@ def test_nearest_quirks_and_tree_mutation(ctx):
     assert ctx.tree_size(2) == 0
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 def test_radius_topk_bit_exact(ctx, variant):
     ctx.set_option("nn_variant", variant)
     try:
@@ -662,12 +662,13 @@ def test_multi_tree_queries_equal_single_tree_calls(ctx):
         ctx.nn_nearest_multi(np.array([5000], dtype=np.int32), queries[:1])
 
 
-def test_fp32_prefilter_is_sound_on_adversarial_trees(ctx):
-    """Variant 3 decides most pairs from an fp32 estimate with a proven error bound; anything inside the bound must fall
-    through to the exact fp64 test.  Trees built to sit inside that bound: clusters whose members differ by 1e-13..1e-7
+@pytest.mark.parametrize("variant", [3, 4])
+def test_fp32_prefilter_is_sound_on_adversarial_trees(ctx, variant):
+    """Variants 3 (fp32 FMA) and 4 (tf32 tensor-core pieces) decide most pairs from an estimate with an error bound;
+    anything inside the bound must fall through to the exact fp64 test.  Trees built to sit inside that bound: clusters whose members differ by 1e-13..1e-7
     (indistinguishable in fp32), coordinates offset by 1e3 / 1e6 (huge cancellation), radius shells at r +- 1e-12."""
     rng = np.random.default_rng(77)
-    ctx.set_option("nn_variant", 3)
+    ctx.set_option("nn_variant", variant)
     try:
         for trial, (offset, jitter) in enumerate(((0.0, 1e-13), (0.0, 1e-8), (1.0e3, 1e-9), (1.0e6, 1e-6), (0.0, 1e-4))):
             centres = syn.sample_configs(40, seed=500 + trial) + offset

@@ -4,6 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from squirrel_motion_planner_b200 import api, synthetic as syn
 ctx = api.default_context(0)
+ctx.set_option("nn_variant", int(os.environ.get("NN_VARIANT", "0")))
 st = torch.cuda.current_stream().cuda_stream
 N, Q = 1 << 20, 1 << 16
 nodes, cost = syn.random_tree(N, 7, 9)
