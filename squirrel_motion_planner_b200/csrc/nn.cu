@@ -486,33 +486,15 @@ constexpr int TC_STAGES = 4;                       // node tiles in flight
 constexpr int TC_EPI_WARPS = 4 * TC_QTILES;        // one warp per (query tile, TMEM lane quarter)
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS; // warp 0: copies, warp 1: MMA issue + TMEM allocation, then the epilogue warps
 constexpr int TC_TMEM_COLS = 2 * TC_QTILES * TC_ROWS;   // two accumulator buffers x query tiles x 128 columns = 512
-constexpr int TC_SMEM_BYTES = (TC_QTILES + TC_STAGES) * TC_TILE_BYTES + 128;
+constexpr int TC_SMEM_BYTES = (TC_QTILES + TC_STAGES) * TC_TILE_BYTES + 128 + TC_EPI_WARPS * 64 * 4;   // tiles, barriers, warp queues
 constexpr double NN_TC_EPS = 1.0 / 16384.0;
 
-struct TcQuery {          // one epilogue thread = one query
-  const double *q;        // its row (nullptr: inactive)
-  int64_t qi;
-  double qq, E;           // |q|^2 and the estimate's error bound
-  Best best;
-  int32_t excl;
-};
-// nearest: exact evaluation of a surviving pair; returns the new threshold
-__device__ __noinline__ float tc_offer(const TreePtrs &t, TcQuery &me, int64_t n, float thr) {
-  const double s = exact_s(t, n, me.q);
-  const double before = me.best.s;
-  offer(me.best, s, int32_t(n));
-  return me.best.s != before ? __double2float_ru(me.best.s + me.E - me.qq) : thr;
-}
-// radius: proven hit, or exact evaluation inside the band
-__device__ __noinline__ void tc_hit(const TreePtrs &t, const TcQuery &me, int64_t n, bool proven, double s_thr,
-                                    int32_t *__restrict__ count, int32_t *__restrict__ hits, int64_t hit_cap) {
-  if (!proven) proven = exact_s(t, n, me.q) < s_thr;
-  if (proven && int32_t(n) != me.excl) {
-    const int32_t slot = atomicAdd(&count[me.qi], 1);
-    if (slot < hit_cap) hits[me.qi * hit_cap + slot] = int32_t(n);
-  }
-}
-
+constexpr int TC_WQ_CAP = 64;   // surviving pairs a warp holds back until 32 of them can be evaluated side by side
+#ifdef SQMP_TC_NO_LD   // bring-up aid: the pipeline without the accumulator reads
+#define TC_LD(a, v) do { for (int i_ = 0; i_ < 32; ++i_) v[i_] = 1e30f + float(a); } while (0)
+#else
+#define TC_LD(a, v) tc_tmem_ld32(a, v)
+#endif
 template <bool RADIUS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ queries, int64_t Q, double rmax2,
@@ -538,30 +520,31 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
     tc_fence_mbar_init();
   }
   if (warp == 1) tc_tmem_alloc(tmem_slot, TC_TMEM_COLS);
-  TcQuery me;
+  // one epilogue thread = one query: its threshold(s) on the accumulator value v = |n|^2 - 2 q.n and its incumbent
   float thr = -CUDART_INF_F, thr_lo = -CUDART_INF_F;   // inactive: nothing passes
+  double qq = 0.0, E = 0.0;
+  Best best;
+  best.s = NN_INIT_SUMSQ; best.d = NN_INIT_DIST; best.id = 0;
+  int32_t excl = -1;
   const int qt = (warp - 2) >> 2, quarter = warp & 3;   // a warp may only read TMEM lanes [32 (warp % 4), +32)
+  const int64_t qi0 = (int64_t(blockIdx.x) * TC_QTILES + qt) * TC_ROWS + quarter * 32;   // query of lane 0
+  const bool live = warp >= 2 && qi0 + lane < Q;
   if (warp >= 2) {
-    const int row = quarter * 32 + lane;
-    me.qi = (int64_t(blockIdx.x) * TC_QTILES + qt) * TC_ROWS + row;
-    me.q = me.qi < Q ? queries + me.qi * SQMP_DOF : nullptr;
     double v[SQMP_DOF];
-    me.qq = 0.0;
 #pragma unroll
     for (int d = 0; d < SQMP_DOF; ++d) {
-      v[d] = me.q ? me.q[d] : 0.0;
-      me.qq += v[d] * v[d];
+      v[d] = live ? queries[(qi0 + lane) * SQMP_DOF + d] : 0.0;
+      qq += v[d] * v[d];
     }
-    tc_write_query_row(reinterpret_cast<float4 *>(sA + qt * TC_TILE_BYTES), row, v);
-    me.E = NN_TC_EPS * fmax(rmax2, me.qq) * 1.000001;
-    me.best.s = NN_INIT_SUMSQ; me.best.d = NN_INIT_DIST; me.best.id = 0;
-    me.excl = (RADIUS && me.q && exclude) ? exclude[me.qi] : -1;
-    if (me.q) {
+    tc_write_query_row(reinterpret_cast<float4 *>(sA + qt * TC_TILE_BYTES), quarter * 32 + lane, v);
+    E = NN_TC_EPS * fmax(rmax2, qq) * 1.000001;
+    if (live) {
+      excl = (RADIUS && exclude) ? exclude[qi0 + lane] : -1;
       if (RADIUS) {
-        thr = __double2float_ru(s_thr + me.E - me.qq);      // v >= thr: proven miss
-        thr_lo = __double2float_rd(s_thr - me.E - me.qq);   // v <  thr_lo: proven hit
+        thr = __double2float_ru(s_thr + E - qq);      // v >= thr: proven miss
+        thr_lo = __double2float_rd(s_thr - E - qq);   // v <  thr_lo: proven hit
       } else {
-        thr = __double2float_ru(NN_INIT_SUMSQ + me.E - me.qq);
+        thr = __double2float_ru(NN_INIT_SUMSQ + E - qq);
       }
     }
     tc_fence_async_smem();   // the A operand was written through the generic proxy; the tensor core reads through the async one
@@ -608,7 +591,41 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
     }
     __syncwarp();
   } else {
-    // ---- epilogue: this thread's query against every node of the chunk
+    // ---- epilogue: this thread's query against every node of the chunk.  Pairs whose estimate passes the threshold are
+    //      not evaluated on the spot (one lane's exact evaluation would stall the warp for an L2 round trip per pair): they
+    //      go to the warp's queue as (node, owner lane, proven) and are evaluated 32 at a time, one pair per lane.
+    uint32_t *wq = reinterpret_cast<uint32_t *>(tmem_slot + 4) + (warp - 2) * TC_WQ_CAP;
+    int qn = 0;   // entries in the queue (warp-uniform)
+    const unsigned lt_mask = (1u << lane) - 1u;
+    auto drain = [&](int cnt) {   // the first cnt (<= 32) entries
+      const bool have = lane < cnt;
+      const uint32_t e = have ? wq[lane] : 0u;
+      const int owner = int(e >> 1) & 31;
+      const int64_t n = n0 + int64_t(e >> 6);
+      double s = CUDART_INF;
+      if (have && !(RADIUS && (e & 1u))) s = exact_s(t, n, queries + (qi0 + owner) * SQMP_DOF);
+      if (RADIUS) {
+        const int32_t ex = __shfl_sync(0xffffffffu, excl, owner);
+        if (have && ((e & 1u) || s < s_thr) && int32_t(n) != ex) {
+          const int32_t slot = atomicAdd(&count[qi0 + owner], 1);
+          if (slot < hit_cap) hits[(qi0 + owner) * hit_cap + slot] = int32_t(n);
+        }
+      } else {
+        const double before = best.s;
+        for (int i = 0; i < cnt; ++i) {   // entries of one owner are in increasing node order, as offer() expects
+          const double si = __shfl_sync(0xffffffffu, s, i);
+          const uint32_t ei = __shfl_sync(0xffffffffu, e, i);
+          if (lane == (int(ei >> 1) & 31)) offer(best, si, int32_t(n0 + int64_t(ei >> 6)));
+        }
+        if (best.s != before) thr = __double2float_ru(best.s + E - qq);
+      }
+      __syncwarp();
+      const uint32_t moved = lane + 32 < qn ? wq[lane + 32] : 0u;
+      __syncwarp();
+      if (lane + 32 < qn) wq[lane] = moved;
+      qn -= cnt;
+      __syncwarp();
+    };
     for (int it = 0; it < n_tiles; ++it) {
       const int buf = it & 1;
       const int64_t base = n0 + int64_t(it) * TC_ROWS;
@@ -616,32 +633,48 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
       tc_fence_after();
       const uint32_t taddr = tmem + (uint32_t(quarter * 32) << 16) + uint32_t((buf * TC_QTILES + qt) * TC_ROWS);
       float va[32], vb[32];
-      tc_tmem_ld32(taddr, va);
+      TC_LD(taddr, va);
       tc_tmem_ld_wait();
       auto group = [&](const float (&v)[32], int c) {
+#ifdef SQMP_TC_LD_ONLY
+        if (v[0] == 123.456f && v[17] == 1.0f) thr = 0.f;
+        return;
+#endif
         float m = tc_min3(v[0], v[1], v[2]);
 #pragma unroll
         for (int j = 3; j + 1 < 32; j += 2) m = tc_min3(m, v[j], v[j + 1]);
         m = fminf(m, v[31]);
-        if (m < thr) {
+        unsigned any = __ballot_sync(0xffffffffu, m < thr);
+        if (any) {   // warp-uniform, rare
+          uint32_t cm = 0u, pm = 0u;   // columns that pass / that are proven hits
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int64_t n = base + c + j;
-            if (v[j] < thr && n < n1) {
-              if (RADIUS) tc_hit(t, me, n, v[j] < thr_lo, s_thr, count, hits, hit_cap);
-              else thr = tc_offer(t, me, n, thr);
-            }
+          for (int j = 0; j < 32; ++j) cm |= v[j] < thr ? 1u << j : 0u;
+          if (RADIUS) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) pm |= v[j] < thr_lo ? 1u << j : 0u;
+          }
+          while (any) {   // one owner at a time; lane j files column j
+            const int owner = __ffs(any) - 1;
+            any &= any - 1u;
+            const uint32_t cmo = __shfl_sync(0xffffffffu, cm, owner), pmo = __shfl_sync(0xffffffffu, pm, owner);
+            const int64_t n = base + c + lane;
+            const bool mine = ((cmo >> lane) & 1u) && n < n1;
+            const unsigned bal = __ballot_sync(0xffffffffu, mine);
+            if (mine) wq[qn + __popc(bal & lt_mask)] = uint32_t(n - n0) << 6 | uint32_t(owner) << 1 | ((pmo >> lane) & 1u);
+            qn += __popc(bal);
+            __syncwarp();
+            if (qn >= 32) drain(32);
           }
         }
       };
       // the next 32 columns are on their way while these are scanned
-      tc_tmem_ld32(taddr + 32, vb);
+      TC_LD(taddr + 32, vb);
       group(va, 0);
       tc_tmem_ld_wait();
-      tc_tmem_ld32(taddr + 64, va);
+      TC_LD(taddr + 64, va);
       group(vb, 32);
       tc_tmem_ld_wait();
-      tc_tmem_ld32(taddr + 96, vb);
+      TC_LD(taddr + 96, vb);
       group(va, 64);
       tc_tmem_ld_wait();
       tc_fence_before();
@@ -649,9 +682,10 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
       if (lane == 0) tc_mbar_arrive(&acc_empty[buf]);   // the buffer's columns are in registers: it may be overwritten
       group(vb, 96);
     }
-    if (!RADIUS && me.q) {
-      part_d[int64_t(blockIdx.y) * Q + me.qi] = me.best.d;
-      part_id[int64_t(blockIdx.y) * Q + me.qi] = me.best.id;
+    if (qn) drain(qn);
+    if (!RADIUS && live) {
+      part_d[int64_t(blockIdx.y) * Q + qi0 + lane] = best.d;
+      part_id[int64_t(blockIdx.y) * Q + qi0 + lane] = best.id;
     }
   }
   tc_fence_before();
