@@ -704,7 +704,7 @@ static int pick_chunk_hint(const Ctx *c, int variant, int64_t N, int64_t Q) {
       const double eff = double(ctas) / double(waves * c->sm_count);
       if (eff > best_eff + 0.02) { best_eff = eff; chunks = k; }
     }
-    const int64_t minc = (N + (int64_t(1) << 25) - 1) >> 25;   // the kernel's queue entries hold node offsets below 2^26
+    const int64_t minc = (N + (int64_t(1) << 21) - 1) >> 21;   // the kernel's ring entries hold node offsets below 2^22
     if (chunks < minc) chunks = minc;
   } else if (variant == 1 || variant == 3) {
     const int64_t per = variant == 3 ? 256 : 128;   // queries per CTA (nn.cu: NN_THREADS * NN_QPT)

@@ -482,14 +482,37 @@ k_nn_qt_pf(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ 
 //   total          < 2^-14 R^2 = NN_TC_EPS R^2.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int TC_QTILES = 2;                       // query tiles per CTA: every node tile is multiplied by both
+constexpr int TC_QUERIES = TC_QTILES * TC_ROWS;    // 256 queries per CTA
 constexpr int TC_STAGES = 4;                       // node tiles in flight
 constexpr int TC_EPI_WARPS = 4 * TC_QTILES;        // one warp per (query tile, TMEM lane quarter)
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS; // warp 0: copies, warp 1: MMA issue + TMEM allocation, then the epilogue warps
+constexpr int TC_EVAL_WARPS = 4;                   // exact evaluation of what the scan could not reject; warp e serves scan warps e and e + 4
+constexpr int TC_FIRST_EPI = 2 + TC_EVAL_WARPS;    // warp 0: copies, warp 1: MMA issue + TMEM, then the evaluation warps, then the scan warps
+constexpr int TC_THREADS = 32 * (TC_FIRST_EPI + TC_EPI_WARPS);
 constexpr int TC_TMEM_COLS = 2 * TC_QTILES * TC_ROWS;   // two accumulator buffers x query tiles x 128 columns = 512
-constexpr int TC_SMEM_BYTES = (TC_QTILES + TC_STAGES) * TC_TILE_BYTES + 128 + TC_EPI_WARPS * 64 * 4;   // tiles, barriers, warp queues
+constexpr int TC_RING = 512;                       // surviving pairs waiting for their exact evaluation, per scan warp
+constexpr int TC_SEEDS = 32;                       // nodes of the chunk every query is measured against before the scan starts
+constexpr int TC_MAX_CHUNK = 1 << 22;              // a ring entry keeps 22 bits of node offset
 constexpr double NN_TC_EPS = 1.0 / 16384.0;
 
-constexpr int TC_WQ_CAP = 64;   // surviving pairs a warp holds back until 32 of them can be evaluated side by side
+struct TcShared {
+  uint64_t full[TC_STAGES], empty[TC_STAGES];   // node tile landed / its MMAs are done
+  uint64_t acc_full[2], acc_empty[2];           // accumulator buffer written / read by every scan warp
+  uint32_t tmem;
+  uint32_t tail[TC_EPI_WARPS], head[TC_EPI_WARPS];     // rings (one per scan warp): filled up to tail, consumed up to head
+  uint32_t done;                                // scan warps that have finished
+  float thr[TC_QUERIES];                        // per query: an accumulator value below this has to be looked at
+  unsigned long long d_bits[TC_QUERIES];        // incumbent: distance (bits of a non-negative double order like integers)
+  double best_s[TC_QUERIES];                    //            its sum of squares
+  double e_minus_qq[TC_QUERIES];                // error bound of the estimate minus |q|^2
+  int32_t best_id[TC_QUERIES];
+  int32_t excl[TC_QUERIES];
+  uint32_t ring[TC_EPI_WARPS][TC_RING];         // node offset in the chunk << 9 | query row << 1 | proven hit
+};
+constexpr int TC_SMEM_BYTES = (TC_QTILES + TC_STAGES) * TC_TILE_BYTES + int(sizeof(TcShared)) + 16;
+
+__device__ __forceinline__ uint32_t ld_vol(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+__device__ __forceinline__ float ld_vol(const float *p) { return *reinterpret_cast<const volatile float *>(p); }
+
 #ifdef SQMP_TC_NO_LD   // bring-up aid: the pipeline without the accumulator reads
 #define TC_LD(a, v) do { for (int i_ = 0; i_ < 32; ++i_) v[i_] = 1e30f + float(a); } while (0)
 #else
@@ -503,65 +526,72 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
         int64_t hit_cap) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char *sA = smem, *sB = smem + TC_QTILES * TC_TILE_BYTES;
-  uint64_t *full = reinterpret_cast<uint64_t *>(sB + TC_STAGES * TC_TILE_BYTES);   // node tile landed
-  uint64_t *empty = full + TC_STAGES;                                               // its MMAs are done
-  uint64_t *acc_full = empty + TC_STAGES;                                           // [2] accumulator buffer written
-  uint64_t *acc_empty = acc_full + 2;                                               // [2] ... and read by every epilogue warp
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+  TcShared *sh = reinterpret_cast<TcShared *>(sB + TC_STAGES * TC_TILE_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n0 = int64_t(blockIdx.y) * chunk_len, n1 = min(N, n0 + chunk_len);
   const int n_tiles = n0 < n1 ? int((n1 - n0 + TC_ROWS - 1) / TC_ROWS) : 0;
   const float4 *img = t.img + (n0 / TC_ROWS) * TC_TILE_FLOAT4;
+  const int64_t q_first = int64_t(blockIdx.x) * TC_QUERIES;   // query of row 0
 
-  // ---- set-up: barriers, TMEM, the queries as the A operand
+  // ---- set-up: barriers, TMEM, the queries as the A operand, their thresholds
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TC_STAGES; ++i) { tc_mbar_init(&full[i], 1); tc_mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc_mbar_init(&acc_full[i], 1); tc_mbar_init(&acc_empty[i], TC_EPI_WARPS); }
+    for (int i = 0; i < TC_STAGES; ++i) { tc_mbar_init(&sh->full[i], 1); tc_mbar_init(&sh->empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc_mbar_init(&sh->acc_full[i], 1); tc_mbar_init(&sh->acc_empty[i], TC_EPI_WARPS); }
+    for (int i = 0; i < TC_EPI_WARPS; ++i) sh->tail[i] = sh->head[i] = 0u;
+    sh->done = 0u;
     tc_fence_mbar_init();
   }
-  if (warp == 1) tc_tmem_alloc(tmem_slot, TC_TMEM_COLS);
-  // one epilogue thread = one query: its threshold(s) on the accumulator value v = |n|^2 - 2 q.n and its incumbent
-  float thr = -CUDART_INF_F, thr_lo = -CUDART_INF_F;   // inactive: nothing passes
-  double qq = 0.0, E = 0.0;
-  Best best;
-  best.s = NN_INIT_SUMSQ; best.d = NN_INIT_DIST; best.id = 0;
-  int32_t excl = -1;
-  const int qt = (warp - 2) >> 2, quarter = warp & 3;   // a warp may only read TMEM lanes [32 (warp % 4), +32)
-  const int64_t qi0 = (int64_t(blockIdx.x) * TC_QTILES + qt) * TC_ROWS + quarter * 32;   // query of lane 0
-  const bool live = warp >= 2 && qi0 + lane < Q;
-  if (warp >= 2) {
-    double v[SQMP_DOF];
+  if (warp == 1) tc_tmem_alloc(&sh->tmem, TC_TMEM_COLS);
+  const int qt = (warp - TC_FIRST_EPI) >> 2, quarter = warp & 3;   // a warp may only read TMEM lanes [32 (warp % 4), +32)
+  const int row = qt * TC_ROWS + quarter * 32 + lane;              // this scan thread's query
+  float thr_lo = -CUDART_INF_F;                                    // radius: an accumulator value below this is a proven hit
+  if (warp >= TC_FIRST_EPI) {
+    const bool live = q_first + row < Q;
+    const double *qp = queries + (q_first + row) * SQMP_DOF;
+    double v[SQMP_DOF], qq = 0.0;
 #pragma unroll
     for (int d = 0; d < SQMP_DOF; ++d) {
-      v[d] = live ? queries[(qi0 + lane) * SQMP_DOF + d] : 0.0;
+      v[d] = live ? qp[d] : 0.0;
       qq += v[d] * v[d];
     }
     tc_write_query_row(reinterpret_cast<float4 *>(sA + qt * TC_TILE_BYTES), quarter * 32 + lane, v);
-    E = NN_TC_EPS * fmax(rmax2, qq) * 1.000001;
+    const double E = NN_TC_EPS * fmax(rmax2, qq) * 1.000001;
+    float thr = -CUDART_INF_F;   // inactive: nothing passes
     if (live) {
-      excl = (RADIUS && exclude) ? exclude[qi0 + lane] : -1;
       if (RADIUS) {
         thr = __double2float_ru(s_thr + E - qq);      // v >= thr: proven miss
-        thr_lo = __double2float_rd(s_thr - E - qq);   // v <  thr_lo: proven hit
+        thr_lo = __double2float_rd(s_thr - E - qq);
       } else {
-        thr = __double2float_ru(NN_INIT_SUMSQ + E - qq);
+        // a few nodes of the chunk measured exactly: the scan starts with a threshold that already rejects most nodes
+        // (they are not offered as incumbents here — the scan meets them again in node order)
+        double smin = NN_INIT_SUMSQ;
+        const int64_t len = n1 - n0, step = len / TC_SEEDS;
+        if (step > 0)
+          for (int k = 0; k < TC_SEEDS; ++k) smin = fmin(smin, exact_s(t, n0 + k * step, qp));
+        thr = __double2float_ru(smin + E - qq);
       }
     }
+    sh->thr[row] = thr;
+    sh->d_bits[row] = (unsigned long long)__double_as_longlong(NN_INIT_DIST);
+    sh->best_s[row] = NN_INIT_SUMSQ;
+    sh->best_id[row] = 0;
+    sh->e_minus_qq[row] = E - qq;
+    sh->excl[row] = (RADIUS && live && exclude) ? exclude[q_first + row] : -1;
     tc_fence_async_smem();   // the A operand was written through the generic proxy; the tensor core reads through the async one
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = sh->tmem;
 
   if (warp == 0) {
     // ---- copies: one thread keeps TC_STAGES node tiles in flight
     if (lane == 0) {
       for (int it = 0; it < n_tiles; ++it) {
         const int s = it % TC_STAGES;
-        tc_mbar_wait(&empty[s], ((it / TC_STAGES) & 1) ^ 1);
-        tc_mbar_expect_tx(&full[s], TC_TILE_BYTES);
-        tc_bulk_g2s(sB + s * TC_TILE_BYTES, img + int64_t(it) * TC_TILE_FLOAT4, TC_TILE_BYTES, &full[s]);
+        tc_mbar_wait(&sh->empty[s], ((it / TC_STAGES) & 1) ^ 1);
+        tc_mbar_expect_tx(&sh->full[s], TC_TILE_BYTES);
+        tc_bulk_g2s(sB + s * TC_TILE_BYTES, img + int64_t(it) * TC_TILE_FLOAT4, TC_TILE_BYTES, &sh->full[s]);
       }
     }
     __syncwarp();
@@ -571,8 +601,8 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
       const uint32_t a_base = tc_smem_u32(sA), b_base = tc_smem_u32(sB);
       for (int it = 0; it < n_tiles; ++it) {
         const int s = it % TC_STAGES, buf = it & 1;
-        tc_mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
-        tc_mbar_wait(&full[s], (it / TC_STAGES) & 1);
+        tc_mbar_wait(&sh->acc_empty[buf], ((it >> 1) & 1) ^ 1);
+        tc_mbar_wait(&sh->full[s], (it / TC_STAGES) & 1);
         tc_fence_after();
         const uint32_t b = b_base + s * TC_TILE_BYTES;
         const uint64_t b_hi = tc_desc(b), b_mid = tc_desc(b + 2 * TC_CHUNK_BYTES), b_nrm = tc_desc(b + 4 * TC_CHUNK_BYTES);
@@ -585,74 +615,122 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
           tc_mma_tf32(d, a_hi, b_mid, true);
           tc_mma_tf32(d, a_one, b_nrm, true);
         }
-        tc_commit(&empty[s]);        // the tile's slot may be refilled
-        tc_commit(&acc_full[buf]);   // the accumulators may be read
+        tc_commit(&sh->empty[s]);        // the tile's slot may be refilled
+        tc_commit(&sh->acc_full[buf]);   // the accumulators may be read
       }
     }
     __syncwarp();
-  } else {
-    // ---- epilogue: this thread's query against every node of the chunk.  Pairs whose estimate passes the threshold are
-    //      not evaluated on the spot (one lane's exact evaluation would stall the warp for an L2 round trip per pair): they
-    //      go to the warp's queue as (node, owner lane, proven) and are evaluated 32 at a time, one pair per lane.
-    uint32_t *wq = reinterpret_cast<uint32_t *>(tmem_slot + 4) + (warp - 2) * TC_WQ_CAP;
-    int qn = 0;   // entries in the queue (warp-uniform)
-    const unsigned lt_mask = (1u << lane) - 1u;
-    auto drain = [&](int cnt) {   // the first cnt (<= 32) entries
+  } else if (warp < TC_FIRST_EPI) {
+    // ---- exact evaluation of the pairs the scan could not reject, 32 at a time (one pair per lane), off the scan's
+    //      critical path: an L2 round trip here does not hold up the accumulator ring.  Warp e serves the rings of scan
+    //      warps e and e + 4, so every query's incumbent has exactly one writer.
+    const int ev = warp - 2;
+    uint32_t head[2] = {0u, 0u};
+    for (;;) {
+      int k = 0;
+      uint32_t avail = ld_vol(&sh->tail[ev]) - head[0];
+      const uint32_t avail1 = ld_vol(&sh->tail[ev + TC_EVAL_WARPS]) - head[1];
+      if (avail1 > avail) { k = 1; avail = avail1; }
+      if (avail == 0u) {
+        if (ld_vol(&sh->done) < uint32_t(TC_EPI_WARPS)) { __nanosleep(100); continue; }
+        // every scan warp has published its last tail before `done`: one more look
+        if (ld_vol(&sh->tail[ev]) == head[0] && ld_vol(&sh->tail[ev + TC_EVAL_WARPS]) == head[1]) break;
+        continue;
+      }
+      const int rid = ev + k * TC_EVAL_WARPS;
+      const int cnt = min(32, int(avail));
       const bool have = lane < cnt;
-      const uint32_t e = have ? wq[lane] : 0u;
-      const int owner = int(e >> 1) & 31;
-      const int64_t n = n0 + int64_t(e >> 6);
-      double s = CUDART_INF;
-      if (have && !(RADIUS && (e & 1u))) s = exact_s(t, n, queries + (qi0 + owner) * SQMP_DOF);
+      const uint32_t e = have ? *reinterpret_cast<volatile uint32_t *>(&sh->ring[rid][(head[k] + lane) % TC_RING]) : 0u;
+      __threadfence_block();
+      __syncwarp();
+      head[k] += cnt;
+      if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&sh->head[rid]) = head[k];   // the slots may be reused
+      const int r = int(e >> 1) & (TC_QUERIES - 1);
+      const int64_t n = n0 + int64_t((e >> 9) & (TC_MAX_CHUNK - 1));
+      const double *qp = queries + (q_first + r) * SQMP_DOF;
       if (RADIUS) {
-        const int32_t ex = __shfl_sync(0xffffffffu, excl, owner);
-        if (have && ((e & 1u) || s < s_thr) && int32_t(n) != ex) {
-          const int32_t slot = atomicAdd(&count[qi0 + owner], 1);
-          if (slot < hit_cap) hits[(qi0 + owner) * hit_cap + slot] = int32_t(n);
+        if (have && ((e & 1u) || exact_s(t, n, qp) < s_thr) && int32_t(n) != sh->excl[r]) {
+          const int32_t slot = atomicAdd(&count[q_first + r], 1);
+          if (slot < hit_cap) hits[(q_first + r) * hit_cap + slot] = int32_t(n);
         }
       } else {
-        const double before = best.s;
-        for (int i = 0; i < cnt; ++i) {   // entries of one owner are in increasing node order, as offer() expects
-          const double si = __shfl_sync(0xffffffffu, s, i);
-          const uint32_t ei = __shfl_sync(0xffffffffu, e, i);
-          if (lane == (int(ei >> 1) & 31)) offer(best, si, int32_t(n0 + int64_t(ei >> 6)));
+        // lexicographic (distance, id) minimum per query = what the reference's serial loop keeps (strict '<', BS:4122)
+        double s = CUDART_INF, d = CUDART_INF;
+        if (have) {
+          s = exact_s(t, n, qp);
+          d = sqrt(s);
         }
-        if (best.s != before) thr = __double2float_ru(best.s + E - qq);
+        const unsigned long long db = (unsigned long long)__double_as_longlong(d);
+        const bool better_d = have && db < sh->d_bits[r];   // (the incumbent has the lower id on a tie: nodes arrive in id order per query)
+        __syncwarp();
+        if (better_d) atomicMin(&sh->d_bits[r], db);
+        __syncwarp();
+        const bool best_d = better_d && sh->d_bits[r] == db;
+        if (best_d) sh->best_id[r] = 0x7fffffff;
+        __syncwarp();
+        if (best_d) atomicMin(&sh->best_id[r], int32_t(n));
+        __syncwarp();
+        if (best_d && sh->best_id[r] == int32_t(n)) {
+          sh->best_s[r] = s;
+          const float nt = __double2float_ru(s + sh->e_minus_qq[r]);
+          if (nt < sh->thr[r]) *reinterpret_cast<volatile float *>(&sh->thr[r]) = nt;
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      const uint32_t moved = lane + 32 < qn ? wq[lane + 32] : 0u;
-      __syncwarp();
-      if (lane + 32 < qn) wq[lane] = moved;
-      qn -= cnt;
-      __syncwarp();
-    };
+    }
+    if (!RADIUS) {
+      for (int k = 0; k < 2; ++k) {   // the queries of its two scan warps
+        const int r = k * TC_ROWS + ((ev + TC_FIRST_EPI) & 3) * 32 + lane;   // scan warp ev + 4 k: query tile k, its TMEM quarter
+        if (q_first + r < Q) {
+          part_d[int64_t(blockIdx.y) * Q + q_first + r] = __longlong_as_double((long long)sh->d_bits[r]);
+          part_id[int64_t(blockIdx.y) * Q + q_first + r] = sh->best_id[r];
+        }
+      }
+    }
+  } else {
+    // ---- scan: this thread's query against every node of the chunk; what passes the threshold goes to the warp's ring
+    //      (single producer: the tail lives in a register and is published once per 32-column group)
+    const int rid = warp - TC_FIRST_EPI;
+    uint32_t *ring = sh->ring[rid];
+    uint32_t tail = 0u, head_seen = 0u;   // warp-uniform
+    const unsigned lt_mask = (1u << lane) - 1u;
     for (int it = 0; it < n_tiles; ++it) {
       const int buf = it & 1;
       const int64_t base = n0 + int64_t(it) * TC_ROWS;
-      tc_mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      tc_mbar_wait(&sh->acc_full[buf], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem + (uint32_t(quarter * 32) << 16) + uint32_t((buf * TC_QTILES + qt) * TC_ROWS);
       float va[32], vb[32];
       TC_LD(taddr, va);
       tc_tmem_ld_wait();
       auto group = [&](const float (&v)[32], int c) {
+        const float thr = ld_vol(&sh->thr[row]);
 #ifdef SQMP_TC_LD_ONLY
-        if (v[0] == 123.456f && v[17] == 1.0f) thr = 0.f;
+        if (v[0] == 123.456f && v[17] == thr) thr_lo = 0.f;
         return;
 #endif
-        float m = tc_min3(v[0], v[1], v[2]);
+        float ms[4];   // minimum of every run of eight estimates
 #pragma unroll
-        for (int j = 3; j + 1 < 32; j += 2) m = tc_min3(m, v[j], v[j + 1]);
-        m = fminf(m, v[31]);
+        for (int k = 0; k < 4; ++k)
+          ms[k] = fminf(tc_min3(tc_min3(v[8 * k], v[8 * k + 1], v[8 * k + 2]), tc_min3(v[8 * k + 3], v[8 * k + 4], v[8 * k + 5]), v[8 * k + 6]),
+                        v[8 * k + 7]);
+        const float m = fminf(tc_min3(ms[0], ms[1], ms[2]), ms[3]);
+#ifdef SQMP_TC_MIN_ONLY
+        if (m == 123.456f) thr_lo = 0.f;
+        return;
+#endif
         unsigned any = __ballot_sync(0xffffffffu, m < thr);
         if (any) {   // warp-uniform, rare
-          uint32_t cm = 0u, pm = 0u;   // columns that pass / that are proven hits
+          uint32_t cm = 0u, pm = 0u;   // columns that pass / that are proven hits; only the runs some lane needs are looked at
 #pragma unroll
-          for (int j = 0; j < 32; ++j) cm |= v[j] < thr ? 1u << j : 0u;
-          if (RADIUS) {
+          for (int k = 0; k < 4; ++k)
+            if (__any_sync(0xffffffffu, ms[k] < thr)) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) pm |= v[j] < thr_lo ? 1u << j : 0u;
-          }
+              for (int j = 8 * k; j < 8 * k + 8; ++j) {
+                cm |= v[j] < thr ? 1u << j : 0u;
+                if (RADIUS) pm |= v[j] < thr_lo ? 1u << j : 0u;
+              }
+            }
           while (any) {   // one owner at a time; lane j files column j
             const int owner = __ffs(any) - 1;
             any &= any - 1u;
@@ -660,11 +738,22 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
             const int64_t n = base + c + lane;
             const bool mine = ((cmo >> lane) & 1u) && n < n1;
             const unsigned bal = __ballot_sync(0xffffffffu, mine);
-            if (mine) wq[qn + __popc(bal & lt_mask)] = uint32_t(n - n0) << 6 | uint32_t(owner) << 1 | ((pmo >> lane) & 1u);
-            qn += __popc(bal);
-            __syncwarp();
-            if (qn >= 32) drain(32);
+            const uint32_t add = uint32_t(__popc(bal));
+            if (tail + add - head_seen > uint32_t(TC_RING)) {   // full: let the evaluator see what is there, wait for it
+              __threadfence_block();
+              __syncwarp();
+              if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&sh->tail[rid]) = tail;
+              do head_seen = ld_vol(&sh->head[rid]);
+              while (tail + add - head_seen > uint32_t(TC_RING));
+            }
+            if (mine)
+              ring[(tail + __popc(bal & lt_mask)) % TC_RING] =
+                  uint32_t(n - n0) << 9 | uint32_t(row - lane + owner) << 1 | ((pmo >> lane) & 1u);
+            tail += add;
           }
+          __threadfence_block();
+          __syncwarp();
+          if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&sh->tail[rid]) = tail;
         }
       };
       // the next 32 columns are on their way while these are scanned
@@ -679,14 +768,12 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
       tc_tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc_mbar_arrive(&acc_empty[buf]);   // the buffer's columns are in registers: it may be overwritten
+      if (lane == 0) tc_mbar_arrive(&sh->acc_empty[buf]);   // the buffer's columns are in registers: it may be overwritten
       group(vb, 96);
     }
-    if (qn) drain(qn);
-    if (!RADIUS && live) {
-      part_d[int64_t(blockIdx.y) * Q + qi0 + lane] = best.d;
-      part_id[int64_t(blockIdx.y) * Q + qi0 + lane] = best.id;
-    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) atomicAdd(&sh->done, 1u);
   }
   tc_fence_before();
   __syncthreads();

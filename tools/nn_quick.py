@@ -26,4 +26,5 @@ out["radius_ms"] = round(t_ms(lambda: ctx.nn_radius_dev(0, d_qs, None, Q, 1.5, 2
 out["nearest_q_per_s"] = round(Q / out["nearest_ms"] * 1e3)
 out["ids_sha"] = hashlib.sha1(d_ids.cpu().numpy().tobytes()).hexdigest()[:12]
 out["radius_sha"] = hashlib.sha1(d_low.cpu().numpy().tobytes() + d_high.cpu().numpy().tobytes() + d_cnt.cpu().numpy().tobytes()).hexdigest()[:12]
+out["mean_hits"] = round(float(d_cnt.float().mean()), 1)
 print(json.dumps(out))
