@@ -485,7 +485,7 @@ constexpr int TC_QTILES = 2;                       // query tiles per CTA: every
 constexpr int TC_QUERIES = TC_QTILES * TC_ROWS;    // 256 queries per CTA
 constexpr int TC_STAGES = 4;                       // node tiles in flight
 constexpr int TC_EPI_WARPS = 4 * TC_QTILES;        // one warp per (query tile, TMEM lane quarter)
-constexpr int TC_EVAL_WARPS = 4;                   // exact evaluation of what the scan could not reject; warp e serves scan warps e and e + 4
+constexpr int TC_EVAL_WARPS = 2;                   // exact evaluation of what the scan could not reject; warp e serves scan warps e, e + 2, ..
 constexpr int TC_FIRST_EPI = 2 + TC_EVAL_WARPS;    // warp 0: copies, warp 1: MMA issue + TMEM, then the evaluation warps, then the scan warps
 constexpr int TC_THREADS = 32 * (TC_FIRST_EPI + TC_EPI_WARPS);
 constexpr int TC_TMEM_COLS = 2 * TC_QTILES * TC_ROWS;   // two accumulator buffers x query tiles x 128 columns = 512
@@ -496,7 +496,7 @@ constexpr double NN_TC_EPS = 1.0 / 16384.0;
 
 struct TcShared {
   uint64_t full[TC_STAGES], empty[TC_STAGES];   // node tile landed / its MMAs are done
-  uint64_t acc_full[2], acc_empty[2];           // accumulator buffer written / read by every scan warp
+  uint64_t acc_full[2][TC_QTILES], acc_empty[2][TC_QTILES];   // accumulator (buffer, query tile) written / copied out by its four scan warps
   uint32_t tmem;
   uint32_t tail[TC_EPI_WARPS], head[TC_EPI_WARPS];     // rings (one per scan warp): filled up to tail, consumed up to head
   uint32_t done;                                // scan warps that have finished
@@ -536,7 +536,7 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
   // ---- set-up: barriers, TMEM, the queries as the A operand, their thresholds
   if (threadIdx.x == 0) {
     for (int i = 0; i < TC_STAGES; ++i) { tc_mbar_init(&sh->full[i], 1); tc_mbar_init(&sh->empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc_mbar_init(&sh->acc_full[i], 1); tc_mbar_init(&sh->acc_empty[i], TC_EPI_WARPS); }
+    for (int i = 0; i < 2 * TC_QTILES; ++i) { tc_mbar_init(&sh->acc_full[0][i], 1); tc_mbar_init(&sh->acc_empty[0][i], 4); }
     for (int i = 0; i < TC_EPI_WARPS; ++i) sh->tail[i] = sh->head[i] = 0u;
     sh->done = 0u;
     tc_fence_mbar_init();
@@ -601,22 +601,22 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
       const uint32_t a_base = tc_smem_u32(sA), b_base = tc_smem_u32(sB);
       for (int it = 0; it < n_tiles; ++it) {
         const int s = it % TC_STAGES, buf = it & 1;
-        tc_mbar_wait(&sh->acc_empty[buf], ((it >> 1) & 1) ^ 1);
         tc_mbar_wait(&sh->full[s], (it / TC_STAGES) & 1);
-        tc_fence_after();
         const uint32_t b = b_base + s * TC_TILE_BYTES;
         const uint64_t b_hi = tc_desc(b), b_mid = tc_desc(b + 2 * TC_CHUNK_BYTES), b_nrm = tc_desc(b + 4 * TC_CHUNK_BYTES);
 #pragma unroll
         for (int k = 0; k < TC_QTILES; ++k) {
           const uint32_t a = a_base + k * TC_TILE_BYTES, d = tmem + uint32_t((buf * TC_QTILES + k) * TC_ROWS);
           const uint64_t a_hi = tc_desc(a), a_mid = tc_desc(a + 2 * TC_CHUNK_BYTES), a_one = tc_desc(a + 4 * TC_CHUNK_BYTES);
+          tc_mbar_wait(&sh->acc_empty[buf][k], ((it >> 1) & 1) ^ 1);
+          tc_fence_after();
           tc_mma_tf32(d, a_hi, b_hi, false);
           tc_mma_tf32(d, a_mid, b_hi, true);
           tc_mma_tf32(d, a_hi, b_mid, true);
           tc_mma_tf32(d, a_one, b_nrm, true);
+          tc_commit(&sh->acc_full[buf][k]);   // this query tile's accumulator may be read
         }
-        tc_commit(&sh->empty[s]);        // the tile's slot may be refilled
-        tc_commit(&sh->acc_full[buf]);   // the accumulators may be read
+        tc_commit(&sh->empty[s]);             // the node tile's slot may be refilled
       }
     }
     __syncwarp();
@@ -625,26 +625,40 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
     //      critical path: an L2 round trip here does not hold up the accumulator ring.  Warp e serves the rings of scan
     //      warps e and e + 4, so every query's incumbent has exactly one writer.
     const int ev = warp - 2;
-    uint32_t head[2] = {0u, 0u};
+    constexpr int SERVED = TC_EPI_WARPS / TC_EVAL_WARPS;
+    uint32_t head[SERVED];
+#pragma unroll
+    for (int k = 0; k < SERVED; ++k) head[k] = 0u;
     for (;;) {
       int k = 0;
-      uint32_t avail = ld_vol(&sh->tail[ev]) - head[0];
-      const uint32_t avail1 = ld_vol(&sh->tail[ev + TC_EVAL_WARPS]) - head[1];
-      if (avail1 > avail) { k = 1; avail = avail1; }
+      uint32_t avail = 0u;
+#pragma unroll
+      for (int i = 0; i < SERVED; ++i) {   // the fullest of its rings
+        const uint32_t a = ld_vol(&sh->tail[ev + i * TC_EVAL_WARPS]) - head[i];
+        if (a > avail) { avail = a; k = i; }
+      }
       if (avail == 0u) {
-        if (ld_vol(&sh->done) < uint32_t(TC_EPI_WARPS)) { __nanosleep(100); continue; }
+        if (ld_vol(&sh->done) < uint32_t(TC_EPI_WARPS)) { __nanosleep(200); continue; }
         // every scan warp has published its last tail before `done`: one more look
-        if (ld_vol(&sh->tail[ev]) == head[0] && ld_vol(&sh->tail[ev + TC_EVAL_WARPS]) == head[1]) break;
+        bool empty = true;
+#pragma unroll
+        for (int i = 0; i < SERVED; ++i) empty = empty && ld_vol(&sh->tail[ev + i * TC_EVAL_WARPS]) == head[i];
+        if (empty) break;
         continue;
       }
       const int rid = ev + k * TC_EVAL_WARPS;
+      uint32_t hk = 0u;
+#pragma unroll
+      for (int i = 0; i < SERVED; ++i) hk = i == k ? head[i] : hk;
       const int cnt = min(32, int(avail));
       const bool have = lane < cnt;
-      const uint32_t e = have ? *reinterpret_cast<volatile uint32_t *>(&sh->ring[rid][(head[k] + lane) % TC_RING]) : 0u;
+      const uint32_t e = have ? *reinterpret_cast<volatile uint32_t *>(&sh->ring[rid][(hk + lane) % TC_RING]) : 0u;
       __threadfence_block();
       __syncwarp();
-      head[k] += cnt;
-      if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&sh->head[rid]) = head[k];   // the slots may be reused
+      hk += cnt;
+#pragma unroll
+      for (int i = 0; i < SERVED; ++i) head[i] = i == k ? hk : head[i];
+      if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&sh->head[rid]) = hk;   // the slots may be reused
       const int r = int(e >> 1) & (TC_QUERIES - 1);
       const int64_t n = n0 + int64_t((e >> 9) & (TC_MAX_CHUNK - 1));
       const double *qp = queries + (q_first + r) * SQMP_DOF;
@@ -679,8 +693,9 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
       }
     }
     if (!RADIUS) {
-      for (int k = 0; k < 2; ++k) {   // the queries of its two scan warps
-        const int r = k * TC_ROWS + ((ev + TC_FIRST_EPI) & 3) * 32 + lane;   // scan warp ev + 4 k: query tile k, its TMEM quarter
+      for (int k = 0; k < SERVED; ++k) {   // the queries of the scan warps it serves
+        const int sw = ev + k * TC_EVAL_WARPS + TC_FIRST_EPI;                // that scan warp: its query tile and TMEM quarter
+        const int r = ((sw - TC_FIRST_EPI) >> 2) * TC_ROWS + (sw & 3) * 32 + lane;
         if (q_first + r < Q) {
           part_d[int64_t(blockIdx.y) * Q + q_first + r] = __longlong_as_double((long long)sh->d_bits[r]);
           part_id[int64_t(blockIdx.y) * Q + q_first + r] = sh->best_id[r];
@@ -697,79 +712,74 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
     for (int it = 0; it < n_tiles; ++it) {
       const int buf = it & 1;
       const int64_t base = n0 + int64_t(it) * TC_ROWS;
-      tc_mbar_wait(&sh->acc_full[buf], (it >> 1) & 1);
+      tc_mbar_wait(&sh->acc_full[buf][qt], (it >> 1) & 1);
       tc_fence_after();
+      // the query's 128 estimates move to registers in one go and the accumulator is handed back before anything is
+      // looked at: the tensor core never waits for the scan, only for this copy
       const uint32_t taddr = tmem + (uint32_t(quarter * 32) << 16) + uint32_t((buf * TC_QTILES + qt) * TC_ROWS);
-      float va[32], vb[32];
-      TC_LD(taddr, va);
-      tc_tmem_ld_wait();
-      auto group = [&](const float (&v)[32], int c) {
-        const float thr = ld_vol(&sh->thr[row]);
-#ifdef SQMP_TC_LD_ONLY
-        if (v[0] == 123.456f && v[17] == thr) thr_lo = 0.f;
-        return;
-#endif
-        float ms[4];   // minimum of every run of eight estimates
+      float v[TC_ROWS];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          ms[k] = fminf(tc_min3(tc_min3(v[8 * k], v[8 * k + 1], v[8 * k + 2]), tc_min3(v[8 * k + 3], v[8 * k + 4], v[8 * k + 5]), v[8 * k + 6]),
-                        v[8 * k + 7]);
-        const float m = fminf(tc_min3(ms[0], ms[1], ms[2]), ms[3]);
-#ifdef SQMP_TC_MIN_ONLY
-        if (m == 123.456f) thr_lo = 0.f;
-        return;
-#endif
-        unsigned any = __ballot_sync(0xffffffffu, m < thr);
-        if (any) {   // warp-uniform, rare
-          uint32_t cm = 0u, pm = 0u;   // columns that pass / that are proven hits; only the runs some lane needs are looked at
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (__any_sync(0xffffffffu, ms[k] < thr)) {
-#pragma unroll
-              for (int j = 8 * k; j < 8 * k + 8; ++j) {
-                cm |= v[j] < thr ? 1u << j : 0u;
-                if (RADIUS) pm |= v[j] < thr_lo ? 1u << j : 0u;
-              }
-            }
-          while (any) {   // one owner at a time; lane j files column j
-            const int owner = __ffs(any) - 1;
-            any &= any - 1u;
-            const uint32_t cmo = __shfl_sync(0xffffffffu, cm, owner), pmo = __shfl_sync(0xffffffffu, pm, owner);
-            const int64_t n = base + c + lane;
-            const bool mine = ((cmo >> lane) & 1u) && n < n1;
-            const unsigned bal = __ballot_sync(0xffffffffu, mine);
-            const uint32_t add = uint32_t(__popc(bal));
-            if (tail + add - head_seen > uint32_t(TC_RING)) {   // full: let the evaluator see what is there, wait for it
-              __threadfence_block();
-              __syncwarp();
-              if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&sh->tail[rid]) = tail;
-              do head_seen = ld_vol(&sh->head[rid]);
-              while (tail + add - head_seen > uint32_t(TC_RING));
-            }
-            if (mine)
-              ring[(tail + __popc(bal & lt_mask)) % TC_RING] =
-                  uint32_t(n - n0) << 9 | uint32_t(row - lane + owner) << 1 | ((pmo >> lane) & 1u);
-            tail += add;
-          }
-          __threadfence_block();
-          __syncwarp();
-          if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&sh->tail[rid]) = tail;
-        }
-      };
-      // the next 32 columns are on their way while these are scanned
-      TC_LD(taddr + 32, vb);
-      group(va, 0);
-      tc_tmem_ld_wait();
-      TC_LD(taddr + 64, va);
-      group(vb, 32);
-      tc_tmem_ld_wait();
-      TC_LD(taddr + 96, vb);
-      group(va, 64);
+      for (int g = 0; g < 4; ++g) TC_LD(taddr + 32 * g, v + 32 * g);
       tc_tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc_mbar_arrive(&sh->acc_empty[buf]);   // the buffer's columns are in registers: it may be overwritten
-      group(vb, 96);
+      if (lane == 0) tc_mbar_arrive(&sh->acc_empty[buf][qt]);
+      const float thr = ld_vol(&sh->thr[row]);
+#ifdef SQMP_TC_LD_ONLY
+      if (v[0] == 123.456f && v[77] == thr) thr_lo = 0.f;
+      continue;
+#endif
+      float ms[16];   // minimum of every run of eight estimates
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        ms[k] = fminf(tc_min3(tc_min3(v[8 * k], v[8 * k + 1], v[8 * k + 2]), tc_min3(v[8 * k + 3], v[8 * k + 4], v[8 * k + 5]), v[8 * k + 6]),
+                      v[8 * k + 7]);
+      float mg[4];    // ... of every 32
+#pragma unroll
+      for (int g = 0; g < 4; ++g) mg[g] = fminf(tc_min3(ms[4 * g], ms[4 * g + 1], ms[4 * g + 2]), ms[4 * g + 3]);
+      const float m = fminf(tc_min3(mg[0], mg[1], mg[2]), mg[3]);
+#ifdef SQMP_TC_MIN_ONLY
+      if (m == 123.456f) thr_lo = 0.f;
+      continue;
+#endif
+      if (!__any_sync(0xffffffffu, m < thr)) continue;   // the common case: nothing in this tile for any of the 32 queries
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        unsigned any = __ballot_sync(0xffffffffu, mg[g] < thr);
+        if (any == 0u) continue;
+        uint32_t cm = 0u, pm = 0u;   // columns that pass / that are proven hits; only the runs some lane needs are looked at
+#pragma unroll
+        for (int k = 4 * g; k < 4 * g + 4; ++k)
+          if (__any_sync(0xffffffffu, ms[k] < thr)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              cm |= v[8 * k + j] < thr ? 1u << (8 * (k & 3) + j) : 0u;
+              if (RADIUS) pm |= v[8 * k + j] < thr_lo ? 1u << (8 * (k & 3) + j) : 0u;
+            }
+          }
+        while (any) {   // one owner at a time; lane j files column j of this run of 32
+          const int owner = __ffs(any) - 1;
+          any &= any - 1u;
+          const uint32_t cmo = __shfl_sync(0xffffffffu, cm, owner), pmo = __shfl_sync(0xffffffffu, pm, owner);
+          const int64_t n = base + 32 * g + lane;
+          const bool mine = ((cmo >> lane) & 1u) && n < n1;
+          const unsigned bal = __ballot_sync(0xffffffffu, mine);
+          const uint32_t add = uint32_t(__popc(bal));
+          if (tail + add - head_seen > uint32_t(TC_RING)) {   // full: let the evaluator see what is there, wait for it
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&sh->tail[rid]) = tail;
+            do head_seen = ld_vol(&sh->head[rid]);
+            while (tail + add - head_seen > uint32_t(TC_RING));
+          }
+          if (mine)
+            ring[(tail + __popc(bal & lt_mask)) % TC_RING] = uint32_t(n - n0) << 9 | uint32_t(row - lane + owner) << 1 | ((pmo >> lane) & 1u);
+          tail += add;
+        }
+      }
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&sh->tail[rid]) = tail;
     }
     __threadfence_block();
     __syncwarp();

@@ -116,7 +116,7 @@ __device__ __forceinline__ void tc_tmem_free(uint32_t addr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
 // 32 consecutive fp32 columns of the calling lane's TMEM row (lane i of warp w reads TMEM lane 32 (w % 4) + i)
-__device__ __forceinline__ void tc_tmem_ld32(uint32_t taddr, float (&v)[32]) {
+__device__ __forceinline__ void tc_tmem_ld32(uint32_t taddr, float *v) {   // v: 32 registers after unrolling
   uint32_t r[32];
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
