@@ -688,7 +688,7 @@ static double sumsq_threshold(double r) {
 
 static int pick_variant(const Ctx *c, int64_t Q) {
   if (c->nn_variant >= 1 && c->nn_variant <= 4) return c->nn_variant;
-  return Q >= 2048 ? 3 : 2;
+  return Q >= 2048 ? 4 : 2;   // many queries: the tensor-core scan; few: a warp per query
 }
 static int pick_chunk_hint(const Ctx *c, int variant, int64_t N, int64_t Q) {
   if (N <= 0) return 1;
