@@ -644,14 +644,14 @@ static int tree_reserve(Ctx *c, TreeDev &t, int64_t need) {
   if (e == cudaSuccess) e = cudaMalloc(&fb, size_t(pitch) * sizeof(float4));
   if (e == cudaSuccess) e = cudaMalloc(&fn, size_t(pitch) * sizeof(float));
   // (cap is a multiple of 128: whole tiles; rows past n are never trusted by the scan, zero keeps them finite)
-  const size_t img_bytes = size_t((pitch + 127) / 128) * 12288;
+  const size_t img_bytes = size_t((pitch + 127) / 128) * SQMP_NN_TILE_IMG_BYTES;
   if (e == cudaSuccess) e = cudaMalloc(&img, img_bytes);
   if (e == cudaSuccess) e = cudaMemset(img, 0, img_bytes);
   if (e == cudaSuccess && t.n > 0) {
     e = cudaMemcpy(fa, t.fa, size_t(t.n) * sizeof(float4), cudaMemcpyDeviceToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(fb, t.fb, size_t(t.n) * sizeof(float4), cudaMemcpyDeviceToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(fn, t.fn, size_t(t.n) * sizeof(float), cudaMemcpyDeviceToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(img, t.img, size_t((t.n + 127) / 128) * 12288, cudaMemcpyDeviceToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(img, t.img, size_t((t.n + 127) / 128) * SQMP_NN_TILE_IMG_BYTES, cudaMemcpyDeviceToDevice);
   }
   if (e != cudaSuccess) {
     cudaFree(blk);
@@ -686,9 +686,10 @@ static double sumsq_threshold(double r) {
   return s;
 }
 
-static int pick_variant(const Ctx *c, int64_t Q) {
-  if (c->nn_variant >= 1 && c->nn_variant <= 4) return c->nn_variant;
-  return Q >= 2048 ? 4 : 2;   // many queries: the tensor-core scan; few: a warp per query
+static int pick_variant(const Ctx *c, const TreeDev &t, int64_t Q) {
+  int v = c->nn_variant >= 1 && c->nn_variant <= 4 ? c->nn_variant : (Q >= 2048 ? 4 : 2);   // many queries: the tensor-core scan; few: a warp per query
+  if (v == 4 && !(t.rmax2 < 6.0e4)) v = 3;   // its fp16 operands cannot hold this tree (tc_umma.cuh: TC_MAX_NORM2): fp32 pre-filter
+  return v;
 }
 static int pick_chunk_hint(const Ctx *c, int variant, int64_t N, int64_t Q) {
   if (N <= 0) return 1;
@@ -1597,7 +1598,7 @@ int sqmp_nn_nearest_dev(sqmp_ctx *ctx, int tree, const double *d_queries, int64_
     CU(cudaMemsetAsync(d_id, 0, size_t(Q) * 4, st));
     return SQMP_OK;
   }
-  const int variant = pick_variant(c, Q);
+  const int variant = pick_variant(c, t, Q);
   const int hint = pick_chunk_hint(c, variant, t.n, Q);
   int rc = nn_prepare(c, Q, hint, false, t.n);
   if (rc) return rc;
@@ -1627,7 +1628,7 @@ int sqmp_nn_radius_dev(sqmp_ctx *ctx, int tree, const double *d_queries, const i
     CU(cudaMemsetAsync(d_high, 0xff, size_t(Q) * k * 4, st));
     return SQMP_OK;
   }
-  const int variant = pick_variant(c, Q);
+  const int variant = pick_variant(c, t, Q);
   const int hint = pick_chunk_hint(c, variant, t.n, Q);
   int rc = nn_prepare(c, Q, hint, true, t.n);
   if (rc) return rc;

@@ -57,7 +57,7 @@ __device__ __forceinline__ void write_shadow(const TreePtrs &t, int64_t i, const
   t.fa[i] = make_float4(f[0], f[1], f[2], f[3]);
   t.fb[i] = make_float4(f[4], f[5], f[6], f[7]);
   t.fn[i] = __double2float_rn(n2);
-  tc_write_node_row(t.img + (i >> 7) * TC_TILE_FLOAT4, int(i & 127), v);   // tf32 operand image (tc_umma.cuh)
+  tc_write_node_row(t.img + (i >> 7) * TC_TILE_FLOAT4, int(i & 127), v);   // fp16 operand image (tc_umma.cuh)
 }
 
 // rows (AoS, n x 8) -> SoA at [first, first+n)
@@ -463,27 +463,28 @@ k_nn_qt_pf(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ 
 // ---------------------------------------------------------------------------------------------------------
 // TC ("tensor-core pre-filter", many queries): the estimate of every (query, node) pair comes out of tcgen05.mma
 // instead of nine FFMA2 per pair.  A CTA keeps TC_QTILES x 128 queries as the A operand in shared memory and streams
-// its node chunk through a ring of 12 KB tile images (bulk async copies, one elected thread); one elected thread issues
-// four K = 8 MMAs per (query tile, node tile) into a double-buffered TMEM accumulator (tc_umma.cuh); the epilogue
-// warps read their query's row of it (one TMEM lane per thread, 32 columns per tcgen05.ld), take the minimum of the 32
-// estimates with three-input min and only look at individual columns when that minimum passes the thread's threshold.
-// Everything that passes is re-evaluated exactly (exact_s) and compared exactly — the same contract as QT/PF, so the
-// answers are bit-identical; the band is wider (tf32 pieces: NN_TC_EPS R^2 instead of a few fp32 ulps) and still
-// admits < 0.1 extra exact evaluations per query on the benchmark's tree.
+// its node chunk through a ring of 6 KB tile images (bulk async copies, one elected thread); one elected thread issues
+// two K = 16 fp16 MMAs per (query tile, node tile) into one of four TMEM accumulators (tc_umma.cuh).  The four scan warps of
+// a query tile copy their query's row of the accumulator to registers (one TMEM lane per thread, 128 columns), hand the
+// accumulator back at once, and reduce the 128 estimates with three-input minima; individual columns are only looked
+// at when that minimum passes the thread's threshold.  What passes goes to a shared-memory ring and is re-evaluated
+// exactly (exact_s) and compared exactly by two dedicated warps, 32 pairs at a time, off the scan's critical path — the
+// same contract as QT/PF, so the answers are bit-identical; the band is wider (fp16 pieces instead of a few fp32 ulps) and
+// still admits < 0.1 extra exact evaluations per query on the benchmark's tree.
 //
 // Error bound of the estimate v = D[query][node] against t = |n|^2 - 2 q.n in real arithmetic, R >= |q|, |n|:
-//   operands:      q = qh + qm + eq, n = nh + nm + en with |eq| <= 2^-21 |q_d|, |en| <= 2^-21 |n_d| (fp32 rounding of the
-//                  fp64 value + two tf32 roundings); the dropped terms qm.nm, eq.n, q.en add up to <= 2.5 * 2^-21 R^2 in 2 q.n
-//   |n|^2 pieces:  <= 2^-30 R^2
-//   accumulation:  25 exact products of magnitude <= R^2 summed by the tensor core over four instructions; budgeted
-//                  2^-15 R^2 (a per-addition error of 2^-22 of the running magnitude 4 R^2, i.e. two fp32 ulps, 32 times).
+//   operands:      q = qh + qm + eq, n = nh + nm + en with |eq| <= 2^-22 |q_d| + 2^-24 (the second piece may be an fp16
+//                  subnormal), same for en; the dropped terms qm.nm, eq.n, q.en add up to <= 3 * 2^-22 R^2 + 2^-20 R in 2 q.n
+//   |n|^2 pieces:  <= 2^-30 R^2 + 2^-23
+//   accumulation:  19 exact products of magnitude <= R^2 summed by the tensor core over two instructions; budgeted
+//                  2^-15 R^2 (a per-addition error of two fp32 ulps of the running magnitude 4 R^2, 32 times).
 //                  The hardware's accumulation order is not documented, which is why the budget is 60 times the error the
-//                  probe (tools/tc_probe.cu) and the parity tests observe (2^-21 R^2).
-//   total          < 2^-14 R^2 = NN_TC_EPS R^2.
+//                  probe (tools/tc_probe_f16.cu) and the parity tests observe (2^-21.8 R^2).
+//   total          < 2^-14 R^2 + 2^-19 R + 2^-22 = tc_error_bound(R^2).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int TC_QTILES = 2;                       // query tiles per CTA: every node tile is multiplied by both
 constexpr int TC_QUERIES = TC_QTILES * TC_ROWS;    // 256 queries per CTA
-constexpr int TC_STAGES = 4;                       // node tiles in flight
+constexpr int TC_STAGES = 8;                       // node tiles in flight
 constexpr int TC_EPI_WARPS = 4 * TC_QTILES;        // one warp per (query tile, TMEM lane quarter)
 constexpr int TC_EVAL_WARPS = 2;                   // exact evaluation of what the scan could not reject; warp e serves scan warps e, e + 2, ..
 constexpr int TC_FIRST_EPI = 2 + TC_EVAL_WARPS;    // warp 0: copies, warp 1: MMA issue + TMEM, then the evaluation warps, then the scan warps
@@ -492,7 +493,10 @@ constexpr int TC_TMEM_COLS = 2 * TC_QTILES * TC_ROWS;   // two accumulator buffe
 constexpr int TC_RING = 512;                       // surviving pairs waiting for their exact evaluation, per scan warp
 constexpr int TC_SEEDS = 32;                       // nodes of the chunk every query is measured against before the scan starts
 constexpr int TC_MAX_CHUNK = 1 << 22;              // a ring entry keeps 22 bits of node offset
-constexpr double NN_TC_EPS = 1.0 / 16384.0;
+static_assert(TC_TILE_BYTES == SQMP_NN_TILE_IMG_BYTES, "capi.cu sizes the image with this");
+__device__ __forceinline__ double tc_error_bound(double R2) {
+  return (R2 * (1.0 / 16384.0) + sqrt(R2) * (1.0 / 524288.0) + 1.0 / 4194304.0) * 1.000001;
+}
 
 struct TcShared {
   uint64_t full[TC_STAGES], empty[TC_STAGES];   // node tile landed / its MMAs are done
@@ -554,10 +558,14 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
       v[d] = live ? qp[d] : 0.0;
       qq += v[d] * v[d];
     }
-    tc_write_query_row(reinterpret_cast<float4 *>(sA + qt * TC_TILE_BYTES), quarter * 32 + lane, v);
-    const double E = NN_TC_EPS * fmax(rmax2, qq) * 1.000001;
+    const bool usable = qq < TC_MAX_NORM2;   // fits fp16; otherwise (or NaN): a zero row, every pair of this query is evaluated exactly
+    tc_write_query_row(reinterpret_cast<float4 *>(sA + qt * TC_TILE_BYTES), quarter * 32 + lane, v, usable);
+    double E = tc_error_bound(fmax(rmax2, qq));
     float thr = -CUDART_INF_F;   // inactive: nothing passes
-    if (live) {
+    if (live && !usable) {
+      thr = CUDART_INF_F;
+      E = CUDART_INF;
+    } else if (live) {
       if (RADIUS) {
         thr = __double2float_ru(s_thr + E - qq);      // v >= thr: proven miss
         thr_lo = __double2float_rd(s_thr - E - qq);
@@ -575,7 +583,7 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
     sh->d_bits[row] = (unsigned long long)__double_as_longlong(NN_INIT_DIST);
     sh->best_s[row] = NN_INIT_SUMSQ;
     sh->best_id[row] = 0;
-    sh->e_minus_qq[row] = E - qq;
+    sh->e_minus_qq[row] = usable ? E - qq : CUDART_INF;
     sh->excl[row] = (RADIUS && live && exclude) ? exclude[q_first + row] : -1;
     tc_fence_async_smem();   // the A operand was written through the generic proxy; the tensor core reads through the async one
   }
@@ -603,17 +611,15 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
         const int s = it % TC_STAGES, buf = it & 1;
         tc_mbar_wait(&sh->full[s], (it / TC_STAGES) & 1);
         const uint32_t b = b_base + s * TC_TILE_BYTES;
-        const uint64_t b_hi = tc_desc(b), b_mid = tc_desc(b + 2 * TC_CHUNK_BYTES), b_nrm = tc_desc(b + 4 * TC_CHUNK_BYTES);
+        const uint64_t b_hi_hi = tc_desc(b, 0), b_mid_nrm = tc_desc(b + TC_CHUNK_BYTES, TC_CHUNK_BYTES);
 #pragma unroll
         for (int k = 0; k < TC_QTILES; ++k) {
           const uint32_t a = a_base + k * TC_TILE_BYTES, d = tmem + uint32_t((buf * TC_QTILES + k) * TC_ROWS);
-          const uint64_t a_hi = tc_desc(a), a_mid = tc_desc(a + 2 * TC_CHUNK_BYTES), a_one = tc_desc(a + 4 * TC_CHUNK_BYTES);
+          const uint64_t a_hi_mid = tc_desc(a, TC_CHUNK_BYTES), a_hi_one = tc_desc(a, 2 * TC_CHUNK_BYTES);
           tc_mbar_wait(&sh->acc_empty[buf][k], ((it >> 1) & 1) ^ 1);
           tc_fence_after();
-          tc_mma_tf32(d, a_hi, b_hi, false);
-          tc_mma_tf32(d, a_mid, b_hi, true);
-          tc_mma_tf32(d, a_hi, b_mid, true);
-          tc_mma_tf32(d, a_one, b_nrm, true);
+          tc_mma_f16(d, a_hi_mid, b_hi_hi, false);    // [qh | qm] . [-2nh | -2nh]
+          tc_mma_f16(d, a_hi_one, b_mid_nrm, true);   // [qh | 1 1 1] . [-2nm | |n|^2 pieces]
           tc_commit(&sh->acc_full[buf][k]);   // this query tile's accumulator may be read
         }
         tc_commit(&sh->empty[s]);             // the node tile's slot may be refilled

@@ -222,6 +222,7 @@ cudaError_t launch_gather_wait(const uint32_t *d_flags, int n, unsigned step, in
 cudaError_t launch_pack_rows(const uint32_t *d_bits_linear, int gx, int gy, int gz, int row_words, uint32_t *d_occ,
                              cudaStream_t st);
 
+constexpr int SQMP_NN_TILE_IMG_BYTES = 6144;
 struct TreeDev {
   double *q[SQMP_DOF];   // SoA: q[d][n]
   double *cost;
@@ -231,7 +232,7 @@ struct TreeDev {
   // fn[n] = |float node|^2 (fp64 sum rounded once)
   float4 *fa, *fb;
   float *fn;
-  // tf32 operand image of the nodes for the tensor-core scan (tc_umma.cuh): one 12 KB record per 128-node tile
+  // fp16 operand image of the nodes for the tensor-core scan (tc_umma.cuh): one SQMP_NN_TILE_IMG_BYTES record per 128-node tile
   float4 *img;
   double rmax2;          // upper bound of |node|^2 over every node written since the last reset (host-tracked)
   int64_t n, cap;

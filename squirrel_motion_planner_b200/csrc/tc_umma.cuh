@@ -1,101 +1,100 @@
 // tc_umma.cuh — the few tcgen05 / TMEM / mbarrier primitives the tensor-core near-neighbour scan (nn.cu: k_nn_tc) uses,
 // and the operand image both sides of its product are stored in.
 //
-// The product: D[query][node] = |n|^2 - 2 q.n for a tile of 128 queries against a tile of 128 nodes, as ONE accumulator
-// of four tcgen05.mma (kind::tf32, M = 128, N = 128, K = 8 each) over operands split into tf32 pieces:
+// The product: D[query][node] = |n|^2 - 2 q.n for a tile of 128 queries against a tile of 128 nodes, as ONE fp32
+// accumulator of two tcgen05.mma (kind::f16, M = 128, N = 128, K = 16 each) over operands split into fp16 pieces:
 //     q = qh + qm (+ eq),  n = nh + nm (+ en),  |n|^2 = p0 + p1 + p2       (every piece has an 11-bit significand)
-//     D = qh.(-2nh) + qm.(-2nh) + qh.(-2nm) + (1,1,1).(p0,p1,p2)
-// Products of two 11-bit significands are exact in the fp32 accumulator's 24 bits; what is lost is qm.nm and the
-// residuals eq, en (each <= 2^-22 relative) and the accumulation roundings: nn.cu budgets 2^-14 R^2 for the lot.
+//     MMA 1:  [ qh | qm ] . [ -2nh | -2nh ]          MMA 2:  [ qh | 1 1 1 0.. ] . [ -2nm | p0 p1 p2 0.. ]
+// Products of two 11-bit significands are exact in the fp32 accumulator's 24 bits; what is lost is qm.nm, the residuals
+// eq, en (<= 2^-22 relative, or half an fp16 subnormal step for tiny values) and the accumulation roundings: nn.cu budgets
+// 2^-14 R^2 + 2^-19 R + 2^-22 for the lot.  fp16 overflows at 65504: the scan is only used while |n|^2 < 6e4 for the whole tree,
+// and a query beyond that gets a zero row and an infinite threshold (every pair of it is evaluated exactly).
 //
 // Operand image ("K-major, no swizzle" canonical layout of the UMMA shared-memory descriptor): an operand tile is 128 rows
-// of K = 24 tf32 values kept as six 16-byte K chunks; chunk c of row r lives at byte  c * 2048 + r * 16.  Eight
-// consecutive rows of one chunk form the 8 x 16 B core matrix (128 contiguous bytes), so
-//     stride between 8-row groups (SBO)      = 128 B
-//     stride between the K chunks  (LBO)     = 2048 B
-// and one MMA (K = 8 = two chunks) addresses chunks (c, c + 1) by starting its descriptor at c * 2048.
-// The tree keeps this image per 128-node tile in global memory (12 KB, contiguous), so a tile reaches shared memory as ONE
-// 1-D bulk copy (cp.async.bulk, SASS UBLKCP) — no tensor map.
+// of three 16-byte K chunks (8 fp16 each); chunk c of row r lives at byte  c * 2048 + r * 16.  Eight consecutive rows of
+// one chunk form the 8 x 16 B core matrix (128 contiguous bytes), so the stride between 8-row groups (SBO) is 128 B, and
+// the descriptor's leading-dimension offset (LBO) is the distance between the two chunks one K = 16 MMA reads:
+//     A, MMA 1: chunks (0, 1), LBO 2048        B, MMA 1: chunks (0, 0), LBO 0  — -2nh is stored once and read twice
+//     A, MMA 2: chunks (0, 2), LBO 4096        B, MMA 2: chunks (1, 2), LBO 2048
+// The tree keeps this image per 128-node tile in global memory (6 KB, contiguous), so a tile reaches shared memory as ONE
+// 1-D bulk copy (cp.async.bulk, SASS UBLKCP) — no tensor map.  (tools/tc_probe_f16.cu checks the arithmetic on the GPU.)
 #pragma once
 #include <cstdint>
+#include <cuda_fp16.h>
 
 namespace sqmp {
 
 constexpr int TC_ROWS = 128;                    // rows of an operand tile: queries of a query tile / nodes of a node tile
-constexpr int TC_CHUNKS = 6;                    // 16-byte K chunks per row
+constexpr int TC_CHUNKS = 3;                    // 16-byte K chunks per row
 constexpr int TC_CHUNK_BYTES = TC_ROWS * 16;    // 2048
-constexpr int TC_TILE_BYTES = TC_CHUNKS * TC_CHUNK_BYTES;   // 12288
+constexpr int TC_TILE_BYTES = TC_CHUNKS * TC_CHUNK_BYTES;   // 6144
 constexpr int TC_TILE_FLOAT4 = TC_TILE_BYTES / 16;
+constexpr double TC_MAX_NORM2 = 6.0e4;          // |x|^2 below this: every coordinate and the norm itself fit fp16
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
 
-// round to tf32 (nearest, ties away), low 13 bits cleared: the value the tensor core multiplies
-__device__ __forceinline__ float tf32_round(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r & 0xffffe000u);
-}
-// x = h + m + e with tf32 h, m and |e| <= 2^-22 |x|   (x - h is exact in fp32)
-__device__ __forceinline__ void tf32_split2(float x, float &h, float &m) {
-  h = tf32_round(x);
-  m = tf32_round(x - h);
-}
-// three tf32 pieces of a non-negative double (|residual| <= 2^-33 v)
-__device__ __forceinline__ void tf32_split3(double v, float &p0, float &p1, float &p2) {
-  p0 = tf32_round(__double2float_rn(v));
-  const double r1 = v - double(p0);
-  p1 = tf32_round(__double2float_rn(r1));
-  const double r2 = r1 - double(p1);
-  p2 = tf32_round(__double2float_rn(r2));
+struct alignas(16) TcChunk {   // eight fp16 = one 16-byte K chunk of one row
+  __half v[8];
+};
+// x = h + m + e with fp16 h, m: |e| <= 2^-22 |x|, or half a subnormal step (2^-25) when m is tiny
+__device__ __forceinline__ void fp16_split2(double x, __half &h, __half &m) {
+  h = __double2half(x);
+  m = __double2half(x - double(__half2float(h)));
 }
 
-// image row of one node (B operand): chunks 0,1 = -2 nh; 2,3 = -2 nm; 4 = (p0, p1, p2, 0); 5 = 0
+// image row of one node (B operand): chunk 0 = -2 nh, 1 = -2 nm, 2 = (p0, p1, p2, 0..)
 __device__ __forceinline__ void tc_write_node_row(float4 *tile, int r, const double (&v)[8]) {
-  float h[8], m[8];
+  TcChunk hi, mid, nrm;
   double n2 = 0.0;
 #pragma unroll
   for (int d = 0; d < 8; ++d) {
-    tf32_split2(__double2float_rn(v[d]), h[d], m[d]);
+    __half h, m;
+    fp16_split2(v[d], h, m);
+    hi.v[d] = __float2half(-2.f * __half2float(h));     // exact (a power of two)
+    mid.v[d] = __float2half(-2.f * __half2float(m));
     n2 += v[d] * v[d];
+    nrm.v[d] = __float2half(0.f);
   }
-  float p0, p1, p2;
-  tf32_split3(n2, p0, p1, p2);
-  tile[0 * TC_ROWS + r] = make_float4(-2.f * h[0], -2.f * h[1], -2.f * h[2], -2.f * h[3]);
-  tile[1 * TC_ROWS + r] = make_float4(-2.f * h[4], -2.f * h[5], -2.f * h[6], -2.f * h[7]);
-  tile[2 * TC_ROWS + r] = make_float4(-2.f * m[0], -2.f * m[1], -2.f * m[2], -2.f * m[3]);
-  tile[3 * TC_ROWS + r] = make_float4(-2.f * m[4], -2.f * m[5], -2.f * m[6], -2.f * m[7]);
-  tile[4 * TC_ROWS + r] = make_float4(p0, p1, p2, 0.f);
-  tile[5 * TC_ROWS + r] = make_float4(0.f, 0.f, 0.f, 0.f);
+  nrm.v[0] = __double2half(n2);
+  double rest = n2 - double(__half2float(nrm.v[0]));
+  nrm.v[1] = __double2half(rest);
+  rest -= double(__half2float(nrm.v[1]));
+  nrm.v[2] = __double2half(rest);
+  TcChunk *t = reinterpret_cast<TcChunk *>(tile);
+  t[0 * TC_ROWS + r] = hi;
+  t[1 * TC_ROWS + r] = mid;
+  t[2 * TC_ROWS + r] = nrm;
 }
-// image row of one query (A operand): chunks 0,1 = qh; 2,3 = qm; 4 = (1, 1, 1, 0); 5 = 0
-__device__ __forceinline__ void tc_write_query_row(float4 *tile, int r, const double (&v)[8]) {
-  float h[8], m[8];
+// image row of one query (A operand): chunk 0 = qh, 1 = qm, 2 = (1, 1, 1, 0..); usable = false: a zero row
+__device__ __forceinline__ void tc_write_query_row(float4 *tile, int r, const double (&v)[8], bool usable) {
+  TcChunk hi, mid, one;
 #pragma unroll
-  for (int d = 0; d < 8; ++d) tf32_split2(__double2float_rn(v[d]), h[d], m[d]);
-  tile[0 * TC_ROWS + r] = make_float4(h[0], h[1], h[2], h[3]);
-  tile[1 * TC_ROWS + r] = make_float4(h[4], h[5], h[6], h[7]);
-  tile[2 * TC_ROWS + r] = make_float4(m[0], m[1], m[2], m[3]);
-  tile[3 * TC_ROWS + r] = make_float4(m[4], m[5], m[6], m[7]);
-  tile[4 * TC_ROWS + r] = make_float4(1.f, 1.f, 1.f, 0.f);
-  tile[5 * TC_ROWS + r] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int d = 0; d < 8; ++d) {
+    fp16_split2(usable ? v[d] : 0.0, hi.v[d], mid.v[d]);
+    one.v[d] = __float2half(d < 3 ? 1.f : 0.f);
+  }
+  TcChunk *t = reinterpret_cast<TcChunk *>(tile);
+  t[0 * TC_ROWS + r] = hi;
+  t[1 * TC_ROWS + r] = mid;
+  t[2 * TC_ROWS + r] = one;
 }
 
 // ---- shared-memory matrix descriptor (64 bit): start >> 4 [0,14) | LBO >> 4 [16,30) | SBO >> 4 [32,46) | version 1 [46,48)
 //      | base offset 0 [49,52) | layout type 0 = no swizzle [61,64)
-__device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr) {
-  return uint64_t((smem_addr & 0x3ffffu) >> 4) | (uint64_t(TC_CHUNK_BYTES >> 4) << 16) | (uint64_t(128 >> 4) << 32) | (uint64_t(1) << 46);
+__device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return uint64_t((smem_addr & 0x3ffffu) >> 4) | (uint64_t(lbo_bytes >> 4) << 16) | (uint64_t(128 >> 4) << 32) | (uint64_t(1) << 46);
 }
-// ---- instruction descriptor (32 bit): D fp32 [4,6) = 1 | A tf32 [7,10) = 2 | B tf32 [10,13) = 2 | A, B K-major [15], [16] = 0
+// ---- instruction descriptor (32 bit): D fp32 [4,6) = 1 | A fp16 [7,10) = 0 | B fp16 [10,13) = 0 | A, B K-major [15], [16] = 0
 //      | N >> 3 [17,23) | M >> 4 [24,29)
-constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(TC_ROWS >> 3) << 17) | (uint32_t(TC_ROWS >> 4) << 24);
+constexpr uint32_t TC_IDESC = (1u << 4) | (uint32_t(TC_ROWS >> 3) << 17) | (uint32_t(TC_ROWS >> 4) << 24);
 
 // D[tmem] (+)= A[smem] . B[smem]^T; one thread issues it for the CTA
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, bool accumulate) {
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, bool accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(TC_IDESC), "r"(uint32_t(accumulate))
       : "memory");
