@@ -635,16 +635,19 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
     uint32_t head[SERVED];
 #pragma unroll
     for (int k = 0; k < SERVED; ++k) head[k] = 0u;
+    int patience = 0;
     for (;;) {
-      int k = 0;
-      uint32_t avail = 0u;
+      // a batch is gathered from all its rings; it waits a little for a full one (an L2 round trip costs the same for 3 pairs
+      // as for 32), but not long: the scan's thresholds tighten only when pairs are evaluated
+      uint32_t av[SERVED], total = 0u;
 #pragma unroll
-      for (int i = 0; i < SERVED; ++i) {   // the fullest of its rings
-        const uint32_t a = ld_vol(&sh->tail[ev + i * TC_EVAL_WARPS]) - head[i];
-        if (a > avail) { avail = a; k = i; }
+      for (int i = 0; i < SERVED; ++i) {
+        av[i] = ld_vol(&sh->tail[ev + i * TC_EVAL_WARPS]) - head[i];
+        total += av[i];
       }
-      if (avail == 0u) {
-        if (ld_vol(&sh->done) < uint32_t(TC_EPI_WARPS)) { __nanosleep(200); continue; }
+      const bool scan_done = ld_vol(&sh->done) == uint32_t(TC_EPI_WARPS);
+      if (total == 0u) {
+        if (!scan_done) { __nanosleep(200); continue; }
         // every scan warp has published its last tail before `done`: one more look
         bool empty = true;
 #pragma unroll
@@ -652,19 +655,28 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
         if (empty) break;
         continue;
       }
-      const int rid = ev + k * TC_EVAL_WARPS;
-      uint32_t hk = 0u;
+      if (total < 32u && !scan_done && patience < 6) { ++patience; __nanosleep(200); continue; }
+      patience = 0;
+      uint32_t e = 0u;
+      int start = 0;
 #pragma unroll
-      for (int i = 0; i < SERVED; ++i) hk = i == k ? head[i] : hk;
-      const int cnt = min(32, int(avail));
-      const bool have = lane < cnt;
-      const uint32_t e = have ? *reinterpret_cast<volatile uint32_t *>(&sh->ring[rid][(hk + lane) % TC_RING]) : 0u;
+      for (int i = 0; i < SERVED; ++i) {
+        const int rid = ev + i * TC_EVAL_WARPS;
+        const int take = min(int(av[i]), 32 - start);
+        if (lane >= start && lane < start + take)
+          e = 0x80000000u | *reinterpret_cast<volatile uint32_t *>(&sh->ring[rid][(head[i] + uint32_t(lane - start)) % TC_RING]);
+        head[i] += uint32_t(take);
+        start += take;
+      }
+      const bool have = e != 0u;
       __threadfence_block();
       __syncwarp();
-      hk += cnt;
+      if (lane < SERVED) {   // the slots may be reused
+        uint32_t h = 0u;
 #pragma unroll
-      for (int i = 0; i < SERVED; ++i) head[i] = i == k ? hk : head[i];
-      if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&sh->head[rid]) = hk;   // the slots may be reused
+        for (int i = 0; i < SERVED; ++i) h = lane == i ? head[i] : h;
+        *reinterpret_cast<volatile uint32_t *>(&sh->head[ev + lane * TC_EVAL_WARPS]) = h;
+      }
       const int r = int(e >> 1) & (TC_QUERIES - 1);
       const int64_t n = n0 + int64_t((e >> 9) & (TC_MAX_CHUNK - 1));
       const double *qp = queries + (q_first + r) * SQMP_DOF;

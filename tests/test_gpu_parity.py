@@ -691,6 +691,34 @@ def test_fp32_prefilter_is_sound_on_adversarial_trees(ctx, variant):
         ctx.set_option("nn_variant", 0)
 
 
+def test_tensor_core_scan_edge_cases(ctx):
+    """Variant 4 (tcgen05 pre-filter on fp16 pieces, nn.cu: k_nn_tc): ragged sizes (Q not a multiple of the 256-query CTA
+    tile, N not a multiple of the 128-node tile, several chunks), queries whose coordinates do not fit fp16 (zero operand
+    row, every pair evaluated exactly), a NaN query, a tree that does not fit fp16 (falls back to variant 3), tiny
+    coordinates (fp16 subnormal pieces) — ids and radius sets equal the oracle's in every case."""
+    ctx.set_option("nn_variant", 4)
+    try:
+        for trial, (N, Q, scale) in enumerate(((70001, 2500, 1.0), (5003, 301, 1.0), (12345, 777, 1e-4), (9000, 513, 300.0))):
+            nodes, cost = syn.random_tree(N, seed=900 + trial, cost_seed=950 + trial)
+            nodes = nodes * scale
+            queries = syn.sample_configs(Q, seed=970 + trial) * scale
+            queries[3] = nodes[11]
+            queries[5] = queries[5] + 1.0e3                # |q|^2 > 6e4: unusable as an fp16 operand
+            queries[7, 2] = np.nan
+            nodes[N - 1] = nodes[11]                        # tie with a later id
+            ctx.tree_reset(6)
+            ctx.tree_append_batch(6, nodes, cost)
+            want = oracle.nearest(nodes, queries, nthreads=8)
+            assert np.array_equal(ctx.nn_nearest(6, queries), want), trial
+            r = 1.5 * scale
+            got = ctx.nn_radius(6, queries, None, float(r), 20)
+            ref = oracle.near_topk(nodes, cost, queries, None, float(r), 20, nthreads=8)
+            for a, b, name in zip(got, ref, ("low", "high", "count")):
+                assert np.array_equal(a, b), (trial, name)
+    finally:
+        ctx.set_option("nn_variant", 0)
+
+
 def test_single_query_fast_path_equals_batched_path(ctx, orc, small_world):
     """Q = 1 (the planner's call shape) takes the one-launch path (k_nn_single, answers in mapped pinned memory) and
     validity calls of <= 4096 states take the zero-copy path; both must equal the batched kernels and the oracle."""
