@@ -44,6 +44,15 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_tensor_peak():
+    """Dense bf16/fp16 TFLOP/s of this pool's B200 (cuBLAS, burst) — the denominator for the tensor-core NN scan."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["bf16_tflops"]), "measured (MEASURED_PEAKS.json, cuBLAS bf16 burst)"
+    return 2250.0, "fallback (nominal dense bf16)"
+
+
 def bind_to_gpu_numa(index):
     """Run this process on the CPU cores local to GPU `index` (sysfs local_cpulist of its PCI function) so that pinned host
     buffers are allocated on the GPU's own NUMA node: the host-buffer (e2e) path is PCIe-bound and a remote node costs up to
@@ -616,13 +625,21 @@ def side_metrics(ctx, torch, dev, stream, d_qs_rot, S):
     ms = t_ms(lambda: ctx.nn_nearest_dev(0, d_qs, Q, d_ids, stream), n=2, warm=1)
     out["nn_nearest_queries_per_s"] = Q / ms * 1e3
     out["nn_nearest_pairs_per_s"] = N * Q / ms * 1e3
-    out["nn_nearest_hbm_frac"] = (N * 64 + Q * 68) / (ms * 1e-3) / 1e9 / peak
+    # the scan's estimates come out of two M128 N128 K16 fp16 MMAs per 128 x 128 pairs (nn.cu: k_nn_tc): 64 issued flop per pair
+    tpeak, tsrc = measured_tensor_peak()
+    out["nn_nearest_ms"] = ms
+    out["nn_nearest_roofline"] = {"bound": "tensor", "achieved": N * Q * 64 / (ms * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                                  "frac": N * Q * 64 / (ms * 1e-3) / 1e12 / tpeak, "peak_source": tsrc,
+                                  "kernel": "k_nn_tc<false> (tcgen05 fp16-split pre-filter + exact fp64 evaluation of what passes)",
+                                  "note": "issued MMA flop (operands are split in two fp16 pieces); the epilogue reads every estimate "
+                                          "from TMEM, which is what bounds the kernel (profiles/r2_k3_tc_nearest_ncu_summary.txt)"}
     d_low = torch.empty((Q, 20), dtype=torch.int32, device=dev)
     d_high = torch.empty_like(d_low)
     d_cnt = torch.empty(Q, dtype=torch.int32, device=dev)
     d_ov = torch.zeros(1, dtype=torch.int32, device=dev)
     ms = t_ms(lambda: ctx.nn_radius_dev(0, d_qs, None, Q, 1.5, 20, d_low, d_high, d_cnt, d_ov, stream), n=2, warm=1)
     out["nn_radius_queries_per_s"] = Q / ms * 1e3
+    out["nn_radius_ms"] = ms
     out["nn_config"] = "N=2^20 nodes, Q=2^16 queries, r=1.5, k=20"
     return out
 
@@ -691,7 +708,7 @@ def run_config3(args):
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
     if rank == 0:
-        peak, peak_src = measured_peaks()
+        tpeak, tsrc = measured_tensor_peak()
         ms = total_ms / steps
         algo = N * (64 + 72) + Q * (64 + 68) + Q * (4 + (2 * K + 1) * 4)      # SURVEY.md §8d rows K3 + K4
         print(json.dumps({
@@ -700,12 +717,14 @@ def run_config3(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "config3: N=2^20-node tree (replicated), Q=2^16 queries sharded over %d GPU(s), nearest + radius r=1.5 k=20, "
                                    "ids all-gathered" % world_size,
-                       "l2": "the 72 MiB tree (+36 MiB fp32 shadow) is L2-resident by design and re-read by every query tile"},
+                       "l2": "the 48 MiB fp16 operand image of the tree is L2-resident by design and re-read by every 256-query tile"},
             "pairs_per_s": 2.0 * N * Q / (ms * 1e-3),
-            "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": algo / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "k_nn_qt_pf<false> + k_nn_qt_pf<true> (fp32 pre-filter, fp64 exact)", "kernel_ms": ms,
-                         "note": "compute-bound scan (FMA pipe / shared-memory pipe ~60 %): the HBM fraction is tiny by construction"},
+            "roofline": {"bound": "tensor", "achieved": 2.0 * N * Q * 64 / (ms * 1e-3) / 1e12 / world_size, "peak": tpeak, "unit": "TFLOP/s",
+                         "frac": 2.0 * N * Q * 64 / (ms * 1e-3) / 1e12 / world_size / tpeak, "traffic": None, "peak_source": tsrc,
+                         "kernel": "k_nn_tc<false> + k_nn_tc<true> (tcgen05 fp16-split pre-filter, fp64 exact)", "kernel_ms": ms,
+                         "algorithmic_hbm_bytes": algo,
+                         "note": "per GPU; issued MMA flop (64 per pair: two K=16 fp16 MMAs over split operands); the scan is bounded by "
+                                 "the TMEM reads of its epilogue, the HBM traffic is tiny by construction"},
             "gpu_launches": int(launches), "clocks": sampler.summary()}))
     ctx.close()
     if world_size > 1:
