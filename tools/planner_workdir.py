@@ -63,7 +63,7 @@ def config5_queries(check_states, n_queries, seed=5, xy_half=11.0, goal_dist=(1.
     rng = np.random.default_rng(seed)
     s0, g0 = config1_queries(1)
     starts, goals = [], []
-    for _ in range(400):
+    for _ in range(1500):   # ~1.5 pairs per round survive in W512 with the covering model
         cand = syn.sample_configs(1 << 15, seed=int(rng.integers(1 << 30)), xy_half=xy_half)
         cand[:, 3:] = s0[0, 3:] + rng.uniform(-0.15, 0.15, size=(len(cand), 5))
         free = cand[~check_states(cand)]
