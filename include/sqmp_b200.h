@@ -237,7 +237,8 @@ int sqmp_nn_radius_dev(sqmp_ctx *ctx, int tree, const double *d_queries, const i
 
 /* Introspection for the bench: number of kernels this context has launched so far. */
 int64_t sqmp_kernel_launches(const sqmp_ctx *ctx);
-/* Tuning knobs (implementation detail, stable names): "fk_precision" 32|64, "nn_variant" 0=auto|1|2 ... */
+/* Tuning knobs (implementation detail, stable names): "fk_precision" 32|64, "nn_variant" 0=auto | 1 query-per-thread fp64 | 2 warp-per-query |
+ * 3 fp32 pre-filter | 4 tensor-core pre-filter (auto for >= 2048 queries while the tree fits fp16; results identical in all) ... */
 int sqmp_set_option(sqmp_ctx *ctx, const char *name, int64_t value);
 
 #ifdef __cplusplus
