@@ -753,6 +753,8 @@ def run_config5(args):
     shim = os.path.join(ROOT, "squirrel_motion_planner_b200", "shim")
     desc = os.path.join(ROOT, "squirrel_motion_planner_b200", "data", "robotino_plan.sqmpdesc")
     n_queries, iters = args.queries, args.iterations
+    if args.threads <= 0:   # the planner front-end is host-bound (SQMP_PLAN_PROFILE=1): give every GPU its share of the host cores
+        args.threads = max(1, min(4, (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)) // max(1, world_size)))
     w = syn.box_world(g=512, n_boxes=2048, seed=4321)                       # W512, SURVEY.md §8d
     # collision-free (start, goal) pairs: rejection sampling with the CUDA checker itself (self + map), seed 5
     ctx = api.default_context(local_rank)
@@ -778,6 +780,8 @@ def run_config5(args):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("sqmp_plan failed: " + r.stderr[-500:])
+    if os.environ.get("SQMP_PLAN_PROFILE") == "1" and rank == 0:          # where the runner's wall time goes (shim/sqmp_multi.hpp)
+        sys.stderr.write("".join(l + "\n" for l in r.stderr.splitlines() if l.startswith("#")))
     tail = [l for l in r.stdout.splitlines() if l.startswith("# queries")][-1].split()
     secs, states, its = float(tail[4]), int(tail[6]), int(tail[8])
     rows = [l.split() for l in r.stdout.splitlines() if l and not l.startswith("#") and "invalid" not in l]
@@ -833,7 +837,7 @@ def main():
     ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5"])
     ap.add_argument("--queries", type=int, default=1024, help="config5: number of planning queries")
     ap.add_argument("--iterations", type=int, default=1000, help="config5: BiRRT* iterations per query")
-    ap.add_argument("--threads", type=int, default=1, help="config5: host threads per GPU, each with its own context")
+    ap.add_argument("--threads", type=int, default=0, help="config5: host threads per GPU, each with its own context (0 = host cores / GPUs, at most 4)")
     ap.add_argument("--batch", type=int, default=512, help="config5: queries in flight per GPU (1 = sequential runner)")
     ap.add_argument("--gather", default="nccl", choices=["auto", "p2p", "nccl"],
                     help="N > 1: mask all-gather fused into the kernel over peer memory (p2p) or ncclAllGather (nccl)")

@@ -93,6 +93,10 @@ struct Ctx {
   unsigned char *pin2_h = nullptr, *pin2_d = nullptr;   // mapped pinned staging of the multi-tree NN calls (lazy)
   unsigned *d_ticket = nullptr;     // [0] ticket, [1] hit counter of k_nn_single
   bool tree_writes_pending = false; // unsynchronised single-node writes are in flight on streams[0]
+  // single-node tree writes wait here (mapped pinned memory, two halves of TW_CAP records) until a call reads a tree
+  unsigned char *tw_h = nullptr, *tw_d = nullptr;
+  int tw_half = 0, tw_n = 0;
+  cudaEvent_t tw_done[2] = {nullptr, nullptr};   // the flush that last read a half
   int64_t small_call_states = 4096; // validity calls up to this many states take the low-latency path
   cudaStream_t streams[2] = {nullptr, nullptr};
   cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -605,8 +609,54 @@ static void tree_track_norm(TreeDev &t, const double *q, int64_t n) {
   t.rmax2 = m;
 }
 
+// ---- deferred single-node writes: sqmp_tree_append / sqmp_tree_update cost a record in pinned memory instead of a launch;
+//      ONE launch on streams[0] writes the queue before anything reads a tree (every sqmp_nn_* entry, the batch writers,
+//      reset, growth).  A second write to the same node replaces its record, so the queue never holds two for one target.
+static const int TW_CAP = 256;
+static int flush_tree_writes(Ctx *c) {
+  if (c->tw_n == 0) return SQMP_OK;
+  const size_t rec = tree_write_bytes();
+  cudaError_t e = launch_tree_write_many(c->tw_d + size_t(c->tw_half) * TW_CAP * rec, c->tw_n, c->streams[0]);
+  if (e == cudaSuccess) e = cudaEventRecord(c->tw_done[c->tw_half], c->streams[0]);
+  if (e != cudaSuccess) return fail(c, SQMP_ERR_CUDA, "tree write flush", e);
+  c->tree_writes_pending = true;
+  c->launches += 1;
+  c->tw_half ^= 1;
+  c->tw_n = 0;
+  e = cudaEventSynchronize(c->tw_done[c->tw_half]);   // the half about to be refilled: its flush (two ago) has long finished
+  if (e != cudaSuccess) return fail(c, SQMP_ERR_CUDA, "cudaEventSynchronize(tree write half)", e);
+  return SQMP_OK;
+}
+static int queue_tree_write(Ctx *c, const TreeDev &t, int64_t id, const double *q, double cost, bool may_be_queued) {
+  const size_t rec = tree_write_bytes();
+  if (!c->tw_h) {
+    cudaError_t e = cudaHostAlloc((void **)&c->tw_h, 2 * TW_CAP * rec, cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void **)&c->tw_d, c->tw_h, 0);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->tw_done[i], cudaEventDisableTiming);
+    if (e != cudaSuccess) return fail(c, SQMP_ERR_NOMEM, "cudaHostAlloc(tree write queue)", e);
+  }
+  unsigned char *base = c->tw_h + size_t(c->tw_half) * TW_CAP * rec;
+  for (int i = may_be_queued ? c->tw_n - 1 : -1; i >= 0; --i)   // (an appended node is new: nothing to look for)
+    if (tree_write_same_target(base + size_t(i) * rec, t, id)) {
+      tree_write_fill(base + size_t(i) * rec, t, id, q, cost);
+      return SQMP_OK;
+    }
+  if (c->tw_n == TW_CAP) {
+    int rc = flush_tree_writes(c);
+    if (rc) return rc;
+    base = c->tw_h + size_t(c->tw_half) * TW_CAP * rec;
+  }
+  tree_write_fill(base + size_t(c->tw_n) * rec, t, id, q, cost);
+  c->tw_n += 1;
+  return SQMP_OK;
+}
+
 static int tree_reserve(Ctx *c, TreeDev &t, int64_t need) {
   if (need <= t.cap) return SQMP_OK;
+  {   // queued single-node writes carry the old buffers' addresses
+    int rcf = flush_tree_writes(c);
+    if (rcf) return rcf;
+  }
   // growing copies the old buffers with blocking copies on the legacy stream, which does not order against the
   // non-blocking streams[0]: single-node writes still in flight there (sqmp_tree_append / sqmp_tree_update) must land
   // in the OLD buffers before they are copied
@@ -950,6 +1000,9 @@ void sqmp_destroy(sqmp_ctx *ctx) {
     if (b.p) cudaFree(b.p);
   if (ctx->pin_h) cudaFreeHost(ctx->pin_h);
   if (ctx->pin2_h) cudaFreeHost(ctx->pin2_h);
+  if (ctx->tw_h) cudaFreeHost(ctx->tw_h);
+  for (auto &e : ctx->tw_done)
+    if (e) cudaEventDestroy(e);
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
   for (auto &s : ctx->streams)
     if (s) cudaStreamDestroy(s);
@@ -1500,9 +1553,16 @@ int sqmp_sample_informed(sqmp_ctx *ctx, uint64_t seed, int64_t first, int64_t n,
   if (tree < 0 || tree >= SQMP_MAX_TREES) return fail(c, SQMP_ERR_INVALID, "bad tree index"); \
   TreeDev &t = c->trees[tree];
 
+#define FLUSH_TREE_WRITES()                  \
+  {                                          \
+    int rc_flush_ = flush_tree_writes(c);    \
+    if (rc_flush_) return rc_flush_;         \
+  }
+
 int sqmp_tree_reset(sqmp_ctx *ctx, int tree) {
   CHECK_CTX();
   CHECK_TREE();
+  FLUSH_TREE_WRITES();
   t.n = 0;
   t.rmax2 = 0.0;
   return SQMP_OK;
@@ -1518,14 +1578,13 @@ int sqmp_tree_append(sqmp_ctx *ctx, int tree, const double q[SQMP_DOF], double c
   CHECK_TREE();
   if (!q) return fail(c, SQMP_ERR_INVALID, "tree_append: null q");
   if (t.n >= 0x7fffffff) return fail(c, SQMP_ERR_INVALID, "tree full");
-  // stream-ordered, not synchronised: the node travels in the kernel parameters, and every later call that reads
-  // the tree runs on (or synchronises with) the same stream.  Growing the buffers synchronises the device itself.
+  // deferred: the node waits in the write queue (queue_tree_write) until a call reads a tree; the flush is stream-ordered
+  // on streams[0] and every reader runs on (or synchronises with) that stream.  Growing the buffers flushes first.
   int rc = tree_reserve(c, t, t.n + 1);   // (synchronises streams[0] itself when it has to grow)
   if (rc) return rc;
   tree_track_norm(t, q, 1);
-  CU(launch_tree_set_one(t, t.n, q, cost, c->streams[0]));
-  c->tree_writes_pending = true;
-  c->launches += 1;
+  rc = queue_tree_write(c, t, t.n, q, cost, false);
+  if (rc) return rc;
   if (id_out) *id_out = int32_t(t.n);
   t.n += 1;
   return SQMP_OK;
@@ -1538,6 +1597,7 @@ int sqmp_tree_append_batch(sqmp_ctx *ctx, int tree, const double *q, const doubl
   if (t.n + n > 0x7fffffff) return fail(c, SQMP_ERR_INVALID, "tree full");
   if (first_id_out) *first_id_out = int32_t(t.n);
   if (n == 0) return SQMP_OK;
+  FLUSH_TREE_WRITES();
   int rc = tree_reserve(c, t, t.n + n);
   if (rc) return rc;
   void *dq, *dc;
@@ -1558,10 +1618,7 @@ int sqmp_tree_update(sqmp_ctx *ctx, int tree, int32_t id, const double q[SQMP_DO
   CHECK_TREE();
   if (!q || id < 0 || id >= t.n) return fail(c, SQMP_ERR_INVALID, "tree_update: bad id");
   tree_track_norm(t, q, 1);
-  CU(launch_tree_set_one(t, id, q, cost, c->streams[0]));   // stream-ordered (see sqmp_tree_append)
-  c->tree_writes_pending = true;
-  c->launches += 1;
-  return SQMP_OK;
+  return queue_tree_write(c, t, id, q, cost, true);   // deferred (see sqmp_tree_append)
 }
 int sqmp_tree_update_costs(sqmp_ctx *ctx, int tree, const int32_t *ids, const double *cost, int64_t n) {
   CHECK_CTX();
@@ -1570,6 +1627,7 @@ int sqmp_tree_update_costs(sqmp_ctx *ctx, int tree, const int32_t *ids, const do
   if (n == 0) return SQMP_OK;
   for (int64_t i = 0; i < n; ++i)
     if (ids[i] < 0 || ids[i] >= t.n) return fail(c, SQMP_ERR_INVALID, "tree_update_costs: bad id");
+  FLUSH_TREE_WRITES();
   void *di, *dc;
   int rc;
   if ((rc = ensure(c, 0, size_t(n) * 4, &di))) return rc;
@@ -1586,6 +1644,7 @@ int sqmp_tree_update_costs(sqmp_ctx *ctx, int tree, const int32_t *ids, const do
 // ---------------------------------------------------------------------------------------------------- NN
 int sqmp_nn_nearest_dev(sqmp_ctx *ctx, int tree, const double *d_queries, int64_t Q, int32_t *d_id, void *stream) {
   CHECK_CTX();
+  FLUSH_TREE_WRITES();
   CHECK_TREE();
   if (Q < 0 || (Q > 0 && (!d_queries || !d_id))) return fail(c, SQMP_ERR_INVALID, "nn_nearest_dev: null pointer");
   if (Q == 0) return SQMP_OK;
@@ -1612,6 +1671,7 @@ int sqmp_nn_radius_dev(sqmp_ctx *ctx, int tree, const double *d_queries, const i
                        double r, int k, int32_t *d_low, int32_t *d_high, int32_t *d_count, int32_t *d_overflow,
                        void *stream) {
   CHECK_CTX();
+  FLUSH_TREE_WRITES();
   CHECK_TREE();
   if (Q < 0 || k < 1 || k > 1024 || (Q > 0 && (!d_queries || !d_low || !d_high || !d_count || !d_overflow)))
     return fail(c, SQMP_ERR_INVALID, "nn_radius_dev: bad argument");
@@ -1641,6 +1701,7 @@ int sqmp_nn_radius_dev(sqmp_ctx *ctx, int tree, const double *d_queries, const i
 
 int sqmp_nn_nearest(sqmp_ctx *ctx, int tree, const double *queries, int64_t Q, int32_t *id_out) {
   CHECK_CTX();
+  FLUSH_TREE_WRITES();
   if (Q < 0 || (Q > 0 && (!queries || !id_out))) return fail(c, SQMP_ERR_INVALID, "nn_nearest: null pointer");
   if (Q == 0) return SQMP_OK;
   if (Q == 1 && c->nn_variant == 0) {   // the planner's call shape: one launch, answer in mapped host memory
@@ -1700,6 +1761,7 @@ static int radius_host_range(sqmp_ctx *ctx, int tree, const double *queries, con
 int sqmp_nn_radius(sqmp_ctx *ctx, int tree, const double *queries, const int32_t *exclude_id, int64_t Q, double r,
                    int k, int32_t *low_ids, int32_t *high_ids, int32_t *count_out) {
   CHECK_CTX();
+  FLUSH_TREE_WRITES();
   if (Q < 0 || k < 1 || k > 1024 || (Q > 0 && (!queries || !low_ids || !high_ids || !count_out)))
     return fail(c, SQMP_ERR_INVALID, "nn_radius: bad argument");
   if (Q == 0) return SQMP_OK;
@@ -1795,6 +1857,7 @@ static int nn_multi_range(Ctx *c, const int32_t *tree, const double *queries, co
 
 int sqmp_nn_nearest_multi(sqmp_ctx *ctx, const int32_t *tree, const double *queries, int64_t Q, int32_t *id_out) {
   CHECK_CTX();
+  FLUSH_TREE_WRITES();
   if (Q < 0 || (Q > 0 && (!tree || !queries || !id_out))) return fail(c, SQMP_ERR_INVALID, "nn_nearest_multi: null pointer");
   for (int64_t q0 = 0; q0 < Q; q0 += MULTI_MAX_Q) {
     const int64_t nq = Q - q0 < MULTI_MAX_Q ? Q - q0 : MULTI_MAX_Q;
@@ -1807,6 +1870,7 @@ int sqmp_nn_nearest_multi(sqmp_ctx *ctx, const int32_t *tree, const double *quer
 int sqmp_nn_radius_multi(sqmp_ctx *ctx, const int32_t *tree, const double *queries, const int32_t *exclude_id, int64_t Q,
                          double r, int k, int32_t *low_ids, int32_t *high_ids, int32_t *count_out) {
   CHECK_CTX();
+  FLUSH_TREE_WRITES();
   if (Q < 0 || k < 1 || k > MULTI_MAX_K || (Q > 0 && (!tree || !queries || !low_ids || !high_ids || !count_out)))
     return fail(c, SQMP_ERR_INVALID, "nn_radius_multi: bad argument");
   for (int64_t q0 = 0; q0 < Q; q0 += MULTI_MAX_Q) {

@@ -93,6 +93,43 @@ __global__ void k_tree_update_costs(TreePtrs t, const int32_t *__restrict__ ids,
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n && ids[i] >= 0 && ids[i] < size) t.cost[ids[i]] = cost[i];
 }
+// Deferred single-node writes (sqmp_tree_append / sqmp_tree_update): capi.cu queues them in mapped pinned memory and one
+// launch writes the whole queue before the next call that reads a tree.  A record carries its tree's pointers.
+struct TreeWrite {
+  TreePtrs p;
+  double q[SQMP_DOF];
+  double cost;
+  int64_t id;
+};
+__global__ void k_tree_write_many(const TreeWrite *__restrict__ w, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const TreeWrite e = w[i];   // (mapped host memory: read once)
+#pragma unroll
+  for (int d = 0; d < SQMP_DOF; ++d) {
+    e.p.q[d][e.id] = e.q[d];
+    e.p.aos[e.id * SQMP_DOF + d] = e.q[d];
+  }
+  e.p.cost[e.id] = e.cost;
+  write_shadow(e.p, e.id, e.q);
+}
+size_t tree_write_bytes() { return sizeof(TreeWrite); }
+void tree_write_fill(void *dst, const TreeDev &t, int64_t id, const double q[SQMP_DOF], double cost) {
+  TreeWrite *w = reinterpret_cast<TreeWrite *>(dst);
+  w->p = ptrs_of(t);
+  for (int d = 0; d < SQMP_DOF; ++d) w->q[d] = q[d];
+  w->cost = cost;
+  w->id = id;
+}
+bool tree_write_same_target(const void *rec, const TreeDev &t, int64_t id) {
+  const TreeWrite *w = reinterpret_cast<const TreeWrite *>(rec);
+  return w->id == id && w->p.cost == t.cost;
+}
+cudaError_t launch_tree_write_many(const void *d_records, int n, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  k_tree_write_many<<<unsigned((n + 63) / 64), 64, 0, st>>>(reinterpret_cast<const TreeWrite *>(d_records), n);
+  return cudaGetLastError();
+}
 cudaError_t launch_tree_append(TreeDev &t, const double *d_q_rows, const double *d_cost, int64_t first, int64_t n,
                                cudaStream_t st) {
   if (n <= 0) return cudaSuccess;

@@ -242,6 +242,11 @@ cudaError_t launch_tree_append(TreeDev &t, const double *d_q_rows, const double 
 cudaError_t launch_tree_set_one(TreeDev &t, int64_t id, const double q[SQMP_DOF], double cost, cudaStream_t st);
 cudaError_t launch_tree_update_costs(TreeDev &t, const int32_t *d_ids, const double *d_cost, int64_t n,
                                      cudaStream_t st);
+// deferred single-node writes (nn.cu: k_tree_write_many): records of tree_write_bytes() each, readable by the device
+size_t tree_write_bytes();
+void tree_write_fill(void *dst, const TreeDev &t, int64_t id, const double q[SQMP_DOF], double cost);
+bool tree_write_same_target(const void *rec, const TreeDev &t, int64_t id);
+cudaError_t launch_tree_write_many(const void *d_records, int n, cudaStream_t st);
 
 struct NNScratch {
   double *part_d;      // [chunks][Q]

@@ -20,8 +20,10 @@
 #include <ucontext.h>
 #endif
 
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -77,6 +79,28 @@ inline void *fiber_prepare(char *stack, size_t bytes, void (*entry)(void *), voi
   return sp;
 }
 #endif
+
+// Where a scheduler's wall time goes (SQMP_PLAN_PROFILE=1 prints it): the batched library calls per kind, the direct
+// per-query calls made from inside the fibers (tree writes, sample pools) and — the remainder — the planner's host logic.
+struct MultiProfile {
+  enum { NEAREST, NEAR, EDGES, VALID, APPEND, UPDATE, SAMPLE, INFORMED, N };
+  double sec[N] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long calls[N] = {0, 0, 0, 0, 0, 0, 0, 0};
+  bool on = false;
+  typedef std::chrono::steady_clock clock;
+  struct Scope {
+    MultiProfile *p; int k; clock::time_point t0;
+    Scope(MultiProfile *p_, int k_) : p(p_ && p_->on ? p_ : NULL), k(k_) { if (p) t0 = clock::now(); }
+    ~Scope() { if (p) { p->sec[k] += std::chrono::duration<double>(clock::now() - t0).count(); p->calls[k] += 1; } }
+  };
+  void print(double total, long rounds) const {
+    static const char *name[N] = {"nearest_multi", "radius_multi", "check_edges", "check_states", "tree_append", "tree_update", "sample", "sample_informed"};
+    double sum = 0.0;
+    for (int i = 0; i < N; ++i) sum += sec[i];
+    std::fprintf(stderr, "# profile: %.3f s, %ld rounds; host logic + scheduling %.3f s\n", total, rounds, total - sum);
+    for (int i = 0; i < N; ++i) std::fprintf(stderr, "#   %-16s %9ld calls %8.3f s %7.1f us/call\n", name[i], calls[i], sec[i], calls[i] ? 1e6 * sec[i] / calls[i] : 0.0);
+  }
+};
 
 struct MultiRequest {
   enum Kind { NONE = 0, NEAREST, NEAR, EDGES, VALID } kind = NONE;
@@ -138,21 +162,29 @@ class MultiSchedulerT;
 template <class Service>
 class FiberBackendT {
  public:
-  FiberBackendT() : sched_(NULL), svc_(NULL), index_(0), flags_(0), failed_(false) {}
-  void bind(MultiSchedulerT<Service> *s, Service *svc, int index) { sched_ = s; svc_ = svc; index_ = index; flags_ = svc->flags(); }
+  FiberBackendT() : sched_(NULL), svc_(NULL), prof_(NULL), index_(0), flags_(0), failed_(false) {}
+  void bind(MultiSchedulerT<Service> *s, Service *svc, int index, MultiProfile *prof = NULL) {
+    sched_ = s; svc_ = svc; index_ = index; flags_ = svc->flags(); prof_ = prof;
+  }
 
   void tree_reset(int slot) { ok(svc_->tree_reset(2 * index_ + slot)); }
   int tree_append(int slot, const double *q, double cost) {
     int32_t id = -1;
+    MultiProfile::Scope sc(prof_, MultiProfile::APPEND);
     ok(svc_->tree_append(2 * index_ + slot, q, cost, &id));
     return id;
   }
-  void tree_update(int slot, int id, const double *q, double cost) { ok(svc_->tree_update(2 * index_ + slot, id, q, cost)); }
+  void tree_update(int slot, int id, const double *q, double cost) {
+    MultiProfile::Scope sc(prof_, MultiProfile::UPDATE);
+    ok(svc_->tree_update(2 * index_ + slot, id, q, cost));
+  }
   void sample_batch(uint64_t seed, long long first, int n, const double *lo, const double *hi, int max_tries, double *q_out) {
+    MultiProfile::Scope sc(prof_, MultiProfile::SAMPLE);
     ok(svc_->sample(seed, first, n, lo, hi, max_tries, q_out));   // once per 256 iterations: not batched
   }
   void sample_informed_batch(uint64_t seed, long long first, int n, const double *lo, const double *hi, int max_tries,
                              const sqmp_informed &el, double *q_out) {
+    MultiProfile::Scope sc(prof_, MultiProfile::INFORMED);
     ok(svc_->sample_informed(seed, first, n, lo, hi, max_tries, el, q_out));   // redrawn when the best cost changes: not batched
   }
   inline int nearest(int slot, const double *q);
@@ -173,6 +205,7 @@ class FiberBackendT {
   }
   MultiSchedulerT<Service> *sched_;
   Service *svc_;
+  MultiProfile *prof_;
   int index_;
   unsigned flags_;
   bool failed_;
@@ -189,7 +222,11 @@ class MultiSchedulerT {
 
   MultiSchedulerT(Service *service, int batch)
       : svc_(service), flags_(service->flags()),
-        batch_(batch < 1 ? 1 : (batch > Service::max_batch() ? Service::max_batch() : batch)), failed_(false), rounds_(0), calls_(0) {}
+        batch_(batch < 1 ? 1 : (batch > Service::max_batch() ? Service::max_batch() : batch)), failed_(false), rounds_(0), calls_(0) {
+    const char *e = std::getenv("SQMP_PLAN_PROFILE");
+    prof_.on = e && e[0] == '1';
+  }
+  const MultiProfile &profile() const { return prof_; }
 
   // queries: rows start[8] goal[8]; results in query order.  Returns false on a library error.
   bool run(const double *queries, size_t n_queries, long iterations, uint64_t seed, size_t first_index, const Params &base,
@@ -201,7 +238,7 @@ class MultiSchedulerT {
       for (size_t i = 0; i < nb; ++i) {
         Fiber &f = fibers_[i];
         f.owner = this;
-        f.be.bind(this, svc_, int(i));
+        f.be.bind(this, svc_, int(i), &prof_);
         f.P = base;
         f.P.seed = seed + first_index + g0 + i;
         f.q = queries + (g0 + i) * 16;
@@ -311,7 +348,8 @@ class MultiSchedulerT {
     }
     if (!idx_.empty()) {
       ids_.assign(idx_.size(), 0);
-      ok(svc_->nearest_multi(trees_.data(), qs_.data(), int64_t(idx_.size()), ids_.data()));
+      { MultiProfile::Scope sc(&prof_, MultiProfile::NEAREST);
+        ok(svc_->nearest_multi(trees_.data(), qs_.data(), int64_t(idx_.size()), ids_.data())); }
       calls_ += 1;
       for (size_t j = 0; j < idx_.size(); ++j) fibers_[size_t(idx_[j])].be.req.id = ids_[j];
     }
@@ -333,8 +371,9 @@ class MultiSchedulerT {
       low_.assign(idx_.size() * size_t(kk), -1);
       high_.assign(idx_.size() * size_t(kk), -1);
       cnt_.assign(idx_.size(), 0);
-      ok(svc_->radius_multi(trees_.data(), qs_.data(), excl_.data(), int64_t(idx_.size()), rr, kk, low_.data(), high_.data(),
-                              cnt_.data()));
+      { MultiProfile::Scope sc(&prof_, MultiProfile::NEAR);
+        ok(svc_->radius_multi(trees_.data(), qs_.data(), excl_.data(), int64_t(idx_.size()), rr, kk, low_.data(), high_.data(),
+                              cnt_.data())); }
       calls_ += 1;
       for (size_t j = 0; j < idx_.size(); ++j) {
         MultiRequest &r = fibers_[size_t(idx_[j])].be.req;
@@ -359,7 +398,8 @@ class MultiSchedulerT {
       first_.assign(size_t(E), -1);
       if (flags_ != 0) {
         mask_.assign(size_t((E * (np + 1) + 31) / 32), 0u);
-        ok(svc_->check_edges(ea_.data(), eb_.data(), E, np, mask_.data(), first_.data()));
+        { MultiProfile::Scope sc(&prof_, MultiProfile::EDGES);
+          ok(svc_->check_edges(ea_.data(), eb_.data(), E, np, mask_.data(), first_.data())); }
         calls_ += 1;
       }
       size_t off = 0;
@@ -381,7 +421,8 @@ class MultiSchedulerT {
     if (!idx_.empty()) {
       mask_.assign((idx_.size() + 31) / 32, 0u);
       if (flags_ != 0) {
-        ok(svc_->check_states(qs_.data(), int64_t(idx_.size()), mask_.data()));
+        { MultiProfile::Scope sc(&prof_, MultiProfile::VALID);
+          ok(svc_->check_states(qs_.data(), int64_t(idx_.size()), mask_.data())); }
         calls_ += 1;
       }
       for (size_t j = 0; j < idx_.size(); ++j)
@@ -395,6 +436,7 @@ class MultiSchedulerT {
   int batch_;
   bool failed_;
   long rounds_, calls_;
+  MultiProfile prof_;
 #ifdef SQMP_FIBER_ASM
   void *main_sp_ = NULL;
 #else

@@ -50,6 +50,7 @@ int main(int argc, char **argv) {
       ok[size_t(t)] = sched.run(a.queries.data() + (a.first + lo) * 16, n, a.iterations, a.seed, a.first + lo, P, res[size_t(t)]) ? 1 : 0;
       rounds[size_t(t)] = sched.rounds();
       calls[size_t(t)] = sched.library_calls();
+      if (sched.profile().on && t == 0) sched.profile().print(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), sched.rounds());
     });
   }
   for (auto &th : pool) th.join();

@@ -580,6 +580,52 @@ def test_nearest_quirks_and_tree_mutation(ctx):
     assert ctx.tree_size(2) == 0
 
 
+def test_deferred_tree_writes_keep_program_order(ctx):
+    """Single-node appends / updates wait in a host-side queue and reach the device in one launch before the next call
+    that reads a tree (capi.cu: queue_tree_write).  Two trees interleaved, nodes updated several times before a read, an
+    update right after its append, more writes than the queue holds, a batch append and a cost update in between: every
+    answer equals the oracle's on the tree the program order defines."""
+    rng = np.random.default_rng(31)
+    mirror = {3: ([], []), 4: ([], [])}
+    for tr in (3, 4):
+        ctx.tree_reset(tr)
+    def check():
+        for tr in (3, 4):
+            nodes, cost = np.array(mirror[tr][0]), np.array(mirror[tr][1])
+            qs = np.concatenate([nodes[rng.integers(0, len(nodes), 8)] + 1e-3, syn.sample_configs(8, seed=int(rng.integers(1 << 30)))])
+            assert np.array_equal(ctx.nn_nearest(tr, qs), oracle.nearest(nodes, qs, nthreads=4))
+            got = ctx.nn_radius(tr, qs, None, 2.0, 5)
+            ref = oracle.near_topk(nodes, cost, qs, None, 2.0, 5, nthreads=4)
+            for a, b in zip(got, ref):
+                assert np.array_equal(a, b)
+    for step in range(700):
+        tr = 3 + int(rng.integers(0, 2))
+        nodes, cost = mirror[tr]
+        kind = rng.integers(0, 10)
+        if kind < 6 or len(nodes) < 4:
+            q, c = syn.sample_configs(1, seed=int(rng.integers(1 << 30)))[0], float(rng.uniform(0, 5))
+            assert ctx.tree_append(tr, q, c) == len(nodes)
+            nodes.append(q); cost.append(c)
+            if kind == 0:                                               # rewired at once
+                nodes[-1] = q + 0.5; cost[-1] = c + 1.0
+                ctx.tree_update(tr, len(nodes) - 1, nodes[-1], cost[-1])
+        elif kind < 9:
+            i = int(rng.integers(0, len(nodes)))
+            for _ in range(int(rng.integers(1, 4))):                    # the last write wins
+                nodes[i] = syn.sample_configs(1, seed=int(rng.integers(1 << 30)))[0]; cost[i] = float(rng.uniform(0, 5))
+                ctx.tree_update(tr, i, nodes[i], cost[i])
+        else:
+            i = int(rng.integers(0, len(nodes)))
+            cost[i] = float(rng.uniform(0, 5))
+            ctx.tree_update_costs(tr, np.array([i], dtype=np.int32), np.array([cost[i]]))
+        if step in (5, 40, 41, 400, 699):                               # (400: well past the 256 records of the queue)
+            check()
+        if step == 200:
+            extra = syn.sample_configs(10, seed=77)
+            ctx.tree_append_batch(tr, extra, np.ones(10))
+            nodes.extend(list(extra)); cost.extend([1.0] * 10)
+
+
 @pytest.mark.parametrize("variant", [1, 2, 3, 4])
 def test_radius_topk_bit_exact(ctx, variant):
     ctx.set_option("nn_variant", variant)
