@@ -158,6 +158,10 @@ int sqmp_sample_informed(sqmp_ctx *ctx, uint64_t seed, int64_t first, int64_t n,
 
 /* ---- tree mirror (DS:29-54; mutation sites BS:3298-3322, 5173-5193, 5518-5520) ------------------- */
 /* Invariant kept from the reference: node_id == index.  tree in [0, SQMP_MAX_TREES). */
+/* sqmp_tree_append / sqmp_tree_update cost a record in a host-side queue, not a launch: the queue reaches the device in
+ * ONE launch before the next call that reads a tree (any sqmp_nn_*, the batch writers, reset, growth).  Program order is
+ * kept — a later write to the same node replaces the queued one — so callers see exactly the semantics of immediate
+ * writes (the reference's push_back / in-place assignment at BS:3298-3322, 5173-5193). */
 int sqmp_tree_reset(sqmp_ctx *ctx, int tree);
 int sqmp_tree_append(sqmp_ctx *ctx, int tree, const double q[SQMP_DOF], double cost, int32_t *id_out);
 int sqmp_tree_append_batch(sqmp_ctx *ctx, int tree, const double *q, const double *cost, int64_t n,
