@@ -528,7 +528,13 @@ constexpr int TC_FIRST_EPI = 2 + TC_EVAL_WARPS;    // warp 0: copies, warp 1: MM
 constexpr int TC_THREADS = 32 * (TC_FIRST_EPI + TC_EPI_WARPS);
 constexpr int TC_TMEM_COLS = 2 * TC_QTILES * TC_ROWS;   // two accumulator buffers x query tiles x 128 columns = 512
 constexpr int TC_RING = 512;                       // surviving pairs waiting for their exact evaluation, per scan warp
-constexpr int TC_SEEDS = 32;                       // nodes of the chunk every query is measured against before the scan starts
+#ifndef TC_SEEDS_DEF
+#define TC_SEEDS_DEF 32
+#endif
+#ifndef TC_PATIENCE_DEF
+#define TC_PATIENCE_DEF 6
+#endif
+constexpr int TC_SEEDS = TC_SEEDS_DEF;                       // nodes of the chunk every query is measured against before the scan starts
 constexpr int TC_MAX_CHUNK = 1 << 22;              // a ring entry keeps 22 bits of node offset
 static_assert(TC_TILE_BYTES == SQMP_NN_TILE_IMG_BYTES, "capi.cu sizes the image with this");
 __device__ __forceinline__ double tc_error_bound(double R2) {
@@ -692,7 +698,7 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
         if (empty) break;
         continue;
       }
-      if (total < 32u && !scan_done && patience < 6) { ++patience; __nanosleep(200); continue; }
+      if (total < 32u && !scan_done && patience < TC_PATIENCE_DEF) { ++patience; __nanosleep(200); continue; }
       patience = 0;
       uint32_t e = 0u;
       int start = 0;
