@@ -45,11 +45,11 @@
 namespace sqmp {
 
 #ifndef KF_THREADS_DEF
-#define KF_THREADS_DEF 64
+#define KF_THREADS_DEF 32
 #endif
 constexpr int KF_THREADS = KF_THREADS_DEF;
 #ifndef KF_MIN_BLOCKS_DEF
-#define KF_MIN_BLOCKS_DEF 9
+#define KF_MIN_BLOCKS_DEF 18
 #endif
 constexpr int KF_MIN_BLOCKS = KF_MIN_BLOCKS_DEF;
 constexpr float KF_MAGIC = 12582912.0f;          // 1.5 * 2^23: (x + MAGIC) has round-to-nearest-even(x) in its low mantissa bits
@@ -102,9 +102,9 @@ __device__ __forceinline__ void kf_stage1(const float4 *__restrict__ rec, bool t
   }
 }
 
-// 64-thread CTAs (10 per SM at 96 registers): the shorter tail of small CTAs is worth 2.7 % over 128-thread ones (measured).
-// __launch_bounds__ asks for 9: ptxas still allocates 96 registers (10 CTAs resident) but spills 60 B instead of 84 B, 3 % faster
-// than asking for 10; asking for 8 (120 registers, no spills, 8 CTAs) and for 12 (80 registers) are both slower.
+// One-warp CTAs (21 per SM at 96 registers): a CTA lives as long as its slowest warp, so the smaller the CTA the shorter
+// the tail — 128 -> 64 threads was worth 2.7 %, 64 -> 32 another 3.3 % (0.350 -> 0.338 ms back to back).  __launch_bounds__
+// asks for 18 per SM: ptxas stays at 96 registers with 28 B of spills; asking for 21 (80 registers) spills 112 B for the same time.
 // SELF keeps the group frames and the pair hierarchy live on top of the map state: 128 registers (512 threads per SM)
 // avoid the spills that cost it 12 % at 96; the map-only kernel is indifferent between 512 and 640 threads per SM.
 // SIG: compile-time chain signature (fk_device.cuh) — for the reference's robot every segment advance is straight-line
