@@ -737,14 +737,14 @@ static double sumsq_threshold(double r) {
 }
 
 static int pick_variant(const Ctx *c, const TreeDev &t, int64_t Q) {
-  int v = c->nn_variant >= 1 && c->nn_variant <= 5 ? c->nn_variant : (Q >= 2048 ? 4 : 2);   // many queries: the tensor-core scan; few: a warp per query
-  if ((v == 4 || v == 5) && !(t.rmax2 < 6.0e4)) v = 3;   // its fp16 operands cannot hold this tree (tc_umma.cuh: TC_MAX_NORM2): fp32 pre-filter
+  int v = c->nn_variant >= 1 && c->nn_variant <= 4 ? c->nn_variant : (Q >= 2048 ? 4 : 2);   // many queries: the tensor-core scan; few: a warp per query
+  if (v == 4 && !(t.rmax2 < 6.0e4)) v = 3;   // its fp16 operands cannot hold this tree (tc_umma.cuh: TC_MAX_NORM2): fp32 pre-filter
   return v;
 }
 static int pick_chunk_hint(const Ctx *c, int variant, int64_t N, int64_t Q) {
   if (N <= 0) return 1;
   int64_t chunks;
-  if (variant == 4 || variant == 5) {
+  if (variant == 4) {
     // one 320-thread CTA per SM: the fewest chunks (each restarts the search for the best) that fill whole waves
     const int64_t qtiles = (Q + 255) / 256;
     const int64_t maxc = (N + 4095) / 4096;
@@ -1030,7 +1030,7 @@ int sqmp_set_option(sqmp_ctx *ctx, const char *name, int64_t value) {
   } else if (n == "chain_specialization") {
     c->chain_specialization = value != 0;
   } else if (n == "nn_variant") {
-    if (value < 0 || value > 5) return fail(c, SQMP_ERR_INVALID, "nn_variant must be 0..5");
+    if (value < 0 || value > 4) return fail(c, SQMP_ERR_INVALID, "nn_variant must be 0..4");
     c->nn_variant = int(value);
   } else if (n == "nn_hit_pool_bytes") {
     if (value < 4096) return fail(c, SQMP_ERR_INVALID, "nn_hit_pool_bytes too small");

@@ -854,313 +854,6 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// TG: the same tensor-core scan with a cheaper hand-over.  k_nn_tc files every (query, node) pair whose estimate passes,
-// which takes a dozen dependent warp collectives per tile that has one — and a scan warp that falls behind by one such
-// tile delays its accumulator.  Here a scan thread only compares the minimum of each run of 32 estimates with its
-// threshold and, when it passes, drops a record (tile, run, lane, minimum) into its warp's ring: no votes, no column
-// masks, a handful of instructions executed by the lanes concerned.  The evaluation warps take a record as one task for
-// the whole warp: 32 lanes evaluate the 32 nodes of the run exactly against that query (one coalesced 2 KB read of the
-// row-major tree), reduce to the lexicographic (distance, id) minimum — or, for the radius search, ballot the hits and
-// reserve their slots with ONE atomicAdd — and update the query's incumbent, which only they write.  The exact work
-// grows 32-fold per survivor but it is done side by side, off the scan's critical path, and a record whose minimum no
-// longer beats the incumbent is dropped unread.  The nearest search needs no feedback to be sound: a thread also keeps
-// the running minimum of its own estimates, and the true nearest node's estimate is at most 2 E above it.
-// ---------------------------------------------------------------------------------------------------------
-constexpr int TG_EVAL_WARPS = 4;                   // warp e serves scan warps e and e + 4
-constexpr int TG_FIRST_EPI = 2 + TG_EVAL_WARPS;
-constexpr int TG_THREADS = 32 * (TG_FIRST_EPI + TC_EPI_WARPS);
-constexpr int TG_RING = 256;                       // records per scan warp
-constexpr int TG_SERVED = TC_EPI_WARPS / TG_EVAL_WARPS;
-
-struct TgShared {
-  uint64_t full[TC_STAGES], empty[TC_STAGES];
-  uint64_t acc_full[2][TC_QTILES], acc_empty[2][TC_QTILES];
-  uint32_t tmem;
-  uint32_t tail[TC_EPI_WARPS], head[TC_EPI_WARPS];   // ring positions handed out (atomicAdd by the filing lanes) / consumed
-  uint32_t done;
-  float thr[TC_QUERIES];                        // per query: a run whose minimum is below this has to be evaluated
-  double best_d[TC_QUERIES], best_s[TC_QUERIES], e_minus_qq[TC_QUERIES];
-  int32_t best_id[TC_QUERIES], excl[TC_QUERIES];
-  uint2 ring[TC_EPI_WARPS][TG_RING];            // x = 1 << 31 | tile << 7 | run << 5 | lane (0 = empty), y = bits of the run's minimum
-};
-constexpr int TG_SMEM_BYTES = (TC_QTILES + TC_STAGES) * TC_TILE_BYTES + int(sizeof(TgShared)) + 16;
-
-template <bool RADIUS>
-__global__ void __launch_bounds__(TG_THREADS, 1)
-k_nn_tg(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ queries, int64_t Q, double rmax2,
-        double *__restrict__ part_d, int32_t *__restrict__ part_id,
-        const int32_t *__restrict__ exclude, double s_thr, int32_t *__restrict__ count, int32_t *__restrict__ hits,
-        int64_t hit_cap) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char *sA = smem, *sB = smem + TC_QTILES * TC_TILE_BYTES;
-  TgShared *sh = reinterpret_cast<TgShared *>(sB + TC_STAGES * TC_TILE_BYTES);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t n0 = int64_t(blockIdx.y) * chunk_len, n1 = min(N, n0 + chunk_len);
-  const int n_tiles = n0 < n1 ? int((n1 - n0 + TC_ROWS - 1) / TC_ROWS) : 0;
-  const float4 *img = t.img + (n0 / TC_ROWS) * TC_TILE_FLOAT4;
-  const int64_t q_first = int64_t(blockIdx.x) * TC_QUERIES;   // query of row 0
-
-  // ---- set-up: barriers, TMEM, rings, the queries as the A operand, their thresholds
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < TC_STAGES; ++i) { tc_mbar_init(&sh->full[i], 1); tc_mbar_init(&sh->empty[i], 1); }
-    for (int i = 0; i < 2 * TC_QTILES; ++i) { tc_mbar_init(&sh->acc_full[0][i], 1); tc_mbar_init(&sh->acc_empty[0][i], 4); }
-    for (int i = 0; i < TC_EPI_WARPS; ++i) sh->tail[i] = sh->head[i] = 0u;
-    sh->done = 0u;
-    tc_fence_mbar_init();
-  }
-  if (warp == 1) tc_tmem_alloc(&sh->tmem, TC_TMEM_COLS);
-  for (int i = threadIdx.x; i < TC_EPI_WARPS * TG_RING; i += TG_THREADS) sh->ring[0][i] = make_uint2(0u, 0u);
-  const int qt = (warp - TG_FIRST_EPI) >> 2, quarter = warp & 3;   // a warp may only read TMEM lanes [32 (warp % 4), +32)
-  const int row = qt * TC_ROWS + quarter * 32 + lane;              // this scan thread's query
-  float two_e = 0.f;                                               // nearest: twice the estimate's error bound
-  if (warp >= TG_FIRST_EPI) {
-    const bool live = q_first + row < Q;
-    const double *qp = queries + (q_first + row) * SQMP_DOF;
-    double v[SQMP_DOF], qq = 0.0;
-#pragma unroll
-    for (int d = 0; d < SQMP_DOF; ++d) {
-      v[d] = live ? qp[d] : 0.0;
-      qq += v[d] * v[d];
-    }
-    const bool usable = qq < TC_MAX_NORM2;   // fits fp16; otherwise (or NaN): a zero row, every run of this query is evaluated exactly
-    tc_write_query_row(reinterpret_cast<float4 *>(sA + qt * TC_TILE_BYTES), quarter * 32 + lane, v, usable);
-    double E = tc_error_bound(fmax(rmax2, qq));
-    float thr = -CUDART_INF_F;   // inactive: nothing passes
-    if (live && !usable) {
-      thr = CUDART_INF_F;
-      E = CUDART_INF;
-    } else if (live) {
-      if (RADIUS) {
-        thr = __double2float_ru(s_thr + E - qq);   // a run whose minimum is >= thr holds no hit
-      } else {
-        // a few nodes of the chunk measured exactly: the scan starts with a threshold that already rejects most runs
-        double smin = NN_INIT_SUMSQ;
-        const int64_t len = n1 - n0, step = len / TC_SEEDS;
-        if (step > 0)
-          for (int k = 0; k < TC_SEEDS; ++k) smin = fmin(smin, exact_s(t, n0 + k * step, qp));
-        thr = __double2float_ru(smin + E - qq);
-      }
-    }
-    two_e = usable ? __double2float_ru(2.0 * E) : CUDART_INF_F;
-    sh->thr[row] = thr;
-    sh->best_d[row] = NN_INIT_DIST;
-    sh->best_s[row] = NN_INIT_SUMSQ;
-    sh->best_id[row] = 0;
-    sh->e_minus_qq[row] = usable ? E - qq : CUDART_INF;
-    sh->excl[row] = (RADIUS && live && exclude) ? exclude[q_first + row] : -1;
-    tc_fence_async_smem();   // the A operand was written through the generic proxy; the tensor core reads through the async one
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = sh->tmem;
-
-  if (warp == 0) {
-    // ---- copies: one thread keeps TC_STAGES node tiles in flight
-    if (lane == 0) {
-      for (int it = 0; it < n_tiles; ++it) {
-        const int s = it % TC_STAGES;
-        tc_mbar_wait(&sh->empty[s], ((it / TC_STAGES) & 1) ^ 1);
-        tc_mbar_expect_tx(&sh->full[s], TC_TILE_BYTES);
-        tc_bulk_g2s(sB + s * TC_TILE_BYTES, img + int64_t(it) * TC_TILE_FLOAT4, TC_TILE_BYTES, &sh->full[s]);
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ---- MMA issue: one thread
-    if (lane == 0) {
-      const uint32_t a_base = tc_smem_u32(sA), b_base = tc_smem_u32(sB);
-      for (int it = 0; it < n_tiles; ++it) {
-        const int s = it % TC_STAGES, buf = it & 1;
-        tc_mbar_wait(&sh->full[s], (it / TC_STAGES) & 1);
-        const uint32_t b = b_base + s * TC_TILE_BYTES;
-        const uint64_t b_hi_hi = tc_desc(b, 0), b_mid_nrm = tc_desc(b + TC_CHUNK_BYTES, TC_CHUNK_BYTES);
-#pragma unroll
-        for (int k = 0; k < TC_QTILES; ++k) {
-          const uint32_t a = a_base + k * TC_TILE_BYTES, d = tmem + uint32_t((buf * TC_QTILES + k) * TC_ROWS);
-          const uint64_t a_hi_mid = tc_desc(a, TC_CHUNK_BYTES), a_hi_one = tc_desc(a, 2 * TC_CHUNK_BYTES);
-          tc_mbar_wait(&sh->acc_empty[buf][k], ((it >> 1) & 1) ^ 1);
-          tc_fence_after();
-          tc_mma_f16(d, a_hi_mid, b_hi_hi, false);    // [qh | qm] . [-2nh | -2nh]
-          tc_mma_f16(d, a_hi_one, b_mid_nrm, true);   // [qh | 1 1 1] . [-2nm | |n|^2 pieces]
-          tc_commit(&sh->acc_full[buf][k]);
-        }
-        tc_commit(&sh->empty[s]);
-      }
-    }
-    __syncwarp();
-  } else if (warp < TG_FIRST_EPI) {
-    // ---- evaluation: a record is one task for the whole warp
-    const int ev = warp - 2;
-    uint32_t head[TG_SERVED];
-#pragma unroll
-    for (int k = 0; k < TG_SERVED; ++k) head[k] = 0u;
-    for (;;) {
-      const bool scan_done = ld_vol(&sh->done) == uint32_t(TC_EPI_WARPS);   // (read before the rings: nothing is filed after it)
-      // lane i looks at slot head + i of each ring; a record is there as soon as its first word is non-zero
-      uint2 rec = make_uint2(0u, 0u);
-      int n_rec = 0, rec_ring = 0;
-#pragma unroll
-      for (int i = 0; i < TG_SERVED; ++i) {
-        const int rid = ev + i * TG_EVAL_WARPS;
-        const volatile uint2 *slot = &sh->ring[rid][(head[i] + uint32_t(lane)) % TG_RING];
-        uint2 x;
-        x.x = slot->x;
-        x.y = slot->y;
-        const unsigned vm = __ballot_sync(0xffffffffu, x.x != 0u);
-        const int c = vm == 0xffffffffu ? 32 : __ffs(~vm) - 1;   // contiguous from the head
-        if (n_rec == 0 && c > 0) {   // one ring per round (warp-uniform)
-          n_rec = c;
-          rec_ring = i;
-          rec = x;
-        }
-      }
-      if (n_rec == 0) {
-        if (scan_done) break;
-        __nanosleep(100);
-        continue;
-      }
-      const int rid = ev + rec_ring * TG_EVAL_WARPS;
-      uint32_t hk = 0u;
-#pragma unroll
-      for (int i = 0; i < TG_SERVED; ++i) hk = i == rec_ring ? head[i] : hk;
-      if (lane < n_rec) {
-        volatile uint2 *slot = &sh->ring[rid][(hk + uint32_t(lane)) % TG_RING];
-        slot->x = 0u;
-      }
-      hk += uint32_t(n_rec);
-#pragma unroll
-      for (int i = 0; i < TG_SERVED; ++i) head[i] = i == rec_ring ? hk : head[i];
-      __threadfence_block();
-      __syncwarp();
-      if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&sh->head[rid]) = hk;   // the (cleared) slots may be reused
-      const int row0 = (rid >> 2) * TC_ROWS + ((rid + TG_FIRST_EPI) & 3) * 32;        // first query of that scan warp
-      for (int k = 0; k < n_rec; ++k) {
-        const uint32_t key = __shfl_sync(0xffffffffu, rec.x, k);
-        const float mg = __uint_as_float(__shfl_sync(0xffffffffu, rec.y, k));
-        const int r = row0 + int(key & 31u);
-        if (!RADIUS && !(mg < ld_vol(&sh->thr[r]))) continue;   // the incumbent got better since: nothing in this run can beat it
-        const int64_t n = n0 + int64_t((key >> 7) & 0xffffffu) * TC_ROWS + int64_t((key >> 5) & 3u) * 32 + lane;
-        const bool valid = n < n1;
-        const double *qp = queries + (q_first + r) * SQMP_DOF;
-        const double s = valid ? exact_s(t, n, qp) : CUDART_INF;
-        if (RADIUS) {
-          const bool hit = valid && s < s_thr && int32_t(n) != sh->excl[r];
-          const unsigned bal = __ballot_sync(0xffffffffu, hit);
-          if (bal) {
-            int32_t first = 0;
-            if (lane == 0) first = atomicAdd(&count[q_first + r], __popc(bal));
-            first = __shfl_sync(0xffffffffu, first, 0);
-            const int32_t slot = first + __popc(bal & ((1u << lane) - 1u));
-            if (hit && slot < hit_cap) hits[(q_first + r) * hit_cap + slot] = int32_t(n);
-          }
-        } else {
-          // lexicographic (distance, id) minimum of the run, then against the incumbent (which has the lower id on a tie:
-          // the records of one query arrive in node order) = what the reference's serial loop keeps (strict '<', BS:4122)
-          double d = valid ? sqrt(s) : CUDART_INF, sb = s;
-          int32_t id = int32_t(n);
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const double d2 = __shfl_xor_sync(0xffffffffu, d, o), s2 = __shfl_xor_sync(0xffffffffu, sb, o);
-            const int32_t id2 = __shfl_xor_sync(0xffffffffu, id, o);
-            if (better(d2, id2, d, id)) { d = d2; sb = s2; id = id2; }
-          }
-          if (lane == 0 && d < sh->best_d[r]) {
-            sh->best_d[r] = d;
-            sh->best_s[r] = sb;
-            sh->best_id[r] = id;
-            const float nt = __double2float_ru(sb + sh->e_minus_qq[r]);
-            if (nt < sh->thr[r]) *reinterpret_cast<volatile float *>(&sh->thr[r]) = nt;
-          }
-          __syncwarp();
-        }
-      }
-    }
-    if (!RADIUS) {
-      for (int k = 0; k < TG_SERVED; ++k) {   // the queries of the scan warps it serves
-        const int rid = ev + k * TG_EVAL_WARPS;
-        const int r = (rid >> 2) * TC_ROWS + ((rid + TG_FIRST_EPI) & 3) * 32 + lane;
-        if (q_first + r < Q) {
-          part_d[int64_t(blockIdx.y) * Q + q_first + r] = sh->best_d[r];
-          part_id[int64_t(blockIdx.y) * Q + q_first + r] = sh->best_id[r];
-        }
-      }
-    }
-  } else {
-    // ---- scan: this thread's query against every node of the chunk
-    const int rid = warp - TG_FIRST_EPI;
-    uint2 *ring = sh->ring[rid];
-    uint32_t head_seen = 0u;
-    float vmin = CUDART_INF_F;   // nearest: the smallest estimate this thread has seen
-    for (int it = 0; it < n_tiles; ++it) {
-      const int buf = it & 1;
-      tc_mbar_wait(&sh->acc_full[buf][qt], (it >> 1) & 1);
-      tc_fence_after();
-      // the query's 128 estimates go through registers 64 at a time; the accumulator is handed back as soon as the second
-      // half has been read
-      const uint32_t taddr = tmem + (uint32_t(quarter * 32) << 16) + uint32_t((buf * TC_QTILES + qt) * TC_ROWS);
-      float mg[4];   // minimum of every run of 32 estimates
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float v[64];
-        TC_LD(taddr + 64 * h, v);
-        TC_LD(taddr + 64 * h + 32, v + 32);
-        tc_tmem_ld_wait();
-        if (h == 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) tc_mbar_arrive(&sh->acc_empty[buf][qt]);
-        }
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          float ms[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float *w = v + 32 * g + 8 * k;
-            ms[k] = fminf(tc_min3(tc_min3(w[0], w[1], w[2]), tc_min3(w[3], w[4], w[5]), w[6]), w[7]);
-          }
-          mg[2 * h + g] = fminf(tc_min3(ms[0], ms[1], ms[2]), ms[3]);
-        }
-      }
-      const float m = fminf(tc_min3(mg[0], mg[1], mg[2]), mg[3]);
-      float thr = ld_vol(&sh->thr[row]);
-      if (!RADIUS) {
-        thr = fminf(thr, vmin + two_e);   // sound without the evaluators: the nearest node's estimate is at most 2 E above the smallest one
-        vmin = fminf(vmin, m);
-      }
-#ifdef SQMP_TC_MIN_ONLY
-      if (m == 123.456f) two_e = 0.f;
-      continue;
-#endif
-      if (m < thr) {   // rare, only the lanes concerned: one record per run that passes
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          if (mg[g] < thr) {
-            const uint32_t pos = atomicAdd(&sh->tail[rid], 1u);
-            if (pos - head_seen >= uint32_t(TG_RING)) {   // full: wait for the evaluator (earlier positions are filed)
-              do head_seen = ld_vol(&sh->head[rid]);
-              while (pos - head_seen >= uint32_t(TG_RING));
-            }
-            volatile uint2 *slot = &ring[pos % TG_RING];
-            slot->y = __float_as_uint(mg[g]);
-            __threadfence_block();
-            slot->x = 0x80000000u | uint32_t(it) << 7 | uint32_t(g) << 5 | uint32_t(lane);
-          }
-      }
-    }
-    __threadfence_block();
-    __syncwarp();
-    if (lane == 0) atomicAdd(&sh->done, 1u);
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tc_tmem_free(tmem, TC_TMEM_COLS);
-  }
-}
-
 // fold the per-chunk partial results in chunk (= id) order; strict '<' keeps the lowest id on ties (BS:4122)
 __global__ void k_nn_merge(const double *__restrict__ part_d, const int32_t *__restrict__ part_id, int chunks,
                            int64_t Q, int32_t *__restrict__ id_out) {
@@ -1488,8 +1181,6 @@ cudaError_t launch_nn_single(const TreeDev &t, const double *h_query, bool radiu
 static cudaError_t tc_prepare() {
   cudaError_t e = cudaFuncSetAttribute(k_nn_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_nn_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_nn_tg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_nn_tg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES);
   return e;
 }
 static void pick_chunks(int64_t N, int64_t Q, int variant, int chunks_hint, int &chunks, int64_t &chunk_len) {
@@ -1509,13 +1200,7 @@ cudaError_t launch_nn_nearest(const TreeDev &t, const double *d_queries, int64_t
   int chunks;
   int64_t chunk_len;
   pick_chunks(t.n, Q, variant, chunks_hint, chunks, chunk_len);
-  if (variant == 5) {
-    cudaError_t ea = tc_prepare();
-    if (ea != cudaSuccess) return ea;
-    dim3 grid(unsigned((Q + TC_QTILES * TC_ROWS - 1) / (TC_QTILES * TC_ROWS)), unsigned(chunks));
-    k_nn_tg<false><<<grid, TG_THREADS, TG_SMEM_BYTES, st>>>(ptrs_of(t), t.n, chunk_len, d_queries, Q, t.rmax2, sc.part_d,
-                                                           sc.part_id, nullptr, 0.0, nullptr, nullptr, 0);
-  } else if (variant == 4) {
+  if (variant == 4) {
     cudaError_t ea = tc_prepare();
     if (ea != cudaSuccess) return ea;
     dim3 grid(unsigned((Q + TC_QTILES * TC_ROWS - 1) / (TC_QTILES * TC_ROWS)), unsigned(chunks));
@@ -1549,13 +1234,7 @@ cudaError_t launch_nn_radius(const TreeDev &t, const double *d_queries, const in
   pick_chunks(t.n, Q, variant, chunks_hint, chunks, chunk_len);
   cudaError_t e = cudaMemsetAsync(d_count, 0, size_t(Q) * sizeof(int32_t), st);
   if (e != cudaSuccess) return e;
-  if (variant == 5) {
-    cudaError_t ea = tc_prepare();
-    if (ea != cudaSuccess) return ea;
-    dim3 grid(unsigned((Q + TC_QTILES * TC_ROWS - 1) / (TC_QTILES * TC_ROWS)), unsigned(chunks));
-    k_nn_tg<true><<<grid, TG_THREADS, TG_SMEM_BYTES, st>>>(ptrs_of(t), t.n, chunk_len, d_queries, Q, t.rmax2, nullptr, nullptr,
-                                                          d_exclude, s_thr, d_count, sc.hits, sc.hit_cap);
-  } else if (variant == 4) {
+  if (variant == 4) {
     cudaError_t ea = tc_prepare();
     if (ea != cudaSuccess) return ea;
     dim3 grid(unsigned((Q + TC_QTILES * TC_ROWS - 1) / (TC_QTILES * TC_ROWS)), unsigned(chunks));

@@ -26,7 +26,7 @@ for t in range(trials):
     ctx.tree_reset(0)
     ctx.tree_append_batch(0, nodes, cost)
     ref = None
-    for variant, reps in ((3, 1), (int(os.environ.get("NN_VARIANT", "4")), 3)):
+    for variant, reps in ((3, 1), (4, 3)):
         ctx.set_option("nn_variant", variant)
         for _ in range(reps):
             got = (ctx.nn_nearest(0, qs),) + tuple(ctx.nn_radius(0, qs, None, r, k))
