@@ -522,12 +522,18 @@ k_nn_qt_pf(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ 
 constexpr int TC_QTILES = 2;                       // query tiles per CTA: every node tile is multiplied by both
 constexpr int TC_QUERIES = TC_QTILES * TC_ROWS;    // 256 queries per CTA
 constexpr int TC_STAGES = 8;                       // node tiles in flight
-constexpr int TC_EPI_WARPS = 4 * TC_QTILES;        // one warp per (query tile, TMEM lane quarter)
+#ifndef TC_HALVES_DEF
+#define TC_HALVES_DEF 2
+#endif
+constexpr int TC_HALVES = TC_HALVES_DEF;           // scan warps per (query tile, TMEM lane quarter): each takes TC_COLS columns of the accumulator
+constexpr int TC_COLS = TC_ROWS / TC_HALVES;
+constexpr int TC_EPI_WARPS = 4 * TC_QTILES * TC_HALVES;   // one scan warp per (query tile, TMEM lane quarter, column part)
 constexpr int TC_EVAL_WARPS = 2;                   // exact evaluation of what the scan could not reject; warp e serves scan warps e, e + 2, ..
 constexpr int TC_FIRST_EPI = 2 + TC_EVAL_WARPS;    // warp 0: copies, warp 1: MMA issue + TMEM, then the evaluation warps, then the scan warps
 constexpr int TC_THREADS = 32 * (TC_FIRST_EPI + TC_EPI_WARPS);
+static_assert(TC_FIRST_EPI % 4 == 0 && TC_EVAL_WARPS == 2, "scan warp k reads TMEM quarter k % 4; evaluation warp e owns the quarters of its parity");
 constexpr int TC_TMEM_COLS = 2 * TC_QTILES * TC_ROWS;   // two accumulator buffers x query tiles x 128 columns = 512
-constexpr int TC_RING = 512;                       // surviving pairs waiting for their exact evaluation, per scan warp
+constexpr int TC_RING = 256;                       // surviving pairs waiting for their exact evaluation, per scan warp
 #ifndef TC_SEEDS_DEF
 #define TC_SEEDS_DEF 32
 #endif
@@ -583,13 +589,14 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
   // ---- set-up: barriers, TMEM, the queries as the A operand, their thresholds
   if (threadIdx.x == 0) {
     for (int i = 0; i < TC_STAGES; ++i) { tc_mbar_init(&sh->full[i], 1); tc_mbar_init(&sh->empty[i], 1); }
-    for (int i = 0; i < 2 * TC_QTILES; ++i) { tc_mbar_init(&sh->acc_full[0][i], 1); tc_mbar_init(&sh->acc_empty[0][i], 4); }
+    for (int i = 0; i < 2 * TC_QTILES; ++i) { tc_mbar_init(&sh->acc_full[0][i], 1); tc_mbar_init(&sh->acc_empty[0][i], 4 * TC_HALVES); }
     for (int i = 0; i < TC_EPI_WARPS; ++i) sh->tail[i] = sh->head[i] = 0u;
     sh->done = 0u;
     tc_fence_mbar_init();
   }
   if (warp == 1) tc_tmem_alloc(&sh->tmem, TC_TMEM_COLS);
-  const int qt = (warp - TC_FIRST_EPI) >> 2, quarter = warp & 3;   // a warp may only read TMEM lanes [32 (warp % 4), +32)
+  const int quarter = warp & 3;   // a warp may only read TMEM lanes [32 (warp % 4), +32)
+  const int qt = ((warp - TC_FIRST_EPI) >> 2) % TC_QTILES, part = (warp - TC_FIRST_EPI) / (4 * TC_QTILES);   // its query tile, its columns
   const int row = qt * TC_ROWS + quarter * 32 + lane;              // this scan thread's query
   float thr_lo = -CUDART_INF_F;                                    // radius: an accumulator value below this is a proven hit
   if (warp >= TC_FIRST_EPI) {
@@ -602,7 +609,7 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
       qq += v[d] * v[d];
     }
     const bool usable = qq < TC_MAX_NORM2;   // fits fp16; otherwise (or NaN): a zero row, every pair of this query is evaluated exactly
-    tc_write_query_row(reinterpret_cast<float4 *>(sA + qt * TC_TILE_BYTES), quarter * 32 + lane, v, usable);
+    if (part == 0) tc_write_query_row(reinterpret_cast<float4 *>(sA + qt * TC_TILE_BYTES), quarter * 32 + lane, v, usable);
     double E = tc_error_bound(fmax(rmax2, qq));
     float thr = -CUDART_INF_F;   // inactive: nothing passes
     if (live && !usable) {
@@ -617,17 +624,19 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
         // (they are not offered as incumbents here — the scan meets them again in node order)
         double smin = NN_INIT_SUMSQ;
         const int64_t len = n1 - n0, step = len / TC_SEEDS;
-        if (step > 0)
+        if (step > 0 && part == 0)
           for (int k = 0; k < TC_SEEDS; ++k) smin = fmin(smin, exact_s(t, n0 + k * step, qp));
         thr = __double2float_ru(smin + E - qq);
       }
     }
-    sh->thr[row] = thr;
-    sh->d_bits[row] = (unsigned long long)__double_as_longlong(NN_INIT_DIST);
-    sh->best_s[row] = NN_INIT_SUMSQ;
-    sh->best_id[row] = 0;
-    sh->e_minus_qq[row] = usable ? E - qq : CUDART_INF;
-    sh->excl[row] = (RADIUS && live && exclude) ? exclude[q_first + row] : -1;
+    if (part == 0) {   // the query's shared state has one owner among the threads that scan for it
+      sh->thr[row] = thr;
+      sh->d_bits[row] = (unsigned long long)__double_as_longlong(NN_INIT_DIST);
+      sh->best_s[row] = NN_INIT_SUMSQ;
+      sh->best_id[row] = 0;
+      sh->e_minus_qq[row] = usable ? E - qq : CUDART_INF;
+      sh->excl[row] = (RADIUS && live && exclude) ? exclude[q_first + row] : -1;
+    }
     tc_fence_async_smem();   // the A operand was written through the generic proxy; the tensor core reads through the async one
   }
   tc_fence_before();
@@ -736,16 +745,21 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
           d = sqrt(s);
         }
         const unsigned long long db = (unsigned long long)__double_as_longlong(d);
-        const bool better_d = have && db < sh->d_bits[r];   // (the incumbent has the lower id on a tie: nodes arrive in id order per query)
+        // (several scan warps file for one query, so its pairs do not arrive in node order: an equal distance with a lower
+        //  id has to replace the incumbent too; INIT's id 0 only ever meets distances below 10000)
+        const unsigned long long before = have ? sh->d_bits[r] : 0ull;
+        const bool better_d = have && db <= before && d < NN_INIT_DIST;
         __syncwarp();
         if (better_d) atomicMin(&sh->d_bits[r], db);
         __syncwarp();
         const bool best_d = better_d && sh->d_bits[r] == db;
-        if (best_d) sh->best_id[r] = 0x7fffffff;
+        const int32_t id_before = best_d ? sh->best_id[r] : 0;
+        __syncwarp();
+        if (best_d && db < before) sh->best_id[r] = 0x7fffffff;   // a strictly smaller distance: the old id is out
         __syncwarp();
         if (best_d) atomicMin(&sh->best_id[r], int32_t(n));
         __syncwarp();
-        if (best_d && sh->best_id[r] == int32_t(n)) {
+        if (best_d && sh->best_id[r] == int32_t(n) && (db < before || int32_t(n) < id_before)) {
           sh->best_s[r] = s;
           const float nt = __double2float_ru(s + sh->e_minus_qq[r]);
           if (nt < sh->thr[r]) *reinterpret_cast<volatile float *>(&sh->thr[r]) = nt;
@@ -755,8 +769,9 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
     }
     if (!RADIUS) {
       for (int k = 0; k < SERVED; ++k) {   // the queries of the scan warps it serves
-        const int sw = ev + k * TC_EVAL_WARPS + TC_FIRST_EPI;                // that scan warp: its query tile and TMEM quarter
-        const int r = ((sw - TC_FIRST_EPI) >> 2) * TC_ROWS + (sw & 3) * 32 + lane;
+        const int sw = ev + k * TC_EVAL_WARPS;                               // that scan warp: its query tile and TMEM quarter
+        if (sw >= 4 * TC_QTILES) continue;                                   // (the other column parts scan for the same queries)
+        const int r = (sw >> 2) * TC_ROWS + (sw & 3) * 32 + lane;
         if (q_first + r < Q) {
           part_d[int64_t(blockIdx.y) * Q + q_first + r] = __longlong_as_double((long long)sh->d_bits[r]);
           part_id[int64_t(blockIdx.y) * Q + q_first + r] = sh->best_id[r];
@@ -772,40 +787,44 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
     const unsigned lt_mask = (1u << lane) - 1u;
     for (int it = 0; it < n_tiles; ++it) {
       const int buf = it & 1;
-      const int64_t base = n0 + int64_t(it) * TC_ROWS;
+      const int64_t base = n0 + int64_t(it) * TC_ROWS + part * TC_COLS;
       tc_mbar_wait(&sh->acc_full[buf][qt], (it >> 1) & 1);
       tc_fence_after();
-      // the query's 128 estimates move to registers in one go and the accumulator is handed back before anything is
-      // looked at: the tensor core never waits for the scan, only for this copy
-      const uint32_t taddr = tmem + (uint32_t(quarter * 32) << 16) + uint32_t((buf * TC_QTILES + qt) * TC_ROWS);
-      float v[TC_ROWS];
+      // the query's estimates for this warp's columns move to registers in one go and the accumulator is handed back before
+      // anything is looked at: the tensor core never waits for the scan, only for this copy
+      const uint32_t taddr = tmem + (uint32_t(quarter * 32) << 16) + uint32_t((buf * TC_QTILES + qt) * TC_ROWS + part * TC_COLS);
+      constexpr int NG = TC_COLS / 32;
+      float v[TC_COLS];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) TC_LD(taddr + 32 * g, v + 32 * g);
+      for (int g = 0; g < NG; ++g) TC_LD(taddr + 32 * g, v + 32 * g);
       tc_tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) tc_mbar_arrive(&sh->acc_empty[buf][qt]);
       const float thr = ld_vol(&sh->thr[row]);
 #ifdef SQMP_TC_LD_ONLY
-      if (v[0] == 123.456f && v[77] == thr) thr_lo = 0.f;
+      if (v[0] == 123.456f && v[17] == thr) thr_lo = 0.f;
       continue;
 #endif
-      float ms[16];   // minimum of every run of eight estimates
+      float ms[4 * NG];   // minimum of every run of eight estimates
 #pragma unroll
-      for (int k = 0; k < 16; ++k)
+      for (int k = 0; k < 4 * NG; ++k)
         ms[k] = fminf(tc_min3(tc_min3(v[8 * k], v[8 * k + 1], v[8 * k + 2]), tc_min3(v[8 * k + 3], v[8 * k + 4], v[8 * k + 5]), v[8 * k + 6]),
                       v[8 * k + 7]);
-      float mg[4];    // ... of every 32
+      float mg[NG];       // ... of every 32
+      float m = CUDART_INF_F;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) mg[g] = fminf(tc_min3(ms[4 * g], ms[4 * g + 1], ms[4 * g + 2]), ms[4 * g + 3]);
-      const float m = fminf(tc_min3(mg[0], mg[1], mg[2]), mg[3]);
+      for (int g = 0; g < NG; ++g) {
+        mg[g] = fminf(tc_min3(ms[4 * g], ms[4 * g + 1], ms[4 * g + 2]), ms[4 * g + 3]);
+        m = fminf(m, mg[g]);
+      }
 #ifdef SQMP_TC_MIN_ONLY
       if (m == 123.456f) thr_lo = 0.f;
       continue;
 #endif
       if (!__any_sync(0xffffffffu, m < thr)) continue;   // the common case: nothing in this tile for any of the 32 queries
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
+      for (int g = 0; g < NG; ++g) {
         unsigned any = __ballot_sync(0xffffffffu, mg[g] < thr);
         if (any == 0u) continue;
         uint32_t cm = 0u, pm = 0u;   // columns that pass / that are proven hits; only the runs some lane needs are looked at
