@@ -737,6 +737,25 @@ def test_fp32_prefilter_is_sound_on_adversarial_trees(ctx, variant):
         ctx.set_option("nn_variant", 0)
 
 
+def test_tensor_core_estimate_error_is_far_inside_its_budget():
+    """tools/tc_probe_f16.cu runs one 128 x 128 tile of the near-neighbour estimate (csrc/tc_umma.cuh: two tcgen05.mma over
+    fp16-split operands, accumulator read back with tcgen05.ld) against fp64.  nn.cu budgets 2^-14 R^2 for the estimate's
+    error because the tensor core's accumulation order is not documented; the measured error has to stay at least 8x
+    below that (it is 2^-21.8 R^2), so a change of hardware or operand layout that eats into the margin is noticed."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "build", "tc_probe_f16")
+    if not os.path.exists(exe):
+        os.makedirs(os.path.dirname(exe), exist_ok=True)
+        subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-I", os.path.join(root, "squirrel_motion_planner_b200", "csrc"),
+                        "-o", exe, os.path.join(root, "tools", "tc_probe_f16.cu")], check=True, timeout=300)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "tc_probe_f16: OK" in r.stdout, r.stdout + r.stderr
+    log2_err = float(re.search(r"= 2\^(-?[0-9.]+) R\^2", r.stdout).group(1))
+    assert log2_err < -17.0, r.stdout
+
+
 def test_tensor_core_scan_edge_cases(ctx):
     """Variant 4 (tcgen05 pre-filter on fp16 pieces, nn.cu: k_nn_tc): ragged sizes (Q not a multiple of the 256-query CTA
     tile, N not a multiple of the 128-node tile, several chunks), queries whose coordinates do not fit fp16 (zero operand
