@@ -1387,7 +1387,9 @@ int sqmp_check_edges(sqmp_ctx *ctx, const double *qa, const double *qb, int64_t 
   // H2D -> kernel (+ first_invalid in its epilogue) -> D2H in stages over two streams: the copies of one stage overlap
   // the kernel of the other.  A stage holds a multiple of 32 edges, so its first state starts a mask word.
   const int P1 = num_points + 1;
-  int64_t ce = (c->pipeline_chunk / P1) / 32 * 32;
+  // (an edge costs 128 B over PCIe for its num_points + 1 states: the copies are short, so a stage holds twice the states of
+  //  the state path's — fewer launches, each with its own ramp-up and tail; tools/e2e_edges_chunk.py)
+  int64_t ce = (2 * c->pipeline_chunk / P1) / 32 * 32;
   if (ce < 32) ce = 32;
   if (ce > E) ce = (E + 31) / 32 * 32;
   void *da[2], *db[2], *dm[2], *df[2];
