@@ -134,26 +134,36 @@ inline double edge_cost(const double *a, const double *b, int num_points) {
 // compute_edge_cost_interpolation (BS:4162-4242) over the interpolated trajectory of BS:4461-4478: per segment the squared
 // coordinate differences, weighted for the total (m_edge_cost_weights), split by joint class for the other two; the
 // three costs are the sums of the segments' square roots.  out = {total, revolute, prismatic}.
-inline void edge_cost3(const double *a, const double *b, int num_points, const double *weights, const int *is_revolute, double *out) {
-  double step[8], prev[8];
-  double edge_cost_total = 0.0, edge_cost_rev = 0.0, edge_cost_prism = 0.0;
+// This is the planner's hottest host function (up to ~40 candidate edges per iteration): the loops run joint-outer,
+// segment-inner so that the compiler vectorises over the segments (an AVX2 clone where the CPU has it; no FMA contraction —
+// that would change the bits).  Every segment's three sums still receive their terms in joint order and the segments are
+// added up in order, so the result is bit for bit that of the reference's nesting (tests/test_planner_frontend.py).
+#if defined(__GNUC__) && defined(__x86_64__) && !defined(SQMP_NO_TARGET_CLONES)
+#define SQMP_SIMD_CLONES __attribute__((target_clones("avx2", "default"), optimize("O3")))
+#else
+#define SQMP_SIMD_CLONES
+#endif
+SQMP_SIMD_CLONES
+static void edge_cost3(const double *a, const double *b, int num_points, const double *weights, const int *is_revolute, double *out) {
+  enum { MAXP = 256 };
+  double tot[MAXP], rot[MAXP], pri[MAXP];
+  const int np = num_points < MAXP ? num_points : MAXP - 1;   // (the library limits num_points to 255)
+  for (int k = 1; k <= np; ++k) tot[k] = rot[k] = pri[k] = 0.0;
   for (int j = 0; j < 8; ++j) {
-    step[j] = (b[j] - a[j]) / double(num_points);
-    prev[j] = a[j] + 0.0 * step[j];
-  }
-  for (int k = 1; k <= num_points; ++k) {
-    double wp_dist_total = 0.0, wp_dist_rot = 0.0, wp_dist_prism = 0.0;
-    for (int j = 0; j < 8; ++j) {
-      const double cur = a[j] + double(k) * step[j];
-      const double coordinate_dist = (cur - prev[j]) * (cur - prev[j]);
-      wp_dist_total += coordinate_dist * weights[j];
-      if (is_revolute[j]) wp_dist_rot += coordinate_dist;
-      else wp_dist_prism += coordinate_dist;
-      prev[j] = cur;
+    const double aj = a[j], step = (b[j] - a[j]) / double(num_points), w = weights[j];
+    double *cls = is_revolute[j] ? rot : pri;
+    for (int k = 1; k <= np; ++k) {
+      const double cur = aj + double(k) * step, prev = aj + double(k - 1) * step;   // prev = the previous segment's cur
+      const double coordinate_dist = (cur - prev) * (cur - prev);
+      tot[k] += coordinate_dist * w;
+      cls[k] += coordinate_dist;
     }
-    edge_cost_total += std::sqrt(wp_dist_total);
-    edge_cost_rev += std::sqrt(wp_dist_rot);
-    edge_cost_prism += std::sqrt(wp_dist_prism);
+  }
+  double edge_cost_total = 0.0, edge_cost_rev = 0.0, edge_cost_prism = 0.0;
+  for (int k = 1; k <= np; ++k) {
+    edge_cost_total += std::sqrt(tot[k]);
+    edge_cost_rev += std::sqrt(rot[k]);
+    edge_cost_prism += std::sqrt(pri[k]);
   }
   out[0] = edge_cost_total;
   out[1] = edge_cost_rev;
