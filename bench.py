@@ -754,7 +754,7 @@ def run_config5(args):
     desc = os.path.join(ROOT, "squirrel_motion_planner_b200", "data", "robotino_plan.sqmpdesc")
     n_queries, iters = args.queries, args.iterations
     if args.threads <= 0:   # the planner front-end is host-bound (SQMP_PLAN_PROFILE=1): give every GPU its share of the host cores
-        args.threads = max(1, min(4, (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)) // max(1, world_size)))
+        args.threads = max(1, min(8, (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)) // max(1, world_size)))
     w = syn.box_world(g=512, n_boxes=2048, seed=4321)                       # W512, SURVEY.md §8d
     # collision-free (start, goal) pairs: rejection sampling with the CUDA checker itself (self + map), seed 5
     ctx = api.default_context(local_rank)
@@ -837,7 +837,7 @@ def main():
     ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5"])
     ap.add_argument("--queries", type=int, default=1024, help="config5: number of planning queries")
     ap.add_argument("--iterations", type=int, default=1000, help="config5: BiRRT* iterations per query")
-    ap.add_argument("--threads", type=int, default=0, help="config5: host threads per GPU, each with its own context (0 = host cores / GPUs, at most 4)")
+    ap.add_argument("--threads", type=int, default=0, help="config5: host threads per GPU, each with its own context (0 = host cores / GPUs, at most 8)")
     ap.add_argument("--batch", type=int, default=512, help="config5: queries in flight per GPU (1 = sequential runner)")
     ap.add_argument("--gather", default="nccl", choices=["auto", "p2p", "nccl"],
                     help="N > 1: mask all-gather fused into the kernel over peer memory (p2p) or ncclAllGather (nccl)")
