@@ -12,12 +12,15 @@
 // to the CPU's, sqrt is IEEE (sqrt.rn.f64), and every comparison is made on the same values the reference
 // compares.  Ties resolve to the lowest node id, which is what the reference's serial loop does.
 //
-// Two mappings, both exact:
+// Three mappings, all exact:
 //   QT ("query per thread", many queries): nodes stream through shared memory in tiles and are broadcast to
 //      all lanes; each lane keeps its query and running best in registers; no cross-lane traffic at all.
 //   WQ ("warp per query", few queries — the planner's own call shape): lanes stride over the nodes of a chunk,
 //      the warp reduces (distance, id) lexicographically with shuffles, radius hits are compacted with a ballot.
-// Both write one partial result per (query, node chunk); a merge kernel folds the chunks in id order.
+//   TC ("tensor-core pre-filter", >= 2048 queries, the default there): the pairwise estimates |n|^2 - 2 q.n of a 256-query
+//      tile against the streamed nodes come out of tcgen05.mma over fp16-split operands (tc_umma.cuh); whatever the
+//      estimate cannot reject is evaluated exactly as in the other mappings.  See k_nn_tc below.
+// All write one partial result per (query, node chunk); a merge kernel folds the chunks in id order.
 #include <math_constants.h>
 
 #include "sqmp_common.cuh"
