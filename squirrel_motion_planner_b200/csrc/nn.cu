@@ -504,10 +504,11 @@ k_nn_qt_pf(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ 
 // TC ("tensor-core pre-filter", many queries): the estimate of every (query, node) pair comes out of tcgen05.mma
 // instead of nine FFMA2 per pair.  A CTA keeps TC_QTILES x 128 queries as the A operand in shared memory and streams
 // its node chunk through a ring of 6 KB tile images (bulk async copies, one elected thread); one elected thread issues
-// two K = 16 fp16 MMAs per (query tile, node tile) into one of four TMEM accumulators (tc_umma.cuh).  The four scan warps of
-// a query tile copy their query's row of the accumulator to registers (one TMEM lane per thread, 128 columns), hand the
-// accumulator back at once, and reduce the 128 estimates with three-input minima; individual columns are only looked
-// at when that minimum passes the thread's threshold.  What passes goes to a shared-memory ring and is re-evaluated
+// two K = 16 fp16 MMAs per (query tile, node tile) into one of four TMEM accumulators (tc_umma.cuh).  The eight scan warps of
+// a query tile (one per TMEM lane quarter and column half: a second warp keeps the TMEM read port busy while the first
+// files) copy their part of their query's accumulator row to registers (one TMEM lane per thread, 64 columns), hand the
+// accumulator back at once, and reduce the estimates with three-input minima; individual columns are only looked at
+// when that minimum passes the thread's threshold.  What passes goes to a shared-memory ring and is re-evaluated
 // exactly (exact_s) and compared exactly by two dedicated warps, 32 pairs at a time, off the scan's critical path — the
 // same contract as QT/PF, so the answers are bit-identical; the band is wider (fp16 pieces instead of a few fp32 ulps) and
 // still admits < 0.1 extra exact evaluations per query on the benchmark's tree.
