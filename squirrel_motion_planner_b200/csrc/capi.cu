@@ -746,7 +746,7 @@ static int pick_chunk_hint(const Ctx *c, int variant, int64_t N, int64_t Q) {
   int64_t chunks;
   if (variant == 4) {
     // one 320-thread CTA per SM: the fewest chunks (each restarts the search for the best) that fill whole waves
-    const int64_t qtiles = (Q + 255) / 256;
+    const int64_t per = nn_tc_queries_per_cta(), qtiles = (Q + per - 1) / per;
     const int64_t maxc = (N + 4095) / 4096;
     chunks = 1;
     double best_eff = 0.0;

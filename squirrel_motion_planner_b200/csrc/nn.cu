@@ -523,7 +523,10 @@ k_nn_qt_pf(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ 
 //                  probe (tools/tc_probe_f16.cu) and the parity tests observe (2^-21.8 R^2).
 //   total          < 2^-14 R^2 + 2^-19 R + 2^-22 = tc_error_bound(R^2).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int TC_QTILES = 2;                       // query tiles per CTA: every node tile is multiplied by both
+#ifndef TC_QTILES_DEF
+#define TC_QTILES_DEF 2
+#endif
+constexpr int TC_QTILES = TC_QTILES_DEF;           // query tiles per CTA: every node tile is multiplied by each
 constexpr int TC_QUERIES = TC_QTILES * TC_ROWS;    // 256 queries per CTA
 constexpr int TC_STAGES = 8;                       // node tiles in flight
 #ifndef TC_HALVES_DEF
@@ -536,7 +539,8 @@ constexpr int TC_EVAL_WARPS = 2;                   // exact evaluation of what t
 constexpr int TC_FIRST_EPI = 2 + TC_EVAL_WARPS;    // warp 0: copies, warp 1: MMA issue + TMEM, then the evaluation warps, then the scan warps
 constexpr int TC_THREADS = 32 * (TC_FIRST_EPI + TC_EPI_WARPS);
 static_assert(TC_FIRST_EPI % 4 == 0 && TC_EVAL_WARPS == 2, "scan warp k reads TMEM quarter k % 4; evaluation warp e owns the quarters of its parity");
-constexpr int TC_TMEM_COLS = 2 * TC_QTILES * TC_ROWS;   // two accumulator buffers x query tiles x 128 columns = 512
+constexpr int TC_TMEM_COLS = 512;                  // all of the SM's tensor memory:
+constexpr int TC_BUFS = TC_TMEM_COLS / (TC_QTILES * TC_ROWS);   // accumulator buffers (node tiles in flight) x query tiles x 128 columns
 constexpr int TC_RING = 256;                       // surviving pairs waiting for their exact evaluation, per scan warp
 #ifndef TC_SEEDS_DEF
 #define TC_SEEDS_DEF 32
@@ -553,7 +557,7 @@ __device__ __forceinline__ double tc_error_bound(double R2) {
 
 struct TcShared {
   uint64_t full[TC_STAGES], empty[TC_STAGES];   // node tile landed / its MMAs are done
-  uint64_t acc_full[2][TC_QTILES], acc_empty[2][TC_QTILES];   // accumulator (buffer, query tile) written / copied out by its four scan warps
+  uint64_t acc_full[TC_BUFS][TC_QTILES], acc_empty[TC_BUFS][TC_QTILES];   // accumulator (buffer, query tile) written / copied out by its four scan warps
   uint32_t tmem;
   uint32_t tail[TC_EPI_WARPS], head[TC_EPI_WARPS];     // rings (one per scan warp): filled up to tail, consumed up to head
   uint32_t done;                                // scan warps that have finished
@@ -593,7 +597,7 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
   // ---- set-up: barriers, TMEM, the queries as the A operand, their thresholds
   if (threadIdx.x == 0) {
     for (int i = 0; i < TC_STAGES; ++i) { tc_mbar_init(&sh->full[i], 1); tc_mbar_init(&sh->empty[i], 1); }
-    for (int i = 0; i < 2 * TC_QTILES; ++i) { tc_mbar_init(&sh->acc_full[0][i], 1); tc_mbar_init(&sh->acc_empty[0][i], 4 * TC_HALVES); }
+    for (int i = 0; i < TC_BUFS * TC_QTILES; ++i) { tc_mbar_init(&sh->acc_full[0][i], 1); tc_mbar_init(&sh->acc_empty[0][i], 4 * TC_HALVES); }
     for (int i = 0; i < TC_EPI_WARPS; ++i) sh->tail[i] = sh->head[i] = 0u;
     sh->done = 0u;
     tc_fence_mbar_init();
@@ -664,7 +668,7 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
     if (lane == 0) {
       const uint32_t a_base = tc_smem_u32(sA), b_base = tc_smem_u32(sB);
       for (int it = 0; it < n_tiles; ++it) {
-        const int s = it % TC_STAGES, buf = it & 1;
+        const int s = it % TC_STAGES, buf = it % TC_BUFS;
         tc_mbar_wait(&sh->full[s], (it / TC_STAGES) & 1);
         const uint32_t b = b_base + s * TC_TILE_BYTES;
         const uint64_t b_hi_hi = tc_desc(b, 0), b_mid_nrm = tc_desc(b + TC_CHUNK_BYTES, TC_CHUNK_BYTES);
@@ -672,7 +676,7 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
         for (int k = 0; k < TC_QTILES; ++k) {
           const uint32_t a = a_base + k * TC_TILE_BYTES, d = tmem + uint32_t((buf * TC_QTILES + k) * TC_ROWS);
           const uint64_t a_hi_mid = tc_desc(a, TC_CHUNK_BYTES), a_hi_one = tc_desc(a, 2 * TC_CHUNK_BYTES);
-          tc_mbar_wait(&sh->acc_empty[buf][k], ((it >> 1) & 1) ^ 1);
+          tc_mbar_wait(&sh->acc_empty[buf][k], ((it / TC_BUFS) & 1) ^ 1);
           tc_fence_after();
           tc_mma_f16(d, a_hi_mid, b_hi_hi, false);    // [qh | qm] . [-2nh | -2nh]
           tc_mma_f16(d, a_hi_one, b_mid_nrm, true);   // [qh | 1 1 1] . [-2nm | |n|^2 pieces]
@@ -790,9 +794,9 @@ k_nn_tc(TreePtrs t, int64_t N, int64_t chunk_len, const double *__restrict__ que
     uint32_t tail = 0u, head_seen = 0u;   // warp-uniform
     const unsigned lt_mask = (1u << lane) - 1u;
     for (int it = 0; it < n_tiles; ++it) {
-      const int buf = it & 1;
+      const int buf = it % TC_BUFS;
       const int64_t base = n0 + int64_t(it) * TC_ROWS + part * TC_COLS;
-      tc_mbar_wait(&sh->acc_full[buf][qt], (it >> 1) & 1);
+      tc_mbar_wait(&sh->acc_full[buf][qt], (it / TC_BUFS) & 1);
       tc_fence_after();
       // the query's estimates for this warp's columns move to registers in one go and the accumulator is handed back before
       // anything is looked at: the tensor core never waits for the scan, only for this copy
@@ -1206,6 +1210,7 @@ static cudaError_t tc_prepare() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_nn_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   return e;
 }
+int nn_tc_queries_per_cta() { return TC_QUERIES; }
 static void pick_chunks(int64_t N, int64_t Q, int variant, int chunks_hint, int &chunks, int64_t &chunk_len) {
   (void)Q;
   chunks = chunks_hint < 1 ? 1 : chunks_hint;

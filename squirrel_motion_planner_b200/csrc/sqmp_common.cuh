@@ -269,6 +269,7 @@ cudaError_t launch_nn_radius(const TreeDev &t, const double *d_queries, const in
 // every query against its own tree (nn.cu: k_nn_multi); d_desc: one 96-byte record per query (nn_multi_fill_desc)
 cudaError_t launch_nn_multi(const void *d_desc, const double *d_queries, int64_t Q, bool radius, double s_thr, int k,
                             NNScratch &sc, int32_t *d_out, cudaStream_t st);
+int nn_tc_queries_per_cta();   // nn.cu: queries a CTA of the tensor-core scan handles
 size_t nn_multi_desc_bytes();
 void nn_multi_fill_desc(void *dst, const TreeDev &t, int32_t exclude);
 
