@@ -241,3 +241,23 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"] and line["gpu_launches"] == 0
+
+
+def test_fp16_operand_pieces_of_the_tensor_core_scan_meet_their_stated_bounds():
+    """csrc/tc_umma.cuh splits every coordinate into two fp16 pieces and |n|^2 into three (round to nearest, like
+    __double2half); nn.cu's error budget for the tcgen05 estimate assumes |x - h - m| <= 2^-22 |x| + 2^-24 and
+    | |n|^2 - p0 - p1 - p2 | <= 2^-30 |n|^2 + 2^-23 inside the range the kernel is used in (|x|^2 < 6e4).  numpy's
+    float16 conversion rounds the same way, so the assumption is checked here without a GPU — including values whose
+    second piece is an fp16 subnormal."""
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.uniform(-244.0, 244.0, 200000), rng.uniform(-1, 1, 200000) * 10.0 ** rng.uniform(-9, 0, 200000),
+                        [0.0, 6.0e-5, 6.2e-5, 244.9, -244.9, 1e-8, 5.96e-8]])
+    h = x.astype(np.float16).astype(np.float64)
+    m = (x - h).astype(np.float16).astype(np.float64)
+    assert np.all(np.isfinite(h)) and np.all(np.abs(x - h - m) <= np.abs(x) * 2.0 ** -22 + 2.0 ** -24)
+    assert np.all((-2.0 * h).astype(np.float16).astype(np.float64) == -2.0 * h)        # the image stores -2 h, -2 m exactly
+    n2 = np.concatenate([rng.uniform(0.0, 6.0e4, 200000), 10.0 ** rng.uniform(-12, 0, 1000)])
+    p0 = n2.astype(np.float16).astype(np.float64)
+    p1 = (n2 - p0).astype(np.float16).astype(np.float64)
+    p2 = (n2 - p0 - p1).astype(np.float16).astype(np.float64)
+    assert np.all(np.isfinite(p0)) and np.all(np.abs(n2 - p0 - p1 - p2) <= n2 * 2.0 ** -30 + 2.0 ** -23)
